@@ -1,0 +1,84 @@
+/*
+ * oracle/backend.h — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Kernel-level interface of the CPU oracle.  Two implementations exist:
+ *   PortBackend (port_backend.cpp)  — plain C++ restatement of ugcore's
+ *       SparseMatrix / Vector / core_smoothers arithmetic, no reference headers;
+ *   RefBackend  (ref_backend.cpp)   — thin adapter around the REAL ugcore
+ *       templates, compiled from /root/reference/ugbase where it lies
+ *       (only built when that tree is present; output in oracle/_ref/).
+ * The solver control flow (solvers.cpp) is written once against this interface.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference
+ * legs may use anything under oracle/.
+ */
+#ifndef ORACLE_BACKEND_H
+#define ORACLE_BACKEND_H
+#include <cstdint>
+#include <memory>
+#include <vector>
+
+namespace oracle {
+
+struct Mat {
+	virtual ~Mat() {}
+	int64_t nrows = 0, ncols = 0;
+	int block = 1;
+};
+
+struct Vec {
+	virtual ~Vec() {}
+	virtual double* data() = 0;
+	virtual const double* data() const = 0;
+	int64_t n = 0; // number of blocks
+	int block = 1;
+	int64_t len() const { return n * block; }
+};
+
+struct DiagInv { virtual ~DiagInv() {} };
+struct DenseLU { virtual ~DenseLU() {} };
+
+struct Backend {
+	virtual ~Backend() {}
+	virtual const char* name() const = 0;
+
+	virtual Mat* matrix(int block, int64_t nrows, int64_t ncols, const int64_t* rowptr,
+	                    const int* cols, const double* vals) = 0;
+	virtual Vec* vector(int64_t nblocks, int block) = 0;
+	virtual int64_t nnz(const Mat& A) = 0;
+	virtual void export_crs(const Mat& A, int64_t* rowptr, int* cols, double* vals) = 0;
+	// set_as_transpose_of (keeps explicit zeros) / set_as_transpose_of2 (drops them)
+	virtual Mat* transpose(const Mat& A, bool keep_zeros) = 0;
+
+	virtual void apply(const Mat& A, Vec& y, const Vec& x) = 0;        // y = A x
+	virtual void matmul_minus(const Mat& A, Vec& y, const Vec& x) = 0; // y -= A x
+	virtual void axpy(const Mat& A, Vec& dest, double alpha, const Vec& v, double beta, const Vec& w) = 0;
+	virtual void apply_ignore_zero_rows(const Mat& A, Vec& dest, double beta, const Vec& w) = 0;
+
+	virtual double dot(const Vec& a, const Vec& b) = 0;
+	virtual double norm(const Vec& a) = 0;
+	virtual void set(Vec& a, double v) = 0;
+	virtual void assign(Vec& dst, const Vec& src) = 0;
+	virtual void add(Vec& dst, const Vec& src) = 0;   // dst += src
+	virtual void sub(Vec& dst, const Vec& src) = 0;   // dst -= src
+	virtual void scale(Vec& dst, double s) = 0;       // dst *= s
+	virtual void scale_add2(Vec& d, double a1, const Vec& v1, double a2, const Vec& v2) = 0;
+	virtual void scale_add3(Vec& d, double a1, const Vec& v1, double a2, const Vec& v2, double a3, const Vec& v3) = 0;
+
+	virtual DiagInv* jacobi_prepare(const Mat& A, double damp, bool block) = 0;
+	virtual void jacobi_step(const DiagInv& D, Vec& c, const Vec& d) = 0;
+	virtual void gs_step_LL(const Mat& A, Vec& c, const Vec& d, double relax) = 0;
+	virtual void gs_step_UR(const Mat& A, Vec& c, const Vec& d, double relax) = 0;
+	virtual void sgs_step(const Mat& A, Vec& c, const Vec& d, double relax) = 0;
+
+	virtual DenseLU* lu_init(const Mat& A) = 0;                  // nullptr if singular
+	virtual void lu_apply(const DenseLU& lu, Vec& x, const Vec& b) = 0;
+};
+
+Backend* make_port_backend();
+#ifdef ORACLE_WITH_UGREF
+Backend* make_ref_backend();
+#endif
+
+} // namespace oracle
+#endif

@@ -1,0 +1,95 @@
+/*
+ * oracle/oracle.h — C ABI of the CPU oracle.  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Loaded with ctypes by tests/, __graft_entry__.smoke() and bench.py's CPU
+ * baseline legs only.  The product (ugcore_b200) never links or calls this.
+ *
+ * Two builds export the same symbols:
+ *   oracle/liboracle.so            backend "port"  (restated arithmetic)
+ *   oracle/_ref/liboracle_ref.so   backend "ref"   (real ugcore templates compiled
+ *                                  from /root/reference/ugbase; solver control
+ *                                  flow still restated, see solvers.h)
+ */
+#ifndef ORACLE_H
+#define ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct oracle_mat oracle_mat;
+
+const char* oracle_backend_name(void);
+const char* oracle_last_error(void);
+
+/* ---- kernel level (raw host arrays; vectors hold block*n doubles) ---- */
+oracle_mat* oracle_mat_create(int block, int64_t nrows, int64_t ncols, const int64_t* rowptr,
+                              const int* cols, const double* vals);
+void    oracle_mat_destroy(oracle_mat* A);
+int64_t oracle_mat_nnz(const oracle_mat* A);
+int64_t oracle_mat_rows(const oracle_mat* A);
+int64_t oracle_mat_cols(const oracle_mat* A);
+int     oracle_mat_export(const oracle_mat* A, int64_t* rowptr, int* cols, double* vals);
+oracle_mat* oracle_mat_transpose(const oracle_mat* A, int keep_zeros);
+
+/* dest = alpha*v + beta*A*w (SparseMatrix::axpy); v may be NULL when alpha == 0;
+ * v == dest selects the in-place branch */
+int oracle_axpy(const oracle_mat* A, double* dest, double alpha, const double* v, double beta, const double* w, int vblock);
+int oracle_apply(const oracle_mat* A, double* y, const double* x, int vblock);
+int oracle_matmul_minus(const oracle_mat* A, double* y, const double* x, int vblock);
+int oracle_apply_ignore_zero_rows(const oracle_mat* A, double* dest, double beta, const double* w, int vblock);
+
+double oracle_dot(int64_t nblocks, int block, const double* a, const double* b);
+double oracle_norm(int64_t nblocks, int block, const double* a);
+int oracle_scale_add2(int64_t len, double* d, double a1, const double* v1, double a2, const double* v2);
+int oracle_scale_add3(int64_t len, double* d, double a1, const double* v1, double a2, const double* v2, double a3, const double* v3);
+
+/* c = Jacobi(A, damp) d */
+int oracle_jacobi(const oracle_mat* A, double damp, int block_inverse, double* c, const double* d);
+/* kind: 0 gs_step_LL, 1 gs_step_UR, 2 sgs_step */
+int oracle_gs(const oracle_mat* A, int kind, double relax, double* c, const double* d);
+int oracle_lu_solve(const oracle_mat* A, double* x, const double* b);
+
+/* ---- solver level ---- */
+enum { ORACLE_SOLVER_CG = 0, ORACLE_SOLVER_BICGSTAB = 1, ORACLE_SOLVER_LINEAR = 2, ORACLE_SOLVER_LU = 3 };
+enum { ORACLE_PRECOND_NONE = 0, ORACLE_PRECOND_JACOBI = 1, ORACLE_PRECOND_GS = 2, ORACLE_PRECOND_BGS = 3,
+       ORACLE_PRECOND_SGS = 4, ORACLE_PRECOND_GMG = 5 };
+
+typedef struct oracle_solver_desc {
+	int solver;            /* ORACLE_SOLVER_* */
+	int precond;           /* ORACLE_PRECOND_* */
+	double damp;           /* Jacobi damping / GS relax when used directly as preconditioner */
+	int max_steps;         /* StdConvCheck */
+	double min_defect;
+	double rel_reduction;
+	/* GMG */
+	int base_lev, top_lev;
+	int cycle;             /* 1 V, 2 W, -1 F */
+	int nu1, nu2;
+	int smoother;          /* ORACLE_PRECOND_JACOBI/GS/BGS/SGS */
+	double smoother_damp;  /* Jacobi: damping; GS family: relax */
+	int base_solver;       /* ORACLE_SOLVER_LU or ORACLE_SOLVER_CG (unpreconditioned, tight tolerance) */
+	int base_max_steps;
+	double base_min_defect, base_rel_reduction;
+} oracle_solver_desc;
+
+typedef struct oracle_solver oracle_solver;
+
+oracle_solver* oracle_solver_create(const oracle_solver_desc* d);
+void oracle_solver_destroy(oracle_solver* s);
+/* GMG level operators; P, R may be NULL on the base level. Matrices stay owned by the caller. */
+int oracle_solver_set_level(oracle_solver* s, int lev, const oracle_mat* A, const oracle_mat* P, const oracle_mat* R);
+int oracle_solver_init(oracle_solver* s, const oracle_mat* A);
+/* x: in = start iterate, out = solution; b is not modified.  Returns 0 on success
+ * (converged), 1 if the convergence check failed, <0 on error. */
+int oracle_solver_apply(oracle_solver* s, double* x, const double* b, int vblock);
+int oracle_solver_steps(const oracle_solver* s);
+/* defect history: entry 0 = initial defect; returns number of entries copied */
+int oracle_solver_history(const oracle_solver* s, double* out, int cap);
+/* one application of the configured preconditioner alone: c = M^{-1} d */
+int oracle_precond_apply(oracle_solver* s, double* c, const double* d, int vblock);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,441 @@
+/*
+ * oracle/port_backend.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Plain C++ restatement ("port") of the arithmetic of ugcore's CPU algebra on
+ * the GMG/Krylov hot path.  No reference headers are included; every routine
+ * cites the reference lines it restates (paths relative to
+ * /root/reference/ugbase).  Compile WITHOUT -ffast-math / -march so that no FMA
+ * contraction happens (reference release flags, cmake/ug/debug.cmake:76-88).
+ *
+ * Pinned against: tests/ref/sm_transpose.out (transpose nnz), the FV1
+ * known-answer stencils, and — when /root/reference is present — bit-for-bit
+ * against the compiled reference templates (oracle/_ref, RefBackend).
+ */
+#include "backend.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+
+namespace oracle {
+namespace {
+
+struct PMat : Mat {
+	std::vector<int64_t> rp;
+	std::vector<int> ci;
+	std::vector<double> va; // block*block per entry, column-major (fixed_array_impl.h:182-203)
+};
+struct PVec : Vec {
+	std::vector<double> v;
+	double* data() override { return v.data(); }
+	const double* data() const override { return v.data(); }
+};
+struct PDiag : DiagInv { int B; std::vector<double> inv; };
+struct PLU : DenseLU { int64_t n; std::vector<double> a; std::vector<size_t> piv; };
+
+inline const PMat& M(const Mat& m) { return static_cast<const PMat&>(m); }
+
+// dest = beta*A*w   (small_matrix/densematrix_operations.h:56-65; scalar: matrix_use_operators.h:43-47)
+inline void blk_mult(int B, double* dest, double beta, const double* A, const double* w)
+{
+	for (int r = 0; r < B; ++r) {
+		dest[r] = beta * A[r] * w[0];
+		for (int c = 1; c < B; ++c) dest[r] = 1.0 * dest[r] + beta * A[r + B * c] * w[c];
+	}
+}
+// dest = 1.0*dest + beta*A*w  (densematrix_operations.h:69-79 with alpha1=1, v1=dest)
+inline void blk_mult_add(int B, double* dest, double beta, const double* A, const double* w)
+{
+	for (int r = 0; r < B; ++r) {
+		dest[r] = 1.0 * dest[r];
+		for (int c = 0; c < B; ++c) dest[r] = 1.0 * dest[r] + beta * A[r + B * c] * w[c];
+	}
+}
+
+// dest = beta * mat^{-1} vec  (double.h:157-161; densematrix_inverse.h:78-86,137-147,229-245)
+inline bool blk_inverse_mult(int B, double* dest, double beta, const double* m, const double* v)
+{
+#define MM(r, c) m[(r) + B * (c)]
+	if (B == 1) { if (m[0] == 0.0) return false; dest[0] = beta * v[0] / m[0]; return true; }
+	if (B == 2) {
+		const double det = MM(0,0) * MM(1,1) - MM(1,0) * MM(0,1);
+		if (det == 0.0) return false;
+		dest[0] = beta * (MM(1,1) * v[0] - MM(0,1) * v[1]) / det;
+		dest[1] = beta * (-MM(1,0) * v[0] + MM(0,0) * v[1]) / det;
+		return true;
+	}
+	const double det = MM(0,0)*MM(1,1)*MM(2,2) + MM(0,1)*MM(1,2)*MM(2,0) + MM(0,2)*MM(1,0)*MM(2,1)
+	                 - MM(0,0)*MM(1,2)*MM(2,1) - MM(0,1)*MM(1,0)*MM(2,2) - MM(0,2)*MM(1,1)*MM(2,0);
+	if (det == 0.0) return false;
+	dest[0] = (( MM(1,1)*MM(2,2) - MM(1,2)*MM(2,1)) * v[0] +
+	           (-MM(0,1)*MM(2,2) + MM(0,2)*MM(2,1)) * v[1] +
+	           ( MM(0,1)*MM(1,2) - MM(0,2)*MM(1,1)) * v[2]) * beta / det;
+	dest[1] = ((-MM(1,0)*MM(2,2) + MM(1,2)*MM(2,0)) * v[0] +
+	           ( MM(0,0)*MM(2,2) - MM(0,2)*MM(2,0)) * v[1] +
+	           (-MM(0,0)*MM(1,2) + MM(0,2)*MM(1,0)) * v[2]) * beta / det;
+	dest[2] = (( MM(1,0)*MM(2,1) - MM(1,1)*MM(2,0)) * v[0] +
+	           (-MM(0,0)*MM(2,1) + MM(0,1)*MM(2,0)) * v[1] +
+	           ( MM(0,0)*MM(1,1) - MM(0,1)*MM(1,0)) * v[2]) * beta / det;
+	return true;
+#undef MM
+}
+
+// inv = m^{-1}  (double.h:197-201; densematrix_inverse.h:46-51,96-108,163-181)
+inline bool blk_get_inverse(int B, double* inv, const double* m)
+{
+#define MM(r, c) m[(r) + B * (c)]
+#define II(r, c) inv[(r) + B * (c)]
+	if (B == 1) { inv[0] = 1.0 / m[0]; return m[0] != 0.0; }
+	if (B == 2) {
+		double invdet = MM(0,0) * MM(1,1) - MM(1,0) * MM(0,1);
+		if (invdet == 0.0) return false;
+		invdet = 1.0 / invdet;
+		II(0,0) = MM(1,1) * invdet; II(1,1) = MM(0,0) * invdet;
+		II(0,1) = MM(0,1) * -invdet; II(1,0) = MM(1,0) * -invdet;
+		return true;
+	}
+	double invdet = MM(0,0)*MM(1,1)*MM(2,2) + MM(0,1)*MM(1,2)*MM(2,0) + MM(0,2)*MM(1,0)*MM(2,1)
+	              - MM(0,0)*MM(1,2)*MM(2,1) - MM(0,1)*MM(1,0)*MM(2,2) - MM(0,2)*MM(1,1)*MM(2,0);
+	if (invdet == 0.0) return false;
+	invdet = 1.0 / invdet;
+	II(0,0) = ( MM(1,1)*MM(2,2) - MM(1,2)*MM(2,1)) * invdet;
+	II(0,1) = (-MM(0,1)*MM(2,2) + MM(0,2)*MM(2,1)) * invdet;
+	II(0,2) = ( MM(0,1)*MM(1,2) - MM(0,2)*MM(1,1)) * invdet;
+	II(1,0) = (-MM(1,0)*MM(2,2) + MM(1,2)*MM(2,0)) * invdet;
+	II(1,1) = ( MM(0,0)*MM(2,2) - MM(0,2)*MM(2,0)) * invdet;
+	II(1,2) = (-MM(0,0)*MM(1,2) + MM(0,2)*MM(1,0)) * invdet;
+	II(2,0) = ( MM(1,0)*MM(2,1) - MM(1,1)*MM(2,0)) * invdet;
+	II(2,1) = (-MM(0,0)*MM(2,1) + MM(0,1)*MM(2,0)) * invdet;
+	II(2,2) = ( MM(0,0)*MM(1,1) - MM(0,1)*MM(1,0)) * invdet;
+	return true;
+#undef MM
+#undef II
+}
+
+struct PortBackend : Backend {
+	const char* name() const override { return "port"; }
+
+	Mat* matrix(int block, int64_t nrows, int64_t ncols, const int64_t* rowptr, const int* cols,
+	            const double* vals) override
+	{
+		PMat* m = new PMat;
+		m->nrows = nrows; m->ncols = ncols; m->block = block;
+		m->rp.assign(rowptr, rowptr + nrows + 1);
+		const int64_t nnz = rowptr[nrows];
+		m->ci.assign(cols, cols + nnz);
+		m->va.assign(vals, vals + nnz * block * block);
+		return m;
+	}
+	Vec* vector(int64_t nblocks, int block) override
+	{
+		PVec* v = new PVec; v->n = nblocks; v->block = block; v->v.assign((size_t)nblocks * block, 0.0);
+		return v;
+	}
+	int64_t nnz(const Mat& A) override { return (int64_t)M(A).ci.size(); }
+	void export_crs(const Mat& A_, int64_t* rowptr, int* cols, double* vals) override
+	{
+		const PMat& A = M(A_);
+		std::copy(A.rp.begin(), A.rp.end(), rowptr);
+		std::copy(A.ci.begin(), A.ci.end(), cols);
+		std::copy(A.va.begin(), A.va.end(), vals);
+	}
+
+	// cpu_algebra/sparsematrix_impl.h:148-183 (set_as_transpose_of: every stored
+	// connection is re-inserted, explicit zeros included) and set_as_transpose_of2
+	// (zero-valued connections are dropped); block entries are transposed.
+	Mat* transpose(const Mat& A_, bool keep_zeros) override
+	{
+		const PMat& A = M(A_);
+		const int B = A.block, BB = B * B;
+		PMat* T = new PMat;
+		T->nrows = A.ncols; T->ncols = A.nrows; T->block = B;
+		T->rp.assign(T->nrows + 1, 0);
+		auto is_zero = [&](int64_t p) {
+			for (int t = 0; t < BB; ++t) if (A.va[p * BB + t] != 0.0) return false;
+			return true;
+		};
+		for (int64_t r = 0; r < A.nrows; ++r)
+			for (int64_t p = A.rp[r]; p < A.rp[r + 1]; ++p)
+				if (keep_zeros || !is_zero(p)) T->rp[A.ci[p] + 1]++;
+		for (int64_t r = 0; r < T->nrows; ++r) T->rp[r + 1] += T->rp[r];
+		T->ci.resize(T->rp[T->nrows]); T->va.resize((size_t)T->rp[T->nrows] * BB);
+		std::vector<int64_t> fill(T->rp.begin(), T->rp.end() - 1);
+		for (int64_t r = 0; r < A.nrows; ++r)
+			for (int64_t p = A.rp[r]; p < A.rp[r + 1]; ++p) {
+				if (!keep_zeros && is_zero(p)) continue;
+				const int64_t q = fill[A.ci[p]]++;
+				T->ci[q] = (int)r;
+				for (int i = 0; i < B; ++i)
+					for (int j = 0; j < B; ++j) T->va[q * BB + i + B * j] = A.va[p * BB + j + B * i];
+			}
+		return T;
+	}
+
+	// sparsematrix_impl.h:300-316 (alpha1 == 0 branch of axpy): first connection
+	// assigned, the others accumulated in ascending column order; empty row -> 0.
+	void apply(const Mat& A_, Vec& y, const Vec& x) override
+	{
+		const PMat& A = M(A_); const int B = A.block, BB = B * B;
+		double* yd = y.data(); const double* xd = x.data();
+		for (int64_t i = 0; i < A.nrows; ++i) {
+			int64_t p = A.rp[i]; const int64_t e = A.rp[i + 1];
+			double* d = yd + i * B;
+			if (p == e) { for (int t = 0; t < B; ++t) d[t] = 0.0; continue; }
+			blk_mult(B, d, 1.0, &A.va[p * BB], xd + (int64_t)A.ci[p] * B);
+			for (++p; p != e; ++p) blk_mult_add(B, d, 1.0, &A.va[p * BB], xd + (int64_t)A.ci[p] * B);
+		}
+	}
+	// sparsematrix.h:199-207 -> axpy(dest,1,dest,-1,w): sparsematrix_impl.h:318-329,
+	// mat_mult_add_row :257-268 — term-by-term accumulation INTO dest[i].
+	void matmul_minus(const Mat& A_, Vec& y, const Vec& x) override
+	{
+		const PMat& A = M(A_); const int B = A.block, BB = B * B;
+		double* yd = y.data(); const double* xd = x.data();
+		for (int64_t i = 0; i < A.nrows; ++i)
+			for (int64_t p = A.rp[i]; p != A.rp[i + 1]; ++p)
+				blk_mult_add(B, yd + i * B, -1.0, &A.va[p * BB], xd + (int64_t)A.ci[p] * B);
+	}
+	// general axpy, sparsematrix_impl.h:291-339
+	void axpy(const Mat& A_, Vec& dest, double alpha, const Vec& v, double beta, const Vec& w) override
+	{
+		const PMat& A = M(A_); const int B = A.block, BB = B * B;
+		double* dd = dest.data(); const double* vd = v.data(); const double* wd = w.data();
+		if (A.block == 1 && dest.block > 1) {
+			// scalar transfer matrix acting on block vectors (prolongation): only the
+			// alpha1 == 0 branch is used on the path (std_transfer_impl.h:738-740)
+			if (alpha != 0.0) throw std::runtime_error("port: scalar-on-block axpy needs alpha == 0");
+			const int VB = dest.block;
+			for (int64_t i = 0; i < A.nrows; ++i) {
+				const int64_t p = A.rp[i], e = A.rp[i + 1];
+				for (int t = 0; t < VB; ++t) {
+					if (p == e) { dd[i * VB + t] = 0.0; continue; }
+					double s = beta * A.va[p] * wd[(int64_t)A.ci[p] * VB + t];
+					for (int64_t q = p + 1; q != e; ++q) s = 1.0 * s + beta * A.va[q] * wd[(int64_t)A.ci[q] * VB + t];
+					dd[i * VB + t] = s;
+				}
+			}
+			return;
+		}
+		if (alpha == 0.0) {
+			for (int64_t i = 0; i < A.nrows; ++i) {
+				int64_t p = A.rp[i]; const int64_t e = A.rp[i + 1];
+				double* d = dd + i * B;
+				if (p == e) { for (int t = 0; t < B; ++t) d[t] = 0.0; continue; }
+				blk_mult(B, d, beta, &A.va[p * BB], wd + (int64_t)A.ci[p] * B);
+				for (++p; p != e; ++p) blk_mult_add(B, d, beta, &A.va[p * BB], wd + (int64_t)A.ci[p] * B);
+			}
+		} else {
+			const bool inplace = (&dest == &v);
+			for (int64_t i = 0; i < A.nrows; ++i) {
+				double* d = dd + i * B;
+				if (inplace) { if (alpha != 1.0) for (int t = 0; t < B; ++t) d[t] *= alpha; }
+				else for (int t = 0; t < B; ++t) d[t] = alpha * vd[i * B + t];
+				for (int64_t p = A.rp[i]; p != A.rp[i + 1]; ++p)
+					blk_mult_add(B, d, beta, &A.va[p * BB], wd + (int64_t)A.ci[p] * B);
+			}
+		}
+	}
+	// sparsematrix_impl.h:271-288: rows without connections leave dest untouched.
+	// A.block == 1 with a block vector = scalar transfer acting per component
+	// (P/R of a block algebra carry the scalar on the block diagonal).
+	void apply_ignore_zero_rows(const Mat& A_, Vec& dest, double beta, const Vec& w) override
+	{
+		const PMat& A = M(A_);
+		const int VB = dest.block;
+		double* dd = dest.data(); const double* wd = w.data();
+		if (A.block == 1 && VB > 1) {
+			for (int64_t i = 0; i < A.nrows; ++i) {
+				int64_t p = A.rp[i]; const int64_t e = A.rp[i + 1];
+				if (p == e) continue;
+				for (int t = 0; t < VB; ++t) {
+					double s = beta * A.va[p] * wd[(int64_t)A.ci[p] * VB + t];
+					for (int64_t q = p + 1; q != e; ++q) s = 1.0 * s + beta * A.va[q] * wd[(int64_t)A.ci[q] * VB + t];
+					dd[i * VB + t] = s;
+				}
+			}
+			return;
+		}
+		const int B = A.block, BB = B * B;
+		for (int64_t i = 0; i < A.nrows; ++i) {
+			int64_t p = A.rp[i]; const int64_t e = A.rp[i + 1];
+			if (p == e) continue;
+			double* d = dd + i * B;
+			blk_mult(B, d, beta, &A.va[p * BB], wd + (int64_t)A.ci[p] * B);
+			for (++p; p != e; ++p) blk_mult_add(B, d, beta, &A.va[p * BB], wd + (int64_t)A.ci[p] * B);
+		}
+	}
+
+	// cpu_algebra/vector_impl.h:72-79: strictly sequential left-to-right sum of
+	// VecProd(values[i], w[i]); for a block entry VecProd is itself a sequential sum
+	// started at 0 (common/operations_vec.h:187-194)
+	double dot(const Vec& a, const Vec& b) override
+	{
+		const double* x = a.data(); const double* y = b.data();
+		const int B = a.block;
+		double s = 0;
+		for (int64_t i = 0; i < a.n; ++i) {
+			double l = 0;
+			for (int t = 0; t < B; ++t) l += x[i * B + t] * y[i * B + t];
+			s += l;
+		}
+		return s;
+	}
+	// vector_impl.h:323-329: sqrt(sum BlockNorm2); BlockNorm2 of a DenseVector is the
+	// sequential sum of squares of its components (small_algebra/blocks.h)
+	double norm(const Vec& a) override
+	{
+		const double* x = a.data(); const int B = a.block;
+		double d = 0;
+		for (int64_t i = 0; i < a.n; ++i) {
+			double s = 0;
+			for (int t = 0; t < B; ++t) s += x[i * B + t] * x[i * B + t];
+			d += s;
+		}
+		return std::sqrt(d);
+	}
+	void set(Vec& a, double v) override { std::fill(a.data(), a.data() + a.len(), v); }
+	void assign(Vec& dst, const Vec& src) override { std::memcpy(dst.data(), src.data(), sizeof(double) * dst.len()); }
+	void add(Vec& dst, const Vec& src) override
+	{ double* d = dst.data(); const double* s = src.data(); for (int64_t i = 0, n = dst.len(); i < n; ++i) d[i] += s[i]; }
+	void sub(Vec& dst, const Vec& src) override
+	{ double* d = dst.data(); const double* s = src.data(); for (int64_t i = 0, n = dst.len(); i < n; ++i) d[i] -= s[i]; }
+	void scale(Vec& dst, double f) override
+	{ double* d = dst.data(); for (int64_t i = 0, n = dst.len(); i < n; ++i) d[i] *= f; }
+	// common/operations_vec.h:55-66, 162-175
+	void scale_add2(Vec& d_, double a1, const Vec& v1_, double a2, const Vec& v2_) override
+	{
+		double* d = d_.data(); const double* v1 = v1_.data(); const double* v2 = v2_.data();
+		for (int64_t i = 0, n = d_.len(); i < n; ++i) d[i] = a1 * v1[i] + a2 * v2[i];
+	}
+	void scale_add3(Vec& d_, double a1, const Vec& v1_, double a2, const Vec& v2_, double a3, const Vec& v3_) override
+	{
+		double* d = d_.data(); const double* v1 = v1_.data(); const double* v2 = v2_.data(); const double* v3 = v3_.data();
+		for (int64_t i = 0, n = d_.len(); i < n; ++i) d[i] = a1 * v1[i] + a2 * v2[i] + a3 * v3[i];
+	}
+
+	// operator/preconditioner/jacobi.h:196-220 (serial branch):
+	//   m = A(i,i) (or only its diagonal when !block);  m *= 1./damp;  GetInverse(diagInv, m)
+	DiagInv* jacobi_prepare(const Mat& A_, double damp, bool block) override
+	{
+		const PMat& A = M(A_); const int B = A.block, BB = B * B;
+		PDiag* D = new PDiag; D->B = B; D->inv.assign((size_t)A.nrows * BB, 0.0);
+		const double s = 1. / damp;
+		for (int64_t i = 0; i < A.nrows; ++i) {
+			double m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+			for (int64_t p = A.rp[i]; p != A.rp[i + 1]; ++p)
+				if (A.ci[p] == i) { std::memcpy(m, &A.va[p * BB], sizeof(double) * BB); break; }
+			if (!block && B > 1)
+				for (int r = 0; r < B; ++r) for (int c = 0; c < B; ++c) if (r != c) m[r + B * c] = 0.0;
+			for (int t = 0; t < BB; ++t) m[t] *= s;
+			blk_get_inverse(B, &D->inv[i * BB], m);
+		}
+		return D;
+	}
+	// jacobi.h:228-232: c[i] = 1.0 * diagInv[i] * d[i]
+	void jacobi_step(const DiagInv& D_, Vec& c, const Vec& d) override
+	{
+		const PDiag& D = static_cast<const PDiag&>(D_); const int B = D.B, BB = B * B;
+		double* cd = c.data(); const double* dd = d.data();
+		for (int64_t i = 0; i < c.n; ++i) blk_mult(B, cd + i * B, 1.0, &D.inv[i * BB], dd + i * B);
+	}
+
+	// algebra_common/core_smoothers.h:105-130
+	void gs_step_LL(const Mat& A_, Vec& c, const Vec& d, double relax) override
+	{
+		const PMat& A = M(A_); const int B = A.block, BB = B * B;
+		double* cd = c.data(); const double* dd = d.data();
+		for (int64_t i = 0; i < A.nrows; ++i) {
+			double s[3];
+			for (int t = 0; t < B; ++t) s[t] = dd[i * B + t];
+			int64_t p = A.rp[i]; const int64_t e = A.rp[i + 1];
+			for (; p != e && A.ci[p] < i; ++p) blk_mult_add(B, s, -1.0, &A.va[p * BB], cd + (int64_t)A.ci[p] * B);
+			double zero[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+			const double* Aii = (p != e && A.ci[p] == i) ? &A.va[p * BB] : zero;
+			blk_inverse_mult(B, cd + i * B, relax, Aii, s);
+		}
+	}
+	// core_smoothers.h:147-169
+	void gs_step_UR(const Mat& A_, Vec& c, const Vec& d, double relax) override
+	{
+		const PMat& A = M(A_); const int B = A.block, BB = B * B;
+		double* cd = c.data(); const double* dd = d.data();
+		if (A.nrows == 0) return;
+		int64_t i = A.nrows - 1;
+		do {
+			double s[3];
+			for (int t = 0; t < B; ++t) s[t] = dd[i * B + t];
+			int64_t diag = A.rp[i]; const int64_t e = A.rp[i + 1];
+			while (diag != e && A.ci[diag] != i) ++diag;
+			for (int64_t p = diag + 1; p < e; ++p) blk_mult_add(B, s, -1.0, &A.va[p * BB], cd + (int64_t)A.ci[p] * B);
+			blk_inverse_mult(B, cd + i * B, relax, &A.va[diag * BB], s);
+		} while (i-- != 0);
+	}
+	// core_smoothers.h:187-206
+	void sgs_step(const Mat& A_, Vec& c, const Vec& d, double relax) override
+	{
+		const PMat& A = M(A_); const int B = A.block, BB = B * B;
+		gs_step_LL(A_, c, d, relax);
+		double* cd = c.data();
+		for (int64_t i = 0; i < A.nrows; ++i) {
+			double s[3];
+			for (int t = 0; t < B; ++t) s[t] = cd[i * B + t];
+			const double* Aii = nullptr;
+			for (int64_t p = A.rp[i]; p != A.rp[i + 1]; ++p) if (A.ci[p] == i) { Aii = &A.va[p * BB]; break; }
+			blk_mult(B, cd + i * B, 1.0, Aii, s);
+		}
+		gs_step_UR(A_, c, c, relax);
+	}
+
+	// operator/linear_solver/lu.h:122-140 (init_dense) with the non-LAPACK kernels
+	// small_algebra/no_lapack/lu_decomp.h:45-75 (LUDecomp with row interchange)
+	DenseLU* lu_init(const Mat& A_) override
+	{
+		const PMat& A = M(A_); const int B = A.block, BB = B * B;
+		const int64_t n = A.nrows * B;
+		PLU* L = new PLU; L->n = n; L->a.assign((size_t)n * n, 0.0); L->piv.assign(n, 0);
+		std::vector<double>& a = L->a;
+#define AA(i, j) a[(size_t)(i) * n + (j)]
+		for (int64_t r = 0; r < A.nrows; ++r)
+			for (int64_t p = A.rp[r]; p != A.rp[r + 1]; ++p)
+				for (int i = 0; i < B; ++i) for (int j = 0; j < B; ++j)
+					AA(r * B + i, (int64_t)A.ci[p] * B + j) = A.va[p * BB + i + B * j];
+		for (int64_t k = 0; k < n; ++k) {
+			int64_t biggest = k;
+			for (int64_t j = k + 1; j < n; ++j) if (std::fabs(AA(biggest, k)) < std::fabs(AA(j, k))) biggest = j;
+			if (biggest != k) for (int64_t j = 0; j < n; ++j) std::swap(AA(k, j), AA(biggest, j));
+			L->piv[k] = (size_t)biggest;
+			if (std::fabs(AA(k, k)) < 1e-10) { delete L; return nullptr; }
+			for (int64_t i = k + 1; i < n; ++i) {
+				AA(i, k) = AA(i, k) / AA(k, k);
+				for (int64_t j = k + 1; j < n; ++j) AA(i, j) = AA(i, j) - AA(i, k) * AA(k, j);
+			}
+		}
+		return L;
+	}
+	// lu.h:189-207 (solve_dense) + lu_decomp.h:160-195 (SolveLU)
+	void lu_apply(const DenseLU& L_, Vec& x_, const Vec& b) override
+	{
+		const PLU& L = static_cast<const PLU&>(L_); const int64_t n = L.n; const std::vector<double>& a = L.a;
+		if (&x_ != &b) assign(x_, b);
+		double* x = x_.data();
+		for (int64_t i = 0; i < n; ++i) if ((size_t)i < L.piv[i]) std::swap(x[i], x[L.piv[i]]);
+		for (int64_t i = 0; i < n; ++i) {
+			double s = x[i];
+			for (int64_t k = 0; k < i; ++k) s -= AA(i, k) * x[k];
+			x[i] = s;
+		}
+		for (int64_t i = n - 1;; --i) {
+			double s = x[i];
+			for (int64_t k = i + 1; k < n; ++k) s -= AA(i, k) * x[k];
+			x[i] = s / AA(i, i);
+			if (i == 0) break;
+		}
+#undef AA
+	}
+};
+
+} // namespace
+
+Backend* make_port_backend() { return new PortBackend; }
+
+} // namespace oracle

@@ -1,0 +1,341 @@
+/*
+ * oracle/solvers.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ * Restated control flow; see solvers.h for the reference line map.
+ */
+#include "solvers.h"
+#include <cmath>
+#include <stdexcept>
+
+namespace oracle {
+
+// ---- StdConvCheck (convergence_check_impl.h:85-169, 246-257) --------------------
+
+void StdConvCheck::start_defect(double d)
+{
+	history.clear();
+	initialDefect = d; currentDefect = d; currentStep = 0; ratesProduct = 1;
+	history.push_back(d);
+}
+void StdConvCheck::update_defect(double d)
+{
+	lastDefect = currentDefect; currentDefect = d; currentStep++;
+	ratesProduct *= d / lastDefect;
+	history.push_back(d);
+}
+bool StdConvCheck::is_valid_number(double v)
+{
+	if (v == 0.0) return true;
+	return v >= std::numeric_limits<double>::min() && v <= std::numeric_limits<double>::max() && v == v && v >= 0.0;
+}
+bool StdConvCheck::iteration_ended() const
+{
+	if (!is_valid_number(currentDefect)) return true;
+	if (step() >= maxSteps) return true;
+	if (defect() < minDefect) return true;
+	if (reduction() < relReduction) return true;
+	return false;
+}
+bool StdConvCheck::post() const
+{
+	bool success = false;
+	if (defect() < minDefect) success = true;
+	if (reduction() < relReduction) success = true;
+	return success;
+}
+
+// ---- IPreconditioner (preconditioner.h:239-348) ---------------------------------
+
+bool Preconditioner::init(const Mat& A_)
+{
+	A = &A_;
+	if (!preprocess()) return false;
+	inited = true;
+	return true;
+}
+bool Preconditioner::apply(Vec& c, const Vec& d)
+{
+	if (!inited) return false;
+	if (!step(c, d)) return false;
+	const double kappa = damping;
+	if (kappa != 1.0) bk.scale(c, kappa);
+	return true;
+}
+bool Preconditioner::apply_update_defect(Vec& c, Vec& d)
+{
+	if (!apply(c, d)) return false;
+	bk.matmul_minus(*A, d, c);
+	return true;
+}
+
+// ---- Jacobi (jacobi.h:155-300) --------------------------------------------------
+
+bool Jacobi::preprocess()
+{
+	if (A->nrows != A->ncols) return false;
+	diagInv.reset(bk.jacobi_prepare(*A, damping, block));
+	return true;
+}
+bool Jacobi::step(Vec& c, const Vec& d) { bk.jacobi_step(*diagInv, c, d); return true; }
+bool Jacobi::apply(Vec& c, const Vec& d)
+{
+	if (!inited) return false;
+	// constant damping is already contained in diagInv (jacobi.h:283-290)
+	return step(c, d);
+}
+
+// ---- Gauss-Seidel (gauss_seidel.h:221-230, 270-380) ------------------------------
+
+bool GaussSeidel::step(Vec& c, const Vec& d)
+{
+	switch (kind) {
+		case FORWARD: bk.gs_step_LL(*A, c, d, relax); break;
+		case BACKWARD: bk.gs_step_UR(*A, c, d, relax); break;
+		case SYMMETRIC: bk.sgs_step(*A, c, d, relax); break;
+	}
+	return true;
+}
+
+// ---- ILinearOperatorInverse::apply (preconditioned_linear_operator_inverse.h:152-160)
+
+bool InverseOperator::apply(Vec& x, const Vec& b)
+{
+	VecP bTmp(bk.vector(b.n, b.block));
+	bk.assign(*bTmp, b);
+	return apply_return_defect(x, *bTmp);
+}
+
+// ---- LU (lu.h:236-263, 322-380) ---------------------------------------------------
+
+bool LU::init(const Mat& A_)
+{
+	A = &A_;
+	if (A_.nrows == 0) return true;
+	lu.reset(bk.lu_init(A_));
+	if (!lu) throw std::runtime_error("LU: matrix is singular");
+	return true;
+}
+bool LU::apply(Vec& x, const Vec& b)
+{
+	if (A->nrows == 0) return true;
+	bk.lu_apply(*lu, x, b);
+	return true;
+}
+bool LU::apply_return_defect(Vec& x, Vec& b)
+{
+	if (!apply(x, b)) return false;
+	bk.matmul_minus(*A, b, x);
+	return true;
+}
+
+// ---- CG (cg.h:103-242) -------------------------------------------------------------
+
+bool CG::apply_return_defect(Vec& x, Vec& b)
+{
+	Vec& r = b;
+	bk.matmul_minus(*A, r, x);                 // r := b - A x
+	VecP q(bk.vector(r.n, r.block)), z(bk.vector(x.n, x.block)), p(bk.vector(x.n, x.block));
+	if (precond) { if (!precond->apply(*z, r)) return false; }
+	else bk.assign(*z, r);
+	conv.start_defect(bk.norm(r));
+	bk.assign(*p, *z);
+	double rhoOld = bk.dot(*z, r), rho;
+	while (!conv.iteration_ended()) {
+		bk.apply(*A, *q, *p);                  // q = A p
+		double lambda = bk.dot(*q, *p);
+		if (lambda == 0.0) {
+			if (p->len()) return false;
+			lambda = 1.0;
+		}
+		const double alpha = rhoOld / lambda;
+		bk.scale_add2(x, 1.0, x, alpha, *p);
+		bk.scale_add2(r, 1.0, r, -alpha, *q);
+		conv.update_defect(bk.norm(r));
+		if (conv.iteration_ended()) break;
+		if (precond) { if (!precond->apply(*z, r)) return false; }
+		else bk.assign(*z, r);
+		rho = bk.dot(*z, r);
+		const double beta = rho / rhoOld;
+		bk.scale_add2(*p, beta, *p, 1.0, *z);
+		rhoOld = rho;
+	}
+	return conv.post();
+}
+
+// ---- BiCGStab (bicgstab.h:112-383) ---------------------------------------------------
+
+bool BiCGStab::apply_return_defect(Vec& x, Vec& b)
+{
+	bk.matmul_minus(*A, b, x);
+	Vec& r = b;
+	VecP r0(bk.vector(r.n, r.block)), p(bk.vector(r.n, r.block)), v(bk.vector(r.n, r.block)),
+	     t(bk.vector(r.n, r.block)), s(bk.vector(r.n, r.block)), q(bk.vector(x.n, x.block));
+	conv.start_defect(bk.norm(r));
+	double rho = 1, alpha = 1, omega = 1, norm_r0 = 0.0;
+	bool bRestart = true;
+	while (!conv.iteration_ended()) {
+		if (numRestarts > 0 && (conv.step() % numRestarts == 0)) bRestart = true;
+		if (bRestart) {
+			bk.assign(*r0, r);
+			bk.set(*p, 0.0); alpha = 0.0;
+			bk.set(*v, 0.0); omega = 1.0;
+			rho = 1.0;
+			norm_r0 = conv.defect();
+			bRestart = false;
+		}
+		const double rhoOld = rho;
+		if (!r.len()) rho = 1.0; else rho = bk.dot(*r0, r);
+		const double norm_r = conv.defect();
+		if (std::fabs(rho) / (norm_r * norm_r0) <= minOrtho) bRestart = true;
+		if (rhoOld == 0.0) return false;
+		const double beta = (rho / rhoOld) * (alpha / omega);
+		bk.scale_add3(*p, 1.0, r, beta, *p, -beta * omega, *v);
+		if (precond) { if (!precond->apply(*q, *p)) return false; }
+		else bk.assign(*q, *p);
+		bk.apply(*A, *v, *q);
+		if (!v->len()) alpha = 1.0; else alpha = bk.dot(*v, *r0);
+		if (alpha == 0.0) return false;
+		alpha = rho / alpha;
+		bk.scale_add2(x, 1.0, x, alpha, *q);
+		bk.scale_add2(*s, 1.0, r, -alpha, *v);
+		conv.update_defect(bk.norm(*s));
+		if (conv.iteration_ended()) { bk.assign(r, *s); break; }
+		if (precond) { if (!precond->apply(*q, *s)) return false; }
+		else bk.assign(*q, *s);
+		bk.apply(*A, *t, *q);
+		double tt;
+		if (!t->len()) tt = 1.0; else tt = bk.dot(*t, *t);
+		if (!s->len()) omega = 1.0; else omega = bk.dot(*s, *t);
+		if (tt == 0.0) return false;
+		omega = omega / tt;
+		bk.scale_add2(x, 1.0, x, omega, *q);
+		bk.scale_add2(r, 1.0, *s, -omega, *t);
+		conv.update_defect(bk.norm(r));
+		if (omega == 0.0) return false;
+	}
+	return conv.post();
+}
+
+// ---- LinearSolver (linear_solver.h:114-196) --------------------------------------------
+
+bool LinearSolver::apply_return_defect(Vec& x, Vec& b)
+{
+	Vec& d = b;
+	bk.matmul_minus(*A, d, x);
+	VecP c(bk.vector(x.n, x.block));
+	conv.start_defect(bk.norm(d));
+	while (!conv.iteration_ended()) {
+		if (precond) { if (!precond->apply_update_defect(*c, d)) return false; }
+		else { bk.assign(*c, d); bk.matmul_minus(*A, d, *c); }
+		bk.add(x, *c);
+		conv.update_defect(bk.norm(d));
+	}
+	return conv.post();
+}
+
+// ---- GMG (mg_solver_impl.hpp) -----------------------------------------------------------
+
+void GMG::set_level(int level, const Mat* A, const Mat* P, const Mat* R)
+{
+	if (level < baseLev || level > topLev) throw std::runtime_error("GMG::set_level: level out of range");
+	if ((int)lev.size() != topLev - baseLev + 1) lev.resize(topLev - baseLev + 1);
+	LevData& ld = L(level);
+	ld.A = A; ld.P = P; ld.R = R;
+}
+
+// init(): mg_solver_impl.hpp:378-496 — level memory, smoother clones + init
+// (:1135-1169), base solver init (:1171-1229); level operators are handed in
+// re-discretised (assemble_level_operator :526-752, rap = false).
+bool GMG::init(const Mat& A_)
+{
+	surfaceMat = &A_;
+	if (baseLev > topLev) throw std::runtime_error("GMG::init: Base Level greater than Surface level.");
+	if (!smootherProto) throw std::runtime_error("GMG::init: PreSmoother not set.");
+	if (!baseSolver) throw std::runtime_error("GMG::init: Base Solver not set.");
+	for (int l = baseLev; l <= topLev; ++l) {
+		LevData& ld = L(l);
+		if (!ld.A) throw std::runtime_error("GMG::init: level operator missing");
+		ld.sc.reset(bk.vector(ld.A->nrows, ld.A->block));
+		ld.sd.reset(bk.vector(ld.A->nrows, ld.A->block));
+		ld.st.reset(bk.vector(ld.A->nrows, ld.A->block));
+		if (l > baseLev) {
+			if (!ld.P || !ld.R) throw std::runtime_error("GMG::init: transfer missing");
+			ld.pre.reset(smootherProto->clone());
+			ld.post.reset(smootherProto->clone());
+			if (!ld.pre->init(*ld.A) || !ld.post->init(*ld.A)) return false;
+		}
+	}
+	return baseSolver->init(*L(baseLev).A);
+}
+
+// apply(): mg_solver_impl.hpp:174-275
+bool GMG::apply(Vec& c, const Vec& d)
+{
+	LevData& top = L(topLev);
+	bk.assign(*top.sd, d);             // surface -> level copy (:211-217), identity map
+	bk.set(c, 0.0);                    // :231
+	bk.set(*top.sc, 0.0);              // :234
+	lmgc(topLev, cycleType);           // :238
+	bk.add(c, *top.sc);                // :244-248
+	if (damping != 1.0) bk.scale(c, damping); // :259-260
+	return true;
+}
+
+// apply_update_defect(): mg_solver_impl.hpp:277-320
+bool GMG::apply_update_defect(Vec& c, Vec& d)
+{
+	if (!apply(c, d)) return false;
+	bk.matmul_minus(*surfaceMat, d, c);
+	return true;
+}
+
+// lmgc(): mg_solver_impl.hpp:2089-2136
+void GMG::lmgc(int l, int cycle)
+{
+	if (l == baseLev) { base_solve(topLev); return; }
+	presmooth_and_restriction(l);
+	if (l - 1 == baseLev) base_solve(l - 1);
+	else if (cycle == F_CYCLE) { lmgc(l - 1, F_CYCLE); lmgc(l - 1, V_CYCLE); }
+	else for (int i = 0; i < cycle; ++i) lmgc(l - 1, cycle);
+	prolongation_and_postsmooth(l);
+}
+
+// presmooth_and_restriction(): mg_solver_impl.hpp:1685-1816
+void GMG::presmooth_and_restriction(int l)
+{
+	LevData& lf = L(l); LevData& lc = L(l - 1);
+	for (int nu = 0; nu < numPreSmooth; ++nu) {
+		if (!lf.pre->apply(*lf.st, *lf.sd)) throw std::runtime_error("GMG: Smoothing step failed.");
+		bk.matmul_minus(*lf.A, *lf.sd, *lf.st);            // :1726
+		if (nu < numPreSmooth - 1) bk.add(*lf.sc, *lf.st); // :1729-1730
+	}
+	bk.set(*lc.sc, 0.0);                                   // :1780
+	if (numPreSmooth > 0) bk.add(*lf.sc, *lf.st);          // :1783-1784
+	// do_restrict: std_transfer_impl.h:791-792
+	bk.apply_ignore_zero_rows(*lf.R, *lc.sd, dampRes, *lf.sd);
+}
+
+// prolongation_and_postsmooth(): mg_solver_impl.hpp:1818-1964
+void GMG::prolongation_and_postsmooth(int l)
+{
+	LevData& lf = L(l); LevData& lc = L(l - 1);
+	// prolongate: std_transfer_impl.h:738-740 — axpy(uFine, 0.0, uFine, dampProl, uCoarse)
+	bk.axpy(*lf.P, *lf.st, 0.0, *lf.st, dampProl, *lc.sc);
+	bk.add(*lf.sc, *lf.st);                                // :1905
+	for (int nu = 0; nu < numPostSmooth; ++nu) {
+		bk.matmul_minus(*lf.A, *lf.sd, *lf.st);            // :1919
+		if (!lf.post->apply(*lf.st, *lf.sd)) throw std::runtime_error("GMG: Smoothing step failed.");
+		bk.add(*lf.sc, *lf.st);                            // :1943
+	}
+	// m_LocalFullRefLevel == topLev on a fully refined grid (:1309, :1359)
+	if (l >= topLev) bk.matmul_minus(*lf.A, *lf.sd, *lf.st); // :1954-1958
+}
+
+// base_solve(): mg_solver_impl.hpp:1967-2086 (non-gathered branch)
+void GMG::base_solve(int l)
+{
+	LevData& ld = L(l);
+	if (!baseSolver->apply(*ld.sc, *ld.sd)) throw std::runtime_error("GMG::lmgc: Base solver failed.");
+	if (l >= topLev) bk.matmul_minus(*ld.A, *ld.sd, *ld.sc); // :2075-2078
+}
+
+} // namespace oracle
