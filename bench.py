@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py — 3-D Poisson GMG-CG solve on B200 (BASELINE.json metric).
+
+A "step" is one full solve (solver:apply) of the synthetic FV1 Poisson problem:
+GMG V(2,2) damped Jacobi (0.66) preconditioning CG, StdConvCheck(100, 1e-12, 1e-10).
+  N = 1 : configs[1], unit cube, numRefs = 7, 129^3 = 2 146 689 DoF.
+  N > 1 : weak scaling, one 129^3 sub-box per GPU (2x1x1, 2x2x1, 2x2x2 boxes; N = 8 is
+          configs[2]: 257^3 = 16 974 593 DoF), interface exchange + all-reduce over NCCL.
+Prints ONE JSON line (see the contract in the task description / DESIGN.md §Measurement).
+
+`--impl reference` times ugcore's own CPU kernels (oracle/_ref: SparseMatrix/Vector/
+smoother templates compiled from the reference) driving the restated solver loop on the
+host cores — the reference has no threading on this path and no MPI is installed, so
+cores = 1.  This is the only place bench.py executes anything under oracle/.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "poisson3d_gmg_cg_mdof_per_s"
+UNIT = "MDoF/s"
+PART = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+
+
+def solver_desc(top, base=0):
+    return {"type": "cg",
+            "precond": {"type": "gmg", "topLevel": top, "baseLevel": base, "smoother": {"type": "jac", "damp": 0.66},
+                        "cycle": "V", "preSmooth": 2, "postSmooth": 2, "baseSolver": "lu"},
+            "convCheck": {"iterations": 100, "absolute": 1e-12, "reduction": 1e-10}}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        for k in ("hbm_gbs", "hbm_gb_s", "hbm_copy_gbs"):
+            if k in d:
+                return float(d[k]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args):
+    """CPU arm: ugcore's own kernels (oracle/_ref) or the port, one core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    from ugcore_b200 import problems as pr
+    kind = "ref" if oracle.have_ref() else "port"
+    orc = oracle.Oracle(kind)
+    refs = args.cpu_refs
+    prob = pr.Problem(dim=3, num_refs=refs)
+    desc = solver_desc(refs)
+    lv = {}
+    for l in range(0, refs + 1):
+        lv[l] = (orc.matrix(prob.matrix(l)), orc.matrix(prob.prolongation(l)) if l else None,
+                 orc.matrix(prob.restriction(l)) if l else None)
+    s = oracle.OSolver(orc, desc, lv[refs][0], lv)
+    b = np.array(prob.rhs())
+    n = prob.num_dofs
+    for _ in range(args.warmup):
+        s.apply(b)
+    t0 = time.perf_counter()
+    its = 0
+    for _ in range(args.steps):
+        x, ok, h = s.apply(b)
+        its = len(h) - 1
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    val = n / dt / 1e6
+    sample = f"{args.steps} full solves of 3-D Poisson {2**refs + 1}^3 ({n} DoF), {its} CG iterations each"
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"3D Poisson unit cube hexahedra numRefs={refs} ({n} DoF) GMG V(2,2) damped-Jacobi + CG, "
+                                  "ugcore CPU kernels, serial", "iterations": its},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "reference" if kind == "ref" else "port",
+                            "sample": sample},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def kernel_roofline(s, prob, top, peak_gbs, peak_src):
+    """Dominant kernel = the top-level fused smoothing step (4 of the 5 top-level matrix
+    sweeps per CG iteration); timed alone with CUDA events on the launching stream, inputs
+    (~0.75 GB) far larger than L2 so every launch streams from HBM."""
+    import ctypes as C
+    from ugcore_b200 import capi
+    from ugcore_b200.solver import host_ctx, DeviceBuffer
+    dev = capi.dev
+    ctx = host_ctx()
+    A = prob.matrix(top)
+    n, nnz = A.nrows, A.nnz
+    m = C.c_void_p()
+    capi.check(dev.ug4b200_matrix_upload_crs(ctx, 1, n, n, A.rowptr.ctypes.data_as(C.c_void_p), A.cols.ctypes.data_as(C.c_void_p),
+                                             A.vals.ctypes.data_as(C.c_void_p), 0, C.byref(m)), ctx)
+    rng = np.random.default_rng(0)
+    sd, st, st2, sc, dinv = (DeviceBuffer.from_numpy(rng.standard_normal(n)) for _ in range(5))
+    capi.check(dev.ug4b200_jacobi_prepare(ctx, m, 0.66, 1, dinv.ptr), ctx)
+    e0, e1 = C.c_void_p(), C.c_void_p()
+    dev.ug4b200_event_create(ctx, C.byref(e0)); dev.ug4b200_event_create(ctx, C.byref(e1))
+
+    def timeit(fn, reps=20):
+        for _ in range(3):
+            fn()
+        dev.ug4b200_sync(ctx)
+        dev.ug4b200_event_record(ctx, e0)
+        for _ in range(reps):
+            fn()
+        dev.ug4b200_event_record(ctx, e1)
+        dev.ug4b200_event_sync(ctx, e1)
+        ms = C.c_float()
+        dev.ug4b200_event_elapsed_ms(ctx, e0, e1, C.byref(ms))
+        return ms.value / reps
+
+    flags = capi.SMOOTH_ADD_IN | capi.SMOOTH_JACOBI
+    t_fused = timeit(lambda: dev.ug4b200_jacobi_smooth_fused(ctx, m, dinv.ptr, sd.ptr, st.ptr, st2.ptr, sc.ptr, flags))
+    t_spmv = timeit(lambda: dev.ug4b200_matrix_matmul_minus(ctx, m, sd.ptr, st.ptr, 1))
+    t_apply = timeit(lambda: dev.ug4b200_matrix_apply(ctx, m, sd.ptr, st.ptr, 1))
+    dev.ug4b200_event_destroy(ctx, e0); dev.ug4b200_event_destroy(ctx, e1)
+    dev.ug4b200_matrix_destroy(ctx, m)
+    # algorithmic (compulsory) bytes, SURVEY.md §8d / DESIGN.md §Kernels
+    b_apply = 12 * nnz + 4 * (n + 1) + 8 * n + 8 * n
+    b_minus = b_apply + 8 * n
+    b_fused = 12 * nnz + 4 * (n + 1) + 64 * n   # + st_in, sd r/w, dinv, st_out, sc r/w
+    b_unfused_seq = b_minus + 24 * n + 24 * n   # y -= Ax ; c = Dinv d ; sc += c as separate sweeps
+    gbs = lambda b, ms: b / (ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "spmv1_kernel<-1,INPLACE,FUSE_JACOBI> (ug4b200_jacobi_smooth_fused)",
+            "achieved": gbs(b_fused, t_fused), "peak": peak_gbs, "unit": "GB/s", "frac": gbs(b_fused, t_fused) / peak_gbs,
+            "peak_source": peak_src, "traffic": None, "bytes_per_launch": b_fused, "ms_per_launch": t_fused,
+            "vs_unfused_bytes_gbs": gbs(b_unfused_seq, t_fused)}
+    extra = {"spmv_matmul_minus": {"achieved": gbs(b_minus, t_spmv), "frac": gbs(b_minus, t_spmv) / peak_gbs,
+                                   "bytes_per_launch": b_minus, "ms_per_launch": t_spmv},
+             "spmv_apply": {"achieved": gbs(b_apply, t_apply), "frac": gbs(b_apply, t_apply) / peak_gbs,
+                            "bytes_per_launch": b_apply, "ms_per_launch": t_apply}}
+    return roof, extra
+
+
+def cpu_baseline_sample(refs):
+    """Bounded CPU sample for the default run: one full solve of the SAME workload with the
+    reference's kernels on one host core (~10-30 s)."""
+    import oracle
+    from ugcore_b200 import problems as pr
+    kind = "ref" if oracle.have_ref() else "port"
+    orc = oracle.Oracle(kind)
+    prob = pr.Problem(dim=3, num_refs=refs)
+    lv = {}
+    for l in range(0, refs + 1):
+        lv[l] = (orc.matrix(prob.matrix(l)), orc.matrix(prob.prolongation(l)) if l else None,
+                 orc.matrix(prob.restriction(l)) if l else None)
+    s = oracle.OSolver(orc, solver_desc(refs), lv[refs][0], lv)
+    b = np.array(prob.rhs())
+    t0 = time.perf_counter()
+    x, ok, h = s.apply(b)
+    dt = time.perf_counter() - t0
+    return {"value": prob.num_dofs / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "reference" if kind == "ref" else "port",
+            "sample": f"1 full solve of the same workload ({prob.num_dofs} DoF, {len(h) - 1} CG iterations, {dt:.1f} s), "
+                      "ugcore SparseMatrix/Vector kernels compiled from the reference, serial (no threading on this path)",
+            "solve_s": dt, "history_last": float(h[-1])}, h
+
+
+def run_ours(args):
+    import ctypes as C
+    import torch
+    from ugcore_b200 import capi, problems as pr
+    from ugcore_b200 import solver as S
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local_rank)
+    stream = torch.cuda.current_stream()
+    S.host_init(local_rank, C.c_void_p(stream.cuda_stream))
+    ctx = S.host_ctx()
+    dev = capi.dev
+    refs = args.refs
+    desc = solver_desc(refs)
+
+    if world > 1:
+        import torch.distributed as dist
+        from ugcore_b200 import dist as ugdist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        part = PART[world]
+        prob, s = ugdist.build_partitioned_solver(desc, refs, part, rank, dist)
+        barrier = lambda: (dist.barrier(), torch.cuda.synchronize())
+    else:
+        part = (1, 1, 1)
+        prob = pr.Problem(dim=3, num_refs=refs)
+        s = S.Solver.from_problem(desc, prob)
+        barrier = lambda: torch.cuda.synchronize()
+    s.init()
+    n_local = prob.num_dofs
+    dims = [part[d] * 2 ** refs + 1 for d in range(3)]
+    n_global = dims[0] * dims[1] * dims[2]
+
+    b_host = torch.from_numpy(np.array(prob.rhs())).pin_memory()
+    x_host = torch.zeros(n_local, dtype=torch.float64).pin_memory()
+    b_dev = b_host.cuda()
+    x_dev = torch.zeros(n_local, dtype=torch.float64, device="cuda")
+
+    def solve_device():
+        x_dev.zero_()
+        ok = s.apply_device(x_dev.data_ptr(), b_dev.data_ptr())
+        assert ok, "solver did not converge"
+
+    def solve_e2e():
+        x_host.zero_()
+        ok = s.apply_pinned(x_host.data_ptr(), b_host.data_ptr())
+        assert ok, "solver did not converge"
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        l0 = s.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        wall = (time.perf_counter() - w0) * 1e3 / steps
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, wall, (s.launch_count() - l0) // steps
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms, wall_ms, launches = timed(solve_device, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    its = s.steps
+    hist = s.history()
+    ms_e2e, wall_e2e, _ = timed(solve_e2e, args.steps, args.warmup)
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak_gbs()
+    out = {"metric": METRIC, "value": n_global / (ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"3D Poisson unit-cell hexahedra numRefs={refs}, {dims[0]}x{dims[1]}x{dims[2]} = {n_global} DoF "
+                                  f"({n_local} per GPU, boxes {part[0]}x{part[1]}x{part[2]}), GMG V(2,2) damped-Jacobi(0.66) + CG, "
+                                  "StdConvCheck(100, 1e-12, 1e-10), base LU on level 0",
+                      "iterations": its, "solve_s": ms * 1e-3, "l2_policy": "inputs larger than L2 (top-level matrix 0.69 GB per GPU)",
+                      "wall_ms_per_step": wall_ms, "final_reduction": float(hist[-1] / hist[0]) if len(hist) else None},
+           "e2e": {"value": n_global / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 16 * n_local,
+                   "d2h_bytes_per_step": 8 * n_local, "ms_per_step": ms_e2e, "wall_ms_per_step": wall_e2e},
+           "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": int(launches), "clocks": clocks}
+    if world == 1:
+        roof, extra = kernel_roofline(s, prob, refs, peak, peak_src)
+        out["roofline"] = roof
+        out["roofline_other_kernels"] = extra
+        # whole-solve figure against the unfused reference sequence (~2.9 kB per fine DoF per iteration)
+        out["solve_algorithmic_gbs_vs_unfused"] = 2.9e3 * n_global * max(its, 1) / (ms * 1e-3) / 1e9
+        if not args.no_cpu_baseline:
+            cb, h_cpu = cpu_baseline_sample(refs)
+            out["cpu_baseline"] = cb
+            k = min(len(h_cpu), len(hist))
+            out["config"]["history_rel_err_vs_cpu"] = float(np.max(np.abs(hist[:k] - h_cpu[:k]) / np.abs(h_cpu[:k])))
+            out["config"]["iterations_cpu"] = len(h_cpu) - 1
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--refs", type=int, default=7, help="refinements per GPU sub-box (7 -> 129^3)")
+    ap.add_argument("--cpu-refs", type=int, default=7, help="workload of the CPU reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,298 @@
+/*
+ * ug4b200.h — C ABI of the B200-native algebra kernels for ugcore's assembled-matrix
+ * linear-solve path (GMG V-cycle preconditioning CG / BiCGStab on CRS matrices).
+ *
+ * This is the drop-in boundary: the functions a ugcore "GPU" algebra
+ * (GPUAlgebra / GPUBlockAlgebra<3>, registered next to CPUAlgebra in
+ * ugbase/bridge/util_algebra_dependent.h:63-100) binds instead of the legacy
+ *   extern "C" bool CUDA_VecAdd2 / CUDA_VecAdd3 / CUDA_JacobiApply(...)
+ *       ugbase/lib_algebra/gpu_algebra/cuda/common_cuda.h:38-51
+ *   cusparseDcsrmv / cublasDdot / cublasDnrm2 call sites
+ *       ugbase/lib_algebra/gpu_algebra/gpusparsematrix_impl.h:157-164
+ *       ugbase/lib_algebra/gpu_algebra/gpuvector.h:200-214, 297-303
+ *   CUDAManager (device selection, handles, H2D/D2H helpers)
+ *       ugbase/lib_algebra/gpu_algebra/cuda/cuda_manager.h:79-180
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; every function returns 0 on success or a
+ *     UG4B200_ERR_* code and never throws; ug4b200_last_error() gives the text.
+ *     (Legacy wrappers returned `bool true` and relied on CUDA_CHECK_STATUS ->
+ *     UG_THROW in the caller, cuda_manager.h:61-77; the C++ wrapper layer turns a
+ *     non-zero code into UG_THROW the same way.)
+ *   - vectors are raw DEVICE pointers to fp64, `n` counts doubles (block vectors:
+ *     n = blocks * block size, block entries contiguous like Vector<DenseVector<..>>).
+ *   - all work is stream-ordered on the context's stream; nothing blocks the host
+ *     unless the function returns a value to a HOST pointer.
+ *   - arithmetic is IEEE fp64 without FMA contraction, summed in ugcore's order
+ *     (ascending column index inside a row), so SpMV / Jacobi / AXPY results are
+ *     bit-identical to the CPU algebra; only reductions differ (tree vs sequential).
+ *   - no CPU fallback: if no CUDA device is usable, ctx_create fails.
+ */
+#ifndef UG4B200_H
+#define UG4B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UG4B200_VERSION 100
+
+enum {
+	UG4B200_OK = 0,
+	UG4B200_ERR_CUDA = 1,      /* a CUDA runtime call failed */
+	UG4B200_ERR_ARG = 2,       /* invalid argument */
+	UG4B200_ERR_NOMEM = 3,
+	UG4B200_ERR_NCCL = 4,
+	UG4B200_ERR_STATE = 5      /* call not valid in the current state */
+};
+
+typedef struct ug4b200_ctx ug4b200_ctx;
+typedef struct ug4b200_matrix ug4b200_matrix;
+typedef struct ug4b200_interface ug4b200_interface;
+
+/* ------------------------------------------------------------------ context */
+
+/* device: CUDA ordinal (one process/rank per device; replaces CUDAManager::init's
+ * "most SMs" pick, cuda_manager.cpp:54-68).  stream: a cudaStream_t created by the
+ * caller (e.g. torch's current stream) or NULL to let the context own one. */
+int ug4b200_ctx_create(int device, void* stream, ug4b200_ctx** out);
+int ug4b200_ctx_destroy(ug4b200_ctx* ctx);
+const char* ug4b200_last_error(const ug4b200_ctx* ctx); /* ctx may be NULL: last global error */
+int ug4b200_sync(ug4b200_ctx* ctx);
+void* ug4b200_stream(ug4b200_ctx* ctx);
+/* number of kernels this context launched so far */
+int ug4b200_launch_count(const ug4b200_ctx* ctx, int64_t* n);
+/* while set, every subsequent kernel of this context returns immediately when
+ * *flag != 0 (device int).  NULL clears.  Used to make queued-ahead Krylov
+ * iterations no-ops once the device-side convergence check has fired. */
+int ug4b200_set_guard(ug4b200_ctx* ctx, const int* dev_flag);
+
+/* CUDA-graph capture of a stream-ordered call sequence (e.g. one Krylov iteration whose
+ * scalars all live on the device): begin, issue calls, end -> replay with launch. */
+typedef struct ug4b200_graph ug4b200_graph;
+int ug4b200_graph_begin(ug4b200_ctx* ctx);
+int ug4b200_graph_end(ug4b200_ctx* ctx, ug4b200_graph** out);
+int ug4b200_graph_launch(ug4b200_ctx* ctx, ug4b200_graph* g);
+int ug4b200_graph_destroy(ug4b200_ctx* ctx, ug4b200_graph* g);
+
+/* events on the context's stream (device-side timing, lagged convergence polling) */
+int ug4b200_event_create(ug4b200_ctx* ctx, void** ev);
+int ug4b200_event_record(ug4b200_ctx* ctx, void* ev);
+int ug4b200_event_sync(ug4b200_ctx* ctx, void* ev);
+int ug4b200_event_elapsed_ms(ug4b200_ctx* ctx, void* ev_start, void* ev_stop, float* ms);
+int ug4b200_event_destroy(ug4b200_ctx* ctx, void* ev);
+
+/* ------------------------------------------------------------------- memory */
+
+int ug4b200_alloc(ug4b200_ctx* ctx, size_t bytes, void** dptr);
+int ug4b200_free(ug4b200_ctx* ctx, void* dptr);
+int ug4b200_h2d(ug4b200_ctx* ctx, void* dst, const void* src, size_t bytes);   /* async if src is pinned */
+int ug4b200_d2h(ug4b200_ctx* ctx, void* dst, const void* src, size_t bytes);   /* returns after completion */
+int ug4b200_d2h_async(ug4b200_ctx* ctx, void* dst_pinned, const void* src, size_t bytes);
+int ug4b200_d2d(ug4b200_ctx* ctx, void* dst, const void* src, size_t bytes);
+int ug4b200_memset(ug4b200_ctx* ctx, void* dst, int byte, size_t bytes);
+int ug4b200_host_alloc(ug4b200_ctx* ctx, size_t bytes, void** hptr);           /* pinned */
+int ug4b200_host_free(ug4b200_ctx* ctx, void* hptr);
+
+/* ------------------------------------------------------------------ vectors
+ * Vector<T> arithmetic, ugbase/lib_algebra/cpu_algebra/vector.h:124-176 and
+ * ugbase/lib_algebra/common/operations_vec.h:49-175. */
+
+int ug4b200_vec_set(ug4b200_ctx* ctx, int64_t n, double* x, double value);            /* x = value */
+int ug4b200_vec_copy(ug4b200_ctx* ctx, int64_t n, double* dst, const double* src);    /* dst = src */
+int ug4b200_vec_scale(ug4b200_ctx* ctx, int64_t n, double* x, double alpha);          /* x *= alpha */
+int ug4b200_vec_add(ug4b200_ctx* ctx, int64_t n, double* dst, const double* src);     /* dst += src */
+int ug4b200_vec_sub(ug4b200_ctx* ctx, int64_t n, double* dst, const double* src);     /* dst -= src */
+/* VecScaleAdd: dest = a1*v1 + a2*v2 (+ a3*v3), evaluated left to right; dest may alias */
+int ug4b200_vec_scale_add2(ug4b200_ctx* ctx, int64_t n, double* dest, double a1, const double* v1,
+                           double a2, const double* v2);
+int ug4b200_vec_scale_add3(ug4b200_ctx* ctx, int64_t n, double* dest, double a1, const double* v1,
+                           double a2, const double* v2, double a3, const double* v3);
+/* Vector::dotprod / Vector::norm (vector_impl.h:72-79, 323-329); host result, blocks on the stream */
+int ug4b200_vec_dot(ug4b200_ctx* ctx, int64_t n, const double* a, const double* b, double* host_out);
+int ug4b200_vec_norm(ug4b200_ctx* ctx, int64_t n, const double* a, double* host_out);
+/* dst[i] = src[idx[i]]  /  dst[idx[i]] += src[i]  (surface<->level copies,
+ * mg_solver_impl.hpp:211-217, 244-248); block = doubles per index */
+int ug4b200_vec_gather(ug4b200_ctx* ctx, int64_t nidx, int block, double* dst, const double* src, const int* idx);
+int ug4b200_vec_scatter(ug4b200_ctx* ctx, int64_t nidx, int block, double* dst, const int* idx, const double* src);
+int ug4b200_vec_scatter_add(ug4b200_ctx* ctx, int64_t nidx, int block, double* dst, const int* idx, const double* src);
+
+/* ---- device-resident scalars (Krylov loops without host round trips) ----
+ * A coefficient is sign * (*dev) when dev != NULL, else the host value. */
+typedef struct ug4b200_coef {
+	const double* dev;  /* device pointer or NULL */
+	double host;        /* value when dev == NULL; multiplier (+1/-1) when dev != NULL */
+} ug4b200_coef;
+
+int ug4b200_vec_scale_add2_ds(ug4b200_ctx* ctx, int64_t n, double* dest, ug4b200_coef a1, const double* v1,
+                              ug4b200_coef a2, const double* v2);
+int ug4b200_vec_scale_add3_ds(ug4b200_ctx* ctx, int64_t n, double* dest, ug4b200_coef a1, const double* v1,
+                              ug4b200_coef a2, const double* v2, ug4b200_coef a3, const double* v3);
+
+/* Device mirror of StdConvCheck (convergence_check_impl.h:85-169). */
+typedef struct ug4b200_conv_state {
+	double initial_defect, current_defect, last_defect;
+	double min_defect, rel_reduction;
+	int step, max_steps;
+	int done;        /* iteration_ended() */
+	int status;      /* 0 running, 1 converged, 2 max steps, 3 invalid number, 4 breakdown */
+	int history_cap;
+	int pad_;
+	double* history; /* device array, history[k] = defect after k updates */
+} ug4b200_conv_state;
+
+/* What the last block of a device reduction does with the result r. */
+enum {
+	UG4B200_FIN_STORE = 0,      /* *out = r */
+	UG4B200_FIN_A_DIV_R = 1,    /* *out = r; *out2 = *a / r  (CG alpha = rhoOld/lambda); r == 0 -> breakdown */
+	UG4B200_FIN_R_DIV_A = 2,    /* *out2 = r / *a; *out = r  (CG beta = rho/rhoOld then rhoOld := rho when out == a) */
+	UG4B200_FIN_SQRT = 3,       /* *out = sqrt(r) */
+	UG4B200_FIN_CONV_START = 4, /* conv->start_defect(sqrt(r)) */
+	UG4B200_FIN_CONV_UPDATE = 5 /* conv->update_defect(sqrt(r)); sets conv->done */
+};
+typedef struct ug4b200_fin {
+	int op;
+	double* out;
+	double* out2;
+	const double* a;
+	ug4b200_conv_state* conv; /* device */
+} ug4b200_fin;
+
+int ug4b200_vec_dot_ds(ug4b200_ctx* ctx, int64_t n, const double* a, const double* b, ug4b200_fin fin);
+/* dest = a1*v1 + a2*v2 and, in the same pass, sum(dest^2) -> fin  (CG: r -= alpha q; ||r||) */
+int ug4b200_vec_scale_add2_norm_ds(ug4b200_ctx* ctx, int64_t n, double* dest, ug4b200_coef a1, const double* v1,
+                                   ug4b200_coef a2, const double* v2, ug4b200_fin fin);
+/* CG inner update in one pass: x += alpha p; r -= alpha q; sum(r^2) -> fin (cg.h:187-198) */
+int ug4b200_cg_update_ds(ug4b200_ctx* ctx, int64_t n, double* x, const double* p, double* r, const double* q,
+                         const double* alpha_dev, ug4b200_fin fin);
+/* generic one-thread scalar program: out = (a/b)*(c/d) with NULL operands = 1 (BiCGStab beta) */
+int ug4b200_scalar_ratio_ds(ug4b200_ctx* ctx, double* out, const double* a, const double* b, const double* c,
+                            const double* d);
+/* apply a finaliser to a value that already sits on the device (after an all-reduce) */
+int ug4b200_scalar_fin_ds(ug4b200_ctx* ctx, const double* r_dev, ug4b200_fin fin);
+int ug4b200_conv_init(ug4b200_ctx* ctx, ug4b200_conv_state* dev_state, int max_steps, double min_defect,
+                      double rel_reduction, double* dev_history, int history_cap);
+
+/* ------------------------------------------------------------------ matrices
+ * SparseMatrix<T> (ugbase/lib_algebra/cpu_algebra/sparsematrix.h:98, 737-747) uploaded
+ * once after assembly.  Input is defragmented CRS (copy_crs, sparsematrix.h:607-617):
+ * rowptr[nrows+1], cols sorted ascending inside a row, vals = block*block doubles per
+ * entry, column-major inside a block.  Device layout is SELL-32 (slice = 32 rows,
+ * entries stored slice-column-major so that a warp reads 32 consecutive values) with
+ * true row lengths kept, explicit zeros preserved.  The handle is immutable. */
+
+enum { UG4B200_MAT_DEFAULT = 0 };
+
+typedef struct ug4b200_matrix_info {
+	int64_t nrows, ncols, nnz, padded_nnz, num_slices, device_bytes;
+	int block;
+	int max_row_len;
+} ug4b200_matrix_info;
+
+int ug4b200_matrix_upload_crs(ug4b200_ctx* ctx, int block, int64_t nrows, int64_t ncols, const int64_t* rowptr,
+                              const int* cols, const double* vals, int flags, ug4b200_matrix** out);
+int ug4b200_matrix_destroy(ug4b200_ctx* ctx, ug4b200_matrix* A);
+int ug4b200_matrix_get_info(const ug4b200_matrix* A, ug4b200_matrix_info* info);
+
+/* SparseMatrix::axpy(dest, alpha, v, beta, w): dest = alpha*v + beta*A*w
+ * (sparsematrix_impl.h:291-339).  alpha == 0: v ignored (may be NULL), empty rows give 0.
+ * vblock = doubles per vector entry; a block-1 matrix with vblock > 1 acts per component
+ * (transfer operators of a block algebra). */
+int ug4b200_matrix_axpy(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* dest, double alpha, const double* v,
+                        double beta, const double* w, int vblock);
+/* y = A x  (SparseMatrix::apply, sparsematrix.h:184-190) */
+int ug4b200_matrix_apply(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* y, const double* x, int vblock);
+/* y -= A x  (SparseMatrix::matmul_minus, sparsematrix.h:199-207) */
+int ug4b200_matrix_matmul_minus(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* y, const double* x, int vblock);
+/* dest = beta*A*w, rows without entries untouched (apply_ignore_zero_rows, sparsematrix_impl.h:271-288) */
+int ug4b200_matrix_apply_ignore_zero_rows(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* dest, double beta,
+                                          const double* w, int vblock);
+/* y = A x fused with the reduction (y, x) -> fin   (CG: q = A p, lambda = (q,p), cg.h:166-169) */
+int ug4b200_matrix_apply_dot_ds(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* y, const double* x,
+                                ug4b200_fin fin);
+
+/* ------------------------------------------------------------------ smoothers */
+
+/* Jacobi::preprocess (jacobi.h:196-220): diaginv[i] = inverse(A_ii * (1./damp));
+ * block_inverse = 0 uses only the diagonal of the block (set_block(false)).
+ * diaginv: device, nrows*block*block doubles (column-major blocks). */
+int ug4b200_jacobi_prepare(ug4b200_ctx* ctx, const ug4b200_matrix* A, double damp, int block_inverse,
+                           double* diaginv);
+/* the two halves of jacobi_prepare, for partitioned runs where the additive diagonal is
+ * summed over the interface copies in between (jacobi.h:171-187) */
+int ug4b200_matrix_get_diag(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* diag);
+int ug4b200_jacobi_invert_diag(ug4b200_ctx* ctx, int64_t nrows, int block, double damp, int block_inverse,
+                               const double* diag, double* diaginv);
+/* Jacobi::step (jacobi.h:222-232): c[i] = diaginv[i] * d[i] */
+int ug4b200_jacobi_step(ug4b200_ctx* ctx, int64_t nblocks, int block, const double* diaginv, double* c,
+                        const double* d);
+/* c = diaginv*d and sc += c in one pass (first pre-smoothing step of a level) */
+int ug4b200_jacobi_step_add(ug4b200_ctx* ctx, int64_t nblocks, int block, const double* diaginv, double* c,
+                            const double* d, double* sc);
+/* One fused smoothing step of the V-cycle (mg_solver_impl.hpp:1919-1943 with Jacobi):
+ *   [sc += st_in]            if flags & UG4B200_SMOOTH_ADD_IN
+ *   sd -= A*st_in
+ *   [st_out = diaginv*sd]    if flags & UG4B200_SMOOTH_JACOBI      (st_out != st_in)
+ *   [sc += st_out]           if flags & UG4B200_SMOOTH_ADD_OUT
+ * Serial V-cycles use JACOBI|ADD_OUT; partitioned ones ADD_IN|JACOBI because st_out must be
+ * made consistent across ranks before it is accumulated. */
+enum { UG4B200_SMOOTH_ADD_IN = 1, UG4B200_SMOOTH_JACOBI = 2, UG4B200_SMOOTH_ADD_OUT = 4 };
+int ug4b200_jacobi_smooth_fused(ug4b200_ctx* ctx, const ug4b200_matrix* A, const double* diaginv, double* sd,
+                                const double* st_in, double* st_out, double* sc, int flags);
+
+/* Multicolour Gauss-Seidel.  The matrix must be given in a colour-sorted DoF order:
+ * rows [color_ptr[k], color_ptr[k+1]) form colour k and have no stored connection to
+ * another row of the same colour.  A lexicographic gs_step_LL / gs_step_UR
+ * (ugbase/lib_algebra/algebra_common/core_smoothers.h:105-169) over such a matrix IS
+ * multicolour GS, so results are bit-identical to the CPU sweeps on the same matrix. */
+int ug4b200_color_greedy(int64_t nrows, const int64_t* rowptr, const int* cols, int* color, int* ncolors); /* host */
+int ug4b200_color_check(int64_t nrows, const int64_t* rowptr, const int* cols, int ncolors,
+                        const int64_t* color_ptr); /* host; 0 if the order is a valid colouring */
+/* kind: 0 forward (gs_step_LL), 1 backward (gs_step_UR), 2 symmetric (sgs_step) */
+int ug4b200_gs_step(ug4b200_ctx* ctx, const ug4b200_matrix* A, int ncolors, const int64_t* color_ptr_host,
+                    int kind, double relax, double* c, const double* d);
+
+/* dense LU base solver (lu.h:122-140, 189-207): factors computed on the host by the
+ * caller (row-major n*n LU with unit lower part, pivot interchanges as in SolveLU,
+ * no_lapack/lu_decomp.h:160-195), applied on the device by one CTA. */
+int ug4b200_lu_apply(ug4b200_ctx* ctx, int n, const double* lu_dev, const int* piv_dev, double* x, const double* b);
+/* small on-device CG base solver: one CTA iterates x (start 0) on A x = b until
+ * ||r|| < max(min_defect, rel_reduction*||r0||) or max_steps (north_star: "coarse-grid solve
+ * done as a small on-device CG") */
+int ug4b200_coarse_cg(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* x, const double* b, double* work4n,
+                      int max_steps, double min_defect, double rel_reduction);
+
+/* ------------------------------------------------------------------ multi-GPU
+ * pcl::InterfaceCommunicator + ProcessCommunicator semantics over NCCL
+ * (ugbase/pcl/pcl_interface_communicator_impl.hpp:408-739,
+ *  ugbase/pcl/pcl_process_communicator.cpp:311-326). */
+
+#define UG4B200_NCCL_ID_BYTES 128
+int ug4b200_comm_unique_id(unsigned char id[UG4B200_NCCL_ID_BYTES]);
+int ug4b200_comm_init(ug4b200_ctx* ctx, int nranks, int rank, const unsigned char id[UG4B200_NCCL_ID_BYTES]);
+int ug4b200_comm_destroy(ug4b200_ctx* ctx);
+/* in-place sum over ranks of n device doubles (ParallelVector::dotprod/norm allreduce,
+ * parallel_vector_impl.h:269-379) */
+int ug4b200_allreduce_sum(ug4b200_ctx* ctx, double* dev, int n);
+/* Horizontal interface: for every neighbour rank p the list of local block indices shared
+ * with p, in an order both sides agree on (IndexLayout, parallel_index_layout.h:52-53).
+ * owner[i] = 1 if this rank is the h-master (lowest rank) of interface index list entry. */
+int ug4b200_interface_create(ug4b200_ctx* ctx, int nneigh, const int* neigh_rank, const int64_t* neigh_ptr,
+                             const int* indices, int64_t nlocal, ug4b200_interface** out);
+int ug4b200_interface_destroy(ug4b200_ctx* ctx, ug4b200_interface* I);
+/* AdditiveToConsistent (parallelization_util.h:159-191): every copy of an interface
+ * DoF ends up with the sum over all copies, summed in ascending rank order on every
+ * rank (bitwise identical copies). */
+int ug4b200_additive_to_consistent(ug4b200_ctx* ctx, ug4b200_interface* I, double* v, int block);
+/* zero every copy that is not the h-master (AdditiveToUnique after a consistent sum /
+ * ConsistentToUnique, parallelization_util.h:260-280, 387-393) */
+int ug4b200_set_slaves_zero(ug4b200_ctx* ctx, ug4b200_interface* I, double* v, int block);
+/* sum over h-master/inner entries of a[i]*b[i] (unique dot of consistent vectors) */
+int ug4b200_vec_dot_unique_ds(ug4b200_ctx* ctx, ug4b200_interface* I, int64_t n, int block, const double* a,
+                              const double* b, double* out_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UG4B200_H */

@@ -1,0 +1,98 @@
+/*
+ * ug4b200_solver.h — descriptor-level C ABI on top of the host-side mirror of ugcore's
+ * operator API (ugcore_b200/csrc/host/: GPUVector, GPUSparseMatrix, CG, BiCGStab,
+ * LinearSolver, Jacobi, GaussSeidel*, LU, StdTransfer, AssembledMultiGridCycle).
+ *
+ * It plays the role of scripts/util/solver_util.lua (util.solver.CreateSolver, :602;
+ * SolveLinearProblem, :1182-1210) for callers that are not Lua: build the solver objects
+ * from a descriptor, hand over the assembled level matrices, then solver:init(A,u) and
+ * solver:apply(u,b) (bound in ugbase/bridge/algebra_bridges/common_bridge.cpp:326-338).
+ * Used by the Python package, the tests and bench.py.  Everything here runs on the GPU;
+ * there is no CPU fallback.
+ */
+#ifndef UG4B200_SOLVER_H
+#define UG4B200_SOLVER_H
+#include "ug4b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { UG4B200_SOLVER_CG = 0, UG4B200_SOLVER_BICGSTAB = 1, UG4B200_SOLVER_LINEAR = 2, UG4B200_SOLVER_LU = 3,
+       UG4B200_SOLVER_COARSE_CG = 4 };
+enum { UG4B200_PRECOND_NONE = 0, UG4B200_PRECOND_JACOBI = 1, UG4B200_PRECOND_GS = 2, UG4B200_PRECOND_BGS = 3,
+       UG4B200_PRECOND_SGS = 4, UG4B200_PRECOND_GMG = 5 };
+enum { UG4B200_FLAG_HOST_SCALARS = 1,   /* CG with host scalars (reference-shaped loop, one sync per dot) */
+       UG4B200_FLAG_NO_GRAPH = 2,       /* do not capture the Krylov iteration into a CUDA graph */
+       UG4B200_FLAG_NO_FUSED_JACOBI = 4,/* V-cycle with separate Jacobi / SpMV / AXPY launches */
+       UG4B200_FLAG_FINAL_LEVEL_DEFECT = 8 /* also do the reference's unused top-level defect update */ };
+
+typedef struct ug4b200_solver_desc {
+	int block;             /* 1 = GPUAlgebra, 2/3 = GPUBlockAlgebra<N> */
+	int solver;            /* UG4B200_SOLVER_* */
+	int precond;           /* UG4B200_PRECOND_* */
+	double damp;           /* Jacobi damping / GS relaxation when used directly as preconditioner */
+	int max_steps;         /* StdConvCheck(maxSteps, minDefect, relReduction) */
+	double min_defect;
+	double rel_reduction;
+	/* GeometricMultiGrid (solver_util.lua:466-483) */
+	int base_lev, top_lev;
+	int cycle;             /* 1 V, 2 W, -1 F */
+	int nu1, nu2;
+	int smoother;          /* UG4B200_PRECOND_JACOBI / GS / BGS / SGS */
+	double smoother_damp;
+	int base_solver;       /* UG4B200_SOLVER_LU or UG4B200_SOLVER_COARSE_CG */
+	int base_max_steps;
+	double base_min_defect, base_rel_reduction;
+	int flags;             /* UG4B200_FLAG_* */
+} ug4b200_solver_desc;
+
+typedef struct ug4b200_solver ug4b200_solver;
+
+/* process-wide device context of the host layer (GPUManager); device < 0: LOCAL_RANK */
+int ug4b200_host_init(int device, void* stream);
+int ug4b200_host_finalize(void);
+ug4b200_ctx* ug4b200_host_ctx(void);
+const char* ug4b200_host_last_error(void);
+/* partitioned runs: NCCL communicator of the host layer's context */
+int ug4b200_host_comm_init(int nranks, int rank, const unsigned char id[UG4B200_NCCL_ID_BYTES]);
+
+int ug4b200_solver_create(const ug4b200_solver_desc* d, ug4b200_solver** out);
+int ug4b200_solver_destroy(ug4b200_solver* s);
+/* the assembled surface matrix A (AssembledLinearOperator); host CRS, copied */
+int ug4b200_solver_set_matrix(ug4b200_solver* s, int64_t nrows, int64_t ncols, const int64_t* rowptr, const int* cols,
+                              const double* vals);
+/* GMG level lev: assembled level matrix and the transfers P (lev-1 -> lev), R (lev -> lev-1);
+ * P/R are scalar CRS and NULL on the base level; the top level may reuse the surface matrix
+ * (pass rowptr == NULL). */
+int ug4b200_solver_set_level(ug4b200_solver* s, int lev, int64_t nrows, const int64_t* rowptr, const int* cols,
+                             const double* vals, int64_t ncoarse, const int64_t* p_rowptr, const int* p_cols,
+                             const double* p_vals, const int64_t* r_rowptr, const int* r_cols, const double* r_vals);
+/* colour-sorted DoF order for the Gauss-Seidel smoother of level lev (lev = -1: the direct
+ * preconditioner): perm maps old -> new index, colours are [color_ptr[k], color_ptr[k+1]) */
+int ug4b200_solver_set_coloring(ug4b200_solver* s, int lev, int64_t n, const int* perm, int ncolors,
+                                const int64_t* color_ptr);
+/* horizontal interfaces of level lev (lev = top level also serves the Krylov vectors) */
+int ug4b200_solver_set_layouts(ug4b200_solver* s, int lev, int nneigh, const int* neigh_rank, const int64_t* neigh_ptr,
+                               const int* indices, int64_t nlocal);
+/* gathered base solve: global base-level matrix and the local -> global index map */
+int ug4b200_solver_set_gathered_base(ug4b200_solver* s, int64_t nrows, const int64_t* rowptr, const int* cols,
+                                     const double* vals, int64_t nlocal, const int* local_to_global);
+/* solver:init(A, u): uploads, smoother preprocess, base factorisation */
+int ug4b200_solver_init(ug4b200_solver* s);
+/* solver:apply(u, b) with HOST vectors: H2D of x and b, solve, D2H of x.
+ * Returns 0 converged, 1 not converged / breakdown, < 0 error. */
+int ug4b200_solver_apply(ug4b200_solver* s, double* x_host, const double* b_host);
+/* same with DEVICE vectors (n = block * rows doubles) */
+int ug4b200_solver_apply_device(ug4b200_solver* s, double* x_dev, const double* b_dev);
+int ug4b200_solver_steps(const ug4b200_solver* s);
+double ug4b200_solver_defect(const ug4b200_solver* s);
+/* defect history, entry 0 = start defect; returns the number of entries copied */
+int ug4b200_solver_history(const ug4b200_solver* s, double* out, int cap);
+/* c = M^-1 d with the configured preconditioner alone (host vectors) */
+int ug4b200_solver_precond_apply(ug4b200_solver* s, double* c_host, const double* d_host);
+int64_t ug4b200_solver_num_dofs(const ug4b200_solver* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,73 @@
+"""In-tree build of the native libraries (no JIT cache: the .so files travel with gpurun).
+
+  lib/libug4b200.so       CUDA kernels + C ABI (include/ug4b200.h), nvcc sm_100a
+  lib/libug4b200_host.so  host-side mirror of ugcore's operator API + descriptor C ABI
+                          (include/ug4b200_solver.h), g++ linked against libug4b200.so
+  lib/libug4synth.so      synthetic problem generator (host, OpenMP)
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(ROOT, "csrc")
+LIB = os.path.join(ROOT, "lib")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+CUDA_SOURCES = ["ctx.cu", "comm.cu", "kernels/blas1.cu", "kernels/spmv.cu", "kernels/smoothers.cu"]
+# -fmad=false: no FMA contraction, so SpMV / Jacobi / AXPY are bit-identical to ugcore's CPU
+# algebra (reference release flags have no -march / -ffast-math, cmake/ug/debug.cmake:76-88)
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
+              "-Xcompiler", "-fPIC,-fopenmp,-O2", "-shared"]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _run(cmd, verbose):
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout[-6000:] + r.stderr[-6000:])
+        raise RuntimeError("build failed: " + " ".join(cmd[:3]) + " ...")
+    if verbose and (r.stdout or r.stderr):
+        print(r.stdout[-3000:], r.stderr[-3000:])
+
+
+def _all_files(d, exts):
+    out = []
+    for base, _, files in os.walk(d):
+        out += [os.path.join(base, f) for f in files if f.endswith(exts)]
+    return out
+
+
+def build(force: bool = False, verbose: bool = False) -> None:
+    os.makedirs(LIB, exist_ok=True)
+    headers = _all_files(CSRC, (".h", ".cuh")) + _all_files(os.path.join(ROOT, "..", "include"), (".h",))
+
+    synth = os.path.join(LIB, "libug4synth.so")
+    ssrc = [os.path.join(CSRC, "synth", "synth.cpp")]
+    if force or _newer(synth, ssrc + headers):
+        _run(["g++", "-O2", "-fopenmp", "-fPIC", "-shared", "-std=c++17", "-w", *ssrc, "-o", synth], verbose)
+
+    dev = os.path.join(LIB, "libug4b200.so")
+    dsrc = [os.path.join(CSRC, s) for s in CUDA_SOURCES]
+    if force or _newer(dev, dsrc + headers):
+        _run([NVCC, *NVCC_FLAGS, *dsrc, "-o", dev, "-ldl", "-lgomp"], verbose)
+
+    host = os.path.join(LIB, "libug4b200_host.so")
+    hsrc = [os.path.join(CSRC, "solver_capi.cpp")]
+    if force or _newer(host, hsrc + headers + [dev]):
+        _run(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-Wall", *hsrc, "-o", host,
+              "-L" + LIB, "-lug4b200", "-Wl,-rpath,$ORIGIN"], verbose)
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)

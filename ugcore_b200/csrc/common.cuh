@@ -1,0 +1,186 @@
+// common.cuh — context, error handling and launch helpers shared by the kernel TUs.
+#pragma once
+#include "../../include/ug4b200.h"
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+struct ug4b200_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	bool own_stream = false;
+	const int* guard = nullptr;   // device flag: kernels return early when *guard != 0
+	int64_t launches = 0;
+	bool capturing = false;
+	int64_t capture_start = 0;
+	std::string err;
+	int num_sms = 148;
+	// reduction workspace (stream-ordered reuse)
+	double* partials = nullptr;   // [kMaxReduceBlocks]
+	unsigned int* counter = nullptr;
+	double* dev_scalar = nullptr; // scratch result slot for host-returning reductions
+	double* host_scalar = nullptr; // pinned
+	// NCCL (comm.cu)
+	void* nccl = nullptr;         // ncclComm_t
+	int nranks = 1, rank = 0;
+};
+
+constexpr int kMaxReduceBlocks = 148 * 8;
+constexpr int kReduceThreads = 256;
+
+extern thread_local std::string g_ug4b200_err;
+
+inline int ug4b200_fail(ug4b200_ctx* ctx, int code, const std::string& msg)
+{
+	g_ug4b200_err = msg;
+	if (ctx) ctx->err = msg;
+	return code;
+}
+
+#define UG_CUDA(ctx, call)                                                                        \
+	do {                                                                                          \
+		cudaError_t e_ = (call);                                                                  \
+		if (e_ != cudaSuccess)                                                                    \
+			return ug4b200_fail(ctx, UG4B200_ERR_CUDA,                                            \
+			                    std::string(#call) + ": " + cudaGetErrorString(e_));              \
+	} while (0)
+
+#define UG_ARG(ctx, cond, msg)                                                                    \
+	do { if (!(cond)) return ug4b200_fail(ctx, UG4B200_ERR_ARG, std::string(__func__) + ": " + msg); } while (0)
+
+// every kernel launch goes through this so launches are counted and checked
+#define UG_LAUNCH(ctx, kernel, grid, block, smem, ...)                                            \
+	do {                                                                                          \
+		kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                          \
+		(ctx)->launches++;                                                                        \
+		cudaError_t e_ = cudaGetLastError();                                                      \
+		if (e_ != cudaSuccess)                                                                    \
+			return ug4b200_fail(ctx, UG4B200_ERR_CUDA, std::string(#kernel) + ": " + cudaGetErrorString(e_)); \
+	} while (0)
+
+__device__ __forceinline__ bool ug_guarded(const int* guard) { return guard != nullptr && *guard != 0; }
+
+__device__ __forceinline__ double ug_coef(const ug4b200_coef& c) { return c.dev ? c.host * (*c.dev) : c.host; }
+
+// ---- device-side StdConvCheck (convergence_check_impl.h:139-169, 246-257) ----
+__device__ __forceinline__ bool ug_valid_number(double v)
+{
+	if (v == 0.0) return true;
+	return v >= 2.2250738585072014e-308 && v <= 1.7976931348623157e308 && v == v && v >= 0.0;
+}
+__device__ inline void ug_conv_check(ug4b200_conv_state* c)
+{
+	const double d = c->current_defect;
+	const double red = d / c->initial_defect;
+	int done = 0, status = 0;
+	if (!ug_valid_number(d)) { done = 1; status = 3; }
+	else if (c->step >= c->max_steps) { done = 1; status = 2; }
+	else if (d < c->min_defect) { done = 1; }
+	else if (red < c->rel_reduction) { done = 1; }
+	if (done && status != 3) {
+		// post(): success iff one of the two criteria holds
+		if (d < c->min_defect || red < c->rel_reduction) status = 1;
+		else status = 2;
+	}
+	if (done) { c->status = status; c->done = 1; }
+}
+__device__ inline void ug_apply_fin(double r, const ug4b200_fin& f)
+{
+	switch (f.op) {
+		case UG4B200_FIN_STORE: *f.out = r; break;
+		case UG4B200_FIN_A_DIV_R:
+			if (f.out) *f.out = r;
+			if (r == 0.0 && f.conv) { f.conv->status = 4; f.conv->done = 1; }
+			*f.out2 = *f.a / r;
+			break;
+		case UG4B200_FIN_R_DIV_A: {
+			const double av = *f.a;
+			*f.out2 = r / av;
+			if (f.out) *f.out = r;
+			break;
+		}
+		case UG4B200_FIN_SQRT: *f.out = sqrt(r); break;
+		case UG4B200_FIN_CONV_START: {
+			ug4b200_conv_state* c = f.conv;
+			const double d = sqrt(r);
+			c->initial_defect = d; c->current_defect = d; c->last_defect = 0.0; c->step = 0;
+			c->done = 0; c->status = 0;
+			if (c->history && c->history_cap > 0) c->history[0] = d;
+			if (f.out) *f.out = d;
+			ug_conv_check(c);
+			break;
+		}
+		case UG4B200_FIN_CONV_UPDATE: {
+			ug4b200_conv_state* c = f.conv;
+			const double d = sqrt(r);
+			c->last_defect = c->current_defect; c->current_defect = d; c->step++;
+			if (c->history && c->step < c->history_cap) c->history[c->step] = d;
+			if (f.out) *f.out = d;
+			ug_conv_check(c);
+			break;
+		}
+	}
+}
+
+// ---- deterministic block reduction + last-block finalisation --------------------
+// Every block reduces its value (fixed shuffle tree), writes partials[blockIdx.x];
+// the last block to arrive sums the partials in a fixed order and applies `fin`.
+// Result is independent of block scheduling: bit-reproducible for a given grid size.
+__device__ __forceinline__ double ug_warp_sum(double v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+	return v;
+}
+// must be called by all threads of the block; blockDim.x multiple of 32, <= 1024
+__device__ inline void ug_block_reduce_fin(double v, double* partials, unsigned int* counter, const ug4b200_fin& fin)
+{
+	__shared__ double s_w[32];
+	__shared__ bool s_last;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+	v = ug_warp_sum(v);
+	if (lane == 0) s_w[wid] = v;
+	__syncthreads();
+	if (wid == 0) {
+		v = lane < nw ? s_w[lane] : 0.0;
+		v = ug_warp_sum(v);
+		if (lane == 0) {
+			partials[blockIdx.x] = v;
+			__threadfence();
+			const unsigned int t = atomicAdd(counter, 1u);
+			s_last = (t == gridDim.x - 1);
+		}
+	}
+	__syncthreads();
+	if (s_last) {
+		__threadfence();
+		double a = 0.0;
+		for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) a += ((volatile double*)partials)[i];
+		a = ug_warp_sum(a);
+		if (lane == 0) s_w[wid] = a;
+		__syncthreads();
+		if (wid == 0) {
+			a = lane < nw ? s_w[lane] : 0.0;
+			a = ug_warp_sum(a);
+			if (lane == 0) { *counter = 0u; ug_apply_fin(a, fin); }
+		}
+	}
+}
+
+// streaming loads for data touched exactly once (matrix values / columns)
+__device__ __forceinline__ double ug_ld_stream(const double* p) { return __ldcs(p); }
+__device__ __forceinline__ int ug_ld_stream(const int* p) { return __ldcs(p); }
+
+struct ug4b200_matrix {
+	int block = 1;
+	int64_t nrows = 0, ncols = 0, nnz = 0, padded_nnz = 0, num_slices = 0;
+	int max_row_len = 0;
+	int64_t* slice_ptr = nullptr; // [num_slices+1] entry offsets (multiples of 32)
+	int* rowlen = nullptr;        // [num_slices*32]
+	int* diagpos = nullptr;       // [num_slices*32] position of the diagonal inside the row, -1 if absent
+	int* cols = nullptr;          // [padded_nnz]
+	double* vals = nullptr;       // [padded_nnz*block*block]; entry e, component q at (e/32*BB + q)*32 + e%32
+	bool has_all_diag = false;
+	size_t device_bytes = 0;
+};

@@ -1,0 +1,206 @@
+// gpu_sparsematrix.h — GPUSparseMatrix<T>: host-assembled sparse matrix with an immutable
+// device mirror (SELL-32) that is uploaded on first device use.
+//
+// Mirrors the part of SparseMatrix<T> (ugbase/lib_algebra/cpu_algebra/sparsematrix.h:116-343)
+// that assembly and the solve path touch; storage on the host is sorted-row CRS (what
+// SparseMatrix holds after defragment(), sparsematrix.h:588-592).  Shape of the drop-in:
+// legacy GPUSparseMatrix::copy_to_device()/check_device()
+// (ugbase/lib_algebra/gpu_algebra/gpusparsematrix.h:614-651).  In partitioned runs the
+// matrix is stored additive (ParallelMatrix, parallel_matrix_impl.h:88-114): SpMV needs
+// no communication and maps consistent -> additive.
+#pragma once
+#include "gpu_vector.h"
+#include <algorithm>
+
+namespace ug {
+
+template <typename T> struct gpu_value_access;
+template <> struct gpu_value_access<double> {
+	enum { B = 1 };
+	static double get(const double& v, int, int) { return v; }
+	static void set(double& v, int, int, double x) { v = x; }
+};
+template <size_t N> struct gpu_value_access<DenseMatrix<FixedArray2<double, N, N> > > {
+	enum { B = N };
+	static double get(const DenseMatrix<FixedArray2<double, N, N> >& v, int r, int c) { return v(r, c); }
+	static void set(DenseMatrix<FixedArray2<double, N, N> >& v, int r, int c, double x) { v(r, c) = x; }
+};
+
+template <typename TValueType>
+class GPUSparseMatrix {
+  public:
+	typedef TValueType value_type;
+	typedef GPUSparseMatrix<TValueType> this_type;
+	enum { blockSize = gpu_value_access<TValueType>::B };
+	struct connection { size_t iIndex; value_type dValue; };
+
+	GPUSparseMatrix() {}
+	virtual ~GPUSparseMatrix() { drop_device(); }
+	GPUSparseMatrix(const GPUSparseMatrix&) = delete;
+	GPUSparseMatrix& operator=(const GPUSparseMatrix&) = delete;
+
+	// ---- assembly-side API (host) ----
+	void resize_and_clear(size_t rows, size_t cols)
+	{
+		m_rows.assign(rows, std::vector<connection>()); m_numCols = cols; m_fragmented = true; m_crsRows = 0;
+		m_rowptr.clear(); m_cols.clear(); m_vals.clear(); touch();
+	}
+	size_t num_rows() const { return m_fragmented ? m_rows.size() : m_crsRows; }
+	size_t num_cols() const { return m_numCols; }
+	size_t total_num_connections() const { const_cast<this_type*>(this)->defragment(); return m_cols.size(); }
+	size_t num_connections(size_t r) const { const_cast<this_type*>(this)->defragment(); return (size_t)(m_rowptr[r + 1] - m_rowptr[r]); }
+
+	/// inserting access (sparsematrix_impl.h:596-700): keeps rows sorted
+	value_type& operator()(size_t r, size_t c)
+	{
+		fragment(); touch();
+		std::vector<connection>& row = m_rows[r];
+		auto it = std::lower_bound(row.begin(), row.end(), c, [](const connection& a, size_t cc) { return a.iIndex < cc; });
+		if (it == row.end() || it->iIndex != c) { connection n; n.iIndex = c; n.dValue = value_type(); zero(n.dValue); it = row.insert(it, n); }
+		return it->dValue;
+	}
+	void set_matrix_row(size_t r, connection* c, size_t nr)
+	{
+		fragment(); touch();
+		m_rows[r].assign(c, c + nr);
+		std::sort(m_rows[r].begin(), m_rows[r].end(), [](const connection& a, const connection& b) { return a.iIndex < b.iIndex; });
+	}
+	/// bulk load of a defragmented CRS (what copy_crs exports, sparsematrix.h:607-617);
+	/// vals: block*block doubles per entry, column-major inside a block
+	void set_from_crs(size_t rows, size_t cols, const int64_t* rowptr, const int* colidx, const double* vals)
+	{
+		m_rows.clear(); m_fragmented = false; m_crsRows = rows; m_numCols = cols;
+		m_rowptr.assign(rowptr, rowptr + rows + 1);
+		m_cols.assign(colidx, colidx + rowptr[rows]);
+		m_vals.assign(vals, vals + (size_t)rowptr[rows] * blockSize * blockSize);
+		touch();
+	}
+	void defragment()
+	{
+		if (!m_fragmented) return;
+		const size_t n = m_rows.size(); const int B = blockSize, BB = B * B;
+		m_rowptr.assign(n + 1, 0);
+		for (size_t r = 0; r < n; ++r) m_rowptr[r + 1] = m_rowptr[r] + (int64_t)m_rows[r].size();
+		m_cols.resize(m_rowptr[n]); m_vals.resize((size_t)m_rowptr[n] * BB);
+		for (size_t r = 0; r < n; ++r) {
+			int64_t p = m_rowptr[r];
+			for (const connection& c : m_rows[r]) {
+				m_cols[p] = (int)c.iIndex;
+				for (int i = 0; i < B; ++i) for (int j = 0; j < B; ++j) m_vals[p * BB + i + B * j] = gpu_value_access<value_type>::get(c.dValue, i, j);
+				++p;
+			}
+		}
+		m_crsRows = n; m_rows.clear(); m_fragmented = false;
+	}
+	/// set_as_transpose_of (sparsematrix_impl.h:148-183): explicit zeros are kept
+	void set_as_transpose_of(const this_type& Bm, double scale = 1.0)
+	{
+		const_cast<this_type&>(Bm).defragment();
+		const int B = blockSize, BB = B * B;
+		const size_t nr = Bm.num_cols(), nc = Bm.num_rows();
+		std::vector<int64_t> rp(nr + 1, 0);
+		for (int c : Bm.m_cols) rp[c + 1]++;
+		for (size_t r = 0; r < nr; ++r) rp[r + 1] += rp[r];
+		std::vector<int> ci(Bm.m_cols.size()); std::vector<double> va(Bm.m_vals.size());
+		std::vector<int64_t> fill(rp.begin(), rp.end() - 1);
+		for (size_t r = 0; r < nc; ++r)
+			for (int64_t p = Bm.m_rowptr[r]; p < Bm.m_rowptr[r + 1]; ++p) {
+				const int64_t q = fill[Bm.m_cols[p]]++;
+				ci[q] = (int)r;
+				for (int i = 0; i < B; ++i) for (int j = 0; j < B; ++j) va[q * BB + i + B * j] = scale * Bm.m_vals[p * BB + j + B * i];
+			}
+		set_from_crs(nr, nc, rp.data(), ci.data(), va.data());
+	}
+	const std::vector<int64_t>& crs_rowptr() const { const_cast<this_type*>(this)->defragment(); return m_rowptr; }
+	const std::vector<int>& crs_cols() const { const_cast<this_type*>(this)->defragment(); return m_cols; }
+	const std::vector<double>& crs_vals() const { const_cast<this_type*>(this)->defragment(); return m_vals; }
+
+	// ---- device mirror ----
+	const ug4b200_matrix* device() const
+	{
+		this_type* s = const_cast<this_type*>(this);
+		if (!s->m_dev) {
+			s->defragment();
+			UG_GPU_CHECK(ug4b200_matrix_upload_crs(GPUManager::ctx(), blockSize, (int64_t)m_crsRows, (int64_t)m_numCols,
+			                                       m_rowptr.data(), m_cols.data(), m_vals.data(), UG4B200_MAT_DEFAULT, &s->m_dev));
+		}
+		return m_dev;
+	}
+	/// free the host copy once uploaded (large level matrices: "uploaded once after assembly")
+	void release_host() { device(); std::vector<int>().swap(m_cols); std::vector<double>().swap(m_vals); m_hostReleased = true; }
+
+	// ---- solve-path API: all on the device (sparsematrix.h:184-230) ----
+	template <typename V> bool apply(V& res, const V& x) const
+	{
+		UG_GPU_CHECK(ug4b200_matrix_apply(GPUManager::ctx(), device(), res.dev(), x.dev(), V::blockSize));
+		res.set_storage_type(PST_ADDITIVE); // parallel_matrix_impl.h:105-114
+		return true;
+	}
+	template <typename V> bool matmul_minus(V& res, const V& x) const
+	{
+		UG_GPU_CHECK(ug4b200_matrix_matmul_minus(GPUManager::ctx(), device(), res.dev(), x.dev(), V::blockSize));
+		return true;
+	}
+	template <typename V> bool axpy(V& dest, const number& alpha1, const V& v1, const number& beta1, const V& w1) const
+	{
+		UG_GPU_CHECK(ug4b200_matrix_axpy(GPUManager::ctx(), device(), dest.dev(), alpha1, alpha1 == 0.0 ? nullptr : v1.dev(), beta1,
+		                                 w1.dev(), V::blockSize));
+		return true;
+	}
+	template <typename V> bool apply_ignore_zero_rows(V& dest, const number& beta1, const V& w1) const
+	{
+		UG_GPU_CHECK(ug4b200_matrix_apply_ignore_zero_rows(GPUManager::ctx(), device(), dest.dev(), beta1, w1.dev(), V::blockSize));
+		return true;
+	}
+
+  private:
+	static void zero(double& v) { v = 0.0; }
+	template <class X> static void zero(X& v) { v = 0.0; }
+	void touch() { drop_device(); UG_COND_THROW(m_hostReleased, "GPUSparseMatrix: host copy was released, matrix is immutable"); }
+	void drop_device()
+	{
+		if (m_dev && GPUManager::ctx_or_null()) ug4b200_matrix_destroy(GPUManager::ctx_or_null(), m_dev);
+		m_dev = nullptr;
+	}
+	void fragment()
+	{
+		if (m_fragmented) return;
+		const int B = blockSize, BB = B * B;
+		m_rows.assign(m_crsRows, std::vector<connection>());
+		for (size_t r = 0; r < m_crsRows; ++r)
+			for (int64_t p = m_rowptr[r]; p < m_rowptr[r + 1]; ++p) {
+				connection c; c.iIndex = (size_t)m_cols[p];
+				for (int i = 0; i < B; ++i) for (int j = 0; j < B; ++j) gpu_value_access<value_type>::set(c.dValue, i, j, m_vals[p * BB + i + B * j]);
+				m_rows[r].push_back(c);
+			}
+		m_fragmented = true;
+	}
+
+	// fragmented (assembly) form
+	std::vector<std::vector<connection> > m_rows;
+	bool m_fragmented = false;
+	// defragmented CRS
+	size_t m_crsRows = 0, m_numCols = 0;
+	std::vector<int64_t> m_rowptr;
+	std::vector<int> m_cols;
+	std::vector<double> m_vals;
+	bool m_hostReleased = false;
+	ug4b200_matrix* m_dev = nullptr;
+};
+
+/// CPUAlgebra / CPUBlockAlgebra<N> counterparts (ugbase/lib_algebra/cpu_algebra_types.h:76-142;
+/// the commented-out GPUAlgebra stub :101-120)
+struct GPUAlgebra {
+	typedef GPUSparseMatrix<double> matrix_type;
+	typedef GPUVector<double> vector_type;
+	static const int blockSize = 1;
+	static AlgebraType get_type() { return AlgebraType(AlgebraType::GPU, 1); }
+};
+template <int TBlockSize> struct GPUBlockAlgebra {
+	typedef GPUSparseMatrix<DenseMatrix<FixedArray2<double, TBlockSize, TBlockSize> > > matrix_type;
+	typedef GPUVector<DenseVector<FixedArray1<double, TBlockSize> > > vector_type;
+	static const int blockSize = TBlockSize;
+	static AlgebraType get_type() { return AlgebraType(AlgebraType::GPU, TBlockSize); }
+};
+
+} // namespace ug

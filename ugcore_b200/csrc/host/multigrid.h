@@ -1,0 +1,344 @@
+// multigrid.h — StdTransfer and AssembledMultiGridCycle for the GPU algebra.
+//
+//   StdTransfer              ugbase/lib_disc/operator/linear_operator/std_transfer.h:56-59,
+//                            std_transfer_impl.h:719-772 (prolongate), :774-806 (do_restrict)
+//   AssembledMultiGridCycle  ugbase/lib_disc/operator/linear_operator/multi_grid_solver/
+//                            mg_solver.h:81-84, mg_solver_impl.hpp:174-275 (apply),
+//                            :1685-1816 (presmooth_and_restriction), :1818-1964
+//                            (prolongation_and_postsmooth), :1967-2086 (base_solve),
+//                            :2089-2136 (lmgc)
+//
+// In ugcore these classes are templated on <TDomain, TAlgebra> and pull level operators
+// and P from the ApproximationSpace; assembly stays on the CPU, so here
+// the assembled level matrices and transfer matrices are handed in after assembly
+// (set_level_operator / set_level_transfer — the hook points named in SURVEY.md §3.2).
+// The cycle itself never touches host memory: every level vector is device resident and
+// the surface<->level copies (mg_solver_impl.hpp:211-217, 244-248) are device gathers.
+#pragma once
+#include "solvers.h"
+
+namespace ug {
+
+/// transfer matrices carry scalars; for block algebras ugcore stores the scalar on the block
+/// diagonal (DoFRef(P, ..)), which acts component-wise — done by the kernel instead
+typedef GPUSparseMatrix<double> GPUTransferMatrix;
+
+template <typename TAlgebra>
+class StdTransfer {
+  public:
+	typedef typename TAlgebra::vector_type vector_type;
+	StdTransfer() : m_dampProl(1.0), m_dampRes(1.0), m_bUseTransposed(true) {}
+	void set_prolongation_damping(number damp) { m_dampProl = damp; }
+	void set_restriction_damping(number damp) { m_dampRes = damp; }
+	void set_use_transposed(bool b) { m_bUseTransposed = b; }
+	/// cached matrices of one level pair (std_transfer.h:195-211); R may be null -> R = P^T
+	void set_matrices(SmartPtr<GPUTransferMatrix> P, SmartPtr<GPUTransferMatrix> R) { m_P = P; m_R = R; }
+	void init()
+	{
+		if (!m_P) UG_THROW("StdTransfer: prolongation matrix not set");
+		if (!m_R) {
+			if (!m_bUseTransposed) UG_THROW("StdTransfer: restriction matrix not set");
+			m_R = make_sp<GPUTransferMatrix>();
+			m_R->set_as_transpose_of(*m_P); // std_transfer_impl.h:694-695
+		}
+		m_P->device(); m_R->device();
+	}
+	SmartPtr<GPUTransferMatrix> prolongation() { return m_P; }
+	SmartPtr<GPUTransferMatrix> restriction() { return m_R; }
+	/// uFine = dampProl * P * uCoarse   (std_transfer_impl.h:738-740)
+	void prolongate(vector_type& uFine, const vector_type& uCoarse)
+	{
+		m_P->axpy(uFine, 0.0, uFine, m_dampProl, uCoarse);
+		uFine.set_storage_type(uCoarse.get_storage_mask());
+	}
+	/// uCoarse = dampRes * R * uFine, rows without connections untouched (std_transfer_impl.h:791-792)
+	void do_restrict(vector_type& uCoarse, const vector_type& uFine)
+	{
+		m_R->apply_ignore_zero_rows(uCoarse, m_dampRes, uFine);
+		uCoarse.set_storage_type(uFine.get_storage_mask());
+	}
+	SmartPtr<StdTransfer> clone() { SmartPtr<StdTransfer> t(new StdTransfer()); t->m_dampProl = m_dampProl; t->m_dampRes = m_dampRes; t->m_bUseTransposed = m_bUseTransposed; return t; }
+  protected:
+	number m_dampProl, m_dampRes;
+	bool m_bUseTransposed;
+	SmartPtr<GPUTransferMatrix> m_P, m_R;
+};
+
+enum { _V_ = 1, _W_ = 2, _F_ = -1 };
+
+template <typename TAlgebra>
+class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector_type> {
+  public:
+	typedef TAlgebra algebra_type;
+	typedef typename TAlgebra::vector_type vector_type;
+	typedef typename TAlgebra::matrix_type matrix_type;
+	typedef MatrixOperator<matrix_type, vector_type> matrix_operator_type;
+	typedef ILinearIterator<vector_type> smoother_type;
+	enum { B = TAlgebra::blockSize };
+
+	AssembledMultiGridCycle()
+	    : m_baseLev(0), m_topLev(0), m_cycleType(_V_), m_numPreSmooth(2), m_numPostSmooth(2), m_bFinalDefect(false),
+	      m_bFuseJacobi(true) {}
+	virtual const char* name() const { return "Geometric MultiGrid"; }
+	virtual bool supports_parallel() const { return true; }
+
+	// ---- configuration (mg_solver.h:113-205) ----
+	void set_base_level(int baseLevel) { m_baseLev = baseLevel; }
+	void set_surface_level(int topLevel) { m_topLev = topLevel; }
+	void set_cycle_type(int type) { m_cycleType = type; }
+	void set_cycle_type(const std::string& type)
+	{
+		if (type == "V") m_cycleType = _V_; else if (type == "W") m_cycleType = _W_; else if (type == "F") m_cycleType = _F_;
+		else UG_THROW("GMG::set_cycle_type: option '" << type << "' not supported.");
+	}
+	void set_num_presmooth(int num) { m_numPreSmooth = num; }
+	void set_num_postsmooth(int num) { m_numPostSmooth = num; }
+	void set_smoother(SmartPtr<smoother_type> smoother) { m_spPreSmootherPrototype = smoother; m_spPostSmootherPrototype = smoother; }
+	void set_presmoother(SmartPtr<smoother_type> smoother) { m_spPreSmootherPrototype = smoother; }
+	void set_postsmoother(SmartPtr<smoother_type> smoother) { m_spPostSmootherPrototype = smoother; }
+	void set_base_solver(SmartPtr<ILinearOperatorInverse<vector_type> > baseSolver) { m_spBaseSolver = baseSolver; }
+	void set_transfer(SmartPtr<StdTransfer<TAlgebra> > P) { m_spTransferPrototype = P; }
+	/// the reference recomputes the top-level defect after the last post-smoothing step
+	/// (mg_solver_impl.hpp:1954-1958) although no caller reads it; off by default
+	void set_compute_final_level_defect(bool b) { m_bFinalDefect = b; }
+	void set_fuse_jacobi(bool b) { m_bFuseJacobi = b; }
+
+	// ---- what assembly hands over (replaces assemble_level_operator :526-752 and the cached
+	//      StdTransfer::prolongation()/restriction() :602-717) ----
+	void set_level_operator(int lev, SmartPtr<matrix_operator_type> A) { level(lev).A = A; }
+	void set_level_transfer(int lev, SmartPtr<GPUTransferMatrix> P, SmartPtr<GPUTransferMatrix> R) { level(lev).P = P; level(lev).R = R; }
+	/// surface index of every top-level index (vSurfLevelMap); empty = identity (full refinement)
+	void set_surface_to_level_map(const std::vector<int>& surfIndexOfLevelIndex) { m_surfMap = surfIndexOfLevelIndex; }
+	// partitioned runs
+	void set_level_layouts(int lev, SmartPtr<GPUAlgebraLayouts> l) { level(lev).layouts = l; }
+	/// gathered base solve (mg_solver_impl.hpp:2003-2070): every rank holds the assembled global
+	/// base matrix; local additive defects are summed into it with one all-reduce
+	void set_gathered_base(SmartPtr<matrix_operator_type> globalA, const std::vector<int>& localToGlobal)
+	{ m_spGatheredA = globalA; m_baseLocalToGlobal = localToGlobal; }
+
+	virtual SmartPtr<ILinearIterator<vector_type> > clone() { UG_THROW("GMG::clone: not supported for the GPU algebra"); }
+
+	virtual bool init(SmartPtr<ILinearOperator<vector_type> > J, const vector_type&) { return init(J); }
+	virtual bool init(SmartPtr<ILinearOperator<vector_type> > L)
+	{
+		m_spSurfaceMat = std::dynamic_pointer_cast<matrix_operator_type>(L);
+		if (!m_spSurfaceMat) UG_THROW("GMG:init: Can not cast Operator to Matrix.");
+		if (m_baseLev > m_topLev) UG_THROW("GMG::init: Base Level greater than Surface level.");
+		if (!m_spBaseSolver) UG_THROW("GMG::init: Base Solver not set.");
+		if (!m_spPreSmootherPrototype) UG_THROW("GMG::init: PreSmoother not set.");
+		if (!m_spPostSmootherPrototype) UG_THROW("GMG::init: PostSmoother not set.");
+		if (!m_spTransferPrototype) m_spTransferPrototype = make_sp<StdTransfer<TAlgebra> >();
+		ug4b200_ctx* ctx = GPUManager::ctx();
+		for (int lev = m_baseLev; lev <= m_topLev; ++lev) {
+			LevData& ld = level(lev);
+			if (!ld.A) {
+				if (lev == m_topLev) ld.A = m_spSurfaceMat; // copy of the surface matrix (:623-656), identity map
+				else UG_THROW("GMG::init: level operator of level " << lev << " missing");
+			}
+			const size_t n = ld.A->num_rows();
+			ld.sc.create(n); ld.sd.create(n); ld.st.create(n); ld.st2.create(n);
+			for (vector_type* v : {&ld.sc, &ld.sd, &ld.st, &ld.st2}) v->set_layouts(ld.layouts);
+			ld.A->device();
+			if (lev > m_baseLev) {
+				if (!ld.P) UG_THROW("GMG::init: prolongation of level " << lev << " missing");
+				ld.transfer = m_spTransferPrototype->clone();
+				ld.transfer->set_matrices(ld.P, ld.R);
+				ld.transfer->init();
+				ld.PreSmoother = m_spPreSmootherPrototype->clone();
+				if (m_spPreSmootherPrototype == m_spPostSmootherPrototype) ld.PostSmoother = ld.PreSmoother;
+				else ld.PostSmoother = m_spPostSmootherPrototype->clone();
+				for (SmartPtr<smoother_type> s : {ld.PreSmoother, ld.PostSmoother}) {
+					Jacobi<TAlgebra>* j = dynamic_cast<Jacobi<TAlgebra>*>(s.get());
+					if (j) j->set_layouts(ld.layouts);
+				}
+				if (!ld.PreSmoother->init(ld.A)) UG_THROW("GMG::init: Cannot init pre-smoother for level " << lev);
+				if (ld.PostSmoother != ld.PreSmoother && !ld.PostSmoother->init(ld.A))
+					UG_THROW("GMG::init: Cannot init post-smoother for level " << lev);
+			}
+		}
+		// base solver (:1171-1229)
+		LevData& lb = level(m_baseLev);
+		if (lb.layouts) {
+			if (!m_spGatheredA) UG_THROW("GMG::init: partitioned hierarchy needs a gathered base matrix");
+			m_gatheredD.create(m_spGatheredA->num_rows()); m_gatheredC.create(m_spGatheredA->num_rows());
+			THROW_IF_NOT_EQUAL(m_baseLocalToGlobal.size(), lb.A->num_rows());
+			GPUManager::free_bytes(m_dBaseMap);
+			m_dBaseMap = (int*)GPUManager::alloc_bytes(sizeof(int) * m_baseLocalToGlobal.size());
+			UG_GPU_CHECK(ug4b200_h2d(ctx, m_dBaseMap, m_baseLocalToGlobal.data(), sizeof(int) * m_baseLocalToGlobal.size()));
+			if (!m_spBaseSolver->init(m_spGatheredA)) UG_THROW("GMG::init: Cannot init base solver");
+		} else if (!m_spBaseSolver->init(lb.A)) UG_THROW("GMG::init: Cannot init base solver on baselevel " << m_baseLev);
+		// surface <-> level map
+		GPUManager::free_bytes(m_dSurfMap); m_dSurfMap = nullptr;
+		if (!m_surfMap.empty()) {
+			THROW_IF_NOT_EQUAL(m_surfMap.size(), level(m_topLev).A->num_rows());
+			m_dSurfMap = (int*)GPUManager::alloc_bytes(sizeof(int) * m_surfMap.size());
+			UG_GPU_CHECK(ug4b200_h2d(ctx, m_dSurfMap, m_surfMap.data(), sizeof(int) * m_surfMap.size()));
+		}
+		UG_GPU_CHECK(ug4b200_sync(ctx));
+		return true;
+	}
+	~AssembledMultiGridCycle() { GPUManager::free_bytes(m_dSurfMap); GPUManager::free_bytes(m_dBaseMap); }
+
+	/// mg_solver_impl.hpp:174-275
+	virtual bool apply(vector_type& c, const vector_type& d)
+	{
+		ug4b200_ctx* ctx = GPUManager::ctx();
+		LevData& top = level(m_topLev);
+		THROW_IF_NOT_EQUAL(d.size(), top.sd.size());
+		// project defect from surface to level (:211-217)
+		if (m_dSurfMap) UG_GPU_CHECK(ug4b200_vec_gather(ctx, (int64_t)top.sd.size(), B, top.sd.dev(), d.dev(), m_dSurfMap));
+		else UG_GPU_CHECK(ug4b200_vec_copy(ctx, top.sd.len(), top.sd.dev(), d.dev()));
+		top.sd.set_storage_type(d.get_storage_mask());
+		top.sc.set(0.0);                       // :234
+		lmgc(m_topLev, m_cycleType);           // :238
+		// c = 0 (:231) ; c[surf] += sc[lev] (:244-248)
+		if (m_dSurfMap) {
+			c.set(0.0);
+			UG_GPU_CHECK(ug4b200_vec_scatter_add(ctx, (int64_t)top.sc.size(), B, c.dev(), m_dSurfMap, top.sc.dev()));
+		} else {
+			// 0.0 + sc == sc bit for bit (up to the sign of zero)
+			UG_GPU_CHECK(ug4b200_vec_copy(ctx, c.len(), c.dev(), top.sc.dev()));
+		}
+		c.set_storage_type(PST_CONSISTENT);
+		const number kappa = this->damping()->damping(c, d, m_spSurfaceMat);
+		if (kappa != 1.0) c *= kappa;          // :259-260
+		return true;
+	}
+	/// mg_solver_impl.hpp:277-320
+	virtual bool apply_update_defect(vector_type& c, vector_type& rD)
+	{
+		if (!apply(c, rD)) return false;
+		m_spSurfaceMat->matmul_minus(rD, c);
+		return true;
+	}
+
+  protected:
+	struct LevData {
+		SmartPtr<matrix_operator_type> A;
+		SmartPtr<GPUTransferMatrix> P, R;
+		SmartPtr<StdTransfer<TAlgebra> > transfer;
+		SmartPtr<smoother_type> PreSmoother, PostSmoother;
+		vector_type sc, sd, st, st2;
+		SmartPtr<GPUAlgebraLayouts> layouts;
+	};
+	LevData& level(int lev)
+	{
+		if (lev < 0) UG_THROW("GMG: negative level");
+		if ((int)m_vLevData.size() <= lev) { const size_t o = m_vLevData.size(); m_vLevData.resize(lev + 1); for (size_t i = o; i < m_vLevData.size(); ++i) m_vLevData[i] = make_sp<LevData>(); }
+		return *m_vLevData[lev];
+	}
+	void make_consistent(vector_type& v)
+	{
+		if (!v.layouts()) return;
+		v.set_storage_type(PST_ADDITIVE);
+		if (!v.change_storage_type(PST_CONSISTENT)) UG_THROW("GMG: cannot make correction consistent");
+	}
+
+	/// mg_solver_impl.hpp:2089-2136
+	void lmgc(int lev, int cycleType)
+	{
+		if (lev == m_baseLev) { base_solve(m_topLev); return; }
+		else if (lev < m_baseLev) UG_THROW("GMG::lmgc: call lmgc only for lev > baseLev.");
+		presmooth_and_restriction(lev);
+		if (lev - 1 == m_baseLev) base_solve(lev - 1);
+		else if (cycleType == _F_) { lmgc(lev - 1, _F_); lmgc(lev - 1, _V_); }
+		else for (int i = 0; i < cycleType; ++i) lmgc(lev - 1, cycleType);
+		prolongation_and_postsmooth(lev);
+	}
+
+	/// mg_solver_impl.hpp:1685-1816
+	void presmooth_and_restriction(int lev)
+	{
+		ug4b200_ctx* ctx = GPUManager::ctx();
+		LevData& lf = level(lev); LevData& lc = level(lev - 1);
+		Jacobi<TAlgebra>* jac = m_bFuseJacobi ? dynamic_cast<Jacobi<TAlgebra>*>(lf.PreSmoother.get()) : nullptr;
+		if (jac && jac->damping()->constant_damping() && m_numPreSmooth > 0) {
+			// fused: st0 = D sd ; then per step one kernel  { sc += st ; sd -= A st ; [st' = D sd] }
+			const int64_t n = (int64_t)lf.sd.size();
+			vector_type* cur = &lf.st; vector_type* alt = &lf.st2;
+			UG_GPU_CHECK(ug4b200_jacobi_step(ctx, n, B, jac->diag_inv_dev(), cur->dev(), lf.sd.dev()));
+			make_consistent(*cur);
+			for (int nu = 0; nu < m_numPreSmooth; ++nu) {
+				const bool last = (nu == m_numPreSmooth - 1);
+				const int flags = UG4B200_SMOOTH_ADD_IN | (last ? 0 : UG4B200_SMOOTH_JACOBI);
+				UG_GPU_CHECK(ug4b200_jacobi_smooth_fused(ctx, lf.A->device(), jac->diag_inv_dev(), lf.sd.dev(), cur->dev(),
+				                                         last ? nullptr : alt->dev(), lf.sc.dev(), flags));
+				if (!last) { make_consistent(*alt); std::swap(cur, alt); }
+			}
+			lc.sc.set(0.0);
+		} else {
+			for (int nu = 0; nu < m_numPreSmooth; ++nu) {
+				if (!lf.PreSmoother->apply(lf.st, lf.sd)) UG_THROW("GMG: Smoothing step " << nu + 1 << " on level " << lev << " failed.");
+				lf.A->apply_sub(lf.sd, lf.st);                      // :1726
+				if (nu < m_numPreSmooth - 1) lf.sc += lf.st;        // :1729-1730
+			}
+			lc.sc.set(0.0);                                         // :1780
+			if (m_numPreSmooth > 0) lf.sc += lf.st;                 // :1783-1784
+		}
+		lf.transfer->do_restrict(lc.sd, lf.sd);                     // :1802
+	}
+
+	/// mg_solver_impl.hpp:1818-1964
+	void prolongation_and_postsmooth(int lev)
+	{
+		ug4b200_ctx* ctx = GPUManager::ctx();
+		LevData& lf = level(lev); LevData& lc = level(lev - 1);
+		lf.transfer->prolongate(lf.st, lc.sc);                      // :1865
+		Jacobi<TAlgebra>* jac = m_bFuseJacobi ? dynamic_cast<Jacobi<TAlgebra>*>(lf.PostSmoother.get()) : nullptr;
+		if (jac && jac->damping()->constant_damping()) {
+			vector_type* cur = &lf.st; vector_type* alt = &lf.st2;
+			for (int nu = 0; nu < m_numPostSmooth; ++nu) {
+				UG_GPU_CHECK(ug4b200_jacobi_smooth_fused(ctx, lf.A->device(), jac->diag_inv_dev(), lf.sd.dev(), cur->dev(), alt->dev(),
+				                                         lf.sc.dev(), UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_JACOBI));
+				make_consistent(*alt);
+				std::swap(cur, alt);
+			}
+			lf.sc += *cur;                                          // last :1905 / :1943
+			if (m_bFinalDefect && lev >= m_topLev) lf.A->apply_sub(lf.sd, *cur);
+		} else {
+			lf.sc += lf.st;                                         // :1905
+			for (int nu = 0; nu < m_numPostSmooth; ++nu) {
+				lf.A->apply_sub(lf.sd, lf.st);                      // :1919
+				if (!lf.PostSmoother->apply(lf.st, lf.sd)) UG_THROW("GMG: Smoothing step " << nu + 1 << " on level " << lev << " failed.");
+				lf.sc += lf.st;                                     // :1943
+			}
+			if (m_bFinalDefect && lev >= m_topLev) lf.A->apply_sub(lf.sd, lf.st); // :1954-1958
+		}
+	}
+
+	/// mg_solver_impl.hpp:1967-2086
+	void base_solve(int lev)
+	{
+		ug4b200_ctx* ctx = GPUManager::ctx();
+		LevData& ld = level(lev);
+		if (!ld.layouts) {
+			if (!m_spBaseSolver->apply(ld.sc, ld.sd)) UG_THROW("GMG::lmgc: Base solver on base level " << lev << " failed.");
+		} else {
+			// gathered: additive local defects -> global consistent defect on every rank
+			m_gatheredD.set(0.0);
+			UG_GPU_CHECK(ug4b200_vec_scatter(ctx, (int64_t)ld.sd.size(), B, m_gatheredD.dev(), m_dBaseMap, ld.sd.dev()));
+			UG_GPU_CHECK(ug4b200_allreduce_sum(ctx, m_gatheredD.dev(), (int)m_gatheredD.len()));
+			if (!m_spBaseSolver->apply(m_gatheredC, m_gatheredD)) UG_THROW("GMG::lmgc: Base solver on base level " << lev << " failed.");
+			UG_GPU_CHECK(ug4b200_vec_gather(ctx, (int64_t)ld.sc.size(), B, ld.sc.dev(), m_gatheredC.dev(), m_dBaseMap));
+			ld.sc.set_storage_type(PST_CONSISTENT);
+		}
+		if (lev >= m_topLev) ld.A->apply_sub(ld.sd, ld.sc);         // :2075-2078
+	}
+
+	int m_baseLev, m_topLev, m_cycleType, m_numPreSmooth, m_numPostSmooth;
+	bool m_bFinalDefect, m_bFuseJacobi;
+	SmartPtr<smoother_type> m_spPreSmootherPrototype, m_spPostSmootherPrototype;
+	SmartPtr<ILinearOperatorInverse<vector_type> > m_spBaseSolver;
+	SmartPtr<StdTransfer<TAlgebra> > m_spTransferPrototype;
+	SmartPtr<matrix_operator_type> m_spSurfaceMat;
+	std::vector<SmartPtr<LevData> > m_vLevData;
+	std::vector<int> m_surfMap;
+	int* m_dSurfMap = nullptr;
+	// gathered base
+	SmartPtr<matrix_operator_type> m_spGatheredA;
+	std::vector<int> m_baseLocalToGlobal;
+	int* m_dBaseMap = nullptr;
+	vector_type m_gatheredD, m_gatheredC;
+};
+
+} // namespace ug

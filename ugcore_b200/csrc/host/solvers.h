@@ -1,0 +1,483 @@
+// solvers.h — CG, BiCGStab, LinearSolver and the base solvers for the GPU algebra.
+//
+//   CG            ugbase/lib_algebra/operator/linear_solver/cg.h:103-242
+//   BiCGStab      ugbase/lib_algebra/operator/linear_solver/bicgstab.h:112-383
+//   LinearSolver  ugbase/lib_algebra/operator/linear_solver/linear_solver.h:114-196
+//   LU            ugbase/lib_algebra/operator/linear_solver/lu.h:122-380
+//                 (dense kernels no_lapack/lu_decomp.h:45-75, 160-195)
+//
+// CG keeps every scalar (rho, lambda, alpha, beta, the StdConvCheck state and the defect
+// history) on the device: an iteration is a fixed sequence of stream-ordered launches
+// with no host round trip, captured once into a CUDA graph and replayed.  The host polls
+// the device convergence flag one iteration late; iterations queued past convergence are
+// no-ops (ug4b200_set_guard), so x, the iteration count and the history are exactly those
+// of the reference loop.
+#pragma once
+#include "preconditioners.h"
+#include <cmath>
+
+namespace ug {
+
+namespace detail {
+/// device scalars + convergence state of one Krylov solve
+struct KrylovDeviceState {
+	enum { RHO_OLD = 0, LAMBDA, ALPHA, RHO, BETA, TMP, OMEGA, NUM };
+	double* s = nullptr;             // NUM doubles
+	ug4b200_conv_state* conv = nullptr;
+	double* history = nullptr;
+	int historyCap = 0;
+	ug4b200_conv_state* pinned = nullptr; // 2 slots
+	void* ev[2] = {nullptr, nullptr};
+	void ensure(int cap)
+	{
+		ug4b200_ctx* c = GPUManager::ctx();
+		if (!s) {
+			s = (double*)GPUManager::alloc_bytes(sizeof(double) * NUM);
+			conv = (ug4b200_conv_state*)GPUManager::alloc_bytes(sizeof(ug4b200_conv_state));
+			UG_GPU_CHECK(ug4b200_host_alloc(c, 2 * sizeof(ug4b200_conv_state), (void**)&pinned));
+			UG_GPU_CHECK(ug4b200_event_create(c, &ev[0]));
+			UG_GPU_CHECK(ug4b200_event_create(c, &ev[1]));
+		}
+		if (cap > historyCap) {
+			GPUManager::free_bytes(history);
+			history = (double*)GPUManager::alloc_bytes(sizeof(double) * cap);
+			historyCap = cap;
+		}
+	}
+	~KrylovDeviceState()
+	{
+		ug4b200_ctx* c = GPUManager::ctx_or_null();
+		if (!c) return;
+		GPUManager::free_bytes(s); GPUManager::free_bytes(conv); GPUManager::free_bytes(history);
+		if (pinned) ug4b200_host_free(c, pinned);
+		if (ev[0]) ug4b200_event_destroy(c, ev[0]);
+		if (ev[1]) ug4b200_event_destroy(c, ev[1]);
+	}
+};
+} // namespace detail
+
+template <typename TVector>
+class CG : public IPreconditionedLinearOperatorInverse<TVector> {
+  public:
+	typedef TVector vector_type;
+	typedef IPreconditionedLinearOperatorInverse<TVector> base_type;
+	using base_type::convergence_check;
+	using base_type::linear_operator;
+	using base_type::preconditioner;
+	enum { B = TVector::blockSize };
+
+	CG() {}
+	explicit CG(SmartPtr<ILinearIterator<vector_type, vector_type> > spPrecond) : base_type(spPrecond) {}
+	~CG() { drop_graph(); }
+	virtual const char* name() const { return "CG"; }
+	/// false: reference-shaped loop with host scalars (one host sync per dot / norm)
+	void set_device_resident(bool b) { m_deviceResident = b; }
+	void set_use_graph(bool b) { m_useGraph = b; }
+
+	virtual bool apply_return_defect(vector_type& x, vector_type& b)
+	{
+		if (x.layouts() && (!b.has_storage_type(PST_ADDITIVE) || !x.has_storage_type(PST_CONSISTENT)))
+			UG_THROW("CG::apply_return_defect: Inadequate storage format of Vectors.");
+		StdConvCheck<vector_type>* std_cc = dynamic_cast<StdConvCheck<vector_type>*>(convergence_check().get());
+		if (m_deviceResident && std_cc) return apply_device(x, b, *std_cc);
+		return apply_host(x, b);
+	}
+
+  protected:
+	// ---- reference-shaped loop, scalars on the host (cg.h:103-242) ----
+	bool apply_host(vector_type& x, vector_type& b)
+	{
+		vector_type& r = b;
+		linear_operator()->apply_sub(r, x);
+		SmartPtr<vector_type> spQ = r.clone_without_values(); vector_type& q = *spQ;
+		SmartPtr<vector_type> spZ = x.clone_without_values(); vector_type& z = *spZ;
+		SmartPtr<vector_type> spP = x.clone_without_values(); vector_type& p = *spP;
+		if (preconditioner()) { if (!preconditioner()->apply(z, r)) return false; }
+		else z = r;
+		if (z.layouts() && !z.change_storage_type(PST_CONSISTENT)) UG_THROW("CG: Cannot convert z to consistent vector.");
+		convergence_check()->start(r);
+		p = z;
+		number rhoOld = z.dotprod(r), rho;
+		while (!convergence_check()->iteration_ended()) {
+			linear_operator()->apply(q, p);
+			number lambda = q.dotprod(p);
+			if (lambda == 0.0) { if (p.size()) return false; lambda = 1.0; }
+			const number alpha = rhoOld / lambda;
+			VecScaleAdd(x, 1.0, x, alpha, p);
+			VecScaleAdd(r, 1.0, r, -alpha, q);
+			convergence_check()->update(r);
+			if (convergence_check()->iteration_ended()) break;
+			if (preconditioner()) { if (!preconditioner()->apply(z, r)) return false; }
+			else z = r;
+			if (z.layouts() && !z.change_storage_type(PST_CONSISTENT)) UG_THROW("CG: Cannot convert z to consistent vector.");
+			rho = z.dotprod(r);
+			const number beta = rho / rhoOld;
+			VecScaleAdd(p, beta, p, 1.0, z);
+			rhoOld = rho;
+		}
+		return convergence_check()->post();
+	}
+
+	// ---- device-resident loop ----
+	typedef detail::KrylovDeviceState KS;
+
+	void reduce_fin(const vector_type& a, const vector_type& bvec, ug4b200_fin fin, bool parallel)
+	{
+		ug4b200_ctx* c = GPUManager::ctx();
+		if (!parallel) { UG_GPU_CHECK(ug4b200_vec_dot_ds(c, a.len(), a.dev(), bvec.dev(), fin)); return; }
+		ug4b200_fin st{UG4B200_FIN_STORE, m_ks.s + KS::TMP, nullptr, nullptr, nullptr};
+		UG_GPU_CHECK(ug4b200_vec_dot_ds(c, a.len(), a.dev(), bvec.dev(), st));
+		UG_GPU_CHECK(ug4b200_allreduce_sum(c, m_ks.s + KS::TMP, 1));
+		UG_GPU_CHECK(ug4b200_scalar_fin_ds(c, m_ks.s + KS::TMP, fin));
+	}
+	void norm_fin(vector_type& r, int op, bool parallel)
+	{
+		ug4b200_fin fin{op, nullptr, nullptr, nullptr, m_ks.conv};
+		if (parallel && !r.change_storage_type(PST_UNIQUE)) UG_THROW("CG: cannot make the defect unique");
+		reduce_fin(r, r, fin, parallel);
+	}
+	void precond_apply(vector_type& z, vector_type& r)
+	{
+		if (preconditioner()) { if (!preconditioner()->apply(z, r)) UG_THROW("CG: Cannot apply preconditioner."); }
+		else { UG_GPU_CHECK(ug4b200_vec_copy(GPUManager::ctx(), z.len(), z.dev(), r.dev())); z.set_storage_type(r.get_storage_mask()); }
+		if (z.layouts() && !z.change_storage_type(PST_CONSISTENT)) UG_THROW("CG: Cannot convert z to consistent vector.");
+	}
+	void iteration_body(vector_type& x, vector_type& r, vector_type& q, vector_type& z, vector_type& p, bool parallel)
+	{
+		ug4b200_ctx* c = GPUManager::ctx();
+		double* S = m_ks.s;
+		// q = A p ; lambda = (q,p) ; alpha = rhoOld / lambda            (cg.h:166-185)
+		ug4b200_fin finL{UG4B200_FIN_A_DIV_R, S + KS::LAMBDA, S + KS::ALPHA, S + KS::RHO_OLD, m_ks.conv};
+		typedef MatrixOperator<GPUSparseMatrix<typename matrix_value<B>::type>, vector_type> matop_t;
+		matop_t* mop = dynamic_cast<matop_t*>(linear_operator().get());
+		if (mop && !parallel) {
+			UG_GPU_CHECK(ug4b200_matrix_apply_dot_ds(c, mop->device(), q.dev(), p.dev(), finL));
+			q.set_storage_type(PST_ADDITIVE);
+		} else {
+			linear_operator()->apply(q, p);
+			reduce_fin(q, p, finL, parallel);
+		}
+		// x += alpha p ; r -= alpha q ; ||r|| ; convergence check          (cg.h:187-199)
+		if (!parallel) {
+			ug4b200_fin finN{UG4B200_FIN_CONV_UPDATE, nullptr, nullptr, nullptr, m_ks.conv};
+			UG_GPU_CHECK(ug4b200_cg_update_ds(c, x.len(), x.dev(), p.dev(), r.dev(), q.dev(), S + KS::ALPHA, finN));
+		} else {
+			ug4b200_fin junk{UG4B200_FIN_STORE, S + KS::TMP, nullptr, nullptr, nullptr};
+			UG_GPU_CHECK(ug4b200_cg_update_ds(c, x.len(), x.dev(), p.dev(), r.dev(), q.dev(), S + KS::ALPHA, junk));
+			r.set_storage_type(PST_ADDITIVE);
+			norm_fin(r, UG4B200_FIN_CONV_UPDATE, true);
+		}
+		// z = M^-1 r ; rho = (z,r) ; beta = rho/rhoOld ; p = beta p + z ; rhoOld = rho   (cg.h:206-240)
+		precond_apply(z, r);
+		ug4b200_fin finR{UG4B200_FIN_R_DIV_A, S + KS::RHO_OLD, S + KS::BETA, S + KS::RHO_OLD, nullptr};
+		reduce_fin(z, r, finR, parallel);
+		UG_GPU_CHECK(ug4b200_vec_scale_add2_ds(c, p.len(), p.dev(), ug4b200_coef{S + KS::BETA, 1.0}, p.dev(),
+		                                       ug4b200_coef{nullptr, 1.0}, z.dev()));
+	}
+
+	bool apply_device(vector_type& x, vector_type& b, StdConvCheck<vector_type>& cc)
+	{
+		ug4b200_ctx* c = GPUManager::ctx();
+		const bool parallel = (bool)x.layouts();
+		vector_type& r = b;
+		linear_operator()->apply_sub(r, x);
+		SmartPtr<vector_type> spQ = r.clone_without_values(); vector_type& q = *spQ;
+		SmartPtr<vector_type> spZ = x.clone_without_values(); vector_type& z = *spZ;
+		SmartPtr<vector_type> spP = x.clone_without_values(); vector_type& p = *spP;
+		const int maxSteps = cc.maximum_steps();
+		m_ks.ensure(maxSteps + 2);
+		UG_GPU_CHECK(ug4b200_conv_init(c, m_ks.conv, maxSteps, cc.minimum_defect(), cc.relative_reduction(), m_ks.history, m_ks.historyCap));
+		UG_GPU_CHECK(ug4b200_set_guard(c, nullptr));
+		precond_apply(z, r);
+		norm_fin(r, UG4B200_FIN_CONV_START, parallel);
+		UG_GPU_CHECK(ug4b200_vec_copy(c, p.len(), p.dev(), z.dev()));
+		p.set_storage_type(z.get_storage_mask());
+		ug4b200_fin finR{UG4B200_FIN_STORE, m_ks.s + KS::RHO_OLD, nullptr, nullptr, nullptr};
+		reduce_fin(z, r, finR, parallel);
+		UG_GPU_CHECK(ug4b200_set_guard(c, &m_ks.conv->done));
+
+		// graph of one iteration, keyed by the buffers it touches
+		const void* key[5] = {x.dev(), r.dev(), q.dev(), z.dev(), p.dev()};
+		bool graphOk = m_useGraph;
+		if (graphOk && (!m_graph || std::memcmp(key, m_graphKey, sizeof(key)) != 0)) {
+			drop_graph();
+			UG_GPU_CHECK(ug4b200_graph_begin(c));
+			try { iteration_body(x, r, q, z, p, parallel); }
+			catch (...) { ug4b200_graph* g = nullptr; ug4b200_graph_end(c, &g); ug4b200_graph_destroy(c, g); ug4b200_set_guard(c, nullptr); throw; }
+			UG_GPU_CHECK(ug4b200_graph_end(c, &m_graph));
+			std::memcpy(m_graphKey, key, sizeof(key));
+		}
+		int it = 0;
+		bool done = false;
+		// the start defect may already satisfy the check: poll once before iterating
+		UG_GPU_CHECK(ug4b200_d2h_async(c, &m_ks.pinned[0], m_ks.conv, sizeof(ug4b200_conv_state)));
+		UG_GPU_CHECK(ug4b200_event_record(c, m_ks.ev[0]));
+		for (; it < maxSteps && !done; ++it) {
+			if (graphOk) UG_GPU_CHECK(ug4b200_graph_launch(c, m_graph));
+			else iteration_body(x, r, q, z, p, parallel);
+			const int slot = (it + 1) & 1;
+			UG_GPU_CHECK(ug4b200_d2h_async(c, &m_ks.pinned[slot], m_ks.conv, sizeof(ug4b200_conv_state)));
+			UG_GPU_CHECK(ug4b200_event_record(c, m_ks.ev[slot]));
+			// look at the state of the PREVIOUS point in time (the GPU stays one iteration ahead)
+			UG_GPU_CHECK(ug4b200_event_sync(c, m_ks.ev[slot ^ 1]));
+			done = m_ks.pinned[slot ^ 1].done != 0;
+		}
+		UG_GPU_CHECK(ug4b200_set_guard(c, nullptr));
+		ug4b200_conv_state fin;
+		UG_GPU_CHECK(ug4b200_d2h(c, &fin, m_ks.conv, sizeof(fin)));
+		std::vector<number> hist(fin.step + 1);
+		UG_GPU_CHECK(ug4b200_d2h(c, hist.data(), m_ks.history, sizeof(double) * hist.size()));
+		cc.adopt_device_state(fin, hist);
+		r.set_storage_type(PST_ADDITIVE);
+		if (fin.status == 4) return false; // lambda == 0 breakdown (cg.h:172-184)
+		return cc.post();
+	}
+	void drop_graph()
+	{
+		if (m_graph && GPUManager::ctx_or_null()) ug4b200_graph_destroy(GPUManager::ctx_or_null(), m_graph);
+		m_graph = nullptr;
+	}
+	template <int N, int dummy = 0> struct matrix_value { typedef DenseMatrix<FixedArray2<double, N, N> > type; };
+	template <int dummy> struct matrix_value<1, dummy> { typedef double type; };
+
+	bool m_deviceResident = true, m_useGraph = true;
+	KS m_ks;
+	ug4b200_graph* m_graph = nullptr;
+	const void* m_graphKey[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+/// BiCGStab, reference-shaped loop (bicgstab.h:112-383); vector work on the device, the
+/// handful of scalars per half-step on the host (restart logic needs them there)
+template <typename TVector>
+class BiCGStab : public IPreconditionedLinearOperatorInverse<TVector> {
+  public:
+	typedef TVector vector_type;
+	typedef IPreconditionedLinearOperatorInverse<TVector> base_type;
+	using base_type::convergence_check;
+	using base_type::linear_operator;
+	using base_type::preconditioner;
+
+	BiCGStab() : m_numRestarts(0), m_minOrtho(0.0) {}
+	virtual const char* name() const { return "BiCGStab"; }
+	void set_restart(int numRestarts) { m_numRestarts = numRestarts; }
+	void set_min_orthogonality(number minOrtho) { m_minOrtho = minOrtho; }
+
+	virtual bool apply_return_defect(vector_type& x, vector_type& b)
+	{
+		const bool par = (bool)x.layouts();
+		if (par && (!b.has_storage_type(PST_ADDITIVE) || !x.has_storage_type(PST_CONSISTENT)))
+			UG_THROW("BiCGStab: Inadequate storage format of Vectors.");
+		linear_operator()->apply_sub(b, x);
+		vector_type& r = b;
+		SmartPtr<vector_type> spR = r.clone_without_values(); vector_type& r0 = *spR;
+		SmartPtr<vector_type> spP = r.clone_without_values(); vector_type& p = *spP;
+		SmartPtr<vector_type> spV = r.clone_without_values(); vector_type& v = *spV;
+		SmartPtr<vector_type> spT = r.clone_without_values(); vector_type& t = *spT;
+		SmartPtr<vector_type> spS = r.clone_without_values(); vector_type& s = *spS;
+		SmartPtr<vector_type> spQ = x.clone_without_values(); vector_type& q = *spQ;
+		convergence_check()->start(r);
+		if (par && !r.change_storage_type(PST_UNIQUE)) UG_THROW("BiCGStab: Cannot convert b to unique.");
+		number rho = 1, alpha = 1, omega = 1, norm_r0 = 0.0;
+		bool bRestart = true;
+		while (!convergence_check()->iteration_ended()) {
+			if (m_numRestarts > 0 && (convergence_check()->step() % m_numRestarts == 0)) bRestart = true;
+			if (bRestart) {
+				r0 = r;
+				if (par && !r0.change_storage_type(PST_UNIQUE)) UG_THROW("BiCGStab: Cannot convert r to unique vector.");
+				p = 0.0; alpha = 0.0; p.set_storage_type(r.get_storage_mask());
+				v = 0.0; omega = 1.0; v.set_storage_type(r.get_storage_mask());
+				rho = 1.0;
+				norm_r0 = convergence_check()->defect();
+				bRestart = false;
+			}
+			const number rhoOld = rho;
+			if (!r.size()) rho = 1.0; else rho = r0.dotprod(r);
+			const number norm_r = convergence_check()->defect();
+			if (std::fabs(rho) / (norm_r * norm_r0) <= m_minOrtho) bRestart = true;
+			if (rhoOld == 0.0) return false;
+			const number beta = (rho / rhoOld) * (alpha / omega);
+			VecScaleAdd(p, 1.0, r, beta, p, -beta * omega, v);
+			if (preconditioner()) { if (!preconditioner()->apply(q, p)) return false; }
+			else { q = p; if (par && !q.change_storage_type(PST_CONSISTENT)) UG_THROW("BiCGStab: Cannot convert q to consistent vector."); }
+			linear_operator()->apply(v, q);
+			if (par && !v.change_storage_type(PST_UNIQUE)) UG_THROW("BiCGStab: Cannot convert v to unique vector.");
+			if (!v.size()) alpha = 1.0; else alpha = v.dotprod(r0);
+			if (alpha == 0.0) return false;
+			alpha = rho / alpha;
+			VecScaleAdd(x, 1.0, x, alpha, q);
+			VecScaleAdd(s, 1.0, r, -alpha, v);
+			convergence_check()->update(s);
+			if (convergence_check()->iteration_ended()) { r = s; break; }
+			if (preconditioner()) { if (!preconditioner()->apply(q, s)) return false; }
+			else { q = s; if (par && !q.change_storage_type(PST_CONSISTENT)) UG_THROW("BiCGStab: Cannot convert q to consistent vector."); }
+			linear_operator()->apply(t, q);
+			if (par && !t.change_storage_type(PST_UNIQUE)) UG_THROW("BiCGStab: Cannot convert t to unique vector.");
+			number tt;
+			if (!t.size()) tt = 1.0; else tt = t.dotprod(t);
+			if (!s.size()) omega = 1.0; else omega = s.dotprod(t);
+			if (tt == 0.0) return false;
+			omega = omega / tt;
+			VecScaleAdd(x, 1.0, x, omega, q);
+			VecScaleAdd(r, 1.0, s, -omega, t);
+			convergence_check()->update(r);
+			if (omega == 0.0) return false;
+		}
+		return convergence_check()->post();
+	}
+
+  protected:
+	int m_numRestarts;
+	number m_minOrtho;
+};
+
+/// LinearSolver (linear_solver.h:114-196): x += B(b - A x) until converged
+template <typename TVector>
+class LinearSolver : public IPreconditionedLinearOperatorInverse<TVector> {
+  public:
+	typedef TVector vector_type;
+	typedef IPreconditionedLinearOperatorInverse<TVector> base_type;
+	using base_type::convergence_check;
+	using base_type::linear_operator;
+	using base_type::preconditioner;
+	virtual const char* name() const { return "Iterative Linear Solver"; }
+	virtual bool apply_return_defect(vector_type& x, vector_type& b)
+	{
+		if (x.layouts() && (!b.has_storage_type(PST_ADDITIVE) || !x.has_storage_type(PST_CONSISTENT)))
+			UG_THROW("LinearSolver::apply: Inadequate parallel storage format of Vectors.");
+		vector_type& d = b;
+		linear_operator()->apply_sub(d, x);
+		SmartPtr<vector_type> spC = x.clone_without_values(); vector_type& c = *spC;
+		c.set_storage_type(PST_CONSISTENT);
+		convergence_check()->start(d);
+		while (!convergence_check()->iteration_ended()) {
+			if (preconditioner()) { if (!preconditioner()->apply_update_defect(c, d)) return false; }
+			else { c = d; linear_operator()->apply_sub(d, c); }
+			x += c;
+			convergence_check()->update(d);
+		}
+		return convergence_check()->post();
+	}
+};
+
+/// LU base solver: dense factorisation on the host at init (assembly side), triangular
+/// solves on the device by one CTA (lu.h:122-140, 189-207)
+template <typename TAlgebra>
+class LU : public ILinearOperatorInverse<typename TAlgebra::vector_type> {
+  public:
+	typedef typename TAlgebra::vector_type vector_type;
+	typedef typename TAlgebra::matrix_type matrix_type;
+	typedef MatrixOperator<matrix_type, vector_type> matrix_operator_type;
+	enum { B = TAlgebra::blockSize };
+	LU() {}
+	~LU() { free_dev(); }
+	virtual const char* name() const { return "LU"; }
+	virtual bool supports_parallel() const { return false; }
+	virtual bool init(SmartPtr<ILinearOperator<vector_type> > L)
+	{
+		m_spOperator = std::dynamic_pointer_cast<matrix_operator_type>(L);
+		if (!m_spOperator) UG_THROW("LU::init: Passed operator is not a matrix operator.");
+		return init_lu(m_spOperator->get_matrix());
+	}
+	virtual bool init(SmartPtr<ILinearOperator<vector_type> > J, const vector_type&) { return init(J); }
+	bool init_lu(matrix_type& A)
+	{
+		const size_t nb = A.num_rows();
+		m_size = nb * B;
+		if (m_size == 0) return true;
+		UG_COND_THROW(m_size > 4096, "LU: dense device LU limited to 4096 unknowns, use a CG base solver");
+		const std::vector<int64_t>& rp = A.crs_rowptr(); const std::vector<int>& ci = A.crs_cols(); const std::vector<double>& va = A.crs_vals();
+		const size_t n = m_size; const int BB = B * B;
+		std::vector<double> a(n * n, 0.0); std::vector<int> piv(n, 0);
+#define AA(i, j) a[(size_t)(i) * n + (j)]
+		for (size_t r = 0; r < nb; ++r)
+			for (int64_t p = rp[r]; p < rp[r + 1]; ++p)
+				for (int i = 0; i < B; ++i) for (int j = 0; j < B; ++j) AA(r * B + i, (size_t)ci[p] * B + j) = va[p * BB + i + B * j];
+		// LUDecomp with row interchange (no_lapack/lu_decomp.h:45-75)
+		for (size_t k = 0; k < n; ++k) {
+			size_t biggest = k;
+			for (size_t j = k + 1; j < n; ++j) if (std::fabs(AA(biggest, k)) < std::fabs(AA(j, k))) biggest = j;
+			if (biggest != k) for (size_t j = 0; j < n; ++j) std::swap(AA(k, j), AA(biggest, j));
+			piv[k] = (int)biggest;
+			if (std::fabs(AA(k, k)) < 1e-10) UG_THROW("ERROR in Matrix is singular");
+			for (size_t i = k + 1; i < n; ++i) {
+				AA(i, k) = AA(i, k) / AA(k, k);
+				for (size_t j = k + 1; j < n; ++j) AA(i, j) = AA(i, j) - AA(i, k) * AA(k, j);
+			}
+		}
+#undef AA
+		free_dev();
+		ug4b200_ctx* c = GPUManager::ctx();
+		m_lu = (double*)GPUManager::alloc_bytes(sizeof(double) * n * n);
+		m_piv = (int*)GPUManager::alloc_bytes(sizeof(int) * n);
+		UG_GPU_CHECK(ug4b200_h2d(c, m_lu, a.data(), sizeof(double) * n * n));
+		UG_GPU_CHECK(ug4b200_h2d(c, m_piv, piv.data(), sizeof(int) * n));
+		UG_GPU_CHECK(ug4b200_sync(c));
+		return true;
+	}
+	virtual bool apply(vector_type& u, const vector_type& f)
+	{
+		if (m_size == 0) return true;
+		THROW_IF_NOT_EQUAL(f.len(), m_size);
+		UG_GPU_CHECK(ug4b200_lu_apply(GPUManager::ctx(), (int)m_size, m_lu, m_piv, u.dev(), f.dev()));
+		u.set_storage_type(PST_CONSISTENT);
+		return true;
+	}
+	virtual bool apply_return_defect(vector_type& u, vector_type& f)
+	{
+		if (!apply(u, f)) return false;
+		m_spOperator->apply_sub(f, u);
+		return true;
+	}
+  protected:
+	void free_dev() { GPUManager::free_bytes(m_lu); GPUManager::free_bytes(m_piv); m_lu = nullptr; m_piv = nullptr; }
+	SmartPtr<matrix_operator_type> m_spOperator;
+	size_t m_size = 0;
+	double* m_lu = nullptr;
+	int* m_piv = nullptr;
+};
+
+/// Small on-device CG as base solver (north_star: "coarse-grid solve done as a small
+/// on-device CG"): one CTA runs the whole unpreconditioned CG (cg.h:103-242 with z = r)
+template <typename TAlgebra>
+class CoarseCG : public ILinearOperatorInverse<typename TAlgebra::vector_type> {
+  public:
+	typedef typename TAlgebra::vector_type vector_type;
+	typedef typename TAlgebra::matrix_type matrix_type;
+	typedef MatrixOperator<matrix_type, vector_type> matrix_operator_type;
+	enum { B = TAlgebra::blockSize };
+	~CoarseCG() { if (m_work) GPUManager::release(m_work, m_n * 4); }
+	virtual const char* name() const { return "CoarseCG"; }
+	virtual bool supports_parallel() const { return false; }
+	virtual bool init(SmartPtr<ILinearOperator<vector_type> > L)
+	{
+		m_spOperator = std::dynamic_pointer_cast<matrix_operator_type>(L);
+		if (!m_spOperator) UG_THROW("CoarseCG::init: Passed operator is not a matrix operator.");
+		if (m_work) GPUManager::release(m_work, m_n * 4);
+		m_n = m_spOperator->num_rows() * B;
+		m_work = GPUManager::alloc(m_n * 4);
+		m_spOperator->device();
+		return true;
+	}
+	virtual bool init(SmartPtr<ILinearOperator<vector_type> > J, const vector_type&) { return init(J); }
+	virtual bool apply(vector_type& u, const vector_type& f)
+	{
+		StdConvCheck<vector_type>* cc = dynamic_cast<StdConvCheck<vector_type>*>(this->convergence_check().get());
+		const int maxSteps = cc ? cc->maximum_steps() : 1000;
+		const number minDef = cc ? cc->minimum_defect() : 1e-30, red = cc ? cc->relative_reduction() : 1e-14;
+		UG_GPU_CHECK(ug4b200_coarse_cg(GPUManager::ctx(), m_spOperator->device(), u.dev(), f.dev(), m_work, maxSteps, minDef, red));
+		u.set_storage_type(PST_CONSISTENT);
+		return true;
+	}
+	virtual bool apply_return_defect(vector_type& u, vector_type& f)
+	{
+		if (!apply(u, f)) return false;
+		m_spOperator->apply_sub(f, u);
+		return true;
+	}
+  protected:
+	SmartPtr<matrix_operator_type> m_spOperator;
+	size_t m_n = 0;
+	double* m_work = nullptr;
+};
+
+} // namespace ug

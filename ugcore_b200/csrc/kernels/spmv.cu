@@ -1,0 +1,538 @@
+// spmv.cu — SELL-32 upload and the SpMV family (SparseMatrix<T>::axpy and friends).
+//
+// Reference semantics (paths relative to /root/reference/ugbase):
+//   lib_algebra/cpu_algebra/sparsematrix_impl.h:291-339  axpy (apply / matmul_minus)
+//   lib_algebra/cpu_algebra/sparsematrix_impl.h:271-288  apply_ignore_zero_rows
+//   lib_algebra/cpu_algebra/sparsematrix_impl.h:257-268  mat_mult_add_row
+//   lib_algebra/small_algebra/small_matrix/densematrix_operations.h:56-79 (block MatMult/MatMultAdd)
+// Every row is accumulated by ONE thread in ascending column order with separate
+// multiply and add (-fmad=false), i.e. exactly the CPU operation sequence: results
+// are bit-identical to ugcore's CPUAlgebra / CPUBlockAlgebra<N>.
+//
+// Layout: SELL-32.  A slice is 32 consecutive rows; entry k of lane l of slice s sits
+// at slice_ptr[s] + 32*k + l, so a warp reads 256 contiguous bytes of values and 128
+// contiguous bytes of column indices per k (fully coalesced, streamed with evict-first
+// loads); the x-gather goes through the read-only path and lives in L1/L2.
+// Roofline: HBM.  Algorithmic bytes per launch:
+//   y = A x : 12*nnz + 4*(n+1) + 8*ncols + 8*n      y -= A x : + 8*n
+// Grid: persistent, (#SMs * 8) CTAs of 8 warps striding over the slices.
+#include "../common.cuh"
+#include <algorithm>
+#include <vector>
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+
+enum { MODE_ASSIGN = 0, MODE_ASSIGN_SKIP_EMPTY = 1, MODE_INPLACE = 2, MODE_GENERAL = 3 };
+enum { FUSE_NONE = 0, FUSE_DOT = 1, FUSE_JACOBI = 2 };
+
+struct Sell {
+	const int64_t* slice_ptr; const int* rowlen; const int* cols; const double* vals;
+	int64_t nrows, num_slices;
+};
+struct Fuse {
+	// FUSE_DOT
+	double* partials; unsigned int* counter; ug4b200_fin fin;
+	// FUSE_JACOBI
+	const double* diaginv; double* st_out; double* sc; int flags;
+};
+
+template <int BETAK> __device__ __forceinline__ double mulbeta(double a, double beta)
+{ return BETAK == 1 ? a : (BETAK == -1 ? -a : beta * a); }
+
+// ---------------------------------------------------------------- scalar (block 1)
+template <int BETAK, int MODE, int FUSE>
+__global__ void __launch_bounds__(kThreads)
+spmv1_kernel(Sell A, double* dest, const double* v, double alpha, double beta, const double* __restrict__ w,
+             Fuse fz, const int* guard)
+{
+	if (ug_guarded(guard)) return;
+	const int lane = threadIdx.x & 31;
+	const int64_t gwarp = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+	const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+	double dot = 0.0;
+	for (int64_t s = gwarp; s < A.num_slices; s += nwarps) {
+		const int64_t row = s * 32 + lane;
+		const int len = A.rowlen[row];
+		const int64_t base = A.slice_ptr[s];
+		const int width = (int)((A.slice_ptr[s + 1] - base) >> 5);
+		const double* vp = A.vals + base + lane;
+		const int* cp = A.cols + base + lane;
+		const bool live = row < A.nrows;
+		double acc;
+		int k = 0;
+		if (MODE == MODE_ASSIGN || MODE == MODE_ASSIGN_SKIP_EMPTY) {
+			// MatMult(dest[i], beta, a_0, w[c_0]): first connection assigned, not added
+			acc = 0.0;
+			if (width > 0) {
+				const double a0 = ug_ld_stream(vp); const int c0 = ug_ld_stream(cp);
+				if (len > 0) acc = mulbeta<BETAK>(a0, beta) * __ldg(w + c0);
+			}
+			k = 1;
+		} else if (MODE == MODE_INPLACE) {
+			acc = live ? dest[row] : 0.0;
+		} else {
+			acc = live ? alpha * v[row] : 0.0;
+		}
+		for (; k < width; k += 4) {
+			double a[4]; int c[4]; double x[4];
+#pragma unroll
+			for (int u = 0; u < 4; ++u)
+				if (k + u < width) { a[u] = ug_ld_stream(vp + (int64_t)(k + u) * 32); c[u] = ug_ld_stream(cp + (int64_t)(k + u) * 32); }
+#pragma unroll
+			for (int u = 0; u < 4; ++u)
+				if (k + u < len) x[u] = __ldg(w + c[u]);
+#pragma unroll
+			for (int u = 0; u < 4; ++u)
+				if (k + u < len) acc = acc + mulbeta<BETAK>(a[u], beta) * x[u];
+		}
+		if (FUSE == FUSE_JACOBI) {
+			if (live) {
+				dest[row] = acc;
+				double scv = 0.0;
+				const bool touch_sc = fz.flags & (UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_ADD_OUT);
+				if (touch_sc) scv = fz.sc[row];
+				if (fz.flags & UG4B200_SMOOTH_ADD_IN) scv = scv + w[row];
+				if (fz.flags & UG4B200_SMOOTH_JACOBI) {
+					const double st = fz.diaginv[row] * acc;   // MatMult(c[i], 1.0, diagInv[i], d[i])
+					fz.st_out[row] = st;
+					if (fz.flags & UG4B200_SMOOTH_ADD_OUT) scv = scv + st;
+				}
+				if (touch_sc) fz.sc[row] = scv;
+			}
+		} else {
+			if (live && (MODE != MODE_ASSIGN_SKIP_EMPTY || len > 0)) dest[row] = acc;
+			if (FUSE == FUSE_DOT && live) dot += acc * w[row];
+		}
+	}
+	if (FUSE == FUSE_DOT) ug_block_reduce_fin(dot, fz.partials, fz.counter, fz.fin);
+}
+
+// ---------------------------------------------------------------- block B x B
+// values of entry e: component (r,c) at vals[(e - lane)*B*B + (r + B*c)*32 + lane]
+template <int B, int BETAK, int MODE, int FUSE>
+__global__ void __launch_bounds__(kThreads)
+spmvB_kernel(Sell A, double* dest, const double* v, double alpha, double beta, const double* __restrict__ w,
+             Fuse fz, const int* guard)
+{
+	if (ug_guarded(guard)) return;
+	constexpr int BB = B * B;
+	const int lane = threadIdx.x & 31;
+	const int64_t gwarp = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+	const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+	double dot = 0.0;
+	for (int64_t s = gwarp; s < A.num_slices; s += nwarps) {
+		const int64_t row = s * 32 + lane;
+		const int len = A.rowlen[row];
+		const int64_t base = A.slice_ptr[s];
+		const int width = (int)((A.slice_ptr[s + 1] - base) >> 5);
+		const double* vp = A.vals + base * BB + lane;
+		const int* cp = A.cols + base + lane;
+		const bool live = row < A.nrows;
+		double acc[B];
+		int k = 0;
+		if (MODE == MODE_ASSIGN || MODE == MODE_ASSIGN_SKIP_EMPTY) {
+#pragma unroll
+			for (int r = 0; r < B; ++r) acc[r] = 0.0;
+			if (width > 0 && len > 0) {
+				const int c0 = ug_ld_stream(cp);
+				double x[B];
+#pragma unroll
+				for (int t = 0; t < B; ++t) x[t] = __ldg(w + (int64_t)c0 * B + t);
+#pragma unroll
+				for (int r = 0; r < B; ++r) {
+					acc[r] = mulbeta<BETAK>(ug_ld_stream(vp + (r + B * 0) * 32), beta) * x[0];
+#pragma unroll
+					for (int c = 1; c < B; ++c)
+						acc[r] = acc[r] + mulbeta<BETAK>(ug_ld_stream(vp + (r + B * c) * 32), beta) * x[c];
+				}
+			}
+			k = 1;
+		} else if (MODE == MODE_INPLACE) {
+#pragma unroll
+			for (int r = 0; r < B; ++r) acc[r] = live ? dest[row * B + r] : 0.0;
+		} else {
+#pragma unroll
+			for (int r = 0; r < B; ++r) acc[r] = live ? alpha * v[row * B + r] : 0.0;
+		}
+		for (; k < width; ++k) {
+			if (k < len) {
+				const int c0 = ug_ld_stream(cp + (int64_t)k * 32);
+				const double* ve = vp + (int64_t)k * 32 * BB;
+				double a[BB]; double x[B];
+#pragma unroll
+				for (int q = 0; q < BB; ++q) a[q] = ug_ld_stream(ve + q * 32);
+#pragma unroll
+				for (int t = 0; t < B; ++t) x[t] = __ldg(w + (int64_t)c0 * B + t);
+#pragma unroll
+				for (int r = 0; r < B; ++r)
+#pragma unroll
+					for (int c = 0; c < B; ++c) acc[r] = acc[r] + mulbeta<BETAK>(a[r + B * c], beta) * x[c];
+			}
+		}
+		if (FUSE == FUSE_JACOBI) {
+			if (live) {
+				const bool touch_sc = fz.flags & (UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_ADD_OUT);
+				double scv[B];
+#pragma unroll
+				for (int r = 0; r < B; ++r) {
+					dest[row * B + r] = acc[r];
+					scv[r] = touch_sc ? fz.sc[row * B + r] : 0.0;
+					if (fz.flags & UG4B200_SMOOTH_ADD_IN) scv[r] = scv[r] + w[row * B + r];
+				}
+				if (fz.flags & UG4B200_SMOOTH_JACOBI) {
+					const double* D = fz.diaginv + row * BB;
+#pragma unroll
+					for (int r = 0; r < B; ++r) {
+						double st = D[r] * acc[0];
+#pragma unroll
+						for (int c = 1; c < B; ++c) st = st + D[r + B * c] * acc[c];
+						fz.st_out[row * B + r] = st;
+						if (fz.flags & UG4B200_SMOOTH_ADD_OUT) scv[r] = scv[r] + st;
+					}
+				}
+				if (touch_sc) {
+#pragma unroll
+					for (int r = 0; r < B; ++r) fz.sc[row * B + r] = scv[r];
+				}
+			}
+		} else {
+			if (live && (MODE != MODE_ASSIGN_SKIP_EMPTY || len > 0)) {
+#pragma unroll
+				for (int r = 0; r < B; ++r) dest[row * B + r] = acc[r];
+			}
+			if (FUSE == FUSE_DOT && live) {
+				double l = 0.0;
+#pragma unroll
+				for (int r = 0; r < B; ++r) l += acc[r] * w[row * B + r];
+				dot += l;
+			}
+		}
+	}
+	if (FUSE == FUSE_DOT) ug_block_reduce_fin(dot, fz.partials, fz.counter, fz.fin);
+}
+
+// ------------------------------------------ scalar matrix acting on VB-block vectors
+// (P / R of a block algebra: the scalar sits on the block diagonal, so each component
+// sees the scalar row product; zero off-diagonal terms add exact zeros)
+template <int VB, int BETAK, int MODE>
+__global__ void __launch_bounds__(kThreads)
+spmv1xV_kernel(Sell A, double* dest, const double* v, double alpha, double beta, const double* __restrict__ w,
+               const int* guard)
+{
+	if (ug_guarded(guard)) return;
+	const int lane = threadIdx.x & 31;
+	const int64_t gwarp = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+	const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+	for (int64_t s = gwarp; s < A.num_slices; s += nwarps) {
+		const int64_t row = s * 32 + lane;
+		const int len = A.rowlen[row];
+		const int64_t base = A.slice_ptr[s];
+		const int width = (int)((A.slice_ptr[s + 1] - base) >> 5);
+		const double* vp = A.vals + base + lane;
+		const int* cp = A.cols + base + lane;
+		const bool live = row < A.nrows;
+		double acc[VB];
+		int k = 0;
+		if (MODE == MODE_ASSIGN || MODE == MODE_ASSIGN_SKIP_EMPTY) {
+#pragma unroll
+			for (int t = 0; t < VB; ++t) acc[t] = 0.0;
+			if (width > 0 && len > 0) {
+				const double a0 = mulbeta<BETAK>(ug_ld_stream(vp), beta); const int c0 = ug_ld_stream(cp);
+#pragma unroll
+				for (int t = 0; t < VB; ++t) acc[t] = a0 * __ldg(w + (int64_t)c0 * VB + t);
+			}
+			k = 1;
+		} else if (MODE == MODE_INPLACE) {
+#pragma unroll
+			for (int t = 0; t < VB; ++t) acc[t] = live ? dest[row * VB + t] : 0.0;
+		} else {
+#pragma unroll
+			for (int t = 0; t < VB; ++t) acc[t] = live ? alpha * v[row * VB + t] : 0.0;
+		}
+		for (; k < width; ++k) {
+			if (k < len) {
+				const double a = mulbeta<BETAK>(ug_ld_stream(vp + (int64_t)k * 32), beta);
+				const int c = ug_ld_stream(cp + (int64_t)k * 32);
+#pragma unroll
+				for (int t = 0; t < VB; ++t) acc[t] = acc[t] + a * __ldg(w + (int64_t)c * VB + t);
+			}
+		}
+		if (live && (MODE != MODE_ASSIGN_SKIP_EMPTY || len > 0)) {
+#pragma unroll
+			for (int t = 0; t < VB; ++t) dest[row * VB + t] = acc[t];
+		}
+	}
+}
+
+inline int spmv_grid(const ug4b200_ctx* ctx, int64_t num_slices)
+{
+	int64_t b = (num_slices + kWarps - 1) / kWarps;
+	int64_t cap = (int64_t)ctx->num_sms * 8;
+	if (cap > kMaxReduceBlocks) cap = kMaxReduceBlocks;
+	if (b > cap) b = cap;
+	if (b < 1) b = 1;
+	return (int)b;
+}
+
+inline Sell view(const ug4b200_matrix* A)
+{ return Sell{A->slice_ptr, A->rowlen, A->cols, A->vals, A->nrows, A->num_slices}; }
+
+template <int BETAK, int MODE, int FUSE>
+int launch_mode(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* dest, const double* v, double alpha, double beta,
+                const double* w, int vblock, const Fuse& fz)
+{
+	const int grid = spmv_grid(ctx, A->num_slices);
+	const Sell S = view(A);
+	if (A->block == 1 && vblock == 1) {
+		UG_LAUNCH(ctx, (spmv1_kernel<BETAK, MODE, FUSE>), grid, kThreads, 0, S, dest, v, alpha, beta, w, fz, ctx->guard);
+	} else if (A->block == 1) {
+		if (FUSE != FUSE_NONE) return ug4b200_fail(ctx, UG4B200_ERR_ARG, "fused SpMV needs matrix block == vector block");
+		if (vblock == 2) { UG_LAUNCH(ctx, (spmv1xV_kernel<2, BETAK, MODE>), grid, kThreads, 0, S, dest, v, alpha, beta, w, ctx->guard); }
+		else if (vblock == 3) { UG_LAUNCH(ctx, (spmv1xV_kernel<3, BETAK, MODE>), grid, kThreads, 0, S, dest, v, alpha, beta, w, ctx->guard); }
+		else return ug4b200_fail(ctx, UG4B200_ERR_ARG, "vector block size must be 1, 2 or 3");
+	} else if (A->block == vblock) {
+		if (vblock == 2) { UG_LAUNCH(ctx, (spmvB_kernel<2, BETAK, MODE, FUSE>), grid, kThreads, 0, S, dest, v, alpha, beta, w, fz, ctx->guard); }
+		else if (vblock == 3) { UG_LAUNCH(ctx, (spmvB_kernel<3, BETAK, MODE, FUSE>), grid, kThreads, 0, S, dest, v, alpha, beta, w, fz, ctx->guard); }
+		else return ug4b200_fail(ctx, UG4B200_ERR_ARG, "matrix block size must be 1, 2 or 3");
+	} else return ug4b200_fail(ctx, UG4B200_ERR_ARG, "matrix / vector block size mismatch");
+	return UG4B200_OK;
+}
+
+template <int MODE>
+int launch_beta(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* dest, const double* v, double alpha, double beta,
+                const double* w, int vblock)
+{
+	Fuse fz{};
+	if (beta == 1.0) return launch_mode<1, MODE, FUSE_NONE>(ctx, A, dest, v, alpha, beta, w, vblock, fz);
+	if (beta == -1.0) return launch_mode<-1, MODE, FUSE_NONE>(ctx, A, dest, v, alpha, beta, w, vblock, fz);
+	return launch_mode<0, MODE, FUSE_NONE>(ctx, A, dest, v, alpha, beta, w, vblock, fz);
+}
+
+__global__ void get_diag_kernel(Sell A, const int* __restrict__ diagpos, int B, double* diag)
+{
+	const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (row >= A.nrows) return;
+	const int BB = B * B;
+	const int64_t s = row >> 5; const int lane = (int)(row & 31);
+	const int dp = diagpos[row];
+	for (int q = 0; q < BB; ++q) diag[row * BB + q] = 0.0;
+	if (dp >= 0) {
+		const double* ve = A.vals + (A.slice_ptr[s] + (int64_t)dp * 32) * BB + lane;
+		for (int q = 0; q < BB; ++q) diag[row * BB + q] = ve[q * 32];
+	}
+}
+
+__global__ void jacobi_invert_kernel(int64_t nrows, int B, double invdamp, int block_inverse, const double* diag,
+                                     double* diaginv)
+{
+	const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (row >= nrows) return;
+	const int BB = B * B;
+	double m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+	for (int q = 0; q < BB; ++q) m[q] = diag[row * BB + q];
+	// jacobi.h:210-215: GetDiag (if !block) ; m *= 1./damp ; GetInverse(diagInv, m)
+	if (!block_inverse && B > 1)
+		for (int r = 0; r < B; ++r) for (int c = 0; c < B; ++c) if (r != c) m[r + B * c] = 0.0;
+	for (int q = 0; q < BB; ++q) m[q] = m[q] * invdamp;
+	double* inv = diaginv + row * BB;
+#define MM(r, c) m[(r) + B * (c)]
+#define II(r, c) inv[(r) + B * (c)]
+	if (B == 1) inv[0] = 1.0 / m[0];
+	else if (B == 2) {
+		// GetInverse2, densematrix_inverse.h:96-108
+		double invdet = MM(0,0) * MM(1,1) - MM(1,0) * MM(0,1);
+		if (invdet == 0.0) return;
+		invdet = 1.0 / invdet;
+		II(0,0) = MM(1,1) * invdet; II(1,1) = MM(0,0) * invdet;
+		II(0,1) = MM(0,1) * -invdet; II(1,0) = MM(1,0) * -invdet;
+	} else {
+		// GetDet3 / GetInverse3, densematrix_inverse.h:155-181
+		double invdet = MM(0,0)*MM(1,1)*MM(2,2) + MM(0,1)*MM(1,2)*MM(2,0) + MM(0,2)*MM(1,0)*MM(2,1)
+		              - MM(0,0)*MM(1,2)*MM(2,1) - MM(0,1)*MM(1,0)*MM(2,2) - MM(0,2)*MM(1,1)*MM(2,0);
+		if (invdet == 0.0) return;
+		invdet = 1.0 / invdet;
+		II(0,0) = ( MM(1,1)*MM(2,2) - MM(1,2)*MM(2,1)) * invdet;
+		II(0,1) = (-MM(0,1)*MM(2,2) + MM(0,2)*MM(2,1)) * invdet;
+		II(0,2) = ( MM(0,1)*MM(1,2) - MM(0,2)*MM(1,1)) * invdet;
+		II(1,0) = (-MM(1,0)*MM(2,2) + MM(1,2)*MM(2,0)) * invdet;
+		II(1,1) = ( MM(0,0)*MM(2,2) - MM(0,2)*MM(2,0)) * invdet;
+		II(1,2) = (-MM(0,0)*MM(1,2) + MM(0,2)*MM(1,0)) * invdet;
+		II(2,0) = ( MM(1,0)*MM(2,1) - MM(1,1)*MM(2,0)) * invdet;
+		II(2,1) = (-MM(0,0)*MM(2,1) + MM(0,1)*MM(2,0)) * invdet;
+		II(2,2) = ( MM(0,0)*MM(1,1) - MM(0,1)*MM(1,0)) * invdet;
+	}
+#undef MM
+#undef II
+}
+
+} // namespace
+
+extern "C" {
+
+int ug4b200_matrix_upload_crs(ug4b200_ctx* ctx, int block, int64_t nrows, int64_t ncols, const int64_t* rowptr,
+                              const int* cols, const double* vals, int flags, ug4b200_matrix** out)
+{
+	(void)flags;
+	UG_ARG(ctx, out != nullptr, "out is NULL");
+	*out = nullptr;
+	UG_ARG(ctx, block >= 1 && block <= 3, "block size must be 1, 2 or 3");
+	UG_ARG(ctx, nrows >= 0 && ncols >= 0 && rowptr != nullptr, "bad dimensions");
+	UG_ARG(ctx, ncols < 2147483647LL && nrows < 2147483647LL, "dimensions exceed int32 columns");
+	const int BB = block * block;
+	const int64_t nnz = rowptr[nrows];
+	const int64_t ns = (nrows + 31) / 32;
+	std::vector<int64_t> sp(ns + 1, 0);
+	std::vector<int> rl(ns * 32 > 0 ? ns * 32 : 1, 0), dp(ns * 32 > 0 ? ns * 32 : 1, -1);
+	int maxlen = 0;
+	bool sorted = true, alldiag = (nrows == ncols);
+#pragma omp parallel for schedule(static) reduction(max : maxlen) reduction(&& : sorted, alldiag)
+	for (int64_t s = 0; s < ns; ++s) {
+		int w = 0;
+		for (int l = 0; l < 32; ++l) {
+			const int64_t r = s * 32 + l;
+			if (r >= nrows) break;
+			const int64_t len = rowptr[r + 1] - rowptr[r];
+			rl[r] = (int)len;
+			if (len > w) w = (int)len;
+			bool hasdiag = false;
+			for (int64_t p = rowptr[r]; p < rowptr[r + 1]; ++p) {
+				if (p > rowptr[r] && cols[p] <= cols[p - 1]) sorted = false;
+				if (cols[p] < 0 || cols[p] >= ncols) sorted = false;
+				if (cols[p] == r) { dp[r] = (int)(p - rowptr[r]); hasdiag = true; }
+			}
+			if (!hasdiag) alldiag = false;
+		}
+		sp[s + 1] = (int64_t)w * 32;
+		if (w > maxlen) maxlen = w;
+	}
+	UG_ARG(ctx, sorted, "columns must be sorted ascending inside every row and lie in [0, ncols)");
+	for (int64_t s = 0; s < ns; ++s) sp[s + 1] += sp[s];
+	const int64_t pnnz = sp[ns];
+	std::vector<int> hc((size_t)(pnnz > 0 ? pnnz : 1), 0);
+	std::vector<double> hv((size_t)(pnnz > 0 ? pnnz : 1) * BB, 0.0);
+#pragma omp parallel for schedule(static)
+	for (int64_t s = 0; s < ns; ++s) {
+		const int64_t base = sp[s];
+		for (int l = 0; l < 32; ++l) {
+			const int64_t r = s * 32 + l;
+			if (r >= nrows) break;
+			for (int64_t p = rowptr[r], k = 0; p < rowptr[r + 1]; ++p, ++k) {
+				hc[base + k * 32 + l] = cols[p];
+				for (int q = 0; q < BB; ++q) hv[(base + k * 32) * BB + (int64_t)q * 32 + l] = vals[p * BB + q];
+			}
+		}
+	}
+	ug4b200_matrix* A = new ug4b200_matrix;
+	A->block = block; A->nrows = nrows; A->ncols = ncols; A->nnz = nnz; A->padded_nnz = pnnz; A->num_slices = ns;
+	A->max_row_len = maxlen; A->has_all_diag = alldiag;
+	auto up = [&](void** d, const void* h, size_t bytes) -> int {
+		if (bytes == 0) bytes = 8;
+		cudaError_t e = cudaMalloc(d, bytes);
+		if (e != cudaSuccess) { cudaGetLastError(); return ug4b200_fail(ctx, UG4B200_ERR_NOMEM, "matrix upload: out of device memory"); }
+		A->device_bytes += bytes;
+		e = cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, ctx->stream);
+		if (e != cudaSuccess) return ug4b200_fail(ctx, UG4B200_ERR_CUDA, cudaGetErrorString(e));
+		return 0;
+	};
+	int rc = 0;
+	if (!rc) rc = up((void**)&A->slice_ptr, sp.data(), sizeof(int64_t) * (ns + 1));
+	if (!rc) rc = up((void**)&A->rowlen, rl.data(), sizeof(int) * rl.size());
+	if (!rc) rc = up((void**)&A->diagpos, dp.data(), sizeof(int) * dp.size());
+	if (!rc) rc = up((void**)&A->cols, hc.data(), sizeof(int) * hc.size());
+	if (!rc) rc = up((void**)&A->vals, hv.data(), sizeof(double) * hv.size());
+	if (rc) { ug4b200_matrix_destroy(ctx, A); return rc; }
+	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // host staging buffers die here
+	*out = A;
+	return UG4B200_OK;
+}
+
+int ug4b200_matrix_destroy(ug4b200_ctx* ctx, ug4b200_matrix* A)
+{
+	if (!A) return UG4B200_OK;
+	if (ctx) cudaStreamSynchronize(ctx->stream);
+	cudaFree(A->slice_ptr); cudaFree(A->rowlen); cudaFree(A->diagpos); cudaFree(A->cols); cudaFree(A->vals);
+	delete A;
+	return UG4B200_OK;
+}
+
+int ug4b200_matrix_get_info(const ug4b200_matrix* A, ug4b200_matrix_info* info)
+{
+	info->nrows = A->nrows; info->ncols = A->ncols; info->nnz = A->nnz; info->padded_nnz = A->padded_nnz;
+	info->num_slices = A->num_slices; info->device_bytes = (int64_t)A->device_bytes; info->block = A->block;
+	info->max_row_len = A->max_row_len;
+	return UG4B200_OK;
+}
+
+int ug4b200_matrix_axpy(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* dest, double alpha, const double* v,
+                        double beta, const double* w, int vblock)
+{
+	UG_ARG(ctx, A && dest && w, "NULL argument");
+	UG_ARG(ctx, dest != w, "dest must not alias w");
+	if (alpha == 0.0) return launch_beta<MODE_ASSIGN>(ctx, A, dest, v, alpha, beta, w, vblock);
+	UG_ARG(ctx, v != nullptr, "v is NULL with alpha != 0");
+	if (v == dest && alpha == 1.0) return launch_beta<MODE_INPLACE>(ctx, A, dest, v, alpha, beta, w, vblock);
+	// dest == v with alpha != 1: dest[i] *= alpha, then accumulate == general branch read of v[i]
+	return launch_beta<MODE_GENERAL>(ctx, A, dest, v, alpha, beta, w, vblock);
+}
+int ug4b200_matrix_apply(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* y, const double* x, int vblock)
+{ return ug4b200_matrix_axpy(ctx, A, y, 0.0, nullptr, 1.0, x, vblock); }
+int ug4b200_matrix_matmul_minus(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* y, const double* x, int vblock)
+{ return ug4b200_matrix_axpy(ctx, A, y, 1.0, y, -1.0, x, vblock); }
+int ug4b200_matrix_apply_ignore_zero_rows(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* dest, double beta,
+                                          const double* w, int vblock)
+{
+	UG_ARG(ctx, A && dest && w && dest != w, "bad argument");
+	return launch_beta<MODE_ASSIGN_SKIP_EMPTY>(ctx, A, dest, nullptr, 0.0, beta, w, vblock);
+}
+int ug4b200_matrix_apply_dot_ds(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* y, const double* x, ug4b200_fin fin)
+{
+	UG_ARG(ctx, A && y && x && y != x, "bad argument");
+	UG_ARG(ctx, A->nrows == A->ncols, "apply_dot needs a square matrix");
+	Fuse fz{}; fz.partials = ctx->partials; fz.counter = ctx->counter; fz.fin = fin;
+	return launch_mode<1, MODE_ASSIGN, FUSE_DOT>(ctx, A, y, nullptr, 0.0, 1.0, x, A->block, fz);
+}
+int ug4b200_jacobi_smooth_fused(ug4b200_ctx* ctx, const ug4b200_matrix* A, const double* diaginv, double* sd,
+                                const double* st_in, double* st_out, double* sc, int flags)
+{
+	UG_ARG(ctx, A && sd && st_in, "NULL argument");
+	UG_ARG(ctx, A->nrows == A->ncols, "square matrix needed");
+	UG_ARG(ctx, !(flags & UG4B200_SMOOTH_JACOBI) || (diaginv && st_out), "JACOBI needs diaginv and st_out");
+	UG_ARG(ctx, !(flags & (UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_ADD_OUT)) || sc, "ADD_* needs sc");
+	UG_ARG(ctx, st_in != st_out && sd != st_in && sc != st_in, "st_in must not alias an output");
+	Fuse fz{}; fz.diaginv = diaginv; fz.st_out = st_out; fz.sc = sc; fz.flags = flags;
+	return launch_mode<-1, MODE_INPLACE, FUSE_JACOBI>(ctx, A, sd, sd, 1.0, -1.0, st_in, A->block, fz);
+}
+
+int ug4b200_jacobi_prepare(ug4b200_ctx* ctx, const ug4b200_matrix* A, double damp, int block_inverse, double* diaginv)
+{
+	UG_ARG(ctx, A && diaginv, "NULL argument");
+	UG_ARG(ctx, A->nrows == A->ncols, "Square Matrix needed for Jacobi Iteration.");
+	if (A->nrows == 0) return UG4B200_OK;
+	// diaginv doubles as scratch for the extracted diagonal (each thread reads its block before writing it)
+	int rc = ug4b200_matrix_get_diag(ctx, A, diaginv);
+	if (rc) return rc;
+	return ug4b200_jacobi_invert_diag(ctx, A->nrows, A->block, damp, block_inverse, diaginv, diaginv);
+}
+
+int ug4b200_matrix_get_diag(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* diag)
+{
+	UG_ARG(ctx, A && diag, "NULL argument");
+	UG_ARG(ctx, A->nrows == A->ncols, "square matrix needed");
+	if (A->nrows == 0) return UG4B200_OK;
+	UG_LAUNCH(ctx, get_diag_kernel, (int)((A->nrows + 255) / 256), 256, 0, view(A), A->diagpos, A->block, diag);
+	return UG4B200_OK;
+}
+
+int ug4b200_jacobi_invert_diag(ug4b200_ctx* ctx, int64_t nrows, int block, double damp, int block_inverse,
+                               const double* diag, double* diaginv)
+{
+	UG_ARG(ctx, diag && diaginv && block >= 1 && block <= 3, "bad argument");
+	if (nrows <= 0) return UG4B200_OK;
+	UG_LAUNCH(ctx, jacobi_invert_kernel, (int)((nrows + 255) / 256), 256, 0, nrows, block, 1. / damp, block_inverse, diag, diaginv);
+	return UG4B200_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,251 @@
+// solver_capi.cpp — descriptor-level C ABI (include/ug4b200_solver.h) over the host-side
+// mirror of ugcore's operator API.  Plays the role of util.solver.CreateSolver /
+// SolveLinearProblem (scripts/util/solver_util.lua:602, :1182-1210) for non-Lua callers.
+#include "../../include/ug4b200_solver.h"
+#include "host/multigrid.h"
+#include <cstring>
+
+using namespace ug;
+
+namespace {
+thread_local std::string g_err;
+
+struct SolverBase {
+	virtual ~SolverBase() {}
+	virtual void set_matrix(int64_t nr, int64_t nc, const int64_t* rp, const int* ci, const double* va) = 0;
+	virtual void set_level(int lev, int64_t nrows, const int64_t* rp, const int* ci, const double* va, int64_t ncoarse,
+	                       const int64_t* prp, const int* pci, const double* pva, const int64_t* rrp, const int* rci,
+	                       const double* rva) = 0;
+	virtual void set_coloring(int lev, int64_t n, const int* perm, int ncolors, const int64_t* cp) = 0;
+	virtual void set_layouts(int lev, int nneigh, const int* ranks, const int64_t* ptr, const int* idx, int64_t nlocal) = 0;
+	virtual void set_gathered_base(int64_t nrows, const int64_t* rp, const int* ci, const double* va, int64_t nlocal, const int* l2g) = 0;
+	virtual void init() = 0;
+	virtual int apply_host(double* x, const double* b) = 0;
+	virtual int apply_device(double* x, const double* b) = 0;
+	virtual void precond_apply(double* c, const double* d) = 0;
+	virtual int64_t num_dofs() const = 0;
+	std::vector<double> history;
+	int steps = 0;
+	double defect = 0;
+};
+
+template <typename TAlgebra>
+struct SolverImpl : SolverBase {
+	typedef typename TAlgebra::vector_type vector_type;
+	typedef typename TAlgebra::matrix_type matrix_type;
+	typedef MatrixOperator<matrix_type, vector_type> matop_t;
+	enum { B = TAlgebra::blockSize };
+
+	ug4b200_solver_desc d;
+	SmartPtr<matop_t> A;
+	SmartPtr<ILinearOperatorInverse<vector_type> > inv;
+	SmartPtr<ILinearIterator<vector_type> > precond;
+	SmartPtr<AssembledMultiGridCycle<TAlgebra> > gmg;
+	SmartPtr<StdConvCheck<vector_type> > conv;
+	std::map<int, std::pair<std::vector<int>, std::vector<int64_t> > > coloring;
+	std::map<int, SmartPtr<GPUAlgebraLayouts> > layouts;
+	vector_type x, b;
+
+	explicit SolverImpl(const ug4b200_solver_desc& desc) : d(desc)
+	{
+		conv = make_sp<StdConvCheck<vector_type> >(d.max_steps, d.min_defect, d.rel_reduction, false);
+		if (d.precond == UG4B200_PRECOND_GMG) {
+			gmg = make_sp<AssembledMultiGridCycle<TAlgebra> >();
+			gmg->set_base_level(d.base_lev); gmg->set_surface_level(d.top_lev);
+			gmg->set_cycle_type(d.cycle); gmg->set_num_presmooth(d.nu1); gmg->set_num_postsmooth(d.nu2);
+			gmg->set_smoother(make_smoother(d.smoother, d.smoother_damp));
+			gmg->set_fuse_jacobi(!(d.flags & UG4B200_FLAG_NO_FUSED_JACOBI));
+			gmg->set_compute_final_level_defect((d.flags & UG4B200_FLAG_FINAL_LEVEL_DEFECT) != 0);
+			if (d.base_solver == UG4B200_SOLVER_LU) gmg->set_base_solver(make_sp<LU<TAlgebra> >());
+			else if (d.base_solver == UG4B200_SOLVER_COARSE_CG || d.base_solver == UG4B200_SOLVER_CG) {
+				SmartPtr<CoarseCG<TAlgebra> > cg = make_sp<CoarseCG<TAlgebra> >();
+				cg->set_convergence_check(make_sp<StdConvCheck<vector_type> >(d.base_max_steps, d.base_min_defect, d.base_rel_reduction, false));
+				gmg->set_base_solver(cg);
+			} else UG_THROW("unsupported base solver " << d.base_solver);
+			precond = gmg;
+		} else if (d.precond != UG4B200_PRECOND_NONE) precond = make_smoother(d.precond, d.damp);
+		switch (d.solver) {
+			case UG4B200_SOLVER_CG: {
+				SmartPtr<CG<vector_type> > s = make_sp<CG<vector_type> >();
+				s->set_device_resident(!(d.flags & UG4B200_FLAG_HOST_SCALARS));
+				s->set_use_graph(!(d.flags & UG4B200_FLAG_NO_GRAPH));
+				s->set_preconditioner(precond); inv = s; break;
+			}
+			case UG4B200_SOLVER_BICGSTAB: { SmartPtr<BiCGStab<vector_type> > s = make_sp<BiCGStab<vector_type> >(); s->set_preconditioner(precond); inv = s; break; }
+			case UG4B200_SOLVER_LINEAR: { SmartPtr<LinearSolver<vector_type> > s = make_sp<LinearSolver<vector_type> >(); s->set_preconditioner(precond); inv = s; break; }
+			case UG4B200_SOLVER_LU: inv = make_sp<LU<TAlgebra> >(); break;
+			case UG4B200_SOLVER_COARSE_CG: inv = make_sp<CoarseCG<TAlgebra> >(); break;
+			default: UG_THROW("unknown solver " << d.solver);
+		}
+		inv->set_convergence_check(conv);
+	}
+
+	SmartPtr<ILinearIterator<vector_type> > make_smoother(int kind, double damp)
+	{
+		switch (kind) {
+			case UG4B200_PRECOND_JACOBI: return make_sp<Jacobi<TAlgebra> >(damp);
+			case UG4B200_PRECOND_GS: { SmartPtr<GaussSeidel<TAlgebra> > g = make_sp<GaussSeidel<TAlgebra> >(); g->set_sor_relax(damp); return g; }
+			case UG4B200_PRECOND_BGS: { SmartPtr<BackwardGaussSeidel<TAlgebra> > g = make_sp<BackwardGaussSeidel<TAlgebra> >(); g->set_sor_relax(damp); return g; }
+			case UG4B200_PRECOND_SGS: { SmartPtr<SymmetricGaussSeidel<TAlgebra> > g = make_sp<SymmetricGaussSeidel<TAlgebra> >(); g->set_sor_relax(damp); return g; }
+		}
+		UG_THROW("unknown smoother / preconditioner kind " << kind);
+	}
+
+	void set_matrix(int64_t nr, int64_t nc, const int64_t* rp, const int* ci, const double* va) override
+	{
+		A = make_sp<matop_t>();
+		A->set_from_crs((size_t)nr, (size_t)nc, rp, ci, va);
+	}
+	void set_level(int lev, int64_t nrows, const int64_t* rp, const int* ci, const double* va, int64_t ncoarse,
+	               const int64_t* prp, const int* pci, const double* pva, const int64_t* rrp, const int* rci,
+	               const double* rva) override
+	{
+		if (!gmg) UG_THROW("solver has no GMG preconditioner");
+		if (rp) {
+			SmartPtr<matop_t> Al = make_sp<matop_t>();
+			Al->set_from_crs((size_t)nrows, (size_t)nrows, rp, ci, va);
+			gmg->set_level_operator(lev, Al);
+		}
+		if (prp) {
+			SmartPtr<GPUTransferMatrix> P = make_sp<GPUTransferMatrix>(), R;
+			P->set_from_crs((size_t)nrows, (size_t)ncoarse, prp, pci, pva);
+			if (rrp) { R = make_sp<GPUTransferMatrix>(); R->set_from_crs((size_t)ncoarse, (size_t)nrows, rrp, rci, rva); }
+			gmg->set_level_transfer(lev, P, R);
+		}
+	}
+	void set_coloring(int lev, int64_t n, const int* perm, int ncolors, const int64_t* cp) override
+	{
+		coloring[lev] = std::make_pair(std::vector<int>(perm, perm + n), std::vector<int64_t>(cp, cp + ncolors + 1));
+		if (lev >= 0) UG_THROW("per-level colourings: greedy colouring is used inside GMG this round");
+		GaussSeidelBase<TAlgebra>* g = dynamic_cast<GaussSeidelBase<TAlgebra>*>(precond.get());
+		if (!g) UG_THROW("set_coloring: preconditioner is not a Gauss-Seidel sweep");
+		g->set_coloring(coloring[lev].first, coloring[lev].second);
+	}
+	void set_layouts(int lev, int nneigh, const int* ranks, const int64_t* ptr, const int* idx, int64_t nlocal) override
+	{
+		SmartPtr<GPUAlgebraLayouts> l = make_sp<GPUAlgebraLayouts>(nneigh, ranks, ptr, idx, nlocal);
+		layouts[lev] = l;
+		if (gmg) gmg->set_level_layouts(lev, l);
+	}
+	void set_gathered_base(int64_t nrows, const int64_t* rp, const int* ci, const double* va, int64_t nlocal, const int* l2g) override
+	{
+		if (!gmg) UG_THROW("solver has no GMG preconditioner");
+		SmartPtr<matop_t> G = make_sp<matop_t>();
+		G->set_from_crs((size_t)nrows, (size_t)nrows, rp, ci, va);
+		gmg->set_gathered_base(G, std::vector<int>(l2g, l2g + nlocal));
+	}
+	SmartPtr<GPUAlgebraLayouts> top_layouts()
+	{
+		if (layouts.empty()) return SmartPtr<GPUAlgebraLayouts>();
+		return layouts.rbegin()->second;
+	}
+	void init() override
+	{
+		if (!A) UG_THROW("solver: matrix not set");
+		Jacobi<TAlgebra>* j = dynamic_cast<Jacobi<TAlgebra>*>(precond.get());
+		if (j) j->set_layouts(top_layouts());
+		x.create(A->num_cols()); b.create(A->num_rows());
+		x.set_layouts(top_layouts()); b.set_layouts(top_layouts());
+		if (!inv->init(A, x)) UG_THROW("solver init failed");
+		if (d.solver == UG4B200_SOLVER_LU || d.solver == UG4B200_SOLVER_COARSE_CG) {
+			if (precond && !precond->init(A, x)) UG_THROW("preconditioner init failed");
+		}
+	}
+	int finish(bool ok)
+	{
+		steps = conv->step(); defect = conv->defect(); history = conv->get_defects();
+		return ok ? 0 : 1;
+	}
+	int apply_host(double* xh, const double* bh) override
+	{
+		ug4b200_ctx* c = GPUManager::ctx();
+		UG_GPU_CHECK(ug4b200_h2d(c, x.dev(), xh, x.len() * sizeof(double)));
+		UG_GPU_CHECK(ug4b200_h2d(c, b.dev(), bh, b.len() * sizeof(double)));
+		x.set_storage_type(PST_CONSISTENT); b.set_storage_type(PST_ADDITIVE);
+		const bool ok = inv->apply(x, b);
+		UG_GPU_CHECK(ug4b200_d2h(c, xh, x.dev(), x.len() * sizeof(double)));
+		return finish(ok);
+	}
+	int apply_device(double* xd, const double* bd) override
+	{
+		ug4b200_ctx* c = GPUManager::ctx();
+		UG_GPU_CHECK(ug4b200_vec_copy(c, x.len(), x.dev(), xd));
+		UG_GPU_CHECK(ug4b200_vec_copy(c, b.len(), b.dev(), bd));
+		x.set_storage_type(PST_CONSISTENT); b.set_storage_type(PST_ADDITIVE);
+		const bool ok = inv->apply(x, b);
+		UG_GPU_CHECK(ug4b200_vec_copy(c, x.len(), xd, x.dev()));
+		return finish(ok);
+	}
+	void precond_apply(double* ch, const double* dh) override
+	{
+		if (!precond) UG_THROW("no preconditioner configured");
+		ug4b200_ctx* c = GPUManager::ctx();
+		UG_GPU_CHECK(ug4b200_h2d(c, b.dev(), dh, b.len() * sizeof(double)));
+		b.set_storage_type(PST_ADDITIVE);
+		if (!precond->apply(x, b)) UG_THROW("preconditioner apply failed");
+		UG_GPU_CHECK(ug4b200_d2h(c, ch, x.dev(), x.len() * sizeof(double)));
+	}
+	int64_t num_dofs() const override { return A ? (int64_t)A->num_rows() * B : 0; }
+};
+
+template <class F> int guard(F f)
+{
+	try { return f(); }
+	catch (const std::exception& e) { g_err = e.what(); return -1; }
+	catch (...) { g_err = "unknown exception"; return -1; }
+}
+} // namespace
+
+struct ug4b200_solver { std::unique_ptr<SolverBase> p; };
+
+extern "C" {
+
+int ug4b200_host_init(int device, void* stream) { return guard([&] { GPUManager::init(device, stream); return 0; }); }
+int ug4b200_host_finalize(void) { return guard([&] { GPUManager::finalize(); return 0; }); }
+ug4b200_ctx* ug4b200_host_ctx(void) { return GPUManager::ctx_or_null(); }
+const char* ug4b200_host_last_error(void) { return g_err.c_str(); }
+int ug4b200_host_comm_init(int nranks, int rank, const unsigned char id[UG4B200_NCCL_ID_BYTES])
+{ return guard([&] { UG_GPU_CHECK(ug4b200_comm_init(GPUManager::ctx(), nranks, rank, id)); return 0; }); }
+
+int ug4b200_solver_create(const ug4b200_solver_desc* d, ug4b200_solver** out)
+{
+	*out = nullptr;
+	return guard([&] {
+		std::unique_ptr<ug4b200_solver> s(new ug4b200_solver);
+		if (d->block == 1) s->p.reset(new SolverImpl<GPUAlgebra>(*d));
+		else if (d->block == 2) s->p.reset(new SolverImpl<GPUBlockAlgebra<2> >(*d));
+		else if (d->block == 3) s->p.reset(new SolverImpl<GPUBlockAlgebra<3> >(*d));
+		else UG_THROW("block size must be 1, 2 or 3");
+		*out = s.release();
+		return 0;
+	});
+}
+int ug4b200_solver_destroy(ug4b200_solver* s) { return guard([&] { delete s; return 0; }); }
+int ug4b200_solver_set_matrix(ug4b200_solver* s, int64_t nrows, int64_t ncols, const int64_t* rowptr, const int* cols, const double* vals)
+{ return guard([&] { s->p->set_matrix(nrows, ncols, rowptr, cols, vals); return 0; }); }
+int ug4b200_solver_set_level(ug4b200_solver* s, int lev, int64_t nrows, const int64_t* rowptr, const int* cols, const double* vals,
+                             int64_t ncoarse, const int64_t* p_rowptr, const int* p_cols, const double* p_vals,
+                             const int64_t* r_rowptr, const int* r_cols, const double* r_vals)
+{ return guard([&] { s->p->set_level(lev, nrows, rowptr, cols, vals, ncoarse, p_rowptr, p_cols, p_vals, r_rowptr, r_cols, r_vals); return 0; }); }
+int ug4b200_solver_set_coloring(ug4b200_solver* s, int lev, int64_t n, const int* perm, int ncolors, const int64_t* color_ptr)
+{ return guard([&] { s->p->set_coloring(lev, n, perm, ncolors, color_ptr); return 0; }); }
+int ug4b200_solver_set_layouts(ug4b200_solver* s, int lev, int nneigh, const int* neigh_rank, const int64_t* neigh_ptr, const int* indices, int64_t nlocal)
+{ return guard([&] { s->p->set_layouts(lev, nneigh, neigh_rank, neigh_ptr, indices, nlocal); return 0; }); }
+int ug4b200_solver_set_gathered_base(ug4b200_solver* s, int64_t nrows, const int64_t* rowptr, const int* cols, const double* vals,
+                                     int64_t nlocal, const int* local_to_global)
+{ return guard([&] { s->p->set_gathered_base(nrows, rowptr, cols, vals, nlocal, local_to_global); return 0; }); }
+int ug4b200_solver_init(ug4b200_solver* s) { return guard([&] { s->p->init(); return 0; }); }
+int ug4b200_solver_apply(ug4b200_solver* s, double* x_host, const double* b_host) { return guard([&] { return s->p->apply_host(x_host, b_host); }); }
+int ug4b200_solver_apply_device(ug4b200_solver* s, double* x_dev, const double* b_dev) { return guard([&] { return s->p->apply_device(x_dev, b_dev); }); }
+int ug4b200_solver_steps(const ug4b200_solver* s) { return s->p->steps; }
+double ug4b200_solver_defect(const ug4b200_solver* s) { return s->p->defect; }
+int ug4b200_solver_history(const ug4b200_solver* s, double* out, int cap)
+{
+	const int n = (int)s->p->history.size() < cap ? (int)s->p->history.size() : cap;
+	for (int i = 0; i < n; ++i) out[i] = s->p->history[i];
+	return n;
+}
+int ug4b200_solver_precond_apply(ug4b200_solver* s, double* c_host, const double* d_host) { return guard([&] { s->p->precond_apply(c_host, d_host); return 0; }); }
+int64_t ug4b200_solver_num_dofs(const ug4b200_solver* s) { return s->p->num_dofs(); }
+
+} // extern "C"

@@ -53,6 +53,7 @@ class Crs:
     rowptr: np.ndarray  # int64 [nrows+1]
     cols: np.ndarray    # int32 [nnz]
     vals: np.ndarray    # float64 [nnz*block*block], column-major inside a block
+    owner: object = None  # keeps the generator (owner of the memory) alive
 
     @property
     def nnz(self):
@@ -103,7 +104,7 @@ class Problem:
         return Crs(c.nrows, c.ncols, c.block,
                    as_arr(c.rowptr, (c.nrows + 1,)),
                    as_arr(c.cols, (c.nnz,)) if c.nnz else np.zeros(0, np.int32),
-                   as_arr(c.vals, (c.nnz * c.block * c.block,)) if c.nnz else np.zeros(0))
+                   as_arr(c.vals, (c.nnz * c.block * c.block,)) if c.nnz else np.zeros(0), self)
 
     def matrix(self, lev=None) -> Crs:
         return self._crs(_load().synth_level_matrix, self.num_refs if lev is None else lev)

@@ -1,0 +1,245 @@
+"""Python face of the descriptor-level driver (include/ug4b200_solver.h).
+
+``Solver(desc, problem)`` is what ``util.solver.CreateSolver(desc)`` followed by
+``solver:init(A, u)`` is in a ugcore Lua script (scripts/util/solver_util.lua:602,
+:1182-1210); ``solver.apply(b)`` is ``solver:apply(u, b)``.  The descriptor uses the same
+vocabulary as solver_util.lua (type, precond, smoother, cycle, preSmooth, postSmooth,
+baseLevel, baseSolver, convCheck{iterations, absolute, reduction}).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import check, check_host, host, dev
+
+SOLVER = {"cg": 0, "bicgstab": 1, "linear": 2, "lu": 3, "coarse_cg": 4}
+PRECOND = {None: 0, "none": 0, "jac": 1, "jacobi": 1, "gs": 2, "bgs": 3, "sgs": 4, "gmg": 5}
+
+_host_ready = False
+
+
+def device_available() -> bool:
+    """True if a CUDA device can be opened (never falls back to the CPU)."""
+    ctx = C.c_void_p()
+    rc = dev.ug4b200_ctx_create(0, None, C.byref(ctx))
+    if rc == 0:
+        dev.ug4b200_ctx_destroy(ctx)
+    return rc == 0
+
+
+def host_init(device: int = -1, stream=None) -> None:
+    """Create the process-wide device context (GPUManager). One process per GPU."""
+    global _host_ready
+    if not _host_ready:
+        check_host(host.ug4b200_host_init(device, stream))
+        _host_ready = True
+
+
+def host_ctx():
+    host_init()
+    return host.ug4b200_host_ctx()
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def make_desc(desc: dict, block: int = 1, flags: int = 0) -> capi.SolverDesc:
+    d = capi.SolverDesc()
+    d.block = block
+    d.solver = SOLVER[desc.get("type", "cg")]
+    cc = desc.get("convCheck", {})
+    d.max_steps = cc.get("iterations", 100)
+    d.min_defect = cc.get("absolute", 1e-12)
+    d.rel_reduction = cc.get("reduction", 1e-6)
+    pc = desc.get("precond")
+    if isinstance(pc, str):
+        pc = {"type": pc}
+    d.precond = PRECOND[pc["type"] if pc else None]
+    d.damp = 1.0
+    d.cycle, d.nu1, d.nu2 = 1, 2, 2
+    d.smoother, d.smoother_damp = 1, 0.66
+    d.base_solver, d.base_max_steps, d.base_min_defect, d.base_rel_reduction = 3, 1000, 1e-30, 1e-14
+    if pc:
+        if pc["type"] in ("jac", "jacobi"):
+            d.damp = pc.get("damp", 0.66)
+        elif pc["type"] in ("gs", "bgs", "sgs"):
+            d.damp = pc.get("relax", 1.0)
+        elif pc["type"] == "gmg":
+            sm = pc.get("smoother", {"type": "jac", "damp": 0.66})
+            if isinstance(sm, str):
+                sm = {"type": sm}
+            d.smoother = PRECOND[sm["type"]]
+            d.smoother_damp = sm.get("damp", 0.66) if d.smoother == 1 else sm.get("relax", 1.0)
+            d.cycle = {"V": 1, "W": 2, "F": -1}[pc.get("cycle", "V")]
+            d.nu1 = pc.get("preSmooth", 2)
+            d.nu2 = pc.get("postSmooth", 2)
+            d.base_lev = pc.get("baseLevel", 0)
+            d.top_lev = pc["topLevel"]
+            bs = pc.get("baseSolver", "lu")
+            if isinstance(bs, str):
+                bs = {"type": bs}
+            d.base_solver = {"lu": 3, "cg": 4, "coarse_cg": 4}[bs["type"]]
+            bcc = bs.get("convCheck", {})
+            d.base_max_steps = bcc.get("iterations", 1000)
+            d.base_min_defect = bcc.get("absolute", 1e-30)
+            d.base_rel_reduction = bcc.get("reduction", 1e-14)
+    d.flags = flags | desc.get("flags", 0)
+    return d
+
+
+class DeviceBuffer:
+    """A device array of doubles owned by the host layer's context."""
+
+    def __init__(self, n: int):
+        self.ctx = host_ctx()
+        self.n = int(n)
+        p = C.c_void_p()
+        check(dev.ug4b200_alloc(self.ctx, max(self.n, 1) * 8, C.byref(p)), self.ctx)
+        self.ptr = p
+
+    @classmethod
+    def from_numpy(cls, a) -> "DeviceBuffer":
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        b = cls(a.size)
+        check(dev.ug4b200_h2d(b.ctx, b.ptr, _ptr(a), a.size * 8), b.ctx)
+        check(dev.ug4b200_sync(b.ctx), b.ctx)
+        return b
+
+    def to_numpy(self):
+        a = np.empty(self.n)
+        check(dev.ug4b200_d2h(self.ctx, _ptr(a), self.ptr, self.n * 8), self.ctx)
+        return a
+
+    def __del__(self):
+        try:
+            dev.ug4b200_free(self.ctx, self.ptr)
+        except Exception:
+            pass
+
+
+class Solver:
+    """CG / BiCGStab / LinearSolver with Jacobi / GS / GMG preconditioning on the GPU.
+
+    ``A`` is a host CRS (``problems.Crs``); ``levels`` maps level -> (A_l, P_l, R_l) for GMG
+    (P_l, R_l None on the base level).  ``Solver.from_problem`` wires a synthetic hierarchy.
+    """
+
+    def __init__(self, desc: dict, A, levels: dict | None = None, flags: int = 0):
+        host_init()
+        self.block = A.block
+        self.desc = make_desc(desc, self.block, flags)
+        self.h = C.c_void_p()
+        check_host(host.ug4b200_solver_create(C.byref(self.desc), C.byref(self.h)))
+        self.n = A.nrows * A.block
+        self._keep = [A, levels]
+        check_host(host.ug4b200_solver_set_matrix(self.h, A.nrows, A.ncols, _ptr(A.rowptr), _ptr(A.cols), _ptr(A.vals)))
+        if levels:
+            for lev, (Al, Pl, Rl) in sorted(levels.items()):
+                top = lev == self.desc.top_lev
+                check_host(host.ug4b200_solver_set_level(
+                    self.h, lev, Al.nrows,
+                    None if top else _ptr(Al.rowptr), None if top else _ptr(Al.cols), None if top else _ptr(Al.vals),
+                    Pl.ncols if Pl else 0,
+                    _ptr(Pl.rowptr) if Pl else None, _ptr(Pl.cols) if Pl else None, _ptr(Pl.vals) if Pl else None,
+                    _ptr(Rl.rowptr) if Rl else None, _ptr(Rl.cols) if Rl else None, _ptr(Rl.vals) if Rl else None))
+        self._inited = False
+
+    @classmethod
+    def from_problem(cls, desc: dict, prob, flags: int = 0) -> "Solver":
+        desc = dict(desc)
+        pc = desc.get("precond")
+        levels = None
+        if isinstance(pc, dict) and pc.get("type") == "gmg":
+            pc = dict(pc)
+            pc.setdefault("topLevel", prob.num_refs)
+            pc.setdefault("baseLevel", prob.base_lev)
+            desc["precond"] = pc
+            levels = {}
+            for lev in range(pc["baseLevel"], pc["topLevel"] + 1):
+                base = lev == pc["baseLevel"]
+                levels[lev] = (prob.matrix(lev), None if base else prob.prolongation(lev),
+                               None if base else prob.restriction(lev))
+        s = cls(desc, prob.matrix(desc["precond"]["topLevel"] if levels else None), levels, flags)
+        s._keep.append(prob)
+        return s
+
+    def set_coloring(self, perm, color_ptr, lev: int = -1):
+        perm = np.ascontiguousarray(perm, dtype=np.int32)
+        cp = np.ascontiguousarray(color_ptr, dtype=np.int64)
+        check_host(host.ug4b200_solver_set_coloring(self.h, lev, perm.size, _ptr(perm), cp.size - 1, _ptr(cp)))
+
+    def set_layouts(self, lev, neigh_rank, neigh_ptr, indices, nlocal):
+        nr = np.ascontiguousarray(neigh_rank, dtype=np.int32)
+        npt = np.ascontiguousarray(neigh_ptr, dtype=np.int64)
+        idx = np.ascontiguousarray(indices, dtype=np.int32)
+        check_host(host.ug4b200_solver_set_layouts(self.h, lev, nr.size, _ptr(nr), _ptr(npt), _ptr(idx), nlocal))
+
+    def set_gathered_base(self, Aglobal, local_to_global):
+        l2g = np.ascontiguousarray(local_to_global, dtype=np.int32)
+        self._keep.append(Aglobal)
+        check_host(host.ug4b200_solver_set_gathered_base(self.h, Aglobal.nrows, _ptr(Aglobal.rowptr), _ptr(Aglobal.cols),
+                                                         _ptr(Aglobal.vals), l2g.size, _ptr(l2g)))
+
+    def init(self):
+        check_host(host.ug4b200_solver_init(self.h))
+        self._inited = True
+        return self
+
+    def apply(self, b, x0=None):
+        """solver:apply(u, b) with host vectors. Returns (x, converged, defect history)."""
+        if not self._inited:
+            self.init()
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.zeros(self.n) if x0 is None else np.ascontiguousarray(x0, dtype=np.float64).copy()
+        rc = check_host(host.ug4b200_solver_apply(self.h, _ptr(x), _ptr(b)))
+        return x, rc == 0, self.history()
+
+    def apply_pinned(self, x_ptr: int, b_ptr: int) -> bool:
+        """Same through raw host pointers (e.g. pinned torch tensors): x in/out, b in."""
+        if not self._inited:
+            self.init()
+        return check_host(host.ug4b200_solver_apply(self.h, C.c_void_p(x_ptr), C.c_void_p(b_ptr))) == 0
+
+    def apply_device(self, x_dev, b_dev) -> bool:
+        """Device-resident solve; x_dev / b_dev are DeviceBuffer or raw device pointers."""
+        if not self._inited:
+            self.init()
+        xp = x_dev.ptr if isinstance(x_dev, DeviceBuffer) else C.c_void_p(x_dev)
+        bp = b_dev.ptr if isinstance(b_dev, DeviceBuffer) else C.c_void_p(b_dev)
+        return check_host(host.ug4b200_solver_apply_device(self.h, xp, bp)) == 0
+
+    def precond_apply(self, d):
+        if not self._inited:
+            self.init()
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        c = np.zeros(self.n)
+        check_host(host.ug4b200_solver_precond_apply(self.h, _ptr(c), _ptr(d)))
+        return c
+
+    @property
+    def steps(self) -> int:
+        return host.ug4b200_solver_steps(self.h)
+
+    @property
+    def defect(self) -> float:
+        return host.ug4b200_solver_defect(self.h)
+
+    def history(self):
+        buf = np.zeros(self.desc.max_steps + 2)
+        n = host.ug4b200_solver_history(self.h, _ptr(buf), buf.size)
+        return buf[:n].copy()
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        dev.ug4b200_launch_count(host_ctx(), C.byref(n))
+        return n.value
+
+    def __del__(self):
+        try:
+            host.ug4b200_solver_destroy(self.h)
+        except Exception:
+            pass
