@@ -13,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(ROOT, "csrc")
-LIB = os.path.join(ROOT, "lib")
+LIB = os.environ.get("UG4B200_LIBDIR", os.path.join(ROOT, "lib"))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 CUDA_SOURCES = ["ctx.cu", "comm.cu", "kernels/blas1.cu", "kernels/spmv.cu", "kernels/smoothers.cu"]
@@ -60,7 +60,8 @@ def build(force: bool = False, verbose: bool = False) -> None:
     dev = os.path.join(LIB, "libug4b200.so")
     dsrc = [os.path.join(CSRC, s) for s in CUDA_SOURCES]
     if force or _newer(dev, dsrc + headers):
-        _run([NVCC, *NVCC_FLAGS, *dsrc, "-o", dev, "-ldl", "-lgomp"], verbose)
+        extra = os.environ.get("UG4B200_EXTRA_NVCC", "").split()  # kernel-tuning experiments only
+        _run([NVCC, *NVCC_FLAGS, *extra, *dsrc, "-o", dev, "-ldl", "-lgomp"], verbose)
 
     host = os.path.join(LIB, "libug4b200_host.so")
     hsrc = [os.path.join(CSRC, "solver_capi.cpp")]

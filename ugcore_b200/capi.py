@@ -5,7 +5,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-_LIBDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
+_LIBDIR = os.environ.get("UG4B200_LIBDIR", os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib"))
 DEV_SO = os.path.join(_LIBDIR, "libug4b200.so")
 HOST_SO = os.path.join(_LIBDIR, "libug4b200_host.so")
 

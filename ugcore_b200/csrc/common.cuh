@@ -26,7 +26,7 @@ struct ug4b200_ctx {
 	int nranks = 1, rank = 0;
 };
 
-constexpr int kMaxReduceBlocks = 148 * 8;
+constexpr int kMaxReduceBlocks = 32768;
 constexpr int kReduceThreads = 256;
 
 extern thread_local std::string g_ug4b200_err;

@@ -43,8 +43,23 @@ template <int BETAK> __device__ __forceinline__ double mulbeta(double a, double 
 { return BETAK == 1 ? a : (BETAK == -1 ? -a : beta * a); }
 
 // ---------------------------------------------------------------- scalar (block 1)
+// One warp per slice.  All per-row streams (dest, sc, diaginv, own st entry) are requested
+// BEFORE the entry loop so their HBM latency overlaps the matrix stream; entries are fetched
+// in batches of UNR with the next batch's values/columns requested before the current
+// batch's x-gather is consumed (software pipelining: two dependent round trips overlap).
+#ifndef UG_UNR
+#define UG_UNR 4
+#endif
+#ifndef UG_PIPE
+#define UG_PIPE 0
+#endif
+#ifndef UG_MINBLK
+#define UG_MINBLK 1
+#endif
+constexpr int UNR = UG_UNR;
+
 template <int BETAK, int MODE, int FUSE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, UG_MINBLK)
 spmv1_kernel(Sell A, double* dest, const double* v, double alpha, double beta, const double* __restrict__ w,
              Fuse fz, const int* guard)
 {
@@ -55,56 +70,69 @@ spmv1_kernel(Sell A, double* dest, const double* v, double alpha, double beta, c
 	double dot = 0.0;
 	for (int64_t s = gwarp; s < A.num_slices; s += nwarps) {
 		const int64_t row = s * 32 + lane;
-		const int len = A.rowlen[row];
 		const int64_t base = A.slice_ptr[s];
 		const int width = (int)((A.slice_ptr[s + 1] - base) >> 5);
+		const int len = A.rowlen[row];
 		const double* vp = A.vals + base + lane;
 		const int* cp = A.cols + base + lane;
 		const bool live = row < A.nrows;
-		double acc;
-		int k = 0;
-		if (MODE == MODE_ASSIGN || MODE == MODE_ASSIGN_SKIP_EMPTY) {
-			// MatMult(dest[i], beta, a_0, w[c_0]): first connection assigned, not added
-			acc = 0.0;
-			if (width > 0) {
-				const double a0 = ug_ld_stream(vp); const int c0 = ug_ld_stream(cp);
-				if (len > 0) acc = mulbeta<BETAK>(a0, beta) * __ldg(w + c0);
-			}
-			k = 1;
-		} else if (MODE == MODE_INPLACE) {
-			acc = live ? dest[row] : 0.0;
-		} else {
-			acc = live ? alpha * v[row] : 0.0;
+		// ---- first batch of the matrix stream
+		double a[UNR]; int c[UNR];
+#pragma unroll
+		for (int u = 0; u < UNR; ++u)
+			if (u < width) { a[u] = ug_ld_stream(vp + u * 32); c[u] = ug_ld_stream(cp + u * 32); }
+		// ---- per-row streams, hoisted
+		double acc = 0.0, own = 0.0, scv = 0.0, dinv = 0.0;
+		if (MODE == MODE_INPLACE) { if (live) acc = dest[row]; }
+		else if (MODE == MODE_GENERAL) { if (live) acc = alpha * v[row]; }
+		if (FUSE == FUSE_DOT) { if (live) own = w[row]; }
+		if (FUSE == FUSE_JACOBI && live) {
+			if (fz.flags & UG4B200_SMOOTH_ADD_IN) own = w[row];
+			if (fz.flags & (UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_ADD_OUT)) scv = fz.sc[row];
+			if (fz.flags & UG4B200_SMOOTH_JACOBI) dinv = fz.diaginv[row];
 		}
-		for (; k < width; k += 4) {
-			double a[4]; int c[4]; double x[4];
+		for (int k = 0; k < width; k += UNR) {
+			double x[UNR];
 #pragma unroll
-			for (int u = 0; u < 4; ++u)
-				if (k + u < width) { a[u] = ug_ld_stream(vp + (int64_t)(k + u) * 32); c[u] = ug_ld_stream(cp + (int64_t)(k + u) * 32); }
-#pragma unroll
-			for (int u = 0; u < 4; ++u)
+			for (int u = 0; u < UNR; ++u)
 				if (k + u < len) x[u] = __ldg(w + c[u]);
+			double an[UNR]; int cn[UNR];
+#if UG_PIPE
 #pragma unroll
-			for (int u = 0; u < 4; ++u)
-				if (k + u < len) acc = acc + mulbeta<BETAK>(a[u], beta) * x[u];
+			for (int u = 0; u < UNR; ++u)
+				if (k + UNR + u < width) { an[u] = ug_ld_stream(vp + (int64_t)(k + UNR + u) * 32); cn[u] = ug_ld_stream(cp + (int64_t)(k + UNR + u) * 32); }
+#endif
+#pragma unroll
+			for (int u = 0; u < UNR; ++u) {
+				if (k + u < len) {
+					const double t = mulbeta<BETAK>(a[u], beta) * x[u];
+					// MatMult(dest[i], beta, a_0, w[c_0]): the first connection is assigned, not added
+					if ((MODE == MODE_ASSIGN || MODE == MODE_ASSIGN_SKIP_EMPTY) && k + u == 0) acc = t;
+					else acc = acc + t;
+				}
+			}
+#if !UG_PIPE
+#pragma unroll
+			for (int u = 0; u < UNR; ++u)
+				if (k + UNR + u < width) { an[u] = ug_ld_stream(vp + (int64_t)(k + UNR + u) * 32); cn[u] = ug_ld_stream(cp + (int64_t)(k + UNR + u) * 32); }
+#endif
+#pragma unroll
+			for (int u = 0; u < UNR; ++u) { a[u] = an[u]; c[u] = cn[u]; }
 		}
 		if (FUSE == FUSE_JACOBI) {
 			if (live) {
 				dest[row] = acc;
-				double scv = 0.0;
-				const bool touch_sc = fz.flags & (UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_ADD_OUT);
-				if (touch_sc) scv = fz.sc[row];
-				if (fz.flags & UG4B200_SMOOTH_ADD_IN) scv = scv + w[row];
+				if (fz.flags & UG4B200_SMOOTH_ADD_IN) scv = scv + own;
 				if (fz.flags & UG4B200_SMOOTH_JACOBI) {
-					const double st = fz.diaginv[row] * acc;   // MatMult(c[i], 1.0, diagInv[i], d[i])
+					const double st = dinv * acc;   // MatMult(c[i], 1.0, diagInv[i], d[i])
 					fz.st_out[row] = st;
 					if (fz.flags & UG4B200_SMOOTH_ADD_OUT) scv = scv + st;
 				}
-				if (touch_sc) fz.sc[row] = scv;
+				if (fz.flags & (UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_ADD_OUT)) fz.sc[row] = scv;
 			}
 		} else {
 			if (live && (MODE != MODE_ASSIGN_SKIP_EMPTY || len > 0)) dest[row] = acc;
-			if (FUSE == FUSE_DOT && live) dot += acc * w[row];
+			if (FUSE == FUSE_DOT && live) dot += acc * own;
 		}
 	}
 	if (FUSE == FUSE_DOT) ug_block_reduce_fin(dot, fz.partials, fz.counter, fz.fin);
@@ -267,12 +295,13 @@ spmv1xV_kernel(Sell A, double* dest, const double* v, double alpha, double beta,
 	}
 }
 
-inline int spmv_grid(const ug4b200_ctx* ctx, int64_t num_slices)
+// One warp per slice, many small CTAs: the hardware block scheduler balances the tail
+// (a fixed persistent grid was measured at 1.6 waves: 44 % of HBM peak, profiles/r01).
+// Only the fused-reduction variant is capped by the size of the partial-sum buffer.
+inline int spmv_grid(const ug4b200_ctx*, int64_t num_slices)
 {
 	int64_t b = (num_slices + kWarps - 1) / kWarps;
-	int64_t cap = (int64_t)ctx->num_sms * 8;
-	if (cap > kMaxReduceBlocks) cap = kMaxReduceBlocks;
-	if (b > cap) b = cap;
+	if (b > kMaxReduceBlocks) b = kMaxReduceBlocks;
 	if (b < 1) b = 1;
 	return (int)b;
 }

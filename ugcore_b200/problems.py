@@ -11,7 +11,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-_LIBDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
+_LIBDIR = os.environ.get("UG4B200_LIBDIR", os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib"))
 _lib = None
 
 POISSON, CONVDIFF, ELASTICITY = 0, 1, 2
