@@ -1,0 +1,114 @@
+"""CPU suite, world_size 2 over gloo: host-side logic of the partitioned path — interface
+lists, additive/consistent/unique protocol, gathered-base map — checked against the serial
+assembly of the same global grid.  (The device kernels need a GPU; their exchange is the same
+protocol over NCCL, covered by tests/test_multi_gpu.py.)"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from ugcore_b200 import dist as ugdist, problems as pr
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        part, refs = (2, 1, 1), 3
+        prob = ugdist.local_problem(refs, part, rank)
+        gprob = ugdist.global_problem(refs, part)
+        for lev in range(0, refs + 1):
+            A, gA = prob.matrix(lev).to_scipy(), gprob.matrix(lev).to_scipy()
+            gid = prob.global_ids(lev)
+            ranks, ptr, idx = ugdist.interfaces(prob, lev)
+            assert list(ranks) == [1 - rank]
+            # both sides list the same global DoFs in the same order
+            mine = torch.from_numpy(gid[idx].copy())
+            theirs = torch.empty_like(mine)
+            reqs = [dist.isend(mine, 1 - rank), dist.irecv(theirs, 1 - rank)]
+            [r.wait() for r in reqs]
+            assert torch.equal(mine, theirs)
+            nodes = prob.dims(lev)
+            assert idx.size == nodes[1] * nodes[2]
+
+            def to_consistent(v):
+                """AdditiveToConsistent, summed in ascending rank order (comm.cu semantics)."""
+                send = torch.from_numpy(v[idx].copy()); recv = torch.empty_like(send)
+                reqs = [dist.isend(send, 1 - rank), dist.irecv(recv, 1 - rank)]
+                [r.wait() for r in reqs]
+                out = v.copy()
+                out[idx] = (v[idx] + recv.numpy()) if rank == 0 else (recv.numpy() + v[idx])
+                return out
+
+            # A_additive * x_consistent made consistent == serial A x (away from Dirichlet rows,
+            # which are identity on every copy: additive sum = multiplicity * identity)
+            rng = np.random.default_rng(lev)
+            xg = rng.standard_normal(gA.shape[0])
+            y = to_consistent(A @ xg[gid])
+            interior = prob.dirichlet(lev) == 0
+            assert np.allclose(y[interior], (gA @ xg)[gid][interior], rtol=1e-13, atol=1e-13)
+            mult = ugdist.multiplicity(prob, lev)
+            assert np.allclose(y[~interior], (mult * xg[gid])[~interior])
+            # unique dot: sum over h-master copies of a consistent vector == serial dot
+            own = ugdist.owned_mask(prob, lev, rank)
+            t = torch.tensor([float(np.dot(xg[gid][own], xg[gid][own]))], dtype=torch.float64)
+            dist.all_reduce(t)
+            assert abs(t.item() - float(xg @ xg)) < 1e-10 * float(xg @ xg)
+            # additive rhs sums to the serial rhs
+            if lev == refs:
+                b = to_consistent(np.array(prob.rhs()))
+                assert np.allclose(b, np.array(gprob.rhs())[gid], rtol=1e-13, atol=1e-15)
+            # P is consistent (same rows as the serial P), R additive sums to serial R
+            if lev > 0:
+                P, gP = prob.prolongation(lev).to_scipy(), gprob.prolongation(lev).to_scipy()
+                cg = prob.global_ids(lev - 1)
+                xc = rng.standard_normal(gP.shape[1])
+                assert np.allclose(P @ xc[cg], (gP @ xc)[gid], rtol=1e-14, atol=1e-14)
+        # gathered base: local level-0 DoFs map into the global base numbering
+        l2g = prob.global_ids(0)
+        assert l2g.size == 8 and set(l2g) <= set(range(12))
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partition_protocol_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650 + os.getpid() % 200
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = [q.get(timeout=240) for _ in ps]
+    [p.join(timeout=60) for p in ps]
+    for rank, msg in res:
+        assert msg == "ok", f"rank {rank}: {msg}"
+
+
+def test_interfaces_2x2x2_symmetry():
+    """All 8 ranks in one process: every pair agrees on its shared DoFs; corner DoF has 8 copies."""
+    sys.path.insert(0, ROOT)
+    from ugcore_b200 import dist as ugdist
+    part, refs = (2, 2, 2), 2
+    probs = [ugdist.local_problem(refs, part, r) for r in range(8)]
+    lists = {}
+    for r, p in enumerate(probs):
+        ranks, ptr, idx = ugdist.interfaces(p, refs)
+        assert len(ranks) == 7
+        gid = p.global_ids(refs)
+        for k, s in enumerate(ranks):
+            lists[(r, int(s))] = gid[idx[ptr[k]:ptr[k + 1]]]
+        mult = ugdist.multiplicity(p, refs)
+        assert mult.max() == 8 and (mult == 8).sum() == 1
+    for (r, s), g in lists.items():
+        assert np.array_equal(g, lists[(s, r)])
+    owned = sum(int(ugdist.owned_mask(p, refs, r).sum()) for r, p in enumerate(probs))
+    assert owned == (2 * 2 ** refs + 1) ** 3

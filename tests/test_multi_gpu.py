@@ -1,0 +1,34 @@
+"""Multi-GPU parity (needs >= 2 GPUs, skipped otherwise): partitioned solve vs serial oracle."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("world,flags", [(2, 0), (2, 2), (4, 0), (8, 0)])
+def test_partitioned_gmg_cg_matches_serial_oracle(world, flags):
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world + flags),
+           os.path.join(ROOT, "tests", "mgpu_worker.py"), "3", str(flags)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    line = [l for l in r.stdout.splitlines() if l.startswith("MGPU_RESULT ")]
+    assert line, r.stdout[-3000:] + r.stderr[-3000:]
+    for res in json.loads(line[0][len("MGPU_RESULT "):]):
+        assert res["ok"] and res["oracle_ok"]
+        assert abs(res["its"] - res["its_oracle"]) <= 1
+        assert res["hist_err"] < 1e-10 and res["sol_err"] < 1e-9, res

@@ -139,6 +139,7 @@ class GPUSparseMatrix {
 	template <typename V> bool matmul_minus(V& res, const V& x) const
 	{
 		UG_GPU_CHECK(ug4b200_matrix_matmul_minus(GPUManager::ctx(), device(), res.dev(), x.dev(), V::blockSize));
+		res.set_storage_type(PST_ADDITIVE); // additive - A_additive * consistent: no longer unique
 		return true;
 	}
 	template <typename V> bool axpy(V& dest, const number& alpha1, const V& v1, const number& beta1, const V& w1) const

@@ -196,7 +196,8 @@ class GaussSeidelBase : public IPreconditioner<TAlgebra> {
 		if (m_PA && GPUManager::ctx_or_null()) ug4b200_matrix_destroy(GPUManager::ctx_or_null(), m_PA);
 		m_PA = nullptr;
 		GPUManager::free_bytes(m_dPerm); m_dPerm = nullptr;
-		if (m_pd) GPUManager::release(m_pd, m_n * B); if (m_pc) GPUManager::release(m_pc, m_n * B);
+		if (m_pd) GPUManager::release(m_pd, m_n * B);
+		if (m_pc) GPUManager::release(m_pc, m_n * B);
 		m_pd = m_pc = nullptr;
 	}
 

@@ -1,0 +1,151 @@
+"""Partitioned (multi-GPU) set-up: one process per GPU, structured box partition.
+
+ugcore's parallel model is kept (Model A): element-wise partition, interface
+vertices duplicated on every rank that touches them, ADDITIVE matrices (each rank assembles
+its own elements only, lib_algebra/parallelization/parallel_matrix_impl.h:88-114), vectors
+carry consistent / additive / unique storage types.  SpMV needs no communication; smoother
+corrections are made consistent by an interface exchange (AdditiveToConsistent,
+parallelization_util.h:159-191), norms / dots all-reduce one double.
+
+This module holds the host-side logic (pure numpy, unit-tested on CPU with gloo):
+  * the process grid and each rank's box,
+  * horizontal interface lists per level (IndexLayout: per neighbour the shared DoFs, in an
+    order both sides agree on — ascending global id),
+  * the gathered base solve map (mg_solver_impl.hpp:2003-2070).
+torch.distributed is only plumbing: it carries the NCCL unique id to the other ranks.
+"""
+from __future__ import annotations
+
+import itertools
+
+import numpy as np
+
+from . import problems as pr
+
+
+def rank_to_coord(rank: int, part):
+    """x fastest."""
+    return (rank % part[0], (rank // part[0]) % part[1], rank // (part[0] * part[1]))
+
+
+def coord_to_rank(coord, part):
+    return coord[0] + part[0] * (coord[1] + part[1] * coord[2])
+
+
+def interfaces(prob: pr.Problem, lev: int):
+    """Horizontal interfaces of one level of this rank's sub-box.
+
+    Returns (neigh_rank[int32], neigh_ptr[int64], indices[int32]) with neighbours sorted by
+    rank and, inside a neighbour, DoFs sorted by global id (identical order on both sides).
+    """
+    part, coord = prob.part, prob.coord
+    dims = prob.dims(lev)
+    d2l = prob.dof_to_lex(lev)
+    gid = prob.global_ids(lev)
+    lex_to_dof = np.empty(d2l.size, np.int64)
+    lex_to_dof[d2l] = np.arange(d2l.size)
+    ii = np.arange(dims[0])[:, None, None]
+    jj = np.arange(dims[1])[None, :, None]
+    kk = np.arange(dims[2])[None, None, :]
+    lex = (ii + dims[0] * (jj + dims[1] * kk))
+    out = []
+    for off in itertools.product((-1, 0, 1), repeat=3):
+        if off == (0, 0, 0):
+            continue
+        nc = tuple(coord[d] + off[d] for d in range(3))
+        if any(nc[d] < 0 or nc[d] >= part[d] for d in range(3)):
+            continue
+        if any(off[d] != 0 and d >= prob.dim for d in range(3)):
+            continue
+        sl = []
+        for d in range(3):
+            if off[d] == -1:
+                sl.append(slice(0, 1))
+            elif off[d] == 1:
+                sl.append(slice(dims[d] - 1, dims[d]))
+            else:
+                sl.append(slice(None))
+        dofs = lex_to_dof[lex[tuple(sl)].ravel()]
+        dofs = dofs[np.argsort(gid[dofs], kind="stable")]
+        out.append((coord_to_rank(nc, part), dofs))
+    out.sort(key=lambda t: t[0])
+    ranks = np.array([r for r, _ in out], np.int32)
+    ptr = np.concatenate([[0], np.cumsum([len(d) for _, d in out])]).astype(np.int64)
+    idx = np.concatenate([d for _, d in out]).astype(np.int32) if out else np.zeros(0, np.int32)
+    return ranks, ptr, idx
+
+
+def multiplicity(prob: pr.Problem, lev: int):
+    """Number of ranks holding a copy of each local DoF (1 in the interior)."""
+    ranks, ptr, idx = interfaces(prob, lev)
+    m = np.ones(prob.matrix(lev).nrows, np.int32)
+    np.add.at(m, idx, 1)
+    return m
+
+
+def owned_mask(prob: pr.Problem, lev: int, rank: int):
+    """True where this rank is the h-master (lowest rank among the sharers)."""
+    ranks, ptr, idx = interfaces(prob, lev)
+    own = np.ones(prob.matrix(lev).nrows, bool)
+    for p, r in enumerate(ranks):
+        if r < rank:
+            own[idx[ptr[p]:ptr[p + 1]]] = False
+    return own
+
+
+def local_problem(refs: int, part, rank: int, problem=pr.POISSON, order=pr.ORDER_LEX, dim=3, **kw) -> pr.Problem:
+    """This rank's sub-box of the global grid whose base grid has one element per rank."""
+    coord = rank_to_coord(rank, part)
+    return pr.Problem(dim=dim, num_refs=refs, problem=problem, base=tuple(part), base_lev=0, order=order,
+                      part=tuple(part), coord=coord, **kw)
+
+
+def global_problem(refs: int, part, problem=pr.POISSON, dim=3, **kw) -> pr.Problem:
+    """The same grid assembled serially (parity target and gathered base matrix)."""
+    return pr.Problem(dim=dim, num_refs=refs, problem=problem, base=tuple(part), base_lev=0, **kw)
+
+
+def nccl_bootstrap(dist) -> None:
+    """Rank 0 draws the NCCL unique id, torch.distributed broadcasts it, every rank joins."""
+    import ctypes as C
+
+    import torch
+
+    from .capi import check, check_host, dev, host
+    from .solver import host_init
+    host_init()
+    ident = (C.c_ubyte * 128)()
+    if dist.get_rank() == 0:
+        check(dev.ug4b200_comm_unique_id(ident))
+    t = torch.tensor(list(ident), dtype=torch.uint8)
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.broadcast(t, src=0)
+    ident = (C.c_ubyte * 128)(*t.cpu().tolist())
+    check_host(host.ug4b200_host_comm_init(dist.get_world_size(), dist.get_rank(), ident))
+
+
+def build_partitioned_solver(desc: dict, refs: int, part, rank: int, dist, problem=pr.POISSON, flags: int = 0, **kw):
+    """Wire a GMG-preconditioned solver on this rank's sub-box: local additive level matrices,
+    interface layouts per level, gathered (replicated, all-reduced) base solve."""
+    from .solver import Solver
+    nccl_bootstrap(dist)
+    prob = local_problem(refs, part, rank, problem=problem, **kw)
+    desc = dict(desc)
+    pc = dict(desc["precond"])
+    pc["topLevel"], pc["baseLevel"] = refs, pc.get("baseLevel", 0)
+    desc["precond"] = pc
+    base = pc["baseLevel"]
+    levels = {}
+    for lev in range(base, refs + 1):
+        levels[lev] = (prob.matrix(lev), None if lev == base else prob.prolongation(lev),
+                       None if lev == base else prob.restriction(lev))
+    s = Solver(desc, prob.matrix(refs), levels, flags)
+    s._keep.append(prob)
+    for lev in range(base, refs + 1):
+        ranks, ptr, idx = interfaces(prob, lev)
+        s.set_layouts(lev, ranks, ptr, idx, prob.matrix(lev).nrows)
+    gprob = global_problem(base, part, problem=problem, **kw)
+    s._keep.append(gprob)
+    s.set_gathered_base(gprob.matrix(base), prob.global_ids(base).astype(np.int32))
+    return prob, s
