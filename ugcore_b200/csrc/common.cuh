@@ -16,6 +16,9 @@ struct ug4b200_ctx {
 	int64_t capture_start = 0;
 	std::string err;
 	int num_sms = 148;
+	int tma_min_slices_per_warp = 2; // UG4B200_TMA_MIN_SLICES=0 forces the bulk-copy kernel (tests)
+	bool tma_all = false;         // UG4B200_TMA_ALL=1: bulk-copy kernel also for unfused sweeps
+	bool no_tma = false;          // UG4B200_NO_TMA=1: register-staged SpMV everywhere (A/B measurements)
 	// reduction workspace (stream-ordered reuse)
 	double* partials = nullptr;   // [kMaxReduceBlocks]
 	unsigned int* counter = nullptr;

@@ -1,6 +1,7 @@
 // ctx.cu — context, memory and stream plumbing of the C ABI (include/ug4b200.h).
 // Replaces CUDAManager (ugbase/lib_algebra/gpu_algebra/cuda/cuda_manager.{h,cpp}).
 #include "common.cuh"
+#include <cstdlib>
 
 thread_local std::string g_ug4b200_err;
 
@@ -25,6 +26,9 @@ int ug4b200_ctx_create(int device, void* stream, ug4b200_ctx** out)
 	cudaDeviceProp prop;
 	UG_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
 	ctx->num_sms = prop.multiProcessorCount;
+	{ const char* e = getenv("UG4B200_NO_TMA"); ctx->no_tma = e && e[0] == '1'; }
+	{ const char* e = getenv("UG4B200_TMA_ALL"); ctx->tma_all = e && e[0] == '1'; }
+	{ const char* e = getenv("UG4B200_TMA_MIN_SLICES"); if (e) ctx->tma_min_slices_per_warp = atoi(e); }
 	if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
 	else { UG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
 	UG_CUDA(ctx, cudaMalloc(&ctx->partials, sizeof(double) * kMaxReduceBlocks));

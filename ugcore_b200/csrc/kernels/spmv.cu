@@ -309,6 +309,36 @@ inline int spmv_grid(const ug4b200_ctx*, int64_t num_slices)
 inline Sell view(const ug4b200_matrix* A)
 { return Sell{A->slice_ptr, A->rowlen, A->cols, A->vals, A->nrows, A->num_slices}; }
 
+#include "spmv_tma.cuh"
+
+
+// Large matrices: persistent bulk-copy-staged kernel, one wave of (#SMs x resident CTAs).
+template <int BETAK, int MODE, int FUSE>
+int launch_tma(ug4b200_ctx* ctx, const Sell& S, double* dest, const double* v, double alpha, double beta,
+               const double* w, const Fuse& fz, bool* used)
+{
+	static int ctas_per_sm = -1;   // per instantiation
+	*used = false;
+	if (ctas_per_sm == -1) {
+		cudaError_t e = cudaFuncSetAttribute(tma::spmv1_tma_kernel<BETAK, MODE, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		                                     tma::SMEM_BYTES);
+		int n = 0;
+		if (e == cudaSuccess)
+			e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tma::spmv1_tma_kernel<BETAK, MODE, FUSE>, tma::WPB * 32,
+			                                                  tma::SMEM_BYTES);
+		if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+		ctas_per_sm = n;
+	}
+	if (ctas_per_sm <= 0) return UG4B200_OK;
+	int64_t grid = (int64_t)ctx->num_sms * ctas_per_sm;
+	if (grid > kMaxReduceBlocks) grid = kMaxReduceBlocks;
+	if (S.num_slices < grid * tma::WPB * ctx->tma_min_slices_per_warp) return UG4B200_OK; // too small to fill the pipeline
+	UG_LAUNCH(ctx, (tma::spmv1_tma_kernel<BETAK, MODE, FUSE>), (int)grid, tma::WPB * 32, tma::SMEM_BYTES, S, dest, v, alpha,
+	          beta, w, fz, ctx->guard);
+	*used = true;
+	return UG4B200_OK;
+}
+
 template <int BETAK, int MODE, int FUSE>
 int launch_mode(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* dest, const double* v, double alpha, double beta,
                 const double* w, int vblock, const Fuse& fz)
@@ -316,7 +346,15 @@ int launch_mode(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* dest, const d
 	const int grid = spmv_grid(ctx, A->num_slices);
 	const Sell S = view(A);
 	if (A->block == 1 && vblock == 1) {
-		UG_LAUNCH(ctx, (spmv1_kernel<BETAK, MODE, FUSE>), grid, kThreads, 0, S, dest, v, alpha, beta, w, fz, ctx->guard);
+		bool used = false;
+		// measured (profiles/r01b): the bulk-copy kernel wins for the fused variants, the
+		// register-staged one for the plain sweep
+		if (!ctx->no_tma && (FUSE != FUSE_NONE || ctx->tma_min_slices_per_warp == 0 || ctx->tma_all)) {
+			const int rc = launch_tma<BETAK, MODE, FUSE>(ctx, S, dest, v, alpha, beta, w, fz, &used);
+			if (rc) return rc;
+		}
+		if (!used)
+			UG_LAUNCH(ctx, (spmv1_kernel<BETAK, MODE, FUSE>), grid, kThreads, 0, S, dest, v, alpha, beta, w, fz, ctx->guard);
 	} else if (A->block == 1) {
 		if (FUSE != FUSE_NONE) return ug4b200_fail(ctx, UG4B200_ERR_ARG, "fused SpMV needs matrix block == vector block");
 		if (vblock == 2) { UG_LAUNCH(ctx, (spmv1xV_kernel<2, BETAK, MODE>), grid, kThreads, 0, S, dest, v, alpha, beta, w, ctx->guard); }
