@@ -237,9 +237,23 @@ int ug4b200_jacobi_step_add(ug4b200_ctx* ctx, int64_t nblocks, int block, const 
  *   [sc += st_out]           if flags & UG4B200_SMOOTH_ADD_OUT
  * Serial V-cycles use JACOBI|ADD_OUT; partitioned ones ADD_IN|JACOBI because st_out must be
  * made consistent across ranks before it is accumulated. */
-enum { UG4B200_SMOOTH_ADD_IN = 1, UG4B200_SMOOTH_JACOBI = 2, UG4B200_SMOOTH_ADD_OUT = 4 };
+/* UG4B200_SMOOTH_SC_ZERO: the incoming sc is taken as 0.0 without reading it (the level's
+ * correction was just reset, mg_solver_impl.hpp:234, 1780) — saves the set(0) sweep; the
+ * additions 0.0 + st are still carried out, so sc is bit-identical. */
+enum { UG4B200_SMOOTH_ADD_IN = 1, UG4B200_SMOOTH_JACOBI = 2, UG4B200_SMOOTH_ADD_OUT = 4, UG4B200_SMOOTH_SC_ZERO = 8 };
 int ug4b200_jacobi_smooth_fused(ug4b200_ctx* ctx, const ug4b200_matrix* A, const double* diaginv, double* sd,
                                 const double* st_in, double* st_out, double* sc, int flags);
+/* same with the incoming defect read from sd_in (sd = 1.0*sd_in - A*st_in): the top level
+ * smooths the caller's defect without the surface->level copy of mg_solver_impl.hpp:211-217
+ * when the index map is the identity.  sd_in == NULL or == sd: in place. */
+int ug4b200_jacobi_smooth_fused_src(ug4b200_ctx* ctx, const ug4b200_matrix* A, const double* diaginv, double* sd,
+                                    const double* sd_in, const double* st_in, double* st_out, double* sc, int flags);
+/* Restriction fused with the first Jacobi step of the coarse level
+ * (mg_solver_impl.hpp:1802 do_restrict -> std_transfer_impl.h:791-792, then :1705 on the
+ * coarse level): sd_coarse = beta*R*sd_fine, rows without connections untouched;
+ * st_coarse = diaginv_coarse * sd_coarse.  Scalar algebra. */
+int ug4b200_restrict_jacobi_fused(ug4b200_ctx* ctx, const ug4b200_matrix* R, const double* diaginv_coarse,
+                                  double* sd_coarse, double beta, const double* sd_fine, double* st_coarse);
 
 /* Multicolour Gauss-Seidel.  The matrix must be given in a colour-sorted DoF order:
  * rows [color_ptr[k], color_ptr[k+1]) form colour k and have no stored connection to
@@ -285,6 +299,36 @@ int ug4b200_interface_destroy(ug4b200_ctx* ctx, ug4b200_interface* I);
  * DoF ends up with the sum over all copies, summed in ascending rank order on every
  * rank (bitwise identical copies). */
 int ug4b200_additive_to_consistent(ug4b200_ctx* ctx, ug4b200_interface* I, double* v, int block);
+/* Peer-window transport (preferred inside one NVSwitch box; replaces the MPI_Isend/Irecv
+ * transport of pcl_interface_communicator_impl.hpp:560-661 and MPI_Allreduce,
+ * pcl_process_communicator.cpp:325): every rank exposes a window of device memory to the
+ * other ranks of the box (CUDA IPC); interface exchange and scalar all-reduce then run as
+ * ONE kernel per rank that stores straight into the neighbours' windows over NVLink and
+ * synchronises through epoch flags there — no NCCL call, no host round trip.
+ *   1. window_create on every rank (bytes == 0: UG4B200_P2P_WINDOW_MB or 64 MiB),
+ *   2. exchange the 64-byte handles (the caller's plumbing, e.g. torch.distributed),
+ *   3. window_open with all handles in rank order (or window_attach with raw base
+ *      pointers when the "ranks" are contexts of one process),
+ *   4. create interfaces: all ranks must create (and destroy) them in the same order.
+ * Interfaces created while a window is open use it; ug4b200_allreduce_sum does for
+ * n <= 1024.  Results are identical to the NCCL transport (same ascending-rank sums). */
+#define UG4B200_IPC_HANDLE_BYTES 64
+int ug4b200_p2p_window_create(ug4b200_ctx* ctx, size_t bytes, unsigned char handle[UG4B200_IPC_HANDLE_BYTES],
+                              void** base);
+int ug4b200_p2p_window_open(ug4b200_ctx* ctx, int nranks, int rank, const unsigned char* handles);
+int ug4b200_p2p_window_attach(ug4b200_ctx* ctx, int nranks, int rank, void* const* bases);
+int ug4b200_p2p_window_destroy(ug4b200_ctx* ctx);
+int ug4b200_p2p_enabled(const ug4b200_ctx* ctx);
+/* non-zero if a kernel gave up waiting for a neighbour (20 s); also reported by ug4b200_sync */
+int ug4b200_p2p_check(ug4b200_ctx* ctx);
+/* resolve where the neighbours receive (blocks until they have created the same interface);
+ * done implicitly by the first exchange, but must happen before a graph capture */
+int ug4b200_interface_commit(ug4b200_ctx* ctx, ug4b200_interface* I);
+/* ParallelVector::dotprod / norm (parallel_vector_impl.h:269-379) without leaving the device:
+ * local dot, sum over ranks and finaliser.  One kernel with the peer-window transport;
+ * dot -> ncclAllReduce -> finaliser through scratch_dev (1 double) otherwise. */
+int ug4b200_vec_dot_allreduce_ds(ug4b200_ctx* ctx, int64_t n, const double* a, const double* b, ug4b200_fin fin,
+                                 double* scratch_dev);
 /* zero every copy that is not the h-master (AdditiveToUnique after a consistent sum /
  * ConsistentToUnique, parallelization_util.h:260-280, 387-393) */
 int ug4b200_set_slaves_zero(ug4b200_ctx* ctx, ug4b200_interface* I, double* v, int block);

@@ -34,7 +34,8 @@ def main():
     lv = oracle_levels(orc, gprob)
     xo, oko, ho = oracle.OSolver(orc, desc, lv[refs][0], lv).apply(gprob.rhs())
     gid = prob.global_ids(refs)
-    res = {"rank": rank, "ok": bool(ok), "oracle_ok": bool(oko), "its": len(h) - 1, "its_oracle": len(ho) - 1,
+    from ugcore_b200 import capi
+    res = {"rank": rank, "p2p": bool(capi.dev.ug4b200_p2p_enabled(S.host_ctx())), "ok": bool(ok), "oracle_ok": bool(oko), "its": len(h) - 1, "its_oracle": len(ho) - 1,
            "hist_err": rel_hist_err(h, ho), "sol_err": float(np.linalg.norm(x - xo[gid]) / np.linalg.norm(xo[gid]))}
     out = [None] * world
     dist.all_gather_object(out, res)

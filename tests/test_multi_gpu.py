@@ -18,17 +18,20 @@ def _ngpu():
         return 0
 
 
-@pytest.mark.parametrize("world,flags", [(2, 0), (2, 2), (4, 0), (8, 0)])
-def test_partitioned_gmg_cg_matches_serial_oracle(world, flags):
+# p2p = 1: peer-window transport (direct NVLink stores + flags), 0: NCCL send/recv + all-reduce
+@pytest.mark.parametrize("world,flags,p2p", [(2, 0, 1), (2, 2, 1), (2, 0, 0), (4, 0, 1), (8, 0, 1), (8, 0, 0)])
+def test_partitioned_gmg_cg_matches_serial_oracle(world, flags, p2p):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
+    env = dict(os.environ, UG4B200_P2P=str(p2p))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world + flags),
+           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world + flags + 20 * p2p),
            os.path.join(ROOT, "tests", "mgpu_worker.py"), "3", str(flags)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     line = [l for l in r.stdout.splitlines() if l.startswith("MGPU_RESULT ")]
     assert line, r.stdout[-3000:] + r.stderr[-3000:]
     for res in json.loads(line[0][len("MGPU_RESULT "):]):
         assert res["ok"] and res["oracle_ok"]
         assert abs(res["its"] - res["its_oracle"]) <= 1
         assert res["hist_err"] < 1e-10 and res["sol_err"] < 1e-9, res
+        assert res["p2p"] == bool(p2p), res

@@ -51,7 +51,7 @@ class SolverDesc(C.Structure):
 
 
 FIN_STORE, FIN_A_DIV_R, FIN_R_DIV_A, FIN_SQRT, FIN_CONV_START, FIN_CONV_UPDATE = range(6)
-SMOOTH_ADD_IN, SMOOTH_JACOBI, SMOOTH_ADD_OUT = 1, 2, 4
+SMOOTH_ADD_IN, SMOOTH_JACOBI, SMOOTH_ADD_OUT, SMOOTH_SC_ZERO = 1, 2, 4, 8
 FLAG_HOST_SCALARS, FLAG_NO_GRAPH, FLAG_NO_FUSED_JACOBI, FLAG_FINAL_LEVEL_DEFECT = 1, 2, 4, 8
 
 # name -> (restype, argtypes); every symbol declared in include/ug4b200.h
@@ -115,6 +115,8 @@ DEV_API = {
     "ug4b200_jacobi_step": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp]),
     "ug4b200_jacobi_step_add": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
     "ug4b200_jacobi_smooth_fused": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int]),
+    "ug4b200_jacobi_smooth_fused_src": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int]),
+    "ug4b200_restrict_jacobi_fused": (c_int, [c_vp, c_vp, c_vp, c_vp, c_dbl, c_vp, c_vp]),
     "ug4b200_color_greedy": (c_int, [c_i64, c_vp, c_vp, c_vp, p_int]),
     "ug4b200_color_check": (c_int, [c_i64, c_vp, c_vp, c_int, c_vp]),
     "ug4b200_gs_step": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_dbl, c_vp, c_vp]),
@@ -129,6 +131,14 @@ DEV_API = {
     "ug4b200_additive_to_consistent": (c_int, [c_vp, c_vp, c_vp, c_int]),
     "ug4b200_set_slaves_zero": (c_int, [c_vp, c_vp, c_vp, c_int]),
     "ug4b200_vec_dot_unique_ds": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp]),
+    "ug4b200_p2p_window_create": (c_int, [c_vp, C.c_size_t, c_vp, C.POINTER(c_vp)]),
+    "ug4b200_p2p_window_open": (c_int, [c_vp, c_int, c_int, c_vp]),
+    "ug4b200_p2p_window_attach": (c_int, [c_vp, c_int, c_int, C.POINTER(c_vp)]),
+    "ug4b200_p2p_window_destroy": (c_int, [c_vp]),
+    "ug4b200_p2p_enabled": (c_int, [c_vp]),
+    "ug4b200_p2p_check": (c_int, [c_vp]),
+    "ug4b200_interface_commit": (c_int, [c_vp, c_vp]),
+    "ug4b200_vec_dot_allreduce_ds": (c_int, [c_vp, c_i64, c_vp, c_vp, Fin, c_vp]),
 }
 
 HOST_API = {

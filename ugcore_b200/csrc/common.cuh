@@ -19,6 +19,7 @@ struct ug4b200_ctx {
 	int tma_min_slices_per_warp = 2; // UG4B200_TMA_MIN_SLICES=0 forces the bulk-copy kernel (tests)
 	bool tma_all = false;         // UG4B200_TMA_ALL=1: bulk-copy kernel also for unfused sweeps
 	bool no_tma = false;          // UG4B200_NO_TMA=1: register-staged SpMV everywhere (A/B measurements)
+	bool pdl = false;             // UG4B200_PDL=1: programmatic dependent launch (next kernel's launch overlaps this one's tail)
 	// reduction workspace (stream-ordered reuse)
 	double* partials = nullptr;   // [kMaxReduceBlocks]
 	unsigned int* counter = nullptr;
@@ -27,7 +28,50 @@ struct ug4b200_ctx {
 	// NCCL (comm.cu)
 	void* nccl = nullptr;         // ncclComm_t
 	int nranks = 1, rank = 0;
+	// peer windows (comm.cu): direct NVLink stores into the other ranks' memory
+	struct ug4b200_p2p* p2p = nullptr;
 };
+
+// ---- peer windows: layout of every rank's window (identical on all ranks) ----------------
+//   [0, 64 KiB)        table   Entry[kP2PMaxIfaces][kP2PMaxRanks]: where rank r writes for interface k
+//   [64 KiB, +512)     all-reduce flags, one uint64 per source rank
+//   [.., +256 KiB)     all-reduce slots  double[2 parities][kP2PMaxRanks][kP2PArMax]
+//   [kP2PHeapOff, ..)  per-interface flags + receive regions (bump allocated)
+constexpr int kP2PMaxRanks = 16;
+constexpr int kP2PMaxIfaces = 64;
+constexpr int kP2PArMax = 1024;
+constexpr size_t kP2PArFlagOff = 65536;
+constexpr size_t kP2PArDataOff = 65536 + 512;
+constexpr size_t kP2PHeapOff = kP2PArDataOff + (size_t)2 * kP2PMaxRanks * kP2PArMax * 8;
+constexpr unsigned long long kP2PTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+
+struct ug4b200_p2p_entry { unsigned long long tag, recv_off, total, ptr_me, flag_off, pad_[3]; }; // 64 bytes
+
+struct ug4b200_p2p {
+	bool ipc = false;             // peers were opened with cudaIpcOpenMemHandle
+	int nranks = 1, rank = 0;
+	char* local = nullptr;
+	size_t bytes = 0, bump = 0;
+	char* peer[kP2PMaxRanks] = {};
+	char** d_peer = nullptr;      // device copy of peer[]
+	unsigned long long* d_epoch = nullptr; // all-reduce epoch (device, local)
+	int* err_host = nullptr;      // mapped pinned: set by a kernel whose wait timed out
+	int* err_dev = nullptr;
+	cudaStream_t aux = nullptr;   // table publication / lookups, independent of the compute stream
+	int next_iface = 0, live_ifaces = 0;
+};
+
+// what a reduction kernel needs to finish with an all-reduce over the peer windows
+struct UgAr {
+	char* const* peer; char* local; unsigned long long* epoch; int* err; int nranks, rank;
+};
+inline UgAr ug_ar_none() { return UgAr{nullptr, nullptr, nullptr, nullptr, 0, 0}; }
+inline UgAr ug_ar_of(const ug4b200_ctx* ctx)
+{
+	const ug4b200_p2p* p = ctx->p2p;
+	if (!p || p->nranks <= 1) return ug_ar_none();
+	return UgAr{p->d_peer, p->local, p->d_epoch, p->err_dev, p->nranks, p->rank};
+}
 
 constexpr int kMaxReduceBlocks = 32768;
 constexpr int kReduceThreads = 256;
@@ -52,17 +96,40 @@ inline int ug4b200_fail(ug4b200_ctx* ctx, int code, const std::string& msg)
 #define UG_ARG(ctx, cond, msg)                                                                    \
 	do { if (!(cond)) return ug4b200_fail(ctx, UG4B200_ERR_ARG, std::string(__func__) + ": " + msg); } while (0)
 
-// every kernel launch goes through this so launches are counted and checked
+// Every kernel launch goes through this so launches are counted and checked.  With ctx->pdl the
+// launch carries the programmatic-stream-serialization attribute: the kernel may be scheduled
+// while its predecessor drains; every kernel of this library therefore starts with ug_pdl_sync()
+// (griddepcontrol.wait: returns once the predecessor has completed and flushed), which is a no-op
+// for ordinary launches.
+template <typename... KArgs, typename... Args>
+inline cudaError_t ug_launch_ex(ug4b200_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args)
+{
+	cudaLaunchConfig_t cfg{};
+	cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+	cudaLaunchAttribute at[1];
+	if (ctx->pdl) {
+		at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		at[0].val.programmaticStreamSerializationAllowed = 1;
+		cfg.attrs = at; cfg.numAttrs = 1;
+	}
+	return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 #define UG_LAUNCH(ctx, kernel, grid, block, smem, ...)                                            \
 	do {                                                                                          \
-		kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                          \
+		cudaError_t e_ = ug_launch_ex(ctx, kernel, dim3(grid), dim3(block), (size_t)(smem), __VA_ARGS__); \
 		(ctx)->launches++;                                                                        \
-		cudaError_t e_ = cudaGetLastError();                                                      \
+		if (e_ == cudaSuccess) e_ = cudaGetLastError(); else cudaGetLastError();                  \
 		if (e_ != cudaSuccess)                                                                    \
 			return ug4b200_fail(ctx, UG4B200_ERR_CUDA, std::string(#kernel) + ": " + cudaGetErrorString(e_)); \
 	} while (0)
 
-__device__ __forceinline__ bool ug_guarded(const int* guard) { return guard != nullptr && *guard != 0; }
+__device__ __forceinline__ void ug_pdl_sync()
+{
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+// first statement of every kernel: dependency wait, then the "iterations queued past convergence" guard
+__device__ __forceinline__ bool ug_guarded(const int* guard) { ug_pdl_sync(); return guard != nullptr && *guard != 0; }
 
 __device__ __forceinline__ double ug_coef(const ug4b200_coef& c) { return c.dev ? c.host * (*c.dev) : c.host; }
 
@@ -126,6 +193,61 @@ __device__ inline void ug_apply_fin(double r, const ug4b200_fin& f)
 	}
 }
 
+// ---- system-scope flags over NVLink ----------------------------------------------
+__device__ __forceinline__ unsigned long long ug_ld_acquire_sys(const unsigned long long* p)
+{ unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void ug_st_release_sys(unsigned long long* p, unsigned long long v)
+{ asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ double ug_ld_relaxed_sys(const double* p)
+{ double v; asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void ug_st_relaxed_sys(double* p, double v)
+{ asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long ug_globaltimer()
+{ unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// spin until *flag >= e (flags are monotone epochs); gives up after kP2PTimeoutNs and raises *err
+__device__ inline bool ug_wait_flag(const unsigned long long* flag, unsigned long long e, int* err)
+{
+	unsigned long long t0 = 0; unsigned int spins = 0;
+	while (ug_ld_acquire_sys(flag) < e) {
+		if ((++spins & 0xfffu) == 0u) {
+			const unsigned long long t = ug_globaltimer();
+			if (t0 == 0) t0 = t;
+			else if (t - t0 > kP2PTimeoutNs) { if (err) *(volatile int*)err = 1; return false; }
+		}
+	}
+	return true;
+}
+// Sum of one double over all ranks, executed by warp 0 of ONE block per rank: every rank stores its
+// value into slot [parity][rank] of every window, raises its flag there (release), waits for the
+// flags of all ranks in its own window (acquire) and adds the slots in ascending rank order, so the
+// result is bitwise identical on every rank.  `a` is taken from lane 0, the result is valid in lane 0.
+__device__ inline double ug_warp_allreduce(double a, const UgAr& ar)
+{
+	const int lane = threadIdx.x & 31;
+	a = __shfl_sync(0xffffffffu, a, 0);
+	const unsigned long long e = *(volatile unsigned long long*)ar.epoch + 1ull;
+	const int par = (int)(e & 1ull);
+	__syncwarp();
+	if (lane < ar.nranks) {
+		char* pw = ar.peer[lane];
+		double* slot = reinterpret_cast<double*>(pw + kP2PArDataOff) + (size_t)(par * kP2PMaxRanks + ar.rank) * kP2PArMax;
+		ug_st_relaxed_sys(slot, a);
+		ug_st_release_sys(reinterpret_cast<unsigned long long*>(pw + kP2PArFlagOff) + ar.rank, e);
+		ug_wait_flag(reinterpret_cast<const unsigned long long*>(ar.local + kP2PArFlagOff) + lane, e, ar.err);
+	}
+	__syncwarp();
+	double s = 0.0;
+	if (lane == 0) {
+		const double* base = reinterpret_cast<const double*>(ar.local + kP2PArDataOff) + (size_t)par * kP2PMaxRanks * kP2PArMax;
+		for (int p = 0; p < ar.nranks; ++p) {
+			const double x = ug_ld_relaxed_sys(base + (size_t)p * kP2PArMax);
+			s = (p == 0) ? x : s + x;
+		}
+		*(volatile unsigned long long*)ar.epoch = e;
+	}
+	return s;
+}
+
 // ---- deterministic block reduction + last-block finalisation --------------------
 // Every block reduces its value (fixed shuffle tree), writes partials[blockIdx.x];
 // the last block to arrive sums the partials in a fixed order and applies `fin`.
@@ -137,7 +259,8 @@ __device__ __forceinline__ double ug_warp_sum(double v)
 	return v;
 }
 // must be called by all threads of the block; blockDim.x multiple of 32, <= 1024
-__device__ inline void ug_block_reduce_fin(double v, double* partials, unsigned int* counter, const ug4b200_fin& fin)
+__device__ inline void ug_block_reduce_fin(double v, double* partials, unsigned int* counter, const ug4b200_fin& fin,
+                                           const UgAr& ar = UgAr{nullptr, nullptr, nullptr, nullptr, 0, 0})
 {
 	__shared__ double s_w[32];
 	__shared__ bool s_last;
@@ -166,6 +289,7 @@ __device__ inline void ug_block_reduce_fin(double v, double* partials, unsigned 
 		if (wid == 0) {
 			a = lane < nw ? s_w[lane] : 0.0;
 			a = ug_warp_sum(a);
+			if (ar.nranks > 1) a = ug_warp_allreduce(a, ar); // local sum -> sum over ranks, same kernel
 			if (lane == 0) { *counter = 0u; ug_apply_fin(a, fin); }
 		}
 	}

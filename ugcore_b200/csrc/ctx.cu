@@ -27,6 +27,7 @@ int ug4b200_ctx_create(int device, void* stream, ug4b200_ctx** out)
 	UG_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
 	ctx->num_sms = prop.multiProcessorCount;
 	{ const char* e = getenv("UG4B200_NO_TMA"); ctx->no_tma = e && e[0] == '1'; }
+	{ const char* e = getenv("UG4B200_PDL"); ctx->pdl = e && e[0] == '1'; }
 	{ const char* e = getenv("UG4B200_TMA_ALL"); ctx->tma_all = e && e[0] == '1'; }
 	{ const char* e = getenv("UG4B200_TMA_MIN_SLICES"); if (e) ctx->tma_min_slices_per_warp = atoi(e); }
 	if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
@@ -46,6 +47,7 @@ int ug4b200_ctx_destroy(ug4b200_ctx* ctx)
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	if (ctx->nccl) ug4b200_comm_destroy(ctx);
+	if (ctx->p2p) ug4b200_p2p_window_destroy(ctx);
 	cudaFree(ctx->partials); cudaFree(ctx->counter); cudaFree(ctx->dev_scalar);
 	cudaFreeHost(ctx->host_scalar);
 	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -58,7 +60,7 @@ const char* ug4b200_last_error(const ug4b200_ctx* ctx) { return ctx ? ctx->err.c
 int ug4b200_sync(ug4b200_ctx* ctx)
 {
 	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	return UG4B200_OK;
+	return ug4b200_p2p_check(ctx);
 }
 void* ug4b200_stream(ug4b200_ctx* ctx) { return (void*)ctx->stream; }
 int ug4b200_launch_count(const ug4b200_ctx* ctx, int64_t* n) { *n = ctx->launches; return UG4B200_OK; }

@@ -19,6 +19,9 @@ class GPUAlgebraLayouts {
 	GPUAlgebraLayouts(int nneigh, const int* neighRank, const int64_t* neighPtr, const int* indices, int64_t nlocal)
 	{
 		UG_GPU_CHECK(ug4b200_interface_create(GPUManager::ctx(), nneigh, neighRank, neighPtr, indices, nlocal, &m_iface));
+		// peer-window transport: look up where the neighbours receive (they publish it when they
+		// create the same interface; every rank builds its layouts in the same order)
+		UG_GPU_CHECK(ug4b200_interface_commit(GPUManager::ctx(), m_iface));
 	}
 	~GPUAlgebraLayouts() { if (m_iface && GPUManager::ctx_or_null()) ug4b200_interface_destroy(GPUManager::ctx_or_null(), m_iface); }
 	ug4b200_interface* iface() const { return m_iface; }

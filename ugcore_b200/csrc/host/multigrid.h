@@ -43,6 +43,7 @@ class StdTransfer {
 		}
 		m_P->device(); m_R->device();
 	}
+	number restriction_damping() const { return m_dampRes; }
 	SmartPtr<GPUTransferMatrix> prolongation() { return m_P; }
 	SmartPtr<GPUTransferMatrix> restriction() { return m_R; }
 	/// uFine = dampProl * P * uCoarse   (std_transfer_impl.h:738-740)
@@ -185,20 +186,37 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 		ug4b200_ctx* ctx = GPUManager::ctx();
 		LevData& top = level(m_topLev);
 		THROW_IF_NOT_EQUAL(d.size(), top.sd.size());
+		m_pTopC = nullptr; m_pTopD = nullptr;
 		// project defect from surface to level (:211-217)
-		if (m_dSurfMap) UG_GPU_CHECK(ug4b200_vec_gather(ctx, (int64_t)top.sd.size(), B, top.sd.dev(), d.dev(), m_dSurfMap));
-		else UG_GPU_CHECK(ug4b200_vec_copy(ctx, top.sd.len(), top.sd.dev(), d.dev()));
-		top.sd.set_storage_type(d.get_storage_mask());
-		top.sc.set(0.0);                       // :234
+		if (m_dSurfMap) {
+			UG_GPU_CHECK(ug4b200_vec_gather(ctx, (int64_t)top.sd.size(), B, top.sd.dev(), d.dev(), m_dSurfMap));
+			top.sd.set_storage_type(d.get_storage_mask());
+		} else {
+			// identity map (full refinement): the top level accumulates its correction straight into c,
+			// and the fused Jacobi pre-smoother reads the caller's defect in its first step — neither
+			// the surface->level copy of d nor the level->surface copy of the correction is needed
+			if (m_topLev > m_baseLev && &c != &d) {
+				THROW_IF_NOT_EQUAL(c.size(), top.sc.size());
+				m_pTopC = &c;
+				if (m_numPreSmooth > 0 && fused_jacobi(top.PreSmoother)) m_pTopD = &d;
+			}
+			if (!m_pTopD) {
+				UG_GPU_CHECK(ug4b200_vec_copy(ctx, top.sd.len(), top.sd.dev(), d.dev()));
+				top.sd.set_storage_type(d.get_storage_mask());
+			}
+		}
+		top.scZero = true;                     // sc = 0 (:234), carried out by the first accumulation
+		if (m_topLev == m_baseLev) materialize_sc(m_topLev);
 		lmgc(m_topLev, m_cycleType);           // :238
 		// c = 0 (:231) ; c[surf] += sc[lev] (:244-248)
 		if (m_dSurfMap) {
 			c.set(0.0);
 			UG_GPU_CHECK(ug4b200_vec_scatter_add(ctx, (int64_t)top.sc.size(), B, c.dev(), m_dSurfMap, top.sc.dev()));
-		} else {
+		} else if (!m_pTopC) {
 			// 0.0 + sc == sc bit for bit (up to the sign of zero)
 			UG_GPU_CHECK(ug4b200_vec_copy(ctx, c.len(), c.dev(), top.sc.dev()));
 		}
+		m_pTopC = nullptr; m_pTopD = nullptr;
 		c.set_storage_type(PST_CONSISTENT);
 		const number kappa = this->damping()->damping(c, d, m_spSurfaceMat);
 		if (kappa != 1.0) c *= kappa;          // :259-260
@@ -220,12 +238,31 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 		SmartPtr<smoother_type> PreSmoother, PostSmoother;
 		vector_type sc, sd, st, st2;
 		SmartPtr<GPUAlgebraLayouts> layouts;
+		bool scZero = false;   // sc is logically 0: the next accumulation assigns (UG4B200_SMOOTH_SC_ZERO)
+		bool stReady = false;  // st already holds S*sd (produced by the fused restriction of the finer level)
 	};
 	LevData& level(int lev)
 	{
 		if (lev < 0) UG_THROW("GMG: negative level");
 		if ((int)m_vLevData.size() <= lev) { const size_t o = m_vLevData.size(); m_vLevData.resize(lev + 1); for (size_t i = o; i < m_vLevData.size(); ++i) m_vLevData[i] = make_sp<LevData>(); }
 		return *m_vLevData[lev];
+	}
+	/// correction of a level; on the top level of a fully refined hierarchy this is the caller's c
+	vector_type& SC(int lev) { return (lev == m_topLev && m_pTopC) ? *m_pTopC : level(lev).sc; }
+	void materialize_sc(int lev)
+	{
+		LevData& ld = level(lev);
+		if (ld.scZero) { SC(lev).set(0.0); ld.scZero = false; }
+	}
+	Jacobi<TAlgebra>* fused_jacobi(SmartPtr<smoother_type> s)
+	{
+		if (!m_bFuseJacobi || !s) return nullptr;
+		Jacobi<TAlgebra>* j = dynamic_cast<Jacobi<TAlgebra>*>(s.get());
+		return (j && j->damping()->constant_damping()) ? j : nullptr;
+	}
+	bool base_solver_overwrites() const
+	{
+		return dynamic_cast<LU<TAlgebra>*>(m_spBaseSolver.get()) != nullptr || dynamic_cast<CoarseCG<TAlgebra>*>(m_spBaseSolver.get()) != nullptr;
 	}
 	void make_consistent(vector_type& v)
 	{
@@ -251,31 +288,52 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 	{
 		ug4b200_ctx* ctx = GPUManager::ctx();
 		LevData& lf = level(lev); LevData& lc = level(lev - 1);
-		Jacobi<TAlgebra>* jac = m_bFuseJacobi ? dynamic_cast<Jacobi<TAlgebra>*>(lf.PreSmoother.get()) : nullptr;
-		if (jac && jac->damping()->constant_damping() && m_numPreSmooth > 0) {
+		Jacobi<TAlgebra>* jac = fused_jacobi(lf.PreSmoother);
+		if (jac && m_numPreSmooth > 0) {
 			// fused: st0 = D sd ; then per step one kernel  { sc += st ; sd -= A st ; [st' = D sd] }
 			const int64_t n = (int64_t)lf.sd.size();
 			vector_type* cur = &lf.st; vector_type* alt = &lf.st2;
-			UG_GPU_CHECK(ug4b200_jacobi_step(ctx, n, B, jac->diag_inv_dev(), cur->dev(), lf.sd.dev()));
-			make_consistent(*cur);
+			const vector_type* dsrc = (lev == m_topLev) ? m_pTopD : nullptr; // defect still in the caller's vector
+			if (!lf.stReady) {
+				UG_GPU_CHECK(ug4b200_jacobi_step(ctx, n, B, jac->diag_inv_dev(), cur->dev(), dsrc ? dsrc->dev() : lf.sd.dev()));
+				make_consistent(*cur);
+			}
+			lf.stReady = false;
 			for (int nu = 0; nu < m_numPreSmooth; ++nu) {
 				const bool last = (nu == m_numPreSmooth - 1);
-				const int flags = UG4B200_SMOOTH_ADD_IN | (last ? 0 : UG4B200_SMOOTH_JACOBI);
-				UG_GPU_CHECK(ug4b200_jacobi_smooth_fused(ctx, lf.A->device(), jac->diag_inv_dev(), lf.sd.dev(), cur->dev(),
-				                                         last ? nullptr : alt->dev(), lf.sc.dev(), flags));
+				const int flags = UG4B200_SMOOTH_ADD_IN | (last ? 0 : UG4B200_SMOOTH_JACOBI) | (lf.scZero ? UG4B200_SMOOTH_SC_ZERO : 0);
+				UG_GPU_CHECK(ug4b200_jacobi_smooth_fused_src(ctx, lf.A->device(), jac->diag_inv_dev(), lf.sd.dev(),
+				                                             dsrc ? dsrc->dev() : nullptr, cur->dev(), last ? nullptr : alt->dev(),
+				                                             SC(lev).dev(), flags));
+				if (dsrc) { lf.sd.set_storage_type(dsrc->get_storage_mask()); dsrc = nullptr; }
+				lf.scZero = false;
 				if (!last) { make_consistent(*alt); std::swap(cur, alt); }
 			}
-			lc.sc.set(0.0);
 		} else {
+			if (m_numPreSmooth > 0) materialize_sc(lev);
 			for (int nu = 0; nu < m_numPreSmooth; ++nu) {
 				if (!lf.PreSmoother->apply(lf.st, lf.sd)) UG_THROW("GMG: Smoothing step " << nu + 1 << " on level " << lev << " failed.");
 				lf.A->apply_sub(lf.sd, lf.st);                      // :1726
-				if (nu < m_numPreSmooth - 1) lf.sc += lf.st;        // :1729-1730
+				if (nu < m_numPreSmooth - 1) SC(lev) += lf.st;      // :1729-1730
 			}
-			lc.sc.set(0.0);                                         // :1780
-			if (m_numPreSmooth > 0) lf.sc += lf.st;                 // :1783-1784
+			if (m_numPreSmooth > 0) SC(lev) += lf.st;               // :1783-1784
 		}
-		lf.transfer->do_restrict(lc.sd, lf.sd);                     // :1802
+		// sc_{l-1} = 0 (:1780): deferred to the first accumulation; the base solvers overwrite it
+		if (lev - 1 == m_baseLev && base_solver_overwrites()) lc.scZero = false;
+		else lc.scZero = true;
+		// restriction (:1802); with a fused Jacobi pre-smoother on the coarse level its first step
+		// st = D sd is computed by the same kernel
+		Jacobi<TAlgebra>* jc = (lev - 1 > m_baseLev && m_numPreSmooth > 0 && B == 1) ? fused_jacobi(lc.PreSmoother) : nullptr;
+		if (jc) {
+			UG_GPU_CHECK(ug4b200_restrict_jacobi_fused(ctx, lf.transfer->restriction()->device(), jc->diag_inv_dev(), lc.sd.dev(),
+			                                           lf.transfer->restriction_damping(), lf.sd.dev(), lc.st.dev()));
+			lc.sd.set_storage_type(lf.sd.get_storage_mask());
+			make_consistent(lc.st);
+			lc.stReady = true;
+		} else {
+			lf.transfer->do_restrict(lc.sd, lf.sd);
+			lc.stReady = false;
+		}
 	}
 
 	/// mg_solver_impl.hpp:1818-1964
@@ -283,24 +341,33 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 	{
 		ug4b200_ctx* ctx = GPUManager::ctx();
 		LevData& lf = level(lev); LevData& lc = level(lev - 1);
-		lf.transfer->prolongate(lf.st, lc.sc);                      // :1865
-		Jacobi<TAlgebra>* jac = m_bFuseJacobi ? dynamic_cast<Jacobi<TAlgebra>*>(lf.PostSmoother.get()) : nullptr;
-		if (jac && jac->damping()->constant_damping()) {
+		lc.stReady = false;
+		materialize_sc(lev - 1);
+		lf.transfer->prolongate(lf.st, SC(lev - 1));                // :1865
+		Jacobi<TAlgebra>* jac = fused_jacobi(lf.PostSmoother);
+		if (jac) {
 			vector_type* cur = &lf.st; vector_type* alt = &lf.st2;
+			// without interfaces the last step's output needs no exchange and is accumulated in the kernel
+			const bool addOut = !lf.layouts && m_numPostSmooth > 0;
 			for (int nu = 0; nu < m_numPostSmooth; ++nu) {
+				const bool last = (nu == m_numPostSmooth - 1);
+				const int flags = UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_JACOBI | (lf.scZero ? UG4B200_SMOOTH_SC_ZERO : 0) |
+				                  ((last && addOut) ? UG4B200_SMOOTH_ADD_OUT : 0);
 				UG_GPU_CHECK(ug4b200_jacobi_smooth_fused(ctx, lf.A->device(), jac->diag_inv_dev(), lf.sd.dev(), cur->dev(), alt->dev(),
-				                                         lf.sc.dev(), UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_JACOBI));
+				                                         SC(lev).dev(), flags));
+				lf.scZero = false;
 				make_consistent(*alt);
 				std::swap(cur, alt);
 			}
-			lf.sc += *cur;                                          // last :1905 / :1943
+			if (!addOut) { materialize_sc(lev); SC(lev) += *cur; }   // last :1905 / :1943
 			if (m_bFinalDefect && lev >= m_topLev) lf.A->apply_sub(lf.sd, *cur);
 		} else {
-			lf.sc += lf.st;                                         // :1905
+			materialize_sc(lev);
+			SC(lev) += lf.st;                                       // :1905
 			for (int nu = 0; nu < m_numPostSmooth; ++nu) {
 				lf.A->apply_sub(lf.sd, lf.st);                      // :1919
 				if (!lf.PostSmoother->apply(lf.st, lf.sd)) UG_THROW("GMG: Smoothing step " << nu + 1 << " on level " << lev << " failed.");
-				lf.sc += lf.st;                                     // :1943
+				SC(lev) += lf.st;                                   // :1943
 			}
 			if (m_bFinalDefect && lev >= m_topLev) lf.A->apply_sub(lf.sd, lf.st); // :1954-1958
 		}
@@ -322,6 +389,7 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 			UG_GPU_CHECK(ug4b200_vec_gather(ctx, (int64_t)ld.sc.size(), B, ld.sc.dev(), m_gatheredC.dev(), m_dBaseMap));
 			ld.sc.set_storage_type(PST_CONSISTENT);
 		}
+		ld.scZero = false;
 		if (lev >= m_topLev) ld.A->apply_sub(ld.sd, ld.sc);         // :2075-2078
 	}
 
@@ -334,6 +402,8 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 	std::vector<SmartPtr<LevData> > m_vLevData;
 	std::vector<int> m_surfMap;
 	int* m_dSurfMap = nullptr;
+	vector_type* m_pTopC = nullptr;        // set during apply(): the caller's c doubles as the top level's sc
+	const vector_type* m_pTopD = nullptr;  // set during apply(): the caller's d is read by the first smoothing step
 	// gathered base
 	SmartPtr<matrix_operator_type> m_spGatheredA;
 	std::vector<int> m_baseLocalToGlobal;

@@ -125,10 +125,8 @@ class CG : public IPreconditionedLinearOperatorInverse<TVector> {
 	{
 		ug4b200_ctx* c = GPUManager::ctx();
 		if (!parallel) { UG_GPU_CHECK(ug4b200_vec_dot_ds(c, a.len(), a.dev(), bvec.dev(), fin)); return; }
-		ug4b200_fin st{UG4B200_FIN_STORE, m_ks.s + KS::TMP, nullptr, nullptr, nullptr};
-		UG_GPU_CHECK(ug4b200_vec_dot_ds(c, a.len(), a.dev(), bvec.dev(), st));
-		UG_GPU_CHECK(ug4b200_allreduce_sum(c, m_ks.s + KS::TMP, 1));
-		UG_GPU_CHECK(ug4b200_scalar_fin_ds(c, m_ks.s + KS::TMP, fin));
+		// local dot + sum over ranks + finaliser: one kernel over the peer windows, three launches over NCCL
+		UG_GPU_CHECK(ug4b200_vec_dot_allreduce_ds(c, a.len(), a.dev(), bvec.dev(), fin, m_ks.s + KS::TMP));
 	}
 	void norm_fin(vector_type& r, int op, bool parallel)
 	{

@@ -168,6 +168,7 @@ __global__ void scalar_fin_kernel(const double* r, ug4b200_fin fin, const int* g
 __global__ void conv_init_kernel(ug4b200_conv_state* s, int max_steps, double min_defect, double rel_reduction,
                                  double* history, int cap)
 {
+	ug_pdl_sync();
 	s->initial_defect = 0; s->current_defect = 0; s->last_defect = 0;
 	s->min_defect = min_defect; s->rel_reduction = rel_reduction;
 	s->step = 0; s->max_steps = max_steps; s->done = 0; s->status = 0;

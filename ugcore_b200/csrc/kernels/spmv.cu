@@ -26,7 +26,7 @@ constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 
 enum { MODE_ASSIGN = 0, MODE_ASSIGN_SKIP_EMPTY = 1, MODE_INPLACE = 2, MODE_GENERAL = 3 };
-enum { FUSE_NONE = 0, FUSE_DOT = 1, FUSE_JACOBI = 2 };
+enum { FUSE_NONE = 0, FUSE_DOT = 1, FUSE_JACOBI = 2, FUSE_RESTRICT_JACOBI = 3 };
 
 struct Sell {
 	const int64_t* slice_ptr; const int* rowlen; const int* cols; const double* vals;
@@ -86,9 +86,10 @@ spmv1_kernel(Sell A, double* dest, const double* v, double alpha, double beta, c
 		if (MODE == MODE_INPLACE) { if (live) acc = dest[row]; }
 		else if (MODE == MODE_GENERAL) { if (live) acc = alpha * v[row]; }
 		if (FUSE == FUSE_DOT) { if (live) own = w[row]; }
+		if (FUSE == FUSE_RESTRICT_JACOBI && live) { dinv = fz.diaginv[row]; if (len == 0) own = dest[row]; }
 		if (FUSE == FUSE_JACOBI && live) {
 			if (fz.flags & UG4B200_SMOOTH_ADD_IN) own = w[row];
-			if (fz.flags & (UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_ADD_OUT)) scv = fz.sc[row];
+			if ((fz.flags & (UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_ADD_OUT)) && !(fz.flags & UG4B200_SMOOTH_SC_ZERO)) scv = fz.sc[row];
 			if (fz.flags & UG4B200_SMOOTH_JACOBI) dinv = fz.diaginv[row];
 		}
 		for (int k = 0; k < width; k += UNR) {
@@ -129,6 +130,14 @@ spmv1_kernel(Sell A, double* dest, const double* v, double alpha, double beta, c
 					if (fz.flags & UG4B200_SMOOTH_ADD_OUT) scv = scv + st;
 				}
 				if (fz.flags & (UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_ADD_OUT)) fz.sc[row] = scv;
+			}
+		} else if (FUSE == FUSE_RESTRICT_JACOBI) {
+			// coarse defect by restriction (rows without connections keep their value), then the first
+			// Jacobi step of the coarse level on it: st = diagInv * sd
+			if (live) {
+				double dv = own;
+				if (len > 0) { dest[row] = acc; dv = acc; }
+				fz.st_out[row] = dinv * dv;
 			}
 		} else {
 			if (live && (MODE != MODE_ASSIGN_SKIP_EMPTY || len > 0)) dest[row] = acc;
@@ -349,9 +358,11 @@ int launch_mode(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* dest, const d
 		bool used = false;
 		// measured (profiles/r01b): the bulk-copy kernel wins for the fused variants, the
 		// register-staged one for the plain sweep
-		if (!ctx->no_tma && (FUSE != FUSE_NONE || ctx->tma_min_slices_per_warp == 0 || ctx->tma_all)) {
-			const int rc = launch_tma<BETAK, MODE, FUSE>(ctx, S, dest, v, alpha, beta, w, fz, &used);
-			if (rc) return rc;
+		if constexpr (FUSE != FUSE_RESTRICT_JACOBI) {
+			if (!ctx->no_tma && (FUSE != FUSE_NONE || ctx->tma_min_slices_per_warp == 0 || ctx->tma_all)) {
+				const int rc = launch_tma<BETAK, MODE, FUSE>(ctx, S, dest, v, alpha, beta, w, fz, &used);
+				if (rc) return rc;
+			}
 		}
 		if (!used)
 			UG_LAUNCH(ctx, (spmv1_kernel<BETAK, MODE, FUSE>), grid, kThreads, 0, S, dest, v, alpha, beta, w, fz, ctx->guard);
@@ -360,6 +371,8 @@ int launch_mode(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* dest, const d
 		if (vblock == 2) { UG_LAUNCH(ctx, (spmv1xV_kernel<2, BETAK, MODE>), grid, kThreads, 0, S, dest, v, alpha, beta, w, ctx->guard); }
 		else if (vblock == 3) { UG_LAUNCH(ctx, (spmv1xV_kernel<3, BETAK, MODE>), grid, kThreads, 0, S, dest, v, alpha, beta, w, ctx->guard); }
 		else return ug4b200_fail(ctx, UG4B200_ERR_ARG, "vector block size must be 1, 2 or 3");
+	} else if (FUSE == FUSE_RESTRICT_JACOBI) {
+		return ug4b200_fail(ctx, UG4B200_ERR_ARG, "restrict_jacobi_fused is implemented for scalar vectors only");
 	} else if (A->block == vblock) {
 		if (vblock == 2) { UG_LAUNCH(ctx, (spmvB_kernel<2, BETAK, MODE, FUSE>), grid, kThreads, 0, S, dest, v, alpha, beta, w, fz, ctx->guard); }
 		else if (vblock == 3) { UG_LAUNCH(ctx, (spmvB_kernel<3, BETAK, MODE, FUSE>), grid, kThreads, 0, S, dest, v, alpha, beta, w, fz, ctx->guard); }
@@ -380,6 +393,7 @@ int launch_beta(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* dest, const d
 
 __global__ void get_diag_kernel(Sell A, const int* __restrict__ diagpos, int B, double* diag)
 {
+	ug_pdl_sync();
 	const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (row >= A.nrows) return;
 	const int BB = B * B;
@@ -395,6 +409,7 @@ __global__ void get_diag_kernel(Sell A, const int* __restrict__ diagpos, int B, 
 __global__ void jacobi_invert_kernel(int64_t nrows, int B, double invdamp, int block_inverse, const double* diag,
                                      double* diaginv)
 {
+	ug_pdl_sync();
 	const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (row >= nrows) return;
 	const int BB = B * B;
@@ -561,16 +576,33 @@ int ug4b200_matrix_apply_dot_ds(ug4b200_ctx* ctx, const ug4b200_matrix* A, doubl
 	Fuse fz{}; fz.partials = ctx->partials; fz.counter = ctx->counter; fz.fin = fin;
 	return launch_mode<1, MODE_ASSIGN, FUSE_DOT>(ctx, A, y, nullptr, 0.0, 1.0, x, A->block, fz);
 }
-int ug4b200_jacobi_smooth_fused(ug4b200_ctx* ctx, const ug4b200_matrix* A, const double* diaginv, double* sd,
-                                const double* st_in, double* st_out, double* sc, int flags)
+int ug4b200_jacobi_smooth_fused_src(ug4b200_ctx* ctx, const ug4b200_matrix* A, const double* diaginv, double* sd,
+                                    const double* sd_in, const double* st_in, double* st_out, double* sc, int flags)
 {
 	UG_ARG(ctx, A && sd && st_in, "NULL argument");
 	UG_ARG(ctx, A->nrows == A->ncols, "square matrix needed");
 	UG_ARG(ctx, !(flags & UG4B200_SMOOTH_JACOBI) || (diaginv && st_out), "JACOBI needs diaginv and st_out");
 	UG_ARG(ctx, !(flags & (UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_ADD_OUT)) || sc, "ADD_* needs sc");
-	UG_ARG(ctx, st_in != st_out && sd != st_in && sc != st_in, "st_in must not alias an output");
+	UG_ARG(ctx, st_in != st_out && sd != st_in && sc != st_in && sd_in != st_out, "st_in must not alias an output");
 	Fuse fz{}; fz.diaginv = diaginv; fz.st_out = st_out; fz.sc = sc; fz.flags = flags;
-	return launch_mode<-1, MODE_INPLACE, FUSE_JACOBI>(ctx, A, sd, sd, 1.0, -1.0, st_in, A->block, fz);
+	if (sd_in == nullptr || sd_in == sd)
+		return launch_mode<-1, MODE_INPLACE, FUSE_JACOBI>(ctx, A, sd, sd, 1.0, -1.0, st_in, A->block, fz);
+	// sd = 1.0*sd_in - A*st_in: the defect is read from another vector (no copy beforehand)
+	return launch_mode<-1, MODE_GENERAL, FUSE_JACOBI>(ctx, A, sd, sd_in, 1.0, -1.0, st_in, A->block, fz);
+}
+int ug4b200_jacobi_smooth_fused(ug4b200_ctx* ctx, const ug4b200_matrix* A, const double* diaginv, double* sd,
+                                const double* st_in, double* st_out, double* sc, int flags)
+{ return ug4b200_jacobi_smooth_fused_src(ctx, A, diaginv, sd, nullptr, st_in, st_out, sc, flags); }
+
+int ug4b200_restrict_jacobi_fused(ug4b200_ctx* ctx, const ug4b200_matrix* R, const double* diaginv_coarse,
+                                  double* sd_coarse, double beta, const double* sd_fine, double* st_coarse)
+{
+	UG_ARG(ctx, R && diaginv_coarse && sd_coarse && sd_fine && st_coarse, "NULL argument");
+	UG_ARG(ctx, R->block == 1, "scalar transfer matrix needed");
+	UG_ARG(ctx, sd_coarse != sd_fine && st_coarse != sd_fine && st_coarse != sd_coarse, "arguments must not alias");
+	Fuse fz{}; fz.diaginv = diaginv_coarse; fz.st_out = st_coarse;
+	if (beta == 1.0) return launch_mode<1, MODE_ASSIGN_SKIP_EMPTY, FUSE_RESTRICT_JACOBI>(ctx, R, sd_coarse, nullptr, 0.0, beta, sd_fine, 1, fz);
+	return launch_mode<0, MODE_ASSIGN_SKIP_EMPTY, FUSE_RESTRICT_JACOBI>(ctx, R, sd_coarse, nullptr, 0.0, beta, sd_fine, 1, fz);
 }
 
 int ug4b200_jacobi_prepare(ug4b200_ctx* ctx, const ug4b200_matrix* A, double damp, int block_inverse, double* diaginv)

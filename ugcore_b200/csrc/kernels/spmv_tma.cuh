@@ -134,7 +134,7 @@ spmv1_tma_kernel(Sell A, double* dest, const double* v, double alpha, double bet
 		if (FUSE == FUSE_DOT) { if (live) own = w[row]; }
 		if (FUSE == FUSE_JACOBI && live) {
 			if (fz.flags & UG4B200_SMOOTH_ADD_IN) own = w[row];
-			if (fz.flags & (UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_ADD_OUT)) scv = fz.sc[row];
+			if ((fz.flags & (UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_ADD_OUT)) && !(fz.flags & UG4B200_SMOOTH_SC_ZERO)) scv = fz.sc[row];
 			if (fz.flags & UG4B200_SMOOTH_JACOBI) dinv = fz.diaginv[row];
 		}
 		const int64_t my_slice = cons.s;

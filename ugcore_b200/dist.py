@@ -105,6 +105,10 @@ def global_problem(refs: int, part, problem=pr.POISSON, dim=3, **kw) -> pr.Probl
     return pr.Problem(dim=dim, num_refs=refs, problem=problem, base=tuple(part), base_lev=0, **kw)
 
 
+_nccl_ready = False
+_p2p_state = None  # None: not tried, True / False: outcome (identical on all ranks)
+
+
 def nccl_bootstrap(dist) -> None:
     """Rank 0 draws the NCCL unique id, torch.distributed broadcasts it, every rank joins."""
     import ctypes as C
@@ -113,7 +117,11 @@ def nccl_bootstrap(dist) -> None:
 
     from .capi import check, check_host, dev, host
     from .solver import host_init
+    global _nccl_ready
     host_init()
+    if _nccl_ready:
+        return
+    _nccl_ready = True
     ident = (C.c_ubyte * 128)()
     if dist.get_rank() == 0:
         check(dev.ug4b200_comm_unique_id(ident))
@@ -125,11 +133,60 @@ def nccl_bootstrap(dist) -> None:
     check_host(host.ug4b200_host_comm_init(dist.get_world_size(), dist.get_rank(), ident))
 
 
+def p2p_bootstrap(dist) -> bool:
+    """Open the peer windows: every rank allocates its window, torch.distributed carries the
+    64-byte CUDA IPC handles, every rank maps the windows of all others.  All ranks agree on the
+    outcome; on failure (or UG4B200_P2P=0) the NCCL transport stays in use."""
+    import ctypes as C
+    import os
+
+    import torch
+
+    from .capi import dev
+    from .solver import host_ctx
+    global _p2p_state
+    if _p2p_state is not None:
+        return _p2p_state
+    world, rank = dist.get_world_size(), dist.get_rank()
+    cuda = dist.get_backend() == "nccl"
+    ctx = host_ctx()
+
+    def agree(ok: bool) -> bool:
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32)
+        if cuda:
+            t = t.cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(int(t.item()))
+
+    want = os.environ.get("UG4B200_P2P", "1") != "0" and world > 1
+    handle = (C.c_ubyte * 64)()
+    ok = want and dev.ug4b200_p2p_window_create(ctx, 0, handle, None) == 0
+    created = ok
+    mine = torch.tensor(list(handle), dtype=torch.uint8)
+    if cuda:
+        mine = mine.cuda()
+    allh = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine)
+    ok = agree(ok)
+    if ok:
+        buf = (C.c_ubyte * (64 * world))(*[int(v) for t in allh for v in t.cpu().tolist()])
+        rc = dev.ug4b200_p2p_window_open(ctx, world, rank, buf)
+        if rc != 0 and rank == 0:
+            msg = dev.ug4b200_last_error(ctx)
+            print(f"ugcore_b200: peer windows unavailable ({msg.decode() if msg else rc}); using NCCL send/recv", flush=True)
+        ok = agree(rc == 0)
+    if not ok and created:
+        dev.ug4b200_p2p_window_destroy(ctx)
+    _p2p_state = ok
+    return ok
+
+
 def build_partitioned_solver(desc: dict, refs: int, part, rank: int, dist, problem=pr.POISSON, flags: int = 0, **kw):
     """Wire a GMG-preconditioned solver on this rank's sub-box: local additive level matrices,
     interface layouts per level, gathered (replicated, all-reduced) base solve."""
     from .solver import Solver
     nccl_bootstrap(dist)
+    p2p_bootstrap(dist)
     prob = local_problem(refs, part, rank, problem=problem, **kw)
     desc = dict(desc)
     pc = dict(desc["precond"])
