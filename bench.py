@@ -9,9 +9,11 @@ GMG V(2,2) damped Jacobi (0.66) preconditioning CG, StdConvCheck(100, 1e-12, 1e-
 Prints ONE JSON line (see the contract in the task description / DESIGN.md §Measurement).
 
 `--impl reference` times ugcore's own CPU kernels (oracle/_ref: SparseMatrix/Vector/
-smoother templates compiled from the reference) driving the restated solver loop on the
-host cores — the reference has no threading on this path and no MPI is installed, so
-cores = 1.  This is the only place bench.py executes anything under oracle/.
+smoother templates compiled from the reference) driving the restated solver loop on ALL
+host cores: the reference has no threading on this path and no MPI is installed, so every
+core runs one serial solve of the workload concurrently (an upper bound for the MPI path:
+no interface exchange).  This and `cpu_baseline` are the only places bench.py executes
+anything under oracle/.
 """
 from __future__ import annotations
 
@@ -95,42 +97,78 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def run_reference(args):
-    """CPU arm: ugcore's own kernels (oracle/_ref) or the port, one core."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def _cpu_replica(refs, steps, warmup, barrier, q):
+    """One CPU process = what one ugcore MPI rank does on this path: a serial GMG-CG solve with
+    the reference's own kernels (oracle/_ref) or the port."""
+    os.environ["OMP_NUM_THREADS"] = "1"
     import oracle
     from ugcore_b200 import problems as pr
     kind = "ref" if oracle.have_ref() else "port"
     orc = oracle.Oracle(kind)
-    refs = args.cpu_refs
     prob = pr.Problem(dim=3, num_refs=refs)
-    desc = solver_desc(refs)
     lv = {}
     for l in range(0, refs + 1):
         lv[l] = (orc.matrix(prob.matrix(l)), orc.matrix(prob.prolongation(l)) if l else None,
                  orc.matrix(prob.restriction(l)) if l else None)
-    s = oracle.OSolver(orc, desc, lv[refs][0], lv)
+    s = oracle.OSolver(orc, solver_desc(refs), lv[refs][0], lv)
     b = np.array(prob.rhs())
-    n = prob.num_dofs
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         s.apply(b)
+    barrier.wait()
     t0 = time.perf_counter()
-    its = 0
-    for _ in range(args.steps):
+    h = None
+    for _ in range(steps):
         x, ok, h = s.apply(b)
-        its = len(h) - 1
-    dt = (time.perf_counter() - t0) / max(args.steps, 1)
-    val = n / dt / 1e6
-    sample = f"{args.steps} full solves of 3-D Poisson {2**refs + 1}^3 ({n} DoF), {its} CG iterations each"
+    dt = time.perf_counter() - t0
+    q.put({"dt": dt, "its": len(h) - 1, "n": prob.num_dofs, "kind": kind, "hist": [float(v) for v in h]})
+
+
+def cpu_replicas(refs, nproc, steps, warmup):
+    """ugcore has no threads on this path and neither MPI nor boost exist here, so
+    "all host cores" = nproc independent serial solves of the same workload running concurrently
+    (they share the memory bus like MPI ranks would, but pay no interface exchange: an upper bound
+    for ugcore's nproc-rank weak-scaling throughput).  Returns aggregate MDoF/s and details."""
+    import multiprocessing as mp
+    mpc = mp.get_context("spawn")
+    barrier, q = mpc.Barrier(nproc), mpc.Queue()
+    procs = [mpc.Process(target=_cpu_replica, args=(refs, steps, warmup, barrier, q)) for _ in range(nproc)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=3600) for _ in range(nproc)]
+    for p in procs:
+        p.join()
+    dt = max(r["dt"] for r in res)
+    n = res[0]["n"]
+    return {"value": nproc * steps * n / dt / 1e6, "dt_per_step": dt / steps, "its": res[0]["its"], "n": n,
+            "kind": "reference" if res[0]["kind"] == "ref" else "port", "cores": nproc, "hist": res[0]["hist"]}
+
+
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def run_reference(args):
+    """CPU arm: ugcore's own kernels (oracle/_ref, else the port) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    refs = args.cpu_refs
+    nproc = args.cpu_procs or host_cores()
+    r = cpu_replicas(refs, nproc, args.steps, args.warmup)
+    n, its, val, dt = r["n"], r["its"], r["value"], r["dt_per_step"]
+    sample = (f"{nproc} concurrent serial solves x {args.steps} steps of 3-D Poisson {2**refs + 1}^3 ({n} DoF, {its} CG "
+              f"iterations each, {dt:.2f} s per solve): one process per host core, no threads inside ugcore on this path, "
+              "no MPI on the box -> no interface exchange (upper bound of the MPI weak-scaling throughput)")
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"3D Poisson unit cube hexahedra numRefs={refs} ({n} DoF) GMG V(2,2) damped-Jacobi + CG, "
-                                  "ugcore CPU kernels, serial", "iterations": its},
-           "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "reference" if kind == "ref" else "port",
-                            "sample": sample},
+           "config": {"workload": f"3D Poisson unit cube hexahedra numRefs={refs} ({n} DoF per process, {nproc} processes) "
+                                  "GMG V(2,2) damped-Jacobi(0.66) + CG, StdConvCheck(100, 1e-12, 1e-10), base LU on level 0, "
+                                  "ugcore CPU kernels", "iterations": its},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": nproc, "kind": r["kind"], "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
@@ -192,26 +230,16 @@ def kernel_roofline(s, prob, top, peak_gbs, peak_src):
 
 
 def cpu_baseline_sample(refs):
-    """Bounded CPU sample for the default run: one full solve of the SAME workload with the
-    reference's kernels on one host core (~10-30 s)."""
-    import oracle
-    from ugcore_b200 import problems as pr
-    kind = "ref" if oracle.have_ref() else "port"
-    orc = oracle.Oracle(kind)
-    prob = pr.Problem(dim=3, num_refs=refs)
-    lv = {}
-    for l in range(0, refs + 1):
-        lv[l] = (orc.matrix(prob.matrix(l)), orc.matrix(prob.prolongation(l)) if l else None,
-                 orc.matrix(prob.restriction(l)) if l else None)
-    s = oracle.OSolver(orc, solver_desc(refs), lv[refs][0], lv)
-    b = np.array(prob.rhs())
-    t0 = time.perf_counter()
-    x, ok, h = s.apply(b)
-    dt = time.perf_counter() - t0
-    return {"value": prob.num_dofs / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "reference" if kind == "ref" else "port",
-            "sample": f"1 full solve of the same workload ({prob.num_dofs} DoF, {len(h) - 1} CG iterations, {dt:.1f} s), "
-                      "ugcore SparseMatrix/Vector kernels compiled from the reference, serial (no threading on this path)",
-            "solve_s": dt, "history_last": float(h[-1])}, h
+    """Bounded CPU sample for the default run: the SAME workload solved once by every host core
+    concurrently with the reference's kernels (~10-30 s including set-up)."""
+    nproc = host_cores()
+    r = cpu_replicas(refs, nproc, 1, 0)
+    serial_equiv = r["n"] / r["dt_per_step"] / 1e6
+    return {"value": r["value"], "unit": UNIT, "cores": nproc, "kind": r["kind"],
+            "sample": f"{nproc} concurrent serial solves of the same workload ({r['n']} DoF, {r['its']} CG iterations, "
+                      f"{r['dt_per_step']:.1f} s each), ugcore SparseMatrix/Vector kernels compiled from the reference; one process "
+                      "per core (no threading on this path, no MPI on the box: no interface exchange)",
+            "solve_s": r["dt_per_step"], "per_core_value": serial_equiv, "history_last": r["hist"][-1]}, np.array(r["hist"])
 
 
 def run_ours(args):
@@ -331,6 +359,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--refs", type=int, default=7, help="refinements per GPU sub-box (7 -> 129^3)")
     ap.add_argument("--cpu-refs", type=int, default=7, help="workload of the CPU reference arm")
+    ap.add_argument("--cpu-procs", type=int, default=0, help="processes of the CPU arm (0 = all host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -212,6 +212,12 @@ int ug4b200_matrix_apply_ignore_zero_rows(ug4b200_ctx* ctx, const ug4b200_matrix
 int ug4b200_matrix_apply_dot_ds(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* y, const double* x,
                                 ug4b200_fin fin);
 
+/* same, the reduction summed over all ranks before fin is applied (ParallelVector::dotprod of an
+ * additive q with a consistent p, parallel_vector_impl.h:323-379): one kernel with the peer-window
+ * transport, apply_dot -> ncclAllReduce -> finaliser through scratch_dev (1 double) otherwise */
+int ug4b200_matrix_apply_dot_allreduce_ds(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* y, const double* x,
+                                          ug4b200_fin fin, double* scratch_dev);
+
 /* ------------------------------------------------------------------ smoothers */
 
 /* Jacobi::preprocess (jacobi.h:196-220): diaginv[i] = inverse(A_ii * (1./damp));
@@ -299,6 +305,10 @@ int ug4b200_interface_destroy(ug4b200_ctx* ctx, ug4b200_interface* I);
  * DoF ends up with the sum over all copies, summed in ascending rank order on every
  * rank (bitwise identical copies). */
 int ug4b200_additive_to_consistent(ug4b200_ctx* ctx, ug4b200_interface* I, double* v, int block);
+/* AdditiveToUnique (parallelization_util.h:260-280): the h-master copy gets the sum over all
+ * copies (same ascending-rank order), every other copy becomes 0 — one kernel with the
+ * peer-window transport */
+int ug4b200_additive_to_unique(ug4b200_ctx* ctx, ug4b200_interface* I, double* v, int block);
 /* Peer-window transport (preferred inside one NVSwitch box; replaces the MPI_Isend/Irecv
  * transport of pcl_interface_communicator_impl.hpp:560-661 and MPI_Allreduce,
  * pcl_process_communicator.cpp:325): every rank exposes a window of device memory to the
@@ -329,6 +339,17 @@ int ug4b200_interface_commit(ug4b200_ctx* ctx, ug4b200_interface* I);
  * dot -> ncclAllReduce -> finaliser through scratch_dev (1 double) otherwise. */
 int ug4b200_vec_dot_allreduce_ds(ug4b200_ctx* ctx, int64_t n, const double* a, const double* b, ug4b200_fin fin,
                                  double* scratch_dev);
+/* Gathered level (mg_solver_impl.hpp:2003-2070: gather the defect of a coarse level, solve
+ * there, hand the correction back).  Every rank holds the whole coarse level; gather_sum turns
+ * the local ADDITIVE vectors into the global vector summed over all ranks (ascending rank
+ * order, identical on every rank) — one kernel over the peer windows, or set/scatter/
+ * ncclAllReduce.  local_to_global: global block index of every local block index. */
+typedef struct ug4b200_gather ug4b200_gather;
+int ug4b200_gather_create(ug4b200_ctx* ctx, int64_t nglobal, int64_t nlocal, const int* local_to_global, int block,
+                          ug4b200_gather** out);
+int ug4b200_gather_commit(ug4b200_ctx* ctx, ug4b200_gather* G);
+int ug4b200_gather_sum(ug4b200_ctx* ctx, ug4b200_gather* G, double* global_out, const double* local_in);
+int ug4b200_gather_destroy(ug4b200_ctx* ctx, ug4b200_gather* G);
 /* zero every copy that is not the h-master (AdditiveToUnique after a consistent sum /
  * ConsistentToUnique, parallelization_util.h:260-280, 387-393) */
 int ug4b200_set_slaves_zero(ug4b200_ctx* ctx, ug4b200_interface* I, double* v, int block);

@@ -44,6 +44,11 @@ typedef struct ug4b200_solver_desc {
 	int base_max_steps;
 	double base_min_defect, base_rel_reduction;
 	int flags;             /* UG4B200_FLAG_* */
+	/* partitioned runs: levels base_lev..gather_lev are gathered — every rank holds them completely
+	 * and runs that part of the V-cycle redundantly (set_gathered_base / set_gathered_level), the
+	 * levels above are partitioned.  gather_lev <= base_lev: only the base solve is gathered
+	 * (mg_solver_impl.hpp:2003-2070). */
+	int gather_lev;
 } ug4b200_solver_desc;
 
 typedef struct ug4b200_solver ug4b200_solver;
@@ -77,6 +82,12 @@ int ug4b200_solver_set_layouts(ug4b200_solver* s, int lev, int nneigh, const int
 /* gathered base solve: global base-level matrix and the local -> global index map */
 int ug4b200_solver_set_gathered_base(ug4b200_solver* s, int64_t nrows, const int64_t* rowptr, const int* cols,
                                      const double* vals, int64_t nlocal, const int* local_to_global);
+/* gathered cycle (desc.gather_lev > base_lev): GLOBAL level matrix and transfers of level lev,
+ * base_lev <= lev <= gather_lev; the matrix of gather_lev itself is the one given to
+ * set_gathered_base (pass rowptr == NULL here), P/R are NULL on base_lev */
+int ug4b200_solver_set_gathered_level(ug4b200_solver* s, int lev, int64_t nrows, const int64_t* rowptr, const int* cols,
+                                      const double* vals, int64_t ncoarse, const int64_t* p_rowptr, const int* p_cols,
+                                      const double* p_vals, const int64_t* r_rowptr, const int* r_cols, const double* r_vals);
 /* solver:init(A, u): uploads, smoother preprocess, base factorisation */
 int ug4b200_solver_init(ug4b200_solver* s);
 /* solver:apply(u, b) with HOST vectors: H2D of x and b, solve, D2H of x.

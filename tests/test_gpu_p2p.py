@@ -199,3 +199,45 @@ def test_allreduce_and_fused_dot_loopback(world):
         assert abs(got[0] - ref) <= 1e-12 * max(1.0, sum(float(np.abs(a[r] * b[r]).sum()) for r in range(world)))
     finally:
         R.close()
+
+
+@pytest.mark.parametrize("world,block", [(2, 1), (8, 1), (4, 3)])
+def test_gather_sum_loopback_bit_exact(world, block):
+    """Gathered level: local additive vectors -> global sum on every rank (ascending rank order)."""
+    from ugcore_b200 import dist as ugdist
+    refs = lev = 3
+    R = Ranks(world)
+    G = []
+    try:
+        part = PART[world]
+        probs = [ugdist.local_problem(refs, part, r) for r in range(world)]
+        gids = [p.global_ids(lev).astype(np.int32) for p in probs]
+        nglobal = int(max(g.max() for g in gids)) + 1
+        for r in range(world):
+            h = C.c_void_p()
+            R.chk(r, R.dev.ug4b200_gather_create(R.ctx[r], nglobal, gids[r].size, gids[r].ctypes.data_as(C.c_void_p), block, C.byref(h)))
+            G.append(h)
+        for r in range(world):
+            R.chk(r, R.dev.ug4b200_gather_commit(R.ctx[r], G[r]))
+        rng = np.random.default_rng(7 + world)
+        rounds = 4
+        vals = [[rng.standard_normal(g.size * block) for g in gids] for _ in range(rounds)]
+        dl = [[R.up(r, vals[k][r]) for r in range(world)] for k in range(rounds)]
+        dg = [[R.up(r, np.full(nglobal * block, np.nan)) for r in range(world)] for k in range(rounds)]
+        for k in range(rounds):
+            for r in range(world):
+                R.chk(r, R.dev.ug4b200_gather_sum(R.ctx[r], G[r], dg[k][r], dl[k][r]))
+        R.sync_all()
+        for k in range(rounds):
+            acc = None
+            for r in range(world):
+                slot = np.zeros(nglobal * block)
+                gi = (gids[r][:, None].astype(np.int64) * block + np.arange(block)[None, :]).ravel()
+                slot[gi] = vals[k][r]
+                acc = slot if acc is None else acc + slot
+            for r in range(world):
+                assert np.array_equal(R.down(r, dg[k][r], nglobal * block), acc), (k, r)
+    finally:
+        for r, h in enumerate(G):
+            R.dev.ug4b200_gather_destroy(R.ctx[r], h)
+        R.close()

@@ -19,13 +19,18 @@ def _ngpu():
 
 
 # p2p = 1: peer-window transport (direct NVLink stores + flags), 0: NCCL send/recv + all-reduce
-@pytest.mark.parametrize("world,flags,p2p", [(2, 0, 1), (2, 2, 1), (2, 0, 0), (4, 0, 1), (8, 0, 1), (8, 0, 0)])
-def test_partitioned_gmg_cg_matches_serial_oracle(world, flags, p2p):
+# gather: levels 0..gather are held by every rank and cycled redundantly (-1: default rule = 2 here)
+@pytest.mark.parametrize("world,flags,p2p,gather", [(2, 0, 1, -1), (2, 2, 1, 0), (2, 0, 0, 1), (2, 0, 1, 0), (2, 0, 0, 0),
+                                                    (4, 0, 1, -1), (8, 0, 1, -1), (8, 0, 1, 0), (8, 0, 0, 1)])
+def test_partitioned_gmg_cg_matches_serial_oracle(world, flags, p2p, gather):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     env = dict(os.environ, UG4B200_P2P=str(p2p))
+    env.pop("UG4B200_GATHER_LEVEL", None)
+    if gather >= 0:
+        env["UG4B200_GATHER_LEVEL"] = str(gather)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world + flags + 20 * p2p),
+           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world + flags + 20 * p2p + 40 * (gather + 1)),
            os.path.join(ROOT, "tests", "mgpu_worker.py"), "3", str(flags)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     line = [l for l in r.stdout.splitlines() if l.startswith("MGPU_RESULT ")]

@@ -47,7 +47,7 @@ class SolverDesc(C.Structure):
                 ("max_steps", c_int), ("min_defect", c_dbl), ("rel_reduction", c_dbl),
                 ("base_lev", c_int), ("top_lev", c_int), ("cycle", c_int), ("nu1", c_int), ("nu2", c_int),
                 ("smoother", c_int), ("smoother_damp", c_dbl), ("base_solver", c_int), ("base_max_steps", c_int),
-                ("base_min_defect", c_dbl), ("base_rel_reduction", c_dbl), ("flags", c_int)]
+                ("base_min_defect", c_dbl), ("base_rel_reduction", c_dbl), ("flags", c_int), ("gather_lev", c_int)]
 
 
 FIN_STORE, FIN_A_DIV_R, FIN_R_DIV_A, FIN_SQRT, FIN_CONV_START, FIN_CONV_UPDATE = range(6)
@@ -129,8 +129,14 @@ DEV_API = {
     "ug4b200_interface_create": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_i64, C.POINTER(c_vp)]),
     "ug4b200_interface_destroy": (c_int, [c_vp, c_vp]),
     "ug4b200_additive_to_consistent": (c_int, [c_vp, c_vp, c_vp, c_int]),
+    "ug4b200_additive_to_unique": (c_int, [c_vp, c_vp, c_vp, c_int]),
+    "ug4b200_matrix_apply_dot_allreduce_ds": (c_int, [c_vp, c_vp, c_vp, c_vp, Fin, c_vp]),
     "ug4b200_set_slaves_zero": (c_int, [c_vp, c_vp, c_vp, c_int]),
     "ug4b200_vec_dot_unique_ds": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp]),
+    "ug4b200_gather_create": (c_int, [c_vp, c_i64, c_i64, c_vp, c_int, C.POINTER(c_vp)]),
+    "ug4b200_gather_commit": (c_int, [c_vp, c_vp]),
+    "ug4b200_gather_sum": (c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "ug4b200_gather_destroy": (c_int, [c_vp, c_vp]),
     "ug4b200_p2p_window_create": (c_int, [c_vp, C.c_size_t, c_vp, C.POINTER(c_vp)]),
     "ug4b200_p2p_window_open": (c_int, [c_vp, c_int, c_int, c_vp]),
     "ug4b200_p2p_window_attach": (c_int, [c_vp, c_int, c_int, C.POINTER(c_vp)]),
@@ -154,6 +160,7 @@ HOST_API = {
     "ug4b200_solver_set_coloring": (c_int, [c_vp, c_int, c_i64, c_vp, c_int, c_vp]),
     "ug4b200_solver_set_layouts": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_i64]),
     "ug4b200_solver_set_gathered_base": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "ug4b200_solver_set_gathered_level": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ug4b200_solver_init": (c_int, [c_vp]),
     "ug4b200_solver_apply": (c_int, [c_vp, c_vp, c_vp]),
     "ug4b200_solver_apply_device": (c_int, [c_vp, c_vp, c_vp]),

@@ -134,64 +134,91 @@ struct P2PNb {
 	unsigned long long* rflag;   // flag in its window that I raise
 };
 struct P2PIfaceDev {
-	int nneigh; int64_t total, nu;
-	const int* idx; const unsigned char* ent_nb; const int64_t* ptr;
+	int nneigh; int ell_w; int64_t total, nu;
+	const int* idx;                    // [total] local index of send entry
+	const int* ent_code;               // [total] (position inside the neighbour's list << 5) | neighbour slot
 	const P2PNb* nb;
 	const unsigned long long* lflag;   // [nneigh] in my window, raised by the neighbours
 	const double* lrecv;               // my receive region (2 parities x total x 9 doubles)
 	int64_t lpar_stride;
-	const int* uidx; const int* uptr; const int* usrc;
+	const int* uidx;                   // [nu] local index of every interface DoF
+	const int* uell;                   // [nu][ell_w] copies in ascending rank order: recv entry, -1 own value, -2 none
+	const unsigned char* owned;        // [nlocal] 1 where this rank is the h-master
 	unsigned long long* epoch; unsigned int* arrive; unsigned int* depart; int* err;
+	int fence_all;                     // A/B switch: every thread fences its remote stores (else: barrier + one release)
 };
 
-// AdditiveToConsistent in one kernel (grid <= #SMs so that all CTAs are co-resident:
-// CTAs that wait for a neighbour must not keep CTAs that still have to send off the SMs)
-__global__ void __launch_bounds__(256)
-p2p_exchange_sum_kernel(P2PIfaceDev d, double* v, int block, const int* guard)
+// sum of all copies of one interface DoF component; the W source loads are independent of each other
+template <int W>
+__device__ __forceinline__ void p2p_unpack(const P2PIfaceDev& d, const double* recv, double* v, int block, int unique,
+                                           int64_t tid, int64_t stride)
+{
+	for (int64_t t = tid; t < d.nu * block; t += stride) {
+		const int64_t u = t / block; const int q = (int)(t - u * block);
+		const int lidx = d.uidx[u];
+		const int64_t li = (int64_t)lidx * block + q;
+		int src[W]; double x[W];
+#pragma unroll
+		for (int k = 0; k < W; ++k) src[k] = d.uell[u * d.ell_w + k];
+		const double own = v[li];
+		const bool keep = !unique || d.owned[lidx];
+#pragma unroll
+		for (int k = 0; k < W; ++k) x[k] = src[k] >= 0 ? ug_ld_relaxed_sys(recv + (int64_t)src[k] * block + q) : own;
+		double s = x[0];
+#pragma unroll
+		for (int k = 1; k < W; ++k) if (src[k] != -2) s = s + x[k];
+		// AdditiveToUnique (parallelization_util.h:260-280): only the h-master keeps the sum
+		v[li] = keep ? s : 0.0;
+	}
+}
+
+// AdditiveToConsistent / AdditiveToUnique in one kernel.  Grid <= #SMs so that all CTAs are
+// co-resident: CTAs that wait for a neighbour must not keep CTAs that still have to send off
+// the SMs.  Small interfaces (the usual case) run as ONE CTA: no inter-CTA hand-shake at all.
+__global__ void __launch_bounds__(1024)
+p2p_exchange_sum_kernel(P2PIfaceDev d, double* v, int block, int unique, const int* guard)
 {
 	if (ug_guarded(guard)) return;
 	__shared__ bool s_last;
+	__shared__ P2PNb s_nb[32];
+	if (threadIdx.x < d.nneigh) s_nb[threadIdx.x] = d.nb[threadIdx.x];
 	const unsigned long long e = *(volatile unsigned long long*)d.epoch + 1ull;
 	const int64_t par = (int64_t)(e & 1ull);
 	const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	__syncthreads();
 	// 1. push my interface values into the neighbours' windows
 	for (int64_t t = tid; t < d.total * block; t += stride) {
 		const int64_t en = t / block; const int q = (int)(t - en * block);
-		const int n = d.ent_nb[en];
-		const P2PNb nb = d.nb[n];
-		double* dst = nb.rbase + par * nb.rpar_stride + (nb.rptr + (en - d.ptr[n])) * block + q;
-		ug_st_relaxed_sys(dst, v[(int64_t)d.idx[en] * block + q]);
+		const int code = d.ent_code[en];
+		const int li = d.idx[en];
+		const P2PNb& nb = s_nb[code & 31];
+		double* dst = nb.rbase + par * nb.rpar_stride + (nb.rptr + (code >> 5)) * block + q;
+		ug_st_relaxed_sys(dst, v[(int64_t)li * block + q]);
 	}
-	__threadfence_system();
+	// the CTA barrier orders every thread's stores before the release below (causality order is
+	// transitive through bar.sync; the same pattern as a CUTLASS semaphore release)
+	if (d.fence_all) __threadfence_system();
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		s_last = true;
 		if (gridDim.x > 1) {
-			__threadfence();
+			__threadfence_system();
 			s_last = (atomicAdd(d.arrive, 1u) == gridDim.x - 1);
-			if (s_last) { *d.arrive = 0u; __threadfence_system(); }
+			if (s_last) { *d.arrive = 0u; __threadfence_system(); } // acquire side of the other CTAs' arrivals
 		}
 	}
 	__syncthreads();
 	// 2. everything of this rank is on its way: raise my flag at every neighbour
-	if (s_last && threadIdx.x < d.nneigh) ug_st_release_sys(d.nb[threadIdx.x].rflag, e);
+	if (s_last && threadIdx.x < d.nneigh) ug_st_release_sys(s_nb[threadIdx.x].rflag, e);
 	// 3. wait for the neighbours
 	if (threadIdx.x < d.nneigh) ug_wait_flag(d.lflag + threadIdx.x, e, d.err);
 	__syncthreads();
-	// 4. sum all copies in ascending rank order (own value where usrc < 0)
+	// 4. sum all copies in ascending rank order
 	const double* recv = d.lrecv + par * d.lpar_stride;
-	for (int64_t t = tid; t < d.nu * block; t += stride) {
-		const int64_t u = t / block; const int q = (int)(t - u * block);
-		const int64_t li = (int64_t)d.uidx[u] * block + q;
-		double s = 0.0;
-		for (int p = d.uptr[u]; p < d.uptr[u + 1]; ++p) {
-			const int src = d.usrc[p];
-			const double x = src < 0 ? v[li] : ug_ld_relaxed_sys(recv + (int64_t)src * block + q);
-			s = (p == d.uptr[u]) ? x : s + x;
-		}
-		v[li] = s;
-	}
+	if (d.ell_w <= 2) p2p_unpack<2>(d, recv, v, block, unique, tid, stride);
+	else if (d.ell_w <= 4) p2p_unpack<4>(d, recv, v, block, unique, tid, stride);
+	else p2p_unpack<8>(d, recv, v, block, unique, tid, stride);
 	// 5. the last CTA to leave publishes the epoch (every CTA read it on entry)
 	__syncthreads();
 	if (threadIdx.x == 0) {
@@ -249,6 +276,78 @@ dot_allreduce_kernel(int64_t n, const double* a, const double* b, double* partia
 	ug_block_reduce_fin(acc, partials, counter, fin, ar);
 }
 
+
+// ---- gathered level: local additive vectors -> global vector summed over all ranks ----------
+struct GatherDst { double* rbase; unsigned long long* rflag; };   // my slot / my flag in rank r's window
+struct GatherDev {
+	int nranks, rank, block; int64_t nlocal, nglobal;               // in blocks
+	const int* l2g; const GatherDst* dst;
+	const unsigned long long* lflag; const double* lrecv;           // [nranks] / [2][nranks][nglobal*block]
+	unsigned long long* epoch; unsigned int* arrive; unsigned int* depart; int* err;
+};
+// Every rank stores its local entries at their GLOBAL position of its own slot in every window
+// (positions outside a rank's box are never written and stay 0 from creation), then each rank adds
+// the nranks slots in ascending rank order: the gathered, consistent global vector of
+// mg_solver_impl.hpp:2008-2068 on every rank, identical bits everywhere.
+__global__ void __launch_bounds__(1024)
+p2p_gather_sum_kernel(GatherDev d, double* gout, const double* lin, const int* guard)
+{
+	if (ug_guarded(guard)) return;
+	__shared__ bool s_last;
+	__shared__ GatherDst s_dst[kP2PMaxRanks];
+	if (threadIdx.x < d.nranks) s_dst[threadIdx.x] = d.dst[threadIdx.x];
+	const unsigned long long e = *(volatile unsigned long long*)d.epoch + 1ull;
+	const int64_t par = (int64_t)(e & 1ull);
+	const int64_t tot = d.nglobal * d.block, pstride = tot * d.nranks;
+	const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+	__syncthreads();
+	for (int64_t t = tid; t < d.nlocal * d.block; t += stride) {
+		const int64_t i = t / d.block; const int q = (int)(t - i * d.block);
+		const double val = lin[t];
+		const int64_t g = (int64_t)d.l2g[i] * d.block + q;
+		for (int r = 0; r < d.nranks; ++r) ug_st_relaxed_sys(s_dst[r].rbase + par * pstride + g, val);
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		s_last = true;
+		if (gridDim.x > 1) {
+			__threadfence_system();
+			s_last = (atomicAdd(d.arrive, 1u) == gridDim.x - 1);
+			if (s_last) { *d.arrive = 0u; __threadfence_system(); }
+		}
+	}
+	__syncthreads();
+	if (s_last && threadIdx.x < d.nranks) ug_st_release_sys(s_dst[threadIdx.x].rflag, e);
+	if (threadIdx.x < d.nranks) ug_wait_flag(d.lflag + threadIdx.x, e, d.err);
+	__syncthreads();
+	const double* base = d.lrecv + par * pstride;
+	for (int64_t t = tid; t < tot; t += stride) {
+		double s = 0.0;
+		for (int r = 0; r < d.nranks; ++r) {
+			const double x = ug_ld_relaxed_sys(base + (int64_t)r * tot + t);
+			s = (r == 0) ? x : s + x;
+		}
+		gout[t] = s;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		if (gridDim.x == 1) *(volatile unsigned long long*)d.epoch = e;
+		else {
+			__threadfence();
+			if (atomicAdd(d.depart, 1u) == gridDim.x - 1) { *d.depart = 0u; *(volatile unsigned long long*)d.epoch = e; }
+		}
+	}
+}
+__global__ void gather_scatter_local_kernel(int64_t nlocal, int block, const int* __restrict__ l2g, double* gout, const double* lin,
+                                            const int* guard)
+{
+	if (ug_guarded(guard)) return;
+	for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nlocal * block; t += (int64_t)gridDim.x * blockDim.x) {
+		const int64_t i = t / block; const int q = (int)(t - i * block);
+		gout[(int64_t)l2g[i] * block + q] = lin[t];
+	}
+}
+
 } // namespace
 
 struct ug4b200_interface {
@@ -266,7 +365,7 @@ struct ug4b200_interface {
 	int id = -1;                  // creation counter, identical on all ranks
 	size_t win_off = 0;           // flags at win_off, receive region behind them
 	size_t recv_off = 0;
-	unsigned char* d_ent_nb = nullptr; int64_t* d_ptr = nullptr; P2PNb* d_nb = nullptr;
+	int* d_ent_code = nullptr; int* d_uell = nullptr; int ell_w = 2; P2PNb* d_nb = nullptr;
 	unsigned long long* d_epoch = nullptr; unsigned int* d_counters = nullptr;
 };
 
@@ -274,10 +373,18 @@ struct ug4b200_interface {
 // Allocate this interface's flags + receive region in the local window and publish, for every
 // neighbour r, where r has to write (table entry [id][r]); neighbours look it up in commit.
 template <class Up>
-static int p2p_interface_setup(ug4b200_ctx* ctx, ug4b200_interface* I, Up& up)
+static int p2p_interface_setup(ug4b200_ctx* ctx, ug4b200_interface* I, Up& up, const std::vector<int>& uptr,
+                               const std::vector<int>& usrc)
 {
 	ug4b200_p2p* P = ctx->p2p;
-	if (I->nneigh > 255) return ug4b200_fail(ctx, UG4B200_ERR_ARG, "interface: too many neighbours for the peer-window transport");
+	// the one-kernel exchange keeps the neighbour table in shared memory and unrolls over <= 8 copies
+	// (a 3-D box partition has <= 26 neighbours and <= 8 copies); anything else stays on NCCL
+	int w = 1;
+	for (size_t u = 0; u + 1 < uptr.size(); ++u) w = std::max(w, uptr[u + 1] - uptr[u]);
+	int64_t maxrel = 0;
+	for (int p = 0; p < I->nneigh; ++p) maxrel = std::max<int64_t>(maxrel, I->ptr[p + 1] - I->ptr[p]);
+	if (I->nneigh > 32 || w > 8 || maxrel >= (1ll << 26)) return UG4B200_OK;
+	I->ell_w = w <= 2 ? 2 : (w <= 4 ? 4 : 8);
 	const size_t flag_bytes = (((size_t)I->nneigh * 8) + 255) / 256 * 256;
 	const size_t recv_bytes = (((size_t)2 * I->total * 9 * 8) + 255) / 256 * 256;
 	if (P->bump + flag_bytes + recv_bytes > P->bytes)
@@ -286,11 +393,16 @@ static int p2p_interface_setup(ug4b200_ctx* ctx, ug4b200_interface* I, Up& up)
 	I->win_off = P->bump; I->recv_off = P->bump + flag_bytes;
 	P->bump += flag_bytes + recv_bytes; P->live_ifaces++;
 	I->p2p = true;
-	std::vector<unsigned char> ent_nb(I->total);
-	for (int p = 0; p < I->nneigh; ++p) for (int64_t e = I->ptr[p]; e < I->ptr[p + 1]; ++e) ent_nb[e] = (unsigned char)p;
+	std::vector<int> ent_code(I->total);
+	for (int p = 0; p < I->nneigh; ++p)
+		for (int64_t e = I->ptr[p]; e < I->ptr[p + 1]; ++e) ent_code[e] = (int)(((e - I->ptr[p]) << 5) | p);
+	const size_t nu = uptr.size() - 1;
+	std::vector<int> uell(nu * I->ell_w > 0 ? nu * I->ell_w : 1, -2);
+	for (size_t u = 0; u < nu; ++u)
+		for (int k = uptr[u]; k < uptr[u + 1]; ++k) uell[u * I->ell_w + (k - uptr[u])] = usrc[k];
 	int rc = 0;
-	if (!rc) rc = up((void**)&I->d_ent_nb, ent_nb.data(), ent_nb.size());
-	if (!rc) rc = up((void**)&I->d_ptr, I->ptr.data(), sizeof(int64_t) * I->ptr.size());
+	if (!rc) rc = up((void**)&I->d_ent_code, ent_code.data(), sizeof(int) * ent_code.size());
+	if (!rc) rc = up((void**)&I->d_uell, uell.data(), sizeof(int) * uell.size());
 	if (!rc) rc = up((void**)&I->d_nb, nullptr, sizeof(P2PNb) * I->nneigh);
 	if (!rc) rc = up((void**)&I->d_epoch, nullptr, 8);
 	if (!rc) rc = up((void**)&I->d_counters, nullptr, 8);
@@ -322,6 +434,16 @@ static int p2p_finish_open(ug4b200_ctx* ctx, ug4b200_p2p* P)
 	ctx->nranks = P->nranks; ctx->rank = P->rank;
 	return UG4B200_OK;
 }
+
+struct ug4b200_gather {
+	int64_t nglobal = 0, nlocal = 0; int block = 1;
+	int* d_l2g = nullptr;
+	bool p2p = false, committed = false;
+	int id = -1;
+	size_t win_off = 0, recv_off = 0;
+	GatherDst* d_dst = nullptr;
+	unsigned long long* d_epoch = nullptr; unsigned int* d_counters = nullptr;
+};
 
 extern "C" {
 
@@ -426,7 +548,7 @@ int ug4b200_interface_create(ug4b200_ctx* ctx, int nneigh, const int* neigh_rank
 	if (!rc) rc = up((void**)&I->d_usrc, usrc.data(), sizeof(int) * usrc.size());
 	if (!rc) rc = up((void**)&I->d_slave, slave.data(), sizeof(int) * slave.size());
 	if (!rc) rc = up((void**)&I->d_owned, owned.data(), owned.size());
-	if (!rc && ctx->p2p && ctx->p2p->nranks > 1 && I->total > 0) rc = p2p_interface_setup(ctx, I, up);
+	if (!rc && ctx->p2p && ctx->p2p->nranks > 1 && I->total > 0) rc = p2p_interface_setup(ctx, I, up, uptr, usrc);
 	if (!rc && !I->p2p) {
 		rc = up((void**)&I->sendbuf, nullptr, sizeof(double) * 9 * I->total);
 		if (!rc) rc = up((void**)&I->recvbuf, nullptr, sizeof(double) * 9 * I->total);
@@ -443,7 +565,7 @@ int ug4b200_interface_destroy(ug4b200_ctx* ctx, ug4b200_interface* I)
 	if (ctx) cudaStreamSynchronize(ctx->stream);
 	cudaFree(I->d_idx); cudaFree(I->d_uidx); cudaFree(I->d_uptr); cudaFree(I->d_usrc); cudaFree(I->d_slave);
 	cudaFree(I->d_owned); cudaFree(I->sendbuf); cudaFree(I->recvbuf);
-	cudaFree(I->d_ent_nb); cudaFree(I->d_ptr); cudaFree(I->d_nb); cudaFree(I->d_epoch); cudaFree(I->d_counters);
+	cudaFree(I->d_ent_code); cudaFree(I->d_uell); cudaFree(I->d_nb); cudaFree(I->d_epoch); cudaFree(I->d_counters);
 	if (I->p2p && ctx && ctx->p2p) {
 		// window space is recycled once no interface is alive (ids keep counting: all ranks create and
 		// destroy interfaces in the same order)
@@ -485,24 +607,28 @@ int ug4b200_interface_commit(ug4b200_ctx* ctx, ug4b200_interface* I)
 	return UG4B200_OK;
 }
 
-int ug4b200_additive_to_consistent(ug4b200_ctx* ctx, ug4b200_interface* I, double* v, int block)
+static int exchange_sum(ug4b200_ctx* ctx, ug4b200_interface* I, double* v, int block, int unique)
 {
 	UG_ARG(ctx, I && v && block >= 1 && block <= 9, "bad argument");
 	if (I->total == 0) return UG4B200_OK;
 	if (I->p2p) {
 		if (!I->committed) { const int rc = ug4b200_interface_commit(ctx, I); if (rc) return rc; }
 		P2PIfaceDev d{};
-		d.nneigh = I->nneigh; d.total = I->total; d.nu = I->nu;
-		d.idx = I->d_idx; d.ent_nb = I->d_ent_nb; d.ptr = I->d_ptr; d.nb = I->d_nb;
+		d.nneigh = I->nneigh; d.ell_w = I->ell_w; d.total = I->total; d.nu = I->nu;
+		d.idx = I->d_idx; d.ent_code = I->d_ent_code; d.nb = I->d_nb;
 		d.lflag = reinterpret_cast<const unsigned long long*>(ctx->p2p->local + I->win_off);
 		d.lrecv = reinterpret_cast<const double*>(ctx->p2p->local + I->recv_off);
 		d.lpar_stride = I->total * 9;
-		d.uidx = I->d_uidx; d.uptr = I->d_uptr; d.usrc = I->d_usrc;
+		d.uidx = I->d_uidx; d.uell = I->d_uell;
+		d.owned = I->d_owned;
 		d.epoch = I->d_epoch; d.arrive = I->d_counters; d.depart = I->d_counters + 1; d.err = ctx->p2p->err_dev;
-		// 4 values per thread; never more CTAs than SMs (co-residency, see kernel)
-		int64_t g = (I->total * block + 1023) / 1024;
-		if (g > ctx->num_sms) g = ctx->num_sms; if (g < 1) g = 1;
-		UG_LAUNCH(ctx, p2p_exchange_sum_kernel, (int)g, 256, 0, d, v, block, ctx->guard);
+		{ static const bool fa = getenv("UG4B200_P2P_FENCE_ALL") && getenv("UG4B200_P2P_FENCE_ALL")[0] == '1'; d.fence_all = fa ? 1 : 0; }
+		// one CTA up to 64 values per thread; never more CTAs than SMs (co-residency, see kernel)
+		const int64_t work = I->total * block;
+		int64_t g = work <= 65536 ? 1 : (work + 16383) / 16384;
+		if (g > ctx->num_sms) g = ctx->num_sms;
+		const int threads = work >= 1024 ? 1024 : (int)std::max<int64_t>(64, (work + 31) / 32 * 32);
+		UG_LAUNCH(ctx, p2p_exchange_sum_kernel, (int)g, threads, 0, d, v, block, unique, ctx->guard);
 		return UG4B200_OK;
 	}
 	if (!ctx->nccl) return ug4b200_fail(ctx, UG4B200_ERR_STATE, "communicator not initialised");
@@ -519,8 +645,14 @@ int ug4b200_additive_to_consistent(ug4b200_ctx* ctx, ug4b200_interface* I, doubl
 	UG_NCCL(ctx, N.GroupEnd());
 	grid = (int)((I->nu * block + 255) / 256); if (grid > ctx->num_sms * 4) grid = ctx->num_sms * 4;
 	UG_LAUNCH(ctx, unpack_sum_kernel, grid, 256, 0, I->nu, block, I->d_uidx, I->d_uptr, I->d_usrc, I->recvbuf, v, ctx->guard);
+	if (unique) return ug4b200_set_slaves_zero(ctx, I, v, block);
 	return UG4B200_OK;
 }
+
+int ug4b200_additive_to_consistent(ug4b200_ctx* ctx, ug4b200_interface* I, double* v, int block)
+{ return exchange_sum(ctx, I, v, block, 0); }
+int ug4b200_additive_to_unique(ug4b200_ctx* ctx, ug4b200_interface* I, double* v, int block)
+{ return exchange_sum(ctx, I, v, block, 1); }
 
 /* ---- peer windows ---- */
 
@@ -636,6 +768,127 @@ int ug4b200_vec_dot_allreduce_ds(ug4b200_ctx* ctx, int64_t n, const double* a, c
 	if (!rc) rc = ug4b200_allreduce_sum(ctx, scratch_dev, 1);
 	if (!rc) rc = ug4b200_scalar_fin_ds(ctx, scratch_dev, fin);
 	return rc;
+}
+
+/* ---- gathered level ---- */
+
+int ug4b200_gather_create(ug4b200_ctx* ctx, int64_t nglobal, int64_t nlocal, const int* local_to_global, int block,
+                          ug4b200_gather** out)
+{
+	UG_ARG(ctx, out && nglobal >= 0 && nlocal >= 0 && block >= 1 && block <= 9 && (local_to_global || nlocal == 0), "bad argument");
+	*out = nullptr;
+	for (int64_t i = 0; i < nlocal; ++i)
+		if (local_to_global[i] < 0 || local_to_global[i] >= nglobal) return ug4b200_fail(ctx, UG4B200_ERR_ARG, "gather: global index out of range");
+	ug4b200_gather* G = new ug4b200_gather;
+	G->nglobal = nglobal; G->nlocal = nlocal; G->block = block;
+	if (cudaMalloc(&G->d_l2g, sizeof(int) * (nlocal > 0 ? nlocal : 1)) != cudaSuccess) { cudaGetLastError(); delete G; return ug4b200_fail(ctx, UG4B200_ERR_NOMEM, "gather: out of device memory"); }
+	if (nlocal) cudaMemcpyAsync(G->d_l2g, local_to_global, sizeof(int) * nlocal, cudaMemcpyHostToDevice, ctx->stream);
+	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ug4b200_p2p* P = ctx->p2p;
+	if (P && P->nranks > 1 && nglobal > 0) {
+		const size_t flag_bytes = 256;
+		const size_t recv_bytes = (((size_t)2 * P->nranks * nglobal * block * 8) + 255) / 256 * 256;
+		if (P->bump + flag_bytes + recv_bytes <= P->bytes) {
+			G->id = P->next_iface++;
+			G->win_off = P->bump; G->recv_off = P->bump + flag_bytes;
+			P->bump += flag_bytes + recv_bytes; P->live_ifaces++;
+			G->p2p = true;
+			cudaMalloc(&G->d_dst, sizeof(GatherDst) * kP2PMaxRanks);
+			cudaMalloc(&G->d_epoch, 8); cudaMalloc(&G->d_counters, 8);
+			cudaMemset(G->d_epoch, 0, 8); cudaMemset(G->d_counters, 0, 8);
+			// slots must read 0 wherever a rank never writes; flags start at epoch 0
+			UG_CUDA(ctx, cudaMemsetAsync(P->local + G->win_off, 0, flag_bytes + recv_bytes, P->aux));
+			UG_CUDA(ctx, cudaStreamSynchronize(P->aux));
+			for (int r = 0; r < P->nranks; ++r) {
+				if (r == P->rank) continue;
+				ug4b200_p2p_entry ent{};
+				ent.tag = (unsigned long long)G->id + 1ull;
+				ent.recv_off = G->recv_off + (size_t)r * nglobal * block * 8;   // slot of source rank r (parity 0)
+				ent.total = (unsigned long long)(nglobal * block);
+				ent.flag_off = G->win_off + (size_t)r * 8;
+				char* dst = P->local + sizeof(ug4b200_p2p_entry) * ((size_t)(G->id % kP2PMaxIfaces) * kP2PMaxRanks + r);
+				UG_CUDA(ctx, cudaMemcpyAsync(dst, &ent, sizeof(ent), cudaMemcpyHostToDevice, P->aux));
+				UG_CUDA(ctx, cudaStreamSynchronize(P->aux));
+			}
+		}
+	}
+	*out = G;
+	return UG4B200_OK;
+}
+
+int ug4b200_gather_commit(ug4b200_ctx* ctx, ug4b200_gather* G)
+{
+	UG_ARG(ctx, G != nullptr, "gather is NULL");
+	if (!G->p2p || G->committed) return UG4B200_OK;
+	if (ctx->capturing) return ug4b200_fail(ctx, UG4B200_ERR_STATE, "gather_commit during graph capture");
+	ug4b200_p2p* P = ctx->p2p;
+	std::vector<GatherDst> dst(kP2PMaxRanks);
+	for (int r = 0; r < P->nranks; ++r) {
+		if (r == P->rank) {
+			dst[r].rbase = reinterpret_cast<double*>(P->local + G->recv_off) + (size_t)r * G->nglobal * G->block;
+			dst[r].rflag = reinterpret_cast<unsigned long long*>(P->local + G->win_off) + r;
+			continue;
+		}
+		const char* src = P->peer[r] + sizeof(ug4b200_p2p_entry) * ((size_t)(G->id % kP2PMaxIfaces) * kP2PMaxRanks + P->rank);
+		ug4b200_p2p_entry ent{};
+		for (int tries = 0;; ++tries) {
+			UG_CUDA(ctx, cudaMemcpyAsync(&ent, src, sizeof(ent), cudaMemcpyDefault, P->aux));
+			UG_CUDA(ctx, cudaStreamSynchronize(P->aux));
+			if (ent.tag == (unsigned long long)G->id + 1ull) break;
+			if (tries > 150000) return ug4b200_fail(ctx, UG4B200_ERR_STATE, "gather_commit: a rank never published its window entry");
+			usleep(200);
+		}
+		if ((int64_t)ent.total != G->nglobal * G->block) return ug4b200_fail(ctx, UG4B200_ERR_STATE, "gather_commit: global size differs between ranks");
+		dst[r].rbase = reinterpret_cast<double*>(P->peer[r] + ent.recv_off);
+		dst[r].rflag = reinterpret_cast<unsigned long long*>(P->peer[r] + ent.flag_off);
+	}
+	UG_CUDA(ctx, cudaMemcpyAsync(G->d_dst, dst.data(), sizeof(GatherDst) * kP2PMaxRanks, cudaMemcpyHostToDevice, P->aux));
+	UG_CUDA(ctx, cudaStreamSynchronize(P->aux));
+	G->committed = true;
+	return UG4B200_OK;
+}
+
+int ug4b200_gather_sum(ug4b200_ctx* ctx, ug4b200_gather* G, double* global_out, const double* local_in)
+{
+	UG_ARG(ctx, G && global_out && (local_in || G->nlocal == 0), "bad argument");
+	const int64_t tot = G->nglobal * G->block;
+	if (tot == 0) return UG4B200_OK;
+	if (G->p2p) {
+		if (!G->committed) { const int rc = ug4b200_gather_commit(ctx, G); if (rc) return rc; }
+		ug4b200_p2p* P = ctx->p2p;
+		GatherDev d{};
+		d.nranks = P->nranks; d.rank = P->rank; d.block = G->block; d.nlocal = G->nlocal; d.nglobal = G->nglobal;
+		d.l2g = G->d_l2g; d.dst = G->d_dst;
+		d.lflag = reinterpret_cast<const unsigned long long*>(P->local + G->win_off);
+		d.lrecv = reinterpret_cast<const double*>(P->local + G->recv_off);
+		d.epoch = G->d_epoch; d.arrive = G->d_counters; d.depart = G->d_counters + 1; d.err = P->err_dev;
+		const int64_t work = tot * P->nranks;
+		int64_t g = work <= 32768 ? 1 : (work + 16383) / 16384;
+		if (g > ctx->num_sms) g = ctx->num_sms;
+		const int threads = work >= 1024 ? 1024 : (int)std::max<int64_t>(64, (work + 31) / 32 * 32);
+		UG_LAUNCH(ctx, p2p_gather_sum_kernel, (int)g, threads, 0, d, global_out, local_in, ctx->guard);
+		return UG4B200_OK;
+	}
+	// single rank or NCCL transport: global = 0 ; global[l2g] = local ; all-reduce
+	int rc = ug4b200_vec_set(ctx, tot, global_out, 0.0);
+	if (rc) return rc;
+	if (G->nlocal) {
+		int grid = (int)((G->nlocal * G->block + 255) / 256); if (grid > ctx->num_sms * 4) grid = ctx->num_sms * 4;
+		UG_LAUNCH(ctx, gather_scatter_local_kernel, grid, 256, 0, G->nlocal, G->block, G->d_l2g, global_out, local_in, ctx->guard);
+	}
+	if (ctx->nranks <= 1) return UG4B200_OK;
+	if (tot > 2147483647LL) return ug4b200_fail(ctx, UG4B200_ERR_ARG, "gather: vector too long");
+	return ug4b200_allreduce_sum(ctx, global_out, (int)tot);
+}
+
+int ug4b200_gather_destroy(ug4b200_ctx* ctx, ug4b200_gather* G)
+{
+	if (!G) return UG4B200_OK;
+	if (ctx) cudaStreamSynchronize(ctx->stream);
+	cudaFree(G->d_l2g); cudaFree(G->d_dst); cudaFree(G->d_epoch); cudaFree(G->d_counters);
+	if (G->p2p && ctx && ctx->p2p) { if (--ctx->p2p->live_ifaces == 0) ctx->p2p->bump = kP2PHeapOff; }
+	delete G;
+	return UG4B200_OK;
 }
 
 int ug4b200_set_slaves_zero(ug4b200_ctx* ctx, ug4b200_interface* I, double* v, int block)

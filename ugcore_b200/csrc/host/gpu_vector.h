@@ -182,8 +182,7 @@ class GPUVector {
 				break;
 			case PST_UNIQUE:
 				if (has_storage_type(PST_ADDITIVE)) {
-					UG_GPU_CHECK(ug4b200_additive_to_consistent(c, I, dev(), blockSize));
-					UG_GPU_CHECK(ug4b200_set_slaves_zero(c, I, dev(), blockSize));
+					UG_GPU_CHECK(ug4b200_additive_to_unique(c, I, dev(), blockSize));
 					add_storage_type(PST_UNIQUE);
 				} else if (has_storage_type(PST_CONSISTENT)) {
 					UG_GPU_CHECK(ug4b200_set_slaves_zero(c, I, dev(), blockSize));

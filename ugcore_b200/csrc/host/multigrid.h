@@ -67,6 +67,31 @@ class StdTransfer {
 
 enum { _V_ = 1, _W_ = 2, _F_ = -1 };
 
+template <typename TAlgebra> class AssembledMultiGridCycle;
+
+/// One multigrid cycle as "base solver" of a partitioned hierarchy: below the gathered level every
+/// rank holds the whole (small) grid and runs the serial cycle redundantly instead of exchanging
+/// interface values of a few hundred DoFs per smoothing step.  This is ugcore's gathered base
+/// solve (mg_solver_impl.hpp:2003-2070) with the coarse levels kept inside the same V-cycle:
+/// lmgc(l) on the gathered level l with sc_l = 0 is exactly apply() of a cycle whose top level is l,
+/// so the result equals the fully partitioned cycle up to summation order (V-cycles only).
+template <typename TAlgebra>
+class CycleAsBaseSolver : public ILinearOperatorInverse<typename TAlgebra::vector_type> {
+  public:
+	typedef typename TAlgebra::vector_type vector_type;
+	explicit CycleAsBaseSolver(SmartPtr<AssembledMultiGridCycle<TAlgebra> > cycle) : m_spCycle(cycle) {}
+	virtual const char* name() const { return "GatheredCycle"; }
+	virtual bool supports_parallel() const { return false; }
+	virtual bool init(SmartPtr<ILinearOperator<vector_type> > L);
+	virtual bool init(SmartPtr<ILinearOperator<vector_type> > J, const vector_type&) { return init(J); }
+	virtual bool apply(vector_type& u, const vector_type& f);
+	virtual bool apply_return_defect(vector_type& u, vector_type& f);
+	SmartPtr<AssembledMultiGridCycle<TAlgebra> > cycle() { return m_spCycle; }
+  protected:
+	SmartPtr<AssembledMultiGridCycle<TAlgebra> > m_spCycle;
+	SmartPtr<ILinearOperator<vector_type> > m_spOp;
+};
+
 template <typename TAlgebra>
 class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector_type> {
   public:
@@ -166,6 +191,10 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 			GPUManager::free_bytes(m_dBaseMap);
 			m_dBaseMap = (int*)GPUManager::alloc_bytes(sizeof(int) * m_baseLocalToGlobal.size());
 			UG_GPU_CHECK(ug4b200_h2d(ctx, m_dBaseMap, m_baseLocalToGlobal.data(), sizeof(int) * m_baseLocalToGlobal.size()));
+			if (m_gather) { ug4b200_gather_destroy(ctx, m_gather); m_gather = nullptr; }
+			UG_GPU_CHECK(ug4b200_gather_create(ctx, (int64_t)m_spGatheredA->num_rows(), (int64_t)m_baseLocalToGlobal.size(),
+			                                   m_baseLocalToGlobal.data(), B, &m_gather));
+			UG_GPU_CHECK(ug4b200_gather_commit(ctx, m_gather));
 			if (!m_spBaseSolver->init(m_spGatheredA)) UG_THROW("GMG::init: Cannot init base solver");
 		} else if (!m_spBaseSolver->init(lb.A)) UG_THROW("GMG::init: Cannot init base solver on baselevel " << m_baseLev);
 		// surface <-> level map
@@ -178,7 +207,11 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 		UG_GPU_CHECK(ug4b200_sync(ctx));
 		return true;
 	}
-	~AssembledMultiGridCycle() { GPUManager::free_bytes(m_dSurfMap); GPUManager::free_bytes(m_dBaseMap); }
+	~AssembledMultiGridCycle()
+	{
+		GPUManager::free_bytes(m_dSurfMap); GPUManager::free_bytes(m_dBaseMap);
+		if (m_gather && GPUManager::ctx_or_null()) ug4b200_gather_destroy(GPUManager::ctx_or_null(), m_gather);
+	}
 
 	/// mg_solver_impl.hpp:174-275
 	virtual bool apply(vector_type& c, const vector_type& d)
@@ -262,7 +295,8 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 	}
 	bool base_solver_overwrites() const
 	{
-		return dynamic_cast<LU<TAlgebra>*>(m_spBaseSolver.get()) != nullptr || dynamic_cast<CoarseCG<TAlgebra>*>(m_spBaseSolver.get()) != nullptr;
+		return dynamic_cast<LU<TAlgebra>*>(m_spBaseSolver.get()) != nullptr || dynamic_cast<CoarseCG<TAlgebra>*>(m_spBaseSolver.get()) != nullptr ||
+		       dynamic_cast<CycleAsBaseSolver<TAlgebra>*>(m_spBaseSolver.get()) != nullptr;
 	}
 	void make_consistent(vector_type& v)
 	{
@@ -382,9 +416,7 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 			if (!m_spBaseSolver->apply(ld.sc, ld.sd)) UG_THROW("GMG::lmgc: Base solver on base level " << lev << " failed.");
 		} else {
 			// gathered: additive local defects -> global consistent defect on every rank
-			m_gatheredD.set(0.0);
-			UG_GPU_CHECK(ug4b200_vec_scatter(ctx, (int64_t)ld.sd.size(), B, m_gatheredD.dev(), m_dBaseMap, ld.sd.dev()));
-			UG_GPU_CHECK(ug4b200_allreduce_sum(ctx, m_gatheredD.dev(), (int)m_gatheredD.len()));
+			UG_GPU_CHECK(ug4b200_gather_sum(ctx, m_gather, m_gatheredD.dev(), ld.sd.dev()));
 			if (!m_spBaseSolver->apply(m_gatheredC, m_gatheredD)) UG_THROW("GMG::lmgc: Base solver on base level " << lev << " failed.");
 			UG_GPU_CHECK(ug4b200_vec_gather(ctx, (int64_t)ld.sc.size(), B, ld.sc.dev(), m_gatheredC.dev(), m_dBaseMap));
 			ld.sc.set_storage_type(PST_CONSISTENT);
@@ -408,7 +440,20 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 	SmartPtr<matrix_operator_type> m_spGatheredA;
 	std::vector<int> m_baseLocalToGlobal;
 	int* m_dBaseMap = nullptr;
+	ug4b200_gather* m_gather = nullptr;
 	vector_type m_gatheredD, m_gatheredC;
 };
+
+template <typename TAlgebra>
+bool CycleAsBaseSolver<TAlgebra>::init(SmartPtr<ILinearOperator<vector_type> > L) { m_spOp = L; return m_spCycle->init(L); }
+template <typename TAlgebra>
+bool CycleAsBaseSolver<TAlgebra>::apply(vector_type& u, const vector_type& f) { return m_spCycle->apply(u, f); }
+template <typename TAlgebra>
+bool CycleAsBaseSolver<TAlgebra>::apply_return_defect(vector_type& u, vector_type& f)
+{
+	if (!m_spCycle->apply(u, f)) return false;
+	m_spOp->apply_sub(f, u);
+	return true;
+}
 
 } // namespace ug

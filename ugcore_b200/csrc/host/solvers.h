@@ -148,8 +148,10 @@ class CG : public IPreconditionedLinearOperatorInverse<TVector> {
 		ug4b200_fin finL{UG4B200_FIN_A_DIV_R, S + KS::LAMBDA, S + KS::ALPHA, S + KS::RHO_OLD, m_ks.conv};
 		typedef MatrixOperator<GPUSparseMatrix<typename matrix_value<B>::type>, vector_type> matop_t;
 		matop_t* mop = dynamic_cast<matop_t*>(linear_operator().get());
-		if (mop && !parallel) {
-			UG_GPU_CHECK(ug4b200_matrix_apply_dot_ds(c, mop->device(), q.dev(), p.dev(), finL));
+		if (mop) {
+			// parallel: q additive, p consistent -> the local dots add up to (q,p); the kernel's last block
+			// sums them over the ranks (parallel_vector_impl.h:366-375)
+			UG_GPU_CHECK(ug4b200_matrix_apply_dot_allreduce_ds(c, mop->device(), q.dev(), p.dev(), finL, S + KS::TMP));
 			q.set_storage_type(PST_ADDITIVE);
 		} else {
 			linear_operator()->apply(q, p);

@@ -33,8 +33,8 @@ struct Sell {
 	int64_t nrows, num_slices;
 };
 struct Fuse {
-	// FUSE_DOT
-	double* partials; unsigned int* counter; ug4b200_fin fin;
+	// FUSE_DOT (ar.nranks > 1: the last block also sums over the ranks through the peer windows)
+	double* partials; unsigned int* counter; ug4b200_fin fin; UgAr ar;
 	// FUSE_JACOBI
 	const double* diaginv; double* st_out; double* sc; int flags;
 };
@@ -144,7 +144,7 @@ spmv1_kernel(Sell A, double* dest, const double* v, double alpha, double beta, c
 			if (FUSE == FUSE_DOT && live) dot += acc * own;
 		}
 	}
-	if (FUSE == FUSE_DOT) ug_block_reduce_fin(dot, fz.partials, fz.counter, fz.fin);
+	if (FUSE == FUSE_DOT) ug_block_reduce_fin(dot, fz.partials, fz.counter, fz.fin, fz.ar);
 }
 
 // ---------------------------------------------------------------- block B x B
@@ -216,7 +216,7 @@ spmvB_kernel(Sell A, double* dest, const double* v, double alpha, double beta, c
 #pragma unroll
 				for (int r = 0; r < B; ++r) {
 					dest[row * B + r] = acc[r];
-					scv[r] = touch_sc ? fz.sc[row * B + r] : 0.0;
+					scv[r] = (touch_sc && !(fz.flags & UG4B200_SMOOTH_SC_ZERO)) ? fz.sc[row * B + r] : 0.0;
 					if (fz.flags & UG4B200_SMOOTH_ADD_IN) scv[r] = scv[r] + w[row * B + r];
 				}
 				if (fz.flags & UG4B200_SMOOTH_JACOBI) {
@@ -248,7 +248,7 @@ spmvB_kernel(Sell A, double* dest, const double* v, double alpha, double beta, c
 			}
 		}
 	}
-	if (FUSE == FUSE_DOT) ug_block_reduce_fin(dot, fz.partials, fz.counter, fz.fin);
+	if (FUSE == FUSE_DOT) ug_block_reduce_fin(dot, fz.partials, fz.counter, fz.fin, fz.ar);
 }
 
 // ------------------------------------------ scalar matrix acting on VB-block vectors
@@ -573,8 +573,25 @@ int ug4b200_matrix_apply_dot_ds(ug4b200_ctx* ctx, const ug4b200_matrix* A, doubl
 {
 	UG_ARG(ctx, A && y && x && y != x, "bad argument");
 	UG_ARG(ctx, A->nrows == A->ncols, "apply_dot needs a square matrix");
-	Fuse fz{}; fz.partials = ctx->partials; fz.counter = ctx->counter; fz.fin = fin;
+	Fuse fz{}; fz.partials = ctx->partials; fz.counter = ctx->counter; fz.fin = fin; fz.ar = ug_ar_none();
 	return launch_mode<1, MODE_ASSIGN, FUSE_DOT>(ctx, A, y, nullptr, 0.0, 1.0, x, A->block, fz);
+}
+int ug4b200_matrix_apply_dot_allreduce_ds(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* y, const double* x,
+                                          ug4b200_fin fin, double* scratch_dev)
+{
+	UG_ARG(ctx, A && y && x && y != x, "bad argument");
+	UG_ARG(ctx, A->nrows == A->ncols, "apply_dot needs a square matrix");
+	if (ctx->nranks <= 1) return ug4b200_matrix_apply_dot_ds(ctx, A, y, x, fin);
+	if (ctx->p2p && ctx->p2p->nranks > 1) {
+		Fuse fz{}; fz.partials = ctx->partials; fz.counter = ctx->counter; fz.fin = fin; fz.ar = ug_ar_of(ctx);
+		return launch_mode<1, MODE_ASSIGN, FUSE_DOT>(ctx, A, y, nullptr, 0.0, 1.0, x, A->block, fz);
+	}
+	UG_ARG(ctx, scratch_dev != nullptr, "scratch_dev needed for the NCCL transport");
+	ug4b200_fin st{UG4B200_FIN_STORE, scratch_dev, nullptr, nullptr, nullptr};
+	int rc = ug4b200_matrix_apply_dot_ds(ctx, A, y, x, st);
+	if (!rc) rc = ug4b200_allreduce_sum(ctx, scratch_dev, 1);
+	if (!rc) rc = ug4b200_scalar_fin_ds(ctx, scratch_dev, fin);
+	return rc;
 }
 int ug4b200_jacobi_smooth_fused_src(ug4b200_ctx* ctx, const ug4b200_matrix* A, const double* diaginv, double* sd,
                                     const double* sd_in, const double* st_in, double* st_out, double* sc, int flags)
@@ -583,7 +600,7 @@ int ug4b200_jacobi_smooth_fused_src(ug4b200_ctx* ctx, const ug4b200_matrix* A, c
 	UG_ARG(ctx, A->nrows == A->ncols, "square matrix needed");
 	UG_ARG(ctx, !(flags & UG4B200_SMOOTH_JACOBI) || (diaginv && st_out), "JACOBI needs diaginv and st_out");
 	UG_ARG(ctx, !(flags & (UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_ADD_OUT)) || sc, "ADD_* needs sc");
-	UG_ARG(ctx, st_in != st_out && sd != st_in && sc != st_in && sd_in != st_out, "st_in must not alias an output");
+	UG_ARG(ctx, st_in != st_out && sd != st_in && sc != st_in && (sd_in == nullptr || sd_in != st_out), "st_in must not alias an output");
 	Fuse fz{}; fz.diaginv = diaginv; fz.st_out = st_out; fz.sc = sc; fz.flags = flags;
 	if (sd_in == nullptr || sd_in == sd)
 		return launch_mode<-1, MODE_INPLACE, FUSE_JACOBI>(ctx, A, sd, sd, 1.0, -1.0, st_in, A->block, fz);

@@ -180,7 +180,7 @@ spmv1_tma_kernel(Sell A, double* dest, const double* v, double alpha, double bet
 			if (FUSE == FUSE_DOT && live) dot += acc * own;
 		}
 	}
-	if (FUSE == FUSE_DOT) ug_block_reduce_fin(dot, fz.partials, fz.counter, fz.fin);
+	if (FUSE == FUSE_DOT) ug_block_reduce_fin(dot, fz.partials, fz.counter, fz.fin, fz.ar);
 }
 
 } // namespace tma

@@ -19,6 +19,9 @@ struct SolverBase {
 	virtual void set_coloring(int lev, int64_t n, const int* perm, int ncolors, const int64_t* cp) = 0;
 	virtual void set_layouts(int lev, int nneigh, const int* ranks, const int64_t* ptr, const int* idx, int64_t nlocal) = 0;
 	virtual void set_gathered_base(int64_t nrows, const int64_t* rp, const int* ci, const double* va, int64_t nlocal, const int* l2g) = 0;
+	virtual void set_gathered_level(int lev, int64_t nrows, const int64_t* rp, const int* ci, const double* va, int64_t ncoarse,
+	                                const int64_t* prp, const int* pci, const double* pva, const int64_t* rrp, const int* rci,
+	                                const double* rva) = 0;
 	virtual void init() = 0;
 	virtual int apply_host(double* x, const double* b) = 0;
 	virtual int apply_device(double* x, const double* b) = 0;
@@ -41,6 +44,7 @@ struct SolverImpl : SolverBase {
 	SmartPtr<ILinearOperatorInverse<vector_type> > inv;
 	SmartPtr<ILinearIterator<vector_type> > precond;
 	SmartPtr<AssembledMultiGridCycle<TAlgebra> > gmg;
+	SmartPtr<AssembledMultiGridCycle<TAlgebra> > gatheredCycle; // serial cycle below the gathered level (partitioned runs)
 	SmartPtr<StdConvCheck<vector_type> > conv;
 	std::map<int, std::pair<std::vector<int>, std::vector<int64_t> > > coloring;
 	std::map<int, SmartPtr<GPUAlgebraLayouts> > layouts;
@@ -50,18 +54,16 @@ struct SolverImpl : SolverBase {
 	{
 		conv = make_sp<StdConvCheck<vector_type> >(d.max_steps, d.min_defect, d.rel_reduction, false);
 		if (d.precond == UG4B200_PRECOND_GMG) {
-			gmg = make_sp<AssembledMultiGridCycle<TAlgebra> >();
-			gmg->set_base_level(d.base_lev); gmg->set_surface_level(d.top_lev);
-			gmg->set_cycle_type(d.cycle); gmg->set_num_presmooth(d.nu1); gmg->set_num_postsmooth(d.nu2);
-			gmg->set_smoother(make_smoother(d.smoother, d.smoother_damp));
-			gmg->set_fuse_jacobi(!(d.flags & UG4B200_FLAG_NO_FUSED_JACOBI));
-			gmg->set_compute_final_level_defect((d.flags & UG4B200_FLAG_FINAL_LEVEL_DEFECT) != 0);
-			if (d.base_solver == UG4B200_SOLVER_LU) gmg->set_base_solver(make_sp<LU<TAlgebra> >());
-			else if (d.base_solver == UG4B200_SOLVER_COARSE_CG || d.base_solver == UG4B200_SOLVER_CG) {
-				SmartPtr<CoarseCG<TAlgebra> > cg = make_sp<CoarseCG<TAlgebra> >();
-				cg->set_convergence_check(make_sp<StdConvCheck<vector_type> >(d.base_max_steps, d.base_min_defect, d.base_rel_reduction, false));
-				gmg->set_base_solver(cg);
-			} else UG_THROW("unsupported base solver " << d.base_solver);
+			const int gatherLev = d.gather_lev > d.base_lev ? d.gather_lev : d.base_lev;
+			if (gatherLev > d.base_lev && d.cycle != 1) UG_THROW("a gathered cycle below the partitioned levels needs a V-cycle");
+			if (gatherLev >= d.top_lev && gatherLev > d.base_lev) UG_THROW("gather level must lie below the top level");
+			gmg = make_cycle(gatherLev, d.top_lev);
+			if (gatherLev > d.base_lev) {
+				// partitioned levels gatherLev+1..top; levels base..gatherLev replicated on every rank
+				gatheredCycle = make_cycle(d.base_lev, gatherLev);
+				gatheredCycle->set_base_solver(make_base_solver());
+				gmg->set_base_solver(make_sp<CycleAsBaseSolver<TAlgebra> >(gatheredCycle));
+			} else gmg->set_base_solver(make_base_solver());
 			precond = gmg;
 		} else if (d.precond != UG4B200_PRECOND_NONE) precond = make_smoother(d.precond, d.damp);
 		switch (d.solver) {
@@ -80,6 +82,26 @@ struct SolverImpl : SolverBase {
 		inv->set_convergence_check(conv);
 	}
 
+	SmartPtr<AssembledMultiGridCycle<TAlgebra> > make_cycle(int base, int top)
+	{
+		SmartPtr<AssembledMultiGridCycle<TAlgebra> > g = make_sp<AssembledMultiGridCycle<TAlgebra> >();
+		g->set_base_level(base); g->set_surface_level(top);
+		g->set_cycle_type(d.cycle); g->set_num_presmooth(d.nu1); g->set_num_postsmooth(d.nu2);
+		g->set_smoother(make_smoother(d.smoother, d.smoother_damp));
+		g->set_fuse_jacobi(!(d.flags & UG4B200_FLAG_NO_FUSED_JACOBI));
+		g->set_compute_final_level_defect((d.flags & UG4B200_FLAG_FINAL_LEVEL_DEFECT) != 0);
+		return g;
+	}
+	SmartPtr<ILinearOperatorInverse<vector_type> > make_base_solver()
+	{
+		if (d.base_solver == UG4B200_SOLVER_LU) return make_sp<LU<TAlgebra> >();
+		if (d.base_solver == UG4B200_SOLVER_COARSE_CG || d.base_solver == UG4B200_SOLVER_CG) {
+			SmartPtr<CoarseCG<TAlgebra> > cg = make_sp<CoarseCG<TAlgebra> >();
+			cg->set_convergence_check(make_sp<StdConvCheck<vector_type> >(d.base_max_steps, d.base_min_defect, d.base_rel_reduction, false));
+			return cg;
+		}
+		UG_THROW("unsupported base solver " << d.base_solver);
+	}
 	SmartPtr<ILinearIterator<vector_type> > make_smoother(int kind, double damp)
 	{
 		switch (kind) {
@@ -133,6 +155,23 @@ struct SolverImpl : SolverBase {
 		SmartPtr<matop_t> G = make_sp<matop_t>();
 		G->set_from_crs((size_t)nrows, (size_t)nrows, rp, ci, va);
 		gmg->set_gathered_base(G, std::vector<int>(l2g, l2g + nlocal));
+	}
+	void set_gathered_level(int lev, int64_t nrows, const int64_t* rp, const int* ci, const double* va, int64_t ncoarse,
+	                        const int64_t* prp, const int* pci, const double* pva, const int64_t* rrp, const int* rci,
+	                        const double* rva) override
+	{
+		if (!gatheredCycle) UG_THROW("solver has no gathered cycle (desc.gather_lev <= base_lev)");
+		if (rp) {
+			SmartPtr<matop_t> Al = make_sp<matop_t>();
+			Al->set_from_crs((size_t)nrows, (size_t)nrows, rp, ci, va);
+			gatheredCycle->set_level_operator(lev, Al);
+		}
+		if (prp) {
+			SmartPtr<GPUTransferMatrix> P = make_sp<GPUTransferMatrix>(), R;
+			P->set_from_crs((size_t)nrows, (size_t)ncoarse, prp, pci, pva);
+			if (rrp) { R = make_sp<GPUTransferMatrix>(); R->set_from_crs((size_t)ncoarse, (size_t)nrows, rrp, rci, rva); }
+			gatheredCycle->set_level_transfer(lev, P, R);
+		}
 	}
 	SmartPtr<GPUAlgebraLayouts> top_layouts()
 	{
@@ -234,6 +273,10 @@ int ug4b200_solver_set_layouts(ug4b200_solver* s, int lev, int nneigh, const int
 int ug4b200_solver_set_gathered_base(ug4b200_solver* s, int64_t nrows, const int64_t* rowptr, const int* cols, const double* vals,
                                      int64_t nlocal, const int* local_to_global)
 { return guard([&] { s->p->set_gathered_base(nrows, rowptr, cols, vals, nlocal, local_to_global); return 0; }); }
+int ug4b200_solver_set_gathered_level(ug4b200_solver* s, int lev, int64_t nrows, const int64_t* rowptr, const int* cols, const double* vals,
+                                      int64_t ncoarse, const int64_t* p_rowptr, const int* p_cols, const double* p_vals,
+                                      const int64_t* r_rowptr, const int* r_cols, const double* r_vals)
+{ return guard([&] { s->p->set_gathered_level(lev, nrows, rowptr, cols, vals, ncoarse, p_rowptr, p_cols, p_vals, r_rowptr, r_cols, r_vals); return 0; }); }
 int ug4b200_solver_init(ug4b200_solver* s) { return guard([&] { s->p->init(); return 0; }); }
 int ug4b200_solver_apply(ug4b200_solver* s, double* x_host, const double* b_host) { return guard([&] { return s->p->apply_host(x_host, b_host); }); }
 int ug4b200_solver_apply_device(ug4b200_solver* s, double* x_dev, const double* b_dev) { return guard([&] { return s->p->apply_device(x_dev, b_dev); }); }

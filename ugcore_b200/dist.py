@@ -181,9 +181,28 @@ def p2p_bootstrap(dist) -> bool:
     return ok
 
 
-def build_partitioned_solver(desc: dict, refs: int, part, rank: int, dist, problem=pr.POISSON, flags: int = 0, **kw):
-    """Wire a GMG-preconditioned solver on this rank's sub-box: local additive level matrices,
-    interface layouts per level, gathered (replicated, all-reduced) base solve."""
+def default_gather_level(refs: int, part, base: int = 0, max_rows: int = 40000, dim: int = 3) -> int:
+    """Highest level whose GLOBAL grid is small enough to be kept (and cycled) redundantly on every
+    rank instead of exchanging a few hundred interface values per smoothing step."""
+    lev = base
+    for l in range(base, refs):
+        rows = 1
+        for d in range(dim):
+            rows *= part[d] * 2 ** l + 1
+        if rows <= max_rows:
+            lev = l
+    return lev
+
+
+def build_partitioned_solver(desc: dict, refs: int, part, rank: int, dist, problem=pr.POISSON, flags: int = 0,
+                             gather_level=None, **kw):
+    """Wire a GMG-preconditioned solver on this rank's sub-box: local additive level matrices and
+    interface layouts for the partitioned levels gather_level+1..refs; the levels base..gather_level
+    are gathered: every rank holds the global matrices and runs that part of the V-cycle
+    redundantly (gather_level = base: only the base solve is gathered, as in
+    mg_solver_impl.hpp:2003-2070).  gather_level None: UG4B200_GATHER_LEVEL or the default rule."""
+    import os
+
     from .solver import Solver
     nccl_bootstrap(dist)
     p2p_bootstrap(dist)
@@ -191,18 +210,31 @@ def build_partitioned_solver(desc: dict, refs: int, part, rank: int, dist, probl
     desc = dict(desc)
     pc = dict(desc["precond"])
     pc["topLevel"], pc["baseLevel"] = refs, pc.get("baseLevel", 0)
-    desc["precond"] = pc
     base = pc["baseLevel"]
+    if gather_level is None:
+        env = os.environ.get("UG4B200_GATHER_LEVEL")
+        gather_level = int(env) if env is not None else default_gather_level(refs, part, base, dim=prob.dim)
+    if pc.get("cycle", "V") != "V":
+        gather_level = base
+    gather = max(base, min(int(gather_level), refs - 1))
+    pc["gatherLevel"] = gather
+    desc["precond"] = pc
     levels = {}
-    for lev in range(base, refs + 1):
-        levels[lev] = (prob.matrix(lev), None if lev == base else prob.prolongation(lev),
-                       None if lev == base else prob.restriction(lev))
+    for lev in range(gather, refs + 1):
+        levels[lev] = (prob.matrix(lev), None if lev == gather else prob.prolongation(lev),
+                       None if lev == gather else prob.restriction(lev))
     s = Solver(desc, prob.matrix(refs), levels, flags)
     s._keep.append(prob)
-    for lev in range(base, refs + 1):
+    for lev in range(gather, refs + 1):
         ranks, ptr, idx = interfaces(prob, lev)
         s.set_layouts(lev, ranks, ptr, idx, prob.matrix(lev).nrows)
-    gprob = global_problem(base, part, problem=problem, **kw)
+    gprob = global_problem(gather, part, problem=problem, **kw)
     s._keep.append(gprob)
-    s.set_gathered_base(gprob.matrix(base), prob.global_ids(base).astype(np.int32))
+    s.set_gathered_base(gprob.matrix(gather), prob.global_ids(gather).astype(np.int32))
+    for lev in range(base, gather + 1):
+        if gather == base:
+            break
+        s.set_gathered_level(lev, None if lev == gather else gprob.matrix(lev),
+                             None if lev == base else gprob.prolongation(lev),
+                             None if lev == base else gprob.restriction(lev), nrows=gprob.matrix(lev).nrows)
     return prob, s

@@ -79,6 +79,7 @@ def make_desc(desc: dict, block: int = 1, flags: int = 0) -> capi.SolverDesc:
             d.nu2 = pc.get("postSmooth", 2)
             d.base_lev = pc.get("baseLevel", 0)
             d.top_lev = pc["topLevel"]
+            d.gather_lev = pc.get("gatherLevel", d.base_lev)
             bs = pc.get("baseSolver", "lu")
             if isinstance(bs, str):
                 bs = {"type": bs}
@@ -183,6 +184,16 @@ class Solver:
         self._keep.append(Aglobal)
         check_host(host.ug4b200_solver_set_gathered_base(self.h, Aglobal.nrows, _ptr(Aglobal.rowptr), _ptr(Aglobal.cols),
                                                          _ptr(Aglobal.vals), l2g.size, _ptr(l2g)))
+
+    def set_gathered_level(self, lev, A, P, R, nrows):
+        """GLOBAL level matrix / transfers of a gathered level (A None on the gather level itself)."""
+        self._keep += [A, P, R]
+        check_host(host.ug4b200_solver_set_gathered_level(
+            self.h, lev, nrows,
+            _ptr(A.rowptr) if A else None, _ptr(A.cols) if A else None, _ptr(A.vals) if A else None,
+            P.ncols if P else 0,
+            _ptr(P.rowptr) if P else None, _ptr(P.cols) if P else None, _ptr(P.vals) if P else None,
+            _ptr(R.rowptr) if R else None, _ptr(R.cols) if R else None, _ptr(R.vals) if R else None))
 
     def init(self):
         check_host(host.ug4b200_solver_init(self.h))
