@@ -182,12 +182,21 @@ int ug4b200_conv_init(ug4b200_ctx* ctx, ug4b200_conv_state* dev_state, int max_s
  * entries stored slice-column-major so that a warp reads 32 consecutive values) with
  * true row lengths kept, explicit zeros preserved.  The handle is immutable. */
 
-enum { UG4B200_MAT_DEFAULT = 0 };
+/* Scalar matrices whose values repeat (at most 65536 distinct fp64 bit patterns — the level
+ * operators of a uniformly refined grid have a few dozen) and whose columns stay within 65535 of
+ * the smallest column of their 32-row slice additionally get a VALUE-INDEXED copy of the entry
+ * stream: u16 index into a dictionary of the exact values + u16 column offset, 4 instead of 12
+ * bytes per entry (cf. CSR-VI / CSR-DU, Kourtis et al. 2008).  Lossless, so every result stays
+ * bit-identical; the SpMV family streams this copy.  UG4B200_MAT_NO_COMPRESS (or the
+ * environment variable UG4B200_NO_COMPRESS=1) keeps the plain stream only. */
+enum { UG4B200_MAT_DEFAULT = 0, UG4B200_MAT_NO_COMPRESS = 1 };
 
 typedef struct ug4b200_matrix_info {
 	int64_t nrows, ncols, nnz, padded_nnz, num_slices, device_bytes;
 	int block;
 	int max_row_len;
+	int value_indexed;        /* 1 if the value-indexed stream exists */
+	int num_distinct_values;
 } ug4b200_matrix_info;
 
 int ug4b200_matrix_upload_crs(ug4b200_ctx* ctx, int block, int64_t nrows, int64_t ncols, const int64_t* rowptr,

@@ -38,12 +38,20 @@ def orc_ref():
     return oracle.Oracle("ref")
 
 
-@pytest.fixture(scope="session")
-def gpu_ctx():
-    """Kernel-level context on cuda:0 (fails, never skips, if the device is unusable)."""
+@pytest.fixture(scope="session", params=["value_indexed", "plain"])
+def gpu_ctx(request):
+    """Kernel-level context on cuda:0 (fails, never skips, if the device is unusable).  Every
+    kernel test runs twice: with the value-indexed entry stream (u16 dictionary index + u16 column
+    offset, chosen automatically for matrices with repeated values) and with the plain
+    8-byte-value / 4-byte-column stream forced (UG4B200_NO_COMPRESS=1)."""
     import ctypes as C
     from ugcore_b200 import capi
     ctx = C.c_void_p()
-    capi.check(capi.dev.ug4b200_ctx_create(0, None, C.byref(ctx)))
+    if request.param == "plain":
+        os.environ["UG4B200_NO_COMPRESS"] = "1"
+    try:
+        capi.check(capi.dev.ug4b200_ctx_create(0, None, C.byref(ctx)))
+    finally:
+        os.environ.pop("UG4B200_NO_COMPRESS", None)
     yield ctx
     capi.dev.ug4b200_ctx_destroy(ctx)

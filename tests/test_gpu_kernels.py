@@ -321,3 +321,43 @@ def test_device_convergence_state_matches_stdconvcheck(D):
     D.chk(D.dev.ug4b200_vec_set(D.ctx, 2, v, 7.0))
     D.chk(D.dev.ug4b200_set_guard(D.ctx, None))
     assert not np.any(D.down(v, 2) == 7.0)
+
+
+def test_value_indexed_stream_selection_and_parity(D, orc):
+    """The value-indexed entry stream is built only when it is lossless and fits 16 bits twice:
+    <= 65536 distinct values and, per 32-row slice, columns within 65535 of the smallest one.
+    Whatever is chosen, y = A x stays bit-identical to the CPU."""
+    from ugcore_b200 import capi, problems as pr
+    plain_ctx = "UG4B200_NO_COMPRESS"  # the 'plain' parametrisation of the context never compresses
+    rng = np.random.default_rng(5)
+
+    def crs(n, ncols, rows):
+        rowptr = np.zeros(n + 1, np.int64)
+        cols, vals = [], []
+        for r, (c, v) in enumerate(rows):
+            order = np.argsort(c)
+            cols.append(np.asarray(c, np.int32)[order]); vals.append(np.asarray(v, np.float64)[order])
+            rowptr[r + 1] = rowptr[r] + len(c)
+        return pr.Crs(n, ncols, 1, rowptr, np.concatenate(cols).astype(np.int32), np.concatenate(vals))
+
+    n = 300
+    band = [(np.unique(np.clip(np.array([r - 3, r - 1, r, r + 1, r + 5]), 0, n - 1)), None) for r in range(n)]
+    few = crs(n, n, [(c, rng.choice([1.5, -0.25, 0.0, -0.0, 3.0], size=c.size)) for c, _ in band])
+    allrandom = crs(n, n, [(c, rng.standard_normal(c.size)) for c, _ in band])
+    wide_n = 70000
+    wide = crs(64, wide_n, [(np.array([r, wide_n - 1 - r]), np.array([2.0, -1.0])) for r in range(64)])
+    many_n = 70000
+    many = crs(many_n, many_n, [(np.array([r]), np.array([float(r) + 0.5])) for r in range(many_n)])
+    expect = {"few": True, "allrandom": True, "wide": False, "many": False}  # allrandom: 1500 distinct values <= 65536
+    for name, A in (("few", few), ("allrandom", allrandom), ("wide", wide), ("many", many)):
+        dA = D.matrix(A)
+        info = capi.MatrixInfo()
+        D.chk(D.dev.ug4b200_matrix_get_info(dA, C.byref(info)))
+        if info.value_indexed:
+            assert expect[name], name
+            assert info.num_distinct_values <= 65536
+        x = rng.standard_normal(A.ncols)
+        y = D.up(np.zeros(A.nrows))
+        D.chk(D.dev.ug4b200_matrix_apply(D.ctx, dA, y, D.up(x), 1))
+        assert np.array_equal(D.down(y, A.nrows), orc.matrix(A).apply(x)), name
+        D.chk(D.dev.ug4b200_matrix_destroy(D.ctx, dA))

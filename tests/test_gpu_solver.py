@@ -211,3 +211,27 @@ def test_full_size_properties_129cubed():
         # discretisation error is O(h^2)
         assert np.abs(x - prob.exact()).max() < 0.6 * (0.5 ** refs) ** 2 * 10
     assert abs(its[6] - its[7]) <= 1
+
+
+def test_value_indexed_and_plain_streams_give_identical_histories():
+    """The value-indexed entry stream is lossless: the whole solve (history, iterates) must be
+    bit-identical to a run with the plain stream (UG4B200_NO_COMPRESS=1, separate process because
+    the host layer's context reads the switch once)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, json; sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests');"
+            "import numpy as np; import ugcore_b200 as ug; from ugcore_b200 import problems as pr; from helpers import gmg_desc;"
+            "p = pr.Problem(dim=3, num_refs=5); s = ug.Solver.from_problem(gmg_desc(5), p); x, ok, h = s.apply(p.rhs());"
+            "print('RES ' + json.dumps({'ok': bool(ok), 'h': [float(v).hex() for v in h], 'x': float(np.sum(x)).hex()}))") % (root, root)
+    out = []
+    for nc in ("0", "1"):
+        env = dict(os.environ, UG4B200_NO_COMPRESS=nc)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+        line = [l for l in r.stdout.splitlines() if l.startswith("RES ")]
+        assert line, r.stdout[-2000:] + r.stderr[-2000:]
+        out.append(json.loads(line[0][4:]))
+    assert out[0]["ok"] and out[1]["ok"]
+    assert out[0]["h"] == out[1]["h"] and out[0]["x"] == out[1]["x"]

@@ -11,15 +11,18 @@ from helpers import Dev
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def tma_ctx():
+@pytest.fixture(scope="module", params=["value_indexed", "plain"])
+def tma_ctx(request):
     from ugcore_b200 import capi
     os.environ["UG4B200_TMA_MIN_SLICES"] = "0"
+    if request.param == "plain":
+        os.environ["UG4B200_NO_COMPRESS"] = "1"
     ctx = C.c_void_p()
     try:
         capi.check(capi.dev.ug4b200_ctx_create(0, None, C.byref(ctx)))
     finally:
         del os.environ["UG4B200_TMA_MIN_SLICES"]
+        os.environ.pop("UG4B200_NO_COMPRESS", None)
     yield ctx
     capi.dev.ug4b200_ctx_destroy(ctx)
 

@@ -39,7 +39,8 @@ class ConvState(C.Structure):
 
 class MatrixInfo(C.Structure):
     _fields_ = [("nrows", c_i64), ("ncols", c_i64), ("nnz", c_i64), ("padded_nnz", c_i64), ("num_slices", c_i64),
-                ("device_bytes", c_i64), ("block", c_int), ("max_row_len", c_int)]
+                ("device_bytes", c_i64), ("block", c_int), ("max_row_len", c_int), ("value_indexed", c_int),
+                ("num_distinct_values", c_int)]
 
 
 class SolverDesc(C.Structure):

@@ -19,6 +19,7 @@ struct ug4b200_ctx {
 	int tma_min_slices_per_warp = 2; // UG4B200_TMA_MIN_SLICES=0 forces the bulk-copy kernel (tests)
 	bool tma_all = false;         // UG4B200_TMA_ALL=1: bulk-copy kernel also for unfused sweeps
 	bool no_tma = false;          // UG4B200_NO_TMA=1: register-staged SpMV everywhere (A/B measurements)
+	bool no_comp = false;         // UG4B200_NO_COMPRESS=1: never build / use the value-indexed entry stream
 	bool pdl = false;             // UG4B200_PDL=1: programmatic dependent launch (next kernel's launch overlaps this one's tail)
 	// reduction workspace (stream-ordered reuse)
 	double* partials = nullptr;   // [kMaxReduceBlocks]
@@ -310,4 +311,13 @@ struct ug4b200_matrix {
 	double* vals = nullptr;       // [padded_nnz*block*block]; entry e, component q at (e/32*BB + q)*32 + e%32
 	bool has_all_diag = false;
 	size_t device_bytes = 0;
+	// value-indexed copy of the entry stream (scalar matrices whose values repeat, e.g. every
+	// uniformly refined level): entry = u16 index into dict + u16 column offset from the slice's
+	// smallest column; 4 B instead of 12 B per entry, lossless (dict holds the exact fp64 bits)
+	bool comp = false;
+	int ndict = 0;
+	unsigned short* vidx = nullptr;   // [padded_nnz]
+	unsigned short* cidx = nullptr;   // [padded_nnz]
+	int* colbase = nullptr;           // [num_slices]
+	double* dict = nullptr;           // [ndict]
 };

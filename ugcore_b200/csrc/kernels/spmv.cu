@@ -18,6 +18,8 @@
 // Grid: persistent, (#SMs * 8) CTAs of 8 warps striding over the slices.
 #include "../common.cuh"
 #include <algorithm>
+#include <cstring>
+#include <unordered_map>
 #include <vector>
 
 namespace {
@@ -31,6 +33,8 @@ enum { FUSE_NONE = 0, FUSE_DOT = 1, FUSE_JACOBI = 2, FUSE_RESTRICT_JACOBI = 3 };
 struct Sell {
 	const int64_t* slice_ptr; const int* rowlen; const int* cols; const double* vals;
 	int64_t nrows, num_slices;
+	// value-indexed stream (COMP kernels)
+	const unsigned short* vidx; const unsigned short* cidx; const int* colbase; const double* dict; int ndict;
 };
 struct Fuse {
 	// FUSE_DOT (ar.nranks > 1: the last block also sums over the ranks through the peer windows)
@@ -58,7 +62,7 @@ template <int BETAK> __device__ __forceinline__ double mulbeta(double a, double 
 #endif
 constexpr int UNR = UG_UNR;
 
-template <int BETAK, int MODE, int FUSE>
+template <int BETAK, int MODE, int FUSE, bool COMP>
 __global__ void __launch_bounds__(kThreads, UG_MINBLK)
 spmv1_kernel(Sell A, double* dest, const double* v, double alpha, double beta, const double* __restrict__ w,
              Fuse fz, const int* guard)
@@ -75,12 +79,20 @@ spmv1_kernel(Sell A, double* dest, const double* v, double alpha, double beta, c
 		const int len = A.rowlen[row];
 		const double* vp = A.vals + base + lane;
 		const int* cp = A.cols + base + lane;
+		const unsigned short* vip = A.vidx + base + lane;
+		const unsigned short* cip = A.cidx + base + lane;
+		const int cbase = COMP ? A.colbase[s] : 0;
 		const bool live = row < A.nrows;
+		// entry k of this lane: value and column (COMP: dictionary look-up, column = slice base + offset)
+		auto ld_entry = [&](int64_t k, double& av, int& cv) {
+			if (COMP) { av = __ldg(A.dict + __ldcs(vip + k * 32)); cv = cbase + (int)__ldcs(cip + k * 32); }
+			else { av = ug_ld_stream(vp + k * 32); cv = ug_ld_stream(cp + k * 32); }
+		};
 		// ---- first batch of the matrix stream
 		double a[UNR]; int c[UNR];
 #pragma unroll
 		for (int u = 0; u < UNR; ++u)
-			if (u < width) { a[u] = ug_ld_stream(vp + u * 32); c[u] = ug_ld_stream(cp + u * 32); }
+			if (u < width) ld_entry(u, a[u], c[u]);
 		// ---- per-row streams, hoisted
 		double acc = 0.0, own = 0.0, scv = 0.0, dinv = 0.0;
 		if (MODE == MODE_INPLACE) { if (live) acc = dest[row]; }
@@ -101,7 +113,7 @@ spmv1_kernel(Sell A, double* dest, const double* v, double alpha, double beta, c
 #if UG_PIPE
 #pragma unroll
 			for (int u = 0; u < UNR; ++u)
-				if (k + UNR + u < width) { an[u] = ug_ld_stream(vp + (int64_t)(k + UNR + u) * 32); cn[u] = ug_ld_stream(cp + (int64_t)(k + UNR + u) * 32); }
+				if (k + UNR + u < width) ld_entry(k + UNR + u, an[u], cn[u]);
 #endif
 #pragma unroll
 			for (int u = 0; u < UNR; ++u) {
@@ -115,7 +127,7 @@ spmv1_kernel(Sell A, double* dest, const double* v, double alpha, double beta, c
 #if !UG_PIPE
 #pragma unroll
 			for (int u = 0; u < UNR; ++u)
-				if (k + UNR + u < width) { an[u] = ug_ld_stream(vp + (int64_t)(k + UNR + u) * 32); cn[u] = ug_ld_stream(cp + (int64_t)(k + UNR + u) * 32); }
+				if (k + UNR + u < width) ld_entry(k + UNR + u, an[u], cn[u]);
 #endif
 #pragma unroll
 			for (int u = 0; u < UNR; ++u) { a[u] = an[u]; c[u] = cn[u]; }
@@ -316,25 +328,27 @@ inline int spmv_grid(const ug4b200_ctx*, int64_t num_slices)
 }
 
 inline Sell view(const ug4b200_matrix* A)
-{ return Sell{A->slice_ptr, A->rowlen, A->cols, A->vals, A->nrows, A->num_slices}; }
+{ return Sell{A->slice_ptr, A->rowlen, A->cols, A->vals, A->nrows, A->num_slices, A->vidx, A->cidx, A->colbase, A->dict, A->ndict}; }
 
 #include "spmv_tma.cuh"
 
 
 // Large matrices: persistent bulk-copy-staged kernel, one wave of (#SMs x resident CTAs).
-template <int BETAK, int MODE, int FUSE>
+template <int BETAK, int MODE, int FUSE, bool COMP, bool SDICT = false>
 int launch_tma(ug4b200_ctx* ctx, const Sell& S, double* dest, const double* v, double alpha, double beta,
                const double* w, const Fuse& fz, bool* used)
 {
+	if constexpr (COMP && !SDICT) {
+		if (S.ndict <= tma::SDICT_MAX) return launch_tma<BETAK, MODE, FUSE, COMP, true>(ctx, S, dest, v, alpha, beta, w, fz, used);
+	}
 	static int ctas_per_sm = -1;   // per instantiation
 	*used = false;
+	auto kernel = tma::spmv1_tma_kernel<BETAK, MODE, FUSE, COMP, SDICT>;
+	constexpr int smem = tma::Cfg<COMP>::SMEM_BYTES + (SDICT ? tma::SDICT_MAX * 8 : 0);
 	if (ctas_per_sm == -1) {
-		cudaError_t e = cudaFuncSetAttribute(tma::spmv1_tma_kernel<BETAK, MODE, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-		                                     tma::SMEM_BYTES);
+		cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		int n = 0;
-		if (e == cudaSuccess)
-			e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tma::spmv1_tma_kernel<BETAK, MODE, FUSE>, tma::WPB * 32,
-			                                                  tma::SMEM_BYTES);
+		if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, tma::WPB * 32, smem);
 		if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
 		ctas_per_sm = n;
 	}
@@ -342,9 +356,29 @@ int launch_tma(ug4b200_ctx* ctx, const Sell& S, double* dest, const double* v, d
 	int64_t grid = (int64_t)ctx->num_sms * ctas_per_sm;
 	if (grid > kMaxReduceBlocks) grid = kMaxReduceBlocks;
 	if (S.num_slices < grid * tma::WPB * ctx->tma_min_slices_per_warp) return UG4B200_OK; // too small to fill the pipeline
-	UG_LAUNCH(ctx, (tma::spmv1_tma_kernel<BETAK, MODE, FUSE>), (int)grid, tma::WPB * 32, tma::SMEM_BYTES, S, dest, v, alpha,
-	          beta, w, fz, ctx->guard);
+	UG_LAUNCH(ctx, kernel, (int)grid, tma::WPB * 32, smem, S, dest, v, alpha, beta, w, fz, ctx->guard);
 	*used = true;
+	return UG4B200_OK;
+}
+
+template <int BETAK, int MODE, int FUSE, bool COMP>
+int launch_scalar(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* dest, const double* v, double alpha, double beta,
+                  const double* w, const Fuse& fz)
+{
+	const int grid = spmv_grid(ctx, A->num_slices);
+	const Sell S = view(A);
+	bool used = false;
+	// measured (profiles/r01b): the bulk-copy kernel wins for the fused variants, the register-staged
+	// one for the plain sweep; the value-indexed stream always goes through the bulk-copy kernel when
+	// the matrix is large enough (its 2-byte loads are a poor fit for register staging)
+	if constexpr (FUSE != FUSE_RESTRICT_JACOBI) {
+		if (!ctx->no_tma && (COMP || FUSE != FUSE_NONE || ctx->tma_min_slices_per_warp == 0 || ctx->tma_all)) {
+			const int rc = launch_tma<BETAK, MODE, FUSE, COMP>(ctx, S, dest, v, alpha, beta, w, fz, &used);
+			if (rc) return rc;
+		}
+	}
+	if (!used)
+		UG_LAUNCH(ctx, (spmv1_kernel<BETAK, MODE, FUSE, COMP>), grid, kThreads, 0, S, dest, v, alpha, beta, w, fz, ctx->guard);
 	return UG4B200_OK;
 }
 
@@ -355,17 +389,8 @@ int launch_mode(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* dest, const d
 	const int grid = spmv_grid(ctx, A->num_slices);
 	const Sell S = view(A);
 	if (A->block == 1 && vblock == 1) {
-		bool used = false;
-		// measured (profiles/r01b): the bulk-copy kernel wins for the fused variants, the
-		// register-staged one for the plain sweep
-		if constexpr (FUSE != FUSE_RESTRICT_JACOBI) {
-			if (!ctx->no_tma && (FUSE != FUSE_NONE || ctx->tma_min_slices_per_warp == 0 || ctx->tma_all)) {
-				const int rc = launch_tma<BETAK, MODE, FUSE>(ctx, S, dest, v, alpha, beta, w, fz, &used);
-				if (rc) return rc;
-			}
-		}
-		if (!used)
-			UG_LAUNCH(ctx, (spmv1_kernel<BETAK, MODE, FUSE>), grid, kThreads, 0, S, dest, v, alpha, beta, w, fz, ctx->guard);
+		if (A->comp && !ctx->no_comp) return launch_scalar<BETAK, MODE, FUSE, true>(ctx, A, dest, v, alpha, beta, w, fz);
+		return launch_scalar<BETAK, MODE, FUSE, false>(ctx, A, dest, v, alpha, beta, w, fz);
 	} else if (A->block == 1) {
 		if (FUSE != FUSE_NONE) return ug4b200_fail(ctx, UG4B200_ERR_ARG, "fused SpMV needs matrix block == vector block");
 		if (vblock == 2) { UG_LAUNCH(ctx, (spmv1xV_kernel<2, BETAK, MODE>), grid, kThreads, 0, S, dest, v, alpha, beta, w, ctx->guard); }
@@ -457,7 +482,6 @@ extern "C" {
 int ug4b200_matrix_upload_crs(ug4b200_ctx* ctx, int block, int64_t nrows, int64_t ncols, const int64_t* rowptr,
                               const int* cols, const double* vals, int flags, ug4b200_matrix** out)
 {
-	(void)flags;
 	UG_ARG(ctx, out != nullptr, "out is NULL");
 	*out = nullptr;
 	UG_ARG(ctx, block >= 1 && block <= 3, "block size must be 1, 2 or 3");
@@ -525,6 +549,62 @@ int ug4b200_matrix_upload_crs(ug4b200_ctx* ctx, int block, int64_t nrows, int64_
 	if (!rc) rc = up((void**)&A->diagpos, dp.data(), sizeof(int) * dp.size());
 	if (!rc) rc = up((void**)&A->cols, hc.data(), sizeof(int) * hc.size());
 	if (!rc) rc = up((void**)&A->vals, hv.data(), sizeof(double) * hv.size());
+	// ---- value-indexed copy of the entry stream (scalar matrices only) ----
+	// Conditions: at most 65536 distinct values (as bit patterns: -0.0 and 0.0 stay distinct) and, in
+	// every slice, all columns within 65535 of the slice's smallest column.  Typical for the level
+	// operators of a uniformly refined grid; otherwise the plain stream is used.
+	std::vector<unsigned short> hvi, hci; std::vector<int> hcb; std::vector<double> hdict;
+	if (!rc && block == 1 && !ctx->no_comp && !(flags & UG4B200_MAT_NO_COMPRESS) && pnnz > 0) {
+		bool ok = true;
+		hcb.assign((size_t)ns, 0);
+#pragma omp parallel for schedule(static) reduction(&& : ok)
+		for (int64_t s = 0; s < ns; ++s) {
+			int lo = 2147483647, hi = -1;
+			for (int l = 0; l < 32; ++l) {
+				const int64_t r = s * 32 + l;
+				if (r >= nrows) break;
+				if (rowptr[r + 1] > rowptr[r]) { lo = std::min(lo, cols[rowptr[r]]); hi = std::max(hi, cols[rowptr[r + 1] - 1]); }
+			}
+			if (hi < 0) lo = 0;
+			hcb[s] = lo;
+			if (hi >= 0 && (int64_t)hi - lo > 65535) ok = false;
+		}
+		std::unordered_map<uint64_t, unsigned short> dict;
+		if (ok) {
+			dict.reserve(1024);
+			for (int64_t p = 0; p < nnz && ok; ++p) {
+				uint64_t bits; std::memcpy(&bits, &vals[p], 8);
+				if (dict.find(bits) == dict.end()) {
+					if (dict.size() >= 65536) { ok = false; break; }
+					const unsigned short id = (unsigned short)dict.size();
+					dict.emplace(bits, id);
+					hdict.push_back(vals[p]);
+				}
+			}
+		}
+		if (ok) {
+			hvi.assign((size_t)pnnz, 0); hci.assign((size_t)pnnz, 0);
+#pragma omp parallel for schedule(static)
+			for (int64_t s = 0; s < ns; ++s) {
+				const int64_t base = sp[s];
+				for (int l = 0; l < 32; ++l) {
+					const int64_t r = s * 32 + l;
+					if (r >= nrows) break;
+					for (int64_t p = rowptr[r], k = 0; p < rowptr[r + 1]; ++p, ++k) {
+						uint64_t bits; std::memcpy(&bits, &vals[p], 8);
+						hvi[base + k * 32 + l] = dict.find(bits)->second;
+						hci[base + k * 32 + l] = (unsigned short)(cols[p] - hcb[s]);
+					}
+				}
+			}
+			if (hdict.empty()) hdict.push_back(0.0);
+			if (!rc) rc = up((void**)&A->vidx, hvi.data(), sizeof(unsigned short) * hvi.size());
+			if (!rc) rc = up((void**)&A->cidx, hci.data(), sizeof(unsigned short) * hci.size());
+			if (!rc) rc = up((void**)&A->colbase, hcb.data(), sizeof(int) * hcb.size());
+			if (!rc) rc = up((void**)&A->dict, hdict.data(), sizeof(double) * hdict.size());
+			if (!rc) { A->comp = true; A->ndict = (int)hdict.size(); }
+		}
+	}
 	if (rc) { ug4b200_matrix_destroy(ctx, A); return rc; }
 	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // host staging buffers die here
 	*out = A;
@@ -536,6 +616,7 @@ int ug4b200_matrix_destroy(ug4b200_ctx* ctx, ug4b200_matrix* A)
 	if (!A) return UG4B200_OK;
 	if (ctx) cudaStreamSynchronize(ctx->stream);
 	cudaFree(A->slice_ptr); cudaFree(A->rowlen); cudaFree(A->diagpos); cudaFree(A->cols); cudaFree(A->vals);
+	cudaFree(A->vidx); cudaFree(A->cidx); cudaFree(A->colbase); cudaFree(A->dict);
 	delete A;
 	return UG4B200_OK;
 }
@@ -545,6 +626,7 @@ int ug4b200_matrix_get_info(const ug4b200_matrix* A, ug4b200_matrix_info* info)
 	info->nrows = A->nrows; info->ncols = A->ncols; info->nnz = A->nnz; info->padded_nnz = A->padded_nnz;
 	info->num_slices = A->num_slices; info->device_bytes = (int64_t)A->device_bytes; info->block = A->block;
 	info->max_row_len = A->max_row_len;
+	info->value_indexed = A->comp ? 1 : 0; info->num_distinct_values = A->ndict;
 	return UG4B200_OK;
 }
 
