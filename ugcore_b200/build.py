@@ -60,8 +60,17 @@ def build(force: bool = False, verbose: bool = False) -> None:
     dev = os.path.join(LIB, "libug4b200.so")
     dsrc = [os.path.join(CSRC, s) for s in CUDA_SOURCES]
     if force or _newer(dev, dsrc + headers):
+        # one object per translation unit, compiled concurrently, then one device link
+        from concurrent.futures import ThreadPoolExecutor
         extra = os.environ.get("UG4B200_EXTRA_NVCC", "").split()  # kernel-tuning experiments only
-        _run([NVCC, *NVCC_FLAGS, *extra, *dsrc, "-o", dev, "-ldl", "-lgomp"], verbose)
+        objdir = os.path.join(LIB, "obj")
+        os.makedirs(objdir, exist_ok=True)
+        cflags = [f for f in NVCC_FLAGS if f != "-shared"]
+        objs = [os.path.join(objdir, os.path.basename(s)[:-3] + ".o") for s in dsrc]
+        todo = [(s, o) for s, o in zip(dsrc, objs) if force or extra or _newer(o, [s] + headers)]
+        with ThreadPoolExecutor(max_workers=max(1, len(todo))) as ex:
+            list(ex.map(lambda so: _run([NVCC, *cflags, *extra, "-c", so[0], "-o", so[1]], verbose), todo))
+        _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", *objs, "-o", dev, "-ldl", "-lgomp"], verbose)
 
     host = os.path.join(LIB, "libug4b200_host.so")
     hsrc = [os.path.join(CSRC, "solver_capi.cpp")]

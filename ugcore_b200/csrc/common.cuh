@@ -312,12 +312,15 @@ struct ug4b200_matrix {
 	bool has_all_diag = false;
 	size_t device_bytes = 0;
 	// value-indexed copy of the entry stream (scalar matrices whose values repeat, e.g. every
-	// uniformly refined level): entry = u16 index into dict + u16 column offset from the slice's
-	// smallest column; 4 B instead of 12 B per entry, lossless (dict holds the exact fp64 bits)
+	// uniformly refined level): one 32-bit word per entry = column offset from the slice's smallest
+	// column in the high half, dictionary index << vshift in the low half; 4 B instead of 12 B per
+	// entry, lossless (dict holds the exact fp64 bits).  vshift = 3 for dictionaries of <= 1024 values
+	// (the low half is then the BYTE offset into the dictionary, and word >> 13 the byte offset of the
+	// column: one instruction each in the kernel), 0 otherwise.  Padding words are 0 (safe to load).
 	bool comp = false;
 	int ndict = 0;
-	unsigned short* vidx = nullptr;   // [padded_nnz]
-	unsigned short* cidx = nullptr;   // [padded_nnz]
+	int vshift = 0;
+	unsigned int* vc = nullptr;       // [padded_nnz]
 	int* colbase = nullptr;           // [num_slices]
 	double* dict = nullptr;           // [ndict]
 };

@@ -33,8 +33,8 @@ enum { FUSE_NONE = 0, FUSE_DOT = 1, FUSE_JACOBI = 2, FUSE_RESTRICT_JACOBI = 3 };
 struct Sell {
 	const int64_t* slice_ptr; const int* rowlen; const int* cols; const double* vals;
 	int64_t nrows, num_slices;
-	// value-indexed stream (COMP kernels)
-	const unsigned short* vidx; const unsigned short* cidx; const int* colbase; const double* dict; int ndict;
+	// value-indexed stream (COMP kernels): word = column offset << 16 | dictionary index << vshift
+	const unsigned int* vc; const int* colbase; const double* dict; int ndict; int vshift;
 };
 struct Fuse {
 	// FUSE_DOT (ar.nranks > 1: the last block also sums over the ranks through the peer windows)
@@ -79,13 +79,12 @@ spmv1_kernel(Sell A, double* dest, const double* v, double alpha, double beta, c
 		const int len = A.rowlen[row];
 		const double* vp = A.vals + base + lane;
 		const int* cp = A.cols + base + lane;
-		const unsigned short* vip = A.vidx + base + lane;
-		const unsigned short* cip = A.cidx + base + lane;
+		const unsigned int* vcp = A.vc + base + lane;
 		const int cbase = COMP ? A.colbase[s] : 0;
 		const bool live = row < A.nrows;
 		// entry k of this lane: value and column (COMP: dictionary look-up, column = slice base + offset)
 		auto ld_entry = [&](int64_t k, double& av, int& cv) {
-			if (COMP) { av = __ldg(A.dict + __ldcs(vip + k * 32)); cv = cbase + (int)__ldcs(cip + k * 32); }
+			if (COMP) { const unsigned int e = __ldcs(vcp + k * 32); av = __ldg(A.dict + ((e & 0xffffu) >> A.vshift)); cv = cbase + (int)(e >> 16); }
 			else { av = ug_ld_stream(vp + k * 32); cv = ug_ld_stream(cp + k * 32); }
 		};
 		// ---- first batch of the matrix stream
@@ -328,37 +327,51 @@ inline int spmv_grid(const ug4b200_ctx*, int64_t num_slices)
 }
 
 inline Sell view(const ug4b200_matrix* A)
-{ return Sell{A->slice_ptr, A->rowlen, A->cols, A->vals, A->nrows, A->num_slices, A->vidx, A->cidx, A->colbase, A->dict, A->ndict}; }
+{ return Sell{A->slice_ptr, A->rowlen, A->cols, A->vals, A->nrows, A->num_slices, A->vc, A->colbase, A->dict, A->ndict, A->vshift}; }
 
 #include "spmv_tma.cuh"
 
 
-// Large matrices: persistent bulk-copy-staged kernel, one wave of (#SMs x resident CTAs).
-template <int BETAK, int MODE, int FUSE, bool COMP, bool SDICT = false>
+// Large matrices: persistent bulk-copy-staged kernels, one wave of (#SMs x resident CTAs).
+template <typename K>
+int launch_persistent(ug4b200_ctx* ctx, K kernel, int* ctas_per_sm, int threads, int smem, int wpb, const Sell& S, double* dest,
+                      const double* v, double alpha, double beta, const double* w, const Fuse& fz, bool* used)
+{
+	*used = false;
+	if (*ctas_per_sm == -1) {
+		cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		int n = 0;
+		if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem);
+		if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+		*ctas_per_sm = n;
+	}
+	if (*ctas_per_sm <= 0) return UG4B200_OK;
+	int64_t grid = (int64_t)ctx->num_sms * *ctas_per_sm;
+	if (grid > kMaxReduceBlocks) grid = kMaxReduceBlocks;
+	if (S.num_slices < grid * wpb * ctx->tma_min_slices_per_warp) return UG4B200_OK; // too small to fill the pipeline
+	UG_LAUNCH(ctx, kernel, (int)grid, threads, smem, S, dest, v, alpha, beta, w, fz, ctx->guard);
+	*used = true;
+	return UG4B200_OK;
+}
+template <int BETAK, int MODE, int FUSE, bool COMP>
 int launch_tma(ug4b200_ctx* ctx, const Sell& S, double* dest, const double* v, double alpha, double beta,
                const double* w, const Fuse& fz, bool* used)
 {
-	if constexpr (COMP && !SDICT) {
-		if (S.ndict <= tma::SDICT_MAX) return launch_tma<BETAK, MODE, FUSE, COMP, true>(ctx, S, dest, v, alpha, beta, w, fz, used);
+	if constexpr (COMP) {
+		typedef tma::VCfg C;
+		if (S.ndict <= tma::SDICT_MAX && S.vshift == 3) {
+			static int cps = -1;   // per instantiation
+			return launch_persistent(ctx, tma::spmv1_vi_kernel<BETAK, MODE, FUSE, true>, &cps, C::WPB * 32, C::SMEM_BYTES_SDICT, C::WPB,
+			                         S, dest, v, alpha, beta, w, fz, used);
+		}
+		static int cps = -1;
+		return launch_persistent(ctx, tma::spmv1_vi_kernel<BETAK, MODE, FUSE, false>, &cps, C::WPB * 32, C::SMEM_BYTES, C::WPB,
+		                         S, dest, v, alpha, beta, w, fz, used);
+	} else {
+		static int cps = -1;
+		return launch_persistent(ctx, tma::spmv1_tma_kernel<BETAK, MODE, FUSE>, &cps, tma::WPB * 32, tma::Cfg::SMEM_BYTES, tma::WPB,
+		                         S, dest, v, alpha, beta, w, fz, used);
 	}
-	static int ctas_per_sm = -1;   // per instantiation
-	*used = false;
-	auto kernel = tma::spmv1_tma_kernel<BETAK, MODE, FUSE, COMP, SDICT>;
-	constexpr int smem = tma::Cfg<COMP>::SMEM_BYTES + (SDICT ? tma::SDICT_MAX * 8 : 0);
-	if (ctas_per_sm == -1) {
-		cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-		int n = 0;
-		if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, tma::WPB * 32, smem);
-		if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
-		ctas_per_sm = n;
-	}
-	if (ctas_per_sm <= 0) return UG4B200_OK;
-	int64_t grid = (int64_t)ctx->num_sms * ctas_per_sm;
-	if (grid > kMaxReduceBlocks) grid = kMaxReduceBlocks;
-	if (S.num_slices < grid * tma::WPB * ctx->tma_min_slices_per_warp) return UG4B200_OK; // too small to fill the pipeline
-	UG_LAUNCH(ctx, kernel, (int)grid, tma::WPB * 32, smem, S, dest, v, alpha, beta, w, fz, ctx->guard);
-	*used = true;
-	return UG4B200_OK;
 }
 
 template <int BETAK, int MODE, int FUSE, bool COMP>
@@ -553,7 +566,7 @@ int ug4b200_matrix_upload_crs(ug4b200_ctx* ctx, int block, int64_t nrows, int64_
 	// Conditions: at most 65536 distinct values (as bit patterns: -0.0 and 0.0 stay distinct) and, in
 	// every slice, all columns within 65535 of the slice's smallest column.  Typical for the level
 	// operators of a uniformly refined grid; otherwise the plain stream is used.
-	std::vector<unsigned short> hvi, hci; std::vector<int> hcb; std::vector<double> hdict;
+	std::vector<unsigned int> hvc; std::vector<int> hcb; std::vector<double> hdict;
 	if (!rc && block == 1 && !ctx->no_comp && !(flags & UG4B200_MAT_NO_COMPRESS) && pnnz > 0) {
 		bool ok = true;
 		hcb.assign((size_t)ns, 0);
@@ -583,7 +596,8 @@ int ug4b200_matrix_upload_crs(ug4b200_ctx* ctx, int block, int64_t nrows, int64_
 			}
 		}
 		if (ok) {
-			hvi.assign((size_t)pnnz, 0); hci.assign((size_t)pnnz, 0);
+			const int vshift = hdict.size() <= 1024 ? 3 : 0;
+			hvc.assign((size_t)pnnz, 0u);
 #pragma omp parallel for schedule(static)
 			for (int64_t s = 0; s < ns; ++s) {
 				const int64_t base = sp[s];
@@ -592,17 +606,15 @@ int ug4b200_matrix_upload_crs(ug4b200_ctx* ctx, int block, int64_t nrows, int64_
 					if (r >= nrows) break;
 					for (int64_t p = rowptr[r], k = 0; p < rowptr[r + 1]; ++p, ++k) {
 						uint64_t bits; std::memcpy(&bits, &vals[p], 8);
-						hvi[base + k * 32 + l] = dict.find(bits)->second;
-						hci[base + k * 32 + l] = (unsigned short)(cols[p] - hcb[s]);
+						hvc[base + k * 32 + l] = ((unsigned int)(cols[p] - hcb[s]) << 16) | ((unsigned int)dict.find(bits)->second << vshift);
 					}
 				}
 			}
 			if (hdict.empty()) hdict.push_back(0.0);
-			if (!rc) rc = up((void**)&A->vidx, hvi.data(), sizeof(unsigned short) * hvi.size());
-			if (!rc) rc = up((void**)&A->cidx, hci.data(), sizeof(unsigned short) * hci.size());
+			if (!rc) rc = up((void**)&A->vc, hvc.data(), sizeof(unsigned int) * hvc.size());
 			if (!rc) rc = up((void**)&A->colbase, hcb.data(), sizeof(int) * hcb.size());
 			if (!rc) rc = up((void**)&A->dict, hdict.data(), sizeof(double) * hdict.size());
-			if (!rc) { A->comp = true; A->ndict = (int)hdict.size(); }
+			if (!rc) { A->comp = true; A->ndict = (int)hdict.size(); A->vshift = vshift; }
 		}
 	}
 	if (rc) { ug4b200_matrix_destroy(ctx, A); return rc; }
@@ -616,7 +628,7 @@ int ug4b200_matrix_destroy(ug4b200_ctx* ctx, ug4b200_matrix* A)
 	if (!A) return UG4B200_OK;
 	if (ctx) cudaStreamSynchronize(ctx->stream);
 	cudaFree(A->slice_ptr); cudaFree(A->rowlen); cudaFree(A->diagpos); cudaFree(A->cols); cudaFree(A->vals);
-	cudaFree(A->vidx); cudaFree(A->cidx); cudaFree(A->colbase); cudaFree(A->dict);
+	cudaFree(A->vc); cudaFree(A->colbase); cudaFree(A->dict);
 	delete A;
 	return UG4B200_OK;
 }

@@ -11,15 +11,14 @@
 // pressure; the only register-staged loads left are the x-gather (L1/L2 resident) and the
 // per-row vectors.  Arithmetic is unchanged: one thread per row, ascending column order, no FMA.
 //
-// Two entry-stream formats (template parameter COMP):
-//   plain   8-byte value + 4-byte column per entry; KC = 16 columns per chunk (6 KB), ring of 2
-//   COMP    value-indexed: u16 dictionary index + u16 column offset from the slice's smallest
-//           column (4 B per entry instead of 12, lossless); KC = 32 (4 KB), ring of 3.  The
-//           dictionary (a few dozen doubles on a uniformly refined level) is read through L1.
-// A chunk is consumed in register batches of UB = 16 entries.
+// Two kernels, one per entry-stream format:
+//   spmv1_tma_kernel  plain stream: 8-byte value + 4-byte column per entry; KC = 16 entry columns per
+//                     chunk (6 KB), ring of 2 per warp; consumed in register batches of UB = 16
+//   spmv1_vi_kernel   value-indexed stream: ONE 32-bit word per entry (column offset from the slice's
+//                     smallest column << 16 | dictionary byte offset), 4 B per entry instead of 12,
+//                     lossless; see below
 //
-// Grid: persistent, 2 CTAs (8 warps each, 96 KB of shared memory) per SM; warp g handles
-// slices g, g + W, g + 2W, ...
+// Grid: persistent, one wave of (#SMs x resident CTAs); warp g handles slices g, g + W, g + 2W, ...
 #pragma once
 
 namespace tma {
@@ -30,12 +29,6 @@ namespace tma {
 #ifndef UG_TMA_NST
 #define UG_TMA_NST 2
 #endif
-#ifndef UG_TMA_KCC
-#define UG_TMA_KCC 32
-#endif
-#ifndef UG_TMA_NSTC
-#define UG_TMA_NSTC 3
-#endif
 #ifndef UG_TMA_WPB
 #define UG_TMA_WPB 8
 #endif
@@ -45,14 +38,8 @@ namespace tma {
 constexpr int WPB = UG_TMA_WPB;   // warps per CTA
 constexpr int UB = 16;            // entries per register batch
 
-template <bool COMP> struct Cfg;
-template <> struct Cfg<false> {
+struct Cfg {
 	static constexpr int KC = UG_TMA_KC, NST = UG_TMA_NST, VB = 8, CB = 4;
-	static constexpr int WARP_BYTES = NST * KC * 32 * (VB + CB) + 64;
-	static constexpr int SMEM_BYTES = WPB * WARP_BYTES + 128;
-};
-template <> struct Cfg<true> {
-	static constexpr int KC = UG_TMA_KCC, NST = UG_TMA_NSTC, VB = 2, CB = 2;
 	static constexpr int WARP_BYTES = NST * KC * 32 * (VB + CB) + 64;
 	static constexpr int SMEM_BYTES = WPB * WARP_BYTES + 128;
 };
@@ -104,34 +91,25 @@ struct Cursor {
 	int k0;         // first entry column of the current chunk
 };
 
-constexpr int SDICT_MAX = 1024;   // dictionaries up to this size are staged in shared memory (8 KB)
-
-template <int BETAK, int MODE, int FUSE, bool COMP, bool SDICT = false>
+// ---------------------------------------------------------------- plain stream
+template <int BETAK, int MODE, int FUSE>
 __global__ void __launch_bounds__(WPB * 32, UG_TMA_MINCTA)
 spmv1_tma_kernel(Sell A, double* dest, const double* v, double alpha, double beta, const double* __restrict__ w,
                  Fuse fz, const int* guard)
 {
 	if (ug_guarded(guard)) return;
-	typedef Cfg<COMP> C;
+	typedef Cfg C;
 	constexpr int KC = C::KC, NST = C::NST, VB = C::VB, CB = C::CB;
 	constexpr int CHUNK = KC * 32;                     // entries per chunk
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const uint32_t smem0 = smem_base_opaque(smem_raw);
 	const uint32_t wbase = smem0 + (uint32_t)wid * C::WARP_BYTES;
-	const uint32_t vbuf_s = wbase;                                   // [NST][CHUNK] values / value indices
-	const uint32_t cbuf_s = wbase + NST * CHUNK * VB;                // [NST][CHUNK] columns / column offsets
+	const uint32_t vbuf_s = wbase;                                   // [NST][CHUNK] values
+	const uint32_t cbuf_s = wbase + NST * CHUNK * VB;                // [NST][CHUNK] columns
 	const uint32_t bars = wbase + NST * CHUNK * (VB + CB);           // [NST] mbarriers (8 bytes each)
 	const int64_t gwarp = (int64_t)blockIdx.x * WPB + wid;
 	const int64_t nwarps = (int64_t)gridDim.x * WPB;
-	// dictionary of the value-indexed stream: behind the rings in shared memory when it is small
-	double* sdict = reinterpret_cast<double*>(smem_raw + (size_t)WPB * C::WARP_BYTES + 128);
-	if (COMP && SDICT) {
-		for (int i = threadIdx.x; i < A.ndict; i += blockDim.x) sdict[i] = A.dict[i];
-		__syncthreads();
-	}
-	const uint32_t sdict_s = smem0 + (uint32_t)WPB * C::WARP_BYTES + 128u;
-	auto dict_at = [&](int vi) -> double { return SDICT ? lds_f64(sdict_s + (uint32_t)vi * 8u) : __ldg(A.dict + vi); };
 
 	if (lane == 0) {
 #pragma unroll
@@ -159,13 +137,8 @@ spmv1_tma_kernel(Sell A, double* dest, const double* v, double alpha, double bet
 				const int64_t e0 = c.base + (int64_t)c.k0 * 32;
 				const uint32_t bar = bars + st * 8;
 				mbar_expect_tx(bar, (uint32_t)nk * 32 * (VB + CB));
-				if (COMP) {
-					bulk_g2s(vbuf_s + st * CHUNK * VB, A.vidx + e0, (uint32_t)nk * 32 * VB, bar);
-					bulk_g2s(cbuf_s + st * CHUNK * CB, A.cidx + e0, (uint32_t)nk * 32 * CB, bar);
-				} else {
-					bulk_g2s(vbuf_s + st * CHUNK * VB, A.vals + e0, (uint32_t)nk * 32 * VB, bar);
-					bulk_g2s(cbuf_s + st * CHUNK * CB, A.cols + e0, (uint32_t)nk * 32 * CB, bar);
-				}
+				bulk_g2s(vbuf_s + st * CHUNK * VB, A.vals + e0, (uint32_t)nk * 32 * VB, bar);
+				bulk_g2s(cbuf_s + st * CHUNK * CB, A.cols + e0, (uint32_t)nk * 32 * CB, bar);
 			} else mbar_arrive(bars + st * 8);
 		}
 	};
@@ -176,16 +149,15 @@ spmv1_tma_kernel(Sell A, double* dest, const double* v, double alpha, double bet
 	for (int i = 0; i < NST; ++i) {
 		if (prod.s < A.num_slices) { issue(prod, i); advance(prod); }
 	}
-	// Consumer side: the metadata of the NEXT slice (entry offset, width, this lane's row length, column
-	// base) is requested while the current slice is processed, so that no slice starts with an exposed
-	// HBM round trip (measured: 30 % of all stall samples before this was done).
-	struct Meta { int64_t s; int width, len, cbase; double acc0; };
+	// Consumer side: the metadata of the NEXT slice (entry offset, width, this lane's row length) is
+	// requested while the current slice is processed, so that no slice starts with an exposed HBM
+	// round trip (measured: 30 % of all stall samples before this was done).
+	struct Meta { int64_t s; int width, len; double acc0; };
 	auto fetch_meta = [&](int64_t sl) {
-		Meta m; m.s = sl; m.width = 0; m.len = 0; m.cbase = 0; m.acc0 = 0.0;
+		Meta m; m.s = sl; m.width = 0; m.len = 0; m.acc0 = 0.0;
 		if (sl < A.num_slices) {
 			m.width = (int)((A.slice_ptr[sl + 1] - A.slice_ptr[sl]) >> 5);
 			m.len = A.rowlen[sl * 32 + lane];
-			if (COMP) m.cbase = A.colbase[sl];
 			// the row sum starts from dest / v: the first addition must not wait for HBM either
 			if (MODE == MODE_INPLACE) { if (sl * 32 + lane < A.nrows) m.acc0 = dest[sl * 32 + lane]; }
 			else if (MODE == MODE_GENERAL) { if (sl * 32 + lane < A.nrows) m.acc0 = v[sl * 32 + lane]; }
@@ -201,7 +173,6 @@ spmv1_tma_kernel(Sell A, double* dest, const double* v, double alpha, double bet
 		const bool live = row < A.nrows;
 		const int len = cur.len;
 		const int width = cur.width;
-		const int cbase = cur.cbase;
 		// per-row streams first: their latency overlaps the whole slice
 		double acc = 0.0, own = 0.0, scv = 0.0, dinv = 0.0;
 		if (MODE == MODE_INPLACE) acc = cur.acc0;
@@ -216,65 +187,265 @@ spmv1_tma_kernel(Sell A, double* dest, const double* v, double alpha, double bet
 		do {
 			const int nk = min(KC, width - k0);
 			mbar_wait(bars + stage * 8, phase);
-			if constexpr (COMP) {
-				// All x-gathers of the chunk are issued before any arithmetic (up to 32 independent loads in
-				// flight per lane; the column offsets come from shared memory and are not kept), then the
-				// row sum is built in column order with the values looked up through the dictionary.
-				const uint32_t vs = vbuf_s + (uint32_t)(stage * CHUNK + lane) * 2u;
-				const uint32_t cs = cbuf_s + (uint32_t)(stage * CHUNK + lane) * 2u;
-				const double* wb = w + cbase;
-				double x[KC];
-				if (__all_sync(0xffffffffu, len >= k0 + nk)) {      // every lane owns all nk entries (interior slices)
 #pragma unroll
-					for (int u = 0; u < KC; ++u)
-						if (u < nk) x[u] = __ldg(wb + lds_u16(cs + u * 64));
+			for (int ub = 0; ub < KC; ub += UB) {
+				if (ub < nk) {
+					double a[UB]; int c[UB]; double x[UB];
+					const uint32_t vs = vbuf_s + (uint32_t)(stage * CHUNK + ub * 32 + lane) * 8u;
+					const uint32_t cs = cbuf_s + (uint32_t)(stage * CHUNK + ub * 32 + lane) * 4u;
 #pragma unroll
-					for (int u = 0; u < KC; ++u) {
-						if (u < nk) {
-							const double t = mulbeta<BETAK>(dict_at(lds_u16(vs + u * 64)), beta) * x[u];
-							if ((MODE == MODE_ASSIGN || MODE == MODE_ASSIGN_SKIP_EMPTY) && u == 0 && k0 == 0) acc = t;
+					for (int u = 0; u < UB; ++u)
+						if (ub + u < nk) { a[u] = lds_f64(vs + u * 256); c[u] = lds_s32(cs + u * 128); }
+#pragma unroll
+					for (int u = 0; u < UB; ++u)
+						if (k0 + ub + u < len) x[u] = __ldg(w + c[u]);
+#pragma unroll
+					for (int u = 0; u < UB; ++u) {
+						if (k0 + ub + u < len) {
+							const double t = mulbeta<BETAK>(a[u], beta) * x[u];
+							if ((MODE == MODE_ASSIGN || MODE == MODE_ASSIGN_SKIP_EMPTY) && k0 + ub + u == 0) acc = t;
 							else acc = acc + t;
-						}
-					}
-				} else {
-#pragma unroll
-					for (int u = 0; u < KC; ++u)
-						if (k0 + u < len) x[u] = __ldg(wb + lds_u16(cs + u * 64));
-#pragma unroll
-					for (int u = 0; u < KC; ++u) {
-						if (k0 + u < len) {
-							const double t = mulbeta<BETAK>(dict_at(lds_u16(vs + u * 64)), beta) * x[u];
-							if ((MODE == MODE_ASSIGN || MODE == MODE_ASSIGN_SKIP_EMPTY) && u == 0 && k0 == 0) acc = t;
-							else acc = acc + t;
-						}
-					}
-				}
-			} else {
-#pragma unroll
-				for (int ub = 0; ub < KC; ub += UB) {
-					if (ub < nk) {
-						double a[UB]; int c[UB]; double x[UB];
-						const uint32_t vs = vbuf_s + (uint32_t)(stage * CHUNK + ub * 32 + lane) * 8u;
-						const uint32_t cs = cbuf_s + (uint32_t)(stage * CHUNK + ub * 32 + lane) * 4u;
-#pragma unroll
-						for (int u = 0; u < UB; ++u)
-							if (ub + u < nk) { a[u] = lds_f64(vs + u * 256); c[u] = lds_s32(cs + u * 128); }
-#pragma unroll
-						for (int u = 0; u < UB; ++u)
-							if (k0 + ub + u < len) x[u] = __ldg(w + c[u]);
-#pragma unroll
-						for (int u = 0; u < UB; ++u) {
-							if (k0 + ub + u < len) {
-								const double t = mulbeta<BETAK>(a[u], beta) * x[u];
-								if ((MODE == MODE_ASSIGN || MODE == MODE_ASSIGN_SKIP_EMPTY) && k0 + ub + u == 0) acc = t;
-								else acc = acc + t;
-							}
 						}
 					}
 				}
 			}
 			__syncwarp();                       // every lane has consumed this stage: refill it
 			if (prod.s < A.num_slices) { issue(prod, stage); advance(prod); }
+			if (++stage == NST) { stage = 0; phase ^= 1u; }
+			k0 += KC;
+		} while (k0 < width);
+		if (FUSE == FUSE_JACOBI) {
+			if (live) {
+				dest[row] = acc;
+				if (fz.flags & UG4B200_SMOOTH_ADD_IN) scv = scv + own;
+				if (fz.flags & UG4B200_SMOOTH_JACOBI) {
+					const double st = dinv * acc;
+					fz.st_out[row] = st;
+					if (fz.flags & UG4B200_SMOOTH_ADD_OUT) scv = scv + st;
+				}
+				if (fz.flags & (UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_ADD_OUT)) fz.sc[row] = scv;
+			}
+		} else {
+			if (live && (MODE != MODE_ASSIGN_SKIP_EMPTY || len > 0)) dest[row] = acc;
+			if (FUSE == FUSE_DOT && live) dot += acc * own;
+		}
+		cur = nxt;
+	}
+	if (FUSE == FUSE_DOT) ug_block_reduce_fin(dot, fz.partials, fz.counter, fz.fin, fz.ar);
+}
+
+// ---------------------------------------------------------------- value-indexed stream
+// One 32-bit word per entry: (column offset from the slice's smallest column) << 16 | (dictionary
+// index << vshift).  With a dictionary of <= 1024 values (SDICT: staged in shared memory at an
+// 8 KB-aligned shared address, vshift = 3) the two look-ups of an entry cost one integer
+// instruction each:
+//     x address (low word) = word >> 13 + low word of (w + colbase)     one IMAD.HI (mul.hi by 2^19 + add)
+//     dictionary address   = (word & 0x1ff8) | dictionary base          one LOP3
+// so an entry is LDS.32, IMAD.HI, LDG.64, LOP3, LDS.64, DMUL, DADD.  (The 64-bit x address is
+// assembled from that low word and the unchanged high word; a slice whose 512 KB window would carry
+// into the high word — once per 4 GB of address space — takes the generic path.)
+// A chunk (one bulk copy) is a slice's whole entry block up to VKC = VNB * VUB columns; it is consumed
+// in register batches of VUB entries, software-pipelined: the x-gathers of batch j + 1 are in flight
+// while batch j is accumulated.  Batches in which every lane owns all VUB entries run unpredicated.
+#ifndef UG_VI_UB
+#define UG_VI_UB 9
+#endif
+#ifndef UG_VI_NB
+#define UG_VI_NB 3
+#endif
+#ifndef UG_VI_NST
+#define UG_VI_NST 2
+#endif
+#ifndef UG_VI_WPB
+#define UG_VI_WPB 8
+#endif
+#ifndef UG_VI_MINCTA
+#define UG_VI_MINCTA 3
+#endif
+#ifndef UG_VI_PIPE
+#define UG_VI_PIPE 0   // 1: gathers of batch j + 1 in flight while batch j is accumulated (two register buffers; measured slower: spills at 80 registers)
+#endif
+constexpr int SDICT_MAX = 1024;   // dictionaries up to this size are staged in shared memory (8 KB)
+struct VCfg {
+	static constexpr int UB = UG_VI_UB, NB = UG_VI_NB, KC = UB * NB, NST = UG_VI_NST, WPB = UG_VI_WPB;
+	static constexpr int STAGE_BYTES = KC * 128;
+	static constexpr int WARP_BYTES = NST * STAGE_BYTES;
+	static constexpr int RING_BYTES = WPB * WARP_BYTES;
+	static constexpr int BAR_BYTES = ((WPB * NST * 8 + 127) / 128) * 128;
+	// dictionary: 8 KB at the next 8 KB-aligned shared address behind rings and barriers
+	static constexpr int SMEM_BYTES_SDICT = RING_BYTES + BAR_BYTES + 2 * SDICT_MAX * 8;
+	static constexpr int SMEM_BYTES = RING_BYTES + BAR_BYTES;
+};
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ double ldg_nc_f64_lohi(uint32_t lo, uint32_t hi)
+{
+	double v;
+	asm volatile("{\n\t.reg .u64 a;\n\tmov.b64 a, {%1, %2};\n\tld.global.nc.f64 %0, [a];\n\t}" : "=d"(v) : "r"(lo), "r"(hi));
+	return v;
+}
+
+template <int BETAK, int MODE, int FUSE, bool SDICT>
+__global__ void __launch_bounds__(VCfg::WPB * 32, UG_VI_MINCTA)
+spmv1_vi_kernel(Sell A, double* dest, const double* v, double alpha, double beta, const double* __restrict__ w,
+                Fuse fz, const int* guard)
+{
+	if (ug_guarded(guard)) return;
+	typedef VCfg C;
+	constexpr int UB = C::UB, NB = C::NB, KC = C::KC, NST = C::NST, VWPB = C::WPB;
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const uint32_t smem0 = smem_base_opaque(smem_raw);
+	const uint32_t ring_s = smem0 + (uint32_t)wid * C::WARP_BYTES;             // [NST][KC][32] words
+	const uint32_t bars = smem0 + C::RING_BYTES + (uint32_t)wid * NST * 8;     // [NST] mbarriers
+	const uint32_t sdict_s = (smem0 + C::RING_BYTES + C::BAR_BYTES + 8191u) & ~8191u;
+	// slices and rows are < 2^31 (checked at upload): 32-bit bookkeeping keeps the kernel at 80 registers
+	const int gwarp = (int)blockIdx.x * VWPB + wid;
+	const int nwarps = (int)gridDim.x * VWPB;
+	const int nslices = (int)A.num_slices, nrows = (int)A.nrows;
+	if (SDICT) {
+		for (int i = threadIdx.x; i < A.ndict; i += blockDim.x)
+			asm volatile("st.shared.f64 [%0], %1;" ::"r"(sdict_s + (uint32_t)i * 8u), "d"(A.dict[i]) : "memory");
+		__syncthreads();
+	}
+	if (lane == 0) {
+#pragma unroll
+		for (int i = 0; i < NST; ++i) mbar_init(bars + i * 8, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncwarp();
+
+	// ---- producer (lane 0): one bulk copy per chunk
+	struct VCursor { int s, width, k0; int64_t base; };
+	auto load_slice = [&](VCursor& c) {
+		if (c.s < nslices) {
+			c.base = A.slice_ptr[c.s];
+			c.width = (int)((A.slice_ptr[c.s + 1] - c.base) >> 5);
+		} else { c.base = 0; c.width = 0; }
+		c.k0 = 0;
+	};
+	auto advance = [&](VCursor& c) {
+		c.k0 += KC;
+		if (c.k0 >= c.width) { c.s += nwarps; load_slice(c); }
+	};
+	auto issue = [&](const VCursor& c, int st) {
+		if (lane == 0) {
+			const int nk = min(KC, c.width - c.k0);
+			const uint32_t bar = bars + st * 8;
+			if (nk > 0) {
+				mbar_expect_tx(bar, (uint32_t)nk * 128u);
+				bulk_g2s(ring_s + st * C::STAGE_BYTES, A.vc + c.base + (int64_t)c.k0 * 32, (uint32_t)nk * 128u, bar);
+			} else mbar_arrive(bar);
+		}
+	};
+	VCursor prod; prod.s = gwarp; load_slice(prod);
+#pragma unroll
+	for (int i = 0; i < NST; ++i) {
+		if (prod.s < nslices) { issue(prod, i); advance(prod); }
+	}
+
+	// ---- consumer
+	struct Meta { int s, width, len, cbase; double acc0; };
+	auto fetch_meta = [&](int sl) {
+		Meta m; m.s = sl; m.width = 0; m.len = 0; m.cbase = 0; m.acc0 = 0.0;
+		if (sl < nslices) {
+			m.width = (int)((A.slice_ptr[sl + 1] - A.slice_ptr[sl]) >> 5);
+			m.len = A.rowlen[sl * 32 + lane];
+			m.cbase = A.colbase[sl];
+			if (MODE == MODE_INPLACE) { if (sl * 32 + lane < nrows) m.acc0 = dest[sl * 32 + lane]; }
+			else if (MODE == MODE_GENERAL) { if (sl * 32 + lane < nrows) m.acc0 = v[sl * 32 + lane]; }
+		}
+		return m;
+	};
+	Meta cur = fetch_meta(gwarp);
+	int stage = 0; uint32_t phase = 0;
+	double dot = 0.0;
+	while (cur.s < nslices) {
+		const Meta nxt = fetch_meta(cur.s + nwarps);
+		const int row = cur.s * 32 + lane;
+		const bool live = row < nrows;
+		const int len = cur.len;
+		const int width = cur.width;
+		// all lanes own the first minlen entry columns of the slice: those batches run unpredicated
+		const int minlen = __reduce_min_sync(0xffffffffu, len);
+		const double* wb = w + cur.cbase;
+		const uint32_t wlo = (uint32_t)(uintptr_t)wb, whi = (uint32_t)((uintptr_t)wb >> 32);
+		const bool fast_addr = SDICT && wlo <= 0xffffffffu - (65535u << 3);
+		double acc = 0.0, own = 0.0, scv = 0.0, dinv = 0.0;
+		if (MODE == MODE_INPLACE) acc = cur.acc0;
+		else if (MODE == MODE_GENERAL) acc = alpha * cur.acc0;
+		if (FUSE == FUSE_DOT) { if (live) own = w[row]; }
+		if (FUSE == FUSE_JACOBI && live) {
+			if (fz.flags & UG4B200_SMOOTH_ADD_IN) own = w[row];
+			if ((fz.flags & (UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_ADD_OUT)) && !(fz.flags & UG4B200_SMOOTH_SC_ZERO)) scv = fz.sc[row];
+			if (fz.flags & UG4B200_SMOOTH_JACOBI) dinv = fz.diaginv[row];
+		}
+		constexpr int NBUF = UG_VI_PIPE ? 2 : 1;
+		uint32_t e[NBUF][UB]; double x[NBUF][UB];
+		// entry words + x-gathers of the batch starting at chunk column kb (absolute column k0 + kb)
+		auto load_batch = [&](uint32_t cs, int k0, int kb, int nk, uint32_t (&eb)[UB], double (&xb)[UB]) {
+			const uint32_t a0 = cs + (uint32_t)kb * 128u;
+			if (fast_addr && k0 + kb + UB <= minlen) {
+#pragma unroll
+				for (int u = 0; u < UB; ++u) {
+					eb[u] = lds_u32(a0 + u * 128);
+					xb[u] = ldg_nc_f64_lohi(__umulhi(eb[u], 1u << 19) + wlo, whi);
+				}
+			} else {
+				// generic: words beyond the chunk's columns are not read; padding words (0) are safe to follow
+#pragma unroll
+				for (int u = 0; u < UB; ++u) {
+					if (kb + u < nk) {
+						eb[u] = lds_u32(a0 + u * 128);
+						xb[u] = __ldg(wb + (eb[u] >> 16));
+					}
+				}
+			}
+		};
+		auto dict_val = [&](uint32_t word) -> double {
+			if (SDICT) return lds_f64((word & 0x1ff8u) | sdict_s);
+			return __ldg(A.dict + ((word & 0xffffu) >> A.vshift));
+		};
+		auto arith_batch = [&](int k0, int kb, const uint32_t (&eb)[UB], const double (&xb)[UB]) {
+			const int k = k0 + kb;
+			if (k + UB <= minlen) {
+#pragma unroll
+				for (int u = 0; u < UB; ++u) {
+					const double t = mulbeta<BETAK>(dict_val(eb[u]), beta) * xb[u];
+					if ((MODE == MODE_ASSIGN || MODE == MODE_ASSIGN_SKIP_EMPTY) && u == 0) acc = (k == 0) ? t : acc + t;
+					else acc = acc + t;
+				}
+			} else {
+#pragma unroll
+				for (int u = 0; u < UB; ++u) {
+					if (k + u < len) {
+						const double t = mulbeta<BETAK>(dict_val(eb[u]), beta) * xb[u];
+						if ((MODE == MODE_ASSIGN || MODE == MODE_ASSIGN_SKIP_EMPTY) && u == 0) acc = (k == 0) ? t : acc + t;
+						else acc = acc + t;
+					}
+				}
+			}
+		};
+		int k0 = 0;
+		do {
+			const int nk = min(KC, width - k0);
+			mbar_wait(bars + stage * 8, phase);
+			const uint32_t cs = ring_s + (uint32_t)stage * C::STAGE_BYTES + (uint32_t)lane * 4u;
+			if (UG_VI_PIPE) load_batch(cs, k0, 0, nk, e[0], x[0]);
+#pragma unroll
+			for (int j = 0; j < NB; ++j) {
+				if (UG_VI_PIPE) {
+					if (j + 1 < NB) { if ((j + 1) * UB < nk) load_batch(cs, k0, (j + 1) * UB, nk, e[(j + 1) % NBUF], x[(j + 1) % NBUF]); }
+				} else {
+					if (j == 0 || j * UB < nk) load_batch(cs, k0, j * UB, nk, e[0], x[0]);
+				}
+				if ((j == 0 || j * UB < nk) && (j + 1) * UB >= nk) {
+					// the chunk's last words are in registers: every lane is done with the stage, refill it
+					__syncwarp();
+					if (prod.s < nslices) { issue(prod, stage); advance(prod); }
+				}
+				if (j * UB < nk) arith_batch(k0, j * UB, e[j % NBUF], x[j % NBUF]);
+			}
 			if (++stage == NST) { stage = 0; phase ^= 1u; }
 			k0 += KC;
 		} while (k0 < width);
