@@ -68,6 +68,21 @@ int ug4b200_launch_count(const ug4b200_ctx* ctx, int64_t* n);
  * iterations no-ops once the device-side convergence check has fired. */
 int ug4b200_set_guard(ug4b200_ctx* ctx, const int* dev_flag);
 
+/* Batched small operations.  Calls of the SpMV family, Jacobi steps, element-wise vector
+ * operations, gathers and the dense LU solve whose operand has at most `max_rows` rows are not
+ * launched one by one: they are recorded in call order and executed by ONE kernel (a single
+ * thread-block cluster, cluster barrier between operations) as soon as any other work is
+ * enqueued on the context's stream or the host synchronises — stream order is unchanged, only
+ * the 4-6 us launch + dependency latency per operation of the multigrid's coarse levels
+ * (mg_solver_impl.hpp:1685-1964 on levels of a few thousand rows) collapses into one launch.
+ * Results are bit-identical to the stand-alone kernels.  on = 0 turns recording off;
+ * max_rows < 0 keeps the current limit (default 16384, UG4B200_BATCH_MAX_ROWS).
+ * ug4b200_stream() flushes, so foreign work enqueued on the stream stays ordered. */
+int ug4b200_batch_enable(ug4b200_ctx* ctx, int on, int64_t max_rows);
+int ug4b200_batch_flush(ug4b200_ctx* ctx);
+/* operations executed inside batch kernels so far; cluster size in use (0: unavailable) */
+int ug4b200_batch_stats(const ug4b200_ctx* ctx, int64_t* batched_ops, int* cluster_size);
+
 /* CUDA-graph capture of a stream-ordered call sequence (e.g. one Krylov iteration whose
  * scalars all live on the device): begin, issue calls, end -> replay with launch. */
 typedef struct ug4b200_graph ug4b200_graph;

@@ -38,20 +38,25 @@ def orc_ref():
     return oracle.Oracle("ref")
 
 
-@pytest.fixture(scope="session", params=["value_indexed", "plain"])
+@pytest.fixture(scope="session", params=["value_indexed", "plain", "unbatched"])
 def gpu_ctx(request):
     """Kernel-level context on cuda:0 (fails, never skips, if the device is unusable).  Every
     kernel test runs twice: with the value-indexed entry stream (u16 dictionary index + u16 column
     offset, chosen automatically for matrices with repeated values) and with the plain
-    8-byte-value / 4-byte-column stream forced (UG4B200_NO_COMPRESS=1)."""
+    8-byte-value / 4-byte-column stream forced (UG4B200_NO_COMPRESS=1).  Small operands are recorded
+    and executed by the one-cluster batch kernel (csrc/batch.cu) in both; "unbatched" turns that off
+    (UG4B200_BATCH=0) so the stand-alone kernels keep their coverage on the same small cases."""
     import ctypes as C
     from ugcore_b200 import capi
     ctx = C.c_void_p()
     if request.param == "plain":
         os.environ["UG4B200_NO_COMPRESS"] = "1"
+    if request.param == "unbatched":
+        os.environ["UG4B200_BATCH"] = "0"
     try:
         capi.check(capi.dev.ug4b200_ctx_create(0, None, C.byref(ctx)))
     finally:
         os.environ.pop("UG4B200_NO_COMPRESS", None)
+        os.environ.pop("UG4B200_BATCH", None)
     yield ctx
     capi.dev.ug4b200_ctx_destroy(ctx)

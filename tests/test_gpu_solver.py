@@ -68,6 +68,36 @@ def test_execution_variants_agree(flags):
     _compare(prob, gmg_desc(3), flags=flags)
 
 
+@pytest.mark.parametrize("graph_flags", [0, 2])
+def test_batched_small_operations_are_bit_identical(graph_flags):
+    """The one-cluster batch kernel (csrc/batch.cu) executes the recorded coarse-level operations in
+    call order with the stand-alone kernels' arithmetic: histories and solutions must be equal bit
+    for bit with recording switched off, with and without CUDA-graph replay, and the batch kernel
+    must actually have run."""
+    import ctypes as C
+    import ugcore_b200 as ug
+    from ugcore_b200 import capi, problems as pr
+    from ugcore_b200.solver import host_ctx
+    prob = pr.Problem(dim=3, num_refs=4)
+    ctx = host_ctx()
+    out = {}
+    for on in (1, 0):
+        capi.check(capi.dev.ug4b200_batch_enable(ctx, on, -1), ctx)
+        n0, cl = C.c_int64(), C.c_int()
+        capi.dev.ug4b200_batch_stats(ctx, C.byref(n0), C.byref(cl))
+        s = ug.Solver.from_problem(gmg_desc(4), prob, flags=graph_flags)
+        x, ok, h = s.apply(prob.rhs())
+        n1 = C.c_int64()
+        capi.dev.ug4b200_batch_stats(ctx, C.byref(n1), C.byref(cl))
+        assert ok
+        out[on] = (np.array(x), np.array(h), n1.value - n0.value, cl.value)
+    capi.check(capi.dev.ug4b200_batch_enable(ctx, 1, -1), ctx)
+    assert out[1][3] >= 1, "no cluster launch available on this device"
+    assert out[1][2] > 0 and out[0][2] == 0, (out[1][2], out[0][2])
+    assert np.array_equal(out[1][1], out[0][1])
+    assert np.array_equal(out[1][0], out[0][0])
+
+
 @pytest.mark.parametrize("cycle,nu", [("V", (1, 1)), ("V", (3, 3)), ("W", (2, 2)), ("F", (2, 1)), ("V", (2, 0))])
 def test_cycle_types_and_smoothing_counts(cycle, nu):
     from ugcore_b200 import problems as pr

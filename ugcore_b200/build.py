@@ -16,7 +16,7 @@ CSRC = os.path.join(ROOT, "csrc")
 LIB = os.environ.get("UG4B200_LIBDIR", os.path.join(ROOT, "lib"))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-CUDA_SOURCES = ["ctx.cu", "comm.cu", "kernels/blas1.cu", "kernels/spmv.cu", "kernels/smoothers.cu"]
+CUDA_SOURCES = ["ctx.cu", "comm.cu", "batch.cu", "kernels/blas1.cu", "kernels/spmv.cu", "kernels/smoothers.cu"]
 # -fmad=false: no FMA contraction, so SpMV / Jacobi / AXPY are bit-identical to ugcore's CPU
 # algebra (reference release flags have no -march / -ffast-math, cmake/ug/debug.cmake:76-88)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",

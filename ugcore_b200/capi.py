@@ -64,6 +64,9 @@ DEV_API = {
     "ug4b200_stream": (c_vp, [c_vp]),
     "ug4b200_launch_count": (c_int, [c_vp, p_i64]),
     "ug4b200_set_guard": (c_int, [c_vp, c_vp]),
+    "ug4b200_batch_enable": (c_int, [c_vp, c_int, c_i64]),
+    "ug4b200_batch_flush": (c_int, [c_vp]),
+    "ug4b200_batch_stats": (c_int, [c_vp, p_i64, C.POINTER(c_int)]),
     "ug4b200_graph_begin": (c_int, [c_vp]),
     "ug4b200_graph_end": (c_int, [c_vp, C.POINTER(c_vp)]),
     "ug4b200_graph_launch": (c_int, [c_vp, c_vp]),

@@ -474,7 +474,7 @@ int ug4b200_comm_init(ug4b200_ctx* ctx, int nranks, int rank, const unsigned cha
 
 int ug4b200_comm_destroy(ug4b200_ctx* ctx)
 {
-	if (ctx->nccl) { cudaStreamSynchronize(ctx->stream); nccl().CommDestroy((ncclComm_t)ctx->nccl); ctx->nccl = nullptr; }
+	if (ctx->nccl) { ug_batch_flush(ctx); cudaStreamSynchronize(ctx->stream); nccl().CommDestroy((ncclComm_t)ctx->nccl); ctx->nccl = nullptr; }
 	if (!(ctx->p2p && ctx->p2p->nranks > 1)) { ctx->nranks = 1; ctx->rank = 0; }
 	return UG4B200_OK;
 }
@@ -489,6 +489,7 @@ int ug4b200_allreduce_sum(ug4b200_ctx* ctx, double* dev, int n)
 		return UG4B200_OK;
 	}
 	if (!ctx->nccl) return ug4b200_fail(ctx, UG4B200_ERR_STATE, "communicator not initialised");
+	UG_FLUSH(ctx);
 	UG_NCCL(ctx, nccl().AllReduce(dev, dev, (size_t)n, kNcclDouble, kNcclSum, (ncclComm_t)ctx->nccl, ctx->stream));
 	return UG4B200_OK;
 }
@@ -562,7 +563,7 @@ int ug4b200_interface_create(ug4b200_ctx* ctx, int nneigh, const int* neigh_rank
 int ug4b200_interface_destroy(ug4b200_ctx* ctx, ug4b200_interface* I)
 {
 	if (!I) return UG4B200_OK;
-	if (ctx) cudaStreamSynchronize(ctx->stream);
+	if (ctx) { ug_batch_flush(ctx); cudaStreamSynchronize(ctx->stream); }
 	cudaFree(I->d_idx); cudaFree(I->d_uidx); cudaFree(I->d_uptr); cudaFree(I->d_usrc); cudaFree(I->d_slave);
 	cudaFree(I->d_owned); cudaFree(I->sendbuf); cudaFree(I->recvbuf);
 	cudaFree(I->d_ent_code); cudaFree(I->d_uell); cudaFree(I->d_nb); cudaFree(I->d_epoch); cudaFree(I->d_counters);
@@ -731,6 +732,7 @@ int ug4b200_p2p_window_destroy(ug4b200_ctx* ctx)
 	ug4b200_p2p* P = ctx ? ctx->p2p : nullptr;
 	if (!P) return UG4B200_OK;
 	cudaSetDevice(ctx->device);
+	ug_batch_flush(ctx);
 	cudaStreamSynchronize(ctx->stream);
 	if (P->ipc) for (int r = 0; r < P->nranks; ++r) if (r != P->rank && P->peer[r]) cudaIpcCloseMemHandle(P->peer[r]);
 	cudaFree(P->d_peer); cudaFree(P->d_epoch); cudaFree(P->local);
@@ -886,7 +888,7 @@ int ug4b200_gather_sum(ug4b200_ctx* ctx, ug4b200_gather* G, double* global_out, 
 int ug4b200_gather_destroy(ug4b200_ctx* ctx, ug4b200_gather* G)
 {
 	if (!G) return UG4B200_OK;
-	if (ctx) cudaStreamSynchronize(ctx->stream);
+	if (ctx) { ug_batch_flush(ctx); cudaStreamSynchronize(ctx->stream); }
 	cudaFree(G->d_l2g); cudaFree(G->d_dst); cudaFree(G->d_epoch); cudaFree(G->d_counters);
 	if (G->p2p && ctx && ctx->p2p) { if (--ctx->p2p->live_ifaces == 0) ctx->p2p->bump = kP2PHeapOff; }
 	delete G;

@@ -5,6 +5,29 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <vector>
+
+// ---- batched small operations (batch.cu) ---------------------------------------------------
+// Levels of a few thousand rows are launch- and latency-bound: a sweep takes ~1 us of dependent
+// L2 round trips but costs 4-6 us as a kernel of its own.  Operations on such vectors/matrices are
+// therefore not launched but RECORDED (in call order); the record is flushed as ONE kernel — a
+// single thread-block cluster that executes the operations one after another with a cluster
+// barrier in between — as soon as anything else is enqueued on the stream (every launch, copy,
+// event, synchronisation and graph boundary flushes first, so stream order is preserved).
+// The operation records travel as kernel parameters (no staging buffer: capture-safe).
+enum { UG_OP_SPMV = 1, UG_OP_EW = 2, UG_OP_JACOBI = 3, UG_OP_LU = 4 };
+enum { UG_EW_SET = 0, UG_EW_COPY, UG_EW_ADD, UG_EW_SUB, UG_EW_SCALE, UG_EW_GATHER, UG_EW_SCALE_ADD2 };
+struct UgBatchOp {
+	int kind, sub;                 // SPMV: sub = mode | fuse << 4 ; EW: sub = UG_EW_* ; JACOBI: sub = 1 adds into sc
+	int flags, comp, vshift, pad_;
+	int64_t n;                     // rows (SPMV, JACOBI, LU) / length (EW)
+	const int64_t* slice_ptr; const int* rowlen; const int* cols; const double* vals;
+	const unsigned int* vc; const int* colbase; const double* dict;
+	double* dest; const double* v; const double* w; const double* diaginv; double* st_out; double* sc;
+	double alpha, beta;
+};
+constexpr int kBatchMaxOps = 56;
+struct UgBatchParams { int nops; int pad_; UgBatchOp op[kBatchMaxOps]; };
 
 struct ug4b200_ctx {
 	int device = 0;
@@ -21,6 +44,12 @@ struct ug4b200_ctx {
 	bool no_tma = false;          // UG4B200_NO_TMA=1: register-staged SpMV everywhere (A/B measurements)
 	bool no_comp = false;         // UG4B200_NO_COMPRESS=1: never build / use the value-indexed entry stream
 	bool pdl = false;             // UG4B200_PDL=1: programmatic dependent launch (next kernel's launch overlaps this one's tail)
+	// batched small operations: UG4B200_BATCH=0 disables, UG4B200_BATCH_MAX_ROWS sets the size limit
+	bool batch = true;
+	int64_t batch_max_rows = 16384;
+	int batch_cluster = -1;       // cluster size the device accepted (16, 8, ... ; 0: unavailable)
+	int64_t batched_ops = 0;      // operations that ran inside batch kernels (statistics)
+	std::vector<UgBatchOp> pending;
 	// reduction workspace (stream-ordered reuse)
 	double* partials = nullptr;   // [kMaxReduceBlocks]
 	unsigned int* counter = nullptr;
@@ -115,8 +144,15 @@ inline cudaError_t ug_launch_ex(ug4b200_ctx* ctx, void (*kernel)(KArgs...), dim3
 	}
 	return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
+int ug_batch_flush(ug4b200_ctx* ctx);   // batch.cu: launch the recorded small operations (no-op if none)
+inline bool ug_batchable(const ug4b200_ctx* ctx, int64_t n) { return ctx->batch && ctx->batch_cluster != 0 && n <= ctx->batch_max_rows; }
+int ug_batch_push(ug4b200_ctx* ctx, const UgBatchOp& op);
+#define UG_FLUSH(ctx)                                                                             \
+	do { if (!(ctx)->pending.empty()) { const int rcf_ = ug_batch_flush(ctx); if (rcf_) return rcf_; } } while (0)
+
 #define UG_LAUNCH(ctx, kernel, grid, block, smem, ...)                                            \
 	do {                                                                                          \
+		UG_FLUSH(ctx);                                                                            \
 		cudaError_t e_ = ug_launch_ex(ctx, kernel, dim3(grid), dim3(block), (size_t)(smem), __VA_ARGS__); \
 		(ctx)->launches++;                                                                        \
 		if (e_ == cudaSuccess) e_ = cudaGetLastError(); else cudaGetLastError();                  \

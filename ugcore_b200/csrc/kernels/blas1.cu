@@ -96,6 +96,14 @@ struct FScaleAdd3 {
 	}
 };
 
+inline int push_ew(ug4b200_ctx* ctx, int sub, int64_t n, double* dest, const double* v, const double* w, double alpha, double beta,
+                   const int* idx = nullptr)
+{
+	UgBatchOp o{};
+	o.kind = UG_OP_EW; o.sub = sub; o.n = n; o.dest = dest; o.v = v; o.w = w; o.alpha = alpha; o.beta = beta; o.cols = idx;
+	return ug_batch_push(ctx, o);
+}
+
 template <class F> int launch_ew(ug4b200_ctx* ctx, int64_t n, F f, bool aligned)
 {
 	if (n <= 0) return UG4B200_OK;
@@ -195,19 +203,20 @@ gather_scatter_kernel(int64_t nidx, int block, double* dst, const double* src, c
 extern "C" {
 
 int ug4b200_vec_set(ug4b200_ctx* ctx, int64_t n, double* x, double value)
-{ return launch_ew(ctx, n, FSet{x, value}, al16(x)); }
+{ if (n > 0 && ug_batchable(ctx, n)) return push_ew(ctx, UG_EW_SET, n, x, nullptr, nullptr, value, 0.0); return launch_ew(ctx, n, FSet{x, value}, al16(x)); }
 int ug4b200_vec_copy(ug4b200_ctx* ctx, int64_t n, double* dst, const double* src)
-{ return launch_ew(ctx, n, FCopy{dst, src}, al16(dst) && al16(src)); }
+{ if (n > 0 && ug_batchable(ctx, n)) return push_ew(ctx, UG_EW_COPY, n, dst, src, nullptr, 0.0, 0.0); return launch_ew(ctx, n, FCopy{dst, src}, al16(dst) && al16(src)); }
 int ug4b200_vec_scale(ug4b200_ctx* ctx, int64_t n, double* x, double alpha)
-{ return launch_ew(ctx, n, FScale{x, alpha}, al16(x)); }
+{ if (n > 0 && ug_batchable(ctx, n)) return push_ew(ctx, UG_EW_SCALE, n, x, nullptr, nullptr, alpha, 0.0); return launch_ew(ctx, n, FScale{x, alpha}, al16(x)); }
 int ug4b200_vec_add(ug4b200_ctx* ctx, int64_t n, double* dst, const double* src)
-{ return launch_ew(ctx, n, FAdd<1>{dst, src}, al16(dst) && al16(src)); }
+{ if (n > 0 && ug_batchable(ctx, n)) return push_ew(ctx, UG_EW_ADD, n, dst, src, nullptr, 0.0, 0.0); return launch_ew(ctx, n, FAdd<1>{dst, src}, al16(dst) && al16(src)); }
 int ug4b200_vec_sub(ug4b200_ctx* ctx, int64_t n, double* dst, const double* src)
-{ return launch_ew(ctx, n, FAdd<-1>{dst, src}, al16(dst) && al16(src)); }
+{ if (n > 0 && ug_batchable(ctx, n)) return push_ew(ctx, UG_EW_SUB, n, dst, src, nullptr, 0.0, 0.0); return launch_ew(ctx, n, FAdd<-1>{dst, src}, al16(dst) && al16(src)); }
 
 int ug4b200_vec_scale_add2_ds(ug4b200_ctx* ctx, int64_t n, double* dest, ug4b200_coef a1, const double* v1,
                               ug4b200_coef a2, const double* v2)
 {
+	if (n > 0 && !a1.dev && !a2.dev && ug_batchable(ctx, n)) return push_ew(ctx, UG_EW_SCALE_ADD2, n, dest, v1, v2, a1.host, a2.host);
 	FScaleAdd2 f{dest, a1, v1, a2, v2, 0, 0};
 	return launch_ew(ctx, n, f, al16(dest) && al16(v1) && al16(v2));
 }
@@ -286,6 +295,7 @@ int ug4b200_conv_init(ug4b200_ctx* ctx, ug4b200_conv_state* dev_state, int max_s
 int ug4b200_vec_gather(ug4b200_ctx* ctx, int64_t nidx, int block, double* dst, const double* src, const int* idx)
 {
 	if (nidx <= 0) return UG4B200_OK;
+	if (block == 1 && ug_batchable(ctx, nidx)) return push_ew(ctx, UG_EW_GATHER, nidx, dst, src, nullptr, 0.0, 0.0, idx);
 	UG_LAUNCH(ctx, gather_scatter_kernel<0>, grid_for(ctx, nidx * block, 1), kThreads, 0, nidx, block, dst, src, idx, ctx->guard);
 	return UG4B200_OK;
 }

@@ -257,6 +257,10 @@ extern "C" {
 int ug4b200_jacobi_step(ug4b200_ctx* ctx, int64_t n, int block, const double* diaginv, double* c, const double* d)
 {
 	if (n <= 0) return UG4B200_OK;
+	if (block == 1 && ug_batchable(ctx, n)) {
+		UgBatchOp o{}; o.kind = UG_OP_JACOBI; o.sub = 0; o.n = n; o.diaginv = diaginv; o.dest = c; o.w = d;
+		return ug_batch_push(ctx, o);
+	}
 	int grid = (int)((n + 255) / 256); if (grid > ctx->num_sms * 8) grid = ctx->num_sms * 8;
 	if (block == 1) { UG_LAUNCH(ctx, (jacobi_step_kernel<1, false>), grid, 256, 0, n, diaginv, c, d, nullptr, ctx->guard); }
 	else if (block == 2) { UG_LAUNCH(ctx, (jacobi_step_kernel<2, false>), grid, 256, 0, n, diaginv, c, d, nullptr, ctx->guard); }
@@ -268,6 +272,10 @@ int ug4b200_jacobi_step_add(ug4b200_ctx* ctx, int64_t n, int block, const double
                             double* sc)
 {
 	if (n <= 0) return UG4B200_OK;
+	if (block == 1 && ug_batchable(ctx, n)) {
+		UgBatchOp o{}; o.kind = UG_OP_JACOBI; o.sub = 1; o.n = n; o.diaginv = diaginv; o.dest = c; o.w = d; o.sc = sc;
+		return ug_batch_push(ctx, o);
+	}
 	int grid = (int)((n + 255) / 256); if (grid > ctx->num_sms * 8) grid = ctx->num_sms * 8;
 	if (block == 1) { UG_LAUNCH(ctx, (jacobi_step_kernel<1, true>), grid, 256, 0, n, diaginv, c, d, sc, ctx->guard); }
 	else if (block == 2) { UG_LAUNCH(ctx, (jacobi_step_kernel<2, true>), grid, 256, 0, n, diaginv, c, d, sc, ctx->guard); }
@@ -325,6 +333,10 @@ int ug4b200_lu_apply(ug4b200_ctx* ctx, int n, const double* lu_dev, const int* p
 {
 	if (n <= 0) return UG4B200_OK;
 	UG_ARG(ctx, n <= 4096, "dense LU base solver limited to 4096 unknowns");
+	if (ug_batchable(ctx, n)) {
+		UgBatchOp o{}; o.kind = UG_OP_LU; o.n = n; o.vals = lu_dev; o.cols = piv_dev; o.dest = x; o.w = b;
+		return ug_batch_push(ctx, o);
+	}
 	UG_LAUNCH(ctx, lu_apply_kernel, 1, 256, sizeof(double) * n, n, lu_dev, piv_dev, x, b, ctx->guard);
 	return UG4B200_OK;
 }

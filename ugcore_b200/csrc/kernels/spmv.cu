@@ -401,6 +401,18 @@ int launch_mode(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* dest, const d
 {
 	const int grid = spmv_grid(ctx, A->num_slices);
 	const Sell S = view(A);
+	if (FUSE != FUSE_DOT && A->block == 1 && vblock == 1 && ug_batchable(ctx, A->nrows)) {
+		// small operand: record instead of launching (batch.cu)
+		if (A->nrows == 0) return UG4B200_OK;
+		UgBatchOp o{};
+		o.kind = UG_OP_SPMV; o.sub = MODE | (FUSE << 4); o.flags = fz.flags;
+		o.comp = (A->comp && !ctx->no_comp) ? 1 : 0; o.vshift = A->vshift; o.n = A->nrows;
+		o.slice_ptr = A->slice_ptr; o.rowlen = A->rowlen; o.cols = A->cols; o.vals = A->vals;
+		o.vc = A->vc; o.colbase = A->colbase; o.dict = A->dict;
+		o.dest = dest; o.v = v; o.w = w; o.diaginv = fz.diaginv; o.st_out = fz.st_out; o.sc = fz.sc;
+		o.alpha = alpha; o.beta = beta;
+		return ug_batch_push(ctx, o);
+	}
 	if (A->block == 1 && vblock == 1) {
 		if (A->comp && !ctx->no_comp) return launch_scalar<BETAK, MODE, FUSE, true>(ctx, A, dest, v, alpha, beta, w, fz);
 		return launch_scalar<BETAK, MODE, FUSE, false>(ctx, A, dest, v, alpha, beta, w, fz);
@@ -626,7 +638,7 @@ int ug4b200_matrix_upload_crs(ug4b200_ctx* ctx, int block, int64_t nrows, int64_
 int ug4b200_matrix_destroy(ug4b200_ctx* ctx, ug4b200_matrix* A)
 {
 	if (!A) return UG4B200_OK;
-	if (ctx) cudaStreamSynchronize(ctx->stream);
+	if (ctx) { ug_batch_flush(ctx); cudaStreamSynchronize(ctx->stream); }
 	cudaFree(A->slice_ptr); cudaFree(A->rowlen); cudaFree(A->diagpos); cudaFree(A->cols); cudaFree(A->vals);
 	cudaFree(A->vc); cudaFree(A->colbase); cudaFree(A->dict);
 	delete A;

@@ -213,6 +213,7 @@ struct SolverImpl : SolverBase {
 		x.set_storage_type(PST_CONSISTENT); b.set_storage_type(PST_ADDITIVE);
 		const bool ok = inv->apply(x, b);
 		UG_GPU_CHECK(ug4b200_vec_copy(c, x.len(), xd, x.dev()));
+		UG_GPU_CHECK(ug4b200_batch_flush(c));   // the caller owns xd and the stream from here on
 		return finish(ok);
 	}
 	void precond_apply(double* ch, const double* dh) override
