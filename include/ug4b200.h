@@ -333,6 +333,16 @@ int ug4b200_additive_to_consistent(ug4b200_ctx* ctx, ug4b200_interface* I, doubl
  * copies (same ascending-rank order), every other copy becomes 0 — one kernel with the
  * peer-window transport */
 int ug4b200_additive_to_unique(ug4b200_ctx* ctx, ug4b200_interface* I, double* v, int block);
+/* Fused interface push (peer-window transport, scalar vectors): announce that the NEXT smoothing
+ * kernel whose output vector is `vec` (ug4b200_jacobi_smooth_fused* / ug4b200_restrict_jacobi_fused)
+ * is followed by ug4b200_additive_to_consistent(I, vec).  That kernel then stores the interface rows
+ * of its result straight into the neighbours' peer windows while it streams the matrix and its last
+ * CTA raises the flags, so the exchange itself only waits for the neighbours and adds the copies
+ * (same ascending-rank sum, bit-identical).  If the producing call cannot push (recorded small
+ * operation, block vectors, NCCL transport) the arm is dropped and the exchange runs in full.
+ * Opt-in (environment UG4B200_FUSED_PUSH=1): at N = 2 it measured slower than the one-kernel
+ * exchange; without it this call is a no-op. */
+int ug4b200_interface_arm(ug4b200_ctx* ctx, ug4b200_interface* I, const double* vec);
 /* Peer-window transport (preferred inside one NVSwitch box; replaces the MPI_Isend/Irecv
  * transport of pcl_interface_communicator_impl.hpp:560-661 and MPI_Allreduce,
  * pcl_process_communicator.cpp:325): every rank exposes a window of device memory to the

@@ -20,12 +20,14 @@ def _ngpu():
 
 # p2p = 1: peer-window transport (direct NVLink stores + flags), 0: NCCL send/recv + all-reduce
 # gather: levels 0..gather are held by every rank and cycled redundantly (-1: default rule = 2 here)
+# p2p = 2: peer windows + interface rows pushed by the smoothing kernels themselves (UG4B200_FUSED_PUSH=1)
 @pytest.mark.parametrize("world,flags,p2p,gather", [(2, 0, 1, -1), (2, 2, 1, 0), (2, 0, 0, 1), (2, 0, 1, 0), (2, 0, 0, 0),
-                                                    (4, 0, 1, -1), (8, 0, 1, -1), (8, 0, 1, 0), (8, 0, 0, 1)])
+                                                    (2, 0, 2, 0), (2, 2, 2, -1),
+                                                    (4, 0, 1, -1), (8, 0, 1, -1), (8, 0, 1, 0), (8, 0, 0, 1), (8, 0, 2, 0)])
 def test_partitioned_gmg_cg_matches_serial_oracle(world, flags, p2p, gather):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
-    env = dict(os.environ, UG4B200_P2P=str(p2p))
+    env = dict(os.environ, UG4B200_P2P=str(min(p2p, 1)), UG4B200_FUSED_PUSH="1" if p2p == 2 else "0")
     env.pop("UG4B200_GATHER_LEVEL", None)
     if gather >= 0:
         env["UG4B200_GATHER_LEVEL"] = str(gather)

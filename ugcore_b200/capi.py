@@ -134,6 +134,7 @@ DEV_API = {
     "ug4b200_interface_destroy": (c_int, [c_vp, c_vp]),
     "ug4b200_additive_to_consistent": (c_int, [c_vp, c_vp, c_vp, c_int]),
     "ug4b200_additive_to_unique": (c_int, [c_vp, c_vp, c_vp, c_int]),
+    "ug4b200_interface_arm": (c_int, [c_vp, c_vp, c_vp]),
     "ug4b200_matrix_apply_dot_allreduce_ds": (c_int, [c_vp, c_vp, c_vp, c_vp, Fin, c_vp]),
     "ug4b200_set_slaves_zero": (c_int, [c_vp, c_vp, c_vp, c_int]),
     "ug4b200_vec_dot_unique_ds": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp]),

@@ -127,12 +127,7 @@ dot_unique_kernel(int64_t nblocks, int block, const unsigned char* __restrict__ 
 
 
 // ---- peer-window exchange ------------------------------------------------------------
-struct P2PNb {
-	double* rbase;               // neighbour's receive region (in ITS window)
-	int64_t rpar_stride;         // doubles between its two parity buffers
-	int64_t rptr;                // my first entry inside its region
-	unsigned long long* rflag;   // flag in its window that I raise
-};
+typedef UgPushNb P2PNb;   // common.cuh: shared with the producing kernels that push interface rows themselves
 struct P2PIfaceDev {
 	int nneigh; int ell_w; int64_t total, nu;
 	const int* idx;                    // [total] local index of send entry
@@ -176,7 +171,7 @@ __device__ __forceinline__ void p2p_unpack(const P2PIfaceDev& d, const double* r
 // co-resident: CTAs that wait for a neighbour must not keep CTAs that still have to send off
 // the SMs.  Small interfaces (the usual case) run as ONE CTA: no inter-CTA hand-shake at all.
 __global__ void __launch_bounds__(1024)
-p2p_exchange_sum_kernel(P2PIfaceDev d, double* v, int block, int unique, const int* guard)
+p2p_exchange_sum_kernel(P2PIfaceDev d, double* v, int block, int unique, int pushed, const int* guard)
 {
 	if (ug_guarded(guard)) return;
 	__shared__ bool s_last;
@@ -187,6 +182,9 @@ p2p_exchange_sum_kernel(P2PIfaceDev d, double* v, int block, int unique, const i
 	const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
 	__syncthreads();
+	// pushed: the kernel that produced v already stored the interface rows into the neighbours' windows
+	// and raised the flags (ug_push_row / ug_push_finish) — only steps 3-5 are left
+	if (!pushed) {
 	// 1. push my interface values into the neighbours' windows
 	for (int64_t t = tid; t < d.total * block; t += stride) {
 		const int64_t en = t / block; const int q = (int)(t - en * block);
@@ -211,6 +209,7 @@ p2p_exchange_sum_kernel(P2PIfaceDev d, double* v, int block, int unique, const i
 	__syncthreads();
 	// 2. everything of this rank is on its way: raise my flag at every neighbour
 	if (s_last && threadIdx.x < d.nneigh) ug_st_release_sys(s_nb[threadIdx.x].rflag, e);
+	}
 	// 3. wait for the neighbours
 	if (threadIdx.x < d.nneigh) ug_wait_flag(d.lflag + threadIdx.x, e, d.err);
 	__syncthreads();
@@ -367,6 +366,10 @@ struct ug4b200_interface {
 	size_t recv_off = 0;
 	int* d_ent_code = nullptr; int* d_uell = nullptr; int ell_w = 2; P2PNb* d_nb = nullptr;
 	unsigned long long* d_epoch = nullptr; unsigned int* d_counters = nullptr;
+	// fused push (block size 1): row bitmap + prefix, sends grouped by interface row, device descriptor
+	unsigned int* d_rowmask = nullptr; int* d_rowprefix = nullptr; int* d_sptr = nullptr; int* d_scode = nullptr; int* d_scode1 = nullptr;
+	unsigned int* d_push_arrive = nullptr; UgPushDev* d_push = nullptr;
+	const double* pushed_vec = nullptr;   // vector whose interface rows a producing kernel has pushed for the next exchange
 };
 
 
@@ -444,6 +447,13 @@ struct ug4b200_gather {
 	GatherDst* d_dst = nullptr;
 	unsigned long long* d_epoch = nullptr; unsigned int* d_counters = nullptr;
 };
+
+const UgPushDev* ug_iface_push_begin(ug4b200_ctx* ctx, ug4b200_interface* I, const double* vec)
+{
+	if (!I || !I->p2p || !I->committed || !I->d_push ) return nullptr;
+	I->pushed_vec = vec;
+	return I->d_push;
+}
 
 extern "C" {
 
@@ -550,6 +560,32 @@ int ug4b200_interface_create(ug4b200_ctx* ctx, int nneigh, const int* neigh_rank
 	if (!rc) rc = up((void**)&I->d_slave, slave.data(), sizeof(int) * slave.size());
 	if (!rc) rc = up((void**)&I->d_owned, owned.data(), owned.size());
 	if (!rc && ctx->p2p && ctx->p2p->nranks > 1 && I->total > 0) rc = p2p_interface_setup(ctx, I, up, uptr, usrc);
+	if (!rc && I->p2p) {
+		// fused push: which rows are interface rows (bitmap + running count per 32-row slice) and, per
+		// interface row (ascending local index = order of uidx), where its value goes
+		const int64_t ns = (nlocal + 31) / 32;
+		std::vector<unsigned int> mask(ns > 0 ? ns : 1, 0u); std::vector<int> prefix(ns > 0 ? ns : 1, 0);
+		for (int li : uidx) mask[li >> 5] |= 1u << (li & 31);
+		for (int64_t sidx = 1; sidx < ns; ++sidx) prefix[sidx] = prefix[sidx - 1] + __builtin_popcount(mask[sidx - 1]);
+		std::vector<int> upos(nlocal > 0 ? nlocal : 1, -1);
+		for (size_t u = 0; u < uidx.size(); ++u) upos[uidx[u]] = (int)u;
+		std::vector<int> sptr(uidx.size() + 1, 0), scode(I->total > 0 ? I->total : 1, 0);
+		for (int64_t e = 0; e < I->total; ++e) sptr[upos[indices[e]] + 1]++;
+		for (size_t u = 0; u < uidx.size(); ++u) sptr[u + 1] += sptr[u];
+		std::vector<int> fill(sptr.begin(), sptr.end() - 1);
+		for (int p = 0; p < nneigh; ++p)
+			for (int64_t e = neigh_ptr[p]; e < neigh_ptr[p + 1]; ++e) scode[fill[upos[indices[e]]]++] = (int)(((e - neigh_ptr[p]) << 5) | p);
+		if (!rc) rc = up((void**)&I->d_rowmask, mask.data(), sizeof(unsigned int) * mask.size());
+		if (!rc) rc = up((void**)&I->d_rowprefix, prefix.data(), sizeof(int) * prefix.size());
+		if (!rc) rc = up((void**)&I->d_sptr, sptr.data(), sizeof(int) * sptr.size());
+		if (!rc) rc = up((void**)&I->d_scode, scode.data(), sizeof(int) * scode.size());
+		std::vector<int> scode1(uidx.size() > 0 ? uidx.size() : 1, -1);
+		for (size_t u = 0; u < uidx.size(); ++u) if (sptr[u + 1] - sptr[u] == 1) scode1[u] = scode[sptr[u]];
+		if (!rc) rc = up((void**)&I->d_scode1, scode1.data(), sizeof(int) * scode1.size());
+		if (!rc) rc = up((void**)&I->d_push_arrive, nullptr, 8);
+		if (!rc) rc = up((void**)&I->d_push, nullptr, sizeof(UgPushDev));
+		if (!rc && cudaMemsetAsync(I->d_push_arrive, 0, 8, ctx->stream) != cudaSuccess) rc = ug4b200_fail(ctx, UG4B200_ERR_CUDA, "interface: memset failed");
+	}
 	if (!rc && !I->p2p) {
 		rc = up((void**)&I->sendbuf, nullptr, sizeof(double) * 9 * I->total);
 		if (!rc) rc = up((void**)&I->recvbuf, nullptr, sizeof(double) * 9 * I->total);
@@ -567,6 +603,8 @@ int ug4b200_interface_destroy(ug4b200_ctx* ctx, ug4b200_interface* I)
 	cudaFree(I->d_idx); cudaFree(I->d_uidx); cudaFree(I->d_uptr); cudaFree(I->d_usrc); cudaFree(I->d_slave);
 	cudaFree(I->d_owned); cudaFree(I->sendbuf); cudaFree(I->recvbuf);
 	cudaFree(I->d_ent_code); cudaFree(I->d_uell); cudaFree(I->d_nb); cudaFree(I->d_epoch); cudaFree(I->d_counters);
+	cudaFree(I->d_rowmask); cudaFree(I->d_rowprefix); cudaFree(I->d_sptr); cudaFree(I->d_scode); cudaFree(I->d_scode1); cudaFree(I->d_push_arrive); cudaFree(I->d_push);
+	if (ctx && ctx->armed_iface == I) { ctx->armed_iface = nullptr; ctx->armed_vec = nullptr; }
 	if (I->p2p && ctx && ctx->p2p) {
 		// window space is recycled once no interface is alive (ids keep counting: all ranks create and
 		// destroy interfaces in the same order)
@@ -603,6 +641,12 @@ int ug4b200_interface_commit(ug4b200_ctx* ctx, ug4b200_interface* I)
 		nb[p].rflag = reinterpret_cast<unsigned long long*>(P->peer[r] + ent.flag_off);
 	}
 	UG_CUDA(ctx, cudaMemcpyAsync(I->d_nb, nb.data(), sizeof(P2PNb) * nb.size(), cudaMemcpyHostToDevice, P->aux));
+	if (I->d_push) {
+		UgPushDev pd{};
+		pd.nneigh = I->nneigh; pd.rowmask = I->d_rowmask; pd.rowprefix = I->d_rowprefix; pd.sptr = I->d_sptr; pd.scode = I->d_scode; pd.scode1 = I->d_scode1;
+		pd.nb = I->d_nb; pd.epoch = I->d_epoch; pd.arrive = I->d_push_arrive;
+		UG_CUDA(ctx, cudaMemcpyAsync(I->d_push, &pd, sizeof(pd), cudaMemcpyHostToDevice, P->aux));
+	}
 	UG_CUDA(ctx, cudaStreamSynchronize(P->aux));
 	I->committed = true;
 	return UG4B200_OK;
@@ -611,6 +655,7 @@ int ug4b200_interface_commit(ug4b200_ctx* ctx, ug4b200_interface* I)
 static int exchange_sum(ug4b200_ctx* ctx, ug4b200_interface* I, double* v, int block, int unique)
 {
 	UG_ARG(ctx, I && v && block >= 1 && block <= 9, "bad argument");
+	ctx->armed_iface = nullptr; ctx->armed_vec = nullptr;   // an arm that no producer consumed is void
 	if (I->total == 0) return UG4B200_OK;
 	if (I->p2p) {
 		if (!I->committed) { const int rc = ug4b200_interface_commit(ctx, I); if (rc) return rc; }
@@ -627,11 +672,18 @@ static int exchange_sum(ug4b200_ctx* ctx, ug4b200_interface* I, double* v, int b
 		// One CTA for small interfaces (no inter-CTA hand-shake); large ones need many SMs because one
 		// SM sustains only a few GB/s of remote stores (measured: 16641 values from one CTA 42 us, from
 		// 17 CTAs 18 us).  Never more CTAs than SMs (co-residency, see kernel).
+		if (I->pushed_vec && (I->pushed_vec != v || block != 1 || unique)) {
+			I->pushed_vec = nullptr;
+			return ug4b200_fail(ctx, UG4B200_ERR_STATE, "interface: a vector whose interface rows were pushed by its producing kernel must be made consistent next");
+		}
+		const int pushed = I->pushed_vec == v ? 1 : 0;
+		I->pushed_vec = nullptr;
 		const int64_t work = I->total * block;
-		int64_t g = work <= 2048 ? 1 : (work + 511) / 512;
+		static const int cta_work = getenv("UG4B200_P2P_CTA_WORK") ? atoi(getenv("UG4B200_P2P_CTA_WORK")) : 128;
+		int64_t g = work <= 2048 ? 1 : (work + cta_work - 1) / cta_work;
 		if (g > ctx->num_sms) g = ctx->num_sms;
 		const int threads = g > 1 ? 256 : (work >= 1024 ? 1024 : (int)std::max<int64_t>(64, (work + 31) / 32 * 32));
-		UG_LAUNCH(ctx, p2p_exchange_sum_kernel, (int)g, threads, 0, d, v, block, unique, ctx->guard);
+		UG_LAUNCH(ctx, p2p_exchange_sum_kernel, (int)g, threads, 0, d, v, block, unique, pushed, ctx->guard);
 		return UG4B200_OK;
 	}
 	if (!ctx->nccl) return ug4b200_fail(ctx, UG4B200_ERR_STATE, "communicator not initialised");
@@ -654,6 +706,19 @@ static int exchange_sum(ug4b200_ctx* ctx, ug4b200_interface* I, double* v, int b
 
 int ug4b200_additive_to_consistent(ug4b200_ctx* ctx, ug4b200_interface* I, double* v, int block)
 { return exchange_sum(ctx, I, v, block, 0); }
+int ug4b200_interface_arm(ug4b200_ctx* ctx, ug4b200_interface* I, const double* vec)
+{
+	ctx->armed_iface = nullptr; ctx->armed_vec = nullptr;
+	// opt-in (UG4B200_FUSED_PUSH=1): measured at N = 2, 129^3 per GPU the fused push is SLOWER than the one-kernel
+	// exchange (8.15 vs 7.76 ms per solve): the system-scope fence at the end of all 444 CTAs and the
+	// look-ups in the epilogue of every fourth slice cost more than the push phase they take out of
+	// the exchange kernel
+	static const bool on = getenv("UG4B200_FUSED_PUSH") && getenv("UG4B200_FUSED_PUSH")[0] == '1';
+	if (!on || !I || !vec || !I->p2p || !I->d_push || I->total == 0) return UG4B200_OK;
+	if (!I->committed) { const int rc = ug4b200_interface_commit(ctx, I); if (rc) return rc; }
+	ctx->armed_iface = I; ctx->armed_vec = vec;
+	return UG4B200_OK;
+}
 int ug4b200_additive_to_unique(ug4b200_ctx* ctx, ug4b200_interface* I, double* v, int block)
 { return exchange_sum(ctx, I, v, block, 1); }
 

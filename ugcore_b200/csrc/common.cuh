@@ -50,6 +50,10 @@ struct ug4b200_ctx {
 	int batch_cluster = -1;       // cluster size the device accepted (16, 8, ... ; 0: unavailable)
 	int64_t batched_ops = 0;      // operations that ran inside batch kernels (statistics)
 	std::vector<UgBatchOp> pending;
+	// fused interface push (comm.cu): the next kernel that produces `armed_vec` as its smoother output
+	// also stores the interface rows into the neighbours' peer windows
+	struct ug4b200_interface* armed_iface = nullptr;
+	const double* armed_vec = nullptr;
 	// reduction workspace (stream-ordered reuse)
 	double* partials = nullptr;   // [kMaxReduceBlocks]
 	unsigned int* counter = nullptr;
@@ -254,6 +258,61 @@ __device__ inline bool ug_wait_flag(const unsigned long long* flag, unsigned lon
 	}
 	return true;
 }
+// ---- interface push fused into a producing kernel (comm.cu holds the host side) ------------
+// The kernel that computes an additive vector whose interface rows must become consistent
+// (AdditiveToConsistent, parallelization_util.h:159-191) stores those rows straight into the
+// neighbours' peer windows while it streams the matrix; its last CTA raises the epoch flags.  The
+// exchange that follows is then only "wait for the neighbours' flags and add the copies".
+struct UgPushNb {
+	double* rbase;               // neighbour's receive region (in ITS window)
+	int64_t rpar_stride;         // doubles between its two parity buffers
+	int64_t rptr;                // my first entry inside its region
+	unsigned long long* rflag;   // flag in its window that I raise
+};
+struct UgPushDev {
+	int nneigh, pad_;
+	const unsigned int* rowmask;   // [ceil(nlocal/32)] bit l: row 32 s + l is an interface row
+	const int* rowprefix;          // [ceil(nlocal/32)] interface rows before slice s
+	const int* sptr;               // [nu + 1] sends of interface row u ...
+	const int* scode;              // ... (position inside the neighbour's list << 5) | neighbour slot
+	const int* scode1;             // [nu] the code of rows with exactly one send (faces), -1 otherwise: one look-up instead of three
+	const UgPushNb* nb;
+	unsigned long long* epoch; unsigned int* arrive;
+};
+__device__ __forceinline__ void ug_push_row(const UgPushDev* P, unsigned long long e, int64_t slice, int lane, unsigned int mask, double val)
+{
+	const int u = P->rowprefix[slice] + __popc(mask & ((1u << lane) - 1u));
+	const int64_t par = (int64_t)(e & 1ull);
+	const int c1 = P->scode1[u];
+	if (c1 >= 0) {
+		const UgPushNb nb = P->nb[c1 & 31];
+		ug_st_relaxed_sys(nb.rbase + par * nb.rpar_stride + nb.rptr + (c1 >> 5), val);
+		return;
+	}
+	for (int p = P->sptr[u]; p < P->sptr[u + 1]; ++p) {
+		const int code = P->scode[p];
+		const UgPushNb nb = P->nb[code & 31];
+		ug_st_relaxed_sys(nb.rbase + par * nb.rpar_stride + nb.rptr + (code >> 5), val);
+	}
+}
+// called by ALL threads of every CTA at the end of the producing kernel: the last CTA to arrive
+// raises this rank's flag at every neighbour (the CTA barrier + the fences order all pushes before it)
+__device__ inline void ug_push_finish(const UgPushDev* P, unsigned long long e)
+{
+	__shared__ bool s_push_last;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence_system();
+		s_push_last = (atomicAdd(P->arrive, 1u) == gridDim.x - 1);
+		if (s_push_last) { *P->arrive = 0u; __threadfence_system(); }
+	}
+	__syncthreads();
+	if (s_push_last && threadIdx.x < P->nneigh) ug_st_release_sys(P->nb[threadIdx.x].rflag, e);
+}
+// comm.cu: if `I` can take a fused push for `vec` return its device descriptor and remember that the
+// next AdditiveToConsistent of `vec` only has to wait and add; nullptr otherwise
+const UgPushDev* ug_iface_push_begin(ug4b200_ctx* ctx, struct ug4b200_interface* I, const double* vec);
+
 // Sum of one double over all ranks, executed by warp 0 of ONE block per rank: every rank stores its
 // value into slot [parity][rank] of every window, raises its flag there (release), waits for the
 // flags of all ranks in its own window (acquire) and adds the slots in ascending rank order, so the

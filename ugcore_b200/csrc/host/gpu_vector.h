@@ -194,6 +194,14 @@ class GPUVector {
 		return true;
 	}
 
+	/// The smoothing kernel that is about to produce this (additive) vector may store its interface
+	/// rows into the neighbours' peer windows itself; the change_storage_type(PST_CONSISTENT) that
+	/// follows then only waits for the neighbours and adds the copies (ug4b200_interface_arm).
+	void arm_consistent_push()
+	{
+		if (m_layouts) UG_GPU_CHECK(ug4b200_interface_arm(GPUManager::ctx(), m_layouts->iface(), dev()));
+	}
+
 	void swap(this_type& o)
 	{
 		std::swap(m_size, o.m_size); std::swap(m_dev, o.m_dev); std::swap(m_host, o.m_host);

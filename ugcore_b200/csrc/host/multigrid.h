@@ -336,6 +336,7 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 			for (int nu = 0; nu < m_numPreSmooth; ++nu) {
 				const bool last = (nu == m_numPreSmooth - 1);
 				const int flags = UG4B200_SMOOTH_ADD_IN | (last ? 0 : UG4B200_SMOOTH_JACOBI) | (lf.scZero ? UG4B200_SMOOTH_SC_ZERO : 0);
+				if (!last) alt->arm_consistent_push();   // the kernel stores the interface rows of its output at the neighbours
 				UG_GPU_CHECK(ug4b200_jacobi_smooth_fused_src(ctx, lf.A->device(), jac->diag_inv_dev(), lf.sd.dev(),
 				                                             dsrc ? dsrc->dev() : nullptr, cur->dev(), last ? nullptr : alt->dev(),
 				                                             SC(lev).dev(), flags));
@@ -359,6 +360,7 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 		// st = D sd is computed by the same kernel
 		Jacobi<TAlgebra>* jc = (lev - 1 > m_baseLev && m_numPreSmooth > 0 && B == 1) ? fused_jacobi(lc.PreSmoother) : nullptr;
 		if (jc) {
+			lc.st.arm_consistent_push();
 			UG_GPU_CHECK(ug4b200_restrict_jacobi_fused(ctx, lf.transfer->restriction()->device(), jc->diag_inv_dev(), lc.sd.dev(),
 			                                           lf.transfer->restriction_damping(), lf.sd.dev(), lc.st.dev()));
 			lc.sd.set_storage_type(lf.sd.get_storage_mask());
@@ -387,6 +389,7 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 				const bool last = (nu == m_numPostSmooth - 1);
 				const int flags = UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_JACOBI | (lf.scZero ? UG4B200_SMOOTH_SC_ZERO : 0) |
 				                  ((last && addOut) ? UG4B200_SMOOTH_ADD_OUT : 0);
+				alt->arm_consistent_push();
 				UG_GPU_CHECK(ug4b200_jacobi_smooth_fused(ctx, lf.A->device(), jac->diag_inv_dev(), lf.sd.dev(), cur->dev(), alt->dev(),
 				                                         SC(lev).dev(), flags));
 				lf.scZero = false;

@@ -41,6 +41,9 @@ struct Fuse {
 	double* partials; unsigned int* counter; ug4b200_fin fin; UgAr ar;
 	// FUSE_JACOBI
 	const double* diaginv; double* st_out; double* sc; int flags;
+	// FUSE_JACOBI / FUSE_RESTRICT_JACOBI in partitioned runs: interface rows of st_out are also stored
+	// into the neighbours' peer windows (common.cuh: ug_push_row / ug_push_finish); nullptr otherwise
+	const UgPushDev* push;
 };
 
 template <int BETAK> __device__ __forceinline__ double mulbeta(double a, double beta)
@@ -72,11 +75,14 @@ spmv1_kernel(Sell A, double* dest, const double* v, double alpha, double beta, c
 	const int64_t gwarp = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
 	const int64_t nwarps = (int64_t)gridDim.x * kWarps;
 	double dot = 0.0;
+	const UgPushDev* push = (FUSE == FUSE_JACOBI || FUSE == FUSE_RESTRICT_JACOBI) ? fz.push : nullptr;
+	const unsigned long long pe = push ? *(volatile unsigned long long*)push->epoch + 1ull : 0ull;
 	for (int64_t s = gwarp; s < A.num_slices; s += nwarps) {
 		const int64_t row = s * 32 + lane;
 		const int64_t base = A.slice_ptr[s];
 		const int width = (int)((A.slice_ptr[s + 1] - base) >> 5);
 		const int len = A.rowlen[row];
+		const unsigned int pmask = push ? push->rowmask[s] : 0u;
 		const double* vp = A.vals + base + lane;
 		const int* cp = A.cols + base + lane;
 		const unsigned int* vcp = A.vc + base + lane;
@@ -138,6 +144,7 @@ spmv1_kernel(Sell A, double* dest, const double* v, double alpha, double beta, c
 				if (fz.flags & UG4B200_SMOOTH_JACOBI) {
 					const double st = dinv * acc;   // MatMult(c[i], 1.0, diagInv[i], d[i])
 					fz.st_out[row] = st;
+					if ((pmask >> lane) & 1u) ug_push_row(push, pe, s, lane, pmask, st);
 					if (fz.flags & UG4B200_SMOOTH_ADD_OUT) scv = scv + st;
 				}
 				if (fz.flags & (UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_ADD_OUT)) fz.sc[row] = scv;
@@ -148,7 +155,9 @@ spmv1_kernel(Sell A, double* dest, const double* v, double alpha, double beta, c
 			if (live) {
 				double dv = own;
 				if (len > 0) { dest[row] = acc; dv = acc; }
-				fz.st_out[row] = dinv * dv;
+				const double st = dinv * dv;
+				fz.st_out[row] = st;
+				if ((pmask >> lane) & 1u) ug_push_row(push, pe, s, lane, pmask, st);
 			}
 		} else {
 			if (live && (MODE != MODE_ASSIGN_SKIP_EMPTY || len > 0)) dest[row] = acc;
@@ -156,6 +165,7 @@ spmv1_kernel(Sell A, double* dest, const double* v, double alpha, double beta, c
 		}
 	}
 	if (FUSE == FUSE_DOT) ug_block_reduce_fin(dot, fz.partials, fz.counter, fz.fin, fz.ar);
+	if (push) ug_push_finish(push, pe);
 }
 
 // ---------------------------------------------------------------- block B x B
@@ -401,6 +411,13 @@ int launch_mode(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* dest, const d
 {
 	const int grid = spmv_grid(ctx, A->num_slices);
 	const Sell S = view(A);
+	// fused interface push: only the stand-alone scalar smoothing kernels take it; any other path drops the arm
+	ug4b200_interface* armed = ctx->armed_iface; const double* armed_vec = ctx->armed_vec;
+	ctx->armed_iface = nullptr; ctx->armed_vec = nullptr;
+	Fuse fzp = fz;
+	if ((FUSE == FUSE_JACOBI || FUSE == FUSE_RESTRICT_JACOBI) && armed && armed_vec == fz.st_out && A->block == 1 && vblock == 1 &&
+	    !ug_batchable(ctx, A->nrows) && (FUSE != FUSE_JACOBI || (fz.flags & UG4B200_SMOOTH_JACOBI)))
+		fzp.push = ug_iface_push_begin(ctx, armed, armed_vec);
 	if (FUSE != FUSE_DOT && A->block == 1 && vblock == 1 && ug_batchable(ctx, A->nrows)) {
 		// small operand: record instead of launching (batch.cu)
 		if (A->nrows == 0) return UG4B200_OK;
@@ -414,8 +431,8 @@ int launch_mode(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* dest, const d
 		return ug_batch_push(ctx, o);
 	}
 	if (A->block == 1 && vblock == 1) {
-		if (A->comp && !ctx->no_comp) return launch_scalar<BETAK, MODE, FUSE, true>(ctx, A, dest, v, alpha, beta, w, fz);
-		return launch_scalar<BETAK, MODE, FUSE, false>(ctx, A, dest, v, alpha, beta, w, fz);
+		if (A->comp && !ctx->no_comp) return launch_scalar<BETAK, MODE, FUSE, true>(ctx, A, dest, v, alpha, beta, w, fzp);
+		return launch_scalar<BETAK, MODE, FUSE, false>(ctx, A, dest, v, alpha, beta, w, fzp);
 	} else if (A->block == 1) {
 		if (FUSE != FUSE_NONE) return ug4b200_fail(ctx, UG4B200_ERR_ARG, "fused SpMV needs matrix block == vector block");
 		if (vblock == 2) { UG_LAUNCH(ctx, (spmv1xV_kernel<2, BETAK, MODE>), grid, kThreads, 0, S, dest, v, alpha, beta, w, ctx->guard); }

@@ -167,12 +167,15 @@ spmv1_tma_kernel(Sell A, double* dest, const double* v, double alpha, double bet
 	Meta cur = fetch_meta(gwarp);
 	int stage = 0; uint32_t phase = 0;
 	double dot = 0.0;
+	const UgPushDev* push = FUSE == FUSE_JACOBI ? fz.push : nullptr;
+	const unsigned long long pe = push ? *(volatile unsigned long long*)push->epoch + 1ull : 0ull;
 	while (cur.s < A.num_slices) {
 		const Meta nxt = fetch_meta(cur.s + nwarps);
 		const int64_t row = cur.s * 32 + lane;
 		const bool live = row < A.nrows;
 		const int len = cur.len;
 		const int width = cur.width;
+		const unsigned int pmask = push ? push->rowmask[cur.s] : 0u;
 		// per-row streams first: their latency overlaps the whole slice
 		double acc = 0.0, own = 0.0, scv = 0.0, dinv = 0.0;
 		if (MODE == MODE_INPLACE) acc = cur.acc0;
@@ -221,6 +224,7 @@ spmv1_tma_kernel(Sell A, double* dest, const double* v, double alpha, double bet
 				if (fz.flags & UG4B200_SMOOTH_JACOBI) {
 					const double st = dinv * acc;
 					fz.st_out[row] = st;
+					if ((pmask >> lane) & 1u) ug_push_row(push, pe, cur.s, lane, pmask, st);
 					if (fz.flags & UG4B200_SMOOTH_ADD_OUT) scv = scv + st;
 				}
 				if (fz.flags & (UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_ADD_OUT)) fz.sc[row] = scv;
@@ -232,6 +236,7 @@ spmv1_tma_kernel(Sell A, double* dest, const double* v, double alpha, double bet
 		cur = nxt;
 	}
 	if (FUSE == FUSE_DOT) ug_block_reduce_fin(dot, fz.partials, fz.counter, fz.fin, fz.ar);
+	if (push) ug_push_finish(push, pe);
 }
 
 // ---------------------------------------------------------------- value-indexed stream
@@ -360,12 +365,15 @@ spmv1_vi_kernel(Sell A, double* dest, const double* v, double alpha, double beta
 	Meta cur = fetch_meta(gwarp);
 	int stage = 0; uint32_t phase = 0;
 	double dot = 0.0;
+	const UgPushDev* push = FUSE == FUSE_JACOBI ? fz.push : nullptr;
+	const unsigned long long pe = push ? *(volatile unsigned long long*)push->epoch + 1ull : 0ull;
 	while (cur.s < nslices) {
 		const Meta nxt = fetch_meta(cur.s + nwarps);
 		const int row = cur.s * 32 + lane;
 		const bool live = row < nrows;
 		const int len = cur.len;
 		const int width = cur.width;
+		const unsigned int pmask = push ? push->rowmask[cur.s] : 0u;
 		// all lanes own the first minlen entry columns of the slice: those batches run unpredicated
 		const int minlen = __reduce_min_sync(0xffffffffu, len);
 		const double* wb = w + cur.cbase;
@@ -456,6 +464,7 @@ spmv1_vi_kernel(Sell A, double* dest, const double* v, double alpha, double beta
 				if (fz.flags & UG4B200_SMOOTH_JACOBI) {
 					const double st = dinv * acc;
 					fz.st_out[row] = st;
+					if ((pmask >> lane) & 1u) ug_push_row(push, pe, cur.s, lane, pmask, st);
 					if (fz.flags & UG4B200_SMOOTH_ADD_OUT) scv = scv + st;
 				}
 				if (fz.flags & (UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_ADD_OUT)) fz.sc[row] = scv;
@@ -467,6 +476,7 @@ spmv1_vi_kernel(Sell A, double* dest, const double* v, double alpha, double beta
 		cur = nxt;
 	}
 	if (FUSE == FUSE_DOT) ug_block_reduce_fin(dot, fz.partials, fz.counter, fz.fin, fz.ar);
+	if (push) ug_push_finish(push, pe);
 }
 
 } // namespace tma
