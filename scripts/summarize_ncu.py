@@ -47,3 +47,20 @@ if os.path.exists(rep):
             for w in want:
                 if w in idx: f.write(f"{w} = {short(r[idx[w]]) if w == 'Kernel Name' else r[idx[w]]} {units[idx[w]]}\n")
     print("wrote", f"{out}/{tag}_spmv_full.txt")
+    # per-launch DRAM traffic of the dominant kernels for bench.py's roofline.traffic
+    import json
+    def num(v, u):
+        x = float(v.replace(",", "")); return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+    tr = {}
+    for r in rows[2:]:
+        k = "spmv1_vi_kernel" if "spmv1_vi_kernel" in r[idx["Kernel Name"]] else ("spmv1_tma_kernel" if "spmv1_tma_kernel" in r[idx["Kernel Name"]] else None)
+        if not k: continue
+        t = num(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) + num(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
+        tr.setdefault(k, []).append(t)
+    old = {}
+    try: old = json.load(open(f"{out}/traffic.json"))
+    except Exception: pass
+    old.update({k: int(sum(v) / len(v)) for k, v in tr.items()})
+    old["_source"] = f"{out}/{tag}_spmv_full.txt (ncu --set full, fused smoothing sweep at 129^3)"
+    json.dump(old, open(f"{out}/traffic.json", "w"), indent=1)
+    print("wrote", f"{out}/traffic.json", old)

@@ -394,7 +394,8 @@ int launch_scalar(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* dest, const
 	// measured (profiles/r01b): the bulk-copy kernel wins for the fused variants, the register-staged
 	// one for the plain sweep; the value-indexed stream always goes through the bulk-copy kernel when
 	// the matrix is large enough (its 2-byte loads are a poor fit for register staging)
-	if constexpr (FUSE != FUSE_RESTRICT_JACOBI) {
+	// (the fused restriction is implemented by the value-indexed bulk-copy kernel and the register-staged one)
+	if constexpr (FUSE != FUSE_RESTRICT_JACOBI || COMP) {
 		if (!ctx->no_tma && (COMP || FUSE != FUSE_NONE || ctx->tma_min_slices_per_warp == 0 || ctx->tma_all)) {
 			const int rc = launch_tma<BETAK, MODE, FUSE, COMP>(ctx, S, dest, v, alpha, beta, w, fz, &used);
 			if (rc) return rc;

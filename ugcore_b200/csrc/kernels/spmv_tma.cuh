@@ -365,7 +365,7 @@ spmv1_vi_kernel(Sell A, double* dest, const double* v, double alpha, double beta
 	Meta cur = fetch_meta(gwarp);
 	int stage = 0; uint32_t phase = 0;
 	double dot = 0.0;
-	const UgPushDev* push = FUSE == FUSE_JACOBI ? fz.push : nullptr;
+	const UgPushDev* push = (FUSE == FUSE_JACOBI || FUSE == FUSE_RESTRICT_JACOBI) ? fz.push : nullptr;
 	const unsigned long long pe = push ? *(volatile unsigned long long*)push->epoch + 1ull : 0ull;
 	while (cur.s < nslices) {
 		const Meta nxt = fetch_meta(cur.s + nwarps);
@@ -383,6 +383,7 @@ spmv1_vi_kernel(Sell A, double* dest, const double* v, double alpha, double beta
 		if (MODE == MODE_INPLACE) acc = cur.acc0;
 		else if (MODE == MODE_GENERAL) acc = alpha * cur.acc0;
 		if (FUSE == FUSE_DOT) { if (live) own = w[row]; }
+		if (FUSE == FUSE_RESTRICT_JACOBI && live) { dinv = fz.diaginv[row]; if (len == 0) own = dest[row]; }
 		if (FUSE == FUSE_JACOBI && live) {
 			if (fz.flags & UG4B200_SMOOTH_ADD_IN) own = w[row];
 			if ((fz.flags & (UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_ADD_OUT)) && !(fz.flags & UG4B200_SMOOTH_SC_ZERO)) scv = fz.sc[row];
@@ -468,6 +469,16 @@ spmv1_vi_kernel(Sell A, double* dest, const double* v, double alpha, double beta
 					if (fz.flags & UG4B200_SMOOTH_ADD_OUT) scv = scv + st;
 				}
 				if (fz.flags & (UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_ADD_OUT)) fz.sc[row] = scv;
+			}
+		} else if (FUSE == FUSE_RESTRICT_JACOBI) {
+			// coarse defect by restriction (rows without connections keep their value), then the first
+			// Jacobi step of the coarse level on it: st = diagInv * sd
+			if (live) {
+				double dv = own;
+				if (len > 0) { dest[row] = acc; dv = acc; }
+				const double st = dinv * dv;
+				fz.st_out[row] = st;
+				if ((pmask >> lane) & 1u) ug_push_row(push, pe, cur.s, lane, pmask, st);
 			}
 		} else {
 			if (live && (MODE != MODE_ASSIGN_SKIP_EMPTY || len > 0)) dest[row] = acc;
