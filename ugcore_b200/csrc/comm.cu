@@ -133,20 +133,22 @@ struct P2PIfaceDev {
 	const int* idx;                    // [total] local index of send entry
 	const int* ent_code;               // [total] (position inside the neighbour's list << 5) | neighbour slot
 	const P2PNb* nb;
-	const unsigned long long* lflag;   // [nneigh] in my window, raised by the neighbours
-	const double* lrecv;               // my receive region (2 parities x total x 9 doubles)
-	int64_t lpar_stride;
+	const unsigned long long* lflag;   // [nneigh] in my window (flag protocol; unused by the tagged-slot exchange)
+	const double* lrecv;               // my receive region (2 parities x total x 9 tagged 16-byte slots)
+	int64_t lpar_stride;               // slots between the parity buffers
 	const int* uidx;                   // [nu] local index of every interface DoF
 	const int* uell;                   // [nu][ell_w] copies in ascending rank order: recv entry, -1 own value, -2 none
+	const int* sptr; const int* scode; // [nu + 1] / [total] sends of interface DoF u: (position in the neighbour's list << 5) | slot
 	const unsigned char* owned;        // [nlocal] 1 where this rank is the h-master
 	unsigned long long* epoch; unsigned int* arrive; unsigned int* depart; int* err;
-	int fence_all;                     // A/B switch: every thread fences its remote stores (else: barrier + one release)
 };
 
-// sum of all copies of one interface DoF component; the W source loads are independent of each other
+// One thread per interface DoF component: it sends its own value to every rank that shares the DoF
+// (tagged slots), then polls the slots of the other copies and adds all copies in ascending rank
+// order.  A DoF is read, sent and overwritten by the same thread, so no barrier is needed anywhere.
 template <int W>
-__device__ __forceinline__ void p2p_unpack(const P2PIfaceDev& d, const double* recv, double* v, int block, int unique,
-                                           int64_t tid, int64_t stride)
+__device__ __forceinline__ void p2p_send_sum(const P2PIfaceDev& d, const P2PNb* s_nb, const unsigned long long* recv, int64_t par,
+                                             unsigned int tag, double* v, int block, int unique, int pushed, int64_t tid, int64_t stride)
 {
 	for (int64_t t = tid; t < d.nu * block; t += stride) {
 		const int64_t u = t / block; const int q = (int)(t - u * block);
@@ -156,9 +158,16 @@ __device__ __forceinline__ void p2p_unpack(const P2PIfaceDev& d, const double* r
 #pragma unroll
 		for (int k = 0; k < W; ++k) src[k] = d.uell[u * d.ell_w + k];
 		const double own = v[li];
+		if (!pushed) {
+			for (int p = d.sptr[u]; p < d.sptr[u + 1]; ++p) {
+				const int code = d.scode[p];
+				const P2PNb& nb = s_nb[code & 31];
+				ug_ll_store(reinterpret_cast<unsigned long long*>(nb.rbase) + 2 * (par * nb.rpar_stride + (nb.rptr + (code >> 5)) * block + q), own, tag);
+			}
+		}
 		const bool keep = !unique || d.owned[lidx];
 #pragma unroll
-		for (int k = 0; k < W; ++k) x[k] = src[k] >= 0 ? ug_ld_relaxed_sys(recv + (int64_t)src[k] * block + q) : own;
+		for (int k = 0; k < W; ++k) x[k] = src[k] >= 0 ? ug_ll_load(recv + 2 * ((int64_t)src[k] * block + q), tag, d.err) : own;
 		double s = x[0];
 #pragma unroll
 		for (int k = 1; k < W; ++k) if (src[k] != -2) s = s + x[k];
@@ -168,57 +177,26 @@ __device__ __forceinline__ void p2p_unpack(const P2PIfaceDev& d, const double* r
 }
 
 // AdditiveToConsistent / AdditiveToUnique in one kernel.  Grid <= #SMs so that all CTAs are
-// co-resident: CTAs that wait for a neighbour must not keep CTAs that still have to send off
-// the SMs.  Small interfaces (the usual case) run as ONE CTA: no inter-CTA hand-shake at all.
+// co-resident: CTAs that poll for a neighbour's values must not keep CTAs that still have to send
+// off the SMs (every CTA sends its share before it polls).
 __global__ void __launch_bounds__(1024)
 p2p_exchange_sum_kernel(P2PIfaceDev d, double* v, int block, int unique, int pushed, const int* guard)
 {
 	if (ug_guarded(guard)) return;
-	__shared__ bool s_last;
 	__shared__ P2PNb s_nb[32];
 	if (threadIdx.x < d.nneigh) s_nb[threadIdx.x] = d.nb[threadIdx.x];
 	const unsigned long long e = *(volatile unsigned long long*)d.epoch + 1ull;
 	const int64_t par = (int64_t)(e & 1ull);
+	const unsigned int tag = ug_ll_tag(e);
 	const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
 	__syncthreads();
-	// pushed: the kernel that produced v already stored the interface rows into the neighbours' windows
-	// and raised the flags (ug_push_row / ug_push_finish) — only steps 3-5 are left
-	if (!pushed) {
-	// 1. push my interface values into the neighbours' windows
-	for (int64_t t = tid; t < d.total * block; t += stride) {
-		const int64_t en = t / block; const int q = (int)(t - en * block);
-		const int code = d.ent_code[en];
-		const int li = d.idx[en];
-		const P2PNb& nb = s_nb[code & 31];
-		double* dst = nb.rbase + par * nb.rpar_stride + (nb.rptr + (code >> 5)) * block + q;
-		ug_st_relaxed_sys(dst, v[(int64_t)li * block + q]);
-	}
-	// the CTA barrier orders every thread's stores before the release below (causality order is
-	// transitive through bar.sync; the same pattern as a CUTLASS semaphore release)
-	if (d.fence_all) __threadfence_system();
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		s_last = true;
-		if (gridDim.x > 1) {
-			__threadfence_system();
-			s_last = (atomicAdd(d.arrive, 1u) == gridDim.x - 1);
-			if (s_last) { *d.arrive = 0u; __threadfence_system(); } // acquire side of the other CTAs' arrivals
-		}
-	}
-	__syncthreads();
-	// 2. everything of this rank is on its way: raise my flag at every neighbour
-	if (s_last && threadIdx.x < d.nneigh) ug_st_release_sys(s_nb[threadIdx.x].rflag, e);
-	}
-	// 3. wait for the neighbours
-	if (threadIdx.x < d.nneigh) ug_wait_flag(d.lflag + threadIdx.x, e, d.err);
-	__syncthreads();
-	// 4. sum all copies in ascending rank order
-	const double* recv = d.lrecv + par * d.lpar_stride;
-	if (d.ell_w <= 2) p2p_unpack<2>(d, recv, v, block, unique, tid, stride);
-	else if (d.ell_w <= 4) p2p_unpack<4>(d, recv, v, block, unique, tid, stride);
-	else p2p_unpack<8>(d, recv, v, block, unique, tid, stride);
-	// 5. the last CTA to leave publishes the epoch (every CTA read it on entry)
+	// send + poll + sum per interface DoF (pushed: the kernel that produced v has already sent, ug_push_row)
+	const unsigned long long* recv = reinterpret_cast<const unsigned long long*>(d.lrecv) + 2 * par * d.lpar_stride;
+	if (d.ell_w <= 2) p2p_send_sum<2>(d, s_nb, recv, par, tag, v, block, unique, pushed, tid, stride);
+	else if (d.ell_w <= 4) p2p_send_sum<4>(d, s_nb, recv, par, tag, v, block, unique, pushed, tid, stride);
+	else p2p_send_sum<8>(d, s_nb, recv, par, tag, v, block, unique, pushed, tid, stride);
+	// the last CTA to leave publishes the epoch (every CTA read it on entry)
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		if (gridDim.x == 1) *(volatile unsigned long long*)d.epoch = e;
@@ -389,7 +367,7 @@ static int p2p_interface_setup(ug4b200_ctx* ctx, ug4b200_interface* I, Up& up, c
 	if (I->nneigh > 32 || w > 8 || maxrel >= (1ll << 26)) return UG4B200_OK;
 	I->ell_w = w <= 2 ? 2 : (w <= 4 ? 4 : 8);
 	const size_t flag_bytes = (((size_t)I->nneigh * 8) + 255) / 256 * 256;
-	const size_t recv_bytes = (((size_t)2 * I->total * 9 * 8) + 255) / 256 * 256;
+	const size_t recv_bytes = (((size_t)2 * I->total * 9 * 16) + 255) / 256 * 256;   // 2 parities x tagged 16-byte slots
 	if (P->bump + flag_bytes + recv_bytes > P->bytes)
 		return ug4b200_fail(ctx, UG4B200_ERR_NOMEM, "interface: peer window exhausted (UG4B200_P2P_WINDOW_MB)");
 	I->id = P->next_iface++;
@@ -413,8 +391,8 @@ static int p2p_interface_setup(ug4b200_ctx* ctx, ug4b200_interface* I, Up& up, c
 	UG_CUDA(ctx, cudaMemsetAsync(I->d_epoch, 0, 8, ctx->stream));
 	UG_CUDA(ctx, cudaMemsetAsync(I->d_counters, 0, 8, ctx->stream));
 	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	// flags start at epoch 0 (the region may be recycled); then publish
-	UG_CUDA(ctx, cudaMemsetAsync(P->local + I->win_off, 0, flag_bytes, P->aux));
+	// slots start untagged (tag 0; the region may be recycled); then publish
+	UG_CUDA(ctx, cudaMemsetAsync(P->local + I->win_off, 0, flag_bytes + recv_bytes, P->aux));
 	UG_CUDA(ctx, cudaStreamSynchronize(P->aux));
 	for (int p = 0; p < I->nneigh; ++p) {
 		ug4b200_p2p_entry ent{};
@@ -644,7 +622,7 @@ int ug4b200_interface_commit(ug4b200_ctx* ctx, ug4b200_interface* I)
 	if (I->d_push) {
 		UgPushDev pd{};
 		pd.nneigh = I->nneigh; pd.rowmask = I->d_rowmask; pd.rowprefix = I->d_rowprefix; pd.sptr = I->d_sptr; pd.scode = I->d_scode; pd.scode1 = I->d_scode1;
-		pd.nb = I->d_nb; pd.epoch = I->d_epoch; pd.arrive = I->d_push_arrive;
+		pd.nb = I->d_nb; pd.epoch = I->d_epoch; pd.arrive = I->d_push_arrive;   // (arrive: unused by the tagged-slot push)
 		UG_CUDA(ctx, cudaMemcpyAsync(I->d_push, &pd, sizeof(pd), cudaMemcpyHostToDevice, P->aux));
 	}
 	UG_CUDA(ctx, cudaStreamSynchronize(P->aux));
@@ -665,10 +643,9 @@ static int exchange_sum(ug4b200_ctx* ctx, ug4b200_interface* I, double* v, int b
 		d.lflag = reinterpret_cast<const unsigned long long*>(ctx->p2p->local + I->win_off);
 		d.lrecv = reinterpret_cast<const double*>(ctx->p2p->local + I->recv_off);
 		d.lpar_stride = I->total * 9;
-		d.uidx = I->d_uidx; d.uell = I->d_uell;
+		d.uidx = I->d_uidx; d.uell = I->d_uell; d.sptr = I->d_sptr; d.scode = I->d_scode;
 		d.owned = I->d_owned;
 		d.epoch = I->d_epoch; d.arrive = I->d_counters; d.depart = I->d_counters + 1; d.err = ctx->p2p->err_dev;
-		{ static const bool fa = getenv("UG4B200_P2P_FENCE_ALL") && getenv("UG4B200_P2P_FENCE_ALL")[0] == '1'; d.fence_all = fa ? 1 : 0; }
 		// One CTA for small interfaces (no inter-CTA hand-shake); large ones need many SMs because one
 		// SM sustains only a few GB/s of remote stores (measured: 16641 values from one CTA 42 us, from
 		// 17 CTAs 18 us).  Never more CTAs than SMs (co-residency, see kernel).
@@ -678,7 +655,7 @@ static int exchange_sum(ug4b200_ctx* ctx, ug4b200_interface* I, double* v, int b
 		}
 		const int pushed = I->pushed_vec == v ? 1 : 0;
 		I->pushed_vec = nullptr;
-		const int64_t work = I->total * block;
+		const int64_t work = I->nu * block;
 		static const int cta_work = getenv("UG4B200_P2P_CTA_WORK") ? atoi(getenv("UG4B200_P2P_CTA_WORK")) : 128;
 		int64_t g = work <= 2048 ? 1 : (work + cta_work - 1) / cta_work;
 		if (g > ctx->num_sms) g = ctx->num_sms;
@@ -730,7 +707,7 @@ int ug4b200_p2p_window_create(ug4b200_ctx* ctx, size_t bytes, unsigned char hand
 	if (ctx->p2p) return ug4b200_fail(ctx, UG4B200_ERR_STATE, "peer window already created");
 	if (bytes == 0) {
 		const char* e = getenv("UG4B200_P2P_WINDOW_MB");
-		bytes = (size_t)(e ? atoi(e) : 64) << 20;
+		bytes = (size_t)(e ? atoi(e) : 128) << 20;
 	}
 	if (bytes < kP2PHeapOff + (1u << 20)) bytes = kP2PHeapOff + (1u << 20);
 	UG_CUDA(ctx, cudaSetDevice(ctx->device));

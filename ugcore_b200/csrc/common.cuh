@@ -68,14 +68,16 @@ struct ug4b200_ctx {
 
 // ---- peer windows: layout of every rank's window (identical on all ranks) ----------------
 //   [0, 64 KiB)        table   Entry[kP2PMaxIfaces][kP2PMaxRanks]: where rank r writes for interface k
-//   [64 KiB, +512)     all-reduce flags, one uint64 per source rank
-//   [.., +256 KiB)     all-reduce slots  double[2 parities][kP2PMaxRanks][kP2PArMax]
+//   [64 KiB, +512)     all-reduce flags, one uint64 per source rank (vector all-reduce, p2p_allreduce_kernel)
+//   [+512, +1024)      scalar all-reduce: tagged 16-byte slots [2 parities][kP2PMaxRanks] (ug_warp_allreduce)
+//   [+2048, +256 KiB)  all-reduce slots  double[2 parities][kP2PMaxRanks][kP2PArMax]
 //   [kP2PHeapOff, ..)  per-interface flags + receive regions (bump allocated)
 constexpr int kP2PMaxRanks = 16;
 constexpr int kP2PMaxIfaces = 64;
 constexpr int kP2PArMax = 1024;
 constexpr size_t kP2PArFlagOff = 65536;
-constexpr size_t kP2PArDataOff = 65536 + 512;
+constexpr size_t kP2PArLLOff = 65536 + 512;
+constexpr size_t kP2PArDataOff = 65536 + 2048;
 constexpr size_t kP2PHeapOff = kP2PArDataOff + (size_t)2 * kP2PMaxRanks * kP2PArMax * 8;
 constexpr unsigned long long kP2PTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
 
@@ -258,16 +260,41 @@ __device__ inline bool ug_wait_flag(const unsigned long long* flag, unsigned lon
 	}
 	return true;
 }
+// ---- flag-in-data slots ("LL"): every double travels as two 8-byte words, each carrying 32 data
+// bits and the 32-bit tag of the exchange epoch.  An 8-byte store is single-copy atomic, so the
+// receiver simply polls the slot until both tags match: no fence, no separate flag, one one-way
+// NVLink trip instead of (store, ack, flag) — measured 8 us -> see DESIGN.md for an empty exchange.
+__device__ __forceinline__ unsigned int ug_ll_tag(unsigned long long e) { return (unsigned int)(e % 0xffffffffull) + 1u; }   // never 0 (= cleared slot)
+__device__ __forceinline__ void ug_ll_store(unsigned long long* slot, double v, unsigned int tag)
+{
+	const unsigned long long b = (unsigned long long)__double_as_longlong(v), t = (unsigned long long)tag << 32;
+	asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"((b & 0xffffffffull) | t), "l"((b >> 32) | t) : "memory");
+}
+__device__ inline double ug_ll_load(const unsigned long long* slot, unsigned int tag, int* err)
+{
+	unsigned long long w0, w1, t0 = 0; unsigned int spins = 0;
+	for (;;) {
+		asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+		if ((unsigned int)(w0 >> 32) == tag && (unsigned int)(w1 >> 32) == tag) break;
+		if ((++spins & 0xfffu) == 0u) {
+			const unsigned long long t = ug_globaltimer();
+			if (t0 == 0) t0 = t;
+			else if (t - t0 > kP2PTimeoutNs) { if (err) *(volatile int*)err = 1; break; }
+		}
+	}
+	return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+}
+
 // ---- interface push fused into a producing kernel (comm.cu holds the host side) ------------
 // The kernel that computes an additive vector whose interface rows must become consistent
 // (AdditiveToConsistent, parallelization_util.h:159-191) stores those rows straight into the
-// neighbours' peer windows while it streams the matrix; its last CTA raises the epoch flags.  The
-// exchange that follows is then only "wait for the neighbours' flags and add the copies".
+// neighbours' peer windows (tagged slots, see above) while it streams the matrix.  The exchange that
+// follows is then only "poll the neighbours' slots and add the copies".
 struct UgPushNb {
-	double* rbase;               // neighbour's receive region (in ITS window)
-	int64_t rpar_stride;         // doubles between its two parity buffers
+	double* rbase;               // neighbour's receive region (in ITS window): 16-byte tagged slots
+	int64_t rpar_stride;         // slots between its two parity buffers
 	int64_t rptr;                // my first entry inside its region
-	unsigned long long* rflag;   // flag in its window that I raise
+	unsigned long long* rflag;   // (flag of the flag protocol; unused by the tagged-slot exchange)
 };
 struct UgPushDev {
 	int nneigh, pad_;
@@ -286,61 +313,40 @@ __device__ __forceinline__ void ug_push_row(const UgPushDev* P, unsigned long lo
 	const int c1 = P->scode1[u];
 	if (c1 >= 0) {
 		const UgPushNb nb = P->nb[c1 & 31];
-		ug_st_relaxed_sys(nb.rbase + par * nb.rpar_stride + nb.rptr + (c1 >> 5), val);
+		ug_ll_store(reinterpret_cast<unsigned long long*>(nb.rbase) + 2 * (par * nb.rpar_stride + nb.rptr + (c1 >> 5)), val, ug_ll_tag(e));
 		return;
 	}
 	for (int p = P->sptr[u]; p < P->sptr[u + 1]; ++p) {
 		const int code = P->scode[p];
 		const UgPushNb nb = P->nb[code & 31];
-		ug_st_relaxed_sys(nb.rbase + par * nb.rpar_stride + nb.rptr + (code >> 5), val);
+		ug_ll_store(reinterpret_cast<unsigned long long*>(nb.rbase) + 2 * (par * nb.rpar_stride + nb.rptr + (code >> 5)), val, ug_ll_tag(e));
 	}
-}
-// called by ALL threads of every CTA at the end of the producing kernel: the last CTA to arrive
-// raises this rank's flag at every neighbour (the CTA barrier + the fences order all pushes before it)
-__device__ inline void ug_push_finish(const UgPushDev* P, unsigned long long e)
-{
-	__shared__ bool s_push_last;
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		__threadfence_system();
-		s_push_last = (atomicAdd(P->arrive, 1u) == gridDim.x - 1);
-		if (s_push_last) { *P->arrive = 0u; __threadfence_system(); }
-	}
-	__syncthreads();
-	if (s_push_last && threadIdx.x < P->nneigh) ug_st_release_sys(P->nb[threadIdx.x].rflag, e);
 }
 // comm.cu: if `I` can take a fused push for `vec` return its device descriptor and remember that the
 // next AdditiveToConsistent of `vec` only has to wait and add; nullptr otherwise
 const UgPushDev* ug_iface_push_begin(ug4b200_ctx* ctx, struct ug4b200_interface* I, const double* vec);
 
 // Sum of one double over all ranks, executed by warp 0 of ONE block per rank: every rank stores its
-// value into slot [parity][rank] of every window, raises its flag there (release), waits for the
-// flags of all ranks in its own window (acquire) and adds the slots in ascending rank order, so the
-// result is bitwise identical on every rank.  `a` is taken from lane 0, the result is valid in lane 0.
+// value as a tagged slot [parity][rank] into every window, polls the slots of all ranks in its own
+// window and adds them in ascending rank order, so the result is bitwise identical on every rank.
+// `a` is taken from lane 0, the result is valid in lane 0.
 __device__ inline double ug_warp_allreduce(double a, const UgAr& ar)
 {
 	const int lane = threadIdx.x & 31;
 	a = __shfl_sync(0xffffffffu, a, 0);
 	const unsigned long long e = *(volatile unsigned long long*)ar.epoch + 1ull;
 	const int par = (int)(e & 1ull);
+	const unsigned int tag = ug_ll_tag(e);
 	__syncwarp();
+	double x = 0.0;
 	if (lane < ar.nranks) {
-		char* pw = ar.peer[lane];
-		double* slot = reinterpret_cast<double*>(pw + kP2PArDataOff) + (size_t)(par * kP2PMaxRanks + ar.rank) * kP2PArMax;
-		ug_st_relaxed_sys(slot, a);
-		ug_st_release_sys(reinterpret_cast<unsigned long long*>(pw + kP2PArFlagOff) + ar.rank, e);
-		ug_wait_flag(reinterpret_cast<const unsigned long long*>(ar.local + kP2PArFlagOff) + lane, e, ar.err);
+		// tagged slots: the value is its own arrival notice (one one-way NVLink trip, no flag, no fence)
+		ug_ll_store(reinterpret_cast<unsigned long long*>(ar.peer[lane] + kP2PArLLOff) + 2 * (par * kP2PMaxRanks + ar.rank), a, tag);
+		x = ug_ll_load(reinterpret_cast<const unsigned long long*>(ar.local + kP2PArLLOff) + 2 * (par * kP2PMaxRanks + lane), tag, ar.err);
 	}
-	__syncwarp();
-	double s = 0.0;
-	if (lane == 0) {
-		const double* base = reinterpret_cast<const double*>(ar.local + kP2PArDataOff) + (size_t)par * kP2PMaxRanks * kP2PArMax;
-		for (int p = 0; p < ar.nranks; ++p) {
-			const double x = ug_ld_relaxed_sys(base + (size_t)p * kP2PArMax);
-			s = (p == 0) ? x : s + x;
-		}
-		*(volatile unsigned long long*)ar.epoch = e;
-	}
+	double s = __shfl_sync(0xffffffffu, x, 0);
+	for (int p = 1; p < ar.nranks; ++p) s = s + __shfl_sync(0xffffffffu, x, p);   // ascending rank order on every rank
+	if (lane == 0) *(volatile unsigned long long*)ar.epoch = e;
 	return s;
 }
 

@@ -165,7 +165,6 @@ spmv1_kernel(Sell A, double* dest, const double* v, double alpha, double beta, c
 		}
 	}
 	if (FUSE == FUSE_DOT) ug_block_reduce_fin(dot, fz.partials, fz.counter, fz.fin, fz.ar);
-	if (push) ug_push_finish(push, pe);
 }
 
 // ---------------------------------------------------------------- block B x B

@@ -236,7 +236,6 @@ spmv1_tma_kernel(Sell A, double* dest, const double* v, double alpha, double bet
 		cur = nxt;
 	}
 	if (FUSE == FUSE_DOT) ug_block_reduce_fin(dot, fz.partials, fz.counter, fz.fin, fz.ar);
-	if (push) ug_push_finish(push, pe);
 }
 
 // ---------------------------------------------------------------- value-indexed stream
@@ -487,7 +486,6 @@ spmv1_vi_kernel(Sell A, double* dest, const double* v, double alpha, double beta
 		cur = nxt;
 	}
 	if (FUSE == FUSE_DOT) ug_block_reduce_fin(dot, fz.partials, fz.counter, fz.fin, fz.ar);
-	if (push) ug_push_finish(push, pe);
 }
 
 } // namespace tma
