@@ -103,6 +103,33 @@ int ug4b200_solver_history(const ug4b200_solver* s, double* out, int cap);
 int ug4b200_solver_precond_apply(ug4b200_solver* s, double* c_host, const double* d_host);
 int64_t ug4b200_solver_num_dofs(const ug4b200_solver* s);
 
+/* ---- import / export of assembled objects (host side, no device involved) -------------------
+ * ConnectionViewer .mat / .vec (ugbase/lib_algebra/common/connection_viewer_{output,input}.h) and
+ * MatrixMarket .mtx (ugbase/lib_algebra/common/matrixio/matrix_io_mtx.{h,cpp}): the formats in which
+ * a ugcore installation dumps A, the level matrices, P, R, b and per-iteration residuals (debug
+ * writers, cg.h:274-280, mg_solver_impl.hpp:692-696, 2181-2200).  Scalar matrices.
+ * format: 0 = by file extension (.mtx -> MatrixMarket, anything else ConnectionViewer), 1 = ConnectionViewer,
+ * 2 = MatrixMarket. */
+typedef struct ug4b200_host_matrix ug4b200_host_matrix;
+/* keep_zeros = 0 follows the reference reader (zero values are not inserted).  n_to > 0: a ConnectionViewer
+ * file written with from / to positions (rectangular P / R): rows 0..n_to-1, columns numbered behind them. */
+int ug4b200_io_read_matrix(const char* filename, int format, int keep_zeros, int64_t n_to, ug4b200_host_matrix** out);
+int ug4b200_io_matrix_info(const ug4b200_host_matrix* m, int64_t* nrows, int64_t* ncols, int64_t* nnz, int* dim, int64_t* npos);
+/* rowptr[nrows+1], cols[nnz], vals[nnz]; positions[3*npos] or NULL */
+int ug4b200_io_matrix_export(const ug4b200_host_matrix* m, int64_t* rowptr, int* cols, double* vals, double* positions);
+void ug4b200_io_matrix_free(ug4b200_host_matrix* m);
+/* positions: 3 doubles per position (NULL: all zero).  ConnectionViewer: npos = nrows positions, or — from / to
+ * form, from_to = 1 — nrows + ncols positions (rows first).  precision 0 = the reference's formatting
+ * (ConnectionViewer: 6 significant digits for matrix values; MatrixMarket: 13 digits), > 0 = that many
+ * digits (17 resp. 16 are lossless for fp64). */
+int ug4b200_io_write_matrix(const char* filename, int format, int64_t nrows, int64_t ncols, const int64_t* rowptr,
+                            const int* cols, const double* vals, const double* positions, int dim, int from_to,
+                            int precision);
+int ug4b200_io_vector_size(const char* filename, int64_t* n, int* dim);
+int ug4b200_io_read_vector(const char* filename, int64_t n, double* values, double* positions);
+int ug4b200_io_write_vector(const char* filename, int64_t n, const double* values, const double* positions, int dim,
+                            int precision);
+
 #ifdef __cplusplus
 }
 #endif

@@ -174,6 +174,14 @@ HOST_API = {
     "ug4b200_solver_history": (c_int, [c_vp, c_vp, c_int]),
     "ug4b200_solver_precond_apply": (c_int, [c_vp, c_vp, c_vp]),
     "ug4b200_solver_num_dofs": (c_i64, [c_vp]),
+    "ug4b200_io_read_matrix": (c_int, [C.c_char_p, c_int, c_int, c_i64, C.POINTER(c_vp)]),
+    "ug4b200_io_matrix_info": (c_int, [c_vp, p_i64, p_i64, p_i64, p_int, p_i64]),
+    "ug4b200_io_matrix_export": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "ug4b200_io_matrix_free": (None, [c_vp]),
+    "ug4b200_io_write_matrix": (c_int, [C.c_char_p, c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int]),
+    "ug4b200_io_vector_size": (c_int, [C.c_char_p, p_i64, p_int]),
+    "ug4b200_io_read_vector": (c_int, [C.c_char_p, c_i64, c_vp, c_vp]),
+    "ug4b200_io_write_vector": (c_int, [C.c_char_p, c_i64, c_vp, c_vp, c_int, c_int]),
 }
 
 for _name, (_res, _args) in DEV_API.items():

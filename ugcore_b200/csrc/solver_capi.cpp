@@ -3,6 +3,7 @@
 // SolveLinearProblem (scripts/util/solver_util.lua:602, :1182-1210) for non-Lua callers.
 #include "../../include/ug4b200_solver.h"
 #include "host/multigrid.h"
+#include "host/matrix_io.h"
 #include <cstring>
 
 using namespace ug;
@@ -291,5 +292,115 @@ int ug4b200_solver_history(const ug4b200_solver* s, double* out, int cap)
 }
 int ug4b200_solver_precond_apply(ug4b200_solver* s, double* c_host, const double* d_host) { return guard([&] { s->p->precond_apply(c_host, d_host); return 0; }); }
 int64_t ug4b200_solver_num_dofs(const ug4b200_solver* s) { return s->p->num_dofs(); }
+
+/* ---- import / export (host/matrix_io.h) ---- */
+} // extern "C"
+struct ug4b200_host_matrix { GPUSparseMatrix<double> A; IOPositions pos; int dim = 3; };
+namespace {
+int io_format(const char* filename, int format)
+{
+	if (format == 1 || format == 2) return format;
+	const std::string f(filename);
+	return (f.size() >= 4 && f.compare(f.size() - 4, 4, ".mtx") == 0) ? 2 : 1;
+}
+IOPositions io_positions(const double* positions, size_t n, int dim)
+{
+	IOPositions p; p.dim = dim; p.resize(n);
+	if (positions) std::memcpy(p.xyz.data(), positions, sizeof(double) * 3 * n);
+	return p;
+}
+} // namespace
+extern "C" {
+
+int ug4b200_io_read_matrix(const char* filename, int format, int keep_zeros, int64_t n_to, ug4b200_host_matrix** out)
+{
+	*out = nullptr;
+	return guard([&] {
+		std::unique_ptr<ug4b200_host_matrix> m(new ug4b200_host_matrix);
+		if (io_format(filename, format) == 2) {
+			MatrixIOMtx io(filename);
+			io.read_into(m->A);
+			m->pos.resize(0);
+		} else if (!ConnectionViewer::ReadMatrix(filename, m->A, m->pos, m->dim, keep_zeros != 0, (size_t)(n_to > 0 ? n_to : 0)))
+			UG_THROW("cannot open " << filename);
+		*out = m.release();
+		return 0;
+	});
+}
+int ug4b200_io_matrix_info(const ug4b200_host_matrix* m, int64_t* nrows, int64_t* ncols, int64_t* nnz, int* dim, int64_t* npos)
+{
+	return guard([&] {
+		if (nrows) *nrows = (int64_t)m->A.num_rows();
+		if (ncols) *ncols = (int64_t)m->A.num_cols();
+		if (nnz) *nnz = (int64_t)m->A.total_num_connections();
+		if (dim) *dim = m->dim;
+		if (npos) *npos = (int64_t)m->pos.size();
+		return 0;
+	});
+}
+int ug4b200_io_matrix_export(const ug4b200_host_matrix* m, int64_t* rowptr, int* cols, double* vals, double* positions)
+{
+	return guard([&] {
+		const std::vector<int64_t>& rp = m->A.crs_rowptr(); const std::vector<int>& ci = m->A.crs_cols(); const std::vector<double>& va = m->A.crs_vals();
+		std::memcpy(rowptr, rp.data(), sizeof(int64_t) * rp.size());
+		if (!ci.empty()) { std::memcpy(cols, ci.data(), sizeof(int) * ci.size()); std::memcpy(vals, va.data(), sizeof(double) * va.size()); }
+		if (positions && m->pos.size()) std::memcpy(positions, m->pos.xyz.data(), sizeof(double) * m->pos.xyz.size());
+		return 0;
+	});
+}
+void ug4b200_io_matrix_free(ug4b200_host_matrix* m) { delete m; }
+int ug4b200_io_write_matrix(const char* filename, int format, int64_t nrows, int64_t ncols, const int64_t* rowptr,
+                            const int* cols, const double* vals, const double* positions, int dim, int from_to,
+                            int precision)
+{
+	return guard([&] {
+		GPUSparseMatrix<double> A;
+		A.set_from_crs((size_t)nrows, (size_t)ncols, rowptr, cols, vals);
+		if (io_format(filename, format) == 2) {
+			MatrixIOMtx io(filename);
+			if (precision > 0) io.set_precision(precision);
+			io.write_from(A);
+		} else if (from_to) {
+			const IOPositions to = io_positions(positions, (size_t)nrows, dim);
+			const IOPositions from = io_positions(positions ? positions + 3 * nrows : nullptr, (size_t)ncols, dim);
+			if (!ConnectionViewer::WriteMatrix(std::string(filename), A, from, to, (size_t)dim, precision)) UG_THROW("WriteMatrix: positions do not match the matrix");
+		} else {
+			if (nrows != ncols) UG_THROW("ConnectionViewer::WriteMatrix: a rectangular matrix needs the from / to form");
+			ConnectionViewer::WriteMatrix(std::string(filename), A, io_positions(positions, (size_t)nrows, dim), dim, precision);
+		}
+		return 0;
+	});
+}
+int ug4b200_io_vector_size(const char* filename, int64_t* n, int* dim)
+{
+	return guard([&] {
+		std::fstream f(filename, std::ios::in);
+		if (!f.is_open()) UG_THROW("cannot open " << filename);
+		int version = -1, d = -1; long long g = -1;
+		f >> version >> d >> g;
+		if (!f || version != 1 || g < 0) UG_THROW(filename << " is not a version-1 ConnectionViewer file");
+		*n = g; if (dim) *dim = d;
+		return 0;
+	});
+}
+int ug4b200_io_read_vector(const char* filename, int64_t n, double* values, double* positions)
+{
+	return guard([&] {
+		std::vector<double> v; IOPositions pos; int dim = 0;
+		if (!ConnectionViewer::ReadVector(filename, v, pos, dim)) UG_THROW("cannot open " << filename);
+		if ((int64_t)v.size() != n) UG_THROW("ReadVector: " << filename << " holds " << v.size() << " entries, caller expects " << n);
+		if (n) std::memcpy(values, v.data(), sizeof(double) * v.size());
+		if (positions && n) std::memcpy(positions, pos.xyz.data(), sizeof(double) * pos.xyz.size());
+		return 0;
+	});
+}
+int ug4b200_io_write_vector(const char* filename, int64_t n, const double* values, const double* positions, int dim,
+                            int precision)
+{
+	return guard([&] {
+		ConnectionViewer::WriteVector(filename, values, (size_t)n, io_positions(positions, (size_t)n, dim), dim, precision);
+		return 0;
+	});
+}
 
 } // extern "C"
