@@ -24,7 +24,10 @@ enum { UG4B200_PRECOND_NONE = 0, UG4B200_PRECOND_JACOBI = 1, UG4B200_PRECOND_GS 
 enum { UG4B200_FLAG_HOST_SCALARS = 1,   /* CG with host scalars (reference-shaped loop, one sync per dot) */
        UG4B200_FLAG_NO_GRAPH = 2,       /* do not capture the Krylov iteration into a CUDA graph */
        UG4B200_FLAG_NO_FUSED_JACOBI = 4,/* V-cycle with separate Jacobi / SpMV / AXPY launches */
-       UG4B200_FLAG_FINAL_LEVEL_DEFECT = 8 /* also do the reference's unused top-level defect update */ };
+       UG4B200_FLAG_FINAL_LEVEL_DEFECT = 8, /* also do the reference's unused top-level defect update */
+       UG4B200_FLAG_RAP = 16            /* gmg:set_rap(true): level operators below the top level are the Galerkin
+                                           products R A P (mg_solver_impl.hpp:828-1013), computed on the host at init;
+                                           ug4b200_solver_set_level then takes rowptr == NULL on those levels */ };
 
 typedef struct ug4b200_solver_desc {
 	int block;             /* 1 = GPUAlgebra, 2/3 = GPUBlockAlgebra<N> */
@@ -127,6 +130,13 @@ int ug4b200_io_write_matrix(const char* filename, int format, int64_t nrows, int
                             int precision);
 int ug4b200_io_vector_size(const char* filename, int64_t* n, int* dim);
 int ug4b200_io_read_vector(const char* filename, int64_t n, double* values, double* positions);
+/* M = R * A * P by the reference's AddMultiplyOf loop (sparsematrix_util.h:152-230; bit-identical): scalar
+ * CRS in (R: nc x nf, A: nf x nf, P: nf x nc), host matrix handle out (read with ug4b200_io_matrix_info /
+ * _export, release with _free).  The solver does this itself under UG4B200_FLAG_RAP (also for block
+ * matrices); the entry point exists for callers that want the coarse operator alone. */
+int ug4b200_host_rap(int64_t nc, int64_t nf, const int64_t* r_rowptr, const int* r_cols, const double* r_vals,
+                     const int64_t* a_rowptr, const int* a_cols, const double* a_vals,
+                     const int64_t* p_rowptr, const int* p_cols, const double* p_vals, ug4b200_host_matrix** out);
 int ug4b200_io_write_vector(const char* filename, int64_t n, const double* values, const double* positions, int dim,
                             int precision);
 

@@ -80,6 +80,8 @@ class Oracle:
         L.oracle_mat_export.argtypes = [C.c_void_p, _lp, _ip, _dp]
         L.oracle_mat_transpose.restype = C.c_void_p
         L.oracle_mat_transpose.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_mat_rap.restype = C.c_void_p
+        L.oracle_mat_rap.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_axpy.argtypes = [C.c_void_p, _dp, C.c_double, C.c_void_p, C.c_double, _dp, C.c_int]
         L.oracle_apply.argtypes = [C.c_void_p, _dp, _dp, C.c_int]
         L.oracle_matmul_minus.argtypes = [C.c_void_p, _dp, _dp, C.c_int]
@@ -159,6 +161,13 @@ class OMat:
         if not h:
             raise RuntimeError("oracle: " + self.o.lib.oracle_last_error().decode())
         return OMat(self.o, self.block, self.ncols, self.nrows, None, None, None, handle=h)
+
+    def rap(self, R: "OMat", P: "OMat") -> "OMat":
+        """R * self * P (AddMultiplyOf): the Galerkin coarse operator of gmg:set_rap(true)."""
+        h = self.o.lib.oracle_mat_rap(R.h, self.h, P.h)
+        if not h:
+            raise RuntimeError("oracle: " + self.o.lib.oracle_last_error().decode())
+        return OMat(self.o, self.block, R.nrows, P.ncols, None, None, None, handle=h)
 
     def export(self):
         nnz = self.nnz

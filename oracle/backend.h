@@ -49,6 +49,10 @@ struct Backend {
 	virtual void export_crs(const Mat& A, int64_t* rowptr, int* cols, double* vals) = 0;
 	// set_as_transpose_of (keeps explicit zeros) / set_as_transpose_of2 (drops them)
 	virtual Mat* transpose(const Mat& A, bool keep_zeros) = 0;
+	// Galerkin product M = R * A * P by AddMultiplyOf (algebra_common/sparsematrix_util.h:152-230), as
+	// AssembledMultiGridCycle::init_rap_operator builds coarse operators (mg_solver_impl.hpp:959);
+	// R, P scalar (expanded to the block diagonal for block A, as ugcore stores them)
+	virtual Mat* rap(const Mat& R, const Mat& A, const Mat& P) = 0;
 
 	virtual void apply(const Mat& A, Vec& y, const Vec& x) = 0;        // y = A x
 	virtual void matmul_minus(const Mat& A, Vec& y, const Vec& x) = 0; // y -= A x

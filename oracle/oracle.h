@@ -31,6 +31,8 @@ int64_t oracle_mat_rows(const oracle_mat* A);
 int64_t oracle_mat_cols(const oracle_mat* A);
 int     oracle_mat_export(const oracle_mat* A, int64_t* rowptr, int* cols, double* vals);
 oracle_mat* oracle_mat_transpose(const oracle_mat* A, int keep_zeros);
+/* R * A * P by AddMultiplyOf (sparsematrix_util.h:152-230), the Galerkin coarse operator of gmg:set_rap(true) */
+oracle_mat* oracle_mat_rap(const oracle_mat* R, const oracle_mat* A, const oracle_mat* P);
 
 /* dest = alpha*v + beta*A*w (SparseMatrix::axpy); v may be NULL when alpha == 0;
  * v == dest selects the in-place branch */

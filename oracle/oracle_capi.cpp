@@ -87,6 +87,12 @@ oracle_mat* oracle_mat_transpose(const oracle_mat* A, int keep_zeros)
 	catch (const std::exception& e) { g_err = e.what(); return nullptr; }
 }
 
+oracle_mat* oracle_mat_rap(const oracle_mat* R, const oracle_mat* A, const oracle_mat* P)
+{
+	try { oracle_mat* T = new oracle_mat; T->m.reset(BK().rap(*R->m, *A->m, *P->m)); return T; }
+	catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+
 int oracle_axpy(const oracle_mat* A, double* dest, double alpha, const double* v, double beta, const double* w, int vb)
 {
 	return guard([&] {

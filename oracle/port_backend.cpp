@@ -171,6 +171,57 @@ struct PortBackend : Backend {
 		return T;
 	}
 
+	// algebra_common/sparsematrix_util.h:152-230 (AddMultiplyOf into an empty M): for row i, for
+	// R_ik != 0, for A_kl != 0: ab = R_ik * A_kl; for P_lj != 0: M_ij += ab * P_lj — accumulated in
+	// that order into an unsorted sparse row (UnsortedSparseVector), then stored sorted by column.
+	// R, P scalar: on the block diagonal they scale every component (zero off-diagonal terms add
+	// exact zeros in the reference's block products).
+	Mat* rap(const Mat& R_, const Mat& A_, const Mat& P_) override
+	{
+		const PMat& R = M(R_); const PMat& A = M(A_); const PMat& P = M(P_);
+		if (R.block != 1 || P.block != 1) throw std::runtime_error("port backend: rap needs scalar transfers");
+		if (R.ncols != A.nrows || A.ncols != P.nrows) throw std::runtime_error("port backend: rap size mismatch");
+		const int B = A.block, BB = B * B;
+		PMat* T = new PMat;
+		T->nrows = R.nrows; T->ncols = P.ncols; T->block = B;
+		T->rp.assign(T->nrows + 1, 0);
+		std::vector<int> slot(P.ncols, -1), touched;
+		std::vector<double> acc, ab(BB);
+		for (int64_t i = 0; i < R.nrows; ++i) {
+			touched.clear(); acc.clear();
+			for (int64_t pr = R.rp[i]; pr < R.rp[i + 1]; ++pr) {
+				const double r = R.va[pr];
+				if (r == 0.0) continue;
+				const int64_t k = R.ci[pr];
+				for (int64_t pa = A.rp[k]; pa < A.rp[k + 1]; ++pa) {
+					bool zero = true;
+					for (int t = 0; t < BB; ++t) if (A.va[pa * BB + t] != 0.0) zero = false;
+					if (zero) continue;
+					for (int t = 0; t < BB; ++t) ab[t] = r * A.va[pa * BB + t];
+					const int64_t l = A.ci[pa];
+					for (int64_t pp = P.rp[l]; pp < P.rp[l + 1]; ++pp) {
+						const double c = P.va[pp];
+						if (c == 0.0) continue;
+						const int j = P.ci[pp];
+						if (slot[j] < 0) { slot[j] = (int)touched.size(); touched.push_back(j); acc.insert(acc.end(), BB, 0.0); }
+						double* d = &acc[(size_t)slot[j] * BB];
+						for (int t = 0; t < BB; ++t) d[t] = d[t] + ab[t] * c;
+					}
+				}
+			}
+			std::vector<std::pair<int, int> > order;
+			for (size_t t = 0; t < touched.size(); ++t) order.push_back(std::make_pair(touched[t], (int)t));
+			std::sort(order.begin(), order.end());
+			for (size_t t = 0; t < order.size(); ++t) {
+				T->ci.push_back(order[t].first);
+				for (int q = 0; q < BB; ++q) T->va.push_back(acc[(size_t)order[t].second * BB + q]);
+			}
+			T->rp[i + 1] = (int64_t)T->ci.size();
+			for (int j : touched) slot[j] = -1;
+		}
+		return T;
+	}
+
 	// sparsematrix_impl.h:300-316 (alpha1 == 0 branch of axpy): first connection
 	// assigned, the others accumulated in ascending column order; empty row -> 0.
 	void apply(const Mat& A_, Vec& y, const Vec& x) override

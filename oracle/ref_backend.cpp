@@ -195,6 +195,17 @@ struct RefBackend : Backend {
 		return t;
 	}
 
+	Mat* rap(const Mat& R0, const Mat& A, const Mat& P0) override
+	{
+		const Mat& R = for_vec(R0, A.block); const Mat& P = for_vec(P0, A.block);
+		Mat* t = nullptr;
+#define CALL(B) { RMat<B>* m = new RMat<B>; m->nrows = R.nrows; m->ncols = P.ncols; m->block = B; \
+		m->A.resize_and_clear(R.nrows, P.ncols); ug::AddMultiplyOf(m->A, SM<B>(R), SM<B>(A), SM<B>(P)); m->A.defragment(); t = m; }
+		DISPATCH(A.block, CALL)
+#undef CALL
+		return t;
+	}
+
 	void apply(const Mat& A0, Vec& y, const Vec& x) override
 	{
 		const Mat& A = for_vec(A0, y.block);

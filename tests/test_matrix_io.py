@@ -109,7 +109,7 @@ def test_connection_viewer_vector_matches_reference_writer_bytes(tmp_path, ref):
 
 
 def test_connection_viewer_reader_equals_reference_reader(tmp_path, ref):
-    prob = pr.Problem(dim=3, num_refs=2, problem=pr.CONVDIFF) if hasattr(pr, "CONVDIFF") else pr.Problem(dim=3, num_refs=2)
+    prob = pr.Problem(dim=3, num_refs=2, problem=pr.CONVDIFF)
     A = prob.matrix(2)
     pos = _positions(prob, 2)
     _ref_write_matrix(ref, tmp_path / "ref.mat", A, pos, 3)

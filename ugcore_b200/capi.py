@@ -53,7 +53,7 @@ class SolverDesc(C.Structure):
 
 FIN_STORE, FIN_A_DIV_R, FIN_R_DIV_A, FIN_SQRT, FIN_CONV_START, FIN_CONV_UPDATE = range(6)
 SMOOTH_ADD_IN, SMOOTH_JACOBI, SMOOTH_ADD_OUT, SMOOTH_SC_ZERO = 1, 2, 4, 8
-FLAG_HOST_SCALARS, FLAG_NO_GRAPH, FLAG_NO_FUSED_JACOBI, FLAG_FINAL_LEVEL_DEFECT = 1, 2, 4, 8
+FLAG_HOST_SCALARS, FLAG_NO_GRAPH, FLAG_NO_FUSED_JACOBI, FLAG_FINAL_LEVEL_DEFECT, FLAG_RAP = 1, 2, 4, 8, 16
 
 # name -> (restype, argtypes); every symbol declared in include/ug4b200.h
 DEV_API = {
@@ -179,6 +179,7 @@ HOST_API = {
     "ug4b200_io_matrix_export": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ug4b200_io_matrix_free": (None, [c_vp]),
     "ug4b200_io_write_matrix": (c_int, [C.c_char_p, c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int]),
+    "ug4b200_host_rap": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.POINTER(c_vp)]),
     "ug4b200_io_vector_size": (c_int, [C.c_char_p, p_i64, p_int]),
     "ug4b200_io_read_vector": (c_int, [C.c_char_p, c_i64, c_vp, c_vp]),
     "ug4b200_io_write_vector": (c_int, [C.c_char_p, c_i64, c_vp, c_vp, c_int, c_int]),

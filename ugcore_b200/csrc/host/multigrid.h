@@ -16,6 +16,7 @@
 // the surface<->level copies (mg_solver_impl.hpp:211-217, 244-248) are device gathers.
 #pragma once
 #include "solvers.h"
+#include "sparse_util.h"
 
 namespace ug {
 
@@ -128,6 +129,10 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 	/// (mg_solver_impl.hpp:1954-1958) although no caller reads it; off by default
 	void set_compute_final_level_defect(bool b) { m_bFinalDefect = b; }
 	void set_fuse_jacobi(bool b) { m_bFuseJacobi = b; }
+	/// Galerkin coarse operators (mg_solver.h: set_rap; solver_util.lua:478 default false): the level
+	/// operators below the top level are not assembled but computed as A_{l-1} = R_l A_l P_l at init
+	/// (init_rap_operator, mg_solver_impl.hpp:828-1013) — only the transfers have to be handed over
+	void set_rap(bool b) { m_bRAP = b; }
 
 	// ---- what assembly hands over (replaces assemble_level_operator :526-752 and the cached
 	//      StdTransfer::prolongation()/restriction() :602-717) ----
@@ -155,6 +160,7 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 		if (!m_spPostSmootherPrototype) UG_THROW("GMG::init: PostSmoother not set.");
 		if (!m_spTransferPrototype) m_spTransferPrototype = make_sp<StdTransfer<TAlgebra> >();
 		ug4b200_ctx* ctx = GPUManager::ctx();
+		if (m_bRAP) init_rap_operator();
 		for (int lev = m_baseLev; lev <= m_topLev; ++lev) {
 			LevData& ld = level(lev);
 			if (!ld.A) {
@@ -280,6 +286,25 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 		if ((int)m_vLevData.size() <= lev) { const size_t o = m_vLevData.size(); m_vLevData.resize(lev + 1); for (size_t i = o; i < m_vLevData.size(); ++i) m_vLevData[i] = make_sp<LevData>(); }
 		return *m_vLevData[lev];
 	}
+	/// mg_solver_impl.hpp:828-1013 on a fully refined hierarchy: the top level is the surface matrix,
+	/// A_{l-1} += R_l A_l P_l (AddMultiplyOf, :959) downwards; host side, results are uploaded like
+	/// assembled level matrices.  Partitioned runs: the additive local matrices give additive coarse
+	/// matrices (R and P of a box partition are local), which is ugcore's parallel RAP without
+	/// vertical interfaces.
+	void init_rap_operator()
+	{
+		if (!level(m_topLev).A) level(m_topLev).A = m_spSurfaceMat;
+		for (int lev = m_topLev; lev > m_baseLev; --lev) {
+			LevData& lf = level(lev); LevData& lc = level(lev - 1);
+			if (!lf.P) UG_THROW("GMG::init_rap_operator: prolongation of level " << lev << " missing");
+			if (!lf.R) { lf.R = make_sp<GPUTransferMatrix>(); lf.R->set_as_transpose_of(*lf.P); }   // std_transfer_impl.h:694-695
+			SmartPtr<matrix_operator_type> Ac = make_sp<matrix_operator_type>();
+			Ac->resize_and_clear(lf.P->num_cols(), lf.P->num_cols());
+			AddMultiplyOf(static_cast<matrix_type&>(*Ac), *lf.R, static_cast<const matrix_type&>(*lf.A), *lf.P);
+			lc.A = Ac;
+		}
+	}
+
 	/// correction of a level; on the top level of a fully refined hierarchy this is the caller's c
 	vector_type& SC(int lev) { return (lev == m_topLev && m_pTopC) ? *m_pTopC : level(lev).sc; }
 	void materialize_sc(int lev)
@@ -430,6 +455,7 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 
 	int m_baseLev, m_topLev, m_cycleType, m_numPreSmooth, m_numPostSmooth;
 	bool m_bFinalDefect, m_bFuseJacobi;
+	bool m_bRAP = false;
 	SmartPtr<smoother_type> m_spPreSmootherPrototype, m_spPostSmootherPrototype;
 	SmartPtr<ILinearOperatorInverse<vector_type> > m_spBaseSolver;
 	SmartPtr<StdTransfer<TAlgebra> > m_spTransferPrototype;

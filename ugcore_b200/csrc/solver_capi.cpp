@@ -91,6 +91,7 @@ struct SolverImpl : SolverBase {
 		g->set_smoother(make_smoother(d.smoother, d.smoother_damp));
 		g->set_fuse_jacobi(!(d.flags & UG4B200_FLAG_NO_FUSED_JACOBI));
 		g->set_compute_final_level_defect((d.flags & UG4B200_FLAG_FINAL_LEVEL_DEFECT) != 0);
+		g->set_rap((d.flags & UG4B200_FLAG_RAP) != 0);
 		return g;
 	}
 	SmartPtr<ILinearOperatorInverse<vector_type> > make_base_solver()
@@ -368,6 +369,24 @@ int ug4b200_io_write_matrix(const char* filename, int format, int64_t nrows, int
 			if (nrows != ncols) UG_THROW("ConnectionViewer::WriteMatrix: a rectangular matrix needs the from / to form");
 			ConnectionViewer::WriteMatrix(std::string(filename), A, io_positions(positions, (size_t)nrows, dim), dim, precision);
 		}
+		return 0;
+	});
+}
+int ug4b200_host_rap(int64_t nc, int64_t nf, const int64_t* r_rowptr, const int* r_cols, const double* r_vals,
+                     const int64_t* a_rowptr, const int* a_cols, const double* a_vals,
+                     const int64_t* p_rowptr, const int* p_cols, const double* p_vals, ug4b200_host_matrix** out)
+{
+	*out = nullptr;
+	return guard([&] {
+		GPUSparseMatrix<double> R, A, P;
+		R.set_from_crs((size_t)nc, (size_t)nf, r_rowptr, r_cols, r_vals);
+		A.set_from_crs((size_t)nf, (size_t)nf, a_rowptr, a_cols, a_vals);
+		P.set_from_crs((size_t)nf, (size_t)nc, p_rowptr, p_cols, p_vals);
+		std::unique_ptr<ug4b200_host_matrix> m(new ug4b200_host_matrix);
+		m->A.resize_and_clear((size_t)nc, (size_t)nc);
+		AddMultiplyOf(m->A, R, A, P);
+		m->pos.resize(0);
+		*out = m.release();
 		return 0;
 	});
 }

@@ -132,6 +132,11 @@ class Solver:
     def __init__(self, desc: dict, A, levels: dict | None = None, flags: int = 0):
         host_init()
         self.block = A.block
+        pc = desc.get("precond")
+        # gmg:set_rap(true): the level operators below the top level are Galerkin products computed at init
+        rap = isinstance(pc, dict) and bool(pc.get("rap", False))
+        if rap:
+            flags |= capi.FLAG_RAP
         self.desc = make_desc(desc, self.block, flags)
         self.h = C.c_void_p()
         check_host(host.ug4b200_solver_create(C.byref(self.desc), C.byref(self.h)))
@@ -141,9 +146,11 @@ class Solver:
         if levels:
             for lev, (Al, Pl, Rl) in sorted(levels.items()):
                 top = lev == self.desc.top_lev
+                skip = top or rap or Al is None          # the top level reuses the surface matrix
+                nrows = Al.nrows if Al is not None else (Pl.nrows if Pl else levels[lev + 1][1].ncols)
                 check_host(host.ug4b200_solver_set_level(
-                    self.h, lev, Al.nrows,
-                    None if top else _ptr(Al.rowptr), None if top else _ptr(Al.cols), None if top else _ptr(Al.vals),
+                    self.h, lev, nrows,
+                    None if skip else _ptr(Al.rowptr), None if skip else _ptr(Al.cols), None if skip else _ptr(Al.vals),
                     Pl.ncols if Pl else 0,
                     _ptr(Pl.rowptr) if Pl else None, _ptr(Pl.cols) if Pl else None, _ptr(Pl.vals) if Pl else None,
                     _ptr(Rl.rowptr) if Rl else None, _ptr(Rl.cols) if Rl else None, _ptr(Rl.vals) if Rl else None))
