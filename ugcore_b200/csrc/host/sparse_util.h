@@ -10,7 +10,7 @@
 // the result is uploaded like an assembled level matrix).  The triple loop is the reference's:
 // for row i, for A_ik != 0, for B_kl != 0: ab = A_ik * B_kl; for C_lj != 0: M_ij += ab * C_lj — the
 // same accumulation order, so the coarse matrices are bit-identical to ugcore's
-// (tests/test_rap.py against the reference's own AddMultiplyOf compiled into oracle/_ref).
+// (tests/test_rap.py checks them against the reference's own AddMultiplyOf, compiled for the tests).
 // Rows are independent: OpenMP over i, each thread with its own sparse accumulator.
 // A and C are scalar matrices (transfers: for block algebras ugcore stores the scalar on the
 // block diagonal, which multiplies every component of the block), B and M carry blocks.
