@@ -8,6 +8,10 @@ GMG V(2,2) damped Jacobi (0.66) preconditioning CG, StdConvCheck(100, 1e-12, 1e-
           configs[2]: 257^3 = 16 974 593 DoF), interface exchange + all-reduce over NCCL.
 Prints ONE JSON line (see the contract in the task description / DESIGN.md §Measurement).
 
+`--workload convdiff` / `--workload elasticity` run BASELINE configs[3] / configs[4] instead (BiCGStab +
+GMG with multicolour Gauss-Seidel on upwind convection-diffusion; CG + GMG block-Jacobi on 3x3-block
+linear elasticity), same JSON contract, own metric names; the default stays configs[1] / configs[2].
+
 `--impl reference` times ugcore's own CPU kernels (oracle/_ref: SparseMatrix/Vector/
 smoother templates compiled from the reference) driving the restated solver loop on ALL
 host cores: the reference has no threading on this path and no MPI is installed, so every
@@ -35,11 +39,33 @@ UNIT = "MDoF/s"
 PART = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 
 
-def solver_desc(top, base=0):
+def solver_desc(top, base=0, workload="poisson"):
+    if workload == "convdiff":     # BASELINE configs[3]: BiCGStab + GMG V(2,2), (multicolour) Gauss-Seidel smoothing
+        return {"type": "bicgstab",
+                "precond": {"type": "gmg", "topLevel": top, "baseLevel": base, "smoother": {"type": "gs", "relax": 1.0},
+                            "cycle": "V", "preSmooth": 2, "postSmooth": 2, "baseSolver": "lu"},
+                "convCheck": {"iterations": 100, "absolute": 1e-12, "reduction": 1e-8}}
+    red, its = (1e-8, 200) if workload == "elasticity" else (1e-10, 100)
     return {"type": "cg",
             "precond": {"type": "gmg", "topLevel": top, "baseLevel": base, "smoother": {"type": "jac", "damp": 0.66},
                         "cycle": "V", "preSmooth": 2, "postSmooth": 2, "baseSolver": "lu"},
-            "convCheck": {"iterations": 100, "absolute": 1e-12, "reduction": 1e-10}}
+            "convCheck": {"iterations": its, "absolute": 1e-12, "reduction": red}}
+
+
+def workload_spec(name):
+    """problem id and keyword arguments of the generator, block size, metric name, label"""
+    if name == "poisson":
+        return {"problem": 0, "kw": {}, "block": 1, "metric": METRIC,
+                "label": "3D Poisson", "method": "GMG V(2,2) damped-Jacobi(0.66) + CG, StdConvCheck(100, 1e-12, 1e-10)"}
+    if name == "convdiff":
+        return {"problem": 1, "kw": {"eps": 1e-1}, "block": 1, "metric": "convdiff3d_bicgstab_gmg_gs_mdof_per_s",
+                "label": "3D convection-diffusion (FV1 full upwind, eps = 0.1, b = (1, 0.5, 0.25))",
+                "method": "GMG V(2,2) multicolour Gauss-Seidel + BiCGStab, StdConvCheck(100, 1e-12, 1e-8)"}
+    if name == "elasticity":
+        return {"problem": 2, "kw": {}, "block": 3, "metric": "elasticity3d_gmg_cg_mdof_per_s",
+                "label": "3D linear elasticity (Q1, E = 1, nu = 0.3, 3x3 block-CRS)",
+                "method": "GMG V(2,2) damped block-Jacobi(0.66) + CG, StdConvCheck(200, 1e-12, 1e-8)"}
+    raise SystemExit(f"unknown workload {name}")
 
 
 def measured_peak_gbs():
@@ -97,20 +123,22 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def _cpu_replica(refs, steps, warmup, barrier, q):
-    """One CPU process = what one ugcore MPI rank does on this path: a serial GMG-CG solve with
-    the reference's own kernels (oracle/_ref) or the port."""
+def _cpu_replica(refs, steps, warmup, barrier, q, workload="poisson", base_mult=1):
+    """One CPU process = what one ugcore MPI rank does on this path: a serial solve with the
+    reference's own kernels (oracle/_ref) or the port.  Gauss-Seidel runs in ugcore's own
+    (lexicographic) order here — the multicolour order is a property of the GPU path."""
     os.environ["OMP_NUM_THREADS"] = "1"
     import oracle
     from ugcore_b200 import problems as pr
     kind = "ref" if oracle.have_ref() else "port"
     orc = oracle.Oracle(kind)
-    prob = pr.Problem(dim=3, num_refs=refs)
+    spec = workload_spec(workload)
+    prob = pr.Problem(dim=3, num_refs=refs, problem=spec["problem"], base=(base_mult,) * 3, **spec["kw"])
     lv = {}
     for l in range(0, refs + 1):
         lv[l] = (orc.matrix(prob.matrix(l)), orc.matrix(prob.prolongation(l)) if l else None,
                  orc.matrix(prob.restriction(l)) if l else None)
-    s = oracle.OSolver(orc, solver_desc(refs), lv[refs][0], lv)
+    s = oracle.OSolver(orc, solver_desc(refs, workload=workload), lv[refs][0], lv)
     b = np.array(prob.rhs())
     for _ in range(warmup):
         s.apply(b)
@@ -123,7 +151,7 @@ def _cpu_replica(refs, steps, warmup, barrier, q):
     q.put({"dt": dt, "its": len(h) - 1, "n": prob.num_dofs, "kind": kind, "hist": [float(v) for v in h]})
 
 
-def cpu_replicas(refs, nproc, steps, warmup):
+def cpu_replicas(refs, nproc, steps, warmup, workload="poisson", base_mult=1):
     """ugcore has no threads on this path and neither MPI nor boost exist here, so
     "all host cores" = nproc independent serial solves of the same workload running concurrently
     (they share the memory bus like MPI ranks would, but pay no interface exchange: an upper bound
@@ -131,7 +159,7 @@ def cpu_replicas(refs, nproc, steps, warmup):
     import multiprocessing as mp
     mpc = mp.get_context("spawn")
     barrier, q = mpc.Barrier(nproc), mpc.Queue()
-    procs = [mpc.Process(target=_cpu_replica, args=(refs, steps, warmup, barrier, q)) for _ in range(nproc)]
+    procs = [mpc.Process(target=_cpu_replica, args=(refs, steps, warmup, barrier, q, workload, base_mult)) for _ in range(nproc)]
     for p in procs:
         p.start()
     res = [q.get(timeout=3600) for _ in range(nproc)]
@@ -155,19 +183,20 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    refs = args.cpu_refs
+    refs = args.cpu_refs if args.cpu_refs is not None else args.refs
     nproc = args.cpu_procs or host_cores()
-    r = cpu_replicas(refs, nproc, args.steps, args.warmup)
+    spec = workload_spec(args.workload)
+    r = cpu_replicas(refs, nproc, args.steps, args.warmup, args.workload, args.base_mult)
     n, its, val, dt = r["n"], r["its"], r["value"], r["dt_per_step"]
-    sample = (f"{nproc} concurrent serial solves x {args.steps} steps of 3-D Poisson {2**refs + 1}^3 ({n} DoF, {its} CG "
+    nodes = args.base_mult * 2 ** refs + 1
+    sample = (f"{nproc} concurrent serial solves x {args.steps} steps of {spec['label']} {nodes}^3 nodes ({n} DoF, {its} "
               f"iterations each, {dt:.2f} s per solve): one process per host core, no threads inside ugcore on this path, "
               "no MPI on the box -> no interface exchange (upper bound of the MPI weak-scaling throughput)")
-    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    out = {"impl": "reference", "metric": spec["metric"], "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"3D Poisson unit cube hexahedra numRefs={refs} ({n} DoF per process, {nproc} processes) "
-                                  "GMG V(2,2) damped-Jacobi(0.66) + CG, StdConvCheck(100, 1e-12, 1e-10), base LU on level 0, "
-                                  "ugcore CPU kernels", "iterations": its},
+           "config": {"workload": f"{spec['label']} unit cube hexahedra numRefs={refs} ({n} DoF per process, {nproc} processes) "
+                                  f"{spec['method']}, base LU on level 0, ugcore CPU kernels", "iterations": its},
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": nproc, "kind": r["kind"], "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
@@ -250,11 +279,75 @@ def kernel_roofline(s, prob, top, peak_gbs, peak_src):
     return roof, extra
 
 
-def cpu_baseline_sample(refs):
+def workload_roofline(workload, prob, top, peak_gbs, peak_src):
+    """Dominant kernel of the non-default workloads, timed alone like kernel_roofline:
+    convdiff   — one forward multicolour Gauss-Seidel sweep over the colour-sorted top-level matrix
+                 (ug4b200_gs_step; a sweep reads every stored entry once: 12 nnz + 4(n+1) + 24 n bytes);
+    elasticity — y -= A x with 3x3 blocks (ug4b200_matrix_matmul_minus; (72+4) nnzb + 4(nb+1) + 72 nb bytes)."""
+    import ctypes as C
+    from ugcore_b200 import capi
+    from ugcore_b200.solver import host_ctx, DeviceBuffer
+    dev = capi.dev
+    ctx = host_ctx()
+    A = prob.matrix(top)
+    n, nnz, b = A.nrows, A.nnz, A.block
+    rng = np.random.default_rng(0)
+    e0, e1 = C.c_void_p(), C.c_void_p()
+    dev.ug4b200_event_create(ctx, C.byref(e0)); dev.ug4b200_event_create(ctx, C.byref(e1))
+
+    def timeit(fn, reps=20):
+        for _ in range(3):
+            fn()
+        dev.ug4b200_sync(ctx)
+        dev.ug4b200_event_record(ctx, e0)
+        for _ in range(reps):
+            fn()
+        dev.ug4b200_event_record(ctx, e1)
+        dev.ug4b200_event_sync(ctx, e1)
+        ms = C.c_float()
+        dev.ug4b200_event_elapsed_ms(ctx, e0, e1, C.byref(ms))
+        return ms.value / reps
+
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    m = C.c_void_p()
+    try:
+        if workload == "convdiff":
+            color = np.zeros(n, np.int32)
+            nc = C.c_int()
+            dev.ug4b200_color_greedy(n, vp(A.rowptr), vp(A.cols), vp(color), C.byref(nc))
+            order = np.argsort(color, kind="stable")
+            perm = np.empty(n, np.int64); perm[order] = np.arange(n)
+            cptr = np.concatenate([[0], np.cumsum(np.bincount(color, minlength=nc.value))]).astype(np.int64)
+            rows = np.repeat(np.arange(n), np.diff(A.rowptr))
+            pr_, pc_ = perm[rows], perm[A.cols]
+            key = np.lexsort((pc_, pr_))
+            rp = np.concatenate([[0], np.cumsum(np.bincount(pr_, minlength=n))]).astype(np.int64)
+            ci = pc_[key].astype(np.int32); va = np.ascontiguousarray(A.vals[key])
+            capi.check(dev.ug4b200_matrix_upload_crs(ctx, 1, n, n, vp(rp), vp(ci), vp(va), 0, C.byref(m)), ctx)
+            d, c = DeviceBuffer.from_numpy(rng.standard_normal(n)), DeviceBuffer.from_numpy(np.zeros(n))
+            t = timeit(lambda: dev.ug4b200_gs_step(ctx, m, cptr.size - 1, vp(cptr), 0, C.c_double(1.0), c.ptr, d.ptr))
+            nbytes = 12 * nnz + 4 * (n + 1) + 24 * n
+            kname = f"gs_color_kernel x {cptr.size - 1} colours (ug4b200_gs_step, forward sweep, plain SELL-32 stream)"
+        else:
+            capi.check(dev.ug4b200_matrix_upload_crs(ctx, b, n, n, vp(A.rowptr), vp(A.cols), vp(A.vals), 0, C.byref(m)), ctx)
+            y, x = DeviceBuffer.from_numpy(rng.standard_normal(n * b)), DeviceBuffer.from_numpy(rng.standard_normal(n * b))
+            t = timeit(lambda: dev.ug4b200_matrix_matmul_minus(ctx, m, y.ptr, x.ptr, b))
+            nbytes = (8 * b * b + 4) * nnz + 4 * (n + 1) + 3 * 8 * b * n
+            kname = f"spmvB_kernel<{b}> (ug4b200_matrix_matmul_minus, {b}x{b} blocks)"
+        gbs = nbytes / (t * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": kname, "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs,
+                "peak_source": peak_src, "traffic": None, "bytes_per_launch": nbytes, "ms_per_launch": t}
+    finally:
+        dev.ug4b200_event_destroy(ctx, e0); dev.ug4b200_event_destroy(ctx, e1)
+        if m:
+            dev.ug4b200_matrix_destroy(ctx, m)
+
+
+def cpu_baseline_sample(refs, workload="poisson", base_mult=1):
     """Bounded CPU sample for the default run: the SAME workload solved once by every host core
     concurrently with the reference's kernels (~10-30 s including set-up)."""
     nproc = host_cores()
-    r = cpu_replicas(refs, nproc, 1, 0)
+    r = cpu_replicas(refs, nproc, 1, 0, workload, base_mult)
     serial_equiv = r["n"] / r["dt_per_step"] / 1e6
     return {"value": r["value"], "unit": UNIT, "cores": nproc, "kind": r["kind"],
             "sample": f"{nproc} concurrent serial solves of the same workload ({r['n']} DoF, {r['its']} CG iterations, "
@@ -284,24 +377,30 @@ def run_ours(args):
     ctx = S.host_ctx()
     dev = capi.dev
     refs = args.refs
-    desc = solver_desc(refs)
+    spec = workload_spec(args.workload)
+    default_workload = args.workload == "poisson" and args.base_mult == 1
+    desc = solver_desc(refs, workload=args.workload)
+    bm = args.base_mult
 
     if world > 1:
         import torch.distributed as dist
         from ugcore_b200 import dist as ugdist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         part = PART[world]
-        prob, s = ugdist.build_partitioned_solver(desc, refs, part, rank, dist)
+        extra = dict(spec["kw"])
+        if bm != 1:
+            extra["base_mult"] = bm
+        prob, s = ugdist.build_partitioned_solver(desc, refs, part, rank, dist, problem=spec["problem"], **extra)
         barrier = lambda: (dist.barrier(), torch.cuda.synchronize())
     else:
         part = (1, 1, 1)
-        prob = pr.Problem(dim=3, num_refs=refs)
+        prob = pr.Problem(dim=3, num_refs=refs, problem=spec["problem"], base=(bm,) * 3, **spec["kw"])
         s = S.Solver.from_problem(desc, prob)
         barrier = lambda: torch.cuda.synchronize()
     s.init()
     n_local = prob.num_dofs
-    dims = [part[d] * 2 ** refs + 1 for d in range(3)]
-    n_global = dims[0] * dims[1] * dims[2]
+    dims = [part[d] * bm * 2 ** refs + 1 for d in range(3)]
+    n_global = dims[0] * dims[1] * dims[2] * spec["block"]
 
     b_host = torch.from_numpy(np.array(prob.rhs())).pin_memory()
     x_host = torch.zeros(n_local, dtype=torch.float64).pin_memory()
@@ -349,28 +448,35 @@ def run_ours(args):
     if rank != 0:
         return
     peak, peak_src = measured_peak_gbs()
-    out = {"metric": METRIC, "value": n_global / (ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+    top = prob.matrix(refs)
+    top_gb = (8 * spec["block"] ** 2 + 4) * top.nnz / 1e9
+    nodes = f"{dims[0]}x{dims[1]}x{dims[2]}" + (f" nodes x {spec['block']}" if spec["block"] > 1 else "")
+    out = {"metric": spec["metric"], "value": n_global / (ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"3D Poisson unit-cell hexahedra numRefs={refs}, {dims[0]}x{dims[1]}x{dims[2]} = {n_global} DoF "
-                                  f"({n_local} per GPU, boxes {part[0]}x{part[1]}x{part[2]}), GMG V(2,2) damped-Jacobi(0.66) + CG, "
-                                  "StdConvCheck(100, 1e-12, 1e-10), base LU on level 0",
-                      "iterations": its, "solve_s": ms * 1e-3, "l2_policy": "inputs larger than L2 (top-level matrix 0.69 GB per GPU)",
+           "config": {"workload": f"{spec['label']} unit-cell hexahedra numRefs={refs}, {nodes} = {n_global} DoF "
+                                  f"({n_local} per GPU, boxes {part[0]}x{part[1]}x{part[2]}), {spec['method']}, base LU on level 0",
+                      "iterations": its, "solve_s": ms * 1e-3,
+                      "l2_policy": f"inputs larger than L2 (top-level matrix {top_gb:.2f} GB per GPU)",
                       "wall_ms_per_step": wall_ms, "final_reduction": float(hist[-1] / hist[0]) if len(hist) else None},
            "e2e": {"value": n_global / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 16 * n_local,
                    "d2h_bytes_per_step": 8 * n_local, "ms_per_step": ms_e2e, "wall_ms_per_step": wall_e2e},
            "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": int(launches), "clocks": clocks}
     if world == 1:
-        roof, extra = kernel_roofline(s, prob, refs, peak, peak_src)
-        out["roofline"] = roof
-        out["roofline_other_kernels"] = extra
-        # whole-solve figure against the unfused reference sequence (~2.9 kB per fine DoF per iteration)
-        out["solve_algorithmic_gbs_vs_unfused"] = 2.9e3 * n_global * max(its, 1) / (ms * 1e-3) / 1e9
+        if args.workload == "poisson":
+            roof, extra = kernel_roofline(s, prob, refs, peak, peak_src)
+            out["roofline"] = roof
+            out["roofline_other_kernels"] = extra
+            # whole-solve figure against the unfused reference sequence (~2.9 kB per fine DoF per iteration)
+            out["solve_algorithmic_gbs_vs_unfused"] = 2.9e3 * n_global * max(its, 1) / (ms * 1e-3) / 1e9
+        else:
+            out["roofline"] = workload_roofline(args.workload, prob, refs, peak, peak_src)
         if not args.no_cpu_baseline:
-            cb, h_cpu = cpu_baseline_sample(refs)
+            cb, h_cpu = cpu_baseline_sample(refs, args.workload, bm)
             out["cpu_baseline"] = cb
-            k = min(len(h_cpu), len(hist))
-            out["config"]["history_rel_err_vs_cpu"] = float(np.max(np.abs(hist[:k] - h_cpu[:k]) / np.abs(h_cpu[:k])))
+            if args.workload != "convdiff":   # the CPU arm sweeps in ugcore's lexicographic order: another smoother
+                k = min(len(h_cpu), len(hist))
+                out["config"]["history_rel_err_vs_cpu"] = float(np.max(np.abs(hist[:k] - h_cpu[:k]) / np.abs(h_cpu[:k])))
             out["config"]["iterations_cpu"] = len(h_cpu) - 1
     print(json.dumps(out), flush=True)
 
@@ -382,7 +488,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--refs", type=int, default=7, help="refinements per GPU sub-box (7 -> 129^3)")
-    ap.add_argument("--cpu-refs", type=int, default=7, help="workload of the CPU reference arm")
+    ap.add_argument("--cpu-refs", type=int, default=None, help="refinements of the CPU reference arm (default: --refs)")
+    ap.add_argument("--workload", default="poisson", choices=["poisson", "convdiff", "elasticity"],
+                    help="poisson: BASELINE configs[1]/[2] (default); convdiff: configs[3]; elasticity: configs[4]")
+    ap.add_argument("--base-mult", type=int, default=1, help="base-grid elements per GPU and direction "
+                    "(--workload elasticity --base-mult 3 --refs 5: 97^3 nodes per GPU, 193^3 x 3 = 21.6 M DoF on 8 GPUs)")
     ap.add_argument("--cpu-procs", type=int, default=0, help="processes of the CPU arm (0 = all host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -82,6 +82,17 @@ int ug4b200_solver_set_coloring(ug4b200_solver* s, int lev, int64_t n, const int
 /* horizontal interfaces of level lev (lev = top level also serves the Krylov vectors) */
 int ug4b200_solver_set_layouts(ug4b200_solver* s, int lev, int nneigh, const int* neigh_rank, const int64_t* neigh_ptr,
                                const int* indices, int64_t nlocal);
+/* partitioned Gauss-Seidel smoothing on level lev (the top level also serves a Gauss-Seidel used directly as
+ * preconditioner): the level matrix made CONSISTENT on the interface rows, i.e. every copy of an
+ * interface row holds the sum over the ranks of the entries whose two DoFs the rank holds — what
+ * GaussSeidelBase::preprocess obtains from MakeConsistent(*pOp, m_A)
+ * (ugbase/lib_algebra/operator/preconditioner/gauss_seidel.h:134-142,
+ * ugbase/lib_algebra/parallelization/parallel_matrix_overlap_impl.h:438-459).  ugcore exchanges the rows
+ * over MPI inside preprocess; here the caller exchanges them on the host at init
+ * (ugcore_b200/dist.py: make_consistent).  The rows of h-slaves are set to Dirichlet rows by the
+ * smoother itself.  Same pattern as the additive level matrix. */
+int ug4b200_solver_set_smoother_matrix(ug4b200_solver* s, int lev, int64_t nrows, const int64_t* rowptr, const int* cols,
+                                       const double* vals);
 /* gathered base solve: global base-level matrix and the local -> global index map */
 int ug4b200_solver_set_gathered_base(ug4b200_solver* s, int64_t nrows, const int64_t* rowptr, const int* cols,
                                      const double* vals, int64_t nlocal, const int* local_to_global);

@@ -99,6 +99,7 @@ class Oracle:
         L.oracle_solver_create.argtypes = [C.POINTER(SolverDesc)]
         L.oracle_solver_destroy.argtypes = [C.c_void_p]
         L.oracle_solver_set_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_solver_set_smoother_matrix.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.oracle_solver_init.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_solver_apply.argtypes = [C.c_void_p, _dp, _dp, C.c_int]
         L.oracle_solver_steps.argtypes = [C.c_void_p]
@@ -277,7 +278,7 @@ def make_desc(desc: dict) -> SolverDesc:
 class OSolver:
     """Solver built from a descriptor; ``levels`` maps level -> (A, P, R) OMat triples."""
 
-    def __init__(self, orc: Oracle, desc: dict, A: OMat, levels: dict | None = None):
+    def __init__(self, orc: Oracle, desc: dict, A: OMat, levels: dict | None = None, smoother_matrices: dict | None = None):
         self.o = orc
         self.desc = make_desc(desc)
         self.h = orc.lib.oracle_solver_create(C.byref(self.desc))
@@ -288,6 +289,10 @@ class OSolver:
         if levels:
             for lev, (Al, Pl, Rl) in levels.items():
                 orc._chk(orc.lib.oracle_solver_set_level(self.h, lev, Al.h, Pl.h if Pl else None, Rl.h if Rl else None))
+        if smoother_matrices:   # level -> OMat the smoothers of that level are initialised with (parallel GS emulation)
+            self._keep.append(smoother_matrices)
+            for lev, S in smoother_matrices.items():
+                orc._chk(orc.lib.oracle_solver_set_smoother_matrix(self.h, lev, S.h))
         orc._chk(orc.lib.oracle_solver_init(self.h, A.h))
 
     def __del__(self):

@@ -81,6 +81,9 @@ oracle_solver* oracle_solver_create(const oracle_solver_desc* d);
 void oracle_solver_destroy(oracle_solver* s);
 /* GMG level operators; P, R may be NULL on the base level. Matrices stay owned by the caller. */
 int oracle_solver_set_level(oracle_solver* s, int lev, const oracle_mat* A, const oracle_mat* P, const oracle_mat* R);
+/* matrix the smoothers of GMG level lev are initialised with instead of the level operator (ugcore's
+ * parallel Gauss-Seidel smooths with its own consistent matrix, gauss_seidel.h:134-142) */
+int oracle_solver_set_smoother_matrix(oracle_solver* s, int lev, const oracle_mat* S);
 int oracle_solver_init(oracle_solver* s, const oracle_mat* A);
 /* x: in = start iterate, out = solution; b is not modified.  Returns 0 on success
  * (converged), 1 if the convergence check failed, <0 on error. */

@@ -221,6 +221,14 @@ int oracle_solver_set_level(oracle_solver* s, int lev, const oracle_mat* A, cons
 		return 0;
 	});
 }
+int oracle_solver_set_smoother_matrix(oracle_solver* s, int lev, const oracle_mat* S)
+{
+	return guard([&] {
+		if (!s->gmg) throw std::runtime_error("solver has no GMG preconditioner");
+		s->gmg->set_level_smoother_matrix(lev, S->m.get());
+		return 0;
+	});
+}
 int oracle_solver_init(oracle_solver* s, const oracle_mat* A)
 {
 	return guard([&] {

@@ -242,6 +242,13 @@ void GMG::set_level(int level, const Mat* A, const Mat* P, const Mat* R)
 	ld.A = A; ld.P = P; ld.R = R;
 }
 
+void GMG::set_level_smoother_matrix(int level, const Mat* S)
+{
+	if (level < baseLev || level > topLev) throw std::runtime_error("GMG::set_level_smoother_matrix: level out of range");
+	if ((int)lev.size() != topLev - baseLev + 1) lev.resize(topLev - baseLev + 1);
+	L(level).S = S;
+}
+
 // init(): mg_solver_impl.hpp:378-496 — level memory, smoother clones + init
 // (:1135-1169), base solver init (:1171-1229); level operators are handed in
 // re-discretised (assemble_level_operator :526-752, rap = false).
@@ -261,7 +268,8 @@ bool GMG::init(const Mat& A_)
 			if (!ld.P || !ld.R) throw std::runtime_error("GMG::init: transfer missing");
 			ld.pre.reset(smootherProto->clone());
 			ld.post.reset(smootherProto->clone());
-			if (!ld.pre->init(*ld.A) || !ld.post->init(*ld.A)) return false;
+			const Mat& S = ld.S ? *ld.S : *ld.A;
+			if (!ld.pre->init(S) || !ld.post->init(S)) return false;
 		}
 	}
 	return baseSolver->init(*L(baseLev).A);

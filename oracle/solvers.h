@@ -156,6 +156,10 @@ struct GMG : LinearIterator {
 		const Mat* A = nullptr;
 		const Mat* P = nullptr; // level-1 -> level
 		const Mat* R = nullptr; // level -> level-1
+		const Mat* S = nullptr; // matrix the smoothers are initialised with (nullptr: A).  ugcore's parallel
+		                        // Gauss-Seidel smooths with its own matrix m_A (gauss_seidel.h:134-142, 225-231):
+		                        // in global terms the level matrix without the couplings between DoFs of
+		                        // different h-masters — tests hand that matrix in here
 		VecP sc, sd, st;
 		std::unique_ptr<LinearIterator> pre, post;
 	};
@@ -171,6 +175,7 @@ struct GMG : LinearIterator {
 	explicit GMG(Backend& b) : LinearIterator(b) {}
 	const char* name() const override { return "Geometric MultiGrid"; }
 	void set_level(int level, const Mat* A, const Mat* P, const Mat* R);
+	void set_level_smoother_matrix(int level, const Mat* S);
 	LevData& L(int l) { return lev[l - baseLev]; }
 	bool init(const Mat& A_) override;
 	bool apply(Vec& c, const Vec& d) override;

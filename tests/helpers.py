@@ -92,3 +92,129 @@ def make_rhs(prob, seed=None):
     mask = np.repeat(prob.dirichlet() != 0, prob.block)
     b[mask] = 0.0
     return b
+
+
+# ---- colour-sorted orderings and the serial emulation of ugcore's parallel Gauss-Seidel ----
+
+def greedy_color_perm(A):
+    """The ordering the library's Gauss-Seidel uses without a user colouring: greedy first-fit
+    colouring of the stored pattern in row order (host helper of the C ABI), colours sorted,
+    stable inside a colour.  Returns (perm old -> new, colour offsets)."""
+    from ugcore_b200 import capi
+    n = A.nrows
+    color = np.zeros(max(n, 1), np.int32)
+    nc = C.c_int()
+    capi.dev.ug4b200_color_greedy(n, A.rowptr.ctypes.data_as(C.c_void_p), A.cols.ctypes.data_as(C.c_void_p),
+                                  color.ctypes.data_as(C.c_void_p), C.byref(nc))
+    color = color[:n]
+    order = np.argsort(color, kind="stable")
+    perm = np.empty(n, np.int64)
+    perm[order] = np.arange(n)
+    cptr = np.concatenate([[0], np.cumsum(np.bincount(color, minlength=nc.value))]).astype(np.int64)
+    return perm, cptr
+
+
+def permute_crs(A, prow, pcol, keep=None):
+    """B(prow[r], pcol[c]) = A(r, c); explicit zeros kept, columns sorted.  keep: boolean mask over
+    the stored entries (dropped entries disappear from the pattern)."""
+    from ugcore_b200.problems import Crs
+    bb = A.block * A.block
+    rows = np.repeat(np.arange(A.nrows), np.diff(A.rowptr))
+    cols = np.asarray(A.cols)
+    vals = np.asarray(A.vals).reshape(-1, bb)
+    if keep is not None:
+        rows, cols, vals = rows[keep], cols[keep], vals[keep]
+    pr_, pc_ = np.asarray(prow)[rows], np.asarray(pcol)[cols]
+    key = np.lexsort((pc_, pr_))
+    rp = np.concatenate([[0], np.cumsum(np.bincount(pr_, minlength=A.nrows))]).astype(np.int64)
+    return Crs(A.nrows, A.ncols, A.block, rp, pc_[key].astype(np.int32), vals[key].ravel().copy())
+
+
+def with_dirichlet_rows(A, rows):
+    """SetDirichletRow (sparsematrix_util.h:878-897): all blocks of the rows 0, diagonal block 1."""
+    from ugcore_b200.problems import Crs
+    b, bb = A.block, A.block * A.block
+    vals = np.array(A.vals, dtype=np.float64).reshape(-1, bb)
+    for r in rows:
+        lo, hi = A.rowptr[r], A.rowptr[r + 1]
+        vals[lo:hi] = 0.0
+        d = lo + int(np.flatnonzero(np.asarray(A.cols[lo:hi]) == r)[0])
+        for t in range(b):
+            vals[d, t + b * t] = 1.0
+    return Crs(A.nrows, A.ncols, A.block, np.array(A.rowptr), np.array(A.cols), vals.ravel().copy())
+
+
+def parallel_gs_global_model(locals_, gprob, lev):
+    """ugcore's parallel Gauss-Seidel (gauss_seidel.h:134-142, 204-215) on one partitioned level, in
+    GLOBAL terms.  Every rank sweeps over its consistent matrix with the h-slave rows set to Dirichlet
+    rows, on the unique defect; the slaves' corrections are exactly 0.  Hence one step is a sweep over the
+    global matrix without the couplings between DoFs of different h-masters, in any global order that
+    keeps, inside each master's block, the order of that rank's sweep (its colour-sorted local order).
+
+    locals_: the ranks' local problems in rank order.  Returns (gperm: global id -> position,
+    keep: mask over the stored entries of the global level matrix)."""
+    from ugcore_b200 import dist as ugdist
+    gA = gprob.matrix(lev)
+    owner = np.full(gA.nrows, -1, np.int64)
+    order = []
+    for r, p in enumerate(locals_):
+        gid = p.global_ids(lev)
+        own = ugdist.owned_mask(p, lev, r)
+        assert np.all(owner[gid[own]] == -1)
+        owner[gid[own]] = r
+        perm, _ = greedy_color_perm(p.matrix(lev))          # pattern only: the Dirichlet rows keep theirs
+        inv = np.empty_like(perm)
+        inv[perm] = np.arange(perm.size)
+        order.append(gid[inv][own[inv]])                    # owned DoFs in the order of the local sweep
+    assert np.all(owner >= 0)
+    order = np.concatenate(order)
+    gperm = np.empty(gA.nrows, np.int64)
+    gperm[order] = np.arange(gA.nrows)
+    rows = np.repeat(np.arange(gA.nrows), np.diff(gA.rowptr))
+    keep = owner[rows] == owner[np.asarray(gA.cols)]
+    return gperm, keep
+
+
+def partitioned_gs_oracle(orc, desc, refs, part, gather, problem=0, **kw):
+    """Serial oracle of the partitioned GMG with Gauss-Seidel smoothing: levels above `gather` smooth
+    like ugcore's parallel Gauss-Seidel (parallel_gs_global_model), the gathered levels below run the
+    serial multicolour sweep on the global matrices.  Everything is permuted into the sweep order
+    (the oracle's Gauss-Seidel is the reference's lexicographic gs_step over the matrix it is given).
+    Returns (solve(b_global) -> (x_global, ok, history), global problem)."""
+    import oracle
+    from ugcore_b200 import dist as ugdist
+    world = part[0] * part[1] * part[2]
+    base = desc["precond"].get("baseLevel", 0)
+    locals_ = [ugdist.local_problem(refs, part, r, problem=problem, **kw) for r in range(world)]
+    gprob = ugdist.global_problem(refs, part, problem=problem, **kw)
+    perms, keeps = {}, {}
+    for l in range(base, refs + 1):
+        if l > gather:
+            perms[l], keeps[l] = parallel_gs_global_model(locals_, gprob, l)
+        elif l > base:
+            perms[l], _ = greedy_color_perm(gprob.matrix(l))
+        else:
+            perms[l] = np.arange(gprob.matrix(l).nrows)
+    lv, sm = {}, {}
+    for l in range(base, refs + 1):
+        A = orc.matrix(permute_crs(gprob.matrix(l), perms[l], perms[l]))
+        P = R = None
+        if l > base:
+            P = orc.matrix(permute_crs(gprob.prolongation(l), perms[l], perms[l - 1]))
+            R = orc.matrix(permute_crs(gprob.restriction(l), perms[l - 1], perms[l]))
+        lv[l] = (A, P, R)
+        if l in keeps:
+            sm[l] = orc.matrix(permute_crs(gprob.matrix(l), perms[l], perms[l], keep=keeps[l]))
+    d = dict(desc)
+    d["precond"] = dict(desc["precond"], topLevel=refs, baseLevel=base)
+    osol = oracle.OSolver(orc, d, lv[refs][0], lv, smoother_matrices=sm)
+    b = gprob.block
+    top = np.repeat(perms[refs] * b, b) + np.tile(np.arange(b), perms[refs].size)   # component-wise permutation
+
+    def solve(bg):
+        bp = np.empty_like(bg)
+        bp[top] = bg
+        xp, ok, h = osol.apply(bp)
+        return xp[top], ok, h
+
+    return solve, gprob

@@ -1,5 +1,15 @@
-"""torchrun entry of the multi-GPU parity test: partitioned GMG-CG on N GPUs vs the SERIAL
-oracle on the same global grid (same math up to summation order)."""
+"""torchrun entry of the multi-GPU parity tests: a partitioned solve on N GPUs vs the SERIAL oracle
+on the same global grid.
+
+  argv: refs flags [case]
+  case "poisson" (default)  GMG V(2,2) Jacobi + CG on 3-D Poisson: same math as the serial solver up to
+                            summation order -> compared with the plain serial oracle
+  case "elasticity"         the same with 3x3 blocks (block Jacobi, interface exchange of blocks)
+  case "convdiff_gs"        BiCGStab + GMG with Gauss-Seidel smoothing on upwind convection-diffusion:
+                            ugcore's parallel Gauss-Seidel is a block Jacobi over the ranks with GS inside
+                            (gauss_seidel.h:134-142, 204-215) -> compared with the serial oracle of exactly
+                            that method (helpers.partitioned_gs_oracle)
+"""
 import json
 import os
 import sys
@@ -15,28 +25,43 @@ def main():
     import torch
     import torch.distributed as dist
     import oracle
-    from helpers import gmg_desc, oracle_levels, rel_hist_err
-    from ugcore_b200 import dist as ugdist, solver as S
+    from helpers import gmg_desc, oracle_levels, partitioned_gs_oracle, rel_hist_err
+    from ugcore_b200 import dist as ugdist, problems as pr, solver as S
 
     refs = int(sys.argv[1]) if len(sys.argv) > 1 else 3
     flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    case = sys.argv[3] if len(sys.argv) > 3 else "poisson"
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     S.host_init(lr, None)
     part = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
-    desc = gmg_desc(refs)
-    prob, s = ugdist.build_partitioned_solver(desc, refs, part, rank, dist, flags=flags)
+    orc = oracle.Oracle("ref" if oracle.have_ref() else "port")
+    block = 1
+    if case == "poisson":
+        problem, kw, desc = pr.POISSON, {}, gmg_desc(refs)
+    elif case == "elasticity":
+        problem, kw, desc, block = pr.ELASTICITY, {}, gmg_desc(refs, reduction=1e-8, its=200), 3
+    elif case == "convdiff_gs":
+        problem, kw = pr.CONVDIFF, {"eps": 1e-1}
+        desc = gmg_desc(refs, solver="bicgstab", smoother={"type": "gs", "relax": 1.0}, reduction=1e-8)
+    else:
+        raise SystemExit(f"unknown case {case}")
+    prob, s = ugdist.build_partitioned_solver(desc, refs, part, rank, dist, problem=problem, flags=flags, **kw)
     x, ok, h = s.apply(prob.rhs())
 
-    gprob = ugdist.global_problem(refs, part)
-    orc = oracle.Oracle("ref" if oracle.have_ref() else "port")
-    lv = oracle_levels(orc, gprob)
-    xo, oko, ho = oracle.OSolver(orc, desc, lv[refs][0], lv).apply(gprob.rhs())
+    if case == "convdiff_gs":
+        solve, gprob = partitioned_gs_oracle(orc, desc, refs, part, s.desc.gather_lev, problem=problem, **kw)
+        xo, oko, ho = solve(np.array(gprob.rhs()))
+    else:
+        gprob = ugdist.global_problem(refs, part, problem=problem, **kw)
+        lv = oracle_levels(orc, gprob)
+        xo, oko, ho = oracle.OSolver(orc, desc, lv[refs][0], lv).apply(gprob.rhs())
     gid = prob.global_ids(refs)
+    g = np.repeat(gid * block, block) + np.tile(np.arange(block), gid.size)
     from ugcore_b200 import capi
     res = {"rank": rank, "p2p": bool(capi.dev.ug4b200_p2p_enabled(S.host_ctx())), "ok": bool(ok), "oracle_ok": bool(oko), "its": len(h) - 1, "its_oracle": len(ho) - 1,
-           "hist_err": rel_hist_err(h, ho), "sol_err": float(np.linalg.norm(x - xo[gid]) / np.linalg.norm(xo[gid]))}
+           "hist_err": rel_hist_err(h, ho), "sol_err": float(np.linalg.norm(x - xo[g]) / np.linalg.norm(xo[g]))}
     out = [None] * world
     dist.all_gather_object(out, res)
     if rank == 0:

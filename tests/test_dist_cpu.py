@@ -69,6 +69,15 @@ def _worker(rank, world, port, q):
                 cg = prob.global_ids(lev - 1)
                 xc = rng.standard_normal(gP.shape[1])
                 assert np.allclose(P @ xc[cg], (gP @ xc)[gid], rtol=1e-14, atol=1e-14)
+        # MakeConsistent over the real transport (all_gather_object): interior rows of the consistent
+        # matrix are the rows of the serially assembled matrix restricted to the local DoFs
+        for lev in range(1, refs + 1):
+            ranks, ptr, idx = ugdist.interfaces(prob, lev)
+            Ac = ugdist.make_consistent(prob.matrix(lev), rank, ranks, ptr, idx, dist)
+            gid = prob.global_ids(lev)
+            G = gprob.matrix(lev).to_scipy()[gid][:, gid].toarray()
+            interior = prob.dirichlet(lev) == 0
+            assert np.array_equal(Ac.to_scipy().toarray()[interior], G[interior])
         # gathered base: local level-0 DoFs map into the global base numbering
         l2g = prob.global_ids(0)
         assert l2g.size == 8 and set(l2g) <= set(range(12))
@@ -112,3 +121,89 @@ def test_interfaces_2x2x2_symmetry():
         assert np.array_equal(g, lists[(s, r)])
     owned = sum(int(ugdist.owned_mask(p, refs, r).sum()) for r, p in enumerate(probs))
     assert owned == (2 * 2 ** refs + 1) ** 3
+
+
+def _comp(idx, b):
+    idx = np.asarray(idx)
+    return np.repeat(idx * b, b) + np.tile(np.arange(b), idx.size)
+
+
+@pytest.mark.parametrize("problem", [0, 1, 2])
+@pytest.mark.parametrize("part", [(2, 1, 1), (2, 2, 2)])
+def test_make_consistent_and_parallel_gs_model(problem, part):
+    """Host logic of the partitioned Gauss-Seidel smoother, all ranks emulated in one process:
+    (1) dist.consistent_contributions / apply_contributions (ugcore: MakeConsistent) reproduce the rows of
+        the serially assembled matrix; Dirichlet rows carry the multiplicity like in ugcore;
+    (2) the global model the multi-GPU parity test solves with the serial oracle (helpers.
+        parallel_gs_global_model) equals the rank-by-rank sweep of gauss_seidel.h:134-142, 204-215 —
+        bit for bit for scalar problems."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle
+    from helpers import greedy_color_perm, parallel_gs_global_model, permute_crs, with_dirichlet_rows
+    from ugcore_b200 import dist as ugdist
+    orc = oracle.Oracle("port")
+    refs = lev = 2
+    world = part[0] * part[1] * part[2]
+    locs = [ugdist.local_problem(refs, part, r, problem=problem) for r in range(world)]
+    gprob = ugdist.global_problem(refs, part, problem=problem)
+    b = gprob.block
+    gA = gprob.matrix(lev)
+    G = gA.to_scipy()
+    ifs = [ugdist.interfaces(p, lev) for p in locs]
+    sent = [ugdist.consistent_contributions(p.matrix(lev), *ifs[r]) for r, p in enumerate(locs)]
+    cons = []
+    for r, p in enumerate(locs):
+        ranks, ptr, idx = ifs[r]
+        A = p.matrix(lev)
+        Ac = ugdist.apply_contributions(A, r, ranks, ptr, idx, {int(s): sent[int(s)][r] for s in ranks})
+        assert np.array_equal(Ac.rowptr, A.rowptr) and np.array_equal(Ac.cols, A.cols)
+        g = _comp(p.global_ids(lev), b)
+        S, Gl = Ac.to_scipy().toarray(), G[g][:, g].toarray()
+        dirn = np.repeat(p.dirichlet(lev) != 0, b)
+        assert np.allclose(S[~dirn], Gl[~dirn], rtol=1e-13, atol=1e-15)
+        mult = np.repeat(ugdist.multiplicity(p, lev), b)
+        assert np.array_equal(S[dirn], (np.eye(S.shape[0]) * mult)[dirn])
+        cons.append(Ac)
+    gperm, keep = parallel_gs_global_model(locs, gprob, lev)
+    rng = np.random.default_rng(1)
+    d = rng.standard_normal(gA.nrows * b)
+    d[np.repeat(gprob.dirichlet(lev) != 0, b)] = 0.0     # a defect vanishes in Dirichlet rows
+    gp = _comp(gperm, b)
+    S = orc.matrix(permute_crs(gA, gperm, gperm, keep=keep))
+    for kind in ("ll", "ur", "sgs"):
+        dp = np.empty_like(d); dp[gp] = d
+        c_model = S.gs(dp, kind, 0.9)[gp]
+        c_ranks = np.zeros_like(d)
+        for r, p in enumerate(locs):
+            own = ugdist.owned_mask(p, lev, r)
+            Ad = with_dirichlet_rows(cons[r], np.flatnonzero(~own))            # SetDirichletRow on the h-slaves
+            perm, _ = greedy_color_perm(Ad)
+            gid = p.global_ids(lev)
+            du = np.where(np.repeat(own, b), d[_comp(gid, b)], 0.0)           # unique defect
+            pp = _comp(perm, b)
+            dl = np.empty_like(du); dl[pp] = du
+            c = orc.matrix(permute_crs(Ad, perm, perm)).gs(dl, kind, 0.9)[pp]
+            assert not c[np.repeat(~own, b)].any()                            # the correction is unique
+            c_ranks[_comp(gid[own], b)] = c[np.repeat(own, b)]
+        if b == 1:
+            assert np.array_equal(c_model, c_ranks), kind
+        else:   # block values are not dyadic: the rank-ordered sums of the interface rows round differently
+            assert np.allclose(c_model, c_ranks, rtol=1e-12, atol=1e-14), kind
+
+
+def test_partitioned_gs_oracle_converges():
+    """The serial oracle of the partitioned BiCGStab + GMG(GS) solve (what tests/test_multi_gpu.py compares
+    the GPUs with) converges like the serial solver, a little slower (block Jacobi over the ranks)."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle
+    from helpers import gmg_desc, partitioned_gs_oracle
+    orc = oracle.Oracle("port")
+    desc = gmg_desc(3, solver="bicgstab", smoother={"type": "gs", "relax": 1.0}, reduction=1e-8)
+    solve, gprob = partitioned_gs_oracle(orc, desc, 3, (2, 2, 1), 1, problem=1, eps=1e-1)
+    b = np.array(gprob.rhs())
+    x, ok, h = solve(b)
+    assert ok and h[-1] < 1e-8 * h[0] and len(h) < 20
+    A = gprob.matrix(3).to_scipy()
+    assert np.linalg.norm(b - A @ x) <= 2e-8 * np.linalg.norm(b)

@@ -25,6 +25,32 @@ def _ngpu():
                                                     (2, 0, 2, 0), (2, 2, 2, -1),
                                                     (4, 0, 1, -1), (8, 0, 1, -1), (8, 0, 1, 0), (8, 0, 0, 1), (8, 0, 2, 0)])
 def test_partitioned_gmg_cg_matches_serial_oracle(world, flags, p2p, gather):
+    _run(world, flags, p2p, gather, "poisson", 1e-10, 1e-9)
+
+
+# Written in a session that had no GPU minutes left: host logic is covered on the CPU
+# (tests/test_dist_cpu.py), the first GPU run is pending -> opt-in until it has been seen green once.
+pending = pytest.mark.skipif(os.environ.get("UG4B200_PENDING_GPU_TESTS") != "1",
+                             reason="first GPU run pending (set UG4B200_PENDING_GPU_TESTS=1)")
+
+
+@pending
+@pytest.mark.parametrize("world,flags,p2p,gather", [(2, 0, 1, -1), (2, 0, 0, 0), (4, 0, 1, 1), (8, 0, 1, -1)])
+def test_partitioned_bicgstab_gmg_gauss_seidel_matches_oracle(world, flags, p2p, gather):
+    """BASELINE configs[3] partitioned: BiCGStab + GMG with ugcore's parallel Gauss-Seidel (multicolour inside
+    a rank) vs the serial oracle of the same method.  Tolerance as in the single-GPU test (BiCGStab
+    amplifies reduction-order noise)."""
+    _run(world, flags, p2p, gather, "convdiff_gs", 1e-8, 1e-7)
+
+
+@pending
+@pytest.mark.parametrize("world,flags,p2p,gather", [(2, 0, 1, -1), (8, 0, 1, -1), (2, 0, 0, 0)])
+def test_partitioned_elasticity_block3_matches_serial_oracle(world, flags, p2p, gather):
+    """BASELINE configs[4] partitioned: 3x3-block GMG-CG, block interface exchange."""
+    _run(world, flags, p2p, gather, "elasticity", 1e-10, 1e-9)
+
+
+def _run(world, flags, p2p, gather, case, hist_tol, sol_tol):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     env = dict(os.environ, UG4B200_P2P=str(min(p2p, 1)), UG4B200_FUSED_PUSH="1" if p2p == 2 else "0")
@@ -33,12 +59,12 @@ def test_partitioned_gmg_cg_matches_serial_oracle(world, flags, p2p, gather):
         env["UG4B200_GATHER_LEVEL"] = str(gather)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + world + flags + 20 * p2p + 40 * (gather + 1)),
-           os.path.join(ROOT, "tests", "mgpu_worker.py"), "3", str(flags)]
+           os.path.join(ROOT, "tests", "mgpu_worker.py"), "3", str(flags), case]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     line = [l for l in r.stdout.splitlines() if l.startswith("MGPU_RESULT ")]
     assert line, r.stdout[-3000:] + r.stderr[-3000:]
     for res in json.loads(line[0][len("MGPU_RESULT "):]):
         assert res["ok"] and res["oracle_ok"]
         assert abs(res["its"] - res["its_oracle"]) <= 1
-        assert res["hist_err"] < 1e-10 and res["sol_err"] < 1e-9, res
+        assert res["hist_err"] < hist_tol and res["sol_err"] < sol_tol, res
         assert res["p2p"] == bool(p2p), res

@@ -16,7 +16,9 @@ namespace ug {
 /// Horizontal layouts + communicator of one level (AlgebraLayouts, algebra_layouts.h:47-150)
 class GPUAlgebraLayouts {
   public:
-	GPUAlgebraLayouts(int nneigh, const int* neighRank, const int64_t* neighPtr, const int* indices, int64_t nlocal)
+	GPUAlgebraLayouts(int nneigh, const int* neighRank, const int64_t* neighPtr, const int* indices, int64_t nlocal, int myRank = -1)
+	    : m_rank(myRank), m_nlocal(nlocal), m_neighRank(neighRank, neighRank + nneigh), m_neighPtr(neighPtr, neighPtr + nneigh + 1),
+	      m_indices(indices, indices + (nneigh ? neighPtr[nneigh] : 0))
 	{
 		UG_GPU_CHECK(ug4b200_interface_create(GPUManager::ctx(), nneigh, neighRank, neighPtr, indices, nlocal, &m_iface));
 		// peer-window transport: look up where the neighbours receive (they publish it when they
@@ -25,8 +27,28 @@ class GPUAlgebraLayouts {
 	}
 	~GPUAlgebraLayouts() { if (m_iface && GPUManager::ctx_or_null()) ug4b200_interface_destroy(GPUManager::ctx_or_null(), m_iface); }
 	ug4b200_interface* iface() const { return m_iface; }
+	int64_t num_local() const { return m_nlocal; }
+	/// h-slave DoFs of this rank: shared with a rank of lower number (the h-master of a DoF is the lowest
+	/// rank that holds a copy; IndexLayout slave(), algebra_layouts.h:47-150), ascending, unique.
+	/// Needs the rank the layouts were created for.
+	std::vector<int> slave_indices() const
+	{
+		if (m_rank < 0) UG_THROW("GPUAlgebraLayouts::slave_indices: rank of the layouts unknown");
+		std::vector<char> slave((size_t)m_nlocal, 0);
+		for (size_t p = 0; p < m_neighRank.size(); ++p)
+			if (m_neighRank[p] < m_rank)
+				for (int64_t k = m_neighPtr[p]; k < m_neighPtr[p + 1]; ++k) slave[(size_t)m_indices[(size_t)k]] = 1;
+		std::vector<int> out;
+		for (int64_t i = 0; i < m_nlocal; ++i) if (slave[(size_t)i]) out.push_back((int)i);
+		return out;
+	}
   private:
 	ug4b200_interface* m_iface = nullptr;
+	int m_rank = -1;
+	int64_t m_nlocal = 0;
+	std::vector<int> m_neighRank;
+	std::vector<int64_t> m_neighPtr;
+	std::vector<int> m_indices;
 };
 
 template <typename TValueType>

@@ -142,6 +142,9 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 	void set_surface_to_level_map(const std::vector<int>& surfIndexOfLevelIndex) { m_surfMap = surfIndexOfLevelIndex; }
 	// partitioned runs
 	void set_level_layouts(int lev, SmartPtr<GPUAlgebraLayouts> l) { level(lev).layouts = l; }
+	/// partitioned Gauss-Seidel smoothing: the level matrix made consistent on the interface rows
+	/// (what GaussSeidelBase::preprocess obtains from MakeConsistent, gauss_seidel.h:137)
+	void set_level_smoother_matrix(int lev, SmartPtr<matrix_type> Acons) { level(lev).Aconsistent = Acons; }
 	/// gathered base solve (mg_solver_impl.hpp:2003-2070): every rank holds the assembled global
 	/// base matrix; local additive defects are summed into it with one all-reduce
 	void set_gathered_base(SmartPtr<matrix_operator_type> globalA, const std::vector<int>& localToGlobal)
@@ -182,6 +185,8 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 				for (SmartPtr<smoother_type> s : {ld.PreSmoother, ld.PostSmoother}) {
 					Jacobi<TAlgebra>* j = dynamic_cast<Jacobi<TAlgebra>*>(s.get());
 					if (j) j->set_layouts(ld.layouts);
+					GaussSeidelBase<TAlgebra>* g = dynamic_cast<GaussSeidelBase<TAlgebra>*>(s.get());
+					if (g) { g->set_layouts(ld.layouts); g->set_consistent_matrix(ld.layouts ? ld.Aconsistent : SmartPtr<matrix_type>()); }
 				}
 				if (!ld.PreSmoother->init(ld.A)) UG_THROW("GMG::init: Cannot init pre-smoother for level " << lev);
 				if (ld.PostSmoother != ld.PreSmoother && !ld.PostSmoother->init(ld.A))
@@ -277,6 +282,7 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 		SmartPtr<smoother_type> PreSmoother, PostSmoother;
 		vector_type sc, sd, st, st2;
 		SmartPtr<GPUAlgebraLayouts> layouts;
+		SmartPtr<matrix_type> Aconsistent;   // partitioned Gauss-Seidel only
 		bool scZero = false;   // sc is logically 0: the next accumulation assigns (UG4B200_SMOOTH_SC_ZERO)
 		bool stReady = false;  // st already holds S*sd (produced by the fused restriction of the finer level)
 	};

@@ -116,7 +116,14 @@ class GaussSeidelBase : public IPreconditioner<TAlgebra> {
 
 	GaussSeidelBase() : m_relax(1.0) {}
 	void set_sor_relax(number relaxFactor) { m_relax = relaxFactor; }
-	virtual bool supports_parallel() const { return false; } // partition-independent colouring: next round
+	virtual bool supports_parallel() const { return true; }
+	/// partitioned runs: layouts of the level this smoother lives on (mat.layouts() in ugcore) and the
+	/// level matrix made consistent on the interface rows (MakeConsistent(*pOp, m_A), gauss_seidel.h:137,
+	/// parallel_matrix_overlap_impl.h:438-459).  ugcore builds m_A inside preprocess by exchanging matrix
+	/// rows over MPI; here the caller does that exchange on the host at init (ugcore_b200/dist.py:
+	/// make_consistent) and hands the result over — the device is not involved.
+	void set_layouts(SmartPtr<GPUAlgebraLayouts> l) { m_layouts = l; }
+	void set_consistent_matrix(SmartPtr<matrix_type> A) { m_spConsistent = A; }
 	/// ordering: old index i -> new index perm[i]; the new order must be colour-sorted with the
 	/// given colour offsets.  Without it a greedy colouring of the stored pattern is used.
 	void set_coloring(const std::vector<int>& perm, const std::vector<int64_t>& colorPtr) { m_perm = perm; m_colorPtr = colorPtr; }
@@ -130,13 +137,29 @@ class GaussSeidelBase : public IPreconditioner<TAlgebra> {
 
 	virtual bool preprocess(SmartPtr<matrix_operator_type> pOp)
 	{
-		matrix_type& A = *pOp;
+		matrix_type& A = m_layouts ? parallel_matrix(*pOp) : static_cast<matrix_type&>(*pOp);
 		THROW_IF_NOT_EQUAL(A.num_rows(), A.num_cols());
 		const size_t n = A.num_rows();
 		const std::vector<int64_t>& rp = A.crs_rowptr();
 		const std::vector<int>& ci = A.crs_cols();
-		const std::vector<double>& va = A.crs_vals();
 		const int BB = B * B;
+		// parallel (gauss_seidel.h:134-142): consistent matrix with the rows of the h-slaves set to
+		// Dirichlet rows (SetDirichletRow, sparsematrix_util.h:878-897: all blocks 0, diagonal block = 1)
+		std::vector<double> vaPar;
+		if (m_layouts) {
+			vaPar = A.crs_vals();
+			const std::vector<int> slaves = m_layouts->slave_indices();
+			for (size_t k = 0; k < slaves.size(); ++k) {
+				const int r = slaves[k];
+				bool haveDiag = false;
+				for (int64_t p = rp[r]; p < rp[r + 1]; ++p) {
+					for (int t = 0; t < BB; ++t) vaPar[p * BB + t] = 0.0;
+					if (ci[p] == r) { haveDiag = true; for (int t = 0; t < B; ++t) vaPar[p * BB + t + B * t] = 1.0; }
+				}
+				if (!haveDiag) UG_THROW(this->name() << ": interface row " << r << " has no diagonal connection");
+			}
+		}
+		const std::vector<double>& va = m_layouts ? vaPar : A.crs_vals();
 		if (m_perm.size() != n) {
 			// greedy colouring in row order, colours sorted, stable inside a colour
 			std::vector<int> color(n); int nc = 0;
@@ -178,17 +201,41 @@ class GaussSeidelBase : public IPreconditioner<TAlgebra> {
 		UG_GPU_CHECK(ug4b200_h2d(ctx, m_dPerm, m_perm.data(), sizeof(int) * n));
 		UG_GPU_CHECK(ug4b200_sync(ctx));
 		m_pd = GPUManager::alloc(n * B); m_pc = GPUManager::alloc(n * B);
+		if (m_layouts) { m_dUnique.create(n); m_dUnique.set_layouts(m_layouts); }
 		return true;
 	}
 	virtual bool step(SmartPtr<matrix_operator_type>, vector_type& c, const vector_type& d)
 	{
 		ug4b200_ctx* ctx = GPUManager::ctx();
+		const double* dsrc = d.dev();
+		if (m_layouts) {
+			// make defect unique (gauss_seidel.h:204-207): the sum of all copies on the h-master, 0 on the
+			// slaves.  The reference clones d in every step ("todo: do not clone every time"); the copy
+			// lives in a member here so that a captured CUDA graph always sees the same buffer.
+			m_dUnique = d;
+			if (!m_dUnique.change_storage_type(PST_UNIQUE)) UG_THROW(this->name() << ": cannot make the defect unique");
+			dsrc = m_dUnique.dev();
+		}
 		// Pd[perm[i]] = d[i]; sweep; c[i] = Pc[perm[i]]   (ilu.h:605-610)
-		UG_GPU_CHECK(ug4b200_vec_scatter(ctx, (int64_t)m_n, B, m_pd, m_dPerm, d.dev()));
+		UG_GPU_CHECK(ug4b200_vec_scatter(ctx, (int64_t)m_n, B, m_pd, m_dPerm, dsrc));
 		UG_GPU_CHECK(ug4b200_gs_step(ctx, m_PA, (int)m_colorPtr.size() - 1, m_colorPtr.data(), kind(), m_relax, m_pc, m_pd));
 		UG_GPU_CHECK(ug4b200_vec_gather(ctx, (int64_t)m_n, B, c.dev(), m_pc, m_dPerm));
-		c.set_storage_type(PST_CONSISTENT);
+		if (m_layouts) {
+			// the slave rows are Dirichlet rows and their defect is 0: the correction is unique; make it
+			// consistent (gauss_seidel.h:211-215)
+			c.set_storage_type(PST_UNIQUE);
+			if (!c.change_storage_type(PST_CONSISTENT)) return false;
+		} else c.set_storage_type(PST_CONSISTENT);
 		return true;
+	}
+	matrix_type& parallel_matrix(matrix_type& A)
+	{
+		if (!m_spConsistent)
+			UG_THROW(this->name() << ": a partitioned level needs the consistent level matrix (set_consistent_matrix; "
+			         "ug4b200_solver_set_smoother_matrix)");
+		THROW_IF_NOT_EQUAL(m_spConsistent->num_rows(), A.num_rows());
+		THROW_IF_NOT_EQUAL((size_t)m_layouts->num_local(), A.num_rows());
+		return *m_spConsistent;
 	}
 	virtual bool postprocess() { return true; }
 	void free_dev()
@@ -209,6 +256,9 @@ class GaussSeidelBase : public IPreconditioner<TAlgebra> {
 	int* m_dPerm = nullptr;
 	double *m_pd = nullptr, *m_pc = nullptr;
 	size_t m_n = 0;
+	SmartPtr<GPUAlgebraLayouts> m_layouts;
+	SmartPtr<matrix_type> m_spConsistent;
+	vector_type m_dUnique;
 };
 
 template <typename TAlgebra>

@@ -129,6 +129,10 @@ class GPUManager {
 		return p;
 	}
 	static void free_bytes(void* p) { if (p && inst().m_ctx) ug4b200_free(inst().m_ctx, p); }
+	/// pcl::ProcRank() / pcl::NumProcs() of this process (0 / 1 until the communicator is set up)
+	static int proc_rank() { return inst().m_rank; }
+	static int num_procs() { return inst().m_nranks; }
+	static void set_procs(int nranks, int rank) { inst().m_nranks = nranks; inst().m_rank = rank; }
 
   private:
 	static GPUManager& inst() { static GPUManager m; return m; }
@@ -138,6 +142,7 @@ class GPUManager {
 		m_pool.clear();
 	}
 	ug4b200_ctx* m_ctx = nullptr;
+	int m_rank = 0, m_nranks = 1;
 	std::map<size_t, std::vector<double*> > m_pool;
 };
 

@@ -19,6 +19,7 @@ struct SolverBase {
 	                       const double* rva) = 0;
 	virtual void set_coloring(int lev, int64_t n, const int* perm, int ncolors, const int64_t* cp) = 0;
 	virtual void set_layouts(int lev, int nneigh, const int* ranks, const int64_t* ptr, const int* idx, int64_t nlocal) = 0;
+	virtual void set_smoother_matrix(int lev, int64_t nrows, const int64_t* rp, const int* ci, const double* va) = 0;
 	virtual void set_gathered_base(int64_t nrows, const int64_t* rp, const int* ci, const double* va, int64_t nlocal, const int* l2g) = 0;
 	virtual void set_gathered_level(int lev, int64_t nrows, const int64_t* rp, const int* ci, const double* va, int64_t ncoarse,
 	                                const int64_t* prp, const int* pci, const double* pva, const int64_t* rrp, const int* rci,
@@ -49,6 +50,7 @@ struct SolverImpl : SolverBase {
 	SmartPtr<StdConvCheck<vector_type> > conv;
 	std::map<int, std::pair<std::vector<int>, std::vector<int64_t> > > coloring;
 	std::map<int, SmartPtr<GPUAlgebraLayouts> > layouts;
+	std::map<int, SmartPtr<matrix_type> > smootherMatrix;   // partitioned Gauss-Seidel: consistent level matrices
 	vector_type x, b;
 
 	explicit SolverImpl(const ug4b200_solver_desc& desc) : d(desc)
@@ -147,9 +149,16 @@ struct SolverImpl : SolverBase {
 	}
 	void set_layouts(int lev, int nneigh, const int* ranks, const int64_t* ptr, const int* idx, int64_t nlocal) override
 	{
-		SmartPtr<GPUAlgebraLayouts> l = make_sp<GPUAlgebraLayouts>(nneigh, ranks, ptr, idx, nlocal);
+		SmartPtr<GPUAlgebraLayouts> l = make_sp<GPUAlgebraLayouts>(nneigh, ranks, ptr, idx, nlocal, GPUManager::proc_rank());
 		layouts[lev] = l;
 		if (gmg) gmg->set_level_layouts(lev, l);
+	}
+	void set_smoother_matrix(int lev, int64_t nrows, const int64_t* rp, const int* ci, const double* va) override
+	{
+		SmartPtr<matrix_type> Ac = make_sp<matrix_type>();
+		Ac->set_from_crs((size_t)nrows, (size_t)nrows, rp, ci, va);
+		smootherMatrix[lev] = Ac;
+		if (gmg) gmg->set_level_smoother_matrix(lev, Ac);
 	}
 	void set_gathered_base(int64_t nrows, const int64_t* rp, const int* ci, const double* va, int64_t nlocal, const int* l2g) override
 	{
@@ -185,6 +194,11 @@ struct SolverImpl : SolverBase {
 		if (!A) UG_THROW("solver: matrix not set");
 		Jacobi<TAlgebra>* j = dynamic_cast<Jacobi<TAlgebra>*>(precond.get());
 		if (j) j->set_layouts(top_layouts());
+		GaussSeidelBase<TAlgebra>* g = dynamic_cast<GaussSeidelBase<TAlgebra>*>(precond.get());
+		if (g && top_layouts()) {
+			g->set_layouts(top_layouts());
+			if (!smootherMatrix.empty()) g->set_consistent_matrix(smootherMatrix.rbegin()->second);
+		}
 		x.create(A->num_cols()); b.create(A->num_rows());
 		x.set_layouts(top_layouts()); b.set_layouts(top_layouts());
 		if (!inv->init(A, x)) UG_THROW("solver init failed");
@@ -247,7 +261,7 @@ int ug4b200_host_finalize(void) { return guard([&] { GPUManager::finalize(); ret
 ug4b200_ctx* ug4b200_host_ctx(void) { return GPUManager::ctx_or_null(); }
 const char* ug4b200_host_last_error(void) { return g_err.c_str(); }
 int ug4b200_host_comm_init(int nranks, int rank, const unsigned char id[UG4B200_NCCL_ID_BYTES])
-{ return guard([&] { UG_GPU_CHECK(ug4b200_comm_init(GPUManager::ctx(), nranks, rank, id)); return 0; }); }
+{ return guard([&] { UG_GPU_CHECK(ug4b200_comm_init(GPUManager::ctx(), nranks, rank, id)); GPUManager::set_procs(nranks, rank); return 0; }); }
 
 int ug4b200_solver_create(const ug4b200_solver_desc* d, ug4b200_solver** out)
 {
@@ -273,6 +287,8 @@ int ug4b200_solver_set_coloring(ug4b200_solver* s, int lev, int64_t n, const int
 { return guard([&] { s->p->set_coloring(lev, n, perm, ncolors, color_ptr); return 0; }); }
 int ug4b200_solver_set_layouts(ug4b200_solver* s, int lev, int nneigh, const int* neigh_rank, const int64_t* neigh_ptr, const int* indices, int64_t nlocal)
 { return guard([&] { s->p->set_layouts(lev, nneigh, neigh_rank, neigh_ptr, indices, nlocal); return 0; }); }
+int ug4b200_solver_set_smoother_matrix(ug4b200_solver* s, int lev, int64_t nrows, const int64_t* rowptr, const int* cols, const double* vals)
+{ return guard([&] { s->p->set_smoother_matrix(lev, nrows, rowptr, cols, vals); return 0; }); }
 int ug4b200_solver_set_gathered_base(ug4b200_solver* s, int64_t nrows, const int64_t* rowptr, const int* cols, const double* vals,
                                      int64_t nlocal, const int* local_to_global)
 { return guard([&] { s->p->set_gathered_base(nrows, rowptr, cols, vals, nlocal, local_to_global); return 0; }); }

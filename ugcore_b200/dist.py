@@ -93,16 +93,90 @@ def owned_mask(prob: pr.Problem, lev: int, rank: int):
     return own
 
 
-def local_problem(refs: int, part, rank: int, problem=pr.POISSON, order=pr.ORDER_LEX, dim=3, **kw) -> pr.Problem:
-    """This rank's sub-box of the global grid whose base grid has one element per rank."""
+def consistent_contributions(A: pr.Crs, ranks, ptr, idx) -> dict:
+    """What this rank sends to each neighbour so that the neighbour can make its copy of the level
+    matrix consistent: every stored entry (i, j) whose two DoFs both lie in the interface to that
+    neighbour, addressed by the POSITIONS of i and j in the interface list (the order both sides
+    agree on) — the role of the global AlgebraIDs in ComPol_MatAddRowsOverlap0
+    (lib_algebra/parallelization/parallelization_util.h:100-150).
+    Returns {neighbour rank: (pos_i[int32], pos_j[int32], vals[k, block*block])}."""
+    bb = A.block * A.block
+    rows = np.repeat(np.arange(A.nrows, dtype=np.int64), np.diff(A.rowptr))
+    vals = np.asarray(A.vals).reshape(-1, bb)
+    out = {}
+    for q, r in enumerate(ranks):
+        shared = np.asarray(idx[ptr[q]:ptr[q + 1]], dtype=np.int64)
+        pos = np.full(A.nrows, -1, np.int64)
+        pos[shared] = np.arange(shared.size)
+        pi, pj = pos[rows], pos[A.cols]
+        sel = (pi >= 0) & (pj >= 0)
+        out[int(r)] = (pi[sel].astype(np.int32), pj[sel].astype(np.int32), vals[sel].copy())
+    return out
+
+
+def apply_contributions(A: pr.Crs, rank: int, ranks, ptr, idx, received: dict) -> pr.Crs:
+    """The consistent level matrix of this rank: the additive local matrix plus the neighbours'
+    entries of the shared rows (MatMakeConsistentOverlap0 / MakeConsistent with overlap 0,
+    parallelization_util.h:126-150, parallel_matrix_overlap_impl.h:438-459).  Every copy of an entry is
+    the sum of the contributions in ASCENDING RANK order (own contribution at the place of the own
+    rank), so all copies of a row are bitwise identical — the convention of the device-side vector
+    exchange (csrc/comm.cu).  A connection that only a neighbour stores is inserted
+    (ComPol_MatAddRowsOverlap0 adds into mat(i, j))."""
+    bb = A.block * A.block
+    n = A.nrows
+    rows = [np.repeat(np.arange(n, dtype=np.int64), np.diff(A.rowptr))]
+    cols = [np.asarray(A.cols, dtype=np.int64)]
+    vals = [np.asarray(A.vals).reshape(-1, bb)]
+    src = [np.full(A.cols.size, rank, np.int64)]
+    for q, r in enumerate(ranks):
+        r = int(r)
+        if r not in received:
+            raise ValueError(f"rank {rank}: no contribution received from neighbour {r}")
+        shared = np.asarray(idx[ptr[q]:ptr[q + 1]], dtype=np.int64)
+        pi, pj, v = received[r]
+        if pi.size and (int(pi.max()) >= shared.size or int(pj.max()) >= shared.size):
+            raise ValueError(f"rank {rank}: neighbour {r} addresses positions outside the shared interface")
+        rows.append(shared[pi]); cols.append(shared[pj]); vals.append(np.asarray(v).reshape(-1, bb))
+        src.append(np.full(pi.size, r, np.int64))
+    rows, cols, vals, src = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals), np.concatenate(src)
+    order = np.lexsort((src, cols, rows))            # by entry, contributions of an entry in ascending rank order
+    rows, cols, vals = rows[order], cols[order], vals[order]
+    first = np.ones(rows.size, bool)
+    first[1:] = (rows[1:] != rows[:-1]) | (cols[1:] != cols[:-1])
+    start = np.flatnonzero(first)
+    count = np.diff(np.append(start, rows.size))
+    acc = vals[start].copy()
+    for k in range(1, int(count.max()) if count.size else 0):
+        m = count > k
+        acc[m] = acc[m] + vals[start[m] + k]         # left to right: ((c0 + c1) + c2) + ...
+    rp = np.zeros(n + 1, np.int64)
+    np.add.at(rp, rows[start] + 1, 1)
+    return pr.Crs(n, A.ncols, A.block, np.cumsum(rp), cols[start].astype(np.int32), acc.ravel().copy())
+
+
+def make_consistent(A: pr.Crs, rank: int, ranks, ptr, idx, dist) -> pr.Crs:
+    """MakeConsistent(A) over torch.distributed (host data, init time only): what ugcore's parallel
+    Gauss-Seidel does in preprocess (gauss_seidel.h:134-142).  Collective: every rank of the
+    process group must call it for the same level, also ranks without neighbours."""
+    mine = consistent_contributions(A, ranks, ptr, idx)
+    everything = [None] * dist.get_world_size()
+    dist.all_gather_object(everything, mine)
+    received = {int(r): everything[int(r)][rank] for r in ranks}
+    return apply_contributions(A, rank, ranks, ptr, idx, received)
+
+
+def local_problem(refs: int, part, rank: int, problem=pr.POISSON, order=pr.ORDER_LEX, dim=3, base_mult: int = 1,
+                  **kw) -> pr.Problem:
+    """This rank's sub-box of the global grid whose base grid has base_mult elements per rank and
+    direction (base_mult = 3, refs = 5: 97 nodes per direction and rank)."""
     coord = rank_to_coord(rank, part)
-    return pr.Problem(dim=dim, num_refs=refs, problem=problem, base=tuple(part), base_lev=0, order=order,
-                      part=tuple(part), coord=coord, **kw)
+    return pr.Problem(dim=dim, num_refs=refs, problem=problem, base=tuple(base_mult * p for p in part), base_lev=0,
+                      order=order, part=tuple(part), coord=coord, **kw)
 
 
-def global_problem(refs: int, part, problem=pr.POISSON, dim=3, **kw) -> pr.Problem:
+def global_problem(refs: int, part, problem=pr.POISSON, dim=3, base_mult: int = 1, **kw) -> pr.Problem:
     """The same grid assembled serially (parity target and gathered base matrix)."""
-    return pr.Problem(dim=dim, num_refs=refs, problem=problem, base=tuple(part), base_lev=0, **kw)
+    return pr.Problem(dim=dim, num_refs=refs, problem=problem, base=tuple(base_mult * p for p in part), base_lev=0, **kw)
 
 
 _nccl_ready = False
@@ -182,7 +256,7 @@ def p2p_bootstrap(dist) -> bool:
 
 
 def default_gather_level(refs: int, part, base: int = 0, max_local_rows: int = 40000, max_global_rows: int = 300000,
-                         dim: int = 3) -> int:
+                         dim: int = 3, base_mult: int = 1) -> int:
     """Highest level that is kept (and cycled) redundantly on every rank instead of being partitioned:
     a level whose LOCAL box has at most max_local_rows rows is latency-bound — its four interface
     exchanges per cycle (~6-8 us each) cost more than smoothing the whole (still small) global level
@@ -192,11 +266,27 @@ def default_gather_level(refs: int, part, base: int = 0, max_local_rows: int = 4
     for l in range(base, refs):
         loc, glob = 1, 1
         for d in range(dim):
-            loc *= 2 ** l + 1
-            glob *= part[d] * 2 ** l + 1
+            loc *= base_mult * 2 ** l + 1
+            glob *= part[d] * base_mult * 2 ** l + 1
         if loc <= max_local_rows and glob <= max_global_rows:
             lev = l
     return lev
+
+
+GS_KINDS = ("gs", "bgs", "sgs")
+
+
+def _smoother_kind(desc: dict):
+    """type of the smoother that will run on partitioned levels (GMG smoother, or the preconditioner itself)"""
+    pc = desc.get("precond")
+    if isinstance(pc, str):
+        pc = {"type": pc}
+    if not pc:
+        return None
+    if pc.get("type") == "gmg":
+        sm = pc.get("smoother", {"type": "jac"})
+        return sm if isinstance(sm, str) else sm.get("type")
+    return pc.get("type")
 
 
 def build_partitioned_solver(desc: dict, refs: int, part, rank: int, dist, problem=pr.POISSON, flags: int = 0,
@@ -218,7 +308,8 @@ def build_partitioned_solver(desc: dict, refs: int, part, rank: int, dist, probl
     base = pc["baseLevel"]
     if gather_level is None:
         env = os.environ.get("UG4B200_GATHER_LEVEL")
-        gather_level = int(env) if env is not None else default_gather_level(refs, part, base, dim=prob.dim)
+        gather_level = int(env) if env is not None else default_gather_level(refs, part, base, dim=prob.dim,
+                                                                             base_mult=kw.get("base_mult", 1))
     if pc.get("cycle", "V") != "V":
         gather_level = base
     gather = max(base, min(int(gather_level), refs - 1))
@@ -230,9 +321,14 @@ def build_partitioned_solver(desc: dict, refs: int, part, rank: int, dist, probl
                        None if lev == gather else prob.restriction(lev))
     s = Solver(desc, prob.matrix(refs), levels, flags)
     s._keep.append(prob)
+    gs = _smoother_kind(desc) in GS_KINDS
     for lev in range(gather, refs + 1):
         ranks, ptr, idx = interfaces(prob, lev)
         s.set_layouts(lev, ranks, ptr, idx, prob.matrix(lev).nrows)
+        if gs and lev > gather:
+            # ugcore's parallel Gauss-Seidel smooths with the level matrix made consistent on the interface
+            # rows (gauss_seidel.h:134-142); the rows are exchanged on the host, once
+            s.set_smoother_matrix(lev, make_consistent(prob.matrix(lev), rank, ranks, ptr, idx, dist))
     gprob = global_problem(gather, part, problem=problem, **kw)
     s._keep.append(gprob)
     s.set_gathered_base(gprob.matrix(gather), prob.global_ids(gather).astype(np.int32))

@@ -186,6 +186,13 @@ class Solver:
         idx = np.ascontiguousarray(indices, dtype=np.int32)
         check_host(host.ug4b200_solver_set_layouts(self.h, lev, nr.size, _ptr(nr), _ptr(npt), _ptr(idx), nlocal))
 
+    def set_smoother_matrix(self, lev, Acons):
+        """Partitioned Gauss-Seidel: the level matrix made consistent on the interface rows
+        (``dist.make_consistent``); the smoother sets the rows of the h-slaves to Dirichlet rows itself."""
+        self._keep.append(Acons)
+        check_host(host.ug4b200_solver_set_smoother_matrix(self.h, lev, Acons.nrows, _ptr(Acons.rowptr), _ptr(Acons.cols),
+                                                           _ptr(Acons.vals)))
+
     def set_gathered_base(self, Aglobal, local_to_global):
         l2g = np.ascontiguousarray(local_to_global, dtype=np.int32)
         self._keep.append(Aglobal)
