@@ -18,9 +18,14 @@ extern "C" {
 #endif
 
 enum { UG4B200_SOLVER_CG = 0, UG4B200_SOLVER_BICGSTAB = 1, UG4B200_SOLVER_LINEAR = 2, UG4B200_SOLVER_LU = 3,
-       UG4B200_SOLVER_COARSE_CG = 4 };
+       UG4B200_SOLVER_COARSE_CG = 4, UG4B200_SOLVER_GMRES = 5 /* lib_algebra/operator/linear_solver/gmres.h */ };
 enum { UG4B200_PRECOND_NONE = 0, UG4B200_PRECOND_JACOBI = 1, UG4B200_PRECOND_GS = 2, UG4B200_PRECOND_BGS = 3,
-       UG4B200_PRECOND_SGS = 4, UG4B200_PRECOND_GMG = 5 };
+       UG4B200_PRECOND_SGS = 4, UG4B200_PRECOND_GMG = 5, UG4B200_PRECOND_ILU = 6 /* operator/preconditioner/ilu.h */ };
+/* ordering of the ILU factorisation (ILU::set_ordering_algorithm / set_sort, ilu.h:397-414) */
+enum { UG4B200_ILU_ORDER_NATURAL = 0,    /* no ordering: level-scheduled triangular solves, one launch per level */
+       UG4B200_ILU_ORDER_CMK = 1,        /* set_sort(true): NativeCuthillMcKeeOrdering; level-scheduled */
+       UG4B200_ILU_ORDER_MULTICOLOR = 2  /* greedy multicolour ordering: one launch per colour, bit-identical to the
+                                            reference's ILU applied in that ordering */ };
 enum { UG4B200_FLAG_HOST_SCALARS = 1,   /* CG with host scalars (reference-shaped loop, one sync per dot) */
        UG4B200_FLAG_NO_GRAPH = 2,       /* do not capture the Krylov iteration into a CUDA graph */
        UG4B200_FLAG_NO_FUSED_JACOBI = 4,/* V-cycle with separate Jacobi / SpMV / AXPY launches */
@@ -52,6 +57,9 @@ typedef struct ug4b200_solver_desc {
 	 * levels above are partitioned.  gather_lev <= base_lev: only the base solve is gathered
 	 * (mg_solver_impl.hpp:2003-2070). */
 	int gather_lev;
+	int restart;           /* GMRES(restart); <= 0: 30 */
+	double ilu_beta;       /* ILU(beta), 0 = ILU(0); for precond == ILU and for smoother == ILU inside GMG */
+	int ilu_order;         /* UG4B200_ILU_ORDER_* */
 } ug4b200_solver_desc;
 
 typedef struct ug4b200_solver ug4b200_solver;
@@ -150,6 +158,21 @@ int ug4b200_host_rap(int64_t nc, int64_t nf, const int64_t* r_rowptr, const int*
                      const int64_t* p_rowptr, const int* p_cols, const double* p_vals, ug4b200_host_matrix** out);
 int ug4b200_io_write_vector(const char* filename, int64_t n, const double* values, const double* positions, int dim,
                             int precision);
+
+/* ---- init-time host kernels of ILU and of DoF reordering, exposed for callers and tests (no device involved) ----
+ * ILU(0) (beta == 0: FactorizeILUSorted, ilu.h:174-228) or ILU(beta) (FactorizeILUBeta, :110-171) of a scalar CRS
+ * matrix with sorted rows, in place in vals: L below the diagonal (unit diagonal implied), U on and above it.
+ * Bit-identical to the reference's factorisation. */
+int ug4b200_host_ilu_factorize(int64_t n, const int64_t* rowptr, const int* cols, double* vals, double beta, double sort_eps);
+/* level sets of the lower (lower != 0) or upper triangle of a stored pattern: level[i] = longest dependency chain below
+ * row i — rows of one level can be solved in one launch of the sweep kernel; *nlevels out */
+int ug4b200_host_level_sets(int64_t n, const int64_t* rowptr, const int* cols, int lower, int* level, int* nlevels);
+/* Cuthill-McKee ordering of the matrix graph, new_index[old] = new: GetCuthillMcKeeOrder
+ * (ugbase/lib_algebra/algebra_common/permutation_util.h:96-114) -> ComputeCuthillMcKeeOrder
+ * (ugbase/lib_algebra/ordering_strategies/algorithms/native_cuthill_mckee.cpp:100-300); same result as the
+ * reference for the same pattern (stable sorts by degree, breadth-first numbering). */
+int ug4b200_host_cuthill_mckee(int64_t n, const int64_t* rowptr, const int* cols, int reverse, int preserve_consec,
+                               int64_t* new_index);
 
 #ifdef __cplusplus
 }

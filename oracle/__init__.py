@@ -19,8 +19,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(_HERE, "liboracle.so")
 REF_SO = os.path.join(_HERE, "_ref", "liboracle_ref.so")
 
-SOLVER = {"cg": 0, "bicgstab": 1, "linear": 2, "lu": 3}
-PRECOND = {None: 0, "none": 0, "jac": 1, "jacobi": 1, "gs": 2, "bgs": 3, "sgs": 4, "gmg": 5}
+SOLVER = {"cg": 0, "bicgstab": 1, "linear": 2, "lu": 3, "gmres": 5}
+PRECOND = {None: 0, "none": 0, "jac": 1, "jacobi": 1, "gs": 2, "bgs": 3, "sgs": 4, "gmg": 5, "ilu": 6}
 
 
 class SolverDesc(C.Structure):
@@ -31,6 +31,7 @@ class SolverDesc(C.Structure):
         ("nu1", C.c_int), ("nu2", C.c_int), ("smoother", C.c_int), ("smoother_damp", C.c_double),
         ("base_solver", C.c_int), ("base_max_steps", C.c_int),
         ("base_min_defect", C.c_double), ("base_rel_reduction", C.c_double),
+        ("restart", C.c_int), ("ilu_beta", C.c_double),
     ]
 
 
@@ -95,6 +96,10 @@ class Oracle:
         L.oracle_jacobi.argtypes = [C.c_void_p, C.c_double, C.c_int, _dp, _dp]
         L.oracle_gs.argtypes = [C.c_void_p, C.c_int, C.c_double, _dp, _dp]
         L.oracle_lu_solve.argtypes = [C.c_void_p, _dp, _dp]
+        L.oracle_ilu_factorize.restype = C.c_void_p
+        L.oracle_ilu_factorize.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.oracle_ilu_apply.argtypes = [C.c_void_p, C.c_double, _dp, _dp]
+        L.oracle_cuthill_mckee.argtypes = [C.c_void_p, C.c_int, C.c_int, _lp]
         L.oracle_solver_create.restype = C.c_void_p
         L.oracle_solver_create.argtypes = [C.POINTER(SolverDesc)]
         L.oracle_solver_destroy.argtypes = [C.c_void_p]
@@ -221,6 +226,25 @@ class OMat:
         self.o._chk(self.o.lib.oracle_gs(self.h, {"ll": 0, "ur": 1, "sgs": 2}[kind], relax, c, _vec(d)))
         return c
 
+    def ilu(self, beta=0.0, sort_eps=1e-50) -> "OMat":
+        """The ILU(0) / ILU(beta) factors of this matrix in one matrix (ilu.h:563-576)."""
+        h = self.o.lib.oracle_ilu_factorize(self.h, beta, sort_eps)
+        if not h:
+            raise RuntimeError("oracle: " + self.o.lib.oracle_last_error().decode())
+        return OMat(self.o, self.block, self.nrows, self.ncols, None, None, None, handle=h)
+
+    def ilu_apply(self, d, inv_eps=1e-8):
+        """c = U^-1 L^-1 d with self = the factor matrix (ILU::applyLU, ilu.h:593-599)."""
+        c = np.zeros(self.nrows * self.block)
+        self.o._chk(self.o.lib.oracle_ilu_apply(self.h, inv_eps, c, _vec(d)))
+        return c
+
+    def cuthill_mckee(self, reverse=True, preserve_consec=False):
+        """new index of every old index (GetCuthillMcKeeOrder's defaults: reverse, not consecutive)."""
+        ni = np.zeros(self.nrows, np.int64)
+        self.o._chk(self.o.lib.oracle_cuthill_mckee(self.h, int(reverse), int(preserve_consec), ni))
+        return ni
+
     def lu_solve(self, b):
         x = np.zeros(self.nrows * self.block)
         self.o._chk(self.o.lib.oracle_lu_solve(self.h, x, _vec(b)))
@@ -245,6 +269,8 @@ def make_desc(desc: dict) -> SolverDesc:
         pc = {"type": pc}
     d.precond = PRECOND[pc["type"] if pc else None]
     d.damp = 1.0
+    d.restart = desc.get("restart", 30)
+    d.ilu_beta = 0.0
     d.cycle, d.nu1, d.nu2 = 1, 2, 2
     d.smoother, d.smoother_damp = 1, 0.66
     d.base_solver, d.base_max_steps, d.base_min_defect, d.base_rel_reduction = 3, 1000, 1e-30, 1e-14
@@ -253,11 +279,14 @@ def make_desc(desc: dict) -> SolverDesc:
             d.damp = pc.get("damp", 0.66)
         elif pc["type"] in ("gs", "bgs", "sgs"):
             d.damp = pc.get("relax", 1.0)
+        elif pc["type"] == "ilu":
+            d.ilu_beta = pc.get("beta", 0.0)
         elif pc["type"] == "gmg":
             sm = pc.get("smoother", {"type": "jac", "damp": 0.66})
             if isinstance(sm, str):
                 sm = {"type": sm}
             d.smoother = PRECOND[sm["type"]]
+            d.ilu_beta = sm.get("beta", 0.0) if sm["type"] == "ilu" else 0.0
             d.smoother_damp = sm.get("damp", 0.66) if d.smoother == 1 else sm.get("relax", 1.0)
             d.cycle = {"V": 1, "W": 2, "F": -1}[pc.get("cycle", "V")]
             d.nu1 = pc.get("preSmooth", 2)

@@ -75,6 +75,17 @@ struct Backend {
 	virtual void gs_step_UR(const Mat& A, Vec& c, const Vec& d, double relax) = 0;
 	virtual void sgs_step(const Mat& A, Vec& c, const Vec& d, double relax) = 0;
 
+	// ILU(0) / ILU(beta) (lib_algebra/operator/preconditioner/ilu.h): factorisation of a copy of A with
+	// FactorizeILUSorted (:174-228; beta == 0) or FactorizeILUBeta (:110-171), L below the diagonal with unit
+	// diagonal implied, U on and above it; invert_L (:233-252), invert_U (:257-322, false = the last row's
+	// near-zero check fired)
+	virtual Mat* ilu_factorize(const Mat& A, double beta, double sortEps) = 0;
+	virtual void ilu_invert_L(const Mat& LU, Vec& x, const Vec& b) = 0;
+	virtual bool ilu_invert_U(const Mat& LU, Vec& x, const Vec& b, double eps) = 0;
+	// Cuthill-McKee order of the matrix graph: GetCuthillMcKeeOrder (algebra_common/permutation_util.h:96-114) ->
+	// ComputeCuthillMcKeeOrder (ordering_strategies/algorithms/native_cuthill_mckee.cpp:100-300); newIndex[old] = new
+	virtual void cuthill_mckee(const Mat& A, bool reverse, bool preserveConsec, std::vector<size_t>& newIndex) = 0;
+
 	virtual DenseLU* lu_init(const Mat& A) = 0;                  // nullptr if singular
 	virtual void lu_apply(const DenseLU& lu, Vec& x, const Vec& b) = 0;
 };

@@ -50,12 +50,19 @@ int oracle_scale_add3(int64_t len, double* d, double a1, const double* v1, doubl
 int oracle_jacobi(const oracle_mat* A, double damp, int block_inverse, double* c, const double* d);
 /* kind: 0 gs_step_LL, 1 gs_step_UR, 2 sgs_step */
 int oracle_gs(const oracle_mat* A, int kind, double relax, double* c, const double* d);
+/* ILU(0) / ILU(beta) of a copy of A (lib_algebra/operator/preconditioner/ilu.h:110-228) and one application
+ * c = U^-1 L^-1 d (invert_L :233-252, invert_U :257-322; returns 1 if the last row's near-zero check fired) */
+oracle_mat* oracle_ilu_factorize(const oracle_mat* A, double beta, double sort_eps);
+int oracle_ilu_apply(const oracle_mat* LU, double inv_eps, double* c, const double* d);
+/* new_index[old] = new; GetCuthillMcKeeOrder (algebra_common/permutation_util.h:96-114) */
+int oracle_cuthill_mckee(const oracle_mat* A, int reverse, int preserve_consec, int64_t* new_index);
 int oracle_lu_solve(const oracle_mat* A, double* x, const double* b);
 
 /* ---- solver level ---- */
 enum { ORACLE_SOLVER_CG = 0, ORACLE_SOLVER_BICGSTAB = 1, ORACLE_SOLVER_LINEAR = 2, ORACLE_SOLVER_LU = 3 };
 enum { ORACLE_PRECOND_NONE = 0, ORACLE_PRECOND_JACOBI = 1, ORACLE_PRECOND_GS = 2, ORACLE_PRECOND_BGS = 3,
-       ORACLE_PRECOND_SGS = 4, ORACLE_PRECOND_GMG = 5 };
+       ORACLE_PRECOND_SGS = 4, ORACLE_PRECOND_GMG = 5, ORACLE_PRECOND_ILU = 6 };
+enum { ORACLE_SOLVER_GMRES = 5 };
 
 typedef struct oracle_solver_desc {
 	int solver;            /* ORACLE_SOLVER_* */
@@ -73,6 +80,8 @@ typedef struct oracle_solver_desc {
 	int base_solver;       /* ORACLE_SOLVER_LU or ORACLE_SOLVER_CG (unpreconditioned, tight tolerance) */
 	int base_max_steps;
 	double base_min_defect, base_rel_reduction;
+	int restart;           /* GMRES(restart) */
+	double ilu_beta;       /* ILU(beta); 0: ILU(0) (also for an ILU smoother inside GMG: smoother = ORACLE_PRECOND_ILU) */
 } oracle_solver_desc;
 
 typedef struct oracle_solver oracle_solver;

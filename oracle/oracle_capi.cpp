@@ -45,9 +45,10 @@ template <class F> int guard(F f)
 	catch (...) { g_err = "unknown exception"; return -1; }
 }
 
-LinearIterator* make_smoother(int kind, double damp)
+LinearIterator* make_smoother(int kind, double damp, double ilu_beta = 0.0)
 {
 	switch (kind) {
+		case ORACLE_PRECOND_ILU: return new ILU(BK(), ilu_beta);
 		case ORACLE_PRECOND_JACOBI: return new Jacobi(BK(), damp);
 		case ORACLE_PRECOND_GS: { GaussSeidel* g = new GaussSeidel(BK(), GaussSeidel::FORWARD); g->relax = damp; return g; }
 		case ORACLE_PRECOND_BGS: { GaussSeidel* g = new GaussSeidel(BK(), GaussSeidel::BACKWARD); g->relax = damp; return g; }
@@ -164,6 +165,33 @@ int oracle_gs(const oracle_mat* A, int kind, double relax, double* c, const doub
 		Cv.back(); return 0;
 	});
 }
+oracle_mat* oracle_ilu_factorize(const oracle_mat* A, double beta, double sort_eps)
+{
+	try { oracle_mat* T = new oracle_mat; T->m.reset(BK().ilu_factorize(*A->m, beta, sort_eps)); return T; }
+	catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+int oracle_ilu_apply(const oracle_mat* LU, double inv_eps, double* c, const double* d)
+{
+	return guard([&] {
+		const int vb = LU->m->block;
+		// ILU::applyLU without ordering (ilu.h:593-599): h = L^-1 d ; c = U^-1 h
+		std::vector<double> h((size_t)LU->m->nrows * vb, 0.0);
+		VIO Hv(LU->m->nrows * vb, vb, h.data(), h.data()), Dv(LU->m->nrows * vb, vb, d), Cv(LU->m->nrows * vb, vb, c, c);
+		BK().ilu_invert_L(*LU->m, *Hv.v, *Dv.v);
+		const bool ok = BK().ilu_invert_U(*LU->m, *Cv.v, *Hv.v, inv_eps);
+		Cv.back();
+		return ok ? 0 : 1;
+	});
+}
+int oracle_cuthill_mckee(const oracle_mat* A, int reverse, int preserve_consec, int64_t* new_index)
+{
+	return guard([&] {
+		std::vector<size_t> ni;
+		BK().cuthill_mckee(*A->m, reverse != 0, preserve_consec != 0, ni);
+		for (size_t i = 0; i < ni.size(); ++i) new_index[i] = (int64_t)ni[i];
+		return 0;
+	});
+}
 int oracle_lu_solve(const oracle_mat* A, double* x, const double* b)
 {
 	return guard([&] {
@@ -186,7 +214,7 @@ oracle_solver* oracle_solver_create(const oracle_solver_desc* d)
 			pc.reset(g); s->gmg = g;
 			g->baseLev = d->base_lev; g->topLev = d->top_lev;
 			g->cycleType = d->cycle; g->numPreSmooth = d->nu1; g->numPostSmooth = d->nu2;
-			g->smootherProto.reset(make_smoother(d->smoother, d->smoother_damp));
+			g->smootherProto.reset(make_smoother(d->smoother, d->smoother_damp, d->ilu_beta));
 			if (d->base_solver == ORACLE_SOLVER_LU) g->baseSolver.reset(new LU(BK()));
 			else if (d->base_solver == ORACLE_SOLVER_CG) {
 				CG* c = new CG(BK());
@@ -195,13 +223,14 @@ oracle_solver* oracle_solver_create(const oracle_solver_desc* d)
 				g->baseSolver.reset(c);
 			} else throw std::runtime_error("unsupported base solver");
 			g->lev.resize(d->top_lev - d->base_lev + 1);
-		} else if (d->precond != ORACLE_PRECOND_NONE) pc.reset(make_smoother(d->precond, d->damp));
+		} else if (d->precond != ORACLE_PRECOND_NONE) pc.reset(make_smoother(d->precond, d->damp, d->ilu_beta));
 		s->precond = pc.get();
 		PrecondInverse* pi = nullptr;
 		switch (d->solver) {
 			case ORACLE_SOLVER_CG: pi = new CG(BK()); break;
 			case ORACLE_SOLVER_BICGSTAB: pi = new BiCGStab(BK()); break;
 			case ORACLE_SOLVER_LINEAR: pi = new LinearSolver(BK()); break;
+			case ORACLE_SOLVER_GMRES: { GMRES* g = new GMRES(BK()); g->restart = (size_t)(d->restart > 0 ? d->restart : 30); pi = g; break; }
 			case ORACLE_SOLVER_LU: s->inv.reset(new LU(BK())); s->lone = std::move(pc); break;
 			default: throw std::runtime_error("unknown solver");
 		}

@@ -437,6 +437,174 @@ struct PortBackend : Backend {
 		gs_step_UR(A_, c, c, relax);
 	}
 
+	// operator/preconditioner/ilu.h:174-228 FactorizeILUSorted (beta == 0), :110-171 FactorizeILUBeta.
+	// Scalar matrices only (the block version needs DenseMatrix::operator/= = multiplication by the inverse
+	// block; the compiled reference covers blocks).
+	Mat* ilu_factorize(const Mat& A_, double beta, double sortEps) override
+	{
+		const PMat& A0 = M(A_);
+		if (A0.block != 1) throw std::runtime_error("port oracle: ILU of block matrices not restated (use the ref backend)");
+		PMat* F = new PMat(A0);
+		std::vector<int64_t>& rp = F->rp; std::vector<int>& ci = F->ci; std::vector<double>& va = F->va;
+		const int64_t n = F->nrows;
+		auto find = [&](int64_t r, int c) -> int64_t {   // get_connection(r, c): binary search in the sorted row
+			const int* b = ci.data() + rp[r]; const int* e = ci.data() + rp[r + 1];
+			const int* p = std::lower_bound(b, e, c);
+			return (p != e && *p == c) ? (int64_t)(p - ci.data()) : -1;
+		};
+		if (beta != 0.0) {
+			for (int64_t i = 1; i < n; ++i) {
+				const int64_t dii = find(i, (int)i);
+				if (dii < 0) throw std::runtime_error("ILU: row without diagonal entry");   // A(i,i) would insert
+				double Nii = va[dii]; Nii *= 0.0;                                           // ilu.h:121-122
+				for (int64_t pik = rp[i]; pik != rp[i + 1] && ci[pik] < i; ++pik) {
+					const int k = ci[pik];
+					va[pik] /= va[find(k, k)];                                              // :138
+					const double a_ik = va[pik];
+					for (int64_t pkj = rp[k]; pkj != rp[k + 1]; ++pkj) {                    // :142-166
+						const int j = ci[pkj];
+						if (j <= k) continue;
+						const double a_kj = va[pkj];
+						const int64_t pij = find(i, j);
+						if (pij >= 0) va[pij] -= a_ik * a_kj;
+						else Nii -= a_ik * a_kj;
+					}
+				}
+				va[dii] += beta * Nii;                                                      // AddMult(Aii, beta, Nii) :170
+			}
+			return F;
+		}
+		for (int64_t i = 1; i < n; ++i) {
+			for (int64_t pik = rp[i]; pik != rp[i + 1] && ci[pik] < i; ++pik) {             // :185
+				const int k = ci[pik];
+				const double a_kk = va[find(k, k)];
+				if (std::fabs(std::fabs(a_kk)) < sortEps * std::fabs(va[pik]))                 // :194 (BlockNorm(double) = |.|)
+					{ delete F; throw std::runtime_error("ILU: Blocknorm of diagonal is near-zero"); }
+				va[pik] /= a_kk;                                                            // :200
+				const double a_ik = va[pik];
+				int64_t pij = pik + 1, pkj = rp[k];                                         // :205-222: merge of the two sorted rows
+				while (pij != rp[i + 1] && pkj != rp[k + 1]) {
+					if (ci[pij] > ci[pkj]) ++pkj;
+					else if (ci[pij] < ci[pkj]) ++pij;
+					else { va[pij] -= a_ik * va[pkj]; ++pkj; ++pij; }
+				}
+			}
+		}
+		return F;
+	}
+	// ilu.h:233-252
+	void ilu_invert_L(const Mat& LU_, Vec& x, const Vec& b) override
+	{
+		const PMat& A = M(LU_);
+		if (A.block != 1) throw std::runtime_error("port oracle: ILU of block matrices not restated");
+		double* xd = x.data(); const double* bd = b.data();
+		for (int64_t i = 0; i < A.nrows; ++i) {
+			double s = bd[i];
+			for (int64_t p = A.rp[i]; p != A.rp[i + 1]; ++p) {
+				if (A.ci[p] >= i) continue;
+				s = 1.0 * s + (-1.0 * A.va[p]) * xd[A.ci[p]];        // MatMultAdd(s, 1.0, s, -1.0, a, x[j])
+			}
+			xd[i] = s;
+		}
+	}
+	// ilu.h:257-322
+	bool ilu_invert_U(const Mat& LU_, Vec& x, const Vec& b, double eps) override
+	{
+		const PMat& A = M(LU_);
+		if (A.block != 1) throw std::runtime_error("port oracle: ILU of block matrices not restated");
+		double* xd = x.data(); const double* bd = b.data();
+		const int64_t n = A.nrows;
+		bool result = true;
+		auto diag = [&](int64_t i) -> double {
+			for (int64_t p = A.rp[i]; p != A.rp[i + 1]; ++p) if (A.ci[p] == i) return A.va[p];
+			return 0.0;
+		};
+		if (n > 0) {
+			const int64_t i = n - 1;
+			const double s = bd[i];
+			if (std::fabs(diag(i)) <= eps * std::fabs(s)) { xd[i] = 0; result = false; }    // :285-297
+			else xd[i] = 1.0 * s / diag(i);                                                  // InverseMatMult(x[i], 1.0, A(i,i), s)
+		}
+		if (n <= 1) return result;
+		for (int64_t i = n - 2;; --i) {
+			double s = bd[i];
+			for (int64_t p = A.rp[i]; p != A.rp[i + 1]; ++p) {
+				if (A.ci[p] <= i) continue;
+				s = 1.0 * s + (-1.0 * A.va[p]) * xd[A.ci[p]];
+			}
+			xd[i] = 1.0 * s / diag(i);
+			if (i == 0) break;
+		}
+		return result;
+	}
+	// ordering_strategies/algorithms/native_cuthill_mckee.cpp:100-300 on the graph GetCuthillMcKeeOrder builds
+	// (algebra_common/permutation_util.h:96-114: every stored column of a row, the diagonal included)
+	void cuthill_mckee(const Mat& A_, bool reverse, bool preserveConsec, std::vector<size_t>& vNewIndex) override
+	{
+		const PMat& A = M(A_);
+		const size_t nDoF = (size_t)A.nrows;
+		std::vector<std::vector<size_t> > con(nDoF);
+		for (size_t i = 0; i < nDoF; ++i) for (int64_t p = A.rp[i]; p != A.rp[i + 1]; ++p) con[i].push_back((size_t)A.ci[p]);
+		auto lessDeg = [&](size_t i, size_t j) { return con[i].size() < con[j].size(); };
+		std::vector<bool> handled(nDoF, false);
+		for (size_t i = 0; i < nDoF; ++i) {
+			if (con[i].empty()) handled[i] = true;
+			else std::stable_sort(con[i].begin(), con[i].end(), lessDeg);                    // :121-133
+		}
+		std::vector<size_t> sorting(nDoF);
+		for (size_t i = 0; i < nDoF; ++i) sorting[i] = i;
+		std::stable_sort(sorting.begin(), sorting.end(), lessDeg);                           // :138-143
+		std::vector<size_t> order;
+		size_t firstNonHandled = 0;
+		while (true) {
+			size_t k = firstNonHandled;
+			for (; k < nDoF; ++k) if (!handled[sorting[k]]) { firstNonHandled = k; break; }
+			if (k == nDoF) break;
+			std::vector<size_t> queue(1, sorting[firstNonHandled]);                          // breadth first, :172-199
+			for (size_t head = 0; head < queue.size(); ++head) {
+				const size_t front = queue[head];
+				if (handled[front]) continue;
+				order.push_back(front); handled[front] = true;
+				for (size_t t = 0; t < con[front].size(); ++t) if (!handled[con[front][t]]) queue.push_back(con[front][t]);
+			}
+		}
+		vNewIndex.assign(nDoF, (size_t)-1);
+		if (preserveConsec) {                                                                // :205-262
+			size_t cnt = 0;
+			for (size_t newInd = 0; newInd < nDoF; ++newInd) {
+				if (con[newInd].empty()) continue;
+				const size_t oldInd = reverse ? order[order.size() - 1 - cnt] : order[cnt];
+				++cnt;
+				vNewIndex[oldInd] = newInd;
+			}
+			if (cnt != order.size()) throw std::runtime_error("OrderCuthillMcKee: Not all indices sorted that must be sorted");
+			// findBlockSize (:68-95)
+			auto gcd = [](size_t a, size_t b) { while (b) { size_t r = a % b; a = b; b = r; } return a; };
+			size_t blockSize;
+			{
+				size_t cd = 0;
+				while (cd < nDoF && con[cd].empty()) ++cd;
+				if (cd == nDoF) blockSize = nDoF;
+				else {
+					size_t bs = 1;
+					for (size_t i = cd + 1; i < nDoF; ++i) {
+						if (con[i].empty()) { ++bs; continue; }
+						cd = gcd(bs, cd);
+						bs = 1;
+					}
+					blockSize = gcd(bs, cd);
+				}
+			}
+			for (size_t i = 0; i < nDoF; i += blockSize) if (vNewIndex[i] == (size_t)-1) vNewIndex[i] = i;
+			for (size_t i = 0; i < nDoF; i += blockSize) for (size_t j = 1; j < blockSize; ++j) vNewIndex[i + j] = vNewIndex[i] + j;
+		} else {                                                                             // :264-291
+			size_t sz = order.size();
+			for (size_t i = 0; i < sz; ++i) vNewIndex[reverse ? order[sz - 1 - i] : order[i]] = i;
+			size_t next = sz;
+			for (size_t i = 0; i < nDoF; ++i) if (vNewIndex[i] == (size_t)-1) vNewIndex[i] = next++;
+		}
+	}
+
 	// operator/linear_solver/lu.h:122-140 (init_dense) with the non-LAPACK kernels
 	// small_algebra/no_lapack/lu_decomp.h:45-75 (LUDecomp with row interchange)
 	DenseLU* lu_init(const Mat& A_) override

@@ -18,6 +18,9 @@
 #include "lib_algebra/algebra_common/core_smoothers.h"
 #include "lib_algebra/algebra_common/sparsematrix_util.h"
 #include "lib_algebra/common/operations_vec.h"
+// the real ILU kernels and Cuthill-McKee (made compilable without boost by ref_prelude.h)
+#include "lib_algebra/operator/preconditioner/ilu.h"
+#include "lib_algebra/algebra_common/permutation_util.h"
 
 #include <stdexcept>
 #include <map>
@@ -344,6 +347,37 @@ struct RefBackend : Backend {
 	void sgs_step(const Mat& A, Vec& c, const Vec& d, double relax) override
 	{
 #define CALL(B) ug::sgs_step(SM<B>(A), V<B>(c), V<B>(d), relax)
+		DISPATCH(A.block, CALL)
+#undef CALL
+	}
+
+	// ilu.h:563-576: m_ILU = mat; FactorizeILUBeta / FactorizeILUSorted (SparseMatrix::rows_sorted is true); defragment
+	Mat* ilu_factorize(const Mat& A, double beta, double sortEps) override
+	{
+		Mat* t = nullptr;
+#define CALL(B) { RMat<B>* m = new RMat<B>; m->nrows = A.nrows; m->ncols = A.ncols; m->block = B; m->A = SM<B>(A); \
+		if (beta != 0.0) ug::FactorizeILUBeta(m->A, beta); else ug::FactorizeILUSorted(m->A, sortEps); m->A.defragment(); t = m; }
+		DISPATCH(A.block, CALL)
+#undef CALL
+		return t;
+	}
+	void ilu_invert_L(const Mat& LU, Vec& x, const Vec& b) override
+	{
+#define CALL(B) ug::invert_L(SM<B>(LU), V<B>(x), V<B>(b))
+		DISPATCH(LU.block, CALL)
+#undef CALL
+	}
+	bool ilu_invert_U(const Mat& LU, Vec& x, const Vec& b, double eps) override
+	{
+		bool ok = true;
+#define CALL(B) ok = ug::invert_U(SM<B>(LU), V<B>(x), V<B>(b), eps)
+		DISPATCH(LU.block, CALL)
+#undef CALL
+		return ok;
+	}
+	void cuthill_mckee(const Mat& A, bool reverse, bool preserveConsec, std::vector<size_t>& newIndex) override
+	{
+#define CALL(B) ug::GetCuthillMcKeeOrder(SM<B>(A), newIndex, reverse, preserveConsec)
 		DISPATCH(A.block, CALL)
 #undef CALL
 	}

@@ -95,6 +95,21 @@ bool GaussSeidel::step(Vec& c, const Vec& d)
 	return true;
 }
 
+// ---- ILU (ilu.h) ---------------------------------------------------------------------------
+
+bool ILU::preprocess()
+{
+	factors.reset(bk.ilu_factorize(*A, beta, sortEps));   // m_ILU = mat; Factorize...(m_ILU) :563-576
+	h.reset(bk.vector(A->ncols, A->block));               // m_h.resize(m_ILU.num_cols()) :556
+	return true;
+}
+bool ILU::step(Vec& c, const Vec& d)
+{
+	bk.ilu_invert_L(*factors, *h, d);                     // h := L^-1 d      :596
+	bk.ilu_invert_U(*factors, c, *h, invEps);             // c := U^-1 h      :598
+	return true;
+}
+
 // ---- ILinearOperatorInverse::apply (preconditioned_linear_operator_inverse.h:152-160)
 
 bool InverseOperator::apply(Vec& x, const Vec& b)
@@ -228,6 +243,63 @@ bool LinearSolver::apply_return_defect(Vec& x, Vec& b)
 		else { bk.assign(*c, d); bk.matmul_minus(*A, d, *c); }
 		bk.add(x, *c);
 		conv.update_defect(bk.norm(d));
+	}
+	return conv.post();
+}
+
+// ---- GMRES (gmres.h:104-278) -----------------------------------------------------------------
+
+bool GMRES::apply_return_defect(Vec& x, Vec& b)
+{
+	VecP spR(bk.vector(b.n, b.block));
+	bk.assign(*spR, b);                                   // spR = b.clone()            :113
+	bk.matmul_minus(*A, *spR, x);                         // b - A x                    :116
+	conv.start_defect(bk.norm(*spR));                     //                            :122
+	const size_t m = restart;
+	std::vector<VecP> v(m + 1);
+	std::vector<std::vector<double> > h(m + 1, std::vector<double>(m + 1, 0.0));
+	std::vector<double> gamma(m + 1), c(m + 1), s(m + 1);
+	while (!conv.iteration_ended()) {
+		if (!v[0]) v[0].reset(bk.vector(x.n, x.block));
+		if (precond) { if (!precond->apply(*v[0], *spR)) return false; }        // :141-146
+		else std::swap(v[0], spR);                                                // :148-150
+		gamma[0] = bk.norm(*v[0]);                                                // :162
+		bk.scale(*v[0], 1. / gamma[0]);                                           // :165
+		size_t numIter = 0;
+		for (size_t j = 0; j < m; ++j) {
+			numIter = j;
+			if (!v[j + 1]) v[j + 1].reset(bk.vector(x.n, x.block));
+			bk.apply(*A, *spR, *v[j]);                                            // :182
+			if (precond) { if (!precond->apply(*v[j + 1], *spR)) return false; }  // :185-190
+			else std::swap(v[j + 1], spR);                                        // :192-194
+			for (size_t i = 0; i <= j; ++i) {
+				h[i][j] = bk.dot(*v[j + 1], *v[i]);                               // :211
+				bk.scale_add2(*v[j + 1], 1.0, *v[j + 1], (-1) * h[i][j], *v[i]);  // VecScaleAppend :214, :341-345
+			}
+			h[j + 1][j] = bk.norm(*v[j + 1]);                                     // :218
+			for (size_t i = 0; i < j; ++i) {                                      // :221-228
+				const double hij = h[i][j], hi1j = h[i + 1][j];
+				h[i][j] = c[i + 1] * hij + s[i + 1] * hi1j;
+				h[i + 1][j] = s[i + 1] * hij - c[i + 1] * hi1j;
+			}
+			const double alpha = std::sqrt(h[j][j] * h[j][j] + h[j + 1][j] * h[j + 1][j]);   // :231
+			s[j + 1] = h[j + 1][j] / alpha;
+			c[j + 1] = h[j][j] / alpha;
+			h[j][j] = alpha;
+			gamma[j + 1] = s[j + 1] * gamma[j];                                   // :239-240
+			gamma[j] = c[j + 1] * gamma[j];
+			if (!precond) conv.update_defect(gamma[j + 1]);                       // :242-252
+			bk.scale(*v[j + 1], 1. / (h[j + 1][j]));                              // :255
+		}
+		for (size_t i = numIter;; --i) {                                          // :259-269
+			for (size_t j = i + 1; j <= numIter; ++j) gamma[i] -= h[i][j] * gamma[j];
+			gamma[i] /= h[i][i];
+			bk.scale_add2(x, 1.0, x, gamma[i], *v[i]);
+			if (i == 0) break;
+		}
+		bk.assign(*spR, b);                                                       // :272-273
+		bk.matmul_minus(*A, *spR, x);
+		if (precond) conv.update_defect(bk.norm(*spR));                           // :275-276
 	}
 	return conv.post();
 }

@@ -16,6 +16,9 @@
  *   CG               lib_algebra/operator/linear_solver/cg.h:103-242
  *   BiCGStab         lib_algebra/operator/linear_solver/bicgstab.h:112-383
  *   LinearSolver     lib_algebra/operator/linear_solver/linear_solver.h:114-196
+ *   GMRES            lib_algebra/operator/linear_solver/gmres.h:104-278
+ *   ILU              lib_algebra/operator/preconditioner/ilu.h:516-660 (kernels through the Backend:
+ *                    the compiled reference's FactorizeILUSorted/Beta, invert_L, invert_U, or the port)
  *   GMG              lib_disc/operator/linear_operator/multi_grid_solver/
  *                    mg_solver_impl.hpp:174-275, 1685-1964, 1967-2136
  *   StdTransfer      lib_disc/operator/linear_operator/std_transfer_impl.h:738-740, 791-792
@@ -95,6 +98,18 @@ struct GaussSeidel : Preconditioner {
 	{ GaussSeidel* g = new GaussSeidel(bk, kind); g->relax = relax; g->damping = damping; return g; }
 };
 
+struct ILU : Preconditioner {
+	double beta = 0.0, sortEps = 1e-50, invEps = 1e-8; // ilu.h:352-355
+	std::unique_ptr<Mat> factors;
+	VecP h;
+	explicit ILU(Backend& b, double beta_ = 0.0) : Preconditioner(b), beta(beta_) {}
+	const char* name() const override { return "ILU"; }
+	bool preprocess() override;                        // ilu.h:516-588 (serial, no ordering algorithm)
+	bool step(Vec& c, const Vec& d) override;          // ilu.h:591-599, 648-652
+	LinearIterator* clone() const override
+	{ ILU* g = new ILU(bk, beta); g->sortEps = sortEps; g->invEps = invEps; g->damping = damping; return g; }
+};
+
 struct InverseOperator {
 	Backend& bk;
 	const Mat* A = nullptr;
@@ -139,6 +154,13 @@ struct BiCGStab : PrecondInverse {
 	double minOrtho = 0.0;
 	explicit BiCGStab(Backend& b) : PrecondInverse(b) {}
 	const char* name() const override { return "BiCGStab"; }
+	bool apply_return_defect(Vec& x, Vec& b) override;
+};
+
+struct GMRES : PrecondInverse {
+	size_t restart = 30;
+	explicit GMRES(Backend& b) : PrecondInverse(b) {}
+	const char* name() const override { return "GMRES"; }
 	bool apply_return_defect(Vec& x, Vec& b) override;
 };
 

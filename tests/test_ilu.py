@@ -1,0 +1,263 @@
+"""ILU(0) / ILU(beta), GMRES and Cuthill-McKee ordering.
+
+CPU (-m "not gpu"):
+  * the oracle's port of FactorizeILUSorted / FactorizeILUBeta / invert_L / invert_U / ComputeCuthillMcKeeOrder
+    against the REAL reference functions compiled into oracle/_ref (operator/preconditioner/ilu.h:110-322,
+    ordering_strategies/algorithms/native_cuthill_mckee.cpp) — bit for bit;
+  * the product's host-side factorisation and ordering (csrc/host/ilu_factor.h, through the C ABI) against
+    the same compiled reference — bit for bit;
+  * the level sets the device sweeps are scheduled by: valid (no dependency inside a level) and minimal;
+  * the oracle's restated GMRES and ILU-preconditioned solvers converge and agree with scipy's view of the
+    solution.
+GPU: ILU / GMRES solves against the oracle (first GPU run pending).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import gmg_desc, greedy_color_perm, permute_crs, rel_hist_err
+from ugcore_b200 import problems as pr
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+PROBLEMS = {
+    "poisson3d": lambda: pr.Problem(dim=3, num_refs=3),
+    "convdiff3d": lambda: pr.Problem(dim=3, num_refs=3, problem=pr.CONVDIFF, eps=1e-1),
+    "poisson2d": lambda: pr.Problem(dim=2, num_refs=4),
+    "hier3d": lambda: pr.Problem(dim=3, num_refs=3, order=pr.ORDER_HIER),
+}
+
+
+def _host_ilu(A, beta=0.0, sort_eps=1e-50):
+    from ugcore_b200.capi import check_host, host
+    va = np.array(A.vals, dtype=np.float64)
+    check_host(host.ug4b200_host_ilu_factorize(A.nrows, _p(np.ascontiguousarray(A.rowptr)), _p(np.ascontiguousarray(A.cols)),
+                                               _p(va), beta, sort_eps))
+    return va
+
+
+def _host_cmk(A, reverse, consec):
+    from ugcore_b200.capi import check_host, host
+    ni = np.zeros(A.nrows, np.int64)
+    check_host(host.ug4b200_host_cuthill_mckee(A.nrows, _p(np.ascontiguousarray(A.rowptr)), _p(np.ascontiguousarray(A.cols)),
+                                               int(reverse), int(consec), _p(ni)))
+    return ni
+
+
+def _host_levels(A, lower):
+    from ugcore_b200.capi import check_host, host
+    lev = np.zeros(A.nrows, np.int32)
+    nl = C.c_int()
+    check_host(host.ug4b200_host_level_sets(A.nrows, _p(np.ascontiguousarray(A.rowptr)), _p(np.ascontiguousarray(A.cols)),
+                                            int(lower), _p(lev), C.byref(nl)))
+    return lev, nl.value
+
+
+@pytest.mark.parametrize("kind", sorted(PROBLEMS))
+@pytest.mark.parametrize("beta", [0.0, 0.5])
+def test_ilu_factorisation_is_bit_identical_to_the_reference(kind, beta, orc, orc_ref):
+    prob = PROBLEMS[kind]()
+    A = prob.matrix()
+    rp, ci, va_ref = orc_ref.matrix(A).ilu(beta).export()
+    assert np.array_equal(rp, A.rowptr) and np.array_equal(ci, A.cols)          # ILU(0): the pattern is A's
+    assert np.array_equal(orc.matrix(A).ilu(beta).export()[2], va_ref)          # port of the oracle
+    assert np.array_equal(_host_ilu(A, beta), va_ref)                           # the product's host factorisation
+    # and one application of (LU)^-1: port == reference
+    d = np.random.default_rng(3).standard_normal(A.nrows)
+    assert np.array_equal(orc.matrix(A).ilu(beta).ilu_apply(d), orc_ref.matrix(A).ilu(beta).ilu_apply(d))
+
+
+def test_ilu_is_exact_on_its_pattern(orc_ref):
+    """ILU(0): (L U)_ij = A_ij wherever A stores an entry (Saad, Iterative Methods, Prop. 10.2)."""
+    import scipy.sparse as sp
+    A = PROBLEMS["convdiff3d"]().matrix()
+    rp, ci, va = orc_ref.matrix(A).ilu(0.0).export()
+    F = sp.csr_matrix((va, ci, rp), shape=(A.nrows, A.nrows))
+    L = sp.tril(F, -1) + sp.identity(A.nrows)
+    U = sp.triu(F, 0)
+    LU = (L @ U).tocsr()
+    S = A.to_scipy()
+    rows = np.repeat(np.arange(A.nrows), np.diff(A.rowptr))
+    assert np.allclose(np.asarray(LU[rows, A.cols]).ravel(), np.asarray(S[rows, A.cols]).ravel(), rtol=1e-12, atol=1e-14)
+
+
+def test_ilu_near_zero_pivot_is_reported():
+    from ugcore_b200.capi import host
+    rp = np.array([0, 2, 4], np.int64); ci = np.array([0, 1, 0, 1], np.int32); va = np.array([0.0, 1.0, 1.0, 1.0])
+    assert host.ug4b200_host_ilu_factorize(2, _p(rp), _p(ci), _p(va), 0.0, 1e-50) != 0
+    assert b"near-zero" in host.ug4b200_host_last_error()
+
+
+@pytest.mark.parametrize("kind", sorted(PROBLEMS))
+def test_cuthill_mckee_equals_the_reference(kind, orc, orc_ref):
+    A = PROBLEMS[kind]().matrix()
+    for reverse in (True, False):
+        for consec in (True, False):
+            ref = orc_ref.matrix(A).cuthill_mckee(reverse, consec)
+            assert np.array_equal(np.sort(ref), np.arange(A.nrows))
+            assert np.array_equal(orc.matrix(A).cuthill_mckee(reverse, consec), ref)
+            assert np.array_equal(_host_cmk(A, reverse, consec), ref)
+    # it does what it is for: the bandwidth of the hierarchically numbered matrix shrinks
+    if kind == "hier3d":
+        ni = _host_cmk(A, True, False)
+        rows = np.repeat(np.arange(A.nrows), np.diff(A.rowptr))
+        assert np.abs(ni[rows] - ni[A.cols]).max() < np.abs(rows - A.cols).max()
+
+
+def test_cuthill_mckee_with_unconnected_rows(orc, orc_ref):
+    """Rows without connections go to the end (bPreserveConsec = false) or keep their place (true)."""
+    from ugcore_b200.problems import Crs
+    A0 = pr.Problem(dim=2, num_refs=2).matrix()
+    keep = np.ones(A0.nrows, bool); keep[[3, 4, 11]] = False
+    lens = np.where(keep, np.diff(A0.rowptr), 0)
+    rows = np.repeat(np.arange(A0.nrows), np.diff(A0.rowptr))
+    sel = keep[rows] & keep[A0.cols]
+    lens = np.bincount(rows[sel], minlength=A0.nrows)
+    A = Crs(A0.nrows, A0.ncols, 1, np.concatenate([[0], np.cumsum(lens)]).astype(np.int64), A0.cols[sel].copy(), A0.vals[sel].copy())
+    for reverse in (True, False):
+        for consec in (True, False):
+            ref = orc_ref.matrix(A).cuthill_mckee(reverse, consec)
+            assert np.array_equal(orc.matrix(A).cuthill_mckee(reverse, consec), ref)
+            assert np.array_equal(_host_cmk(A, reverse, consec), ref)
+
+
+@pytest.mark.parametrize("kind", ["poisson3d", "hier3d"])
+def test_level_sets_schedule_the_triangular_solves(kind):
+    A = PROBLEMS[kind]().matrix()
+    rows = np.repeat(np.arange(A.nrows), np.diff(A.rowptr))
+    for lower in (True, False):
+        lev, nl = _host_levels(A, lower)
+        dep = (A.cols < rows) if lower else (A.cols > rows)
+        assert np.all(lev[A.cols[dep]] < lev[rows[dep]])              # a row only depends on earlier levels
+        need = np.zeros(A.nrows, np.int64)
+        np.maximum.at(need, rows[dep], lev[A.cols[dep]] + 1)
+        assert np.array_equal(need, lev) and nl == lev.max() + 1      # and sits on the earliest possible one
+    # a colour-sorted matrix has at most as many levels as colours
+    perm, cptr = greedy_color_perm(A)
+    lev, nl = _host_levels(permute_crs(A, perm, perm), True)
+    assert nl <= cptr.size - 1
+
+
+DESCS = {
+    "gmres_ilu": {"type": "gmres", "restart": 10, "precond": {"type": "ilu"}, "convCheck": {"iterations": 50, "absolute": 1e-12, "reduction": 1e-8}},
+    "gmres": {"type": "gmres", "restart": 20, "convCheck": {"iterations": 200, "absolute": 1e-12, "reduction": 1e-6}},
+    "bicgstab_ilub": {"type": "bicgstab", "precond": {"type": "ilu", "beta": 0.3}, "convCheck": {"iterations": 100, "absolute": 1e-12, "reduction": 1e-8}},
+    "cg_ilu": {"type": "cg", "precond": {"type": "ilu"}, "convCheck": {"iterations": 100, "absolute": 1e-12, "reduction": 1e-8}},
+    "linear_ilu": {"type": "linear", "precond": {"type": "ilu"}, "convCheck": {"iterations": 300, "absolute": 1e-12, "reduction": 1e-6}},
+}
+
+
+@pytest.mark.parametrize("name", sorted(DESCS))
+def test_oracle_solvers_with_ilu_and_gmres(name, orc, orc_ref):
+    """The restated GMRES (gmres.h:104-278) and ILU preconditioner on both backends: identical histories, and the
+    returned solution really has the defect the history claims."""
+    prob = PROBLEMS["poisson3d" if name == "cg_ilu" else "convdiff3d"]()
+    A = prob.matrix()
+    b = np.array(prob.rhs())
+    xr, okr, hr = oracle.OSolver(orc_ref, DESCS[name], orc_ref.matrix(A)).apply(b)
+    xp, okp, hp = oracle.OSolver(orc, DESCS[name], orc.matrix(A)).apply(b)
+    assert okr and okp and np.array_equal(hr, hp) and np.array_equal(xr, xp)
+    res = np.linalg.norm(b - A.to_scipy() @ xr)
+    assert abs(res - hr[-1]) <= 1e-6 * hr[0]
+    if name == "gmres":          # unpreconditioned: one convergence-check update per inner step, the last one of a cycle
+        assert (len(hr) - 1) % 20 == 0
+
+
+# ---- GPU ----------------------------------------------------------------------------------------------------
+pending = pytest.mark.skipif(os.environ.get("UG4B200_PENDING_GPU_TESTS") != "1",
+                             reason="first GPU run pending (set UG4B200_PENDING_GPU_TESTS=1)")
+
+
+def _best():
+    return oracle.Oracle("ref" if oracle.have_ref() else "port")
+
+
+@pending
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["poisson3d", "convdiff3d"])
+@pytest.mark.parametrize("beta", [0.0, 0.4])
+def test_gpu_ilu_multicolor_apply_is_bit_identical(kind, beta):
+    """One application of the ILU preconditioner in the multicolour ordering == the reference's
+    FactorizeILU* + invert_L + invert_U on the colour-permuted matrix, bit for bit."""
+    import ugcore_b200 as ug
+    prob = PROBLEMS[kind]()
+    A = prob.matrix()
+    desc = {"type": "linear", "precond": {"type": "ilu", "beta": beta, "ordering": "multicolor"},
+            "convCheck": {"iterations": 1, "absolute": 1e-30, "reduction": 1e-30}}
+    s = ug.Solver(desc, A)
+    d = np.random.default_rng(5).standard_normal(A.nrows)
+    c = s.precond_apply(d)
+    perm, _ = greedy_color_perm(A)
+    F = _best().matrix(permute_crs(A, perm, perm)).ilu(beta)
+    dp = np.empty_like(d); dp[perm] = d
+    assert np.array_equal(c, F.ilu_apply(dp)[perm])
+
+
+@pending
+@pytest.mark.gpu
+@pytest.mark.parametrize("ordering", ["natural", "cmk"])
+def test_gpu_ilu_level_scheduled_apply(ordering):
+    """Natural / Cuthill-McKee ordering: level-scheduled sweeps; same numbers as the reference up to the
+    order in which a row sums its terms."""
+    import ugcore_b200 as ug
+    prob = PROBLEMS["convdiff3d"]()
+    A = prob.matrix()
+    desc = {"type": "linear", "precond": {"type": "ilu", "ordering": ordering},
+            "convCheck": {"iterations": 1, "absolute": 1e-30, "reduction": 1e-30}}
+    c = ug.Solver(desc, A).precond_apply(np.array(prob.rhs()))
+    orc = _best()
+    if ordering == "cmk":
+        ni = orc.matrix(A).cuthill_mckee(False, True)        # NativeCuthillMcKeeOrdering: reverse = false, consecutive
+        F = orc.matrix(permute_crs(A, ni, ni)).ilu(0.0)
+        dp = np.empty(A.nrows); dp[ni] = prob.rhs()
+        ref = F.ilu_apply(dp)[ni]
+    else:
+        ref = orc.matrix(A).ilu(0.0).ilu_apply(np.array(prob.rhs()))
+    assert np.linalg.norm(c - ref) <= 1e-13 * np.linalg.norm(ref)
+
+
+@pending
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(DESCS))
+def test_gpu_solvers_with_ilu_and_gmres_match_oracle(name):
+    """CG / BiCGStab / LinearSolver / GMRES with ILU (natural ordering, level-scheduled) vs the oracle."""
+    import ugcore_b200 as ug
+    prob = PROBLEMS["poisson3d" if name == "cg_ilu" else "convdiff3d"]()
+    A = prob.matrix()
+    b = np.array(prob.rhs())
+    x, ok, h = ug.Solver(DESCS[name], A).apply(b)
+    orc = _best()
+    xo, oko, ho = oracle.OSolver(orc, DESCS[name], orc.matrix(A)).apply(b)
+    assert ok and oko and abs(len(h) - len(ho)) <= 1
+    tol = 1e-8 if name in ("bicgstab_ilub", "gmres") else 1e-10      # BiCGStab / unrestarted GMRES amplify round-off
+    assert rel_hist_err(h, ho) < tol
+    assert np.linalg.norm(x - xo) <= 1e-7 * np.linalg.norm(xo)
+
+
+@pending
+@pytest.mark.gpu
+def test_gpu_gmg_with_ilu_smoother_matches_oracle():
+    """GMG V(2,2) with ILU(0) smoothing in the multicolour ordering + CG: the oracle runs on the colour-permuted
+    hierarchy (like the Gauss-Seidel test)."""
+    import ugcore_b200 as ug
+    prob = pr.Problem(dim=3, num_refs=3)
+    desc = gmg_desc(3, smoother={"type": "ilu", "ordering": "multicolor"})
+    x, ok, h = ug.Solver.from_problem(desc, prob).apply(prob.rhs())
+    orc = _best()
+    perms = {l: (greedy_color_perm(prob.matrix(l))[0] if l else np.arange(prob.matrix(0).nrows)) for l in range(0, 4)}
+    lv = {}
+    for l in range(0, 4):
+        lv[l] = (orc.matrix(permute_crs(prob.matrix(l), perms[l], perms[l])),
+                 orc.matrix(permute_crs(prob.prolongation(l), perms[l], perms[l - 1])) if l else None,
+                 orc.matrix(permute_crs(prob.restriction(l), perms[l - 1], perms[l])) if l else None)
+    bp = np.empty(prob.num_dofs); bp[perms[3]] = prob.rhs()
+    xo, oko, ho = oracle.OSolver(orc, desc, lv[3][0], lv).apply(bp)
+    assert ok and oko and abs(len(h) - len(ho)) <= 1
+    assert rel_hist_err(h, ho) < 1e-10
+    assert np.linalg.norm(x - xo[perms[3]]) <= 1e-9 * np.linalg.norm(xo)

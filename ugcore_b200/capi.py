@@ -48,7 +48,8 @@ class SolverDesc(C.Structure):
                 ("max_steps", c_int), ("min_defect", c_dbl), ("rel_reduction", c_dbl),
                 ("base_lev", c_int), ("top_lev", c_int), ("cycle", c_int), ("nu1", c_int), ("nu2", c_int),
                 ("smoother", c_int), ("smoother_damp", c_dbl), ("base_solver", c_int), ("base_max_steps", c_int),
-                ("base_min_defect", c_dbl), ("base_rel_reduction", c_dbl), ("flags", c_int), ("gather_lev", c_int)]
+                ("base_min_defect", c_dbl), ("base_rel_reduction", c_dbl), ("flags", c_int), ("gather_lev", c_int),
+                ("restart", c_int), ("ilu_beta", c_dbl), ("ilu_order", c_int)]
 
 
 FIN_STORE, FIN_A_DIV_R, FIN_R_DIV_A, FIN_SQRT, FIN_CONV_START, FIN_CONV_UPDATE = range(6)
@@ -165,6 +166,9 @@ HOST_API = {
     "ug4b200_solver_set_coloring": (c_int, [c_vp, c_int, c_i64, c_vp, c_int, c_vp]),
     "ug4b200_solver_set_layouts": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_i64]),
     "ug4b200_solver_set_smoother_matrix": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),
+    "ug4b200_host_ilu_factorize": (c_int, [c_i64, c_vp, c_vp, c_vp, c_dbl, c_dbl]),
+    "ug4b200_host_level_sets": (c_int, [c_i64, c_vp, c_vp, c_int, c_vp, C.POINTER(c_int)]),
+    "ug4b200_host_cuthill_mckee": (c_int, [c_i64, c_vp, c_vp, c_int, c_int, c_vp]),
     "ug4b200_solver_set_gathered_base": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "ug4b200_solver_set_gathered_level": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ug4b200_solver_init": (c_int, [c_vp]),

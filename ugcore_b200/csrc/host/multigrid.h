@@ -187,6 +187,8 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 					if (j) j->set_layouts(ld.layouts);
 					GaussSeidelBase<TAlgebra>* g = dynamic_cast<GaussSeidelBase<TAlgebra>*>(s.get());
 					if (g) { g->set_layouts(ld.layouts); g->set_consistent_matrix(ld.layouts ? ld.Aconsistent : SmartPtr<matrix_type>()); }
+					ILU<TAlgebra>* ilu = dynamic_cast<ILU<TAlgebra>*>(s.get());
+					if (ilu) { ilu->set_layouts(ld.layouts); ilu->set_consistent_matrix(ld.layouts ? ld.Aconsistent : SmartPtr<matrix_type>()); }
 				}
 				if (!ld.PreSmoother->init(ld.A)) UG_THROW("GMG::init: Cannot init pre-smoother for level " << lev);
 				if (ld.PostSmoother != ld.PreSmoother && !ld.PostSmoother->init(ld.A))

@@ -8,8 +8,11 @@
 // Multicolour GS = the reference's lexicographic sweep applied in a colour-sorted DoF
 // order; the reordering follows the pattern ILU uses for its ordering algorithms
 // (ilu.h:434-461 SetMatrixAsPermutation, :593-610 SetVectorAsPermutation).
+//   ILU               ugbase/lib_algebra/operator/preconditioner/ilu.h:324-700 (factorisation on the host at
+//                     init: ilu_factor.h; triangular solves = the Gauss-Seidel sweep kernels over the two factors)
 #pragma once
 #include "operators.h"
+#include "ilu_factor.h"
 
 namespace ug {
 
@@ -255,6 +258,272 @@ class GaussSeidelBase : public IPreconditioner<TAlgebra> {
 	ug4b200_matrix* m_PA = nullptr;
 	int* m_dPerm = nullptr;
 	double *m_pd = nullptr, *m_pc = nullptr;
+	size_t m_n = 0;
+	SmartPtr<GPUAlgebraLayouts> m_layouts;
+	SmartPtr<matrix_type> m_spConsistent;
+	vector_type m_dUnique;
+};
+
+/// ILU(0) / ILU(beta) (ilu.h:324-700).  preprocess keeps ugcore's sequence — copy of the matrix, parallel:
+/// slave rows added to the master rows + Dirichlet rows on the slaves (:536-543), ordering (:434-461),
+/// FactorizeILUSorted / FactorizeILUBeta (:573-575) — on the host; the factors are then split into
+/// L (strictly lower part + unit diagonal) and U (diagonal + upper part) and uploaded.  invert_L (:233-252) is
+/// a forward Gauss-Seidel sweep over L with relaxation 1 (c_i = 1.0 * (d_i - sum_j<i l_ij c_j) / 1.0), invert_U
+/// (:257-322) a backward sweep over U (c_i = 1.0 * (d_i - sum_j>i u_ij c_j) / u_ii): the same expressions as
+/// the reference's, evaluated by the sweep kernels group by group, where a group is a set of rows without
+/// mutual dependencies:
+///   * colour-sorted ordering (set_coloring / set_multicolor_ordering, the ordering "algorithm" made for the
+///     device): groups = colours, rows keep their order -> bit-identical to the reference's ILU in that ordering;
+///   * any other ordering (natural, Cuthill-McKee, user): groups = level sets of the factor's dependency graph
+///     (level scheduling); rows are renumbered by level, so a row accumulates its terms in another order than
+///     the reference does (round-off level differences), and a sweep costs one launch per level.
+/// invert_U's "near-zero last diagonal entry" guard (ilu.h:285-297, set_inversion_eps) is not evaluated on the
+/// device.  Scalar algebra only.
+template <typename TAlgebra>
+class ILU : public IPreconditioner<TAlgebra> {
+  public:
+	typedef typename TAlgebra::vector_type vector_type;
+	typedef typename TAlgebra::matrix_type matrix_type;
+	typedef IPreconditioner<TAlgebra> base_type;
+	typedef typename base_type::matrix_operator_type matrix_operator_type;
+	typedef std::vector<size_t> ordering_container_type;
+	enum { B = TAlgebra::blockSize };
+
+	explicit ILU(double beta = 0.0) : m_beta(beta) {}
+	~ILU() { free_dev(); }
+	virtual const char* name() const { return "ILU"; }
+	virtual bool supports_parallel() const { return true; }
+	virtual SmartPtr<ILinearIterator<vector_type> > clone()
+	{
+		SmartPtr<ILU> c(new ILU(m_beta));
+		c->m_sortEps = m_sortEps; c->m_invEps = m_invEps; c->m_bDisablePreprocessing = m_bDisablePreprocessing;
+		c->m_mode = m_mode; c->m_userOrdering = m_userOrdering; c->m_userColorPtr = m_userColorPtr;
+		c->set_damp(this->damping());
+		return c;
+	}
+	void set_beta(double beta) { m_beta = beta; }
+	void set_sort_eps(number eps) { m_sortEps = eps; }
+	void set_inversion_eps(number eps) { m_invEps = eps; }
+	void set_disable_preprocessing(bool b) { m_bDisablePreprocessing = b; }
+	/// ILU::set_sort(true) (ilu.h:403-414): NativeCuthillMcKeeOrdering, i.e. ComputeCuthillMcKeeOrder(o, neighbours,
+	/// reverse = false, preserveConsec = true) (native_cuthill_mckee.h:101, 124)
+	void set_sort(bool b) { m_mode = b ? ORDER_CMK : ORDER_NONE; }
+	/// what set_ordering_algorithm(..) ends in (ilu.h:434-461): ordering[old] = new
+	void set_ordering(const ordering_container_type& o) { m_userOrdering = o; m_userColorPtr.clear(); m_mode = ORDER_USER; }
+	/// colour-sorted ordering with its colour offsets (see class comment)
+	void set_coloring(const std::vector<int>& perm, const std::vector<int64_t>& colorPtr)
+	{ m_userOrdering.assign(perm.begin(), perm.end()); m_userColorPtr = colorPtr; m_mode = ORDER_USER; }
+	/// greedy multicolour ordering of the stored pattern (the one the Gauss-Seidel smoothers use)
+	void set_multicolor_ordering(bool b) { m_mode = b ? ORDER_COLOR : ORDER_NONE; }
+	/// partitioned runs: see GaussSeidelBase
+	void set_layouts(SmartPtr<GPUAlgebraLayouts> l) { m_layouts = l; }
+	void set_consistent_matrix(SmartPtr<matrix_type> A) { m_spConsistent = A; }
+	int num_groups_L() const { return (int)m_ptrL.size() - 1; }
+	int num_groups_U() const { return (int)m_ptrU.size() - 1; }
+
+  protected:
+	enum { ORDER_NONE = 0, ORDER_CMK, ORDER_COLOR, ORDER_USER };
+
+	virtual bool preprocess(SmartPtr<matrix_operator_type> pOp)
+	{
+		if (m_bDisablePreprocessing && m_L) return true;
+		if (B != 1) UG_THROW("ILU: only the scalar GPU algebra is supported (block ILU: use Jacobi / Gauss-Seidel)");
+		matrix_type* pA = &static_cast<matrix_type&>(*pOp);
+		if (m_layouts) {
+			if (!m_spConsistent) UG_THROW("ILU: a partitioned matrix needs its consistent counterpart (set_consistent_matrix)");
+			pA = m_spConsistent.get();
+		}
+		matrix_type& A = *pA;
+		THROW_IF_NOT_EQUAL(A.num_rows(), A.num_cols());
+		const int64_t n = (int64_t)A.num_rows();
+		const std::vector<int64_t>& rp = A.crs_rowptr();
+		const std::vector<int>& ci = A.crs_cols();
+		std::vector<double> va = A.crs_vals();                 // m_ILU = mat (ilu.h:533)
+		if (m_layouts) {
+			// rows of the h-slaves become Dirichlet rows (ilu.h:539-543)
+			const std::vector<int> slaves = m_layouts->slave_indices();
+			for (size_t k = 0; k < slaves.size(); ++k) {
+				const int r = slaves[k];
+				bool haveDiag = false;
+				for (int64_t p = rp[r]; p < rp[r + 1]; ++p) { va[p] = 0.0; if (ci[p] == r) { va[p] = 1.0; haveDiag = true; } }
+				if (!haveDiag) UG_THROW("ILU: interface row " << r << " has no diagonal connection");
+			}
+		}
+		// ---- ordering (apply_ordering, ilu.h:434-461) ----
+		std::vector<size_t> ord((size_t)n);
+		std::vector<int64_t> colorPtr;
+		for (int64_t i = 0; i < n; ++i) ord[(size_t)i] = (size_t)i;
+		if (m_mode == ORDER_CMK) GetCuthillMcKeeOrder(n, rp.data(), ci.data(), ord, false, true);
+		else if (m_mode == ORDER_COLOR) {
+			std::vector<int> color((size_t)(n > 0 ? n : 1)); int nc = 0;
+			ug4b200_color_greedy(n, rp.data(), ci.data(), color.data(), &nc);
+			colorPtr.assign((size_t)nc + 1, 0);
+			for (int64_t i = 0; i < n; ++i) colorPtr[(size_t)color[(size_t)i] + 1]++;
+			for (int k = 0; k < nc; ++k) colorPtr[(size_t)k + 1] += colorPtr[(size_t)k];
+			std::vector<int64_t> fill(colorPtr.begin(), colorPtr.end() - 1);
+			for (int64_t i = 0; i < n; ++i) ord[(size_t)i] = (size_t)fill[(size_t)color[(size_t)i]]++;
+		} else if (m_mode == ORDER_USER) {
+			THROW_IF_NOT_EQUAL(m_userOrdering.size(), (size_t)n);
+			ord = m_userOrdering; colorPtr = m_userColorPtr;
+		}
+		{
+			std::vector<char> seen((size_t)n, 0);
+			for (int64_t i = 0; i < n; ++i) {
+				if (ord[(size_t)i] >= (size_t)n || seen[ord[(size_t)i]]) UG_THROW("ILU: the ordering is not a permutation");
+				seen[ord[(size_t)i]] = 1;
+			}
+		}
+		// PA(ord[r], ord[c]) = A(r, c)  (SetMatrixAsPermutation, permutation_util.h:50-64)
+		std::vector<int64_t> prp; std::vector<int> pci; std::vector<double> pva;
+		permute(n, rp, ci, va, ord, ord, prp, pci, pva);
+		// ---- factorisation (ilu.h:573-575; SparseMatrix::rows_sorted == true) ----
+		if (m_beta != 0.0) FactorizeILUBeta(n, prp, pci, pva, m_beta);
+		else FactorizeILUSorted(n, prp, pci, pva, m_sortEps);
+		// ---- split into L (unit diagonal) and U ----
+		std::vector<int64_t> lrp((size_t)n + 1, 0), urp((size_t)n + 1, 0);
+		std::vector<int> lci, uci; std::vector<double> lva, uva;
+		for (int64_t i = 0; i < n; ++i) {
+			bool haveDiag = false;
+			for (int64_t p = prp[(size_t)i]; p < prp[(size_t)i + 1]; ++p) {
+				if (pci[(size_t)p] < i) { lci.push_back(pci[(size_t)p]); lva.push_back(pva[(size_t)p]); }
+				else { if (pci[(size_t)p] == i) haveDiag = true; uci.push_back(pci[(size_t)p]); uva.push_back(pva[(size_t)p]); }
+			}
+			if (!haveDiag) UG_THROW("ILU: row " << i << " has no diagonal entry");
+			lci.push_back((int)i); lva.push_back(1.0);
+			lrp[(size_t)i + 1] = (int64_t)lci.size(); urp[(size_t)i + 1] = (int64_t)uci.size();
+		}
+		// ---- groups of independent rows ----
+		std::vector<size_t> permL((size_t)n), permU((size_t)n);
+		bool identity = true;
+		if (!colorPtr.empty()) {
+			if (ug4b200_color_check(n, prp.data(), pci.data(), (int)colorPtr.size() - 1, colorPtr.data()) != 0)
+				UG_THROW("ILU: the given ordering is not a valid multicolour ordering of the matrix pattern");
+			for (int64_t i = 0; i < n; ++i) permL[(size_t)i] = permU[(size_t)i] = (size_t)i;
+			m_ptrL = colorPtr; m_ptrU = colorPtr;
+		} else {
+			std::vector<int> lev;
+			const int nl = level_sets(n, lrp, lci, true, lev);
+			sort_by_level(n, lev, nl, false, permL, m_ptrL);
+			const int nu = level_sets(n, urp, uci, false, lev);
+			sort_by_level(n, lev, nu, true, permU, m_ptrU);
+			for (int64_t i = 0; i < n && identity; ++i) identity = permL[(size_t)i] == (size_t)i && permU[(size_t)i] == (size_t)i;
+			if (!identity) {
+				std::vector<int64_t> rp2; std::vector<int> ci2; std::vector<double> va2;
+				permute(n, lrp, lci, lva, permL, permL, rp2, ci2, va2); lrp.swap(rp2); lci.swap(ci2); lva.swap(va2);
+				permute(n, urp, uci, uva, permU, permU, rp2, ci2, va2); urp.swap(rp2); uci.swap(ci2); uva.swap(va2);
+			}
+		}
+		// ---- upload ----
+		free_dev();
+		ug4b200_ctx* ctx = GPUManager::ctx();
+		UG_GPU_CHECK(ug4b200_matrix_upload_crs(ctx, 1, n, n, lrp.data(), lci.data(), lva.data(), UG4B200_MAT_DEFAULT, &m_L));
+		UG_GPU_CHECK(ug4b200_matrix_upload_crs(ctx, 1, n, n, urp.data(), uci.data(), uva.data(), UG4B200_MAT_DEFAULT, &m_U));
+		m_n = (size_t)n;
+		std::vector<int> mapIn((size_t)n), mapLU((size_t)n), mapOut((size_t)n);
+		for (int64_t i = 0; i < n; ++i) {
+			mapIn[(size_t)i] = (int)permL[ord[(size_t)i]];             // dL[mapIn[i]] = d[i]
+			mapOut[(size_t)i] = (int)permU[ord[(size_t)i]];            // c[i] = cU[mapOut[i]]
+			mapLU[permU[(size_t)i]] = (int)permL[(size_t)i];           // yU[j] = yL[mapLU[j]]
+		}
+		m_bSameOrder = identity;
+		m_dIn = upload_ints(mapIn); m_dOut = upload_ints(mapOut); m_dLU = m_bSameOrder ? nullptr : upload_ints(mapLU);
+		UG_GPU_CHECK(ug4b200_sync(ctx));
+		m_t0 = GPUManager::alloc(m_n); m_t1 = GPUManager::alloc(m_n);
+		if (m_layouts) { m_dUnique.create(m_n); m_dUnique.set_layouts(m_layouts); }
+		return true;
+	}
+
+	/// ILU::step (ilu.h:614-655) with applyLU (:591-611)
+	virtual bool step(SmartPtr<matrix_operator_type>, vector_type& c, const vector_type& d)
+	{
+		ug4b200_ctx* ctx = GPUManager::ctx();
+		if (m_n == 0) return true;
+		const double* dsrc = d.dev();
+		if (m_layouts) {
+			m_dUnique = d;                                                  // make defect unique (:640-644)
+			if (!m_dUnique.change_storage_type(PST_UNIQUE)) UG_THROW("ILU: cannot make the defect unique");
+			dsrc = m_dUnique.dev();
+		}
+		const int64_t n = (int64_t)m_n;
+		UG_GPU_CHECK(ug4b200_vec_scatter(ctx, n, 1, m_t0, m_dIn, dsrc));                                            // SetVectorAsPermutation(tmp, d, ordering)
+		UG_GPU_CHECK(ug4b200_gs_step(ctx, m_L, (int)m_ptrL.size() - 1, m_ptrL.data(), 0, 1.0, m_t1, m_t0));           // invert_L
+		if (m_bSameOrder) {
+			UG_GPU_CHECK(ug4b200_gs_step(ctx, m_U, (int)m_ptrU.size() - 1, m_ptrU.data(), 1, 1.0, m_t0, m_t1));       // invert_U
+		} else {
+			UG_GPU_CHECK(ug4b200_vec_gather(ctx, n, 1, m_t0, m_t1, m_dLU));
+			UG_GPU_CHECK(ug4b200_gs_step(ctx, m_U, (int)m_ptrU.size() - 1, m_ptrU.data(), 1, 1.0, m_t1, m_t0));
+			std::swap(m_t0, m_t1);
+		}
+		UG_GPU_CHECK(ug4b200_vec_gather(ctx, n, 1, c.dev(), m_t0, m_dOut));                                          // SetVectorAsPermutation(c, tmp, old_ordering)
+		if (m_layouts) {
+			c.set_storage_type(PST_ADDITIVE);                               // :646
+			if (!c.change_storage_type(PST_CONSISTENT)) return false;       // :652
+		} else c.set_storage_type(PST_CONSISTENT);
+		return true;
+	}
+	virtual bool postprocess() { return true; }
+
+	/// B(pr[r], pc[c]) = A(r, c), rows sorted
+	static void permute(int64_t n, const std::vector<int64_t>& rp, const std::vector<int>& ci, const std::vector<double>& va,
+	                    const std::vector<size_t>& pr, const std::vector<size_t>& pc, std::vector<int64_t>& orp, std::vector<int>& oci,
+	                    std::vector<double>& ova)
+	{
+		std::vector<size_t> inv((size_t)n);
+		for (int64_t i = 0; i < n; ++i) inv[pr[(size_t)i]] = (size_t)i;
+		orp.assign((size_t)n + 1, 0);
+		for (int64_t nr = 0; nr < n; ++nr) orp[(size_t)nr + 1] = orp[(size_t)nr] + (rp[inv[(size_t)nr] + 1] - rp[inv[(size_t)nr]]);
+		oci.resize(ci.size()); ova.resize(va.size());
+		std::vector<std::pair<int, int64_t> > row;
+		for (int64_t nr = 0; nr < n; ++nr) {
+			const size_t r = inv[(size_t)nr];
+			row.clear();
+			for (int64_t p = rp[r]; p < rp[r + 1]; ++p) row.push_back(std::make_pair((int)pc[(size_t)ci[(size_t)p]], p));
+			std::sort(row.begin(), row.end());
+			int64_t q = orp[(size_t)nr];
+			for (size_t k = 0; k < row.size(); ++k, ++q) { oci[(size_t)q] = row[k].first; ova[(size_t)q] = va[(size_t)row[k].second]; }
+		}
+	}
+	/// rows grouped by level, stable inside a level; descending = true puts the highest level first (U: the
+	/// backward sweep walks the groups from the last to the first)
+	static void sort_by_level(int64_t n, const std::vector<int>& lev, int nlev, bool descending, std::vector<size_t>& perm,
+	                          std::vector<int64_t>& ptr)
+	{
+		ptr.assign((size_t)nlev + 1, 0);
+		for (int64_t i = 0; i < n; ++i) { const int g = descending ? nlev - 1 - lev[(size_t)i] : lev[(size_t)i]; ptr[(size_t)g + 1]++; }
+		for (int g = 0; g < nlev; ++g) ptr[(size_t)g + 1] += ptr[(size_t)g];
+		std::vector<int64_t> fill(ptr.begin(), ptr.end() - 1);
+		for (int64_t i = 0; i < n; ++i) { const int g = descending ? nlev - 1 - lev[(size_t)i] : lev[(size_t)i]; perm[(size_t)i] = (size_t)fill[(size_t)g]++; }
+	}
+	static int* upload_ints(const std::vector<int>& v)
+	{
+		int* d = (int*)GPUManager::alloc_bytes(sizeof(int) * (v.empty() ? 1 : v.size()));
+		UG_GPU_CHECK(ug4b200_h2d(GPUManager::ctx(), d, v.data(), sizeof(int) * v.size()));
+		return d;
+	}
+	void free_dev()
+	{
+		ug4b200_ctx* c = GPUManager::ctx_or_null();
+		if (m_L && c) ug4b200_matrix_destroy(c, m_L);
+		if (m_U && c) ug4b200_matrix_destroy(c, m_U);
+		m_L = m_U = nullptr;
+		GPUManager::free_bytes(m_dIn); GPUManager::free_bytes(m_dOut); GPUManager::free_bytes(m_dLU);
+		m_dIn = m_dOut = m_dLU = nullptr;
+		if (m_t0) GPUManager::release(m_t0, m_n);
+		if (m_t1) GPUManager::release(m_t1, m_n);
+		m_t0 = m_t1 = nullptr;
+	}
+
+	double m_beta;
+	number m_sortEps = 1e-50, m_invEps = 1e-8;
+	bool m_bDisablePreprocessing = false;
+	int m_mode = ORDER_NONE;
+	ordering_container_type m_userOrdering;
+	std::vector<int64_t> m_userColorPtr;
+	ug4b200_matrix *m_L = nullptr, *m_U = nullptr;
+	std::vector<int64_t> m_ptrL, m_ptrU;
+	int *m_dIn = nullptr, *m_dOut = nullptr, *m_dLU = nullptr;
+	bool m_bSameOrder = true;
+	double *m_t0 = nullptr, *m_t1 = nullptr;
 	size_t m_n = 0;
 	SmartPtr<GPUAlgebraLayouts> m_layouts;
 	SmartPtr<matrix_type> m_spConsistent;

@@ -3,6 +3,7 @@
 //   CG            ugbase/lib_algebra/operator/linear_solver/cg.h:103-242
 //   BiCGStab      ugbase/lib_algebra/operator/linear_solver/bicgstab.h:112-383
 //   LinearSolver  ugbase/lib_algebra/operator/linear_solver/linear_solver.h:114-196
+//   GMRES         ugbase/lib_algebra/operator/linear_solver/gmres.h:64-351
 //   LU            ugbase/lib_algebra/operator/linear_solver/lu.h:122-380
 //                 (dense kernels no_lapack/lu_decomp.h:45-75, 160-195)
 //
@@ -328,6 +329,106 @@ class BiCGStab : public IPreconditionedLinearOperatorInverse<TVector> {
   protected:
 	int m_numRestarts;
 	number m_minOrtho;
+};
+
+/// GMRES(restart), left preconditioned (gmres.h:104-278), reference-shaped: vector work on the device, the
+/// Hessenberg matrix and the Givens rotations (a few dozen scalars) on the host, one sync per dot / norm.
+/// As in the reference every cycle runs all `restart` inner steps; with a preconditioner the convergence check
+/// sees the true defect once per cycle (:275-276), without one the rotated residual norm of every inner
+/// step (:249-251).
+template <typename TVector>
+class GMRES : public IPreconditionedLinearOperatorInverse<TVector> {
+  public:
+	typedef TVector vector_type;
+	typedef IPreconditionedLinearOperatorInverse<TVector> base_type;
+	using base_type::convergence_check;
+	using base_type::linear_operator;
+	using base_type::preconditioner;
+
+	explicit GMRES(size_t restart) : m_restart(restart) {}
+	virtual const char* name() const { return "GMRES"; }
+
+	virtual bool apply_return_defect(vector_type& x, vector_type& b)
+	{
+		const bool par = (bool)x.layouts();
+		if (par && (!b.has_storage_type(PST_ADDITIVE) || !x.has_storage_type(PST_CONSISTENT)))
+			UG_THROW("GMRES: Inadequate storage format of Vectors.");
+		if (m_restart == 0) UG_THROW("GMRES: restart must be positive");
+		SmartPtr<vector_type> spR = b.clone();                       // copy rhs
+		linear_operator()->apply_sub(*spR, x);                       // b - A x
+		convergence_check()->start(*spR);
+		std::vector<SmartPtr<vector_type> > v(m_restart + 1);
+		std::vector<std::vector<number> > h(m_restart + 1);
+		for (size_t i = 0; i < h.size(); ++i) h[i].resize(m_restart + 1);
+		std::vector<number> gamma(m_restart + 1), c(m_restart + 1), s(m_restart + 1);
+		while (!convergence_check()->iteration_ended()) {
+			if (!v[0]) v[0] = x.clone_without_values();
+			// v[0] = M^-1 (b - A x), or reuse the defect vector
+			if (preconditioner()) { if (!preconditioner()->apply(*v[0], *spR)) return false; }
+			else std::swap(v[0], spR);
+			if (par && !v[0]->change_storage_type(PST_UNIQUE)) UG_THROW("GMRES: Cannot convert v0 to consistent vector.");
+			gamma[0] = v[0]->norm();
+			*v[0] *= 1. / gamma[0];
+			size_t numIter = 0;
+			for (size_t j = 0; j < m_restart; ++j) {
+				numIter = j;
+				if (!v[j + 1]) v[j + 1] = x.clone_without_values();
+				if (par && !v[j]->change_storage_type(PST_CONSISTENT)) UG_THROW("GMRES: Cannot convert v[" << j + 1 << "] to consistent vector.");
+				linear_operator()->apply(*spR, *v[j]);                 // r = A v[j]
+				if (preconditioner()) { if (!preconditioner()->apply(*v[j + 1], *spR)) return false; }
+				else std::swap(v[j + 1], spR);
+				if (par) {
+					if (!v[j]->change_storage_type(PST_UNIQUE)) UG_THROW("GMRES: Cannot convert v0 to consistent vector.");
+					if (!v[j + 1]->change_storage_type(PST_UNIQUE)) UG_THROW("GMRES: Cannot convert v[" << j << "] to consistent vector.");
+				}
+				for (size_t i = 0; i <= j; ++i) {
+					h[i][j] = v[j + 1]->dotprod(*v[i]);                // h_ij := (v[j+1], v[i])
+					VecScaleAppend(*v[j + 1], *v[i], (-1) * h[i][j]);  // v[j+1] -= h_ij v[i]
+				}
+				h[j + 1][j] = v[j + 1]->norm();
+				for (size_t i = 0; i < j; ++i) {                       // apply the previous rotations to the new column
+					const number hij = h[i][j], hi1j = h[i + 1][j];
+					h[i][j] = c[i + 1] * hij + s[i + 1] * hi1j;
+					h[i + 1][j] = s[i + 1] * hij - c[i + 1] * hi1j;
+				}
+				const number alpha = std::sqrt(h[j][j] * h[j][j] + h[j + 1][j] * h[j + 1][j]);
+				s[j + 1] = h[j + 1][j] / alpha;
+				c[j + 1] = h[j][j] / alpha;
+				h[j][j] = alpha;
+				gamma[j + 1] = s[j + 1] * gamma[j];
+				gamma[j] = c[j + 1] * gamma[j];
+				if (!preconditioner()) convergence_check()->update_defect(gamma[j + 1]);
+				*v[j + 1] *= 1. / (h[j + 1][j]);
+			}
+			for (size_t i = numIter;; --i) {                           // back substitution, x += gamma_i v[i]
+				for (size_t j = i + 1; j <= numIter; ++j) gamma[i] -= h[i][j] * gamma[j];
+				gamma[i] /= h[i][i];
+				VecScaleAppend(x, *v[i], gamma[i]);
+				if (i == 0) break;
+			}
+			*spR = b;                                                  // fresh defect
+			linear_operator()->apply_sub(*spR, x);
+			if (preconditioner()) convergence_check()->update(*spR);
+		}
+		return convergence_check()->post();
+	}
+
+  protected:
+	/// a += s * b with the storage-type reconciliation of gmres.h:326-347
+	bool VecScaleAppend(vector_type& a, vector_type& b, number s)
+	{
+		if (a.layouts()) {
+			if (a.has_storage_type(PST_UNIQUE) && b.has_storage_type(PST_UNIQUE)) {}
+			else if (a.has_storage_type(PST_CONSISTENT) && b.has_storage_type(PST_CONSISTENT)) {}
+			else if (a.has_storage_type(PST_ADDITIVE) && b.has_storage_type(PST_ADDITIVE)) {}
+			else { a.change_storage_type(PST_ADDITIVE); b.change_storage_type(PST_ADDITIVE); }
+		}
+		const unsigned type = a.get_storage_mask();
+		VecScaleAdd(a, 1.0, a, s, b);
+		a.set_storage_type(type);                                      // the element loop of the reference leaves a's type alone
+		return true;
+	}
+	size_t m_restart;
 };
 
 /// LinearSolver (linear_solver.h:114-196): x += B(b - A x) until converged

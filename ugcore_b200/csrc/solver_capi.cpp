@@ -78,6 +78,7 @@ struct SolverImpl : SolverBase {
 			}
 			case UG4B200_SOLVER_BICGSTAB: { SmartPtr<BiCGStab<vector_type> > s = make_sp<BiCGStab<vector_type> >(); s->set_preconditioner(precond); inv = s; break; }
 			case UG4B200_SOLVER_LINEAR: { SmartPtr<LinearSolver<vector_type> > s = make_sp<LinearSolver<vector_type> >(); s->set_preconditioner(precond); inv = s; break; }
+			case UG4B200_SOLVER_GMRES: { SmartPtr<GMRES<vector_type> > s = make_sp<GMRES<vector_type> >((size_t)(d.restart > 0 ? d.restart : 30)); s->set_preconditioner(precond); inv = s; break; }
 			case UG4B200_SOLVER_LU: inv = make_sp<LU<TAlgebra> >(); break;
 			case UG4B200_SOLVER_COARSE_CG: inv = make_sp<CoarseCG<TAlgebra> >(); break;
 			default: UG_THROW("unknown solver " << d.solver);
@@ -113,6 +114,13 @@ struct SolverImpl : SolverBase {
 			case UG4B200_PRECOND_GS: { SmartPtr<GaussSeidel<TAlgebra> > g = make_sp<GaussSeidel<TAlgebra> >(); g->set_sor_relax(damp); return g; }
 			case UG4B200_PRECOND_BGS: { SmartPtr<BackwardGaussSeidel<TAlgebra> > g = make_sp<BackwardGaussSeidel<TAlgebra> >(); g->set_sor_relax(damp); return g; }
 			case UG4B200_PRECOND_SGS: { SmartPtr<SymmetricGaussSeidel<TAlgebra> > g = make_sp<SymmetricGaussSeidel<TAlgebra> >(); g->set_sor_relax(damp); return g; }
+			case UG4B200_PRECOND_ILU: {
+				SmartPtr<ILU<TAlgebra> > g = make_sp<ILU<TAlgebra> >(d.ilu_beta);
+				if (d.ilu_order == UG4B200_ILU_ORDER_CMK) g->set_sort(true);
+				else if (d.ilu_order == UG4B200_ILU_ORDER_MULTICOLOR) g->set_multicolor_ordering(true);
+				else if (d.ilu_order != UG4B200_ILU_ORDER_NATURAL) UG_THROW("unknown ILU ordering " << d.ilu_order);
+				return g;
+			}
 		}
 		UG_THROW("unknown smoother / preconditioner kind " << kind);
 	}
@@ -198,6 +206,11 @@ struct SolverImpl : SolverBase {
 		if (g && top_layouts()) {
 			g->set_layouts(top_layouts());
 			if (!smootherMatrix.empty()) g->set_consistent_matrix(smootherMatrix.rbegin()->second);
+		}
+		ILU<TAlgebra>* ilu = dynamic_cast<ILU<TAlgebra>*>(precond.get());
+		if (ilu && top_layouts()) {
+			ilu->set_layouts(top_layouts());
+			if (!smootherMatrix.empty()) ilu->set_consistent_matrix(smootherMatrix.rbegin()->second);
 		}
 		x.create(A->num_cols()); b.create(A->num_rows());
 		x.set_layouts(top_layouts()); b.set_layouts(top_layouts());
@@ -403,6 +416,42 @@ int ug4b200_host_rap(int64_t nc, int64_t nf, const int64_t* r_rowptr, const int*
 		AddMultiplyOf(m->A, R, A, P);
 		m->pos.resize(0);
 		*out = m.release();
+		return 0;
+	});
+}
+int ug4b200_host_ilu_factorize(int64_t n, const int64_t* rowptr, const int* cols, double* vals, double beta, double sort_eps)
+{
+	return guard([&] {
+		std::vector<int64_t> rp(rowptr, rowptr + n + 1);
+		std::vector<int> ci(cols, cols + rp[(size_t)n]);
+		std::vector<double> va(vals, vals + rp[(size_t)n]);
+		for (int64_t i = 0; i < n; ++i)
+			for (int64_t p = rp[(size_t)i] + 1; p < rp[(size_t)i + 1]; ++p)
+				if (ci[(size_t)p - 1] >= ci[(size_t)p]) UG_THROW("ILU: columns of row " << i << " are not sorted");
+		if (beta != 0.0) FactorizeILUBeta(n, rp, ci, va, beta);
+		else FactorizeILUSorted(n, rp, ci, va, sort_eps);
+		std::memcpy(vals, va.data(), sizeof(double) * va.size());
+		return 0;
+	});
+}
+int ug4b200_host_level_sets(int64_t n, const int64_t* rowptr, const int* cols, int lower, int* level, int* nlevels)
+{
+	return guard([&] {
+		std::vector<int64_t> rp(rowptr, rowptr + n + 1);
+		std::vector<int> ci(cols, cols + rp[(size_t)n]);
+		std::vector<int> lev;
+		*nlevels = level_sets(n, rp, ci, lower != 0, lev);
+		for (int64_t i = 0; i < n; ++i) level[i] = lev[(size_t)i];
+		return 0;
+	});
+}
+int ug4b200_host_cuthill_mckee(int64_t n, const int64_t* rowptr, const int* cols, int reverse, int preserve_consec,
+                               int64_t* new_index)
+{
+	return guard([&] {
+		std::vector<size_t> ni;
+		GetCuthillMcKeeOrder(n, rowptr, cols, ni, reverse != 0, preserve_consec != 0);
+		for (size_t i = 0; i < ni.size(); ++i) new_index[i] = (int64_t)ni[i];
 		return 0;
 	});
 }

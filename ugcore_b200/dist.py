@@ -273,7 +273,7 @@ def default_gather_level(refs: int, part, base: int = 0, max_local_rows: int = 4
     return lev
 
 
-GS_KINDS = ("gs", "bgs", "sgs")
+GS_KINDS = ("gs", "bgs", "sgs", "ilu")   # smoothers that sweep over the CONSISTENT level matrix in partitioned runs
 
 
 def _smoother_kind(desc: dict):

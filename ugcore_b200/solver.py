@@ -15,8 +15,9 @@ import numpy as np
 from . import capi
 from .capi import check, check_host, host, dev
 
-SOLVER = {"cg": 0, "bicgstab": 1, "linear": 2, "lu": 3, "coarse_cg": 4}
-PRECOND = {None: 0, "none": 0, "jac": 1, "jacobi": 1, "gs": 2, "bgs": 3, "sgs": 4, "gmg": 5}
+SOLVER = {"cg": 0, "bicgstab": 1, "linear": 2, "lu": 3, "coarse_cg": 4, "gmres": 5}
+PRECOND = {None: 0, "none": 0, "jac": 1, "jacobi": 1, "gs": 2, "bgs": 3, "sgs": 4, "gmg": 5, "ilu": 6}
+ILU_ORDER = {None: 0, "natural": 0, "none": 0, "cmk": 1, "cuthill-mckee": 1, "multicolor": 2, "multicolour": 2}
 
 _host_ready = False
 
@@ -60,6 +61,8 @@ def make_desc(desc: dict, block: int = 1, flags: int = 0) -> capi.SolverDesc:
         pc = {"type": pc}
     d.precond = PRECOND[pc["type"] if pc else None]
     d.damp = 1.0
+    d.restart = desc.get("restart", 30)          # GMRES(restart), solver_util.lua: gmres.restart
+    d.ilu_beta, d.ilu_order = 0.0, 0
     d.cycle, d.nu1, d.nu2 = 1, 2, 2
     d.smoother, d.smoother_damp = 1, 0.66
     d.base_solver, d.base_max_steps, d.base_min_defect, d.base_rel_reduction = 3, 1000, 1e-30, 1e-14
@@ -68,11 +71,17 @@ def make_desc(desc: dict, block: int = 1, flags: int = 0) -> capi.SolverDesc:
             d.damp = pc.get("damp", 0.66)
         elif pc["type"] in ("gs", "bgs", "sgs"):
             d.damp = pc.get("relax", 1.0)
+        elif pc["type"] == "ilu":                # solver_util.lua: ilu = {beta, sort, ...}
+            d.ilu_beta = pc.get("beta", 0.0)
+            d.ilu_order = ILU_ORDER[pc.get("ordering", "cmk" if pc.get("sort") else None)]
         elif pc["type"] == "gmg":
             sm = pc.get("smoother", {"type": "jac", "damp": 0.66})
             if isinstance(sm, str):
                 sm = {"type": sm}
             d.smoother = PRECOND[sm["type"]]
+            if sm["type"] == "ilu":
+                d.ilu_beta = sm.get("beta", 0.0)
+                d.ilu_order = ILU_ORDER[sm.get("ordering", "cmk" if sm.get("sort") else None)]
             d.smoother_damp = sm.get("damp", 0.66) if d.smoother == 1 else sm.get("relax", 1.0)
             d.cycle = {"V": 1, "W": 2, "F": -1}[pc.get("cycle", "V")]
             d.nu1 = pc.get("preSmooth", 2)
@@ -122,15 +131,73 @@ class DeviceBuffer:
             pass
 
 
+def cuthill_mckee(A, reverse: bool = True, preserve_consec: bool = False):
+    """new index of every old index: ugcore's native Cuthill-McKee on the matrix graph (GetCuthillMcKeeOrder,
+    ugbase/lib_algebra/algebra_common/permutation_util.h:96-114; same result as the reference).  Host only."""
+    ni = np.zeros(A.nrows, np.int64)
+    rp, ci = np.ascontiguousarray(A.rowptr, np.int64), np.ascontiguousarray(A.cols, np.int32)
+    check_host(host.ug4b200_host_cuthill_mckee(A.nrows, _ptr(rp), _ptr(ci), int(reverse), int(preserve_consec), _ptr(ni)))
+    return ni
+
+
+def permute_crs(A, prow, pcol):
+    """B(prow[r], pcol[c]) = A(r, c) with sorted rows, explicit zeros kept (SetMatrixAsPermutation,
+    permutation_util.h:50-64, generalised to rectangular transfers)."""
+    from .problems import Crs
+    bb = A.block * A.block
+    rows = np.repeat(np.arange(A.nrows), np.diff(A.rowptr))
+    pr_, pc_ = np.asarray(prow)[rows], np.asarray(pcol)[np.asarray(A.cols)]
+    key = np.lexsort((pc_, pr_))
+    rp = np.concatenate([[0], np.cumsum(np.bincount(pr_, minlength=A.nrows))]).astype(np.int64)
+    vals = np.asarray(A.vals).reshape(-1, bb)[key].ravel().copy()
+    return Crs(A.nrows, A.ncols, A.block, rp, pc_[key].astype(np.int32), vals)
+
+
+def reorder_hierarchy(A, levels, order):
+    """DoF reordering before upload: every level is renumbered by ``order`` —
+    "cmk" / "rcmk" (Cuthill-McKee / reverse Cuthill-McKee of the level matrix) or a dict level -> permutation
+    (new index of every old index).  Returns (A', levels', perms); the level matrices, P (rows: fine, columns:
+    coarse numbering) and R are permuted consistently."""
+    top = max(levels) if levels else None
+    mats = {l: t[0] for l, t in levels.items()} if levels else {None: A}
+    if levels and mats.get(top) is None:
+        mats[top] = A
+    perms = {}
+    for l, M in mats.items():
+        if isinstance(order, dict):
+            perms[l] = np.asarray(order[l], dtype=np.int64)
+        elif M is None:
+            raise ValueError(f"reordering needs the level matrix of level {l} (not available with rap=True)")
+        elif order in ("cmk", "rcmk"):
+            perms[l] = cuthill_mckee(M, reverse=(order == "rcmk"))
+        else:
+            raise ValueError(f"unknown ordering {order!r}")
+    if not levels:
+        return permute_crs(A, perms[None], perms[None]), None, perms
+    out = {}
+    for l, (Al, Pl, Rl) in levels.items():
+        out[l] = (permute_crs(Al, perms[l], perms[l]) if Al is not None else None,
+                  permute_crs(Pl, perms[l], perms[l - 1]) if Pl is not None else None,
+                  permute_crs(Rl, perms[l - 1], perms[l]) if Rl is not None else None)
+    return permute_crs(A, perms[top], perms[top]), out, perms
+
+
 class Solver:
-    """CG / BiCGStab / LinearSolver with Jacobi / GS / GMG preconditioning on the GPU.
+    """CG / BiCGStab / LinearSolver / GMRES with Jacobi / GS / ILU / GMG preconditioning on the GPU.
 
     ``A`` is a host CRS (``problems.Crs``); ``levels`` maps level -> (A_l, P_l, R_l) for GMG
     (P_l, R_l None on the base level).  ``Solver.from_problem`` wires a synthetic hierarchy.
+    ``order``: DoF reordering applied before upload (``reorder_hierarchy``); ``apply`` takes and returns
+    vectors in the caller's numbering.
     """
 
-    def __init__(self, desc: dict, A, levels: dict | None = None, flags: int = 0):
+    def __init__(self, desc: dict, A, levels: dict | None = None, flags: int = 0, order=None):
         host_init()
+        self.perm = None
+        if order is not None:
+            A, levels, perms = reorder_hierarchy(A, levels, order)
+            p = perms[max(levels)] if levels else perms[None]
+            self.perm = np.repeat(p * A.block, A.block) + np.tile(np.arange(A.block), p.size)
         self.block = A.block
         pc = desc.get("precond")
         # gmg:set_rap(true): the level operators below the top level are Galerkin products computed at init
@@ -157,7 +224,7 @@ class Solver:
         self._inited = False
 
     @classmethod
-    def from_problem(cls, desc: dict, prob, flags: int = 0) -> "Solver":
+    def from_problem(cls, desc: dict, prob, flags: int = 0, order=None) -> "Solver":
         desc = dict(desc)
         pc = desc.get("precond")
         levels = None
@@ -171,7 +238,7 @@ class Solver:
                 base = lev == pc["baseLevel"]
                 levels[lev] = (prob.matrix(lev), None if base else prob.prolongation(lev),
                                None if base else prob.restriction(lev))
-        s = cls(desc, prob.matrix(desc["precond"]["topLevel"] if levels else None), levels, flags)
+        s = cls(desc, prob.matrix(desc["precond"]["topLevel"] if levels else None), levels, flags, order=order)
         s._keep.append(prob)
         return s
 
@@ -220,11 +287,18 @@ class Solver:
             self.init()
         b = np.ascontiguousarray(b, dtype=np.float64)
         x = np.zeros(self.n) if x0 is None else np.ascontiguousarray(x0, dtype=np.float64).copy()
+        if self.perm is not None:      # Pv[perm[i]] = v[i]  (SetVectorAsPermutation, permutation_util.h:72-78)
+            bp, xp = np.empty_like(b), np.empty_like(x)
+            bp[self.perm], xp[self.perm] = b, x
+            rc = check_host(host.ug4b200_solver_apply(self.h, _ptr(xp), _ptr(bp)))
+            return xp[self.perm], rc == 0, self.history()
         rc = check_host(host.ug4b200_solver_apply(self.h, _ptr(x), _ptr(b)))
         return x, rc == 0, self.history()
 
     def apply_pinned(self, x_ptr: int, b_ptr: int) -> bool:
         """Same through raw host pointers (e.g. pinned torch tensors): x in/out, b in."""
+        if self.perm is not None:
+            raise ValueError("apply_pinned works in the solver's own numbering: permute the vectors (Solver.perm) or use apply")
         if not self._inited:
             self.init()
         return check_host(host.ug4b200_solver_apply(self.h, C.c_void_p(x_ptr), C.c_void_p(b_ptr))) == 0
@@ -242,6 +316,11 @@ class Solver:
             self.init()
         d = np.ascontiguousarray(d, dtype=np.float64)
         c = np.zeros(self.n)
+        if self.perm is not None:
+            dp = np.empty_like(d)
+            dp[self.perm] = d
+            check_host(host.ug4b200_solver_precond_apply(self.h, _ptr(c), _ptr(dp)))
+            return c[self.perm]
         check_host(host.ug4b200_solver_precond_apply(self.h, _ptr(c), _ptr(d)))
         return c
 
