@@ -7,7 +7,7 @@
 // The factorisation is init-time work on the assembled matrix (everything before
 // solver:apply stays on the CPU); it runs here on the defragmented CRS arrays with the reference's loop
 // order and operations, so the factors are bit-identical to ugcore's (tests/test_ilu.py compares them with
-// the reference's own FactorizeILUSorted / FactorizeILUBeta compiled into oracle/_ref).  The triangular
+// the reference's own FactorizeILUSorted / FactorizeILUBeta, compiled for the tests).  The triangular
 // solves run on the device (preconditioners.h: ILU) as level-scheduled sweeps: level_sets() below groups the
 // rows of a triangular factor so that a row only depends on rows of earlier groups.
 #pragma once
