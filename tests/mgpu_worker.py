@@ -9,6 +9,7 @@ on the same global grid.
                             ugcore's parallel Gauss-Seidel is a block Jacobi over the ranks with GS inside
                             (gauss_seidel.h:134-142, 204-215) -> compared with the serial oracle of exactly
                             that method (helpers.partitioned_gs_oracle)
+  case "convdiff_ilu"       the same with ILU(0) smoothing (ilu.h:536-543, 640-652: same parallel structure)
 """
 import json
 import os
@@ -45,12 +46,15 @@ def main():
     elif case == "convdiff_gs":
         problem, kw = pr.CONVDIFF, {"eps": 1e-1}
         desc = gmg_desc(refs, solver="bicgstab", smoother={"type": "gs", "relax": 1.0}, reduction=1e-8)
+    elif case == "convdiff_ilu":   # ILU(0) smoothing, multicolour ordering inside a rank; parallel mode of ilu.h:536-543, 640-652
+        problem, kw = pr.CONVDIFF, {"eps": 1e-1}
+        desc = gmg_desc(refs, solver="bicgstab", smoother={"type": "ilu", "ordering": "multicolor"}, reduction=1e-8)
     else:
         raise SystemExit(f"unknown case {case}")
     prob, s = ugdist.build_partitioned_solver(desc, refs, part, rank, dist, problem=problem, flags=flags, **kw)
     x, ok, h = s.apply(prob.rhs())
 
-    if case == "convdiff_gs":
+    if case in ("convdiff_gs", "convdiff_ilu"):
         solve, gprob = partitioned_gs_oracle(orc, desc, refs, part, s.desc.gather_lev, problem=problem, **kw)
         xo, oko, ho = solve(np.array(gprob.rhs()))
     else:

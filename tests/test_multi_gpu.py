@@ -44,6 +44,13 @@ def test_partitioned_bicgstab_gmg_gauss_seidel_matches_oracle(world, flags, p2p,
 
 
 @pending
+@pytest.mark.parametrize("world,flags,p2p,gather", [(2, 0, 1, -1), (4, 0, 0, 0)])
+def test_partitioned_bicgstab_gmg_ilu_matches_oracle(world, flags, p2p, gather):
+    """The same with ILU(0) smoothing in the multicolour ordering (parallel ILU of ilu.h:536-543, 640-652)."""
+    _run(world, flags, p2p, gather, "convdiff_ilu", 1e-8, 1e-7)
+
+
+@pending
 @pytest.mark.parametrize("world,flags,p2p,gather", [(2, 0, 1, -1), (8, 0, 1, -1), (2, 0, 0, 0)])
 def test_partitioned_elasticity_block3_matches_serial_oracle(world, flags, p2p, gather):
     """BASELINE configs[4] partitioned: 3x3-block GMG-CG, block interface exchange."""
