@@ -164,6 +164,9 @@ int ug4b200_io_write_vector(const char* filename, int64_t n, const double* value
  * matrix with sorted rows, in place in vals: L below the diagonal (unit diagonal implied), U on and above it.
  * Bit-identical to the reference's factorisation. */
 int ug4b200_host_ilu_factorize(int64_t n, const int64_t* rowptr, const int* cols, double* vals, double beta, double sort_eps);
+/* same for block x block entries (block*block doubles per entry, column-major; block = 1, 2, 3) */
+int ug4b200_host_ilu_factorize_block(int block, int64_t n, const int64_t* rowptr, const int* cols, double* vals, double beta,
+                                     double sort_eps);
 /* level sets of the lower (lower != 0) or upper triangle of a stored pattern: level[i] = longest dependency chain below
  * row i — rows of one level can be solved in one launch of the sweep kernel; *nlevels out */
 int ug4b200_host_level_sets(int64_t n, const int64_t* rowptr, const int* cols, int lower, int* level, int* nlevels);

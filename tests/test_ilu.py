@@ -73,6 +73,21 @@ def test_ilu_factorisation_is_bit_identical_to_the_reference(kind, beta, orc, or
     assert np.array_equal(orc.matrix(A).ilu(beta).ilu_apply(d), orc_ref.matrix(A).ilu(beta).ilu_apply(d))
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("beta", [0.0, 0.4])
+def test_block_ilu_factorisation_is_bit_identical_to_the_reference(dim, beta, orc_ref):
+    """2x2 / 3x3 blocks (elasticity): DenseMatrix /=, *, -= and the Cramer inverses restated in
+    csrc/host/ilu_factor.h against the real small_algebra templates under the reference's FactorizeILU*."""
+    from ugcore_b200.capi import check_host, host
+    prob = pr.Problem(dim=dim, num_refs=2 if dim == 3 else 3, problem=pr.ELASTICITY)
+    A = prob.matrix()
+    assert A.block == dim
+    va = np.array(A.vals, dtype=np.float64)
+    check_host(host.ug4b200_host_ilu_factorize_block(A.block, A.nrows, _p(np.ascontiguousarray(A.rowptr)),
+                                                     _p(np.ascontiguousarray(A.cols)), _p(va), beta, 1e-50))
+    assert np.array_equal(va, orc_ref.matrix(A).ilu(beta).export()[2])
+
+
 def test_ilu_is_exact_on_its_pattern(orc_ref):
     """ILU(0): (L U)_ij = A_ij wherever A stores an entry (Saad, Iterative Methods, Prop. 10.2)."""
     import scipy.sparse as sp
@@ -197,6 +212,33 @@ def test_gpu_ilu_multicolor_apply_is_bit_identical(kind, beta):
     F = _best().matrix(permute_crs(A, perm, perm)).ilu(beta)
     dp = np.empty_like(d); dp[perm] = d
     assert np.array_equal(c, F.ilu_apply(dp)[perm])
+
+
+@pending
+@pytest.mark.gpu
+def test_gpu_block_ilu_multicolor_apply_and_solve():
+    """3x3-block ILU(0) on elasticity: one application bit-identical to the reference in the multicolour ordering,
+    and ILU-preconditioned CG (natural ordering, level-scheduled) vs the oracle."""
+    import ugcore_b200 as ug
+    if not oracle.have_ref():
+        pytest.skip("block ILU oracle needs oracle/_ref (the port restates the scalar case only)")
+    orc = oracle.Oracle("ref")
+    prob = pr.Problem(dim=3, num_refs=2, problem=pr.ELASTICITY)
+    A, b = prob.matrix(), prob.block
+    desc = {"type": "cg", "precond": {"type": "ilu", "ordering": "multicolor"},
+            "convCheck": {"iterations": 100, "absolute": 1e-12, "reduction": 1e-8}}
+    d = np.random.default_rng(8).standard_normal(A.nrows * b)
+    c = ug.Solver(desc, A).precond_apply(d)
+    perm, _ = greedy_color_perm(A)
+    pp = np.repeat(perm * b, b) + np.tile(np.arange(b), perm.size)
+    dp = np.empty_like(d); dp[pp] = d
+    assert np.array_equal(c, orc.matrix(permute_crs(A, perm, perm)).ilu(0.0).ilu_apply(dp)[pp])
+    desc["precond"] = {"type": "ilu"}
+    x, ok, h = ug.Solver(desc, A).apply(prob.rhs())
+    xo, oko, ho = oracle.OSolver(orc, desc, orc.matrix(A)).apply(np.array(prob.rhs()))
+    assert ok and oko and abs(len(h) - len(ho)) <= 1
+    assert rel_hist_err(h, ho) < 1e-9
+    assert np.linalg.norm(x - xo) <= 1e-8 * np.linalg.norm(xo)
 
 
 @pending

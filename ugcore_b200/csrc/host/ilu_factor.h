@@ -30,9 +30,147 @@ inline int64_t find(const std::vector<int64_t>& rp, const std::vector<int>& ci, 
 }
 } // namespace ilu_detail
 
+// ---- B x B blocks, column-major like FixedArray2 (small_algebra/storage/fixed_array_impl.h:182-203): the few
+//      DenseMatrix operations the factorisation uses, with the reference's evaluation order ----
+namespace ilu_detail {
+#define UG_BLK(m, r, c) (m)[(r) + B * (c)]
+/// Invert(mat) for 1x1 / 2x2 / 3x3 (small_matrix/densematrix_inverse.h:75-86, 121-147, 172-229); false if singular
+template <int B> inline bool blk_invert(double* m)
+{
+	if (B == 1) { if (m[0] == 0.0) return false; m[0] = 1.0 / m[0]; return true; }
+	if (B == 2) {
+		double invdet = UG_BLK(m, 0, 0) * UG_BLK(m, 1, 1) - UG_BLK(m, 1, 0) * UG_BLK(m, 0, 1);
+		if (invdet == 0.0) return false;
+		invdet = 1.0 / invdet;
+		std::swap(UG_BLK(m, 0, 0), UG_BLK(m, 1, 1));
+		UG_BLK(m, 0, 0) *= invdet; UG_BLK(m, 0, 1) *= -invdet; UG_BLK(m, 1, 0) *= -invdet; UG_BLK(m, 1, 1) *= invdet;
+		return true;
+	}
+	double invdet = UG_BLK(m, 0, 0) * UG_BLK(m, 1, 1) * UG_BLK(m, 2, 2) + UG_BLK(m, 0, 1) * UG_BLK(m, 1, 2) * UG_BLK(m, 2, 0) +
+	                UG_BLK(m, 0, 2) * UG_BLK(m, 1, 0) * UG_BLK(m, 2, 1) - UG_BLK(m, 0, 0) * UG_BLK(m, 1, 2) * UG_BLK(m, 2, 1) -
+	                UG_BLK(m, 0, 1) * UG_BLK(m, 1, 0) * UG_BLK(m, 2, 2) - UG_BLK(m, 0, 2) * UG_BLK(m, 1, 1) * UG_BLK(m, 2, 0);
+	if (invdet == 0.0) return false;
+	invdet = 1.0 / invdet;
+	double inv[9];
+	UG_BLK(inv, 0, 0) = ( UG_BLK(m, 1, 1) * UG_BLK(m, 2, 2) - UG_BLK(m, 1, 2) * UG_BLK(m, 2, 1)) * invdet;
+	UG_BLK(inv, 0, 1) = (-UG_BLK(m, 0, 1) * UG_BLK(m, 2, 2) + UG_BLK(m, 0, 2) * UG_BLK(m, 2, 1)) * invdet;
+	UG_BLK(inv, 0, 2) = ( UG_BLK(m, 0, 1) * UG_BLK(m, 1, 2) - UG_BLK(m, 0, 2) * UG_BLK(m, 1, 1)) * invdet;
+	UG_BLK(inv, 1, 0) = (-UG_BLK(m, 1, 0) * UG_BLK(m, 2, 2) + UG_BLK(m, 1, 2) * UG_BLK(m, 2, 0)) * invdet;
+	UG_BLK(inv, 1, 1) = ( UG_BLK(m, 0, 0) * UG_BLK(m, 2, 2) - UG_BLK(m, 0, 2) * UG_BLK(m, 2, 0)) * invdet;
+	UG_BLK(inv, 1, 2) = (-UG_BLK(m, 0, 0) * UG_BLK(m, 1, 2) + UG_BLK(m, 0, 2) * UG_BLK(m, 1, 0)) * invdet;
+	UG_BLK(inv, 2, 0) = ( UG_BLK(m, 1, 0) * UG_BLK(m, 2, 1) - UG_BLK(m, 1, 1) * UG_BLK(m, 2, 0)) * invdet;
+	UG_BLK(inv, 2, 1) = (-UG_BLK(m, 0, 0) * UG_BLK(m, 2, 1) + UG_BLK(m, 0, 1) * UG_BLK(m, 2, 0)) * invdet;
+	UG_BLK(inv, 2, 2) = ( UG_BLK(m, 0, 0) * UG_BLK(m, 1, 1) - UG_BLK(m, 0, 1) * UG_BLK(m, 1, 0)) * invdet;
+	for (int t = 0; t < 9; ++t) m[t] = inv[t];
+	return true;
+}
+/// erg = a * b (DenseMatrix::operator*, densematrix_impl.h:251-267: erg(r,c) = 0; erg(r,c) += a(r,i) * b(i,c))
+template <int B> inline void blk_mul(double* erg, const double* a, const double* b)
+{
+	for (int r = 0; r < B; ++r)
+		for (int c = 0; c < B; ++c) {
+			double e = 0.0;
+			for (int i = 0; i < B; ++i) e += UG_BLK(a, r, i) * UG_BLK(b, i, c);
+			UG_BLK(erg, r, c) = e;
+		}
+}
+/// a /= d: a = a * d^-1 (densematrix_impl.h:191-200)
+template <int B> inline void blk_div(double* a, const double* d)
+{
+	double tmp[B * B], erg[B * B];
+	for (int t = 0; t < B * B; ++t) tmp[t] = d[t];
+	if (!blk_invert<B>(tmp)) UG_THROW("Failed to invert dense matrix.");
+	blk_mul<B>(erg, a, tmp);
+	for (int t = 0; t < B * B; ++t) a[t] = erg[t];
+}
+/// a -= b * c
+template <int B> inline void blk_sub_mul(double* a, const double* b, const double* c)
+{
+	double erg[B * B];
+	blk_mul<B>(erg, b, c);
+	for (int r = 0; r < B; ++r) for (int cc = 0; cc < B; ++cc) UG_BLK(a, r, cc) -= UG_BLK(erg, r, cc);
+}
+/// BlockNorm (small_algebra/blocks.h:51-60): Frobenius norm
+template <int B> inline double blk_norm(const double* a)
+{
+	double s = 0.0;
+	for (int t = 0; t < B * B; ++t) s += a[t] * a[t];
+	return std::sqrt(s);
+}
+#undef UG_BLK
+} // namespace ilu_detail
+
+/// ILU(0) on the stored pattern, rows sorted (ilu.h:174-228); B x B block entries, B*B doubles each
+template <int B>
+inline void FactorizeILUSortedBlock(int64_t n, const std::vector<int64_t>& rp, const std::vector<int>& ci, std::vector<double>& va,
+                                    number eps = 1e-50)
+{
+	const int BB = B * B;
+	std::vector<int64_t> diag((size_t)n);
+	for (int64_t i = 0; i < n; ++i) diag[(size_t)i] = ilu_detail::find(rp, ci, i, (int)i);
+	for (int64_t i = 1; i < n; ++i) {
+		for (int64_t pik = rp[(size_t)i]; pik != rp[(size_t)i + 1] && ci[(size_t)pik] < i; ++pik) {
+			const int k = ci[(size_t)pik];
+			if (diag[(size_t)k] < 0) UG_THROW("ILU: row " << k << " has no diagonal entry");
+			double* a_ik = &va[(size_t)pik * BB];
+			const double* a_kk = &va[(size_t)diag[(size_t)k] * BB];
+			if (std::fabs(ilu_detail::blk_norm<B>(a_kk)) < eps * ilu_detail::blk_norm<B>(a_ik))
+				UG_THROW("ILU: Blocknorm of diagonal is near-zero for k=" << k << " with eps: " << eps);
+			ilu_detail::blk_div<B>(a_ik, a_kk);
+			int64_t pij = pik + 1, pkj = rp[(size_t)k];
+			const int64_t ei = rp[(size_t)i + 1], ek = rp[(size_t)k + 1];
+			while (pij != ei && pkj != ek) {
+				if (ci[(size_t)pij] > ci[(size_t)pkj]) ++pkj;
+				else if (ci[(size_t)pij] < ci[(size_t)pkj]) ++pij;
+				else { ilu_detail::blk_sub_mul<B>(&va[(size_t)pij * BB], a_ik, &va[(size_t)pkj * BB]); ++pkj; ++pij; }
+			}
+		}
+	}
+}
+
+/// ILU(beta) with blocks (ilu.h:110-171)
+template <int B>
+inline void FactorizeILUBetaBlock(int64_t n, const std::vector<int64_t>& rp, const std::vector<int>& ci, std::vector<double>& va, number beta)
+{
+	const int BB = B * B;
+	for (int64_t i = 1; i < n; ++i) {
+		const int64_t dii = ilu_detail::find(rp, ci, i, (int)i);
+		if (dii < 0) UG_THROW("ILU: row " << i << " has no diagonal entry");
+		double Nii[BB];
+		for (int t = 0; t < BB; ++t) { Nii[t] = va[(size_t)dii * BB + t]; Nii[t] *= 0.0; }
+		for (int64_t pik = rp[(size_t)i]; pik != rp[(size_t)i + 1] && ci[(size_t)pik] < i; ++pik) {
+			const int k = ci[(size_t)pik];
+			const int64_t dkk = ilu_detail::find(rp, ci, k, k);
+			if (dkk < 0) UG_THROW("ILU: row " << k << " has no diagonal entry");
+			double* a_ik = &va[(size_t)pik * BB];
+			ilu_detail::blk_div<B>(a_ik, &va[(size_t)dkk * BB]);
+			for (int64_t pkj = rp[(size_t)k]; pkj != rp[(size_t)k + 1]; ++pkj) {
+				const int j = ci[(size_t)pkj];
+				if (j <= k) continue;
+				const int64_t pij = ilu_detail::find(rp, ci, i, j);
+				if (pij >= 0) ilu_detail::blk_sub_mul<B>(&va[(size_t)pij * BB], a_ik, &va[(size_t)pkj * BB]);
+				else ilu_detail::blk_sub_mul<B>(Nii, a_ik, &va[(size_t)pkj * BB]);
+			}
+		}
+		for (int t = 0; t < BB; ++t) va[(size_t)dii * BB + t] += beta * Nii[t];   // AddMult(Aii, beta, Nii)
+	}
+}
+
+/// dispatch on the block size (1: the scalar routines below)
+inline void FactorizeILUSorted(int64_t n, const std::vector<int64_t>& rp, const std::vector<int>& ci, std::vector<double>& va, number eps);
+inline void FactorizeILUBeta(int64_t n, const std::vector<int64_t>& rp, const std::vector<int>& ci, std::vector<double>& va, number beta);
+inline void FactorizeILU(int block, int64_t n, const std::vector<int64_t>& rp, const std::vector<int>& ci, std::vector<double>& va, number beta,
+                         number eps)
+{
+	if (block == 1) { if (beta != 0.0) FactorizeILUBeta(n, rp, ci, va, beta); else FactorizeILUSorted(n, rp, ci, va, eps); }
+	else if (block == 2) { if (beta != 0.0) FactorizeILUBetaBlock<2>(n, rp, ci, va, beta); else FactorizeILUSortedBlock<2>(n, rp, ci, va, eps); }
+	else if (block == 3) { if (beta != 0.0) FactorizeILUBetaBlock<3>(n, rp, ci, va, beta); else FactorizeILUSortedBlock<3>(n, rp, ci, va, eps); }
+	else UG_THROW("ILU: block size must be 1, 2 or 3");
+}
+
 /// ILU(0) on the stored pattern, rows sorted (ilu.h:174-228); scalar entries
 inline void FactorizeILUSorted(int64_t n, const std::vector<int64_t>& rp, const std::vector<int>& ci, std::vector<double>& va,
-                               number eps = 1e-50)
+                               number eps)
 {
 	std::vector<int64_t> diag((size_t)n);
 	for (int64_t i = 0; i < n; ++i) diag[(size_t)i] = ilu_detail::find(rp, ci, i, (int)i);

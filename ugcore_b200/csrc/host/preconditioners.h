@@ -278,7 +278,7 @@ class GaussSeidelBase : public IPreconditioner<TAlgebra> {
 ///     (level scheduling); rows are renumbered by level, so a row accumulates its terms in another order than
 ///     the reference does (round-off level differences), and a sweep costs one launch per level.
 /// invert_U's "near-zero last diagonal entry" guard (ilu.h:285-297, set_inversion_eps) is not evaluated on the
-/// device.  Scalar algebra only.
+/// device.  Scalar and 2x2 / 3x3 block algebras (block entries: DenseMatrix arithmetic restated in ilu_factor.h).
 template <typename TAlgebra>
 class ILU : public IPreconditioner<TAlgebra> {
   public:
@@ -327,7 +327,6 @@ class ILU : public IPreconditioner<TAlgebra> {
 	virtual bool preprocess(SmartPtr<matrix_operator_type> pOp)
 	{
 		if (m_bDisablePreprocessing && m_L) return true;
-		if (B != 1) UG_THROW("ILU: only the scalar GPU algebra is supported (block ILU: use Jacobi / Gauss-Seidel)");
 		matrix_type* pA = &static_cast<matrix_type&>(*pOp);
 		if (m_layouts) {
 			if (!m_spConsistent) UG_THROW("ILU: a partitioned matrix needs its consistent counterpart (set_consistent_matrix)");
@@ -339,13 +338,17 @@ class ILU : public IPreconditioner<TAlgebra> {
 		const std::vector<int64_t>& rp = A.crs_rowptr();
 		const std::vector<int>& ci = A.crs_cols();
 		std::vector<double> va = A.crs_vals();                 // m_ILU = mat (ilu.h:533)
+		const int BB = B * B;
 		if (m_layouts) {
 			// rows of the h-slaves become Dirichlet rows (ilu.h:539-543)
 			const std::vector<int> slaves = m_layouts->slave_indices();
 			for (size_t k = 0; k < slaves.size(); ++k) {
 				const int r = slaves[k];
 				bool haveDiag = false;
-				for (int64_t p = rp[r]; p < rp[r + 1]; ++p) { va[p] = 0.0; if (ci[p] == r) { va[p] = 1.0; haveDiag = true; } }
+				for (int64_t p = rp[r]; p < rp[r + 1]; ++p) {
+					for (int t = 0; t < BB; ++t) va[p * BB + t] = 0.0;
+					if (ci[p] == r) { for (int t = 0; t < B; ++t) va[p * BB + t + B * t] = 1.0; haveDiag = true; }
+				}
 				if (!haveDiag) UG_THROW("ILU: interface row " << r << " has no diagonal connection");
 			}
 		}
@@ -377,19 +380,19 @@ class ILU : public IPreconditioner<TAlgebra> {
 		std::vector<int64_t> prp; std::vector<int> pci; std::vector<double> pva;
 		permute(n, rp, ci, va, ord, ord, prp, pci, pva);
 		// ---- factorisation (ilu.h:573-575; SparseMatrix::rows_sorted == true) ----
-		if (m_beta != 0.0) FactorizeILUBeta(n, prp, pci, pva, m_beta);
-		else FactorizeILUSorted(n, prp, pci, pva, m_sortEps);
+		FactorizeILU(B, n, prp, pci, pva, m_beta, m_sortEps);
 		// ---- split into L (unit diagonal) and U ----
 		std::vector<int64_t> lrp((size_t)n + 1, 0), urp((size_t)n + 1, 0);
 		std::vector<int> lci, uci; std::vector<double> lva, uva;
 		for (int64_t i = 0; i < n; ++i) {
 			bool haveDiag = false;
 			for (int64_t p = prp[(size_t)i]; p < prp[(size_t)i + 1]; ++p) {
-				if (pci[(size_t)p] < i) { lci.push_back(pci[(size_t)p]); lva.push_back(pva[(size_t)p]); }
-				else { if (pci[(size_t)p] == i) haveDiag = true; uci.push_back(pci[(size_t)p]); uva.push_back(pva[(size_t)p]); }
+				if (pci[(size_t)p] < i) { lci.push_back(pci[(size_t)p]); lva.insert(lva.end(), pva.begin() + p * BB, pva.begin() + (p + 1) * BB); }
+				else { if (pci[(size_t)p] == i) haveDiag = true; uci.push_back(pci[(size_t)p]); uva.insert(uva.end(), pva.begin() + p * BB, pva.begin() + (p + 1) * BB); }
 			}
 			if (!haveDiag) UG_THROW("ILU: row " << i << " has no diagonal entry");
-			lci.push_back((int)i); lva.push_back(1.0);
+			lci.push_back((int)i);
+			for (int t = 0; t < BB; ++t) lva.push_back((t % B) == (t / B) ? 1.0 : 0.0);   // unit diagonal block
 			lrp[(size_t)i + 1] = (int64_t)lci.size(); urp[(size_t)i + 1] = (int64_t)uci.size();
 		}
 		// ---- groups of independent rows ----
@@ -416,8 +419,8 @@ class ILU : public IPreconditioner<TAlgebra> {
 		// ---- upload ----
 		free_dev();
 		ug4b200_ctx* ctx = GPUManager::ctx();
-		UG_GPU_CHECK(ug4b200_matrix_upload_crs(ctx, 1, n, n, lrp.data(), lci.data(), lva.data(), UG4B200_MAT_DEFAULT, &m_L));
-		UG_GPU_CHECK(ug4b200_matrix_upload_crs(ctx, 1, n, n, urp.data(), uci.data(), uva.data(), UG4B200_MAT_DEFAULT, &m_U));
+		UG_GPU_CHECK(ug4b200_matrix_upload_crs(ctx, B, n, n, lrp.data(), lci.data(), lva.data(), UG4B200_MAT_DEFAULT, &m_L));
+		UG_GPU_CHECK(ug4b200_matrix_upload_crs(ctx, B, n, n, urp.data(), uci.data(), uva.data(), UG4B200_MAT_DEFAULT, &m_U));
 		m_n = (size_t)n;
 		std::vector<int> mapIn((size_t)n), mapLU((size_t)n), mapOut((size_t)n);
 		for (int64_t i = 0; i < n; ++i) {
@@ -428,7 +431,7 @@ class ILU : public IPreconditioner<TAlgebra> {
 		m_bSameOrder = identity;
 		m_dIn = upload_ints(mapIn); m_dOut = upload_ints(mapOut); m_dLU = m_bSameOrder ? nullptr : upload_ints(mapLU);
 		UG_GPU_CHECK(ug4b200_sync(ctx));
-		m_t0 = GPUManager::alloc(m_n); m_t1 = GPUManager::alloc(m_n);
+		m_t0 = GPUManager::alloc(m_n * B); m_t1 = GPUManager::alloc(m_n * B);
 		if (m_layouts) { m_dUnique.create(m_n); m_dUnique.set_layouts(m_layouts); }
 		return true;
 	}
@@ -445,16 +448,16 @@ class ILU : public IPreconditioner<TAlgebra> {
 			dsrc = m_dUnique.dev();
 		}
 		const int64_t n = (int64_t)m_n;
-		UG_GPU_CHECK(ug4b200_vec_scatter(ctx, n, 1, m_t0, m_dIn, dsrc));                                            // SetVectorAsPermutation(tmp, d, ordering)
+		UG_GPU_CHECK(ug4b200_vec_scatter(ctx, n, B, m_t0, m_dIn, dsrc));                                            // SetVectorAsPermutation(tmp, d, ordering)
 		UG_GPU_CHECK(ug4b200_gs_step(ctx, m_L, (int)m_ptrL.size() - 1, m_ptrL.data(), 0, 1.0, m_t1, m_t0));           // invert_L
 		if (m_bSameOrder) {
 			UG_GPU_CHECK(ug4b200_gs_step(ctx, m_U, (int)m_ptrU.size() - 1, m_ptrU.data(), 1, 1.0, m_t0, m_t1));       // invert_U
 		} else {
-			UG_GPU_CHECK(ug4b200_vec_gather(ctx, n, 1, m_t0, m_t1, m_dLU));
+			UG_GPU_CHECK(ug4b200_vec_gather(ctx, n, B, m_t0, m_t1, m_dLU));
 			UG_GPU_CHECK(ug4b200_gs_step(ctx, m_U, (int)m_ptrU.size() - 1, m_ptrU.data(), 1, 1.0, m_t1, m_t0));
 			std::swap(m_t0, m_t1);
 		}
-		UG_GPU_CHECK(ug4b200_vec_gather(ctx, n, 1, c.dev(), m_t0, m_dOut));                                          // SetVectorAsPermutation(c, tmp, old_ordering)
+		UG_GPU_CHECK(ug4b200_vec_gather(ctx, n, B, c.dev(), m_t0, m_dOut));                                          // SetVectorAsPermutation(c, tmp, old_ordering)
 		if (m_layouts) {
 			c.set_storage_type(PST_ADDITIVE);                               // :646
 			if (!c.change_storage_type(PST_CONSISTENT)) return false;       // :652
@@ -468,6 +471,7 @@ class ILU : public IPreconditioner<TAlgebra> {
 	                    const std::vector<size_t>& pr, const std::vector<size_t>& pc, std::vector<int64_t>& orp, std::vector<int>& oci,
 	                    std::vector<double>& ova)
 	{
+		const int BB = B * B;
 		std::vector<size_t> inv((size_t)n);
 		for (int64_t i = 0; i < n; ++i) inv[pr[(size_t)i]] = (size_t)i;
 		orp.assign((size_t)n + 1, 0);
@@ -480,7 +484,10 @@ class ILU : public IPreconditioner<TAlgebra> {
 			for (int64_t p = rp[r]; p < rp[r + 1]; ++p) row.push_back(std::make_pair((int)pc[(size_t)ci[(size_t)p]], p));
 			std::sort(row.begin(), row.end());
 			int64_t q = orp[(size_t)nr];
-			for (size_t k = 0; k < row.size(); ++k, ++q) { oci[(size_t)q] = row[k].first; ova[(size_t)q] = va[(size_t)row[k].second]; }
+			for (size_t k = 0; k < row.size(); ++k, ++q) {
+				oci[(size_t)q] = row[k].first;
+				for (int t = 0; t < BB; ++t) ova[(size_t)q * BB + t] = va[(size_t)row[k].second * BB + t];
+			}
 		}
 	}
 	/// rows grouped by level, stable inside a level; descending = true puts the highest level first (U: the
@@ -508,8 +515,8 @@ class ILU : public IPreconditioner<TAlgebra> {
 		m_L = m_U = nullptr;
 		GPUManager::free_bytes(m_dIn); GPUManager::free_bytes(m_dOut); GPUManager::free_bytes(m_dLU);
 		m_dIn = m_dOut = m_dLU = nullptr;
-		if (m_t0) GPUManager::release(m_t0, m_n);
-		if (m_t1) GPUManager::release(m_t1, m_n);
+		if (m_t0) GPUManager::release(m_t0, m_n * B);
+		if (m_t1) GPUManager::release(m_t1, m_n * B);
 		m_t0 = m_t1 = nullptr;
 	}
 

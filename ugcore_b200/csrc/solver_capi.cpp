@@ -419,21 +419,23 @@ int ug4b200_host_rap(int64_t nc, int64_t nf, const int64_t* r_rowptr, const int*
 		return 0;
 	});
 }
-int ug4b200_host_ilu_factorize(int64_t n, const int64_t* rowptr, const int* cols, double* vals, double beta, double sort_eps)
+int ug4b200_host_ilu_factorize_block(int block, int64_t n, const int64_t* rowptr, const int* cols, double* vals, double beta, double sort_eps)
 {
 	return guard([&] {
+		if (block < 1 || block > 3) UG_THROW("ILU: block size must be 1, 2 or 3");
 		std::vector<int64_t> rp(rowptr, rowptr + n + 1);
 		std::vector<int> ci(cols, cols + rp[(size_t)n]);
-		std::vector<double> va(vals, vals + rp[(size_t)n]);
+		std::vector<double> va(vals, vals + rp[(size_t)n] * block * block);
 		for (int64_t i = 0; i < n; ++i)
 			for (int64_t p = rp[(size_t)i] + 1; p < rp[(size_t)i + 1]; ++p)
 				if (ci[(size_t)p - 1] >= ci[(size_t)p]) UG_THROW("ILU: columns of row " << i << " are not sorted");
-		if (beta != 0.0) FactorizeILUBeta(n, rp, ci, va, beta);
-		else FactorizeILUSorted(n, rp, ci, va, sort_eps);
+		FactorizeILU(block, n, rp, ci, va, beta, sort_eps);
 		std::memcpy(vals, va.data(), sizeof(double) * va.size());
 		return 0;
 	});
 }
+int ug4b200_host_ilu_factorize(int64_t n, const int64_t* rowptr, const int* cols, double* vals, double beta, double sort_eps)
+{ return ug4b200_host_ilu_factorize_block(1, n, rowptr, cols, vals, beta, sort_eps); }
 int ug4b200_host_level_sets(int64_t n, const int64_t* rowptr, const int* cols, int lower, int* level, int* nlevels)
 {
 	return guard([&] {
