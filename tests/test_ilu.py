@@ -184,6 +184,22 @@ def test_oracle_solvers_with_ilu_and_gmres(name, orc, orc_ref):
         assert (len(hr) - 1) % 20 == 0
 
 
+def _tiny():
+    from ugcore_b200.problems import Crs
+    return Crs(1, 1, 1, np.array([0, 1], np.int64), np.array([0], np.int32), np.array([2.0]))
+
+
+GMRES_TINY = {"type": "gmres", "restart": 3, "precond": {"type": "ilu"}, "convCheck": {"iterations": 50, "absolute": 1e-12, "reduction": 1e-10}}
+
+
+def test_oracle_gmres_without_lucky_breakdown_handling(orc, orc_ref):
+    """gmres.h always runs all `restart` inner steps; once the Krylov space is exhausted h[j+1][j] = 0 and the
+    normalisation divides by it (gmres.h:255).  The restated loop keeps that: NaN defect, not converged."""
+    for o in (orc, orc_ref):
+        x, ok, h = oracle.OSolver(o, GMRES_TINY, o.matrix(_tiny())).apply(np.array([4.0]))
+        assert not ok and np.isnan(x).all() and h[0] == 4.0 and np.isnan(h[1])
+
+
 # ---- GPU ----------------------------------------------------------------------------------------------------
 pending = pytest.mark.skipif(os.environ.get("UG4B200_PENDING_GPU_TESTS") != "1",
                              reason="first GPU run pending (set UG4B200_PENDING_GPU_TESTS=1)")
@@ -303,3 +319,32 @@ def test_gpu_gmg_with_ilu_smoother_matches_oracle():
     assert ok and oko and abs(len(h) - len(ho)) <= 1
     assert rel_hist_err(h, ho) < 1e-10
     assert np.linalg.norm(x - xo[perms[3]]) <= 1e-9 * np.linalg.norm(xo)
+
+
+@pending
+@pytest.mark.gpu
+def test_gpu_edge_cases_ilu_gmres():
+    """1x1 and diagonal systems, a matrix without diagonal (error like ugcore's), zero right-hand side, and the
+    reference's GMRES behaviour once the Krylov space is exhausted (see the oracle test above)."""
+    import scipy.sparse as sp
+    import ugcore_b200 as ug
+    from ugcore_b200.problems import Crs
+    cc = {"iterations": 50, "absolute": 1e-12, "reduction": 1e-10}
+
+    def crs(M):
+        M = sp.csr_matrix(M); M.sort_indices()
+        return Crs(M.shape[0], M.shape[1], 1, M.indptr.astype(np.int64), M.indices.astype(np.int32), M.data.astype(np.float64))
+
+    for t in ("cg", "bicgstab", "linear"):
+        x, ok, h = ug.Solver({"type": t, "precond": {"type": "ilu"}, "convCheck": cc}, _tiny()).apply(np.array([4.0]))
+        assert ok and x[0] == 2.0
+    x, ok, h = ug.Solver(GMRES_TINY, _tiny()).apply(np.array([4.0]))
+    assert not ok and np.isnan(x).all() and h[0] == 4.0 and np.isnan(h[1])
+    x, ok, h = ug.Solver({"type": "cg", "precond": {"type": "ilu", "ordering": "cmk"}, "convCheck": cc},
+                         crs(np.diag([1., 2., 4., 8.]))).apply(np.ones(4))
+    assert ok and np.array_equal(x, [1.0, 0.5, 0.25, 0.125])
+    with pytest.raises(Exception, match="no diagonal entry"):
+        ug.Solver({"type": "cg", "precond": {"type": "ilu"}, "convCheck": cc}, crs(np.array([[0, 1.], [1., 0]]))).apply(np.ones(2))
+    prob = pr.Problem(dim=2, num_refs=3)
+    x, ok, h = ug.Solver({"type": "gmres", "restart": 5, "precond": {"type": "ilu"}, "convCheck": cc}, prob.matrix()).apply(np.zeros(prob.num_dofs))
+    assert ok and len(h) == 1 and h[0] == 0.0 and not x.any()
