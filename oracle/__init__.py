@@ -264,33 +264,35 @@ def make_desc(desc: dict) -> SolverDesc:
     d.max_steps = cc.get("iterations", 100)
     d.min_defect = cc.get("absolute", 1e-12)
     d.rel_reduction = cc.get("reduction", 1e-6)
-    pc = desc.get("precond")
+    # util.solver.defaults (solver_util.lua:423-575): linear / cg / bicgstab are preconditioned by ILU unless the
+    # descriptor names a preconditioner; an explicit None (or "none") means no preconditioner at all
+    pc = desc["precond"] if "precond" in desc else ("ilu" if desc.get("type", "cg") in ("linear", "cg", "bicgstab", "gmres") else None)
     if isinstance(pc, str):
-        pc = {"type": pc}
+        pc = None if pc == "none" else {"type": pc}
     d.precond = PRECOND[pc["type"] if pc else None]
     d.damp = 1.0
-    d.restart = desc.get("restart", 30)
+    d.restart = desc.get("restart", 5)
     d.ilu_beta = 0.0
     d.cycle, d.nu1, d.nu2 = 1, 2, 2
     d.smoother, d.smoother_damp = 1, 0.66
     d.base_solver, d.base_max_steps, d.base_min_defect, d.base_rel_reduction = 3, 1000, 1e-30, 1e-14
     if pc:
         if pc["type"] in ("jac", "jacobi"):
-            d.damp = pc.get("damp", 0.66)
+            d.damp = pc.get("damping", pc.get("damp", 0.66))
         elif pc["type"] in ("gs", "bgs", "sgs"):
             d.damp = pc.get("relax", 1.0)
         elif pc["type"] == "ilu":
             d.ilu_beta = pc.get("beta", 0.0)
         elif pc["type"] == "gmg":
-            sm = pc.get("smoother", {"type": "jac", "damp": 0.66})
+            sm = pc.get("smoother", "gs")          # defaults.preconditioner.gmg: smoother "gs", preSmooth = postSmooth = 3
             if isinstance(sm, str):
                 sm = {"type": sm}
             d.smoother = PRECOND[sm["type"]]
             d.ilu_beta = sm.get("beta", 0.0) if sm["type"] == "ilu" else 0.0
-            d.smoother_damp = sm.get("damp", 0.66) if d.smoother == 1 else sm.get("relax", 1.0)
+            d.smoother_damp = sm.get("damping", sm.get("damp", 0.66)) if d.smoother == 1 else sm.get("relax", 1.0)
             d.cycle = {"V": 1, "W": 2, "F": -1}[pc.get("cycle", "V")]
-            d.nu1 = pc.get("preSmooth", 2)
-            d.nu2 = pc.get("postSmooth", 2)
+            d.nu1 = pc.get("preSmooth", 3)
+            d.nu2 = pc.get("postSmooth", 3)
             d.base_lev = pc.get("baseLevel", 0)
             d.top_lev = pc["topLevel"]
             bs = pc.get("baseSolver", "lu")

@@ -100,3 +100,21 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(base, f), errors="ignore").read()
                 assert "import oracle" not in txt and "liboracle" not in txt and "oracle/" not in txt, os.path.join(base, f)
+
+
+def test_descriptor_defaults_follow_solver_util_lua():
+    """The descriptor layer plays util.solver.CreateSolver: absent entries take util.solver.defaults
+    (scripts/util/solver_util.lua:423-575, GMRES(5) at :669-670) — for the product and for the oracle alike."""
+    import oracle
+    from ugcore_b200 import solver as S
+    for make, ILU_, GS_, JAC_ in ((lambda d: S.make_desc(d), 6, 2, 1), (oracle.make_desc, 6, 2, 1)):
+        d = make({"type": "cg"})
+        assert d.precond == ILU_ and d.ilu_beta == 0.0 and d.max_steps == 100 and d.min_defect == 1e-12 and d.rel_reduction == 1e-6
+        assert make({"type": "bicgstab", "precond": None}).precond == 0 and make({"type": "linear", "precond": "none"}).precond == 0
+        assert make({"type": "gmres"}).restart == 5
+        g = make({"type": "linear", "precond": {"type": "gmg", "topLevel": 3}})
+        assert (g.nu1, g.nu2, g.smoother, g.cycle, g.base_lev, g.base_solver) == (3, 3, GS_, 1, 0, 3)
+        j = make({"type": "cg", "precond": "jac"})
+        assert j.precond == JAC_ and j.damp == 0.66
+        assert make({"type": "cg", "precond": {"type": "jac", "damping": 0.5}}).damp == 0.5
+        assert make({"type": "cg", "precond": {"type": "ilu", "beta": 0.25}}).ilu_beta == 0.25

@@ -131,7 +131,7 @@ def test_cg_jacobi_and_plain_cg():
     prob = pr.Problem(dim=2, num_refs=4)
     cc = {"iterations": 400, "absolute": 1e-12, "reduction": 1e-8}
     _compare(prob, {"type": "cg", "precond": {"type": "jac", "damp": 0.66}, "convCheck": cc})
-    _compare(prob, {"type": "cg", "convCheck": cc})
+    _compare(prob, {"type": "cg", "precond": None, "convCheck": cc})
 
 
 def test_max_steps_reached_reports_failure():

@@ -161,7 +161,7 @@ def test_level_sets_schedule_the_triangular_solves(kind):
 
 DESCS = {
     "gmres_ilu": {"type": "gmres", "restart": 10, "precond": {"type": "ilu"}, "convCheck": {"iterations": 50, "absolute": 1e-12, "reduction": 1e-8}},
-    "gmres": {"type": "gmres", "restart": 20, "convCheck": {"iterations": 200, "absolute": 1e-12, "reduction": 1e-6}},
+    "gmres": {"type": "gmres", "restart": 20, "precond": None, "convCheck": {"iterations": 200, "absolute": 1e-12, "reduction": 1e-6}},
     "bicgstab_ilub": {"type": "bicgstab", "precond": {"type": "ilu", "beta": 0.3}, "convCheck": {"iterations": 100, "absolute": 1e-12, "reduction": 1e-8}},
     "cg_ilu": {"type": "cg", "precond": {"type": "ilu"}, "convCheck": {"iterations": 100, "absolute": 1e-12, "reduction": 1e-8}},
     "linear_ilu": {"type": "linear", "precond": {"type": "ilu"}, "convCheck": {"iterations": 300, "absolute": 1e-12, "reduction": 1e-6}},

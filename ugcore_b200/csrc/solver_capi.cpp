@@ -78,7 +78,7 @@ struct SolverImpl : SolverBase {
 			}
 			case UG4B200_SOLVER_BICGSTAB: { SmartPtr<BiCGStab<vector_type> > s = make_sp<BiCGStab<vector_type> >(); s->set_preconditioner(precond); inv = s; break; }
 			case UG4B200_SOLVER_LINEAR: { SmartPtr<LinearSolver<vector_type> > s = make_sp<LinearSolver<vector_type> >(); s->set_preconditioner(precond); inv = s; break; }
-			case UG4B200_SOLVER_GMRES: { SmartPtr<GMRES<vector_type> > s = make_sp<GMRES<vector_type> >((size_t)(d.restart > 0 ? d.restart : 30)); s->set_preconditioner(precond); inv = s; break; }
+			case UG4B200_SOLVER_GMRES: { SmartPtr<GMRES<vector_type> > s = make_sp<GMRES<vector_type> >((size_t)(d.restart > 0 ? d.restart : 5)); s->set_preconditioner(precond); inv = s; break; }
 			case UG4B200_SOLVER_LU: inv = make_sp<LU<TAlgebra> >(); break;
 			case UG4B200_SOLVER_COARSE_CG: inv = make_sp<CoarseCG<TAlgebra> >(); break;
 			default: UG_THROW("unknown solver " << d.solver);

@@ -278,13 +278,13 @@ GS_KINDS = ("gs", "bgs", "sgs", "ilu")   # smoothers that sweep over the CONSIST
 
 def _smoother_kind(desc: dict):
     """type of the smoother that will run on partitioned levels (GMG smoother, or the preconditioner itself)"""
-    pc = desc.get("precond")
+    pc = desc["precond"] if "precond" in desc else "ilu"
     if isinstance(pc, str):
-        pc = {"type": pc}
+        pc = None if pc == "none" else {"type": pc}
     if not pc:
         return None
     if pc.get("type") == "gmg":
-        sm = pc.get("smoother", {"type": "jac"})
+        sm = pc.get("smoother", "gs")
         return sm if isinstance(sm, str) else sm.get("type")
     return pc.get("type")
 
