@@ -151,12 +151,31 @@ def _cpu_replica(refs, steps, warmup, barrier, q, workload="poisson", base_mult=
     q.put({"dt": dt, "its": len(h) - 1, "n": prob.num_dofs, "kind": kind, "hist": [float(v) for v in h]})
 
 
+def replica_bytes(refs, workload="poisson", base_mult=1):
+    """Rough host memory of one CPU replica: the generator's hierarchy plus the oracle's copy of it
+    (27 entries per row, (8 B^2 + 4) bytes per entry, 8/7 for the coarser levels, transfers and vectors ~ +25 %)."""
+    b = workload_spec(workload)["block"]
+    n = (base_mult * 2 ** refs + 1) ** 3
+    return int(2 * 1.25 * (8.0 / 7.0) * 27 * n * (8 * b * b + 4))
+
+
+def bounded_procs(nproc, refs, workload="poisson", base_mult=1):
+    """Never let the CPU arm exhaust the box: at most 40 % of the available memory over all replicas."""
+    try:
+        with open("/proc/meminfo") as f:
+            avail = next(int(l.split()[1]) * 1024 for l in f if l.startswith("MemAvailable"))
+    except Exception:
+        return nproc
+    return max(1, min(nproc, int(0.4 * avail / max(replica_bytes(refs, workload, base_mult), 1))))
+
+
 def cpu_replicas(refs, nproc, steps, warmup, workload="poisson", base_mult=1):
     """ugcore has no threads on this path and neither MPI nor boost exist here, so
     "all host cores" = nproc independent serial solves of the same workload running concurrently
     (they share the memory bus like MPI ranks would, but pay no interface exchange: an upper bound
     for ugcore's nproc-rank weak-scaling throughput).  Returns aggregate MDoF/s and details."""
     import multiprocessing as mp
+    nproc = bounded_procs(nproc, refs, workload, base_mult)
     mpc = mp.get_context("spawn")
     barrier, q = mpc.Barrier(nproc), mpc.Queue()
     procs = [mpc.Process(target=_cpu_replica, args=(refs, steps, warmup, barrier, q, workload, base_mult)) for _ in range(nproc)]
@@ -187,6 +206,7 @@ def run_reference(args):
     nproc = args.cpu_procs or host_cores()
     spec = workload_spec(args.workload)
     r = cpu_replicas(refs, nproc, args.steps, args.warmup, args.workload, args.base_mult)
+    nproc = r["cores"]           # may have been reduced to fit the host memory
     n, its, val, dt = r["n"], r["its"], r["value"], r["dt_per_step"]
     nodes = args.base_mult * 2 ** refs + 1
     sample = (f"{nproc} concurrent serial solves x {args.steps} steps of {spec['label']} {nodes}^3 nodes ({n} DoF, {its} "
@@ -346,8 +366,8 @@ def workload_roofline(workload, prob, top, peak_gbs, peak_src):
 def cpu_baseline_sample(refs, workload="poisson", base_mult=1):
     """Bounded CPU sample for the default run: the SAME workload solved once by every host core
     concurrently with the reference's kernels (~10-30 s including set-up)."""
-    nproc = host_cores()
-    r = cpu_replicas(refs, nproc, 1, 0, workload, base_mult)
+    r = cpu_replicas(refs, host_cores(), 1, 0, workload, base_mult)
+    nproc = r["cores"]
     serial_equiv = r["n"] / r["dt_per_step"] / 1e6
     return {"value": r["value"], "unit": UNIT, "cores": nproc, "kind": r["kind"],
             "sample": f"{nproc} concurrent serial solves of the same workload ({r['n']} DoF, {r['its']} CG iterations, "
