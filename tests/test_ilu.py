@@ -200,6 +200,40 @@ def test_oracle_gmres_without_lucky_breakdown_handling(orc, orc_ref):
         assert not ok and np.isnan(x).all() and h[0] == 4.0 and np.isnan(h[1])
 
 
+GOLDEN_ILU = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ilu_gmres_histories.json")
+
+
+def _golden_solver(orc, case):
+    from helpers import oracle_levels
+    prob = pr.Problem(**case["problem"])
+    desc = case["desc"]
+    pc = desc.get("precond")
+    if isinstance(pc, dict) and pc.get("type") == "gmg":
+        lv = oracle_levels(orc, prob, pc["baseLevel"], pc["topLevel"])
+        return prob, oracle.OSolver(orc, desc, lv[pc["topLevel"]][0], lv)
+    return prob, oracle.OSolver(orc, desc, orc.matrix(prob.matrix()))
+
+
+@pytest.mark.parametrize("kind", ["port", "ref"])
+def test_golden_ilu_gmres_histories(kind, request):
+    """tests/golden/ilu_gmres_histories.json was generated with the reference's own ILU kernels (oracle/_ref);
+    both backends reproduce it bit for bit (the port has no block ILU: that case is the ref backend's alone)."""
+    import json
+    from helpers import make_rhs
+    orc = request.getfixturevalue("orc" if kind == "port" else "orc_ref")
+    with open(GOLDEN_ILU) as f:
+        gold = json.load(f)
+    assert gold["oracle_backend"] == "ref" and len(gold["cases"]) == 7
+    for case in gold["cases"]:
+        if kind == "port" and case["problem"].get("problem") == 2:
+            continue
+        prob, s = _golden_solver(orc, case)
+        x, ok, h = s.apply(make_rhs(prob, case.get("rhs_seed")))
+        assert ok == case["converged"], case["name"]
+        assert np.array_equal(h, np.array(case["history"])), case["name"]
+        assert np.linalg.norm(x) == case["solution_norm"], case["name"]
+
+
 # ---- GPU ----------------------------------------------------------------------------------------------------
 pending = pytest.mark.skipif(os.environ.get("UG4B200_PENDING_GPU_TESTS") != "1",
                              reason="first GPU run pending (set UG4B200_PENDING_GPU_TESTS=1)")
@@ -348,3 +382,29 @@ def test_gpu_edge_cases_ilu_gmres():
     prob = pr.Problem(dim=2, num_refs=3)
     x, ok, h = ug.Solver({"type": "gmres", "restart": 5, "precond": {"type": "ilu"}, "convCheck": cc}, prob.matrix()).apply(np.zeros(prob.num_dofs))
     assert ok and len(h) == 1 and h[0] == 0.0 and not x.any()
+
+
+@pending
+@pytest.mark.gpu
+def test_gpu_golden_ilu_gmres_fixture():
+    """GPU vs the committed histories of the reference's ILU / GMRES (no /root/reference needed on the GPU box)."""
+    import json
+    import ugcore_b200 as ug
+    from helpers import make_rhs
+    with open(GOLDEN_ILU) as f:
+        gold = json.load(f)
+    for case in gold["cases"]:
+        prob = pr.Problem(**case["problem"])
+        pc = case["desc"].get("precond")
+        if isinstance(pc, dict) and pc.get("type") == "gmg":
+            s = ug.Solver.from_problem(case["desc"], prob)
+        else:
+            s = ug.Solver(case["desc"], prob.matrix())
+        x, ok, h = s.apply(make_rhs(prob, case.get("rhs_seed")))
+        ref = np.array(case["history"])
+        assert ok == case["converged"], case["name"]
+        assert abs(len(h) - len(ref)) <= 1, case["name"]
+        # Krylov methods amplify the round-off of another summation order (device reductions, level-scheduled rows)
+        tol = 1e-10 if case["desc"]["type"] in ("linear",) or isinstance(pc, dict) and pc.get("type") == "gmg" else 1e-7
+        assert rel_hist_err(h, ref) < tol, (case["name"], rel_hist_err(h, ref))
+        assert abs(np.linalg.norm(x) - case["solution_norm"]) <= 1e-7 * case["solution_norm"], case["name"]
