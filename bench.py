@@ -398,7 +398,6 @@ def run_ours(args):
     dev = capi.dev
     refs = args.refs
     spec = workload_spec(args.workload)
-    default_workload = args.workload == "poisson" and args.base_mult == 1
     desc = solver_desc(refs, workload=args.workload)
     bm = args.base_mult
 
@@ -407,10 +406,10 @@ def run_ours(args):
         from ugcore_b200 import dist as ugdist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         part = PART[world]
-        extra = dict(spec["kw"])
+        gen_kw = dict(spec["kw"])
         if bm != 1:
-            extra["base_mult"] = bm
-        prob, s = ugdist.build_partitioned_solver(desc, refs, part, rank, dist, problem=spec["problem"], **extra)
+            gen_kw["base_mult"] = bm
+        prob, s = ugdist.build_partitioned_solver(desc, refs, part, rank, dist, problem=spec["problem"], **gen_kw)
         barrier = lambda: (dist.barrier(), torch.cuda.synchronize())
     else:
         part = (1, 1, 1)
