@@ -105,6 +105,7 @@ class Oracle:
         L.oracle_solver_destroy.argtypes = [C.c_void_p]
         L.oracle_solver_set_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_solver_set_smoother_matrix.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.oracle_solver_set_precond_matrix.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_solver_init.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_solver_apply.argtypes = [C.c_void_p, _dp, _dp, C.c_int]
         L.oracle_solver_steps.argtypes = [C.c_void_p]
@@ -309,7 +310,8 @@ def make_desc(desc: dict) -> SolverDesc:
 class OSolver:
     """Solver built from a descriptor; ``levels`` maps level -> (A, P, R) OMat triples."""
 
-    def __init__(self, orc: Oracle, desc: dict, A: OMat, levels: dict | None = None, smoother_matrices: dict | None = None):
+    def __init__(self, orc: Oracle, desc: dict, A: OMat, levels: dict | None = None, smoother_matrices: dict | None = None,
+                 precond_matrix: "OMat | None" = None):
         self.o = orc
         self.desc = make_desc(desc)
         self.h = orc.lib.oracle_solver_create(C.byref(self.desc))
@@ -324,6 +326,9 @@ class OSolver:
             self._keep.append(smoother_matrices)
             for lev, S in smoother_matrices.items():
                 orc._chk(orc.lib.oracle_solver_set_smoother_matrix(self.h, lev, S.h))
+        if precond_matrix is not None:   # one-level preconditioner initialised with another matrix (parallel GS / ILU emulation)
+            self._keep.append(precond_matrix)
+            orc._chk(orc.lib.oracle_solver_set_precond_matrix(self.h, precond_matrix.h))
         orc._chk(orc.lib.oracle_solver_init(self.h, A.h))
 
     def __del__(self):

@@ -93,6 +93,9 @@ int oracle_solver_set_level(oracle_solver* s, int lev, const oracle_mat* A, cons
 /* matrix the smoothers of GMG level lev are initialised with instead of the level operator (ugcore's
  * parallel Gauss-Seidel smooths with its own consistent matrix, gauss_seidel.h:134-142) */
 int oracle_solver_set_smoother_matrix(oracle_solver* s, int lev, const oracle_mat* S);
+/* one-level preconditioner (Jacobi / GS / ILU) initialised with M instead of the solver's matrix: ugcore's parallel
+ * Gauss-Seidel / ILU precondition with their own consistent matrix m_A / m_ILU (gauss_seidel.h:134-142, ilu.h:536-543) */
+int oracle_solver_set_precond_matrix(oracle_solver* s, const oracle_mat* M);
 int oracle_solver_init(oracle_solver* s, const oracle_mat* A);
 /* x: in = start iterate, out = solution; b is not modified.  Returns 0 on success
  * (converged), 1 if the convergence check failed, <0 on error. */

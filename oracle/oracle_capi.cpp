@@ -63,6 +63,7 @@ struct oracle_solver {
 	std::unique_ptr<InverseOperator> inv;
 	LinearIterator* precond = nullptr; // owned by inv (or by lone below)
 	std::unique_ptr<LinearIterator> lone;
+	const oracle_mat* precond_matrix = nullptr; // matrix the (one-level) preconditioner is initialised with instead of A
 	GMG* gmg = nullptr;
 };
 
@@ -258,11 +259,14 @@ int oracle_solver_set_smoother_matrix(oracle_solver* s, int lev, const oracle_ma
 		return 0;
 	});
 }
+int oracle_solver_set_precond_matrix(oracle_solver* s, const oracle_mat* M) { s->precond_matrix = M; return 0; }
 int oracle_solver_init(oracle_solver* s, const oracle_mat* A)
 {
 	return guard([&] {
 		if (!s->inv->init(*A->m)) throw std::runtime_error("solver init failed");
 		if (s->lone && !s->lone->init(*A->m)) throw std::runtime_error("preconditioner init failed");
+		if (s->precond_matrix && s->precond && !s->gmg && !s->precond->init(*s->precond_matrix->m))
+			throw std::runtime_error("preconditioner init failed");
 		return 0;
 	});
 }

@@ -218,3 +218,45 @@ def partitioned_gs_oracle(orc, desc, refs, part, gather, problem=0, **kw):
         return xp[top], ok, h
 
     return solve, gprob
+
+
+def partitioned_onelevel_oracle(orc, desc, refs, part, problem=0, colored=False, **kw):
+    """Serial oracle of a partitioned Krylov solve with a ONE-LEVEL Gauss-Seidel / ILU preconditioner in ugcore's
+    parallel mode (gauss_seidel.h:134-142, ilu.h:536-543): the preconditioner works on the global matrix without
+    the couplings between DoFs of different h-masters, every master's block in the order of that rank's sweep
+    (colored: its greedy multicolour order — Gauss-Seidel, ILU with ordering "multicolor"; else the rank's own
+    numbering — ILU in natural ordering).  Returns (solve(b_global) -> (x_global, ok, history), global problem)."""
+    import oracle
+    from ugcore_b200 import dist as ugdist
+    world = part[0] * part[1] * part[2]
+    locals_ = [ugdist.local_problem(refs, part, r, problem=problem, **kw) for r in range(world)]
+    gprob = ugdist.global_problem(refs, part, problem=problem, **kw)
+    gA = gprob.matrix(refs)
+    if colored:
+        gperm, keep = parallel_gs_global_model(locals_, gprob, refs)
+    else:
+        owner = np.full(gA.nrows, -1, np.int64)
+        order = []
+        for r, p in enumerate(locals_):
+            gid = p.global_ids(refs)
+            own = ugdist.owned_mask(p, refs, r)
+            owner[gid[own]] = r
+            order.append(gid[own])
+        order = np.concatenate(order)
+        gperm = np.empty(gA.nrows, np.int64)
+        gperm[order] = np.arange(gA.nrows)
+        rows = np.repeat(np.arange(gA.nrows), np.diff(gA.rowptr))
+        keep = owner[rows] == owner[np.asarray(gA.cols)]
+    A = orc.matrix(permute_crs(gA, gperm, gperm))
+    M = orc.matrix(permute_crs(gA, gperm, gperm, keep=keep))
+    osol = oracle.OSolver(orc, desc, A, precond_matrix=M)
+    b = gprob.block
+    top = np.repeat(gperm * b, b) + np.tile(np.arange(b), gperm.size)
+
+    def solve(bg):
+        bp = np.empty_like(bg)
+        bp[top] = bg
+        xp, ok, h = osol.apply(bp)
+        return xp[top], ok, h
+
+    return solve, gprob

@@ -10,6 +10,8 @@ on the same global grid.
                             (gauss_seidel.h:134-142, 204-215) -> compared with the serial oracle of exactly
                             that method (helpers.partitioned_gs_oracle)
   case "convdiff_ilu"       the same with ILU(0) smoothing (ilu.h:536-543, 640-652: same parallel structure)
+  case "cg_ilu"             no multigrid: CG + ILU(0) (util.solver's default), natural ordering inside a rank
+  case "bicgstab_gs"        no multigrid: BiCGStab + one (multicolour) Gauss-Seidel sweep
 """
 import json
 import os
@@ -26,7 +28,7 @@ def main():
     import torch
     import torch.distributed as dist
     import oracle
-    from helpers import gmg_desc, oracle_levels, partitioned_gs_oracle, rel_hist_err
+    from helpers import gmg_desc, oracle_levels, partitioned_gs_oracle, partitioned_onelevel_oracle, rel_hist_err
     from ugcore_b200 import dist as ugdist, problems as pr, solver as S
 
     refs = int(sys.argv[1]) if len(sys.argv) > 1 else 3
@@ -49,12 +51,21 @@ def main():
     elif case == "convdiff_ilu":   # ILU(0) smoothing, multicolour ordering inside a rank; parallel mode of ilu.h:536-543, 640-652
         problem, kw = pr.CONVDIFF, {"eps": 1e-1}
         desc = gmg_desc(refs, solver="bicgstab", smoother={"type": "ilu", "ordering": "multicolor"}, reduction=1e-8)
+    elif case == "cg_ilu":         # util.solver's default configuration: CG preconditioned by ILU(0), one level
+        problem, kw = pr.POISSON, {}
+        desc = {"type": "cg", "precond": {"type": "ilu"}, "convCheck": {"iterations": 100, "absolute": 1e-12, "reduction": 1e-8}}
+    elif case == "bicgstab_gs":    # BiCGStab preconditioned by one Gauss-Seidel sweep
+        problem, kw = pr.CONVDIFF, {"eps": 1e-1}
+        desc = {"type": "bicgstab", "precond": {"type": "gs"}, "convCheck": {"iterations": 200, "absolute": 1e-12, "reduction": 1e-8}}
     else:
         raise SystemExit(f"unknown case {case}")
     prob, s = ugdist.build_partitioned_solver(desc, refs, part, rank, dist, problem=problem, flags=flags, **kw)
     x, ok, h = s.apply(prob.rhs())
 
-    if case in ("convdiff_gs", "convdiff_ilu"):
+    if case in ("cg_ilu", "bicgstab_gs"):
+        solve, gprob = partitioned_onelevel_oracle(orc, desc, refs, part, problem=problem, colored=(case == "bicgstab_gs"), **kw)
+        xo, oko, ho = solve(np.array(gprob.rhs()))
+    elif case in ("convdiff_gs", "convdiff_ilu"):
         solve, gprob = partitioned_gs_oracle(orc, desc, refs, part, s.desc.gather_lev, problem=problem, **kw)
         xo, oko, ho = solve(np.array(gprob.rhs()))
     else:

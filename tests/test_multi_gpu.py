@@ -51,6 +51,15 @@ def test_partitioned_bicgstab_gmg_ilu_matches_oracle(world, flags, p2p, gather):
 
 
 @pending
+@pytest.mark.parametrize("world,p2p,case,tol", [(2, 1, "cg_ilu", 1e-10), (4, 0, "cg_ilu", 1e-10), (2, 1, "bicgstab_gs", 1e-8),
+                                                (8, 1, "bicgstab_gs", 1e-7)])
+def test_partitioned_one_level_preconditioners_match_oracle(world, p2p, case, tol):
+    """No multigrid: CG + ILU(0) (util.solver's default solver) and BiCGStab + Gauss-Seidel on a partitioned grid,
+    ugcore's parallel mode of both (consistent matrix, Dirichlet rows on the h-slaves, unique defect)."""
+    _run(world, 0, p2p, -1, case, tol, 1e-7)
+
+
+@pending
 @pytest.mark.parametrize("world,flags,p2p,gather", [(2, 0, 1, -1), (8, 0, 1, -1), (2, 0, 0, 0)])
 def test_partitioned_elasticity_block3_matches_serial_oracle(world, flags, p2p, gather):
     """BASELINE configs[4] partitioned: 3x3-block GMG-CG, block interface exchange."""

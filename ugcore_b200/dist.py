@@ -303,7 +303,20 @@ def build_partitioned_solver(desc: dict, refs: int, part, rank: int, dist, probl
     p2p_bootstrap(dist)
     prob = local_problem(refs, part, rank, problem=problem, **kw)
     desc = dict(desc)
-    pc = dict(desc["precond"])
+    pc = desc["precond"] if "precond" in desc else "ilu"
+    if isinstance(pc, str):
+        pc = None if pc == "none" else {"type": pc}
+    if not pc or pc.get("type") != "gmg":
+        # one-level preconditioner (Jacobi / Gauss-Seidel / ILU — util.solver's default is ILU) or none: the
+        # Krylov vectors and the preconditioner live on the top level's layouts
+        s = Solver(desc, prob.matrix(refs), None, flags)
+        s._keep.append(prob)
+        ranks, ptr, idx = interfaces(prob, refs)
+        s.set_layouts(refs, ranks, ptr, idx, prob.matrix(refs).nrows)
+        if _smoother_kind(desc) in GS_KINDS:
+            s.set_smoother_matrix(refs, make_consistent(prob.matrix(refs), rank, ranks, ptr, idx, dist))
+        return prob, s
+    pc = dict(pc)
     pc["topLevel"], pc["baseLevel"] = refs, pc.get("baseLevel", 0)
     base = pc["baseLevel"]
     if gather_level is None:
