@@ -409,12 +409,12 @@ def run_ours(args):
         gen_kw = dict(spec["kw"])
         if bm != 1:
             gen_kw["base_mult"] = bm
-        prob, s = ugdist.build_partitioned_solver(desc, refs, part, rank, dist, problem=spec["problem"], **gen_kw)
+        prob, s = ugdist.build_partitioned_solver(desc, refs, part, rank, dist, problem=spec["problem"], flags=args.flags, **gen_kw)
         barrier = lambda: (dist.barrier(), torch.cuda.synchronize())
     else:
         part = (1, 1, 1)
         prob = pr.Problem(dim=3, num_refs=refs, problem=spec["problem"], base=(bm,) * 3, **spec["kw"])
-        s = S.Solver.from_problem(desc, prob)
+        s = S.Solver.from_problem(desc, prob, flags=args.flags)
         barrier = lambda: torch.cuda.synchronize()
     s.init()
     n_local = prob.num_dofs
@@ -510,6 +510,7 @@ def main():
     ap.add_argument("--cpu-refs", type=int, default=None, help="refinements of the CPU reference arm (default: --refs)")
     ap.add_argument("--workload", default="poisson", choices=["poisson", "convdiff", "elasticity"],
                     help="poisson: BASELINE configs[1]/[2] (default); convdiff: configs[3]; elasticity: configs[4]")
+    ap.add_argument("--flags", type=int, default=0, help="UG4B200_FLAG_* bits for the solver (32: device-resident BiCGStab)")
     ap.add_argument("--base-mult", type=int, default=1, help="base-grid elements per GPU and direction "
                     "(--workload elasticity --base-mult 3 --refs 5: 97^3 nodes per GPU, 193^3 x 3 = 21.6 M DoF on 8 GPUs)")
     ap.add_argument("--cpu-procs", type=int, default=0, help="processes of the CPU arm (0 = all host cores)")

@@ -25,6 +25,9 @@ for w in poisson convdiff elasticity; do
   timeout 900 python bench.py --workload $w $extra --steps 5 --warmup 3 > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err
   cut -c1-900 gpurun_out/bench_$w.json; tail -2 gpurun_out/bench_$w.err
 done
+# device-resident BiCGStab (flag 32) against the host loop on the same workload
+timeout 900 python bench.py --workload convdiff --flags 32 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_convdiff_devbicgstab.json 2> gpurun_out/bench_convdiff_devbicgstab.err
+cut -c1-400 gpurun_out/bench_convdiff_devbicgstab.json; tail -2 gpurun_out/bench_convdiff_devbicgstab.err
 for w in convdiff elasticity; do
   extra=""; [ $w = elasticity ] && extra="--refs 6"
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$w.csv \

@@ -408,3 +408,26 @@ def test_gpu_golden_ilu_gmres_fixture():
         tol = 1e-10 if case["desc"]["type"] in ("linear",) or isinstance(pc, dict) and pc.get("type") == "gmg" else 1e-7
         assert rel_hist_err(h, ref) < tol, (case["name"], rel_hist_err(h, ref))
         assert abs(np.linalg.norm(x) - case["solution_norm"]) <= 1e-7 * case["solution_norm"], case["name"]
+
+
+@pending
+@pytest.mark.gpu
+@pytest.mark.parametrize("graph", [0, 2])
+def test_gpu_device_resident_bicgstab_equals_host_loop(graph):
+    """UG4B200_FLAG_DEVICE_BICGSTAB: rho, alpha, omega, beta and the convergence state stay on the device and an
+    iteration is one CUDA graph.  Same kernels, same scalar expressions as the reference-shaped host loop
+    (bicgstab.h:161-380) -> identical histories and iterates, also when the check after the half step ends the solve
+    and when the step limit is hit."""
+    import ugcore_b200 as ug
+    from ugcore_b200 import capi
+    prob = pr.Problem(dim=3, num_refs=3, problem=pr.CONVDIFF, eps=1e-1)
+    cases = {"gmg_gs": gmg_desc(3, solver="bicgstab", smoother={"type": "gs", "relax": 1.0}, reduction=1e-8),
+             "ilu": {"type": "bicgstab", "precond": {"type": "ilu"}, "convCheck": {"iterations": 100, "absolute": 1e-12, "reduction": 1e-8}},
+             "none": {"type": "bicgstab", "precond": None, "convCheck": {"iterations": 200, "absolute": 1e-12, "reduction": 1e-8}},
+             "maxsteps": {"type": "bicgstab", "precond": None, "convCheck": {"iterations": 7, "absolute": 1e-12, "reduction": 1e-30}}}
+    for name, desc in cases.items():
+        mk = (lambda fl: ug.Solver.from_problem(desc, prob, flags=fl)) if name == "gmg_gs" else (lambda fl: ug.Solver(desc, prob.matrix(), flags=fl))
+        x0, ok0, h0 = mk(0).apply(prob.rhs())
+        x1, ok1, h1 = mk(capi.FLAG_DEVICE_BICGSTAB | graph).apply(prob.rhs())
+        assert ok0 == ok1 and ok0 == (name != "maxsteps"), name
+        assert np.array_equal(h0, h1) and np.array_equal(x0, x1), name

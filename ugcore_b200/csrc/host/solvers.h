@@ -259,15 +259,22 @@ class BiCGStab : public IPreconditionedLinearOperatorInverse<TVector> {
 	using base_type::preconditioner;
 
 	BiCGStab() : m_numRestarts(0), m_minOrtho(0.0) {}
+	~BiCGStab() { drop_graph(); if (m_scal) GPUManager::free_bytes(m_scal); }
 	virtual const char* name() const { return "BiCGStab"; }
 	void set_restart(int numRestarts) { m_numRestarts = numRestarts; }
 	void set_min_orthogonality(number minOrtho) { m_minOrtho = minOrtho; }
+	/// true: every scalar of the iteration (rho, alpha, omega, beta, the convergence state) stays on the device and one
+	/// iteration is a CUDA graph, like CG::apply_device; false (default until measured): reference-shaped host loop
+	void set_device_resident(bool b) { m_deviceResident = b; }
+	void set_use_graph(bool b) { m_useGraph = b; }
 
 	virtual bool apply_return_defect(vector_type& x, vector_type& b)
 	{
 		const bool par = (bool)x.layouts();
 		if (par && (!b.has_storage_type(PST_ADDITIVE) || !x.has_storage_type(PST_CONSISTENT)))
 			UG_THROW("BiCGStab: Inadequate storage format of Vectors.");
+		StdConvCheck<vector_type>* std_cc = dynamic_cast<StdConvCheck<vector_type>*>(convergence_check().get());
+		if (m_deviceResident && std_cc && m_minOrtho == 0.0) return apply_device(x, b, *std_cc);
 		linear_operator()->apply_sub(b, x);
 		vector_type& r = b;
 		SmartPtr<vector_type> spR = r.clone_without_values(); vector_type& r0 = *spR;
@@ -327,8 +334,150 @@ class BiCGStab : public IPreconditionedLinearOperatorInverse<TVector> {
 	}
 
   protected:
+	// ---- device-resident loop: the statements of bicgstab.h:161-380 with device scalars ----
+	typedef detail::KrylovDeviceState KS;
+	enum { S_RHO = KS::RHO, S_RHO_OLD = KS::RHO_OLD, S_ALPHA = KS::ALPHA, S_OMEGA = KS::OMEGA, S_BETA = KS::BETA, S_TMP = KS::TMP,
+	       S_TT = KS::LAMBDA, S_BO = KS::NUM };   // BO = beta * omega lives behind the shared enum (ensure() allocates NUM + 1)
+
+	void reduce_fin(const vector_type& a, const vector_type& bvec, ug4b200_fin fin, bool par)
+	{
+		ug4b200_ctx* c = GPUManager::ctx();
+		if (!par) { UG_GPU_CHECK(ug4b200_vec_dot_ds(c, a.len(), a.dev(), bvec.dev(), fin)); return; }
+		UG_GPU_CHECK(ug4b200_vec_dot_allreduce_ds(c, a.len(), a.dev(), bvec.dev(), fin, m_scal + S_TMP));
+	}
+	void precond_apply(vector_type& q, vector_type& p, bool par)
+	{
+		if (preconditioner()) { if (!preconditioner()->apply(q, p)) UG_THROW("BiCGStab: Cannot apply preconditioner."); }
+		else {
+			UG_GPU_CHECK(ug4b200_vec_copy(GPUManager::ctx(), q.len(), q.dev(), p.dev())); q.set_storage_type(p.get_storage_mask());
+			if (par && !q.change_storage_type(PST_CONSISTENT)) UG_THROW("BiCGStab: Cannot convert q to consistent vector.");
+		}
+	}
+	/// dest = 1.0 * a + (sign * *coef) * bvec, then ||dest|| -> convergence update   (bicgstab.h:285-291, 362-368)
+	void update_and_check(vector_type& dest, const vector_type& a, const double* coef, double sign, const vector_type& bvec, bool par)
+	{
+		ug4b200_ctx* c = GPUManager::ctx();
+		ug4b200_fin fin{UG4B200_FIN_CONV_UPDATE, nullptr, nullptr, nullptr, m_ks.conv};
+		const unsigned type = a.get_storage_mask() & bvec.get_storage_mask();
+		if (!par) {
+			UG_GPU_CHECK(ug4b200_vec_scale_add2_norm_ds(c, dest.len(), dest.dev(), ug4b200_coef{nullptr, 1.0}, a.dev(), ug4b200_coef{coef, sign}, bvec.dev(), fin));
+			dest.set_storage_type(type);
+			return;
+		}
+		UG_GPU_CHECK(ug4b200_vec_scale_add2_ds(c, dest.len(), dest.dev(), ug4b200_coef{nullptr, 1.0}, a.dev(), ug4b200_coef{coef, sign}, bvec.dev()));
+		dest.set_storage_type(type);
+		if (!dest.change_storage_type(PST_UNIQUE)) UG_THROW("BiCGStab: cannot make the defect unique");
+		reduce_fin(dest, dest, fin, true);
+	}
+	void restart_block(vector_type& r, vector_type& r0, vector_type& p, vector_type& v, bool par)
+	{
+		ug4b200_ctx* c = GPUManager::ctx();
+		r0 = r;                                                                     // :167
+		if (par && !r0.change_storage_type(PST_UNIQUE)) UG_THROW("BiCGStab: Cannot convert r to unique vector.");
+		p.set(0.0); p.set_storage_type(r.get_storage_mask());                       // :176-181
+		v.set(0.0); v.set_storage_type(r.get_storage_mask());
+		UG_GPU_CHECK(ug4b200_vec_set(c, 1, m_scal + S_ALPHA, 0.0));
+		UG_GPU_CHECK(ug4b200_vec_set(c, 1, m_scal + S_OMEGA, 1.0));
+		UG_GPU_CHECK(ug4b200_vec_set(c, 1, m_scal + S_RHO, 1.0));                  // :184
+	}
+	void iteration_body(vector_type& x, vector_type& r, vector_type& r0, vector_type& p, vector_type& v, vector_type& t,
+	                    vector_type& s, vector_type& q, bool par)
+	{
+		ug4b200_ctx* c = GPUManager::ctx();
+		double* S = m_scal;
+		UG_GPU_CHECK(ug4b200_vec_copy(c, 1, S + S_RHO_OLD, S + S_RHO));             // rhoOld = rho                  :198
+		reduce_fin(r0, r, ug4b200_fin{UG4B200_FIN_STORE, S + S_RHO, nullptr, nullptr, nullptr}, par);   // rho = (r0, r) :204
+		UG_GPU_CHECK(ug4b200_scalar_ratio_ds(c, S + S_BETA, S + S_RHO, S + S_RHO_OLD, S + S_ALPHA, S + S_OMEGA));   // :227
+		UG_GPU_CHECK(ug4b200_scalar_ratio_ds(c, S + S_BO, S + S_BETA, nullptr, S + S_OMEGA, nullptr));              // beta*omega
+		UG_GPU_CHECK(ug4b200_vec_scale_add3_ds(c, p.len(), p.dev(), ug4b200_coef{nullptr, 1.0}, r.dev(), ug4b200_coef{S + S_BETA, 1.0}, p.dev(),
+		                                       ug4b200_coef{S + S_BO, -1.0}, v.dev()));                           // :230
+		p.set_storage_type(r.get_storage_mask() & p.get_storage_mask() & v.get_storage_mask());
+		precond_apply(q, p, par);                                                   // :236-251
+		linear_operator()->apply(v, q);                                             // :260
+		if (par && !v.change_storage_type(PST_UNIQUE)) UG_THROW("BiCGStab: Cannot convert v to unique vector.");
+		reduce_fin(v, r0, ug4b200_fin{UG4B200_FIN_A_DIV_R, S + S_TMP, S + S_ALPHA, S + S_RHO, m_ks.conv}, par);   // alpha = rho / (v, r0)  :272-282
+		UG_GPU_CHECK(ug4b200_vec_scale_add2_ds(c, x.len(), x.dev(), ug4b200_coef{nullptr, 1.0}, x.dev(), ug4b200_coef{S + S_ALPHA, 1.0}, q.dev()));   // :285
+		update_and_check(s, r, S + S_ALPHA, -1.0, v, par);                          // s = r - alpha v ; check   :288-291
+		// (converged here: the guard turns the rest of the iteration into no-ops; r = s is done by the caller, :294-297)
+		precond_apply(q, s, par);                                                   // :305-320
+		linear_operator()->apply(t, q);                                             // :329
+		if (par && !t.change_storage_type(PST_UNIQUE)) UG_THROW("BiCGStab: Cannot convert t to unique vector.");
+		reduce_fin(t, t, ug4b200_fin{UG4B200_FIN_STORE, S + S_TT, nullptr, nullptr, nullptr}, par);               // tt = (t, t)   :342
+		reduce_fin(s, t, ug4b200_fin{UG4B200_FIN_R_DIV_A, S + S_TMP, S + S_OMEGA, S + S_TT, nullptr}, par);       // omega = (s, t) / tt   :348-359
+		UG_GPU_CHECK(ug4b200_vec_scale_add2_ds(c, x.len(), x.dev(), ug4b200_coef{nullptr, 1.0}, x.dev(), ug4b200_coef{S + S_OMEGA, 1.0}, q.dev()));   // :362
+		update_and_check(r, s, S + S_OMEGA, -1.0, t, par);                          // r = s - omega t ; check   :365-368
+	}
+	bool apply_device(vector_type& x, vector_type& b, StdConvCheck<vector_type>& cc)
+	{
+		ug4b200_ctx* c = GPUManager::ctx();
+		const bool par = (bool)x.layouts();
+		linear_operator()->apply_sub(b, x);
+		vector_type& r = b;
+		SmartPtr<vector_type> spR = r.clone_without_values(); vector_type& r0 = *spR;
+		SmartPtr<vector_type> spP = r.clone_without_values(); vector_type& p = *spP;
+		SmartPtr<vector_type> spV = r.clone_without_values(); vector_type& v = *spV;
+		SmartPtr<vector_type> spT = r.clone_without_values(); vector_type& t = *spT;
+		SmartPtr<vector_type> spS = r.clone_without_values(); vector_type& s = *spS;
+		SmartPtr<vector_type> spQ = x.clone_without_values(); vector_type& q = *spQ;
+		const int maxSteps = cc.maximum_steps();
+		m_ks.ensure(maxSteps + 2);
+		if (!m_scal) m_scal = (double*)GPUManager::alloc_bytes(sizeof(double) * (KS::NUM + 1));
+		UG_GPU_CHECK(ug4b200_conv_init(c, m_ks.conv, maxSteps, cc.minimum_defect(), cc.relative_reduction(), m_ks.history, m_ks.historyCap));
+		UG_GPU_CHECK(ug4b200_set_guard(c, nullptr));
+		{   // convergence_check()->start(r), then r unique  (:154-158)
+			if (par && !r.change_storage_type(PST_UNIQUE)) UG_THROW("BiCGStab: Cannot convert b to unique.");
+			reduce_fin(r, r, ug4b200_fin{UG4B200_FIN_CONV_START, nullptr, nullptr, nullptr, m_ks.conv}, par);
+		}
+		UG_GPU_CHECK(ug4b200_set_guard(c, &m_ks.conv->done));
+		restart_block(r, r0, p, v, par);            // sets the storage types the captured body relies on
+		const void* key[8] = {x.dev(), r.dev(), r0.dev(), p.dev(), v.dev(), t.dev(), s.dev(), q.dev()};
+		bool graphOk = m_useGraph;
+		if (graphOk && (!m_graph || std::memcmp(key, m_graphKey, sizeof(key)) != 0)) {
+			drop_graph();
+			UG_GPU_CHECK(ug4b200_graph_begin(c));
+			try { iteration_body(x, r, r0, p, v, t, s, q, par); }
+			catch (...) { ug4b200_graph* g = nullptr; ug4b200_graph_end(c, &g); ug4b200_graph_destroy(c, g); ug4b200_set_guard(c, nullptr); throw; }
+			UG_GPU_CHECK(ug4b200_graph_end(c, &m_graph));
+			std::memcpy(m_graphKey, key, sizeof(key));
+		}
+		bool done = false;
+		UG_GPU_CHECK(ug4b200_d2h_async(c, &m_ks.pinned[0], m_ks.conv, sizeof(ug4b200_conv_state)));
+		UG_GPU_CHECK(ug4b200_event_record(c, m_ks.ev[0]));
+		const int maxIts = (maxSteps + 1) / 2;
+		for (int it = 0; it < maxIts && !done; ++it) {
+			// periodic restart (:161-163): an iteration advances the step count by two
+			if (it > 0 && m_numRestarts > 0 && (2 * it) % m_numRestarts == 0) restart_block(r, r0, p, v, par);
+			if (graphOk) UG_GPU_CHECK(ug4b200_graph_launch(c, m_graph));
+			else iteration_body(x, r, r0, p, v, t, s, q, par);
+			const int slot = (it + 1) & 1;
+			UG_GPU_CHECK(ug4b200_d2h_async(c, &m_ks.pinned[slot], m_ks.conv, sizeof(ug4b200_conv_state)));
+			UG_GPU_CHECK(ug4b200_event_record(c, m_ks.ev[slot]));
+			UG_GPU_CHECK(ug4b200_event_sync(c, m_ks.ev[slot ^ 1]));
+			done = m_ks.pinned[slot ^ 1].done != 0;
+		}
+		UG_GPU_CHECK(ug4b200_set_guard(c, nullptr));
+		ug4b200_conv_state fin;
+		UG_GPU_CHECK(ug4b200_d2h(c, &fin, m_ks.conv, sizeof(fin)));
+		std::vector<number> hist(fin.step + 1);
+		UG_GPU_CHECK(ug4b200_d2h(c, hist.data(), m_ks.history, sizeof(double) * hist.size()));
+		cc.adopt_device_state(fin, hist);
+		if (fin.step % 2 == 1) r = s;               // the check after the half step ended the iteration (:294-297)
+		if (fin.status == 4) return false;          // (v, r0) == 0 (:276-281)
+		return cc.post();
+	}
+	void drop_graph()
+	{
+		if (m_graph && GPUManager::ctx_or_null()) ug4b200_graph_destroy(GPUManager::ctx_or_null(), m_graph);
+		m_graph = nullptr;
+	}
+
 	int m_numRestarts;
 	number m_minOrtho;
+	bool m_deviceResident = false, m_useGraph = true;
+	KS m_ks;
+	double* m_scal = nullptr;
+	ug4b200_graph* m_graph = nullptr;
+	const void* m_graphKey[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 /// GMRES(restart), left preconditioned (gmres.h:104-278), reference-shaped: vector work on the device, the
