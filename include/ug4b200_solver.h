@@ -160,6 +160,20 @@ int ug4b200_host_rap(int64_t nc, int64_t nf, const int64_t* r_rowptr, const int*
 int ug4b200_io_write_vector(const char* filename, int64_t n, const double* values, const double* positions, int dim,
                             int precision);
 
+/* ---- assembly-side API of the GPU matrix type (what DomainDiscretization, constraints and transfers call on
+ * matrix_type before the solve; ugbase/lib_algebra/cpu_algebra/sparsematrix.h:116-343): a small
+ * interpreter so that callers without C++ (and the tests) can drive it.  Scalar matrices.  ops: nops x 4 doubles
+ * (code, r, c, v):
+ *   0 resize_and_clear(r, c)        1 A(r,c) = v                   2 A(r,c) += v             3 scale(v)
+ *   4 clear_retain_structure()      5 resize_and_keep_values(r, c) 6 defragment()            7 set(v): diagonal v, rest 0
+ *   8 A := transpose(A) * v         9 A := copy of A * v           10 read A(r,c) through the const access (creates nothing)
+ *  11 set_matrix_row(r): the following c ops of code 12 (.., col, value) form the row
+ *  13 add_matrix_row(r): likewise
+ * Returns a host matrix handle (ug4b200_io_matrix_info / _export / _free). */
+int ug4b200_host_matrix_script(int64_t nops, const double* ops, ug4b200_host_matrix** out);
+/* is_isolated(i) for every row of a host matrix (sparsematrix_impl.h:416-425) */
+int ug4b200_host_matrix_isolated(const ug4b200_host_matrix* m, unsigned char* isolated);
+
 /* ---- init-time host kernels of ILU and of DoF reordering, exposed for callers and tests (no device involved) ----
  * ILU(0) (beta == 0: FactorizeILUSorted, ilu.h:174-228) or ILU(beta) (FactorizeILUBeta, :110-171) of a scalar CRS
  * matrix with sorted rows, in place in vals: L below the diagonal (unit diagonal implied), U on and above it.

@@ -96,6 +96,8 @@ class Oracle:
         L.oracle_jacobi.argtypes = [C.c_void_p, C.c_double, C.c_int, _dp, _dp]
         L.oracle_gs.argtypes = [C.c_void_p, C.c_int, C.c_double, _dp, _dp]
         L.oracle_lu_solve.argtypes = [C.c_void_p, _dp, _dp]
+        L.oracle_mat_script.restype = C.c_void_p
+        L.oracle_mat_script.argtypes = [C.c_int64, _dp, C.c_void_p, C.c_int64]
         L.oracle_ilu_factorize.restype = C.c_void_p
         L.oracle_ilu_factorize.argtypes = [C.c_void_p, C.c_double, C.c_double]
         L.oracle_ilu_apply.argtypes = [C.c_void_p, C.c_double, _dp, _dp]
@@ -121,6 +123,16 @@ class Oracle:
     def matrix(self, crs) -> "OMat":
         """crs: object with nrows, ncols, block, rowptr(int64), cols(int32), vals(float64)."""
         return OMat(self, crs.block, crs.nrows, crs.ncols, crs.rowptr, crs.cols, crs.vals)
+
+    def matrix_script(self, ops, max_rows=4096):
+        """Run an op script against the reference's SparseMatrix (ref backend). Returns (OMat, isolated[nrows])."""
+        ops = np.ascontiguousarray(ops, dtype=np.float64).reshape(-1, 4)
+        iso = np.zeros(max_rows, np.uint8)
+        h = self.lib.oracle_mat_script(ops.shape[0], ops.ravel(), iso.ctypes.data_as(C.c_void_p), max_rows)
+        if not h:
+            raise RuntimeError("oracle: " + self.lib.oracle_last_error().decode())
+        m = OMat(self, 1, self.lib.oracle_mat_rows(h), self.lib.oracle_mat_cols(h), None, None, None, handle=h)
+        return m, iso[:m.nrows].copy()
 
     def dot(self, a, b, block=1):
         a = _vec(a); b = _vec(b)

@@ -86,6 +86,11 @@ struct Backend {
 	// ComputeCuthillMcKeeOrder (ordering_strategies/algorithms/native_cuthill_mckee.cpp:100-300); newIndex[old] = new
 	virtual void cuthill_mckee(const Mat& A, bool reverse, bool preserveConsec, std::vector<size_t>& newIndex) = 0;
 
+	// the assembly-side API of SparseMatrix (cpu_algebra/sparsematrix.h:116-343) driven by a small op script
+	// (codes as in include/ug4b200_solver.h: ug4b200_host_matrix_script); isolated[i] = is_isolated(i).
+	// Only the compiled reference implements it (the port restates the solve path, not the assembly side).
+	virtual Mat* matrix_script(int64_t nops, const double* ops, std::vector<unsigned char>& isolated) = 0;
+
 	virtual DenseLU* lu_init(const Mat& A) = 0;                  // nullptr if singular
 	virtual void lu_apply(const DenseLU& lu, Vec& x, const Vec& b) = 0;
 };

@@ -52,6 +52,9 @@ int oracle_jacobi(const oracle_mat* A, double damp, int block_inverse, double* c
 int oracle_gs(const oracle_mat* A, int kind, double relax, double* c, const double* d);
 /* ILU(0) / ILU(beta) of a copy of A (lib_algebra/operator/preconditioner/ilu.h:110-228) and one application
  * c = U^-1 L^-1 d (invert_L :233-252, invert_U :257-322; returns 1 if the last row's near-zero check fired) */
+/* SparseMatrix's assembly-side API driven by an op script (codes: include/ug4b200_solver.h, ug4b200_host_matrix_script);
+ * ref backend only */
+oracle_mat* oracle_mat_script(int64_t nops, const double* ops, unsigned char* isolated, int64_t isolated_cap);
 oracle_mat* oracle_ilu_factorize(const oracle_mat* A, double beta, double sort_eps);
 int oracle_ilu_apply(const oracle_mat* LU, double inv_eps, double* c, const double* d);
 /* new_index[old] = new; GetCuthillMcKeeOrder (algebra_common/permutation_util.h:96-114) */

@@ -166,6 +166,15 @@ int oracle_gs(const oracle_mat* A, int kind, double relax, double* c, const doub
 		Cv.back(); return 0;
 	});
 }
+oracle_mat* oracle_mat_script(int64_t nops, const double* ops, unsigned char* isolated, int64_t isolated_cap)
+{
+	try {
+		std::vector<unsigned char> iso;
+		oracle_mat* T = new oracle_mat; T->m.reset(BK().matrix_script(nops, ops, iso));
+		for (size_t i = 0; i < iso.size() && (int64_t)i < isolated_cap; ++i) isolated[i] = iso[i];
+		return T;
+	} catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
 oracle_mat* oracle_ilu_factorize(const oracle_mat* A, double beta, double sort_eps)
 {
 	try { oracle_mat* T = new oracle_mat; T->m.reset(BK().ilu_factorize(*A->m, beta, sort_eps)); return T; }

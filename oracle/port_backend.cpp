@@ -605,6 +605,9 @@ struct PortBackend : Backend {
 		}
 	}
 
+	Mat* matrix_script(int64_t, const double*, std::vector<unsigned char>&) override
+	{ throw std::runtime_error("port oracle: the assembly-side matrix API is not restated (use the ref backend)"); }
+
 	// operator/linear_solver/lu.h:122-140 (init_dense) with the non-LAPACK kernels
 	// small_algebra/no_lapack/lu_decomp.h:45-75 (LUDecomp with row interchange)
 	DenseLU* lu_init(const Mat& A_) override

@@ -382,6 +382,45 @@ struct RefBackend : Backend {
 #undef CALL
 	}
 
+	Mat* matrix_script(int64_t nops, const double* ops, std::vector<unsigned char>& isolated) override
+	{
+		typedef ug::SparseMatrix<double> SM1;
+		std::unique_ptr<RMat<1> > m(new RMat<1>);
+		for (int64_t k = 0; k < nops; ++k) {
+			const int code = (int)ops[4 * k]; const size_t r = (size_t)ops[4 * k + 1], c = (size_t)ops[4 * k + 2]; const double v = ops[4 * k + 3];
+			SM1& A = m->A;
+			switch (code) {
+				case 0: A.resize_and_clear(r, c); break;
+				case 1: A(r, c) = v; break;
+				case 2: A(r, c) += v; break;
+				case 3: A.scale(v); break;
+				case 4: A.clear_retain_structure(); break;
+				case 5: A.resize_and_keep_values(r, c); break;
+				case 6: A.defragment(); break;
+				case 7: A.set(v); break;
+				case 8: case 9: {
+					std::unique_ptr<RMat<1> > t(new RMat<1>);
+					if (code == 8) t->A.set_as_transpose_of(A, v); else t->A.set_as_copy_of(A, v);
+					m.swap(t);
+					break;
+				}
+				case 10: { const SM1& cA = A; volatile double sink = cA(r, c); (void)sink; break; }
+				case 11: case 13: {
+					std::vector<SM1::connection> row(c);
+					for (size_t t = 0; t < c; ++t) { row[t].iIndex = (size_t)ops[4 * (k + 1 + t) + 2]; row[t].dValue = ops[4 * (k + 1 + t) + 3]; }
+					if (code == 11) A.set_matrix_row(r, row.data(), c); else A.add_matrix_row(r, row.data(), c);
+					k += (int64_t)c;
+					break;
+				}
+				default: throw std::runtime_error("matrix script: unknown operation");
+			}
+		}
+		m->nrows = (int64_t)m->A.num_rows(); m->ncols = (int64_t)m->A.num_cols(); m->block = 1;
+		isolated.resize(m->A.num_rows());
+		for (size_t i = 0; i < m->A.num_rows(); ++i) isolated[i] = m->A.is_isolated(i) ? 1 : 0;
+		return m.release();
+	}
+
 	// lu.h:122-140 init_dense / :189-207 solve_dense with the reference's dense kernels
 	template <int B> DenseLU* luinit(const Mat& A_)
 	{

@@ -59,12 +59,96 @@ class GPUSparseMatrix {
 		if (it == row.end() || it->iIndex != c) { connection n; n.iIndex = c; n.dValue = value_type(); zero(n.dValue); it = row.insert(it, n); }
 		return it->dValue;
 	}
+	/// sparsematrix_impl.h:429-460: the given connections are set, other connections of the row stay
 	void set_matrix_row(size_t r, connection* c, size_t nr)
+	{ for (size_t i = 0; i < nr; ++i) (*this)(r, c[i].iIndex) = c[i].dValue; }
+	/// sparsematrix_impl.h:463-468
+	void add_matrix_row(size_t row, connection* c, size_t nr)
+	{ for (size_t i = 0; i < nr; ++i) add_value((*this)(row, c[i].iIndex), c[i].dValue); }
+	/// const access: 0 if the connection is not stored (sparsematrix.h:272-283)
+	const value_type& operator()(size_t r, size_t c) const
+	{
+		static const value_type zeroValue = make_zero();
+		const this_type* self = this;
+		const_cast<this_type*>(self)->fragment();
+		const std::vector<connection>& row = m_rows[r];
+		auto it = std::lower_bound(row.begin(), row.end(), c, [](const connection& a, size_t cc) { return a.iIndex < cc; });
+		return (it == row.end() || it->iIndex != c) ? zeroValue : it->dValue;
+	}
+	bool has_connection(size_t r, size_t c) const
+	{
+		const_cast<this_type*>(this)->fragment();
+		const std::vector<connection>& row = m_rows[r];
+		auto it = std::lower_bound(row.begin(), row.end(), c, [](const connection& a, size_t cc) { return a.iIndex < cc; });
+		return it != row.end() && it->iIndex == c;
+	}
+	void clear_and_free() { resize_and_clear(0, 0); }
+	/// sparsematrix_impl.h:112-139: new rows are empty, connections to columns >= newCols disappear
+	void resize_and_keep_values(size_t newRows, size_t newCols)
+	{
+		if (newRows == 0 && newCols == 0) return resize_and_clear(0, 0);
+		fragment(); touch();
+		m_rows.resize(newRows);
+		if (newCols < m_numCols)
+			for (std::vector<connection>& row : m_rows)
+				while (!row.empty() && row.back().iIndex >= newCols) row.pop_back();
+		m_numCols = newCols;
+	}
+	/// all values 0, pattern kept (sparsematrix_impl.h:142-145)
+	void clear_retain_structure() { fragment(); touch(); for (std::vector<connection>& row : m_rows) for (connection& c : row) zero(c.dValue); }
+	/// sparsematrix_impl.h:472-482
+	void set_as_copy_of(const this_type& Bm, double scaleFactor = 1.0)
+	{
+		const_cast<this_type&>(Bm).fragment();
+		resize_and_clear(Bm.num_rows(), Bm.num_cols());
+		for (size_t i = 0; i < Bm.m_rows.size(); ++i)
+			for (const connection& c : Bm.m_rows[i]) { value_type v = c.dValue; scale_value(v, scaleFactor); (*this)(i, c.iIndex) = v; }
+	}
+	/// sparsematrix_impl.h:487-496
+	void scale(double d) { fragment(); touch(); for (std::vector<connection>& row : m_rows) for (connection& c : row) scale_value(c.dValue, d); }
+	/// diagonal entries := a, all others := 0, pattern kept (sparsematrix_impl.h:397-412)
+	void set(double a)
 	{
 		fragment(); touch();
-		m_rows[r].assign(c, c + nr);
-		std::sort(m_rows[r].begin(), m_rows[r].end(), [](const connection& a, const connection& b) { return a.iIndex < b.iIndex; });
+		for (size_t r = 0; r < m_rows.size(); ++r) for (connection& c : m_rows[r]) { if (c.iIndex == r) c.dValue = a; else c.dValue = 0.0; }
 	}
+	/// no non-zero connection to another index (sparsematrix_impl.h:416-425)
+	bool is_isolated(size_t i) const
+	{
+		const_cast<this_type*>(this)->fragment();
+		for (const connection& c : m_rows[i]) if (c.iIndex != i && !is_zero(c.dValue)) return false;
+		return true;
+	}
+	/// local (element) matrices: M offers num_rows/num_cols, row_index(i), col_index(j), operator()(i,j)
+	/// (sparsematrix_impl.h:505-548)
+	template <typename M> void add(const M& mat)
+	{ for (size_t i = 0; i < mat.num_rows(); ++i) for (size_t j = 0; j < mat.num_cols(); ++j) add_value((*this)(mat.row_index(i), mat.col_index(j)), mat(i, j)); }
+	template <typename M> void set(const M& mat)
+	{ for (size_t i = 0; i < mat.num_rows(); ++i) for (size_t j = 0; j < mat.num_cols(); ++j) (*this)(mat.row_index(i), mat.col_index(j)) = mat(i, j); }
+	template <typename M> void get(M& mat) const
+	{ for (size_t i = 0; i < mat.num_rows(); ++i) for (size_t j = 0; j < mat.num_cols(); ++j) mat(i, j) = (*this)(mat.row_index(i), mat.col_index(j)); }
+	/// row access in ascending column order (begin_row / end_row, sparsematrix.h:484-487); the iterators offer
+	/// index() and value() like ugcore's
+	struct row_iterator {
+		typename std::vector<connection>::iterator it;
+		size_t index() const { return it->iIndex; }
+		value_type& value() { return it->dValue; }
+		bool operator!=(const row_iterator& o) const { return it != o.it; }
+		bool operator==(const row_iterator& o) const { return it == o.it; }
+		void operator++() { ++it; }
+	};
+	struct const_row_iterator {
+		typename std::vector<connection>::const_iterator it;
+		size_t index() const { return it->iIndex; }
+		const value_type& value() const { return it->dValue; }
+		bool operator!=(const const_row_iterator& o) const { return it != o.it; }
+		bool operator==(const const_row_iterator& o) const { return it == o.it; }
+		void operator++() { ++it; }
+	};
+	row_iterator begin_row(size_t r) { fragment(); touch(); return row_iterator{m_rows[r].begin()}; }
+	row_iterator end_row(size_t r) { fragment(); return row_iterator{m_rows[r].end()}; }
+	const_row_iterator begin_row(size_t r) const { const_cast<this_type*>(this)->fragment(); return const_row_iterator{m_rows[r].begin()}; }
+	const_row_iterator end_row(size_t r) const { const_cast<this_type*>(this)->fragment(); return const_row_iterator{m_rows[r].end()}; }
 	/// bulk load of a defragmented CRS (what copy_crs exports, sparsematrix.h:607-617);
 	/// vals: block*block doubles per entry, column-major inside a block
 	void set_from_crs(size_t rows, size_t cols, const int64_t* rowptr, const int* colidx, const double* vals)
@@ -157,6 +241,13 @@ class GPUSparseMatrix {
   private:
 	static void zero(double& v) { v = 0.0; }
 	template <class X> static void zero(X& v) { v = 0.0; }
+	static value_type make_zero() { value_type v = value_type(); zero(v); return v; }
+	static void add_value(value_type& a, const value_type& b)
+	{ for (int i = 0; i < blockSize; ++i) for (int j = 0; j < blockSize; ++j) gpu_value_access<value_type>::set(a, i, j, gpu_value_access<value_type>::get(a, i, j) + gpu_value_access<value_type>::get(b, i, j)); }
+	static void scale_value(value_type& a, double d)
+	{ for (int i = 0; i < blockSize; ++i) for (int j = 0; j < blockSize; ++j) gpu_value_access<value_type>::set(a, i, j, gpu_value_access<value_type>::get(a, i, j) * d); }
+	static bool is_zero(const value_type& a)
+	{ for (int i = 0; i < blockSize; ++i) for (int j = 0; j < blockSize; ++j) if (gpu_value_access<value_type>::get(a, i, j) != 0.0) return false; return true; }
 	void touch() { drop_device(); UG_COND_THROW(m_hostReleased, "GPUSparseMatrix: host copy was released, matrix is immutable"); }
 	void drop_device()
 	{

@@ -424,6 +424,54 @@ int ug4b200_host_rap(int64_t nc, int64_t nf, const int64_t* r_rowptr, const int*
 		return 0;
 	});
 }
+int ug4b200_host_matrix_script(int64_t nops, const double* ops, ug4b200_host_matrix** out)
+{
+	*out = nullptr;
+	return guard([&] {
+		typedef GPUSparseMatrix<double> M;
+		std::unique_ptr<ug4b200_host_matrix> m(new ug4b200_host_matrix);
+		M* A = &m->A;
+		std::unique_ptr<ug4b200_host_matrix> tmp;
+		for (int64_t k = 0; k < nops; ++k) {
+			const int code = (int)ops[4 * k]; const size_t r = (size_t)ops[4 * k + 1], c = (size_t)ops[4 * k + 2]; const double v = ops[4 * k + 3];
+			switch (code) {
+				case 0: A->resize_and_clear(r, c); break;
+				case 1: (*A)(r, c) = v; break;
+				case 2: (*A)(r, c) += v; break;
+				case 3: A->scale(v); break;
+				case 4: A->clear_retain_structure(); break;
+				case 5: A->resize_and_keep_values(r, c); break;
+				case 6: A->defragment(); break;
+				case 7: A->set(v); break;
+				case 8: case 9: {
+					tmp.reset(new ug4b200_host_matrix);
+					if (code == 8) tmp->A.set_as_transpose_of(*A, v); else tmp->A.set_as_copy_of(*A, v);
+					m.swap(tmp); A = &m->A;
+					break;
+				}
+				case 10: { const M& cA = *A; volatile double sink = cA(r, c); (void)sink; break; }
+				case 11: case 13: {
+					std::vector<M::connection> row(c);
+					for (size_t t = 0; t < c; ++t) {
+						if (k + 1 + (int64_t)t >= nops || (int)ops[4 * (k + 1 + t)] != 12) UG_THROW("matrix script: row entries (code 12) missing");
+						row[t].iIndex = (size_t)ops[4 * (k + 1 + t) + 2]; row[t].dValue = ops[4 * (k + 1 + t) + 3];
+					}
+					if (code == 11) A->set_matrix_row(r, row.data(), c); else A->add_matrix_row(r, row.data(), c);
+					k += (int64_t)c;
+					break;
+				}
+				default: UG_THROW("matrix script: unknown operation " << code);
+			}
+		}
+		m->pos.resize(0);
+		*out = m.release();
+		return 0;
+	});
+}
+int ug4b200_host_matrix_isolated(const ug4b200_host_matrix* m, unsigned char* isolated)
+{
+	return guard([&] { for (size_t i = 0; i < m->A.num_rows(); ++i) isolated[i] = m->A.is_isolated(i) ? 1 : 0; return 0; });
+}
 int ug4b200_host_ilu_factorize_block(int block, int64_t n, const int64_t* rowptr, const int* cols, double* vals, double beta, double sort_eps)
 {
 	return guard([&] {
