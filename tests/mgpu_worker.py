@@ -1,7 +1,7 @@
 """torchrun entry of the multi-GPU parity tests: a partitioned solve on N GPUs vs the SERIAL oracle
 on the same global grid.
 
-  argv: refs flags [case]
+  argv: refs flags [case [cycle]]
   case "poisson" (default)  GMG V(2,2) Jacobi + CG on 3-D Poisson: same math as the serial solver up to
                             summation order -> compared with the plain serial oracle
   case "elasticity"         the same with 3x3 blocks (block Jacobi, interface exchange of blocks)
@@ -34,6 +34,7 @@ def main():
     refs = int(sys.argv[1]) if len(sys.argv) > 1 else 3
     flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     case = sys.argv[3] if len(sys.argv) > 3 else "poisson"
+    cycle = sys.argv[4] if len(sys.argv) > 4 else "V"          # "V" | "W" | "F" (poisson / elasticity cases)
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
@@ -42,7 +43,7 @@ def main():
     orc = oracle.Oracle("ref" if oracle.have_ref() else "port")
     block = 1
     if case == "poisson":
-        problem, kw, desc = pr.POISSON, {}, gmg_desc(refs)
+        problem, kw, desc = pr.POISSON, {}, gmg_desc(refs, cycle=cycle)
     elif case == "elasticity":
         problem, kw, desc, block = pr.ELASTICITY, {}, gmg_desc(refs, reduction=1e-8, its=200), 3
     elif case == "convdiff_gs":

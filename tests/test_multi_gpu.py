@@ -66,7 +66,15 @@ def test_partitioned_elasticity_block3_matches_serial_oracle(world, flags, p2p, 
     _run(world, flags, p2p, gather, "elasticity", 1e-10, 1e-9)
 
 
-def _run(world, flags, p2p, gather, case, hist_tol, sol_tol):
+@pending
+@pytest.mark.parametrize("world,cycle", [(2, "W"), (4, "F")])
+def test_partitioned_w_and_f_cycles_match_serial_oracle(world, cycle):
+    """W- and F-cycles visit the coarse levels several times: everything below the top level stays partitioned down
+    to the gathered base solve (no replicated coarse cycle)."""
+    _run(world, 0, 1, -1, "poisson", 1e-10, 1e-9, extra=[cycle])
+
+
+def _run(world, flags, p2p, gather, case, hist_tol, sol_tol, extra=()):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     env = dict(os.environ, UG4B200_P2P=str(min(p2p, 1)), UG4B200_FUSED_PUSH="1" if p2p == 2 else "0")
@@ -75,7 +83,7 @@ def _run(world, flags, p2p, gather, case, hist_tol, sol_tol):
         env["UG4B200_GATHER_LEVEL"] = str(gather)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + world + flags + 20 * p2p + 40 * (gather + 1)),
-           os.path.join(ROOT, "tests", "mgpu_worker.py"), "3", str(flags), case]
+           os.path.join(ROOT, "tests", "mgpu_worker.py"), "3", str(flags), case] + list(extra)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     line = [l for l in r.stdout.splitlines() if l.startswith("MGPU_RESULT ")]
     assert line, r.stdout[-3000:] + r.stderr[-3000:]
