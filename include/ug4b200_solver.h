@@ -30,6 +30,7 @@ enum { UG4B200_FLAG_HOST_SCALARS = 1,   /* CG with host scalars (reference-shape
        UG4B200_FLAG_NO_GRAPH = 2,       /* do not capture the Krylov iteration into a CUDA graph */
        UG4B200_FLAG_NO_FUSED_JACOBI = 4,/* V-cycle with separate Jacobi / SpMV / AXPY launches */
        UG4B200_FLAG_FINAL_LEVEL_DEFECT = 8, /* also do the reference's unused top-level defect update */
+       UG4B200_FLAG_DEVICE_LINEAR = 64,   /* LinearSolver with the convergence state on the device + CUDA graph; default: host loop */
        UG4B200_FLAG_DEVICE_BICGSTAB = 32, /* BiCGStab with device-resident scalars + CUDA graph (like CG); default: host scalars */
        UG4B200_FLAG_RAP = 16            /* gmg:set_rap(true): level operators below the top level are the Galerkin
                                            products R A P (mg_solver_impl.hpp:828-1013), computed on the host at init;

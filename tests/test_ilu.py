@@ -431,3 +431,24 @@ def test_gpu_device_resident_bicgstab_equals_host_loop(graph):
         x1, ok1, h1 = mk(capi.FLAG_DEVICE_BICGSTAB | graph).apply(prob.rhs())
         assert ok0 == ok1 and ok0 == (name != "maxsteps"), name
         assert np.array_equal(h0, h1) and np.array_equal(x0, x1), name
+
+
+@pending
+@pytest.mark.gpu
+@pytest.mark.parametrize("graph", [0, 2])
+def test_gpu_device_resident_linear_solver_equals_host_loop(graph):
+    """UG4B200_FLAG_DEVICE_LINEAR: LinearSolver (linear_solver.h:114-196) with the convergence state on the device and one
+    CUDA graph per iteration — same histories and iterates as the reference-shaped loop, also when the step limit is hit."""
+    import ugcore_b200 as ug
+    from ugcore_b200 import capi
+    prob = pr.Problem(dim=3, num_refs=3)
+    cases = {"gmg": gmg_desc(3, solver="linear", reduction=1e-8), "gmg_W": gmg_desc(3, solver="linear", cycle="W", reduction=1e-8),
+             "jac": {"type": "linear", "precond": {"type": "jac", "damping": 0.66}, "convCheck": {"iterations": 50, "absolute": 1e-12, "reduction": 1e-30}},
+             "ilu": {"type": "linear", "precond": {"type": "ilu"}, "convCheck": {"iterations": 300, "absolute": 1e-12, "reduction": 1e-6}},
+             "none": {"type": "linear", "precond": None, "convCheck": {"iterations": 5, "absolute": 1e-12, "reduction": 1e-6}}}
+    for name, desc in cases.items():
+        mk = (lambda fl: ug.Solver.from_problem(desc, prob, flags=fl)) if name.startswith("gmg") else (lambda fl: ug.Solver(desc, prob.matrix(), flags=fl))
+        x0, ok0, h0 = mk(0).apply(prob.rhs())
+        x1, ok1, h1 = mk(capi.FLAG_DEVICE_LINEAR | graph).apply(prob.rhs())
+        assert ok0 == ok1 and ok0 == (name not in ("jac", "none")), name
+        assert np.array_equal(h0, h1) and np.array_equal(x0, x1), name

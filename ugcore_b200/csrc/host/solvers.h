@@ -590,10 +590,17 @@ class LinearSolver : public IPreconditionedLinearOperatorInverse<TVector> {
 	using base_type::linear_operator;
 	using base_type::preconditioner;
 	virtual const char* name() const { return "Iterative Linear Solver"; }
+	~LinearSolver() { drop_graph(); }
+	/// true: the convergence state stays on the device and one iteration (c = B d, d -= A c, x += c, ||d||) is a CUDA
+	/// graph, like CG::apply_device; false (default until measured): the reference-shaped loop, one host sync per step
+	void set_device_resident(bool b) { m_deviceResident = b; }
+	void set_use_graph(bool b) { m_useGraph = b; }
 	virtual bool apply_return_defect(vector_type& x, vector_type& b)
 	{
 		if (x.layouts() && (!b.has_storage_type(PST_ADDITIVE) || !x.has_storage_type(PST_CONSISTENT)))
 			UG_THROW("LinearSolver::apply: Inadequate parallel storage format of Vectors.");
+		StdConvCheck<vector_type>* std_cc = dynamic_cast<StdConvCheck<vector_type>*>(convergence_check().get());
+		if (m_deviceResident && std_cc) return apply_device(x, b, *std_cc);
 		vector_type& d = b;
 		linear_operator()->apply_sub(d, x);
 		SmartPtr<vector_type> spC = x.clone_without_values(); vector_type& c = *spC;
@@ -607,6 +614,78 @@ class LinearSolver : public IPreconditionedLinearOperatorInverse<TVector> {
 		}
 		return convergence_check()->post();
 	}
+
+  protected:
+	typedef detail::KrylovDeviceState KS;
+	void norm_fin(vector_type& d, int op, bool par)
+	{
+		ug4b200_ctx* ctx = GPUManager::ctx();
+		ug4b200_fin fin{op, nullptr, nullptr, nullptr, m_ks.conv};
+		if (!par) { UG_GPU_CHECK(ug4b200_vec_dot_ds(ctx, d.len(), d.dev(), d.dev(), fin)); return; }
+		if (!d.change_storage_type(PST_UNIQUE)) UG_THROW("LinearSolver: cannot make the defect unique");
+		UG_GPU_CHECK(ug4b200_vec_dot_allreduce_ds(ctx, d.len(), d.dev(), d.dev(), fin, m_ks.s + KS::TMP));
+	}
+	void iteration_body(vector_type& x, vector_type& d, vector_type& c, bool par)
+	{
+		if (preconditioner()) { if (!preconditioner()->apply_update_defect(c, d)) UG_THROW("LinearSolver: Cannot apply preconditioner."); }
+		else { c = d; linear_operator()->apply_sub(d, c); }                        // linear_solver.h:160-175
+		x += c;                                                                      // :178
+		norm_fin(d, UG4B200_FIN_CONV_UPDATE, par);                                   // :181
+	}
+	bool apply_device(vector_type& x, vector_type& b, StdConvCheck<vector_type>& cc)
+	{
+		ug4b200_ctx* ctx = GPUManager::ctx();
+		const bool par = (bool)x.layouts();
+		vector_type& d = b;
+		linear_operator()->apply_sub(d, x);
+		SmartPtr<vector_type> spC = x.clone_without_values(); vector_type& c = *spC;
+		c.set_storage_type(PST_CONSISTENT);
+		const int maxSteps = cc.maximum_steps();
+		m_ks.ensure(maxSteps + 2);
+		UG_GPU_CHECK(ug4b200_conv_init(ctx, m_ks.conv, maxSteps, cc.minimum_defect(), cc.relative_reduction(), m_ks.history, m_ks.historyCap));
+		UG_GPU_CHECK(ug4b200_set_guard(ctx, nullptr));
+		norm_fin(d, UG4B200_FIN_CONV_START, par);
+		UG_GPU_CHECK(ug4b200_set_guard(ctx, &m_ks.conv->done));
+		const void* key[3] = {x.dev(), d.dev(), c.dev()};
+		const bool graphOk = m_useGraph;
+		if (graphOk && (!m_graph || std::memcmp(key, m_graphKey, sizeof(key)) != 0)) {
+			drop_graph();
+			UG_GPU_CHECK(ug4b200_graph_begin(ctx));
+			try { iteration_body(x, d, c, par); }
+			catch (...) { ug4b200_graph* g = nullptr; ug4b200_graph_end(ctx, &g); ug4b200_graph_destroy(ctx, g); ug4b200_set_guard(ctx, nullptr); throw; }
+			UG_GPU_CHECK(ug4b200_graph_end(ctx, &m_graph));
+			std::memcpy(m_graphKey, key, sizeof(key));
+		}
+		bool done = false;
+		UG_GPU_CHECK(ug4b200_d2h_async(ctx, &m_ks.pinned[0], m_ks.conv, sizeof(ug4b200_conv_state)));
+		UG_GPU_CHECK(ug4b200_event_record(ctx, m_ks.ev[0]));
+		for (int it = 0; it < maxSteps && !done; ++it) {
+			if (graphOk) UG_GPU_CHECK(ug4b200_graph_launch(ctx, m_graph));
+			else iteration_body(x, d, c, par);
+			const int slot = (it + 1) & 1;
+			UG_GPU_CHECK(ug4b200_d2h_async(ctx, &m_ks.pinned[slot], m_ks.conv, sizeof(ug4b200_conv_state)));
+			UG_GPU_CHECK(ug4b200_event_record(ctx, m_ks.ev[slot]));
+			UG_GPU_CHECK(ug4b200_event_sync(ctx, m_ks.ev[slot ^ 1]));      // the GPU stays one iteration ahead of the host
+			done = m_ks.pinned[slot ^ 1].done != 0;
+		}
+		UG_GPU_CHECK(ug4b200_set_guard(ctx, nullptr));
+		ug4b200_conv_state fin;
+		UG_GPU_CHECK(ug4b200_d2h(ctx, &fin, m_ks.conv, sizeof(fin)));
+		std::vector<number> hist(fin.step + 1);
+		UG_GPU_CHECK(ug4b200_d2h(ctx, hist.data(), m_ks.history, sizeof(double) * hist.size()));
+		cc.adopt_device_state(fin, hist);
+		d.set_storage_type(PST_ADDITIVE);
+		return cc.post();
+	}
+	void drop_graph()
+	{
+		if (m_graph && GPUManager::ctx_or_null()) ug4b200_graph_destroy(GPUManager::ctx_or_null(), m_graph);
+		m_graph = nullptr;
+	}
+	bool m_deviceResident = false, m_useGraph = true;
+	KS m_ks;
+	ug4b200_graph* m_graph = nullptr;
+	const void* m_graphKey[3] = {nullptr, nullptr, nullptr};
 };
 
 /// LU base solver: dense factorisation on the host at init (assembly side), triangular

@@ -82,7 +82,12 @@ struct SolverImpl : SolverBase {
 				s->set_use_graph(!(d.flags & UG4B200_FLAG_NO_GRAPH));
 				s->set_preconditioner(precond); inv = s; break;
 			}
-			case UG4B200_SOLVER_LINEAR: { SmartPtr<LinearSolver<vector_type> > s = make_sp<LinearSolver<vector_type> >(); s->set_preconditioner(precond); inv = s; break; }
+			case UG4B200_SOLVER_LINEAR: {
+				SmartPtr<LinearSolver<vector_type> > s = make_sp<LinearSolver<vector_type> >();
+				s->set_device_resident((d.flags & UG4B200_FLAG_DEVICE_LINEAR) != 0);
+				s->set_use_graph(!(d.flags & UG4B200_FLAG_NO_GRAPH));
+				s->set_preconditioner(precond); inv = s; break;
+			}
 			case UG4B200_SOLVER_GMRES: { SmartPtr<GMRES<vector_type> > s = make_sp<GMRES<vector_type> >((size_t)(d.restart > 0 ? d.restart : 5)); s->set_preconditioner(precond); inv = s; break; }
 			case UG4B200_SOLVER_LU: inv = make_sp<LU<TAlgebra> >(); break;
 			case UG4B200_SOLVER_COARSE_CG: inv = make_sp<CoarseCG<TAlgebra> >(); break;
