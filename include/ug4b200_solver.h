@@ -85,6 +85,12 @@ int ug4b200_solver_set_matrix(ug4b200_solver* s, int64_t nrows, int64_t ncols, c
 int ug4b200_solver_set_level(ug4b200_solver* s, int lev, int64_t nrows, const int64_t* rowptr, const int* cols,
                              const double* vals, int64_t ncoarse, const int64_t* p_rowptr, const int* p_cols,
                              const double* p_vals, const int64_t* r_rowptr, const int* r_cols, const double* r_vals);
+/* surface <-> level index map of the GMG (vSurfLevelMap, mg_solver_impl.hpp:1344-1369): surface index of every top-level
+ * index, for hierarchies whose surface DoF distribution numbers the top level differently from the level DoF
+ * distribution (the matrix given to set_matrix and the vectors of apply are in SURFACE numbering, the level matrices
+ * and transfers in LEVEL numbering).  Without it the map is the identity and the surface <-> level copies of
+ * AssembledMultiGridCycle::apply (:211-217, 244-248) are elided. */
+int ug4b200_solver_set_surface_map(ug4b200_solver* s, int64_t n, const int* surf_index_of_level_index);
 /* colour-sorted DoF order for the Gauss-Seidel smoother of level lev (lev = -1: the direct
  * preconditioner): perm maps old -> new index, colours are [color_ptr[k], color_ptr[k+1]) */
 int ug4b200_solver_set_coloring(ug4b200_solver* s, int lev, int64_t n, const int* perm, int ncolors,

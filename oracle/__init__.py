@@ -108,6 +108,7 @@ class Oracle:
         L.oracle_solver_set_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_solver_set_smoother_matrix.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.oracle_solver_set_precond_matrix.argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_solver_set_surface_map.argtypes = [C.c_void_p, C.c_int64, _ip]
         L.oracle_solver_init.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_solver_apply.argtypes = [C.c_void_p, _dp, _dp, C.c_int]
         L.oracle_solver_steps.argtypes = [C.c_void_p]
@@ -323,7 +324,7 @@ class OSolver:
     """Solver built from a descriptor; ``levels`` maps level -> (A, P, R) OMat triples."""
 
     def __init__(self, orc: Oracle, desc: dict, A: OMat, levels: dict | None = None, smoother_matrices: dict | None = None,
-                 precond_matrix: "OMat | None" = None):
+                 precond_matrix: "OMat | None" = None, surface_map=None):
         self.o = orc
         self.desc = make_desc(desc)
         self.h = orc.lib.oracle_solver_create(C.byref(self.desc))
@@ -338,6 +339,9 @@ class OSolver:
             self._keep.append(smoother_matrices)
             for lev, S in smoother_matrices.items():
                 orc._chk(orc.lib.oracle_solver_set_smoother_matrix(self.h, lev, S.h))
+        if surface_map is not None:      # surface index of every top-level index (GMG only)
+            sm = np.ascontiguousarray(surface_map, dtype=np.int32)
+            orc._chk(orc.lib.oracle_solver_set_surface_map(self.h, sm.size, sm))
         if precond_matrix is not None:   # one-level preconditioner initialised with another matrix (parallel GS / ILU emulation)
             self._keep.append(precond_matrix)
             orc._chk(orc.lib.oracle_solver_set_precond_matrix(self.h, precond_matrix.h))

@@ -99,6 +99,8 @@ int oracle_solver_set_smoother_matrix(oracle_solver* s, int lev, const oracle_ma
 /* one-level preconditioner (Jacobi / GS / ILU) initialised with M instead of the solver's matrix: ugcore's parallel
  * Gauss-Seidel / ILU precondition with their own consistent matrix m_A / m_ILU (gauss_seidel.h:134-142, ilu.h:536-543) */
 int oracle_solver_set_precond_matrix(oracle_solver* s, const oracle_mat* M);
+/* surface index of every top-level index (GMG::apply's surface <-> level copies, mg_solver_impl.hpp:211-217, 244-248) */
+int oracle_solver_set_surface_map(oracle_solver* s, int64_t n, const int* surf_index_of_level_index);
 int oracle_solver_init(oracle_solver* s, const oracle_mat* A);
 /* x: in = start iterate, out = solution; b is not modified.  Returns 0 on success
  * (converged), 1 if the convergence check failed, <0 on error. */

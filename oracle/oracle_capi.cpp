@@ -268,6 +268,14 @@ int oracle_solver_set_smoother_matrix(oracle_solver* s, int lev, const oracle_ma
 		return 0;
 	});
 }
+int oracle_solver_set_surface_map(oracle_solver* s, int64_t n, const int* surf_index_of_level_index)
+{
+	return guard([&] {
+		if (!s->gmg) throw std::runtime_error("solver has no GMG preconditioner");
+		s->gmg->surfMap.assign(surf_index_of_level_index, surf_index_of_level_index + n);
+		return 0;
+	});
+}
 int oracle_solver_set_precond_matrix(oracle_solver* s, const oracle_mat* M) { s->precond_matrix = M; return 0; }
 int oracle_solver_init(oracle_solver* s, const oracle_mat* A)
 {

@@ -351,11 +351,17 @@ bool GMG::init(const Mat& A_)
 bool GMG::apply(Vec& c, const Vec& d)
 {
 	LevData& top = L(topLev);
-	bk.assign(*top.sd, d);             // surface -> level copy (:211-217), identity map
+	const int B = d.block;
+	if (surfMap.empty()) bk.assign(*top.sd, d);   // surface -> level copy (:211-217), identity map
+	else {
+		if ((int64_t)surfMap.size() != top.sd->n) throw std::runtime_error("GMG: surface map has the wrong size");
+		for (int64_t i = 0; i < top.sd->n; ++i) for (int t = 0; t < B; ++t) top.sd->data()[i * B + t] = d.data()[(int64_t)surfMap[i] * B + t];
+	}
 	bk.set(c, 0.0);                    // :231
 	bk.set(*top.sc, 0.0);              // :234
 	lmgc(topLev, cycleType);           // :238
-	bk.add(c, *top.sc);                // :244-248
+	if (surfMap.empty()) bk.add(c, *top.sc);      // :244-248
+	else for (int64_t i = 0; i < top.sc->n; ++i) for (int t = 0; t < B; ++t) c.data()[(int64_t)surfMap[i] * B + t] += top.sc->data()[i * B + t];
 	if (damping != 1.0) bk.scale(c, damping); // :259-260
 	return true;
 }

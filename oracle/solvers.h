@@ -193,6 +193,9 @@ struct GMG : LinearIterator {
 	std::unique_ptr<InverseOperator> baseSolver;
 	std::vector<LevData> lev; // index = level - baseLev
 	double damping = 1.0;
+	// surface index of every top-level index (vSurfLevelMap of a fully refined grid whose surface and level DoF
+	// distributions number the DoFs differently, mg_solver_impl.hpp:1344-1369); empty = identity
+	std::vector<int> surfMap;
 
 	explicit GMG(Backend& b) : LinearIterator(b) {}
 	const char* name() const override { return "Geometric MultiGrid"; }

@@ -73,3 +73,51 @@ def test_gpu_solve_with_reordered_hierarchy_matches_oracle(order):
     # and it is the same problem: the un-reordered solve agrees to solver accuracy
     x0, ok0, h0 = ug.Solver.from_problem(desc, prob).apply(prob.rhs())
     assert ok0 and np.linalg.norm(x - x0) <= 1e-8 * np.linalg.norm(x0)
+
+
+def _surface_problem(seed=4):
+    """A hierarchy whose surface numbering of the top level is a random permutation of its level numbering."""
+    from ugcore_b200.solver import permute_crs
+    prob = pr.Problem(dim=3, num_refs=3)
+    sigma = np.random.default_rng(seed).permutation(prob.matrix(3).nrows)       # surface index of level index
+    A_surf = permute_crs(prob.matrix(3), sigma, sigma)
+    b_surf = np.empty(prob.num_dofs); b_surf[sigma] = prob.rhs()
+    return prob, sigma, A_surf, b_surf
+
+
+@pytest.mark.parametrize("kind", ["port", "ref"])
+def test_oracle_surface_level_map(kind, request):
+    """GMG::apply's surface <-> level copies (mg_solver_impl.hpp:211-217, 244-248) with a non-identity vSurfLevelMap:
+    the solve in surface numbering is the level-numbered solve, permuted (same V-cycle; the Krylov part sums its rows
+    in another order, hence round-off level differences only)."""
+    from helpers import oracle_levels
+    orc = request.getfixturevalue("orc" if kind == "port" else "orc_ref")
+    prob, sigma, A_surf, b_surf = _surface_problem()
+    desc = gmg_desc(3)
+    lv = oracle_levels(orc, prob)
+    x0, ok0, h0 = oracle.OSolver(orc, desc, lv[3][0], lv).apply(np.array(prob.rhs()))
+    x1, ok1, h1 = oracle.OSolver(orc, desc, orc.matrix(A_surf), lv, surface_map=sigma).apply(b_surf)
+    assert ok0 and ok1 and len(h0) == len(h1)
+    assert rel_hist_err(h1, h0) < 1e-11
+    assert np.linalg.norm(x1[sigma] - x0) <= 1e-12 * np.linalg.norm(x0)
+
+
+@pending
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags", [0, 4])
+def test_gpu_surface_level_map_matches_oracle(flags):
+    """The device gathers / scatters of AssembledMultiGridCycle::apply (ug4b200_vec_gather / _scatter_add through the
+    surface map) against the oracle with the same map; flags = 4: unfused V-cycle."""
+    import ugcore_b200 as ug
+    from helpers import oracle_levels
+    prob, sigma, A_surf, b_surf = _surface_problem()
+    desc = gmg_desc(3)
+    levels = _levels(prob)
+    x, ok, h = ug.Solver(dict(desc), A_surf, levels, flags=flags, surface_map=sigma).apply(b_surf)
+    orc = oracle.Oracle("ref" if oracle.have_ref() else "port")
+    xo, oko, ho = oracle.OSolver(orc, desc, orc.matrix(A_surf), oracle_levels(orc, prob), surface_map=sigma).apply(b_surf)
+    assert ok and oko and abs(len(h) - len(ho)) <= 1
+    assert rel_hist_err(h, ho) < 1e-10
+    assert np.linalg.norm(x - xo) <= 1e-9 * np.linalg.norm(xo)
+    with pytest.raises(Exception, match="not a permutation"):
+        ug.Solver(dict(desc), A_surf, levels, surface_map=np.zeros(sigma.size, np.int32))

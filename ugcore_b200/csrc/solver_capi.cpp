@@ -18,6 +18,7 @@ struct SolverBase {
 	                       const int64_t* prp, const int* pci, const double* pva, const int64_t* rrp, const int* rci,
 	                       const double* rva) = 0;
 	virtual void set_coloring(int lev, int64_t n, const int* perm, int ncolors, const int64_t* cp) = 0;
+	virtual void set_surface_map(int64_t n, const int* map) = 0;
 	virtual void set_layouts(int lev, int nneigh, const int* ranks, const int64_t* ptr, const int* idx, int64_t nlocal) = 0;
 	virtual void set_smoother_matrix(int lev, int64_t nrows, const int64_t* rp, const int* ci, const double* va) = 0;
 	virtual void set_gathered_base(int64_t nrows, const int64_t* rp, const int* ci, const double* va, int64_t nlocal, const int* l2g) = 0;
@@ -156,6 +157,13 @@ struct SolverImpl : SolverBase {
 			if (rrp) { R = make_sp<GPUTransferMatrix>(); R->set_from_crs((size_t)ncoarse, (size_t)nrows, rrp, rci, rva); }
 			gmg->set_level_transfer(lev, P, R);
 		}
+	}
+	void set_surface_map(int64_t n, const int* map) override
+	{
+		if (!gmg) UG_THROW("solver has no GMG preconditioner");
+		std::vector<char> seen((size_t)n, 0);
+		for (int64_t i = 0; i < n; ++i) { if (map[i] < 0 || map[i] >= n || seen[(size_t)map[i]]) UG_THROW("surface map is not a permutation"); seen[(size_t)map[i]] = 1; }
+		gmg->set_surface_to_level_map(std::vector<int>(map, map + n));
 	}
 	void set_coloring(int lev, int64_t n, const int* perm, int ncolors, const int64_t* cp) override
 	{
@@ -306,6 +314,8 @@ int ug4b200_solver_set_level(ug4b200_solver* s, int lev, int64_t nrows, const in
                              int64_t ncoarse, const int64_t* p_rowptr, const int* p_cols, const double* p_vals,
                              const int64_t* r_rowptr, const int* r_cols, const double* r_vals)
 { return guard([&] { s->p->set_level(lev, nrows, rowptr, cols, vals, ncoarse, p_rowptr, p_cols, p_vals, r_rowptr, r_cols, r_vals); return 0; }); }
+int ug4b200_solver_set_surface_map(ug4b200_solver* s, int64_t n, const int* surf_index_of_level_index)
+{ return guard([&] { s->p->set_surface_map(n, surf_index_of_level_index); return 0; }); }
 int ug4b200_solver_set_coloring(ug4b200_solver* s, int lev, int64_t n, const int* perm, int ncolors, const int64_t* color_ptr)
 { return guard([&] { s->p->set_coloring(lev, n, perm, ncolors, color_ptr); return 0; }); }
 int ug4b200_solver_set_layouts(ug4b200_solver* s, int lev, int nneigh, const int* neigh_rank, const int64_t* neigh_ptr, const int* indices, int64_t nlocal)

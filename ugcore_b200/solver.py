@@ -190,11 +190,14 @@ class Solver:
     ``A`` is a host CRS (``problems.Crs``); ``levels`` maps level -> (A_l, P_l, R_l) for GMG
     (P_l, R_l None on the base level).  ``Solver.from_problem`` wires a synthetic hierarchy.
     ``order``: DoF reordering applied before upload (``reorder_hierarchy``); ``apply`` takes and returns
-    vectors in the caller's numbering.
+    vectors in the caller's numbering.  ``surface_map``: surface index of every top-level index when ``A`` (and the
+    vectors) are in a surface numbering that differs from the level numbering of ``levels`` (ugcore's vSurfLevelMap).
     """
 
-    def __init__(self, desc: dict, A, levels: dict | None = None, flags: int = 0, order=None):
+    def __init__(self, desc: dict, A, levels: dict | None = None, flags: int = 0, order=None, surface_map=None):
         host_init()
+        if surface_map is not None and order is not None:
+            raise ValueError("order= renumbers surface and levels alike; it cannot be combined with a surface map")
         self.perm = None
         if order is not None:
             A, levels, perms = reorder_hierarchy(A, levels, order)
@@ -215,7 +218,8 @@ class Solver:
         if levels:
             for lev, (Al, Pl, Rl) in sorted(levels.items()):
                 top = lev == self.desc.top_lev
-                skip = top or rap or Al is None          # the top level reuses the surface matrix
+                # the top level reuses the surface matrix — unless the surface is numbered differently (surface_map)
+                skip = (top and surface_map is None) or (rap and not top) or Al is None
                 nrows = Al.nrows if Al is not None else (Pl.nrows if Pl else levels[lev + 1][1].ncols)
                 check_host(host.ug4b200_solver_set_level(
                     self.h, lev, nrows,
@@ -223,6 +227,8 @@ class Solver:
                     Pl.ncols if Pl else 0,
                     _ptr(Pl.rowptr) if Pl else None, _ptr(Pl.cols) if Pl else None, _ptr(Pl.vals) if Pl else None,
                     _ptr(Rl.rowptr) if Rl else None, _ptr(Rl.cols) if Rl else None, _ptr(Rl.vals) if Rl else None))
+        if surface_map is not None:
+            self.set_surface_map(surface_map)
         self._inited = False
 
     @classmethod
@@ -243,6 +249,12 @@ class Solver:
         s = cls(desc, prob.matrix(desc["precond"]["topLevel"] if levels else None), levels, flags, order=order)
         s._keep.append(prob)
         return s
+
+    def set_surface_map(self, surf_index_of_level_index):
+        """GMG on a hierarchy whose SURFACE numbering of the top level differs from its LEVEL numbering
+        (vSurfLevelMap): ``A`` and the vectors of ``apply`` are in surface numbering, ``levels`` in level numbering."""
+        m = np.ascontiguousarray(surf_index_of_level_index, dtype=np.int32)
+        check_host(host.ug4b200_solver_set_surface_map(self.h, m.size, _ptr(m)))
 
     def set_coloring(self, perm, color_ptr, lev: int = -1):
         perm = np.ascontiguousarray(perm, dtype=np.int32)
