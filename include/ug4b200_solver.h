@@ -181,6 +181,12 @@ int ug4b200_host_matrix_script(int64_t nops, const double* ops, ug4b200_host_mat
 /* is_isolated(i) for every row of a host matrix (sparsematrix_impl.h:416-425) */
 int ug4b200_host_matrix_isolated(const ug4b200_host_matrix* m, unsigned char* isolated);
 
+/* y = A^T x on the device through the matrix type's apply_transposed (sparsematrix.h:194-197, sparsematrix_impl.h:341-370):
+ * host CRS in (block x block entries), host vectors in / out; for callers and tests — the solve path itself applies
+ * explicit restriction matrices and never needs the transposed product (std_transfer_impl.h:694-695). */
+int ug4b200_host_apply_transposed(int block, int64_t nrows, int64_t ncols, const int64_t* rowptr, const int* cols,
+                                  const double* vals, double* y_host, const double* x_host);
+
 /* ---- init-time host kernels of ILU and of DoF reordering, exposed for callers and tests (no device involved) ----
  * ILU(0) (beta == 0: FactorizeILUSorted, ilu.h:174-228) or ILU(beta) (FactorizeILUBeta, :110-171) of a scalar CRS
  * matrix with sorted rows, in place in vals: L below the diagonal (unit diagonal implied), U on and above it.

@@ -85,6 +85,7 @@ class Oracle:
         L.oracle_mat_rap.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_axpy.argtypes = [C.c_void_p, _dp, C.c_double, C.c_void_p, C.c_double, _dp, C.c_int]
         L.oracle_apply.argtypes = [C.c_void_p, _dp, _dp, C.c_int]
+        L.oracle_apply_transposed.argtypes = [C.c_void_p, _dp, _dp]
         L.oracle_matmul_minus.argtypes = [C.c_void_p, _dp, _dp, C.c_int]
         L.oracle_apply_ignore_zero_rows.argtypes = [C.c_void_p, _dp, C.c_double, _dp, C.c_int]
         L.oracle_dot.restype = C.c_double
@@ -203,6 +204,11 @@ class OMat:
         vb = self._vb(vblock)
         y = np.zeros(self.nrows * vb)
         self.o._chk(self.o.lib.oracle_apply(self.h, y, _vec(x), vb))
+        return y
+
+    def apply_transposed(self, x):
+        y = np.zeros(self.ncols * self.block)
+        self.o._chk(self.o.lib.oracle_apply_transposed(self.h, y, _vec(x)))
         return y
 
     def matmul_minus(self, y, x, vblock=None):

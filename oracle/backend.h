@@ -58,6 +58,7 @@ struct Backend {
 	virtual void matmul_minus(const Mat& A, Vec& y, const Vec& x) = 0; // y -= A x
 	virtual void axpy(const Mat& A, Vec& dest, double alpha, const Vec& v, double beta, const Vec& w) = 0;
 	virtual void apply_ignore_zero_rows(const Mat& A, Vec& dest, double beta, const Vec& w) = 0;
+	virtual void apply_transposed(const Mat& A, Vec& y, const Vec& x) = 0;  // y = A^T x, sparsematrix_impl.h:341-370
 
 	virtual double dot(const Vec& a, const Vec& b) = 0;
 	virtual double norm(const Vec& a) = 0;

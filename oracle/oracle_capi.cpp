@@ -104,6 +104,15 @@ int oracle_axpy(const oracle_mat* A, double* dest, double alpha, const double* v
 		D.back(); return 0;
 	});
 }
+int oracle_apply_transposed(const oracle_mat* A, double* y, const double* x)
+{
+	return guard([&] {
+		const int vb = A->m->block;
+		VIO Y(A->m->ncols * vb, vb, y, y), X(A->m->nrows * vb, vb, x);
+		BK().apply_transposed(*A->m, *Y.v, *X.v);
+		Y.back(); return 0;
+	});
+}
 int oracle_apply(const oracle_mat* A, double* y, const double* x, int vb)
 {
 	return guard([&] {

@@ -605,6 +605,25 @@ struct PortBackend : Backend {
 		}
 	}
 
+	// sparsematrix_impl.h:341-370 with alpha1 = 0, beta1 = 1: dest = 0; for every stored, non-zero a_ij in row order:
+	// dest[j] = 1.0 * dest[j] + (1.0 * a_ij^T) * w[i]   (MatMultTransposedAdd)
+	void apply_transposed(const Mat& A_, Vec& y, const Vec& x) override
+	{
+		const PMat& A = M(A_); const int B = A.block, BB = B * B;
+		double* yd = y.data(); const double* xd = x.data();
+		for (int64_t i = 0; i < y.len(); ++i) yd[i] = 0.0;
+		for (int64_t i = 0; i < A.nrows; ++i)
+			for (int64_t p = A.rp[i]; p != A.rp[i + 1]; ++p) {
+				bool zero = true;
+				for (int t = 0; t < BB; ++t) if (A.va[p * BB + t] != 0.0) { zero = false; break; }
+				if (zero) continue;
+				double* d = yd + (int64_t)A.ci[p] * B;
+				for (int r = 0; r < B; ++r) {
+					d[r] = 1.0 * d[r];
+					for (int c = 0; c < B; ++c) d[r] = 1.0 * d[r] + 1.0 * A.va[p * BB + c + B * r] * xd[i * B + c];
+				}
+			}
+	}
 	Mat* matrix_script(int64_t, const double*, std::vector<unsigned char>&) override
 	{ throw std::runtime_error("port oracle: the assembly-side matrix API is not restated (use the ref backend)"); }
 

@@ -223,6 +223,12 @@ struct RefBackend : Backend {
 		DISPATCH(A.block, CALL)
 #undef CALL
 	}
+	void apply_transposed(const Mat& A, Vec& y, const Vec& x) override
+	{
+#define CALL(B) SM<B>(A).apply_transposed(V<B>(y), V<B>(x))
+		DISPATCH(A.block, CALL)
+#undef CALL
+	}
 	void axpy(const Mat& A0, Vec& dest, double alpha, const Vec& v, double beta, const Vec& w) override
 	{
 		const Mat& A = for_vec(A0, dest.block);

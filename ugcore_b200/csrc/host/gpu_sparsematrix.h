@@ -232,6 +232,23 @@ class GPUSparseMatrix {
 		                                 w1.dev(), V::blockSize));
 		return true;
 	}
+	/// dest = alpha1 * v1 + beta1 * A^T * w1 (sparsematrix_impl.h:341-370; sparsematrix.h:194-197 apply_transposed).
+	/// The reference scatters row by row; the explicit transpose (built and uploaded on first use, dropped when the
+	/// matrix changes) accumulates every entry of dest over the same terms in the same (ascending row) order.
+	template <typename V> bool axpy_transposed(V& dest, const number& alpha1, const V& v1, const number& beta1, const V& w1) const
+	{
+		if (!m_spTransposed) {
+			UG_COND_THROW(m_hostReleased, "GPUSparseMatrix: host copy was released before the transpose was built");
+			m_spTransposed.reset(new this_type()); m_spTransposed->set_as_transpose_of(*this);
+		}
+		return m_spTransposed->axpy(dest, alpha1, v1, beta1, w1);
+	}
+	template <typename V> bool apply_transposed(V& res, const V& x) const
+	{
+		if (!axpy_transposed(res, 0.0, res, 1.0, x)) return false;
+		res.set_storage_type(PST_ADDITIVE);
+		return true;
+	}
 	template <typename V> bool apply_ignore_zero_rows(V& dest, const number& beta1, const V& w1) const
 	{
 		UG_GPU_CHECK(ug4b200_matrix_apply_ignore_zero_rows(GPUManager::ctx(), device(), dest.dev(), beta1, w1.dev(), V::blockSize));
@@ -253,6 +270,7 @@ class GPUSparseMatrix {
 	{
 		if (m_dev && GPUManager::ctx_or_null()) ug4b200_matrix_destroy(GPUManager::ctx_or_null(), m_dev);
 		m_dev = nullptr;
+		m_spTransposed.reset();
 	}
 	void fragment()
 	{
@@ -278,6 +296,7 @@ class GPUSparseMatrix {
 	std::vector<double> m_vals;
 	bool m_hostReleased = false;
 	ug4b200_matrix* m_dev = nullptr;
+	mutable std::unique_ptr<this_type> m_spTransposed;   // explicit transpose for axpy_transposed / apply_transposed
 };
 
 /// CPUAlgebra / CPUBlockAlgebra<N> counterparts (ugbase/lib_algebra/cpu_algebra_types.h:76-142;

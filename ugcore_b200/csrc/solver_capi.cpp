@@ -439,6 +439,31 @@ int ug4b200_host_rap(int64_t nc, int64_t nf, const int64_t* r_rowptr, const int*
 		return 0;
 	});
 }
+} // extern "C"
+namespace {
+template <typename TAlgebra>
+void apply_transposed_impl(int64_t nrows, int64_t ncols, const int64_t* rp, const int* ci, const double* va, double* y, const double* x)
+{
+	typename TAlgebra::matrix_type A;
+	A.set_from_crs((size_t)nrows, (size_t)ncols, rp, ci, va);
+	typename TAlgebra::vector_type vx((size_t)nrows), vy((size_t)ncols);
+	vx.assign_from_host(x);
+	if (!A.apply_transposed(vy, vx)) UG_THROW("apply_transposed failed");
+	vy.copy_to_host(y);
+}
+} // namespace
+extern "C" {
+int ug4b200_host_apply_transposed(int block, int64_t nrows, int64_t ncols, const int64_t* rowptr, const int* cols,
+                                  const double* vals, double* y_host, const double* x_host)
+{
+	return guard([&] {
+		if (block == 1) apply_transposed_impl<GPUAlgebra>(nrows, ncols, rowptr, cols, vals, y_host, x_host);
+		else if (block == 2) apply_transposed_impl<GPUBlockAlgebra<2> >(nrows, ncols, rowptr, cols, vals, y_host, x_host);
+		else if (block == 3) apply_transposed_impl<GPUBlockAlgebra<3> >(nrows, ncols, rowptr, cols, vals, y_host, x_host);
+		else UG_THROW("block size must be 1, 2 or 3");
+		return 0;
+	});
+}
 int ug4b200_host_matrix_script(int64_t nops, const double* ops, ug4b200_host_matrix** out)
 {
 	*out = nullptr;
