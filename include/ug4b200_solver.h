@@ -187,6 +187,13 @@ int ug4b200_host_matrix_isolated(const ug4b200_host_matrix* m, unsigned char* is
 int ug4b200_host_apply_transposed(int block, int64_t nrows, int64_t ncols, const int64_t* rowptr, const int* cols,
                                   const double* vals, double* y_host, const double* x_host);
 
+/* assembly-side API of the GPU vector type (ugbase/lib_algebra/cpu_algebra/vector.h:63-221), for callers and tests:
+ * srand(seed); v.set_random(from, to)  -> values_out[n*block]  (same numbers as ugcore's Vector for the same seed);
+ * then v.add(add_vals, idx, nidx) on the host mirror, one device operation (v *= 2) and the read-back through
+ * get(idx) -> got_out[nidx*block]; maxnorm_out = v.maxnorm().  Exercises the host mirror <-> device hand-over. */
+int ug4b200_host_vector_selftest(int block, int64_t n, unsigned seed, double from, double to, int64_t nidx, const int64_t* idx,
+                                 const double* add_vals, double* values_out, double* got_out, double* maxnorm_out);
+
 /* ---- init-time host kernels of ILU and of DoF reordering, exposed for callers and tests (no device involved) ----
  * ILU(0) (beta == 0: FactorizeILUSorted, ilu.h:174-228) or ILU(beta) (FactorizeILUBeta, :110-171) of a scalar CRS
  * matrix with sorted rows, in place in vals: L below the diagonal (unit diagonal implied), U on and above it.

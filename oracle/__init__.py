@@ -86,6 +86,7 @@ class Oracle:
         L.oracle_axpy.argtypes = [C.c_void_p, _dp, C.c_double, C.c_void_p, C.c_double, _dp, C.c_int]
         L.oracle_apply.argtypes = [C.c_void_p, _dp, _dp, C.c_int]
         L.oracle_apply_transposed.argtypes = [C.c_void_p, _dp, _dp]
+        L.oracle_vec_set_random.argtypes = [C.c_int64, C.c_int, C.c_uint, C.c_double, C.c_double, _dp, _dp]
         L.oracle_matmul_minus.argtypes = [C.c_void_p, _dp, _dp, C.c_int]
         L.oracle_apply_ignore_zero_rows.argtypes = [C.c_void_p, _dp, C.c_double, _dp, C.c_int]
         L.oracle_dot.restype = C.c_double
@@ -135,6 +136,12 @@ class Oracle:
             raise RuntimeError("oracle: " + self.lib.oracle_last_error().decode())
         m = OMat(self, 1, self.lib.oracle_mat_rows(h), self.lib.oracle_mat_cols(h), None, None, None, handle=h)
         return m, iso[:m.nrows].copy()
+
+    def set_random(self, nblocks, block, seed, lo, hi):
+        """(values, maxnorm) of Vector::set_random(lo, hi) after srand(seed)."""
+        out, mx = np.zeros(nblocks * block), np.zeros(1)
+        self._chk(self.lib.oracle_vec_set_random(nblocks, block, seed, lo, hi, out, mx))
+        return out, float(mx[0])
 
     def dot(self, a, b, block=1):
         a = _vec(a); b = _vec(b)

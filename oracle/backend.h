@@ -62,6 +62,8 @@ struct Backend {
 
 	virtual double dot(const Vec& a, const Vec& b) = 0;
 	virtual double norm(const Vec& a) = 0;
+	virtual double maxnorm(const Vec& a) = 0;                         // vector_impl.h:332-338
+	virtual void set_random(Vec& a, double from, double to) = 0;      // vector_impl.h:91-96 (C rand(), seeded by the caller)
 	virtual void set(Vec& a, double v) = 0;
 	virtual void assign(Vec& dst, const Vec& src) = 0;
 	virtual void add(Vec& dst, const Vec& src) = 0;   // dst += src

@@ -38,6 +38,8 @@ oracle_mat* oracle_mat_rap(const oracle_mat* R, const oracle_mat* A, const oracl
  * v == dest selects the in-place branch */
 int oracle_axpy(const oracle_mat* A, double* dest, double alpha, const double* v, double beta, const double* w, int vblock);
 int oracle_apply(const oracle_mat* A, double* y, const double* x, int vblock);
+/* srand(seed); Vector::set_random(from, to) (vector_impl.h:91-96) and its maxnorm (:332-338) */
+int oracle_vec_set_random(int64_t nblocks, int block, unsigned seed, double from, double to, double* out, double* maxnorm);
 /* y = A^T x (SparseMatrix::apply_transposed -> axpy_transposed, sparsematrix_impl.h:341-370) */
 int oracle_apply_transposed(const oracle_mat* A, double* y, const double* x);
 int oracle_matmul_minus(const oracle_mat* A, double* y, const double* x, int vblock);

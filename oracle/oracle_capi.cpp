@@ -5,6 +5,7 @@
 #include "oracle.h"
 #include "backend.h"
 #include "solvers.h"
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -102,6 +103,16 @@ int oracle_axpy(const oracle_mat* A, double* dest, double alpha, const double* v
 		if (v == dest || alpha == 0.0) BK().axpy(*A->m, *D.v, alpha, *D.v, beta, *W.v);
 		else { VIO V(A->m->nrows * vb, vb, v); BK().axpy(*A->m, *D.v, alpha, *V.v, beta, *W.v); }
 		D.back(); return 0;
+	});
+}
+int oracle_vec_set_random(int64_t nblocks, int block, unsigned seed, double from, double to, double* out, double* maxnorm)
+{
+	return guard([&] {
+		VIO A(nblocks * block, block, nullptr, out);
+		std::srand(seed);
+		BK().set_random(*A.v, from, to);
+		*maxnorm = BK().maxnorm(*A.v);
+		A.back(); return 0;
 	});
 }
 int oracle_apply_transposed(const oracle_mat* A, double* y, const double* x)

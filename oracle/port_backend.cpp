@@ -14,6 +14,7 @@
 #include "backend.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -605,6 +606,14 @@ struct PortBackend : Backend {
 		}
 	}
 
+	double maxnorm(const Vec& a) override
+	{ double d = 0; const double* v = a.data(); for (int64_t i = 0; i < a.len(); ++i) d = std::max(d, std::fabs(v[i])); return d; }
+	// vector_impl.h:91-96 with urand of common/math/misc/math_util_impl.hpp:64-74
+	void set_random(Vec& a, double from, double to) override
+	{
+		double* v = a.data();
+		for (int64_t i = 0; i < a.len(); ++i) { long t = std::rand(); if (t == RAND_MAX) t -= 1; v[i] = from + (double)((to - from) * ((double)t / (double)RAND_MAX)); }
+	}
 	// sparsematrix_impl.h:341-370 with alpha1 = 0, beta1 = 1: dest = 0; for every stored, non-zero a_ij in row order:
 	// dest[j] = 1.0 * dest[j] + (1.0 * a_ij^T) * w[i]   (MatMultTransposedAdd)
 	void apply_transposed(const Mat& A_, Vec& y, const Vec& x) override

@@ -223,6 +223,20 @@ struct RefBackend : Backend {
 		DISPATCH(A.block, CALL)
 #undef CALL
 	}
+	double maxnorm(const Vec& a) override
+	{
+		double r = 0;
+#define CALL(B) r = V<B>(a).maxnorm()
+		DISPATCH(a.block, CALL)
+#undef CALL
+		return r;
+	}
+	void set_random(Vec& a, double from, double to) override
+	{
+#define CALL(B) V<B>(a).set_random(from, to)
+		DISPATCH(a.block, CALL)
+#undef CALL
+	}
 	void apply_transposed(const Mat& A, Vec& y, const Vec& x) override
 	{
 #define CALL(B) SM<B>(A).apply_transposed(V<B>(y), V<B>(x))

@@ -123,3 +123,35 @@ def test_gpu_apply_transposed_is_bit_identical(orc):
         check_host(host.ug4b200_host_apply_transposed(A.block, A.nrows, A.ncols, p(np.ascontiguousarray(A.rowptr)),
                                                       p(np.ascontiguousarray(A.cols)), p(np.ascontiguousarray(A.vals)), p(y), p(x)))
         assert np.array_equal(y, orc.matrix(A).apply_transposed(x))
+
+
+def test_oracle_set_random_and_maxnorm(orc, orc_ref):
+    """Vector::set_random / maxnorm (vector_impl.h:91-96, 332-338): the port restates urand over the C library's rand()."""
+    for block in (1, 3):
+        a, b = orc_ref.set_random(40, block, 7, -1.0, 2.0), orc.set_random(40, block, 7, -1.0, 2.0)
+        assert np.array_equal(a[0], b[0]) and a[1] == b[1] == np.abs(a[0]).max()
+        assert a[0].min() >= -1.0 and a[0].max() < 2.0
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(__import__("os").environ.get("UG4B200_PENDING_GPU_TESTS") != "1",
+                    reason="first GPU run pending (set UG4B200_PENDING_GPU_TESTS=1)")
+@pytest.mark.parametrize("block", [1, 3])
+def test_gpu_vector_assembly_side_api(block, orc):
+    """GPUVector::set_random (same numbers as ugcore's Vector for the same seed), add / get through index lists on the
+    host mirror around a device operation, maxnorm."""
+    from ugcore_b200.capi import check_host, host
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    n, seed = 200, 11
+    idx = np.array([3, 17, 3, 199], np.int64)                       # a repeated index accumulates twice
+    addv = np.arange(1, idx.size * block + 1, dtype=np.float64)
+    vals, got, mx = np.zeros(n * block), np.zeros(idx.size * block), np.zeros(1)
+    check_host(host.ug4b200_host_vector_selftest(block, n, seed, -1.0, 1.0, idx.size, p(idx), p(addv), p(vals), p(got), p(mx)))
+    ref, _ = orc.set_random(n, block, seed, -1.0, 1.0)
+    assert np.array_equal(vals, ref)
+    want = ref.reshape(n, block).copy()
+    for k, i in enumerate(idx):
+        want[i] += addv.reshape(-1, block)[k]
+    want *= 2.0
+    assert np.array_equal(got.reshape(-1, block), want[idx])
+    assert mx[0] == np.abs(want).max()

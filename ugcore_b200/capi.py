@@ -167,6 +167,7 @@ HOST_API = {
     "ug4b200_solver_set_surface_map": (c_int, [c_vp, c_i64, c_vp]),
     "ug4b200_solver_set_layouts": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_i64]),
     "ug4b200_solver_set_smoother_matrix": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),
+    "ug4b200_host_vector_selftest": (c_int, [c_int, c_i64, C.c_uint, c_dbl, c_dbl, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ug4b200_host_apply_transposed": (c_int, [c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ug4b200_host_matrix_script": (c_int, [c_i64, c_vp, C.POINTER(c_vp)]),
     "ug4b200_host_matrix_isolated": (c_int, [c_vp, c_vp]),

@@ -8,7 +8,9 @@
 // ON_CPU/ON_GPU dirty bits; arithmetic never touches the host.
 #pragma once
 #include "ug_base.h"
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace ug {
@@ -87,6 +89,41 @@ class GPUVector {
 		v->m_layouts = m_layouts; v->m_type = PST_UNDEFINED;
 		return v;
 	}
+
+	void create(const this_type& v) { create(v.size()); }                              // vector.h:84
+	void reserve_sloppy(size_t, bool = true) {}                                        // capacity == size on the device
+	void reserve_exactly(size_t, bool) {}
+	void reserve(size_t, bool = true) {}
+	size_t capacity() const { return m_size; }
+	/// values[i] = urand(from, to) in index order with the C library's rand(), like the reference
+	/// (vector_impl.h:91-96, common/math/misc/math_util_impl.hpp:64-74): same seed, same vector
+	void set_random(double from, double to)
+	{
+		std::vector<double> h(len());
+		for (size_t i = 0; i < h.size(); ++i) {
+			long t = std::rand();
+			if (t == RAND_MAX) t -= 1;
+			h[i] = from + (double)((to - from) * ((double)t / (double)RAND_MAX));
+		}
+		if (!h.empty()) assign_from_host(h.data());
+	}
+	/// max_i BlockMaxNorm(values[i]) (vector_impl.h:332-338); not on the solve path: evaluated on the host mirror
+	double maxnorm() const
+	{
+		const_cast<this_type*>(this)->to_host();
+		const double* h = m_size ? reinterpret_cast<const double*>(&m_host[0]) : nullptr;
+		double d = 0;
+		for (size_t i = 0; i < len(); ++i) d = std::max(d, std::fabs(h[i]));
+		return d;
+	}
+	/// element-wise access by index lists (vector.h:158-160; assembly side: host mirror)
+	void add(const value_type* u, const size_t* indices, size_t nr) { for (size_t i = 0; i < nr; ++i) add_block((*this)[indices[i]], u[i]); }
+	void set(const value_type* u, const size_t* indices, size_t nr) { for (size_t i = 0; i < nr; ++i) (*this)[indices[i]] = u[i]; }
+	void get(value_type* u, const size_t* indices, size_t nr) const { for (size_t i = 0; i < nr; ++i) u[i] = (*this)[indices[i]]; }
+	/// local (element) vectors: V offers size(), index(i), operator[](i) (vector.h:153-155)
+	template <typename V> void add(const V& u) { for (size_t i = 0; i < u.size(); ++i) add_block((*this)[u.index(i)], u[i]); }
+	template <typename V> void set(const V& u) { for (size_t i = 0; i < u.size(); ++i) (*this)[u.index(i)] = u[i]; }
+	template <typename V> void get(V& u) const { for (size_t i = 0; i < u.size(); ++i) u[i] = (*this)[u.index(i)]; }
 
 	// ---- host element access (assembly, Dirichlet adjust, output): forces a D2H mirror ----
 	value_type& operator[](size_t i) { to_host(); m_devValid = false; return m_host[i]; }
@@ -240,6 +277,8 @@ class GPUVector {
 	}
 
   protected:
+	static void add_block(double& a, const double& b) { a += b; }
+	template <class X> static void add_block(X& a, const X& b) { for (size_t t = 0; t < X::size(); ++t) a[t] += b[t]; }
 	double* dev_w() { m_devValid = true; m_hostValid = false; return m_dev; } // overwrite: no mirror needed
 	void check_size(const this_type& v) const { UG_COND_THROW(v.m_size != m_size, "GPUVector: size mismatch " << m_size << " vs " << v.m_size); }
 	void to_host()

@@ -452,7 +452,39 @@ void apply_transposed_impl(int64_t nrows, int64_t ncols, const int64_t* rp, cons
 	vy.copy_to_host(y);
 }
 } // namespace
+namespace {
+template <typename TAlgebra>
+void vector_selftest_impl(int64_t n, unsigned seed, double from, double to, int64_t nidx, const int64_t* idx, const double* addv,
+                          double* values, double* got, double* maxnorm)
+{
+	typedef typename TAlgebra::vector_type V;
+	typedef typename V::value_type T;
+	enum { B = TAlgebra::blockSize };
+	V v((size_t)n);
+	std::srand(seed);
+	v.set_random(from, to);
+	v.copy_to_host(values);
+	std::vector<size_t> ind(idx, idx + nidx);
+	std::vector<T> u((size_t)nidx);
+	std::memcpy((void*)u.data(), addv, sizeof(double) * B * (size_t)nidx);
+	v.add(u.data(), ind.data(), (size_t)nidx);          // host mirror
+	v *= 2.0;                                            // device (uploads the mirror first)
+	v.get(u.data(), ind.data(), (size_t)nidx);          // host mirror again (downloads)
+	std::memcpy(got, (const void*)u.data(), sizeof(double) * B * (size_t)nidx);
+	*maxnorm = v.maxnorm();
+}
+} // namespace
 extern "C" {
+int ug4b200_host_vector_selftest(int block, int64_t n, unsigned seed, double from, double to, int64_t nidx, const int64_t* idx,
+                                 const double* add_vals, double* values_out, double* got_out, double* maxnorm_out)
+{
+	return guard([&] {
+		if (block == 1) vector_selftest_impl<GPUAlgebra>(n, seed, from, to, nidx, idx, add_vals, values_out, got_out, maxnorm_out);
+		else if (block == 3) vector_selftest_impl<GPUBlockAlgebra<3> >(n, seed, from, to, nidx, idx, add_vals, values_out, got_out, maxnorm_out);
+		else UG_THROW("block size must be 1 or 3");
+		return 0;
+	});
+}
 int ug4b200_host_apply_transposed(int block, int64_t nrows, int64_t ncols, const int64_t* rowptr, const int* cols,
                                   const double* vals, double* y_host, const double* x_host)
 {
