@@ -133,6 +133,22 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 	/// operators below the top level are not assembled but computed as A_{l-1} = R_l A_l P_l at init
 	/// (init_rap_operator, mg_solver_impl.hpp:828-1013) — only the transfers have to be handed over
 	void set_rap(bool b) { m_bRAP = b; }
+	// ---- the remaining calls util.solver.CreatePreconditioner makes on every GMG (solver_util.lua:846-904) ----
+	/// mg_solver.h: set_gathered_base_solver_if_ambiguous — a partitioned hierarchy always gathers its base solve here
+	/// (mg_solver_impl.hpp:2003-2070), so both settings give the same cycle
+	void set_gathered_base_solver_if_ambiguous(bool b) { m_bGatheredBaseIfAmbiguous = b; }
+	/// adaptive-grid options (rim smoothing :1830-1850, emulation of a fully refined grid): only fully refined
+	/// hierarchies are handed to this class (adaptive rim handling is outside the path)
+	void set_smooth_on_surface_rim(bool b) { if (b) UG_THROW("GMG: adaptive hierarchies (surface rim) are not supported by the GPU algebra"); }
+	void set_emulate_full_refined_grid(bool b) { if (b) UG_THROW("GMG: adaptive hierarchies are not supported by the GPU algebra"); }
+	/// inside ugcore the discretisation assembles the level operators on the CPU (assemble_level_operator :526-752) and
+	/// the results arrive through set_level_operator; debug writer and statistics objects are CPU-side tooling.
+	/// The stand-alone mirror accepts and ignores them so that the factory code compiles unchanged.
+	template <typename TAss> void set_discretization(SmartPtr<TAss>) {}
+	template <typename TWriter> void set_debug(SmartPtr<TWriter>) {}
+	template <typename TStats> void set_mg_stats(SmartPtr<TStats>) {}
+	/// projection of the solution to coarser levels (nonlinear / time-dependent problems): not used by the linear solve
+	template <typename TTransfer> void set_projection(SmartPtr<TTransfer>) {}
 
 	// ---- what assembly hands over (replaces assemble_level_operator :526-752 and the cached
 	//      StdTransfer::prolongation()/restriction() :602-717) ----
@@ -463,7 +479,7 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 
 	int m_baseLev, m_topLev, m_cycleType, m_numPreSmooth, m_numPostSmooth;
 	bool m_bFinalDefect, m_bFuseJacobi;
-	bool m_bRAP = false;
+	bool m_bRAP = false, m_bGatheredBaseIfAmbiguous = false;
 	SmartPtr<smoother_type> m_spPreSmootherPrototype, m_spPostSmootherPrototype;
 	SmartPtr<ILinearOperatorInverse<vector_type> > m_spBaseSolver;
 	SmartPtr<StdTransfer<TAlgebra> > m_spTransferPrototype;
