@@ -32,6 +32,9 @@ class StdTransfer {
 	void set_prolongation_damping(number damp) { m_dampProl = damp; }
 	void set_restriction_damping(number damp) { m_dampRes = damp; }
 	void set_use_transposed(bool b) { m_bUseTransposed = b; }
+	/// std_transfer.h: the P1 fast path of the CPU-side assembly of P (std_transfer_impl.h:46-168) — assembly is upstream
+	void enable_p1_lagrange_optimization(bool) {}
+	template <typename TWriter> void set_debug(SmartPtr<TWriter>) {}
 	/// cached matrices of one level pair (std_transfer.h:195-211); R may be null -> R = P^T
 	void set_matrices(SmartPtr<GPUTransferMatrix> P, SmartPtr<GPUTransferMatrix> R) { m_P = P; m_R = R; }
 	void init()

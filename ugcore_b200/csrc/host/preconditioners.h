@@ -127,6 +127,10 @@ class GaussSeidelBase : public IPreconditioner<TAlgebra> {
 	/// make_consistent) and hands the result over — the device is not involved.
 	void set_layouts(SmartPtr<GPUAlgebraLayouts> l) { m_layouts = l; }
 	void set_consistent_matrix(SmartPtr<matrix_type> A) { m_spConsistent = A; }
+	/// gauss_seidel.h:96-100: the two other parallel modes of ugcore's Gauss-Seidel (consistent interfaces, overlap);
+	/// the default mode (unique defect, Dirichlet rows on the h-slaves) is the one implemented
+	void enable_consistent_interfaces(bool enable) { if (enable) UG_THROW(this->name() << ": the consistent-interfaces mode is not available for the GPU algebra"); }
+	void enable_overlap(bool enable) { if (enable) UG_THROW(this->name() << ": the overlap mode is not available for the GPU algebra"); }
 	/// ordering: old index i -> new index perm[i]; the new order must be colour-sorted with the
 	/// given colour offsets.  Without it a greedy colouring of the stored pattern is used.
 	void set_coloring(const std::vector<int>& perm, const std::vector<int64_t>& colorPtr) { m_perm = perm; m_colorPtr = colorPtr; }
@@ -318,6 +322,13 @@ class ILU : public IPreconditioner<TAlgebra> {
 	/// partitioned runs: see GaussSeidelBase
 	void set_layouts(SmartPtr<GPUAlgebraLayouts> l) { m_layouts = l; }
 	void set_consistent_matrix(SmartPtr<matrix_type> A) { m_spConsistent = A; }
+	/// ilu.h:423-429: ugcore's two other parallel modes; the default one (ilu.h:536-543) is implemented
+	void enable_consistent_interfaces(bool enable) { if (enable) UG_THROW("ILU: the consistent-interfaces mode is not available for the GPU algebra"); }
+	void enable_overlap(bool enable) { if (enable) UG_THROW("ILU: the overlap mode is not available for the GPU algebra"); }
+	/// ilu.h:397-400: any object with ugcore's IOrderingAlgorithm interface (init(&A), compute(), ordering())
+	/// is evaluated on the host copy at preprocess time inside ugcore; here its result is what counts
+	template <typename TOrderingAlgo> void set_ordering_algorithm(SmartPtr<TOrderingAlgo> algo)
+	{ if (algo) set_ordering(algo->ordering()); else { m_mode = ORDER_NONE; m_userOrdering.clear(); m_userColorPtr.clear(); } }
 	int num_groups_L() const { return (int)m_ptrL.size() - 1; }
 	int num_groups_U() const { return (int)m_ptrU.size() - 1; }
 
