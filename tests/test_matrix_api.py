@@ -112,8 +112,6 @@ def test_apply_transposed_scatter_equals_explicit_transpose(orc, orc_ref):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(__import__("os").environ.get("UG4B200_PENDING_GPU_TESTS") != "1",
-                    reason="first GPU run pending (set UG4B200_PENDING_GPU_TESTS=1)")
 def test_gpu_apply_transposed_is_bit_identical(orc):
     from ugcore_b200.capi import check_host, host
     p = lambda a: a.ctypes.data_as(C.c_void_p)
@@ -134,8 +132,6 @@ def test_oracle_set_random_and_maxnorm(orc, orc_ref):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(__import__("os").environ.get("UG4B200_PENDING_GPU_TESTS") != "1",
-                    reason="first GPU run pending (set UG4B200_PENDING_GPU_TESTS=1)")
 @pytest.mark.parametrize("block", [1, 3])
 def test_gpu_vector_assembly_side_api(block, orc):
     """GPUVector::set_random (same numbers as ugcore's Vector for the same seed), add / get through index lists on the
