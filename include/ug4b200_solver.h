@@ -59,7 +59,8 @@ typedef struct ug4b200_solver_desc {
 	 * levels above are partitioned.  gather_lev <= base_lev: only the base solve is gathered
 	 * (mg_solver_impl.hpp:2003-2070). */
 	int gather_lev;
-	int restart;           /* GMRES(restart); <= 0: 5 (solver_util.lua:669-670 creates GMRES(5)) */
+	int restart;           /* GMRES(restart); <= 0: 5 (solver_util.lua:669-670 creates GMRES(5)).  BiCGStab: set_restart(restart),
+	                          <= 0: no periodic restart (bicgstab.h:161-163) */
 	double ilu_beta;       /* ILU(beta), 0 = ILU(0); for precond == ILU and for smoother == ILU inside GMG */
 	int ilu_order;         /* UG4B200_ILU_ORDER_* */
 } ug4b200_solver_desc;

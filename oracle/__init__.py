@@ -298,7 +298,8 @@ def make_desc(desc: dict) -> SolverDesc:
         pc = None if pc == "none" else {"type": pc}
     d.precond = PRECOND[pc["type"] if pc else None]
     d.damp = 1.0
-    d.restart = desc.get("restart", 5)
+    # GMRES(restart): solver_util.lua:669-670 creates GMRES(5); BiCGStab: set_restart(n), 0 = never (bicgstab.h:161-163)
+    d.restart = desc.get("restart", 0 if desc.get("type") == "bicgstab" else 5)
     d.ilu_beta = 0.0
     d.cycle, d.nu1, d.nu2 = 1, 2, 2
     d.smoother, d.smoother_damp = 1, 0.66

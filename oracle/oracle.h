@@ -87,7 +87,7 @@ typedef struct oracle_solver_desc {
 	int base_solver;       /* ORACLE_SOLVER_LU or ORACLE_SOLVER_CG (unpreconditioned, tight tolerance) */
 	int base_max_steps;
 	double base_min_defect, base_rel_reduction;
-	int restart;           /* GMRES(restart) */
+	int restart;           /* GMRES(restart); BiCGStab: numRestarts (0 = never) */
 	double ilu_beta;       /* ILU(beta); 0: ILU(0) (also for an ILU smoother inside GMG: smoother = ORACLE_PRECOND_ILU) */
 } oracle_solver_desc;
 

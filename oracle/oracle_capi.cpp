@@ -258,7 +258,7 @@ oracle_solver* oracle_solver_create(const oracle_solver_desc* d)
 		PrecondInverse* pi = nullptr;
 		switch (d->solver) {
 			case ORACLE_SOLVER_CG: pi = new CG(BK()); break;
-			case ORACLE_SOLVER_BICGSTAB: pi = new BiCGStab(BK()); break;
+			case ORACLE_SOLVER_BICGSTAB: { BiCGStab* b = new BiCGStab(BK()); b->numRestarts = d->restart > 0 ? d->restart : 0; pi = b; break; }
 			case ORACLE_SOLVER_LINEAR: pi = new LinearSolver(BK()); break;
 			case ORACLE_SOLVER_GMRES: { GMRES* g = new GMRES(BK()); g->restart = (size_t)(d->restart > 0 ? d->restart : 5); pi = g; break; }
 			case ORACLE_SOLVER_LU: s->inv.reset(new LU(BK())); s->lone = std::move(pc); break;

@@ -452,3 +452,40 @@ def test_gpu_device_resident_linear_solver_equals_host_loop(graph):
         x1, ok1, h1 = mk(capi.FLAG_DEVICE_LINEAR | graph).apply(prob.rhs())
         assert ok0 == ok1 and ok0 == (name not in ("jac", "none")), name
         assert np.array_equal(h0, h1) and np.array_equal(x0, x1), name
+
+
+def _restart_desc(rs):
+    return {"type": "bicgstab", "restart": rs, "precond": {"type": "jac", "damping": 0.8},
+            "convCheck": {"iterations": 200, "absolute": 1e-12, "reduction": 1e-8}}
+
+
+def test_oracle_bicgstab_periodic_restart(orc, orc_ref):
+    """BiCGStab::set_restart (bicgstab.h:161-216): r0, p, v and the scalars are reset every n steps — a different,
+    converging iteration; both backends agree bit for bit."""
+    prob = pr.Problem(dim=3, num_refs=3, problem=pr.CONVDIFF, eps=1e-2)
+    b = np.array(prob.rhs())
+    hs = {}
+    for rs in (0, 3, 4):
+        x, ok, h = oracle.OSolver(orc_ref, _restart_desc(rs), orc_ref.matrix(prob.matrix())).apply(b)
+        xp, okp, hp = oracle.OSolver(orc, _restart_desc(rs), orc.matrix(prob.matrix())).apply(b)
+        assert ok and okp and np.array_equal(h, hp) and np.array_equal(x, xp)
+        hs[rs] = h
+    assert len(hs[4]) != len(hs[0]) or not np.array_equal(hs[4], hs[0])
+
+
+@pending
+@pytest.mark.gpu
+@pytest.mark.parametrize("rs", [0, 3, 4])
+def test_gpu_bicgstab_periodic_restart_host_and_device_loop(rs):
+    """The restart schedule of the device-resident loop (decided by the host: an iteration is two steps) against the host
+    loop (identical) and the oracle."""
+    import ugcore_b200 as ug
+    from ugcore_b200 import capi
+    prob = pr.Problem(dim=3, num_refs=3, problem=pr.CONVDIFF, eps=1e-2)
+    desc = _restart_desc(rs)
+    x0, ok0, h0 = ug.Solver(desc, prob.matrix()).apply(prob.rhs())
+    x1, ok1, h1 = ug.Solver(desc, prob.matrix(), flags=capi.FLAG_DEVICE_BICGSTAB).apply(prob.rhs())
+    assert ok0 and ok1 and np.array_equal(h0, h1) and np.array_equal(x0, x1)
+    orc = _best()
+    xo, oko, ho = oracle.OSolver(orc, desc, orc.matrix(prob.matrix())).apply(np.array(prob.rhs()))
+    assert oko and abs(len(h0) - len(ho)) <= 1 and rel_hist_err(h0, ho) < 1e-7

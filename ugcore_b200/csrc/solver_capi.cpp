@@ -79,6 +79,7 @@ struct SolverImpl : SolverBase {
 			}
 			case UG4B200_SOLVER_BICGSTAB: {
 				SmartPtr<BiCGStab<vector_type> > s = make_sp<BiCGStab<vector_type> >();
+				s->set_restart(d.restart > 0 ? d.restart : 0);
 				s->set_device_resident((d.flags & UG4B200_FLAG_DEVICE_BICGSTAB) != 0);
 				s->set_use_graph(!(d.flags & UG4B200_FLAG_NO_GRAPH));
 				s->set_preconditioner(precond); inv = s; break;
