@@ -118,3 +118,13 @@ def test_descriptor_defaults_follow_solver_util_lua():
         assert j.precond == JAC_ and j.damp == 0.66
         assert make({"type": "cg", "precond": {"type": "jac", "damping": 0.5}}).damp == 0.5
         assert make({"type": "cg", "precond": {"type": "ilu", "beta": 0.25}}).ilu_beta == 0.25
+
+
+def test_descriptor_errors_name_the_problem():
+    from ugcore_b200 import solver as S
+    for bad, word in (({"type": "sor"}, "linear solver"), ({"type": "cg", "precond": "amg"}, "preconditioner"),
+                      ({"type": "cg", "precond": {"type": "gmg", "topLevel": 2, "smoother": "vanka"}}, "smoother"),
+                      ({"type": "cg", "precond": {"type": "ilu", "ordering": "nested-dissection"}}, "ILU ordering")):
+        with pytest.raises(ValueError, match=word):
+            S.make_desc(bad)
+    assert S.make_desc({"type": "bicgstab"}).restart == 0 and S.make_desc({"type": "bicgstab", "restart": 6}).restart == 6

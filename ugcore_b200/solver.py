@@ -48,10 +48,17 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
+def _lookup(table: dict, key, what: str):
+    try:
+        return table[key]
+    except KeyError:
+        raise ValueError(f"unknown {what} {key!r}; known: {sorted(k for k in table if isinstance(k, str))}") from None
+
+
 def make_desc(desc: dict, block: int = 1, flags: int = 0) -> capi.SolverDesc:
     d = capi.SolverDesc()
     d.block = block
-    d.solver = SOLVER[desc.get("type", "cg")]
+    d.solver = _lookup(SOLVER, desc.get("type", "cg"), "linear solver")
     cc = desc.get("convCheck", {})
     d.max_steps = cc.get("iterations", 100)
     d.min_defect = cc.get("absolute", 1e-12)
@@ -61,7 +68,7 @@ def make_desc(desc: dict, block: int = 1, flags: int = 0) -> capi.SolverDesc:
     pc = desc["precond"] if "precond" in desc else ("ilu" if desc.get("type", "cg") in ("linear", "cg", "bicgstab", "gmres") else None)
     if isinstance(pc, str):
         pc = None if pc == "none" else {"type": pc}
-    d.precond = PRECOND[pc["type"] if pc else None]
+    d.precond = _lookup(PRECOND, pc["type"] if pc else None, "preconditioner")
     d.damp = 1.0
     # GMRES(restart): solver_util.lua:669-670 creates GMRES(5); BiCGStab: set_restart(n), 0 = never (bicgstab.h:161-163)
     d.restart = desc.get("restart", 0 if desc.get("type") == "bicgstab" else 5)
@@ -76,15 +83,17 @@ def make_desc(desc: dict, block: int = 1, flags: int = 0) -> capi.SolverDesc:
             d.damp = pc.get("relax", 1.0)
         elif pc["type"] == "ilu":                # solver_util.lua: ilu = {beta, sort, ...}
             d.ilu_beta = pc.get("beta", 0.0)
-            d.ilu_order = ILU_ORDER[pc.get("ordering", "cmk" if pc.get("sort") else None)]
+            d.ilu_order = _lookup(ILU_ORDER, pc.get("ordering", "cmk" if pc.get("sort") else None), "ILU ordering")
         elif pc["type"] == "gmg":
             sm = pc.get("smoother", "gs")          # defaults.preconditioner.gmg: smoother "gs", preSmooth = postSmooth = 3
             if isinstance(sm, str):
                 sm = {"type": sm}
-            d.smoother = PRECOND[sm["type"]]
+            d.smoother = _lookup(PRECOND, sm["type"], "smoother")
+            if d.smoother == PRECOND["gmg"]:
+                raise ValueError("a GMG cannot smooth a GMG")
             if sm["type"] == "ilu":
                 d.ilu_beta = sm.get("beta", 0.0)
-                d.ilu_order = ILU_ORDER[sm.get("ordering", "cmk" if sm.get("sort") else None)]
+                d.ilu_order = _lookup(ILU_ORDER, sm.get("ordering", "cmk" if sm.get("sort") else None), "ILU ordering")
             d.smoother_damp = sm.get("damping", sm.get("damp", 0.66)) if d.smoother == 1 else sm.get("relax", 1.0)
             d.cycle = {"V": 1, "W": 2, "F": -1}[pc.get("cycle", "V")]
             d.nu1 = pc.get("preSmooth", 3)
