@@ -10,6 +10,7 @@ on the same global grid.
                             (gauss_seidel.h:134-142, 204-215) -> compared with the serial oracle of exactly
                             that method (helpers.partitioned_gs_oracle)
   case "convdiff_ilu"       the same with ILU(0) smoothing (ilu.h:536-543, 640-652: same parallel structure)
+  case "poisson_sgs", "elasticity_sgs"   CG + GMG with symmetric Gauss-Seidel smoothing, scalar and 3x3 blocks
   case "cg_ilu"             no multigrid: CG + ILU(0) (util.solver's default), natural ordering inside a rank
   case "bicgstab_gs"        no multigrid: BiCGStab + one (multicolour) Gauss-Seidel sweep
 """
@@ -52,6 +53,10 @@ def main():
     elif case == "convdiff_ilu":   # ILU(0) smoothing, multicolour ordering inside a rank; parallel mode of ilu.h:536-543, 640-652
         problem, kw = pr.CONVDIFF, {"eps": 1e-1}
         desc = gmg_desc(refs, solver="bicgstab", smoother={"type": "ilu", "ordering": "multicolor"}, reduction=1e-8)
+    elif case == "poisson_sgs":    # CG + GMG with symmetric Gauss-Seidel smoothing (forward, diagonal, backward sweep)
+        problem, kw, desc = pr.POISSON, {}, gmg_desc(refs, smoother={"type": "sgs", "relax": 1.0})
+    elif case == "elasticity_sgs": # the same with 3x3 blocks
+        problem, kw, desc, block = pr.ELASTICITY, {}, gmg_desc(refs, smoother={"type": "sgs", "relax": 1.0}, reduction=1e-8, its=200), 3
     elif case == "cg_ilu":         # util.solver's default configuration: CG preconditioned by ILU(0), one level
         problem, kw = pr.POISSON, {}
         desc = {"type": "cg", "precond": {"type": "ilu"}, "convCheck": {"iterations": 100, "absolute": 1e-12, "reduction": 1e-8}}
@@ -66,7 +71,7 @@ def main():
     if case in ("cg_ilu", "bicgstab_gs"):
         solve, gprob = partitioned_onelevel_oracle(orc, desc, refs, part, problem=problem, colored=(case == "bicgstab_gs"), **kw)
         xo, oko, ho = solve(np.array(gprob.rhs()))
-    elif case in ("convdiff_gs", "convdiff_ilu"):
+    elif case in ("convdiff_gs", "convdiff_ilu", "poisson_sgs", "elasticity_sgs"):
         solve, gprob = partitioned_gs_oracle(orc, desc, refs, part, s.desc.gather_lev, problem=problem, **kw)
         xo, oko, ho = solve(np.array(gprob.rhs()))
     else:

@@ -67,6 +67,13 @@ def test_partitioned_elasticity_block3_matches_serial_oracle(world, flags, p2p, 
 
 
 @pending
+@pytest.mark.parametrize("world,case,tol", [(2, "poisson_sgs", 1e-10), (4, "elasticity_sgs", 1e-9)])
+def test_partitioned_symmetric_gauss_seidel_matches_oracle(world, case, tol):
+    """CG + GMG with symmetric Gauss-Seidel smoothing (scalar and 3x3 blocks) in ugcore's parallel mode."""
+    _run(world, 0, 1, -1, case, tol, 1e-8)
+
+
+@pending
 @pytest.mark.parametrize("world,cycle", [(2, "W"), (4, "F")])
 def test_partitioned_w_and_f_cycles_match_serial_oracle(world, cycle):
     """W- and F-cycles visit the coarse levels several times: everything below the top level stays partitioned down
