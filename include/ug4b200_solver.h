@@ -119,6 +119,13 @@ int ug4b200_solver_set_gathered_base(ug4b200_solver* s, int64_t nrows, const int
 int ug4b200_solver_set_gathered_level(ug4b200_solver* s, int lev, int64_t nrows, const int64_t* rowptr, const int* cols,
                                       const double* vals, int64_t ncoarse, const int64_t* p_rowptr, const int* p_cols,
                                       const double* p_vals, const int64_t* r_rowptr, const int* r_cols, const double* r_vals);
+/* solver:set_debug(GridFunctionDebugWriter): while CG runs, the residual and the solution are written after every step
+ * as <dir>/CG_Residual_iterNNN.vec and <dir>/CG_Solution_iterNNN.vec in ConnectionViewer form (write_debugXR,
+ * ugbase/lib_algebra/operator/linear_solver/cg.h:124, 195, 273-280) — the files a ugcore run with a debug writer leaves,
+ * for side-by-side comparison.  positions: 3 doubles per node or NULL (zeros); precision 0 = the
+ * reference's 16 digits, 17 = lossless.  The solve then runs the host-paced loop (one sync per step).  dir == NULL
+ * switches the writer off again. */
+int ug4b200_solver_set_debug_dir(ug4b200_solver* s, const char* dir, const double* positions, int64_t npos, int dim, int precision);
 /* solver:init(A, u): uploads, smoother preprocess, base factorisation */
 int ug4b200_solver_init(ug4b200_solver* s);
 /* solver:apply(u, b) with HOST vectors: H2D of x and b, solve, D2H of x.

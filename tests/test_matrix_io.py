@@ -262,3 +262,30 @@ def test_solve_from_dumped_files(tmp_path):
     x1, ok1, h1 = oracle.OSolver(orc, desc, lv_file[3][0], lv_file).apply(b)
     x2, ok2, h2 = oracle.OSolver(orc, desc, lv_gen[3][0], lv_gen).apply(np.array(prob.rhs()))
     assert ok1 and ok2 and np.array_equal(h1, h2) and np.array_equal(x1, x2)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("UG4B200_PENDING_GPU_TESTS") != "1", reason="first GPU run pending (set UG4B200_PENDING_GPU_TESTS=1)")
+def test_gpu_cg_debug_writer_leaves_the_reference_file_set(tmp_path):
+    """solver:set_debug(writer): CG_Residual_iterNNN.vec / CG_Solution_iterNNN.vec after every step (cg.h:124, 195,
+    273-280) — readable by the ConnectionViewer reader, residual norms = the defect history, last solution = the result;
+    the history equals the run without a writer (which uses the device-resident loop)."""
+    import ugcore_b200 as ug
+    from ugcore_b200 import io as ugio, problems as pr
+    from helpers import gmg_desc
+    prob = pr.Problem(dim=3, num_refs=3)
+    desc = gmg_desc(3)
+    s = ug.Solver.from_problem(desc, prob)
+    s.set_debug_dir(tmp_path, precision=17)
+    x, ok, h = s.apply(prob.rhs())
+    x0, ok0, h0 = ug.Solver.from_problem(desc, prob).apply(prob.rhs())
+    assert ok and ok0 and len(h) == len(h0) and np.allclose(h, h0, rtol=1e-10)
+    steps = len(h) - 1
+    names = sorted(p.name for p in tmp_path.iterdir())
+    # the write before the loop and the one of the first step both carry the step count 0 (the reference's numbering)
+    assert names == sorted([f"CG_{k}_iter{i:03d}.vec" for k in ("Residual", "Solution") for i in range(steps)])
+    for i in range(steps):
+        r = ugio.read_vector(str(tmp_path / f"CG_Residual_iter{i:03d}.vec"))[0]
+        assert abs(np.linalg.norm(r) - h[i + 1]) <= 1e-12 * h[0]
+    xs = ugio.read_vector(str(tmp_path / f"CG_Solution_iter{steps - 1:03d}.vec"))[0]
+    assert np.array_equal(xs, x)

@@ -165,6 +165,7 @@ HOST_API = {
     "ug4b200_solver_set_level": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ug4b200_solver_set_coloring": (c_int, [c_vp, c_int, c_i64, c_vp, c_int, c_vp]),
     "ug4b200_solver_set_surface_map": (c_int, [c_vp, c_i64, c_vp]),
+    "ug4b200_solver_set_debug_dir": (c_int, [c_vp, C.c_char_p, c_vp, c_i64, c_int, c_int]),
     "ug4b200_solver_set_layouts": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_i64]),
     "ug4b200_solver_set_smoother_matrix": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),
     "ug4b200_host_vector_selftest": (c_int, [c_int, c_i64, C.c_uint, c_dbl, c_dbl, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),

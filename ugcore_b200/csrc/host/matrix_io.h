@@ -333,4 +333,30 @@ class MatrixIOMtx {
 	int m_precision = 13;
 };
 
+/// Writes every vector it is handed as <dir>/<name> in ConnectionViewer form (what GridFunctionDebugWriter does with
+/// its base directory, lib_disc/function_spaces/grid_function_util.h; values with 16+ digits like WriteVector)
+template <typename TVector>
+class ConnectionViewerVectorWriter : public IVectorDebugWriter<TVector> {
+  public:
+	ConnectionViewerVectorWriter(const std::string& dir, const IOPositions& pos, int dim, int precision = 0)
+	    : m_dir(dir), m_pos(pos), m_dim(dim), m_precision(precision) {}
+	virtual void write_vector(const TVector& vec, const char* name)
+	{
+		std::vector<double> h(vec.len());
+		if (!h.empty()) vec.copy_to_host(h.data());
+		IOPositions pos = m_pos;
+		if (pos.size() < h.size()) {   // block vectors: one entry per component, the node's position repeated
+			const size_t B = TVector::blockSize;
+			IOPositions p; p.dim = m_pos.dim; p.resize(h.size());
+			for (size_t i = 0; i < h.size(); ++i) for (int d = 0; d < 3; ++d) p.xyz[3 * i + d] = (i / B) < m_pos.size() ? m_pos[i / B][d] : 0.0;
+			pos = p;
+		}
+		ConnectionViewer::WriteVector(m_dir + "/" + name, h.data(), h.size(), pos, m_dim, m_precision);
+	}
+  private:
+	std::string m_dir;
+	IOPositions m_pos;
+	int m_dim, m_precision;
+};
+
 } // namespace ug

@@ -239,11 +239,24 @@ class StdConvCheck : public IConvergenceCheck<TVector> {
 	std::vector<number> _defects;
 };
 
+/// ugbase/lib_algebra/operator/debug_writer.h: IVectorDebugWriter — receives vectors by name while a solver runs
+/// (CG_Residual_iterNNN.vec …); concrete writer: ConnectionViewerVectorWriter (matrix_io.h)
+template <typename TVector>
+class IVectorDebugWriter {
+  public:
+	virtual ~IVectorDebugWriter() {}
+	virtual void write_vector(const TVector& vec, const char* name) = 0;
+};
+
 template <typename X, typename Y = X>
 class ILinearOperatorInverse {
   public:
 	ILinearOperatorInverse() : m_spConvCheck(new StdConvCheck<X>(100, 1e-12, 1e-12, true)) {}
 	virtual ~ILinearOperatorInverse() {}
+	/// VectorDebugWritingObject (debug_writer.h:262-330): set_debug / vector_debug_writer_valid / write_debug
+	void set_debug(SmartPtr<IVectorDebugWriter<X> > spDebugWriter) { m_spVectorDebugWriter = spDebugWriter; }
+	bool vector_debug_writer_valid() const { return (bool)m_spVectorDebugWriter; }
+	void write_debug(const X& vec, const std::string& name) { if (m_spVectorDebugWriter) m_spVectorDebugWriter->write_vector(vec, name.c_str()); }
 	virtual const char* name() const = 0;
 	virtual bool supports_parallel() const = 0;
 	virtual bool init(SmartPtr<ILinearOperator<Y, X> > L) { m_spLinearOperator = L; return true; }
@@ -260,6 +273,7 @@ class ILinearOperatorInverse {
   protected:
 	SmartPtr<ILinearOperator<Y, X> > m_spLinearOperator;
 	SmartPtr<IConvergenceCheck<X> > m_spConvCheck;
+	SmartPtr<IVectorDebugWriter<X> > m_spVectorDebugWriter;
 };
 
 template <typename X>

@@ -80,11 +80,20 @@ class CG : public IPreconditionedLinearOperatorInverse<TVector> {
 		if (x.layouts() && (!b.has_storage_type(PST_ADDITIVE) || !x.has_storage_type(PST_CONSISTENT)))
 			UG_THROW("CG::apply_return_defect: Inadequate storage format of Vectors.");
 		StdConvCheck<vector_type>* std_cc = dynamic_cast<StdConvCheck<vector_type>*>(convergence_check().get());
-		if (m_deviceResident && std_cc) return apply_device(x, b, *std_cc);
+		// a debug writer wants x and r after every step (cg.h:124, 195): that is the host-paced loop
+		if (m_deviceResident && std_cc && !this->vector_debug_writer_valid()) return apply_device(x, b, *std_cc);
 		return apply_host(x, b);
 	}
 
   protected:
+	/// debugger output: solution and residual (cg.h:273-280)
+	void write_debugXR(vector_type& x, vector_type& r, int loopCnt)
+	{
+		if (!this->vector_debug_writer_valid()) return;
+		char ext[20]; snprintf(ext, 20, "_iter%03d", loopCnt);
+		this->write_debug(r, std::string("CG_Residual") + ext + ".vec");
+		this->write_debug(x, std::string("CG_Solution") + ext + ".vec");
+	}
 	// ---- reference-shaped loop, scalars on the host (cg.h:103-242) ----
 	bool apply_host(vector_type& x, vector_type& b)
 	{
@@ -93,6 +102,7 @@ class CG : public IPreconditionedLinearOperatorInverse<TVector> {
 		SmartPtr<vector_type> spQ = r.clone_without_values(); vector_type& q = *spQ;
 		SmartPtr<vector_type> spZ = x.clone_without_values(); vector_type& z = *spZ;
 		SmartPtr<vector_type> spP = x.clone_without_values(); vector_type& p = *spP;
+		write_debugXR(x, r, convergence_check()->step());                  // cg.h:124 (the step count is the check's current one)
 		if (preconditioner()) { if (!preconditioner()->apply(z, r)) return false; }
 		else z = r;
 		if (z.layouts() && !z.change_storage_type(PST_CONSISTENT)) UG_THROW("CG: Cannot convert z to consistent vector.");
@@ -106,6 +116,7 @@ class CG : public IPreconditionedLinearOperatorInverse<TVector> {
 			const number alpha = rhoOld / lambda;
 			VecScaleAdd(x, 1.0, x, alpha, p);
 			VecScaleAdd(r, 1.0, r, -alpha, q);
+			write_debugXR(x, r, convergence_check()->step());              // cg.h:195 (before the check counts the step)
 			convergence_check()->update(r);
 			if (convergence_check()->iteration_ended()) break;
 			if (preconditioner()) { if (!preconditioner()->apply(z, r)) return false; }

@@ -19,6 +19,7 @@ struct SolverBase {
 	                       const double* rva) = 0;
 	virtual void set_coloring(int lev, int64_t n, const int* perm, int ncolors, const int64_t* cp) = 0;
 	virtual void set_surface_map(int64_t n, const int* map) = 0;
+	virtual void set_debug_dir(const char* dir, const double* positions, int64_t npos, int dim, int precision) = 0;
 	virtual void set_layouts(int lev, int nneigh, const int* ranks, const int64_t* ptr, const int* idx, int64_t nlocal) = 0;
 	virtual void set_smoother_matrix(int lev, int64_t nrows, const int64_t* rp, const int* ci, const double* va) = 0;
 	virtual void set_gathered_base(int64_t nrows, const int64_t* rp, const int* ci, const double* va, int64_t nlocal, const int* l2g) = 0;
@@ -158,6 +159,14 @@ struct SolverImpl : SolverBase {
 			if (rrp) { R = make_sp<GPUTransferMatrix>(); R->set_from_crs((size_t)ncoarse, (size_t)nrows, rrp, rci, rva); }
 			gmg->set_level_transfer(lev, P, R);
 		}
+	}
+	void set_debug_dir(const char* dir, const double* positions, int64_t npos, int dim, int precision) override
+	{
+		if (!dir) { inv->set_debug(SmartPtr<IVectorDebugWriter<vector_type> >()); return; }
+		IOPositions p; p.dim = dim; p.resize((size_t)(npos > 0 ? npos : 0));
+		if (positions && npos > 0) std::memcpy(p.xyz.data(), positions, sizeof(double) * 3 * (size_t)npos);
+		if (!positions) p.resize((size_t)num_dofs());
+		inv->set_debug(make_sp<ConnectionViewerVectorWriter<vector_type> >(std::string(dir), p, dim, precision));
 	}
 	void set_surface_map(int64_t n, const int* map) override
 	{
@@ -315,6 +324,8 @@ int ug4b200_solver_set_level(ug4b200_solver* s, int lev, int64_t nrows, const in
                              int64_t ncoarse, const int64_t* p_rowptr, const int* p_cols, const double* p_vals,
                              const int64_t* r_rowptr, const int* r_cols, const double* r_vals)
 { return guard([&] { s->p->set_level(lev, nrows, rowptr, cols, vals, ncoarse, p_rowptr, p_cols, p_vals, r_rowptr, r_cols, r_vals); return 0; }); }
+int ug4b200_solver_set_debug_dir(ug4b200_solver* s, const char* dir, const double* positions, int64_t npos, int dim, int precision)
+{ return guard([&] { s->p->set_debug_dir(dir, positions, npos, dim, precision); return 0; }); }
 int ug4b200_solver_set_surface_map(ug4b200_solver* s, int64_t n, const int* surf_index_of_level_index)
 { return guard([&] { s->p->set_surface_map(n, surf_index_of_level_index); return 0; }); }
 int ug4b200_solver_set_coloring(ug4b200_solver* s, int lev, int64_t n, const int* perm, int ncolors, const int64_t* color_ptr)

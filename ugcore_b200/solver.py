@@ -266,6 +266,15 @@ class Solver:
         m = np.ascontiguousarray(surf_index_of_level_index, dtype=np.int32)
         check_host(host.ug4b200_solver_set_surface_map(self.h, m.size, _ptr(m)))
 
+    def set_debug_dir(self, path, positions=None, dim: int = 3, precision: int = 0):
+        """solver:set_debug(writer): CG then leaves CG_Residual_iterNNN.vec / CG_Solution_iterNNN.vec in ``path`` after
+        every step, as a ugcore run with a debug writer does (cg.h:124, 195, 273-280).  ``path`` None: off."""
+        if path is None:
+            check_host(host.ug4b200_solver_set_debug_dir(self.h, None, None, 0, dim, precision))
+            return
+        pos = None if positions is None else np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)
+        check_host(host.ug4b200_solver_set_debug_dir(self.h, str(path).encode(), _ptr(pos), 0 if pos is None else pos.shape[0], dim, precision))
+
     def set_coloring(self, perm, color_ptr, lev: int = -1):
         perm = np.ascontiguousarray(perm, dtype=np.int32)
         cp = np.ascontiguousarray(color_ptr, dtype=np.int64)
