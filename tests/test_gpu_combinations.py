@@ -54,5 +54,8 @@ def test_gmg_cycles_and_smoothers(problem, solver):
             desc["restart"] = 4
             x, ok, h = ug.Solver.from_problem(desc, prob).apply(prob.rhs())
             xo, oko, ho = oracle.OSolver(orc, desc, lv[3][0], lv).apply(np.array(prob.rhs()))
-            assert ok and oko and abs(len(h) - len(ho)) <= 1, (solver, sm, cycle)
-            assert rel_hist_err(h, ho) < 1e-8, (solver, sm, cycle, rel_hist_err(h, ho))
+            # (CG is not a solver for the non-symmetric operator: it need not converge, but must fail the same way)
+            assert ok == oko and abs(len(h) - len(ho)) <= 1, (solver, sm, cycle)
+            assert oko or (solver == "cg" and problem == "convdiff"), (solver, sm, cycle)
+            if oko:
+                assert rel_hist_err(h, ho) < 1e-8, (solver, sm, cycle, rel_hist_err(h, ho))
