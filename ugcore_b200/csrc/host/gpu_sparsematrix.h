@@ -268,6 +268,7 @@ class GPUSparseMatrix {
 	void touch() { drop_device(); UG_COND_THROW(m_hostReleased, "GPUSparseMatrix: host copy was released, matrix is immutable"); }
 	void drop_device()
 	{
+		if (m_dev) GPUManager::bump_generation();   // graphs that captured this mirror must not be replayed
 		if (m_dev && GPUManager::ctx_or_null()) ug4b200_matrix_destroy(GPUManager::ctx_or_null(), m_dev);
 		m_dev = nullptr;
 		m_spTransposed.reset();

@@ -182,6 +182,7 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 		if (!m_spPostSmootherPrototype) UG_THROW("GMG::init: PostSmoother not set.");
 		if (!m_spTransferPrototype) m_spTransferPrototype = make_sp<StdTransfer<TAlgebra> >();
 		ug4b200_ctx* ctx = GPUManager::ctx();
+		GPUManager::bump_generation();   // level vectors / matrices are rebuilt: captured solver graphs are stale
 		if (m_bRAP) init_rap_operator();
 		for (int lev = m_baseLev; lev <= m_topLev; ++lev) {
 			LevData& ld = level(lev);

@@ -105,6 +105,7 @@ class IPreconditioner : public ILinearIterator<typename TAlgebra::vector_type> {
 	{
 		m_spApproxOperator = Op; m_spDefectOperator = Op;
 		if (!m_spApproxOperator) UG_THROW(name() << "::init': Passed Operator is invalid.");
+		GPUManager::bump_generation();   // preprocess rebuilds the device buffers a captured graph points at
 		if (!preprocess(m_spApproxOperator)) return false;
 		m_bInit = true;
 		return true;
@@ -259,8 +260,8 @@ class ILinearOperatorInverse {
 	void write_debug(const X& vec, const std::string& name) { if (m_spVectorDebugWriter) m_spVectorDebugWriter->write_vector(vec, name.c_str()); }
 	virtual const char* name() const = 0;
 	virtual bool supports_parallel() const = 0;
-	virtual bool init(SmartPtr<ILinearOperator<Y, X> > L) { m_spLinearOperator = L; return true; }
-	virtual bool init(SmartPtr<ILinearOperator<Y, X> > J, const Y&) { m_spLinearOperator = J; return true; }
+	virtual bool init(SmartPtr<ILinearOperator<Y, X> > L) { GPUManager::bump_generation(); m_spLinearOperator = L; return true; }
+	virtual bool init(SmartPtr<ILinearOperator<Y, X> > J, const Y&) { GPUManager::bump_generation(); m_spLinearOperator = J; return true; }
 	virtual bool apply(Y& u, const X& f) = 0;
 	virtual bool apply_return_defect(Y& u, X& f) = 0;
 	number defect() const { return convergence_check()->defect(); }
@@ -284,7 +285,7 @@ class IPreconditionedLinearOperatorInverse : public ILinearOperatorInverse<X> {
 	using base_type::name;
 	IPreconditionedLinearOperatorInverse() {}
 	explicit IPreconditionedLinearOperatorInverse(SmartPtr<ILinearIterator<X, X> > spPrecond) : m_spPrecond(spPrecond) {}
-	void set_preconditioner(SmartPtr<ILinearIterator<X, X> > spPrecond) { m_spPrecond = spPrecond; }
+	void set_preconditioner(SmartPtr<ILinearIterator<X, X> > spPrecond) { GPUManager::bump_generation(); m_spPrecond = spPrecond; }
 	SmartPtr<ILinearIterator<X, X> > preconditioner() { return m_spPrecond; }
 	virtual bool supports_parallel() const { return m_spPrecond ? m_spPrecond->supports_parallel() : true; }
 	virtual bool init(SmartPtr<ILinearOperator<X, X> > J, const X& u)

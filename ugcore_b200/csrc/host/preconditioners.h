@@ -133,7 +133,7 @@ class GaussSeidelBase : public IPreconditioner<TAlgebra> {
 	void enable_overlap(bool enable) { if (enable) UG_THROW(this->name() << ": the overlap mode is not available for the GPU algebra"); }
 	/// ordering: old index i -> new index perm[i]; the new order must be colour-sorted with the
 	/// given colour offsets.  Without it a greedy colouring of the stored pattern is used.
-	void set_coloring(const std::vector<int>& perm, const std::vector<int64_t>& colorPtr) { m_perm = perm; m_colorPtr = colorPtr; }
+	void set_coloring(const std::vector<int>& perm, const std::vector<int64_t>& colorPtr) { m_perm = perm; m_colorPtr = colorPtr; m_userPerm = true; }
 	const std::vector<int>& ordering() const { return m_perm; }
 	const std::vector<int64_t>& color_ptr() const { return m_colorPtr; }
 	~GaussSeidelBase() { free_dev(); }
@@ -167,8 +167,17 @@ class GaussSeidelBase : public IPreconditioner<TAlgebra> {
 			}
 		}
 		const std::vector<double>& va = m_layouts ? vaPar : A.crs_vals();
-		if (m_perm.size() != n) {
-			// greedy colouring in row order, colours sorted, stable inside a colour
+		// the sweeps divide by a_ii (core_smoothers.h:105-206): a row without a stored diagonal connection has no
+		// meaningful sweep (the reference divides by the 0 its const access returns) — refuse it here
+		for (size_t r = 0; r < n; ++r) {
+			bool haveDiag = false;
+			for (int64_t p = rp[r]; p < rp[r + 1] && !haveDiag; ++p) haveDiag = ((size_t)ci[p] == r);
+			if (!haveDiag) UG_THROW(this->name() << ": row " << r << " has no diagonal connection");
+		}
+		if (m_userPerm) THROW_IF_NOT_EQUAL(m_perm.size(), n);
+		else {
+			// greedy colouring in row order, colours sorted, stable inside a colour; recomputed on every
+			// preprocess (the pattern may have changed at the same n)
 			std::vector<int> color(n); int nc = 0;
 			ug4b200_color_greedy((int64_t)n, rp.data(), ci.data(), color.data(), &nc);
 			m_colorPtr.assign(nc + 1, 0);
@@ -177,8 +186,7 @@ class GaussSeidelBase : public IPreconditioner<TAlgebra> {
 			std::vector<int64_t> fill(m_colorPtr.begin(), m_colorPtr.end() - 1);
 			m_perm.resize(n);
 			for (size_t i = 0; i < n; ++i) m_perm[i] = (int)fill[color[i]]++;
-			m_userPerm = false;
-		} else m_userPerm = true;
+		}
 		// PA(perm[r], perm[c]) = A(r, c)   (SetMatrixAsPermutation, permutation_util.h:50-64)
 		std::vector<int> inv(n);
 		for (size_t i = 0; i < n; ++i) inv[m_perm[i]] = (int)i;

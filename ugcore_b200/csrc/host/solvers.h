@@ -211,8 +211,9 @@ class CG : public IPreconditionedLinearOperatorInverse<TVector> {
 		// graph of one iteration, keyed by the buffers it touches
 		const void* key[5] = {x.dev(), r.dev(), q.dev(), z.dev(), p.dev()};
 		bool graphOk = m_useGraph;
-		if (graphOk && (!m_graph || std::memcmp(key, m_graphKey, sizeof(key)) != 0)) {
+		if (graphOk && (!m_graph || m_graphGen != GPUManager::generation() || std::memcmp(key, m_graphKey, sizeof(key)) != 0)) {
 			drop_graph();
+			m_graphGen = GPUManager::generation();
 			UG_GPU_CHECK(ug4b200_graph_begin(c));
 			try { iteration_body(x, r, q, z, p, parallel); }
 			catch (...) { ug4b200_graph* g = nullptr; ug4b200_graph_end(c, &g); ug4b200_graph_destroy(c, g); ug4b200_set_guard(c, nullptr); throw; }
@@ -255,6 +256,7 @@ class CG : public IPreconditionedLinearOperatorInverse<TVector> {
 	bool m_deviceResident = true, m_useGraph = true;
 	KS m_ks;
 	ug4b200_graph* m_graph = nullptr;
+	unsigned long long m_graphGen = 0;   // GPUManager::generation() the graph was captured under
 	const void* m_graphKey[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -443,8 +445,9 @@ class BiCGStab : public IPreconditionedLinearOperatorInverse<TVector> {
 		restart_block(r, r0, p, v, par);            // sets the storage types the captured body relies on
 		const void* key[8] = {x.dev(), r.dev(), r0.dev(), p.dev(), v.dev(), t.dev(), s.dev(), q.dev()};
 		bool graphOk = m_useGraph;
-		if (graphOk && (!m_graph || std::memcmp(key, m_graphKey, sizeof(key)) != 0)) {
+		if (graphOk && (!m_graph || m_graphGen != GPUManager::generation() || std::memcmp(key, m_graphKey, sizeof(key)) != 0)) {
 			drop_graph();
+			m_graphGen = GPUManager::generation();
 			UG_GPU_CHECK(ug4b200_graph_begin(c));
 			try { iteration_body(x, r, r0, p, v, t, s, q, par); }
 			catch (...) { ug4b200_graph* g = nullptr; ug4b200_graph_end(c, &g); ug4b200_graph_destroy(c, g); ug4b200_set_guard(c, nullptr); throw; }
@@ -488,6 +491,7 @@ class BiCGStab : public IPreconditionedLinearOperatorInverse<TVector> {
 	KS m_ks;
 	double* m_scal = nullptr;
 	ug4b200_graph* m_graph = nullptr;
+	unsigned long long m_graphGen = 0;   // GPUManager::generation() the graph was captured under
 	const void* m_graphKey[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -659,8 +663,9 @@ class LinearSolver : public IPreconditionedLinearOperatorInverse<TVector> {
 		UG_GPU_CHECK(ug4b200_set_guard(ctx, &m_ks.conv->done));
 		const void* key[3] = {x.dev(), d.dev(), c.dev()};
 		const bool graphOk = m_useGraph;
-		if (graphOk && (!m_graph || std::memcmp(key, m_graphKey, sizeof(key)) != 0)) {
+		if (graphOk && (!m_graph || m_graphGen != GPUManager::generation() || std::memcmp(key, m_graphKey, sizeof(key)) != 0)) {
 			drop_graph();
+			m_graphGen = GPUManager::generation();
 			UG_GPU_CHECK(ug4b200_graph_begin(ctx));
 			try { iteration_body(x, d, c, par); }
 			catch (...) { ug4b200_graph* g = nullptr; ug4b200_graph_end(ctx, &g); ug4b200_graph_destroy(ctx, g); ug4b200_set_guard(ctx, nullptr); throw; }
@@ -696,6 +701,7 @@ class LinearSolver : public IPreconditionedLinearOperatorInverse<TVector> {
 	bool m_deviceResident = false, m_useGraph = true;
 	KS m_ks;
 	ug4b200_graph* m_graph = nullptr;
+	unsigned long long m_graphGen = 0;   // GPUManager::generation() the graph was captured under
 	const void* m_graphKey[3] = {nullptr, nullptr, nullptr};
 };
 
@@ -746,6 +752,7 @@ class LU : public ILinearOperatorInverse<typename TAlgebra::vector_type> {
 		}
 #undef AA
 		free_dev();
+		GPUManager::bump_generation();
 		ug4b200_ctx* c = GPUManager::ctx();
 		m_lu = (double*)GPUManager::alloc_bytes(sizeof(double) * n * n);
 		m_piv = (int*)GPUManager::alloc_bytes(sizeof(int) * n);
@@ -793,6 +800,7 @@ class CoarseCG : public ILinearOperatorInverse<typename TAlgebra::vector_type> {
 		m_spOperator = std::dynamic_pointer_cast<matrix_operator_type>(L);
 		if (!m_spOperator) UG_THROW("CoarseCG::init: Passed operator is not a matrix operator.");
 		if (m_work) GPUManager::release(m_work, m_n * 4);
+		GPUManager::bump_generation();
 		m_n = m_spOperator->num_rows() * B;
 		m_work = GPUManager::alloc(m_n * 4);
 		m_spOperator->device();

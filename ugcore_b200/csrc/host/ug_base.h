@@ -133,6 +133,11 @@ class GPUManager {
 	static int proc_rank() { return inst().m_rank; }
 	static int num_procs() { return inst().m_nranks; }
 	static void set_procs(int nranks, int rank) { inst().m_nranks = nranks; inst().m_rank = rank; }
+	/// Generation of the device-side solver data.  Bumped whenever a matrix mirror, a preconditioner's device
+	/// buffers or a level hierarchy is (re)built or dropped; captured CUDA graphs bake those pointers in and are
+	/// only replayed while the generation they were captured under is still current (solvers.h).
+	static unsigned long long generation() { return inst().m_generation; }
+	static void bump_generation() { ++inst().m_generation; }
 
   private:
 	static GPUManager& inst() { static GPUManager m; return m; }
@@ -143,6 +148,7 @@ class GPUManager {
 	}
 	ug4b200_ctx* m_ctx = nullptr;
 	int m_rank = 0, m_nranks = 1;
+	unsigned long long m_generation = 1;
 	std::map<size_t, std::vector<double*> > m_pool;
 };
 

@@ -377,21 +377,31 @@ void build_rhs(synth_problem& Pb)
 	Pb.exact.assign((size_t)L.nn * B, 0.0);
 	const double pi = 3.14159265358979323846;
 	const double scv = std::ldexp(std::pow(L.h, dim), -dim); // per adjacent element
+	// Poisson: u = 1/2 (u1 + u2), u1 = prod sin(pi x_q / D_q) the fundamental mode of the whole domain
+	// [0, D_0] x .. (D_q = base[q] unit cells), u2 = prod sin(pi x_q) the fundamental mode of one base cell.
+	// On the unit cube both coincide (u = u1 = u2 bit for bit: s + s and 0.5 * are exact).  On a domain of several
+	// base cells — the partitioned runs, one cell per rank — u2 alone would be antisymmetric about every partition
+	// plane, so that solution, defect and corrections vanish on all interfaces and the exchanges only ever add
+	// +v and -v; with u1 the interface values are O(1) and the solution is neither symmetric nor antisymmetric.
+	double lam1 = 0.0;
+	for (int q = 0; q < dim; ++q) lam1 += 1.0 / ((double)d.base[q] * (double)d.base[q]);
 #pragma omp parallel for schedule(static)
 	for (int64_t dof = 0; dof < L.nn; ++dof) {
 		int64_t lex = L.lexof[dof];
 		const int ii[3] = {(int)(lex % L.n[0]), (int)((lex / L.n[0]) % L.n[1]), (int)(lex / ((int64_t)L.n[0] * L.n[1]))};
 		int nel = 1;
-		double s = 1.0;
+		double s = 1.0, s1 = 1.0;
 		for (int q = 0; q < dim; ++q) {
 			nel *= (ii[q] > 0) + (ii[q] < L.n[q] - 1);
-			s *= std::sin(pi * (double)(L.e0[q] + ii[q]) * L.h);
+			const double xq = (double)(L.e0[q] + ii[q]) * L.h;
+			s *= std::sin(pi * xq);
+			s1 *= std::sin(pi * xq / (double)d.base[q]);
 		}
 		const double vol = nel * scv;
 		if (d.problem == SYNTH_POISSON) {
-			Pb.exact[dof] = s;
+			Pb.exact[dof] = 0.5 * (s1 + s);
 			// FV1 source: f evaluated at the vertex times the SCV volume (fv1_geom.h:314)
-			if (!L.dir[dof]) Pb.rhs[dof] = (dim * pi * pi * s) * vol;
+			if (!L.dir[dof]) Pb.rhs[dof] = (0.5 * (lam1 * pi * pi * s1 + dim * pi * pi * s)) * vol;
 		} else if (d.problem == SYNTH_CONVDIFF) {
 			if (!L.dir[dof]) Pb.rhs[dof] = vol;
 		} else {
