@@ -66,23 +66,39 @@ def main():
     else:
         raise SystemExit(f"unknown case {case}")
     prob, s = ugdist.build_partitioned_solver(desc, refs, part, rank, dist, problem=problem, flags=flags, **kw)
-    x, ok, h = s.apply(prob.rhs())
+    gid = prob.global_ids(refs)
+    g = np.repeat(gid * block, block) + np.tile(np.arange(block), gid.size)
+    seed = os.environ.get("UG4B200_TEST_RHS_SEED")
+    if seed:
+        # seeded random global right-hand side (0 on Dirichlet DoFs), handed to the ranks in UNIQUE form (the h-master
+        # holds the value, the other copies 0 — a valid additive vector whose sum over the copies is exactly b_glob):
+        # interface values are O(1) and unrelated on the two sides of every partition plane
+        gtop = ugdist.global_problem(refs, part, problem=problem, **kw)
+        b_glob = np.random.default_rng(int(seed)).standard_normal(gtop.num_dofs)
+        b_glob[np.repeat(np.asarray(gtop.dirichlet(refs), bool), block)] = 0.0
+        own = np.repeat(ugdist.owned_mask(prob, refs, rank), block)
+        b_loc = np.where(own, b_glob[g], 0.0)
+        rhs_of = lambda gp: b_glob
+    else:
+        b_loc = prob.rhs()
+        rhs_of = lambda gp: np.array(gp.rhs())
+    x, ok, h = s.apply(b_loc)
 
     if case in ("cg_ilu", "bicgstab_gs"):
         solve, gprob = partitioned_onelevel_oracle(orc, desc, refs, part, problem=problem, colored=(case == "bicgstab_gs"), **kw)
-        xo, oko, ho = solve(np.array(gprob.rhs()))
+        xo, oko, ho = solve(rhs_of(gprob))
     elif case in ("convdiff_gs", "convdiff_ilu", "poisson_sgs", "elasticity_sgs"):
         solve, gprob = partitioned_gs_oracle(orc, desc, refs, part, s.desc.gather_lev, problem=problem, **kw)
-        xo, oko, ho = solve(np.array(gprob.rhs()))
+        xo, oko, ho = solve(rhs_of(gprob))
     else:
         gprob = ugdist.global_problem(refs, part, problem=problem, **kw)
         lv = oracle_levels(orc, gprob)
-        xo, oko, ho = oracle.OSolver(orc, desc, lv[refs][0], lv).apply(gprob.rhs())
-    gid = prob.global_ids(refs)
-    g = np.repeat(gid * block, block) + np.tile(np.arange(block), gid.size)
+        xo, oko, ho = oracle.OSolver(orc, desc, lv[refs][0], lv).apply(rhs_of(gprob))
     from ugcore_b200 import capi
     res = {"rank": rank, "p2p": bool(capi.dev.ug4b200_p2p_enabled(S.host_ctx())), "ok": bool(ok), "oracle_ok": bool(oko), "its": len(h) - 1, "its_oracle": len(ho) - 1,
-           "hist_err": rel_hist_err(h, ho), "sol_err": float(np.linalg.norm(x - xo[g]) / np.linalg.norm(xo[g]))}
+           "hist_err": rel_hist_err(h, ho), "sol_err": float(np.linalg.norm(x - xo[g]) / np.linalg.norm(xo[g])),
+           "iface_rel": float(np.max(np.abs(x[np.repeat(ugdist.multiplicity(prob, refs) > 1, block)])) / max(np.max(np.abs(x)), 1e-300)),
+           "final_reduction": float(h[-1] / h[0])}
     out = [None] * world
     dist.all_gather_object(out, res)
     if rank == 0:

@@ -11,9 +11,7 @@ import oracle
 from helpers import gmg_desc, oracle_levels, rel_hist_err
 from ugcore_b200 import problems as pr
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("UG4B200_PENDING_GPU_TESTS") != "1",
-                                 reason="first GPU run pending (set UG4B200_PENDING_GPU_TESTS=1)")]
+pytestmark = pytest.mark.gpu
 CC = {"iterations": 60, "absolute": 1e-12, "reduction": 1e-8}
 
 

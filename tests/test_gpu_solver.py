@@ -265,3 +265,74 @@ def test_value_indexed_and_plain_streams_give_identical_histories():
         out.append(json.loads(line[0][4:]))
     assert out[0]["ok"] and out[1]["ok"]
     assert out[0]["h"] == out[1]["h"] and out[0]["x"] == out[1]["x"]
+
+
+@pytest.mark.parametrize("precond", ["jac", "gs", "ilu", "gmg"])
+@pytest.mark.parametrize("solver", ["cg", "bicgstab", "linear"])
+def test_reinit_with_a_changed_matrix_recaptures_the_graph(solver, precond):
+    """solver:init(J, u) with a re-assembled J on the SAME solver object (every Newton / time step in ugcore): first
+    with other values, then with another pattern at the same n (an explicit-zero connection removed from some rows).
+    The device-resident loops replay a CUDA graph that bakes in the matrix mirror and the preconditioner's buffers;
+    the pool hands the re-created work vectors the same addresses, so only the generation of the device data
+    tells a stale graph from a valid one.  Every solve must equal the oracle's solve of the matrix it was given."""
+    import oracle
+    import ugcore_b200 as ug
+    from ugcore_b200 import capi, problems as pr
+    orc = _best_oracle()
+    prob = pr.Problem(dim=3, num_refs=3, problem=pr.CONVDIFF if solver != "cg" else pr.POISSON, eps=0.5)
+    A0 = prob.matrix()
+    cc = {"iterations": 200, "absolute": 1e-14, "reduction": 1e-8}
+    if precond == "gmg":
+        desc = gmg_desc(3, solver=solver, reduction=1e-8)
+    else:
+        pc = {"jac": {"type": "jac", "damp": 0.66}, "gs": {"type": "sgs" if solver == "cg" else "gs"},
+              "ilu": {"type": "ilu", "ordering": "multicolor"}}[precond]
+        desc = {"type": solver, "precond": pc, "convCheck": cc}
+    flags = capi.FLAG_DEVICE_BICGSTAB | capi.FLAG_DEVICE_LINEAR
+    # second matrix: same pattern, other values (2 A + 25 % more diagonal); third: another pattern at the same n (the
+    # explicit zeros that the Dirichlet rows keep, sparsematrix_util.h:850-861, removed: nnz and the slices change)
+    rows = np.repeat(np.arange(A0.nrows), np.diff(A0.rowptr))
+    diag = rows == A0.cols
+    v1 = 2.0 * np.asarray(A0.vals) + np.where(diag, 0.25 * np.asarray(A0.vals), 0.0)
+    A1 = pr.Crs(A0.nrows, A0.ncols, 1, A0.rowptr.copy(), A0.cols.copy(), v1)
+    dirich = np.asarray(prob.dirichlet(), bool)
+    keep = ~(dirich[rows] & ~diag)
+    assert keep.sum() < A0.nnz
+    rp2 = np.concatenate([[0], np.cumsum(np.bincount(rows[keep], minlength=A0.nrows))]).astype(np.int64)
+    A2 = pr.Crs(A0.nrows, A0.ncols, 1, rp2, A0.cols[keep].copy(), np.asarray(A0.vals)[keep].copy())
+    b = make_rhs(prob, 7)
+
+    def levels_of(A):
+        if precond != "gmg":
+            return None
+        return {l: (A if l == 3 else prob.matrix(l), prob.prolongation(l) if l else None, prob.restriction(l) if l else None)
+                for l in range(0, 4)}
+
+    def oracle_solve(A):
+        if precond == "gmg":
+            lv = oracle_levels(orc, prob, 0, 3)
+            lv[3] = (orc.matrix(A), lv[3][1], lv[3][2])
+            return oracle.OSolver(orc, desc, lv[3][0], lv).apply(b)
+        if precond in ("gs", "ilu"):   # the device sweeps in the greedy multicolour order of the given pattern
+            from helpers import greedy_color_perm, permute_crs
+            perm, _ = greedy_color_perm(A)
+            PA = permute_crs(A, perm, perm)
+            pb = np.empty_like(b); pb[perm] = b
+            odesc = dict(desc)
+            if precond == "ilu":
+                odesc["precond"] = {"type": "ilu"}
+            xo, ok, h = oracle.OSolver(orc, odesc, orc.matrix(PA)).apply(pb)
+            return xo[perm], ok, h
+        return oracle.OSolver(orc, desc, orc.matrix(A)).apply(b)
+
+    s = ug.Solver(desc, A0, levels_of(A0), flags=flags)
+    tol = 1e-8 if solver == "bicgstab" else HIST_TOL
+    for A in (A0, A1, A2, A0):
+        if A is not A0 or s._inited:
+            s.set_matrix(A)
+        xg, okg, hg = s.apply(b)
+        xo, oko, ho = oracle_solve(A)
+        assert okg == oko
+        assert abs(len(hg) - len(ho)) <= 1, (len(hg), len(ho))
+        assert rel_hist_err(hg, ho) < tol, (hg, ho)
+        assert np.linalg.norm(xg - xo) <= 1e-7 * np.linalg.norm(xo)

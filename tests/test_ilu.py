@@ -235,8 +235,6 @@ def test_golden_ilu_gmres_histories(kind, request):
 
 
 # ---- GPU ----------------------------------------------------------------------------------------------------
-pending = pytest.mark.skipif(os.environ.get("UG4B200_PENDING_GPU_TESTS") != "1",
-                             reason="first GPU run pending (set UG4B200_PENDING_GPU_TESTS=1)")
 
 
 def _best():
@@ -265,7 +263,6 @@ def test_gpu_ilu_multicolor_apply_is_bit_identical(kind, beta):
     assert np.array_equal(c, F.ilu_apply(dp)[perm])
 
 
-@pending
 @pytest.mark.gpu
 def test_gpu_block_ilu_multicolor_apply_and_solve():
     """3x3-block ILU(0) on elasticity: one application bit-identical to the reference in the multicolour ordering,
@@ -314,7 +311,6 @@ def test_gpu_ilu_level_scheduled_apply(ordering):
     assert np.linalg.norm(c - ref) <= 1e-13 * np.linalg.norm(ref)
 
 
-@pending
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(DESCS))
 def test_gpu_solvers_with_ilu_and_gmres_match_oracle(name):
@@ -332,7 +328,6 @@ def test_gpu_solvers_with_ilu_and_gmres_match_oracle(name):
     assert np.linalg.norm(x - xo) <= 1e-7 * np.linalg.norm(xo)
 
 
-@pending
 @pytest.mark.gpu
 def test_gpu_gmg_with_ilu_smoother_matches_oracle():
     """GMG V(2,2) with ILU(0) smoothing in the multicolour ordering + CG: the oracle runs on the colour-permuted
@@ -355,7 +350,6 @@ def test_gpu_gmg_with_ilu_smoother_matches_oracle():
     assert np.linalg.norm(x - xo[perms[3]]) <= 1e-9 * np.linalg.norm(xo)
 
 
-@pending
 @pytest.mark.gpu
 def test_gpu_edge_cases_ilu_gmres():
     """1x1 and diagonal systems, a matrix without diagonal (error like ugcore's), zero right-hand side, and the
@@ -384,7 +378,6 @@ def test_gpu_edge_cases_ilu_gmres():
     assert ok and len(h) == 1 and h[0] == 0.0 and not x.any()
 
 
-@pending
 @pytest.mark.gpu
 def test_gpu_golden_ilu_gmres_fixture():
     """GPU vs the committed histories of the reference's ILU / GMRES (no /root/reference needed on the GPU box)."""
@@ -410,7 +403,6 @@ def test_gpu_golden_ilu_gmres_fixture():
         assert abs(np.linalg.norm(x) - case["solution_norm"]) <= 1e-7 * case["solution_norm"], case["name"]
 
 
-@pending
 @pytest.mark.gpu
 @pytest.mark.parametrize("graph", [0, 2])
 def test_gpu_device_resident_bicgstab_equals_host_loop(graph):
@@ -433,7 +425,6 @@ def test_gpu_device_resident_bicgstab_equals_host_loop(graph):
         assert np.array_equal(h0, h1) and np.array_equal(x0, x1), name
 
 
-@pending
 @pytest.mark.gpu
 @pytest.mark.parametrize("graph", [0, 2])
 def test_gpu_device_resident_linear_solver_equals_host_loop(graph):
@@ -473,7 +464,6 @@ def test_oracle_bicgstab_periodic_restart(orc, orc_ref):
     assert len(hs[4]) != len(hs[0]) or not np.array_equal(hs[4], hs[0])
 
 
-@pending
 @pytest.mark.gpu
 @pytest.mark.parametrize("rs", [0, 3, 4])
 def test_gpu_bicgstab_periodic_restart_host_and_device_loop(rs):

@@ -265,7 +265,6 @@ def test_solve_from_dumped_files(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("UG4B200_PENDING_GPU_TESTS") != "1", reason="first GPU run pending (set UG4B200_PENDING_GPU_TESTS=1)")
 def test_gpu_cg_debug_writer_leaves_the_reference_file_set(tmp_path):
     """solver:set_debug(writer): CG_Residual_iterNNN.vec / CG_Solution_iterNNN.vec after every step (cg.h:124, 195,
     273-280) — readable by the ConnectionViewer reader, residual norms = the defect history, last solution = the result;

@@ -28,13 +28,6 @@ def test_partitioned_gmg_cg_matches_serial_oracle(world, flags, p2p, gather):
     _run(world, flags, p2p, gather, "poisson", 1e-10, 1e-9)
 
 
-# Written in a session that had no GPU minutes left: host logic is covered on the CPU
-# (tests/test_dist_cpu.py), the first GPU run is pending -> opt-in until it has been seen green once.
-pending = pytest.mark.skipif(os.environ.get("UG4B200_PENDING_GPU_TESTS") != "1",
-                             reason="first GPU run pending (set UG4B200_PENDING_GPU_TESTS=1)")
-
-
-@pending
 @pytest.mark.parametrize("world,flags,p2p,gather", [(2, 0, 1, -1), (2, 0, 0, 0), (4, 0, 1, 1), (8, 0, 1, -1)])
 def test_partitioned_bicgstab_gmg_gauss_seidel_matches_oracle(world, flags, p2p, gather):
     """BASELINE configs[3] partitioned: BiCGStab + GMG with ugcore's parallel Gauss-Seidel (multicolour inside
@@ -43,14 +36,12 @@ def test_partitioned_bicgstab_gmg_gauss_seidel_matches_oracle(world, flags, p2p,
     _run(world, flags, p2p, gather, "convdiff_gs", 1e-8, 1e-7)
 
 
-@pending
 @pytest.mark.parametrize("world,flags,p2p,gather", [(2, 0, 1, -1), (4, 0, 0, 0)])
 def test_partitioned_bicgstab_gmg_ilu_matches_oracle(world, flags, p2p, gather):
     """The same with ILU(0) smoothing in the multicolour ordering (parallel ILU of ilu.h:536-543, 640-652)."""
     _run(world, flags, p2p, gather, "convdiff_ilu", 1e-8, 1e-7)
 
 
-@pending
 @pytest.mark.parametrize("world,p2p,case,tol", [(2, 1, "cg_ilu", 1e-10), (4, 0, "cg_ilu", 1e-10), (2, 1, "bicgstab_gs", 1e-8),
                                                 (8, 1, "bicgstab_gs", 1e-7)])
 def test_partitioned_one_level_preconditioners_match_oracle(world, p2p, case, tol):
@@ -59,21 +50,18 @@ def test_partitioned_one_level_preconditioners_match_oracle(world, p2p, case, to
     _run(world, 0, p2p, -1, case, tol, 1e-7)
 
 
-@pending
 @pytest.mark.parametrize("world,flags,p2p,gather", [(2, 0, 1, -1), (8, 0, 1, -1), (2, 0, 0, 0)])
 def test_partitioned_elasticity_block3_matches_serial_oracle(world, flags, p2p, gather):
     """BASELINE configs[4] partitioned: 3x3-block GMG-CG, block interface exchange."""
     _run(world, flags, p2p, gather, "elasticity", 1e-10, 1e-9)
 
 
-@pending
 @pytest.mark.parametrize("world,case,tol", [(2, "poisson_sgs", 1e-10), (4, "elasticity_sgs", 1e-9)])
 def test_partitioned_symmetric_gauss_seidel_matches_oracle(world, case, tol):
     """CG + GMG with symmetric Gauss-Seidel smoothing (scalar and 3x3 blocks) in ugcore's parallel mode."""
     _run(world, 0, 1, -1, case, tol, 1e-8)
 
 
-@pending
 @pytest.mark.parametrize("world,cycle", [(2, "W"), (4, "F")])
 def test_partitioned_w_and_f_cycles_match_serial_oracle(world, cycle):
     """W- and F-cycles visit the coarse levels several times: everything below the top level stays partitioned down
@@ -81,10 +69,23 @@ def test_partitioned_w_and_f_cycles_match_serial_oracle(world, cycle):
     _run(world, 0, 1, -1, "poisson", 1e-10, 1e-9, extra=[cycle])
 
 
-def _run(world, flags, p2p, gather, case, hist_tol, sol_tol, extra=()):
+@pytest.mark.parametrize("world,p2p,case,tol", [(2, 1, "poisson", 1e-10), (2, 0, "poisson", 1e-10), (4, 1, "poisson", 1e-10),
+                                                (8, 1, "poisson", 1e-10), (2, 1, "elasticity", 1e-10), (8, 1, "elasticity", 1e-10),
+                                                (2, 1, "convdiff_gs", 1e-8), (4, 1, "poisson_sgs", 1e-10)])
+def test_partitioned_solves_with_random_rhs_match_serial_oracle(world, p2p, case, tol):
+    """Seeded random global right-hand side: values on the two sides of every partition plane are unrelated and O(1)
+    on the interfaces, so summation order, master / slave choice and the 4- and 8-way sharers all show up in the
+    history (parallel_vector_impl.h:269-379, parallelization_util.h:159-280)."""
+    _run(world, 0, p2p, -1, case, tol, 1e-7 if tol > 1e-9 else 1e-9, seed=20261017)
+
+
+def _run(world, flags, p2p, gather, case, hist_tol, sol_tol, extra=(), seed=None):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     env = dict(os.environ, UG4B200_P2P=str(min(p2p, 1)), UG4B200_FUSED_PUSH="1" if p2p == 2 else "0")
+    env.pop("UG4B200_TEST_RHS_SEED", None)
+    if seed is not None:
+        env["UG4B200_TEST_RHS_SEED"] = str(seed)
     env.pop("UG4B200_GATHER_LEVEL", None)
     if gather >= 0:
         env["UG4B200_GATHER_LEVEL"] = str(gather)
@@ -99,3 +100,5 @@ def _run(world, flags, p2p, gather, case, hist_tol, sol_tol, extra=()):
         assert abs(res["its"] - res["its_oracle"]) <= 1
         assert res["hist_err"] < hist_tol and res["sol_err"] < sol_tol, res
         assert res["p2p"] == bool(p2p), res
+        # the interfaces must carry real data (round 1's Poisson rhs was antisymmetric about every partition plane)
+        assert res["iface_rel"] > 1e-3, res

@@ -309,6 +309,30 @@ class Solver:
             _ptr(P.rowptr) if P else None, _ptr(P.cols) if P else None, _ptr(P.vals) if P else None,
             _ptr(R.rowptr) if R else None, _ptr(R.cols) if R else None, _ptr(R.vals) if R else None))
 
+    def set_matrix(self, A, levels: dict | None = None):
+        """A new operator for the same solver object — what ``solver:init(J, u)`` sees in every Newton or time step
+        (the matrix was re-assembled).  The next ``apply`` re-runs ``init``: preconditioner preprocess, uploads, and
+        the CUDA graphs of the Krylov loops are re-captured (they are tied to the generation of the device data)."""
+        if self.perm is not None:
+            raise ValueError("set_matrix: a solver created with order= keeps its permutation; create a new Solver")
+        if A.nrows * A.block != self.n:
+            raise ValueError("set_matrix: the number of unknowns must not change")
+        self._keep[0] = A
+        check_host(host.ug4b200_solver_set_matrix(self.h, A.nrows, A.ncols, _ptr(A.rowptr), _ptr(A.cols), _ptr(A.vals)))
+        if levels:
+            self._keep.append(levels)
+            for lev, (Al, Pl, Rl) in sorted(levels.items()):
+                skip = lev == self.desc.top_lev or Al is None
+                nrows = Al.nrows if Al is not None else Pl.nrows
+                check_host(host.ug4b200_solver_set_level(
+                    self.h, lev, nrows,
+                    None if skip else _ptr(Al.rowptr), None if skip else _ptr(Al.cols), None if skip else _ptr(Al.vals),
+                    Pl.ncols if Pl else 0,
+                    _ptr(Pl.rowptr) if Pl else None, _ptr(Pl.cols) if Pl else None, _ptr(Pl.vals) if Pl else None,
+                    _ptr(Rl.rowptr) if Rl else None, _ptr(Rl.cols) if Rl else None, _ptr(Rl.vals) if Rl else None))
+        self._inited = False
+        return self
+
     def init(self):
         check_host(host.ug4b200_solver_init(self.h))
         self._inited = True
