@@ -116,7 +116,13 @@ class Oracle:
         L.oracle_solver_steps.argtypes = [C.c_void_p]
         L.oracle_solver_history.argtypes = [C.c_void_p, _dp, C.c_int]
         L.oracle_precond_apply.argtypes = [C.c_void_p, _dp, _dp, C.c_int]
+        L.oracle_set_reduction_mode.argtypes = [C.c_int]
         assert L.oracle_backend_name().decode() == kind
+
+    def set_reduction_mode(self, mode: int):
+        """0: ugcore's sequential dot / norm (the reference, default); 1: pairwise tree over the same products.
+        Mode 1 only serves to measure the sensitivity of a residual history to the summation order."""
+        self.lib.oracle_set_reduction_mode(int(mode))
 
     def _chk(self, rc):
         if rc < 0:

@@ -95,6 +95,10 @@ typedef struct oracle_solver oracle_solver;
 
 oracle_solver* oracle_solver_create(const oracle_solver_desc* d);
 void oracle_solver_destroy(oracle_solver* s);
+/* 0 (default): the reference's sequential dot / norm; 1: pairwise-tree summation of the same products — NOT ugcore's
+ * arithmetic, a measurement aid: how far does the reference's own history move under another summation order? */
+void oracle_set_reduction_mode(int mode);
+int oracle_reduction_mode(void);
 /* GMG level operators; P, R may be NULL on the base level. Matrices stay owned by the caller. */
 int oracle_solver_set_level(oracle_solver* s, int lev, const oracle_mat* A, const oracle_mat* P, const oracle_mat* R);
 /* matrix the smoothers of GMG level lev are initialised with instead of the level operator (ugcore's

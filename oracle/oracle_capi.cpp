@@ -271,6 +271,8 @@ oracle_solver* oracle_solver_create(const oracle_solver_desc* d)
 	} catch (const std::exception& e) { g_err = e.what(); return nullptr; }
 }
 void oracle_solver_destroy(oracle_solver* s) { delete s; }
+void oracle_set_reduction_mode(int mode) { oracle::set_reduction_mode(mode); }
+int oracle_reduction_mode(void) { return oracle::reduction_mode(); }
 
 int oracle_solver_set_level(oracle_solver* s, int lev, const oracle_mat* A, const oracle_mat* P, const oracle_mat* R)
 {

@@ -8,6 +8,26 @@
 
 namespace oracle {
 
+// ---- reductions ------------------------------------------------------------------------
+// Mode 0 (default, THE reference): the backend's dot / norm = ugcore's strictly sequential left-to-right sums
+// (vector_impl.h:72-79, 323-329).  Mode 1: the same products summed by a pairwise tree.  Mode 1 is not ugcore's
+// arithmetic; it exists only so that a test can MEASURE how far the reference's own residual history moves when
+// nothing but the summation order of its reductions changes (tests/test_reduction_order.py) — the yardstick for
+// the tolerance a GPU reduction tree can be held to.
+static int g_reduction_mode = 0;
+void set_reduction_mode(int mode) { g_reduction_mode = mode; }
+int reduction_mode() { return g_reduction_mode; }
+namespace {
+double pairwise(const double* a, const double* b, int64_t n)
+{
+	if (n <= 8) { double s = 0.0; for (int64_t i = 0; i < n; ++i) s += a[i] * b[i]; return s; }
+	const int64_t h = n / 2;
+	return pairwise(a, b, h) + pairwise(a + h, b + h, n - h);
+}
+double rdot(Backend& bk, const Vec& a, const Vec& b) { return g_reduction_mode == 0 ? bk.dot(a, b) : pairwise(a.data(), b.data(), a.len()); }
+double rnorm(Backend& bk, const Vec& a) { return g_reduction_mode == 0 ? bk.norm(a) : std::sqrt(pairwise(a.data(), a.data(), a.len())); }
+} // namespace
+
 // ---- StdConvCheck (convergence_check_impl.h:85-169, 246-257) --------------------
 
 void StdConvCheck::start_defect(double d)
@@ -151,12 +171,12 @@ bool CG::apply_return_defect(Vec& x, Vec& b)
 	VecP q(bk.vector(r.n, r.block)), z(bk.vector(x.n, x.block)), p(bk.vector(x.n, x.block));
 	if (precond) { if (!precond->apply(*z, r)) return false; }
 	else bk.assign(*z, r);
-	conv.start_defect(bk.norm(r));
+	conv.start_defect(rnorm(bk, r));
 	bk.assign(*p, *z);
-	double rhoOld = bk.dot(*z, r), rho;
+	double rhoOld = rdot(bk, *z, r), rho;
 	while (!conv.iteration_ended()) {
 		bk.apply(*A, *q, *p);                  // q = A p
-		double lambda = bk.dot(*q, *p);
+		double lambda = rdot(bk, *q, *p);
 		if (lambda == 0.0) {
 			if (p->len()) return false;
 			lambda = 1.0;
@@ -164,11 +184,11 @@ bool CG::apply_return_defect(Vec& x, Vec& b)
 		const double alpha = rhoOld / lambda;
 		bk.scale_add2(x, 1.0, x, alpha, *p);
 		bk.scale_add2(r, 1.0, r, -alpha, *q);
-		conv.update_defect(bk.norm(r));
+		conv.update_defect(rnorm(bk, r));
 		if (conv.iteration_ended()) break;
 		if (precond) { if (!precond->apply(*z, r)) return false; }
 		else bk.assign(*z, r);
-		rho = bk.dot(*z, r);
+		rho = rdot(bk, *z, r);
 		const double beta = rho / rhoOld;
 		bk.scale_add2(*p, beta, *p, 1.0, *z);
 		rhoOld = rho;
@@ -184,7 +204,7 @@ bool BiCGStab::apply_return_defect(Vec& x, Vec& b)
 	Vec& r = b;
 	VecP r0(bk.vector(r.n, r.block)), p(bk.vector(r.n, r.block)), v(bk.vector(r.n, r.block)),
 	     t(bk.vector(r.n, r.block)), s(bk.vector(r.n, r.block)), q(bk.vector(x.n, x.block));
-	conv.start_defect(bk.norm(r));
+	conv.start_defect(rnorm(bk, r));
 	double rho = 1, alpha = 1, omega = 1, norm_r0 = 0.0;
 	bool bRestart = true;
 	while (!conv.iteration_ended()) {
@@ -198,7 +218,7 @@ bool BiCGStab::apply_return_defect(Vec& x, Vec& b)
 			bRestart = false;
 		}
 		const double rhoOld = rho;
-		if (!r.len()) rho = 1.0; else rho = bk.dot(*r0, r);
+		if (!r.len()) rho = 1.0; else rho = rdot(bk, *r0, r);
 		const double norm_r = conv.defect();
 		if (std::fabs(rho) / (norm_r * norm_r0) <= minOrtho) bRestart = true;
 		if (rhoOld == 0.0) return false;
@@ -207,24 +227,24 @@ bool BiCGStab::apply_return_defect(Vec& x, Vec& b)
 		if (precond) { if (!precond->apply(*q, *p)) return false; }
 		else bk.assign(*q, *p);
 		bk.apply(*A, *v, *q);
-		if (!v->len()) alpha = 1.0; else alpha = bk.dot(*v, *r0);
+		if (!v->len()) alpha = 1.0; else alpha = rdot(bk, *v, *r0);
 		if (alpha == 0.0) return false;
 		alpha = rho / alpha;
 		bk.scale_add2(x, 1.0, x, alpha, *q);
 		bk.scale_add2(*s, 1.0, r, -alpha, *v);
-		conv.update_defect(bk.norm(*s));
+		conv.update_defect(rnorm(bk, *s));
 		if (conv.iteration_ended()) { bk.assign(r, *s); break; }
 		if (precond) { if (!precond->apply(*q, *s)) return false; }
 		else bk.assign(*q, *s);
 		bk.apply(*A, *t, *q);
 		double tt;
-		if (!t->len()) tt = 1.0; else tt = bk.dot(*t, *t);
-		if (!s->len()) omega = 1.0; else omega = bk.dot(*s, *t);
+		if (!t->len()) tt = 1.0; else tt = rdot(bk, *t, *t);
+		if (!s->len()) omega = 1.0; else omega = rdot(bk, *s, *t);
 		if (tt == 0.0) return false;
 		omega = omega / tt;
 		bk.scale_add2(x, 1.0, x, omega, *q);
 		bk.scale_add2(r, 1.0, *s, -omega, *t);
-		conv.update_defect(bk.norm(r));
+		conv.update_defect(rnorm(bk, r));
 		if (omega == 0.0) return false;
 	}
 	return conv.post();
@@ -237,12 +257,12 @@ bool LinearSolver::apply_return_defect(Vec& x, Vec& b)
 	Vec& d = b;
 	bk.matmul_minus(*A, d, x);
 	VecP c(bk.vector(x.n, x.block));
-	conv.start_defect(bk.norm(d));
+	conv.start_defect(rnorm(bk, d));
 	while (!conv.iteration_ended()) {
 		if (precond) { if (!precond->apply_update_defect(*c, d)) return false; }
 		else { bk.assign(*c, d); bk.matmul_minus(*A, d, *c); }
 		bk.add(x, *c);
-		conv.update_defect(bk.norm(d));
+		conv.update_defect(rnorm(bk, d));
 	}
 	return conv.post();
 }
@@ -254,7 +274,7 @@ bool GMRES::apply_return_defect(Vec& x, Vec& b)
 	VecP spR(bk.vector(b.n, b.block));
 	bk.assign(*spR, b);                                   // spR = b.clone()            :113
 	bk.matmul_minus(*A, *spR, x);                         // b - A x                    :116
-	conv.start_defect(bk.norm(*spR));                     //                            :122
+	conv.start_defect(rnorm(bk, *spR));                     //                            :122
 	const size_t m = restart;
 	std::vector<VecP> v(m + 1);
 	std::vector<std::vector<double> > h(m + 1, std::vector<double>(m + 1, 0.0));
@@ -263,7 +283,7 @@ bool GMRES::apply_return_defect(Vec& x, Vec& b)
 		if (!v[0]) v[0].reset(bk.vector(x.n, x.block));
 		if (precond) { if (!precond->apply(*v[0], *spR)) return false; }        // :141-146
 		else std::swap(v[0], spR);                                                // :148-150
-		gamma[0] = bk.norm(*v[0]);                                                // :162
+		gamma[0] = rnorm(bk, *v[0]);                                                // :162
 		bk.scale(*v[0], 1. / gamma[0]);                                           // :165
 		size_t numIter = 0;
 		for (size_t j = 0; j < m; ++j) {
@@ -273,10 +293,10 @@ bool GMRES::apply_return_defect(Vec& x, Vec& b)
 			if (precond) { if (!precond->apply(*v[j + 1], *spR)) return false; }  // :185-190
 			else std::swap(v[j + 1], spR);                                        // :192-194
 			for (size_t i = 0; i <= j; ++i) {
-				h[i][j] = bk.dot(*v[j + 1], *v[i]);                               // :211
+				h[i][j] = rdot(bk, *v[j + 1], *v[i]);                               // :211
 				bk.scale_add2(*v[j + 1], 1.0, *v[j + 1], (-1) * h[i][j], *v[i]);  // VecScaleAppend :214, :341-345
 			}
-			h[j + 1][j] = bk.norm(*v[j + 1]);                                     // :218
+			h[j + 1][j] = rnorm(bk, *v[j + 1]);                                     // :218
 			for (size_t i = 0; i < j; ++i) {                                      // :221-228
 				const double hij = h[i][j], hi1j = h[i + 1][j];
 				h[i][j] = c[i + 1] * hij + s[i + 1] * hi1j;
@@ -299,7 +319,7 @@ bool GMRES::apply_return_defect(Vec& x, Vec& b)
 		}
 		bk.assign(*spR, b);                                                       // :272-273
 		bk.matmul_minus(*A, *spR, x);
-		if (precond) conv.update_defect(bk.norm(*spR));                           // :275-276
+		if (precond) conv.update_defect(rnorm(bk, *spR));                           // :275-276
 	}
 	return conv.post();
 }

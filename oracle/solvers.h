@@ -33,6 +33,11 @@
 
 namespace oracle {
 
+/// 0: the reference's sequential reductions (default); 1: pairwise tree (measurement aid, see solvers.cpp)
+void set_reduction_mode(int mode);
+int reduction_mode();
+
+
 typedef std::unique_ptr<Vec> VecP;
 
 struct StdConvCheck {

@@ -1,6 +1,8 @@
 """Shared helpers of the test-suite (oracle-side hierarchy wiring, device buffers)."""
 import ctypes as C
 
+import os
+
 import numpy as np
 
 
@@ -27,17 +29,65 @@ def gmg_desc(top, solver="cg", smoother=None, nu=(2, 2), cycle="V", base=0, base
             "convCheck": {"iterations": its, "absolute": absolute, "reduction": reduction}}
 
 
-def rel_hist_err(h_gpu, h_ref):
-    """max_k |h_gpu[k] - h_ref[k]| / |h_ref[k]| over the common prefix.
+def rel_hist_err(h_gpu, h_ref, allowance=0.0):
+    """max_k |h_gpu[k] - h_ref[k]| / |h_ref[k]| over the common prefix — north_star's "residual history within
+    1e-10 relative per iteration", strict: no absolute allowance unless the caller asks for one.
 
-    An absolute allowance of 1e-14 * (start defect) is subtracted first: a defect norm cannot
-    be known more accurately than fp64 round-off of the start defect (eps * ||b||), whatever
-    the summation order of the dot products — on the CPU as well."""
+    (Round 1 subtracted 1e-14 * start defect first; at the end of a history that has dropped by 1e-10 that is a
+    relative 1e-4 — it hid everything but the first steps.  What a history can be held to is measured instead:
+    tests/test_reduction_order.py records how far the REFERENCE's own history moves when only the summation order
+    of its dot products changes.)  UG4B200_RECORD_HIST_ERR=<file>: every evaluation is appended to that file."""
     n = min(len(h_gpu), len(h_ref))
     if not n:
         return 0.0
-    diff = np.maximum(np.abs(h_gpu[:n] - h_ref[:n]) - 1e-14 * abs(h_ref[0]), 0.0)
-    return float(np.max(diff / np.abs(h_ref[:n])))
+    h_gpu, h_ref = np.asarray(h_gpu[:n], float), np.asarray(h_ref[:n], float)
+    diff = np.maximum(np.abs(h_gpu - h_ref) - allowance * abs(h_ref[0]), 0.0)
+    err = float(np.max(diff / np.abs(h_ref)))
+    rec = os.environ.get("UG4B200_RECORD_HIST_ERR")
+    if rec:
+        import json
+        with open(rec, "a") as f:
+            f.write(json.dumps({"test": os.environ.get("PYTEST_CURRENT_TEST", ""), "steps": n - 1, "err": err,
+                                "strict": float(np.max(np.abs(h_gpu - h_ref) / np.abs(h_ref))),
+                                "reduction": float(h_ref[-1] / h_ref[0])}) + "\n")
+    return err
+
+
+def osolver_sensitivity(orc, osol, b):
+    """Per-step relative movement of the history of the oracle solver `osol` when its dot products / norms are summed
+    by a pairwise tree instead of ugcore's sequential loop (everything else bit-identical); plus both histories."""
+    _, _, h0 = osol.apply(b)
+    orc.set_reduction_mode(1)
+    try:
+        _, _, h1 = osol.apply(b)
+    finally:
+        orc.set_reduction_mode(0)
+    k = min(len(h0), len(h1))
+    with np.errstate(all="ignore"):
+        return np.abs(h0[:k] - h1[:k]) / np.abs(h0[:k]), h0, h1
+
+
+def reduction_order_sensitivity(orc, prob, desc, b):
+    """The same for a solver descriptor on a generated problem (tests/test_reduction_order.py)."""
+    import oracle
+    pc = desc.get("precond")
+    if isinstance(pc, dict) and pc.get("type") == "gmg":
+        levels = oracle_levels(orc, prob, pc["baseLevel"], pc["topLevel"])
+        osol = oracle.OSolver(orc, desc, levels[pc["topLevel"]][0], levels)
+    else:
+        osol = oracle.OSolver(orc, desc, orc.matrix(prob.matrix()))
+    return osolver_sensitivity(orc, osol, b)
+
+
+def sens_tol(orc, osol, b, base=1e-10, factor=10.0):
+    """Tolerance for a GPU-vs-reference history comparison: north_star's 1e-10 per iteration, or — where the
+    REFERENCE's own history moves by more than a tenth of that when only the summation order of its reductions
+    changes (BiCGStab, GMRES, long unpreconditioned runs) — `factor` times that measured movement.  The GPU's
+    reduction tree is one more summation order; it cannot be expected to land closer to the sequential sum than
+    another valid order does."""
+    sens, _, _ = osolver_sensitivity(orc, osol, b)
+    sens = sens[np.isfinite(sens)]
+    return max(base, factor * float(sens.max())) if sens.size else base
 
 
 class Dev:

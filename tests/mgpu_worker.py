@@ -86,19 +86,30 @@ def main():
 
     if case in ("cg_ilu", "bicgstab_gs"):
         solve, gprob = partitioned_onelevel_oracle(orc, desc, refs, part, problem=problem, colored=(case == "bicgstab_gs"), **kw)
-        xo, oko, ho = solve(rhs_of(gprob))
+        osolve = lambda: solve(rhs_of(gprob))
     elif case in ("convdiff_gs", "convdiff_ilu", "poisson_sgs", "elasticity_sgs"):
         solve, gprob = partitioned_gs_oracle(orc, desc, refs, part, s.desc.gather_lev, problem=problem, **kw)
-        xo, oko, ho = solve(rhs_of(gprob))
+        osolve = lambda: solve(rhs_of(gprob))
     else:
         gprob = ugdist.global_problem(refs, part, problem=problem, **kw)
         lv = oracle_levels(orc, gprob)
-        xo, oko, ho = oracle.OSolver(orc, desc, lv[refs][0], lv).apply(rhs_of(gprob))
+        osol = oracle.OSolver(orc, desc, lv[refs][0], lv)
+        osolve = lambda: osol.apply(rhs_of(gprob))
+    xo, oko, ho = osolve()
+    # how far the reference's own history moves when only the summation order of its reductions changes
+    # (tests/test_reduction_order.py): the partitioned sum IS another summation order
+    orc.set_reduction_mode(1)
+    try:
+        _, _, h1 = osolve()
+    finally:
+        orc.set_reduction_mode(0)
+    k = min(len(ho), len(h1))
+    sens = float(np.max(np.abs(ho[:k] - h1[:k]) / np.abs(ho[:k])))
     from ugcore_b200 import capi
     res = {"rank": rank, "p2p": bool(capi.dev.ug4b200_p2p_enabled(S.host_ctx())), "ok": bool(ok), "oracle_ok": bool(oko), "its": len(h) - 1, "its_oracle": len(ho) - 1,
            "hist_err": rel_hist_err(h, ho), "sol_err": float(np.linalg.norm(x - xo[g]) / np.linalg.norm(xo[g])),
            "iface_rel": float(np.max(np.abs(x[np.repeat(ugdist.multiplicity(prob, refs) > 1, block)])) / max(np.max(np.abs(x)), 1e-300)),
-           "final_reduction": float(h[-1] / h[0])}
+           "final_reduction": float(h[-1] / h[0]), "ref_reorder_sensitivity": sens}
     out = [None] * world
     dist.all_gather_object(out, res)
     if rank == 0:

@@ -1,5 +1,6 @@
-"""GPU: the grid of solver x preconditioner x cycle combinations against the oracle (history within 1e-8 relative per
-step, same step count, same convergence flag).  Gauss-Seidel-type preconditioners are left to their own tests: the
+"""GPU: the grid of solver x preconditioner x cycle combinations against the oracle (history within 1e-10 relative per
+step — or 10 x what the reference's own history moves under a reordered sum, whichever is larger: helpers.sens_tol —,
+same step count, same convergence flag).  Gauss-Seidel-type preconditioners are left to their own tests: the
 device sweeps in a multicolour ordering, so the oracle has to be run on the colour-permuted problem
 (tests/test_gpu_solver.py, tests/test_ilu.py)."""
 import os
@@ -8,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle
-from helpers import gmg_desc, oracle_levels, rel_hist_err
+from helpers import gmg_desc, oracle_levels, rel_hist_err, sens_tol
 from ugcore_b200 import problems as pr
 
 pytestmark = pytest.mark.gpu
@@ -31,13 +32,15 @@ def test_one_level_preconditioners(problem, solver):
     for pc in (None, {"type": "jac", "damping": 0.7}, {"type": "ilu"}, {"type": "ilu", "beta": 0.5}):
         desc = {"type": solver, "restart": 8, "precond": pc, "convCheck": CC}
         x, ok, h = ug.Solver(desc, prob.matrix()).apply(prob.rhs())
-        xo, oko, ho = oracle.OSolver(orc, desc, orc.matrix(prob.matrix())).apply(np.array(prob.rhs()))
+        osol = oracle.OSolver(orc, desc, orc.matrix(prob.matrix()))
+        xo, oko, ho = osol.apply(np.array(prob.rhs()))
         if not np.isfinite(ho).all():        # CG on the non-symmetric operator may break down: both must say so
             assert not ok and not oko, (solver, pc)
             continue
         assert ok == oko and abs(len(h) - len(ho)) <= 1, (solver, pc)
         if oko:
-            assert rel_hist_err(h, ho) < 1e-6, (solver, pc, rel_hist_err(h, ho))
+            tol = sens_tol(orc, osol, np.array(prob.rhs()))
+            assert rel_hist_err(h, ho) < tol, (solver, pc, rel_hist_err(h, ho), tol)
 
 
 @pytest.mark.parametrize("problem", ["poisson", "convdiff"])
@@ -51,9 +54,11 @@ def test_gmg_cycles_and_smoothers(problem, solver):
             desc = gmg_desc(3, solver=solver, smoother=sm, cycle=cycle, reduction=1e-8)
             desc["restart"] = 4
             x, ok, h = ug.Solver.from_problem(desc, prob).apply(prob.rhs())
-            xo, oko, ho = oracle.OSolver(orc, desc, lv[3][0], lv).apply(np.array(prob.rhs()))
+            osol = oracle.OSolver(orc, desc, lv[3][0], lv)
+            xo, oko, ho = osol.apply(np.array(prob.rhs()))
             # (CG is not a solver for the non-symmetric operator: it need not converge, but must fail the same way)
             assert ok == oko and abs(len(h) - len(ho)) <= 1, (solver, sm, cycle)
             assert oko or (solver == "cg" and problem == "convdiff"), (solver, sm, cycle)
             if oko:
-                assert rel_hist_err(h, ho) < 1e-8, (solver, sm, cycle, rel_hist_err(h, ho))
+                tol = sens_tol(orc, osol, np.array(prob.rhs()))
+                assert rel_hist_err(h, ho) < tol, (solver, sm, cycle, rel_hist_err(h, ho), tol)

@@ -10,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import gmg_desc, make_rhs, oracle_levels, rel_hist_err
+from helpers import gmg_desc, make_rhs, oracle_levels, rel_hist_err, sens_tol
 
 pytestmark = pytest.mark.gpu
 
@@ -189,7 +189,8 @@ def test_convdiff_bicgstab_gmg_multicolor_gs():
     xo, oko, ho = osol.apply(bperm)
     assert oko
     assert abs(len(hg) - len(ho)) <= 1
-    assert rel_hist_err(hg, ho) < 1e-8  # BiCGStab amplifies reduction-order noise; see DESIGN.md
+    # north_star's 1e-10 unless the reference's own history moves more under a reordered sum (measured, helpers.sens_tol)
+    assert rel_hist_err(hg, ho) < sens_tol(orc, osol, bperm)
     xo_orig = xo[perms[3]]
     assert np.linalg.norm(xg - xo_orig) <= 1e-7 * np.linalg.norm(xo_orig)
 
@@ -326,7 +327,6 @@ def test_reinit_with_a_changed_matrix_recaptures_the_graph(solver, precond):
         return oracle.OSolver(orc, desc, orc.matrix(A)).apply(b)
 
     s = ug.Solver(desc, A0, levels_of(A0), flags=flags)
-    tol = 1e-8 if solver == "bicgstab" else HIST_TOL
     for A in (A0, A1, A2, A0):
         if A is not A0 or s._inited:
             s.set_matrix(A)
@@ -334,5 +334,5 @@ def test_reinit_with_a_changed_matrix_recaptures_the_graph(solver, precond):
         xo, oko, ho = oracle_solve(A)
         assert okg == oko
         assert abs(len(hg) - len(ho)) <= 1, (len(hg), len(ho))
-        assert rel_hist_err(hg, ho) < tol, (hg, ho)
+        assert rel_hist_err(hg, ho) < 1e-8, (hg, ho)    # a stale graph gives O(1) errors; exact parity is other tests' job
         assert np.linalg.norm(xg - xo) <= 1e-7 * np.linalg.norm(xo)
