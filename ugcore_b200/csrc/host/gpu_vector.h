@@ -269,12 +269,7 @@ class GPUVector {
 	}
 
 	/// one device double per process for reductions that must pass through an all-reduce
-	static double* scalar_slot()
-	{
-		static double* s = nullptr;
-		if (!s) s = (double*)GPUManager::alloc_bytes(8 * sizeof(double));
-		return s;
-	}
+	static double* scalar_slot() { return GPUManager::scalar_slot(); }
 
   protected:
 	static void add_block(double& a, const double& b) { a += b; }

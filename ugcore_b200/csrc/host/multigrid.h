@@ -174,7 +174,7 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 	virtual bool init(SmartPtr<ILinearOperator<vector_type> > J, const vector_type&) { return init(J); }
 	virtual bool init(SmartPtr<ILinearOperator<vector_type> > L)
 	{
-		m_spSurfaceMat = std::dynamic_pointer_cast<matrix_operator_type>(L);
+		m_spSurfaceMat = sp_cast_dynamic<matrix_operator_type>(L);
 		if (!m_spSurfaceMat) UG_THROW("GMG:init: Can not cast Operator to Matrix.");
 		if (m_baseLev > m_topLev) UG_THROW("GMG::init: Base Level greater than Surface level.");
 		if (!m_spBaseSolver) UG_THROW("GMG::init: Base Solver not set.");
@@ -348,8 +348,9 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 	}
 	bool base_solver_overwrites() const
 	{
-		return dynamic_cast<LU<TAlgebra>*>(m_spBaseSolver.get()) != nullptr || dynamic_cast<CoarseCG<TAlgebra>*>(m_spBaseSolver.get()) != nullptr ||
-		       dynamic_cast<CycleAsBaseSolver<TAlgebra>*>(m_spBaseSolver.get()) != nullptr;
+		const ILinearOperatorInverse<vector_type>* bs = m_spBaseSolver.get();
+		return dynamic_cast<const LU<TAlgebra>*>(bs) != nullptr || dynamic_cast<const CoarseCG<TAlgebra>*>(bs) != nullptr ||
+		       dynamic_cast<const CycleAsBaseSolver<TAlgebra>*>(bs) != nullptr;
 	}
 	void make_consistent(vector_type& v)
 	{

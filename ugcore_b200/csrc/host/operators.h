@@ -9,12 +9,28 @@
 //                              ugbase/lib_algebra/operator/interface/preconditioned_linear_operator_inverse.h:59-237
 //   IConvergenceCheck/StdConvCheck  ugbase/lib_algebra/operator/convergence_check.h, _impl.h:85-169
 //   IDamping/ConstantDamping   ugbase/lib_algebra/operator/damping.h:100-127
+//
+// Inside a ugcore build (UG4B200_WITH_UGCORE) the four interface headers that compile without boost are the REAL
+// ones — ILinearOperator, MatrixOperator, IDamping / ConstantDamping, ILinearIterator, IPreconditioner,
+// IVectorDebugWriter — and only the three classes whose ugcore headers pull boost::mpl through
+// lib_disc/domain_traits.h (convergence_check.h, linear_operator_inverse.h,
+// preconditioned_linear_operator_inverse.h) keep their restatement below.  tests/boundary/ builds that
+// configuration against /root/reference.
 #pragma once
 #include "gpu_sparsematrix.h"
 #include <limits>
 
+#ifdef UG4B200_WITH_UGCORE
+#include "lib_algebra/operator/interface/linear_operator.h"
+#include "lib_algebra/operator/interface/matrix_operator.h"
+#include "lib_algebra/operator/interface/linear_iterator.h"
+#include "lib_algebra/operator/interface/preconditioner.h"
+#include "lib_algebra/operator/debug_writer.h"
+#endif
+
 namespace ug {
 
+#ifndef UG4B200_WITH_UGCORE
 template <typename X, typename Y = X>
 class ILinearOperator {
   public:
@@ -91,13 +107,13 @@ class IPreconditioner : public ILinearIterator<typename TAlgebra::vector_type> {
 
 	virtual bool init(SmartPtr<ILinearOperator<vector_type> > J, const vector_type&)
 	{
-		SmartPtr<matrix_operator_type> pOp = std::dynamic_pointer_cast<matrix_operator_type>(J);
+		SmartPtr<matrix_operator_type> pOp = sp_cast_dynamic<matrix_operator_type>(J);
 		if (!pOp) UG_THROW(name() << "::init': Passed Operator is not based on matrix. This Preconditioner can only handle matrix-based operators.");
 		return init(pOp);
 	}
 	virtual bool init(SmartPtr<ILinearOperator<vector_type> > L)
 	{
-		SmartPtr<matrix_operator_type> pOp = std::dynamic_pointer_cast<matrix_operator_type>(L);
+		SmartPtr<matrix_operator_type> pOp = sp_cast_dynamic<matrix_operator_type>(L);
 		if (!pOp) UG_THROW(name() << "::init': Passed Operator is not based on matrix. This Preconditioner can only handle matrix-based operators.");
 		return init(pOp);
 	}
@@ -105,7 +121,6 @@ class IPreconditioner : public ILinearIterator<typename TAlgebra::vector_type> {
 	{
 		m_spApproxOperator = Op; m_spDefectOperator = Op;
 		if (!m_spApproxOperator) UG_THROW(name() << "::init': Passed Operator is invalid.");
-		GPUManager::bump_generation();   // preprocess rebuilds the device buffers a captured graph points at
 		if (!preprocess(m_spApproxOperator)) return false;
 		m_bInit = true;
 		return true;
@@ -142,6 +157,8 @@ class IPreconditioner : public ILinearIterator<typename TAlgebra::vector_type> {
 	SmartPtr<matrix_operator_type> m_spApproxOperator;
 	bool m_bInit;
 };
+
+#endif // !UG4B200_WITH_UGCORE
 
 // ---- convergence check ----
 template <typename TVector>
@@ -242,12 +259,14 @@ class StdConvCheck : public IConvergenceCheck<TVector> {
 
 /// ugbase/lib_algebra/operator/debug_writer.h: IVectorDebugWriter — receives vectors by name while a solver runs
 /// (CG_Residual_iterNNN.vec …); concrete writer: ConnectionViewerVectorWriter (matrix_io.h)
+#ifndef UG4B200_WITH_UGCORE
 template <typename TVector>
 class IVectorDebugWriter {
   public:
 	virtual ~IVectorDebugWriter() {}
 	virtual void write_vector(const TVector& vec, const char* name) = 0;
 };
+#endif
 
 template <typename X, typename Y = X>
 class ILinearOperatorInverse {

@@ -66,6 +66,7 @@ class Jacobi : public IPreconditioner<TAlgebra> {
 		matrix_type& mat = *pOp;
 		if (mat.num_rows() != mat.num_cols()) return false;
 		ug4b200_ctx* ctx = GPUManager::ctx();
+		GPUManager::bump_generation();   // the device buffers a captured solver graph points at are rebuilt
 		free_diag();
 		m_n = mat.num_rows();
 		m_diagInv = GPUManager::alloc(m_n * B * B);
@@ -174,7 +175,7 @@ class GaussSeidelBase : public IPreconditioner<TAlgebra> {
 			for (int64_t p = rp[r]; p < rp[r + 1] && !haveDiag; ++p) haveDiag = ((size_t)ci[p] == r);
 			if (!haveDiag) UG_THROW(this->name() << ": row " << r << " has no diagonal connection");
 		}
-		if (m_userPerm) THROW_IF_NOT_EQUAL(m_perm.size(), n);
+		if (m_userPerm) { THROW_IF_NOT_EQUAL(m_perm.size(), n); }
 		else {
 			// greedy colouring in row order, colours sorted, stable inside a colour; recomputed on every
 			// preprocess (the pattern may have changed at the same n)
@@ -208,6 +209,7 @@ class GaussSeidelBase : public IPreconditioner<TAlgebra> {
 		if (ug4b200_color_check((int64_t)n, prp.data(), pci.data(), (int)m_colorPtr.size() - 1, m_colorPtr.data()) != 0)
 			UG_THROW(this->name() << ": the given ordering is not a valid multicolour ordering of the matrix pattern");
 		free_dev();
+		GPUManager::bump_generation();   // the device buffers a captured solver graph points at are rebuilt
 		ug4b200_ctx* ctx = GPUManager::ctx();
 		UG_GPU_CHECK(ug4b200_matrix_upload_crs(ctx, B, (int64_t)n, (int64_t)n, prp.data(), pci.data(), pva.data(), 0, &m_PA));
 		ug4b200_matrix_info info; ug4b200_matrix_get_info(m_PA, &info);
@@ -437,6 +439,7 @@ class ILU : public IPreconditioner<TAlgebra> {
 		}
 		// ---- upload ----
 		free_dev();
+		GPUManager::bump_generation();   // the device buffers a captured solver graph points at are rebuilt
 		ug4b200_ctx* ctx = GPUManager::ctx();
 		UG_GPU_CHECK(ug4b200_matrix_upload_crs(ctx, B, n, n, lrp.data(), lci.data(), lva.data(), UG4B200_MAT_DEFAULT, &m_L));
 		UG_GPU_CHECK(ug4b200_matrix_upload_crs(ctx, B, n, n, urp.data(), uci.data(), uva.data(), UG4B200_MAT_DEFAULT, &m_U));

@@ -720,7 +720,7 @@ class LU : public ILinearOperatorInverse<typename TAlgebra::vector_type> {
 	virtual bool supports_parallel() const { return false; }
 	virtual bool init(SmartPtr<ILinearOperator<vector_type> > L)
 	{
-		m_spOperator = std::dynamic_pointer_cast<matrix_operator_type>(L);
+		m_spOperator = sp_cast_dynamic<matrix_operator_type>(L);
 		if (!m_spOperator) UG_THROW("LU::init: Passed operator is not a matrix operator.");
 		return init_lu(m_spOperator->get_matrix());
 	}
@@ -797,7 +797,7 @@ class CoarseCG : public ILinearOperatorInverse<typename TAlgebra::vector_type> {
 	virtual bool supports_parallel() const { return false; }
 	virtual bool init(SmartPtr<ILinearOperator<vector_type> > L)
 	{
-		m_spOperator = std::dynamic_pointer_cast<matrix_operator_type>(L);
+		m_spOperator = sp_cast_dynamic<matrix_operator_type>(L);
 		if (!m_spOperator) UG_THROW("CoarseCG::init: Passed operator is not a matrix operator.");
 		if (m_work) GPUManager::release(m_work, m_n * 4);
 		GPUManager::bump_generation();

@@ -6,7 +6,11 @@
 // this directory read like their CPU counterparts and can be moved into
 // ugbase/lib_algebra/gpu_algebra/ unchanged.
 #pragma once
+#ifdef UG4B200_WITH_UGCORE
+#include "ug4b200.h"                       // on the include path of the ugcore build (integration/0005-cuda_cmake.patch)
+#else
 #include "../../../include/ug4b200.h"
+#endif
 #include <cstddef>
 #include <cstdlib>
 #include <map>
@@ -16,6 +20,29 @@
 #include <string>
 #include <vector>
 
+#ifdef UG4B200_WITH_UGCORE
+// ---- inside a ugcore build (-I<ug4>/ugcore/ugbase): the real infrastructure, no stand-ins ----
+//   UG_THROW / UG_COND_THROW / THROW_IF_NOT_EQUAL   ugbase/common/error.h:57-85, 61, 181
+//   SmartPtr / ConstSmartPtr / make_sp(T*)          ugbase/common/util/smart_pointer.h:109-260, 839-850
+//   DenseMatrix / DenseVector / FixedArray1/2       ugbase/lib_algebra/small_algebra/small_algebra.h
+//   AlgebraType (has GPU = 1)                       ugbase/lib_algebra/algebra_type.h:50-60
+//   ParallelStorageType                             ugbase/lib_algebra/parallelization/parallel_storage_type.h:65-71
+// tests/boundary/ compiles this configuration against /root/reference (tests/test_boundary.py).
+#include "common/common.h"
+#include "common/util/smart_pointer.h"
+#include "lib_algebra/small_algebra/small_algebra.h"
+#include "lib_algebra/algebra_type.h"
+#include "lib_algebra/parallelization/parallel_storage_type.h"
+
+// ugcore's SmartPtr and make_sp(T*) live in the GLOBAL namespace (smart_pointer.h:109, 839-850); the helpers go next to
+// them — a ug::make_sp would hide ugcore's own inside namespace ug (linear_iterator.h:169 calls make_sp(new ...))
+/// make_sp<T>(ctor args...): this overload does the `new`
+template <class T, class... Args> SmartPtr<T> make_sp(Args&&... a) { return SmartPtr<T>(new T(std::forward<Args>(a)...)); }
+/// SmartPtr::cast_dynamic under a name that also exists for the stand-alone build's std::shared_ptr
+template <class TDest, class T> SmartPtr<TDest> sp_cast_dynamic(const SmartPtr<T>& p) { return p.template cast_dynamic<TDest>(); }
+
+#else
+// ---- stand-alone build: minimal stand-ins with ugcore's names and meaning ----
 namespace ug {
 
 typedef double number;
@@ -34,6 +61,7 @@ class UGError : public std::runtime_error {
 template <class T> using SmartPtr = std::shared_ptr<T>;
 template <class T> using ConstSmartPtr = std::shared_ptr<const T>;
 template <class T, class... Args> SmartPtr<T> make_sp(Args&&... a) { return std::make_shared<T>(std::forward<Args>(a)...); }
+template <class TDest, class T> SmartPtr<TDest> sp_cast_dynamic(const SmartPtr<T>& p) { return std::dynamic_pointer_cast<TDest>(p); }
 
 // ---- small algebra (ugbase/lib_algebra/small_algebra): column-major fixed blocks ----
 template <class T, size_t N> struct FixedArray1 {
@@ -77,6 +105,11 @@ struct AlgebraType {
 // ---- parallel storage types (lib_algebra/parallelization/parallel_storage_type.h:65-71) ----
 enum ParallelStorageType { PST_UNDEFINED = 0, PST_CONSISTENT = 1, PST_ADDITIVE = 2, PST_UNIQUE = 4 };
 
+} // namespace ug
+#endif // UG4B200_WITH_UGCORE
+
+namespace ug {
+
 /// Turns a C-ABI error code into a UGError (what CUDA_CHECK_STATUS did, cuda_manager.h:61-77)
 #define UG_GPU_CHECK(call)                                                                  \
 	do {                                                                                    \
@@ -107,7 +140,10 @@ class GPUManager {
 	{
 		GPUManager& m = inst();
 		m.release_pool();
+		if (m.m_ctx && m.m_scalarSlot) ug4b200_free(m.m_ctx, m.m_scalarSlot);
+		m.m_scalarSlot = nullptr;
 		if (m.m_ctx) { ug4b200_ctx_destroy(m.m_ctx); m.m_ctx = nullptr; }
+		bump_generation();
 	}
 	/// pooled device allocation: solver work vectors are cloned per apply (cg.h:120-122)
 	static double* alloc(size_t n)
@@ -120,7 +156,16 @@ class GPUManager {
 		if (rc != 0) UG_THROW("GPUManager: device allocation of " << n * sizeof(double) << " bytes failed: " << ug4b200_last_error(ctx()));
 		return (double*)p;
 	}
-	static void release(double* p, size_t n) { if (p) inst().m_pool[n].push_back(p); }
+	/// back into the pool — unless the context is gone (a vector that outlives finalize()): its memory went with the context
+	static void release(double* p, size_t n) { if (p && inst().m_ctx) inst().m_pool[n].push_back(p); }
+	/// a few device doubles per process for reductions that pass through an all-reduce; owned here so that
+	/// finalize() / a new context never leave a dangling pointer behind
+	static double* scalar_slot()
+	{
+		GPUManager& m = inst();
+		if (!m.m_scalarSlot) m.m_scalarSlot = (double*)alloc_bytes(8 * sizeof(double));
+		return m.m_scalarSlot;
+	}
 	static void* alloc_bytes(size_t bytes)
 	{
 		void* p = nullptr;
@@ -149,6 +194,7 @@ class GPUManager {
 	ug4b200_ctx* m_ctx = nullptr;
 	int m_rank = 0, m_nranks = 1;
 	unsigned long long m_generation = 1;
+	double* m_scalarSlot = nullptr;
 	std::map<size_t, std::vector<double*> > m_pool;
 };
 
