@@ -12,6 +12,11 @@ Prints ONE JSON line (see the contract in the task description / DESIGN.md §Mea
 GMG with multicolour Gauss-Seidel on upwind convection-diffusion; CG + GMG block-Jacobi on 3x3-block
 linear elasticity), same JSON contract, own metric names; the default stays configs[1] / configs[2].
 
+`--scaling strong` fixes the GLOBAL grid instead of the per-GPU box: 2x2x2 base cells, numRefs = 7 -> 257^3 =
+16 974 593 DoF (BASELINE configs[2]: the unit cube with numRefs = 8 minus its one-cell base level) on 1, 2, 4 or 8
+GPUs; parallel efficiency = T1 / (P TP).  `--order hier` numbers the DoFs the way ugcore's global refinement does
+(coarse vertices first), `--reorder cmk|rcmk` applies (reverse) Cuthill-McKee before upload.
+
 `--impl reference` times ugcore's own CPU kernels (oracle/_ref: SparseMatrix/Vector/
 smoother templates compiled from the reference) driving the restated solver loop on ALL
 host cores: the reference has no threading on this path and no MPI is installed, so every
@@ -123,7 +128,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def _cpu_replica(refs, steps, warmup, barrier, q, workload="poisson", base_mult=1):
+def _cpu_replica(refs, steps, warmup, barrier, q, workload="poisson", base_mult=1, order=0):
     """One CPU process = what one ugcore MPI rank does on this path: a serial solve with the
     reference's own kernels (oracle/_ref) or the port.  Gauss-Seidel runs in ugcore's own
     (lexicographic) order here — the multicolour order is a property of the GPU path."""
@@ -133,7 +138,7 @@ def _cpu_replica(refs, steps, warmup, barrier, q, workload="poisson", base_mult=
     kind = "ref" if oracle.have_ref() else "port"
     orc = oracle.Oracle(kind)
     spec = workload_spec(workload)
-    prob = pr.Problem(dim=3, num_refs=refs, problem=spec["problem"], base=(base_mult,) * 3, **spec["kw"])
+    prob = pr.Problem(dim=3, num_refs=refs, problem=spec["problem"], base=(base_mult,) * 3, order=order, **spec["kw"])
     lv = {}
     for l in range(0, refs + 1):
         lv[l] = (orc.matrix(prob.matrix(l)), orc.matrix(prob.prolongation(l)) if l else None,
@@ -169,7 +174,7 @@ def bounded_procs(nproc, refs, workload="poisson", base_mult=1):
     return max(1, min(nproc, int(0.4 * avail / max(replica_bytes(refs, workload, base_mult), 1))))
 
 
-def cpu_replicas(refs, nproc, steps, warmup, workload="poisson", base_mult=1):
+def cpu_replicas(refs, nproc, steps, warmup, workload="poisson", base_mult=1, order=0):
     """ugcore has no threads on this path and neither MPI nor boost exist here, so
     "all host cores" = nproc independent serial solves of the same workload running concurrently
     (they share the memory bus like MPI ranks would, but pay no interface exchange: an upper bound
@@ -178,7 +183,7 @@ def cpu_replicas(refs, nproc, steps, warmup, workload="poisson", base_mult=1):
     nproc = bounded_procs(nproc, refs, workload, base_mult)
     mpc = mp.get_context("spawn")
     barrier, q = mpc.Barrier(nproc), mpc.Queue()
-    procs = [mpc.Process(target=_cpu_replica, args=(refs, steps, warmup, barrier, q, workload, base_mult)) for _ in range(nproc)]
+    procs = [mpc.Process(target=_cpu_replica, args=(refs, steps, warmup, barrier, q, workload, base_mult, order)) for _ in range(nproc)]
     for p in procs:
         p.start()
     res = [q.get(timeout=3600) for _ in range(nproc)]
@@ -205,15 +210,17 @@ def run_reference(args):
     refs = args.cpu_refs if args.cpu_refs is not None else args.refs
     nproc = args.cpu_procs or host_cores()
     spec = workload_spec(args.workload)
-    r = cpu_replicas(refs, nproc, args.steps, args.warmup, args.workload, args.base_mult)
+    bmult = 2 * args.base_mult if args.scaling == "strong" else args.base_mult
+    order = {"lex": 0, "hier": 1}[args.order]
+    r = cpu_replicas(refs, nproc, args.steps, args.warmup, args.workload, bmult, order)
     nproc = r["cores"]           # may have been reduced to fit the host memory
     n, its, val, dt = r["n"], r["its"], r["value"], r["dt_per_step"]
-    nodes = args.base_mult * 2 ** refs + 1
+    nodes = bmult * 2 ** refs + 1
     sample = (f"{nproc} concurrent serial solves x {args.steps} steps of {spec['label']} {nodes}^3 nodes ({n} DoF, {its} "
               f"iterations each, {dt:.2f} s per solve): one process per host core, no threads inside ugcore on this path, "
               "no MPI on the box -> no interface exchange (upper bound of the MPI weak-scaling throughput)")
     out = {"impl": "reference", "metric": spec["metric"], "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
            "config": {"workload": f"{spec['label']} unit cube hexahedra numRefs={refs} ({n} DoF per process, {nproc} processes) "
                                   f"{spec['method']}, base LU on level 0, ugcore CPU kernels", "iterations": its},
@@ -223,9 +230,16 @@ def run_reference(args):
 
 
 def kernel_roofline(s, prob, top, peak_gbs, peak_src):
-    """Dominant kernel = the top-level fused smoothing step (4 of the 5 top-level matrix
-    sweeps per CG iteration); timed alone with CUDA events on the launching stream, inputs
-    (~0.75 GB) far larger than L2 so every launch streams from HBM."""
+    """Dominant kernel = the top-level fused smoothing step `sc += st; sd -= A st; st' = Dinv sd` (4 of the 5 top-level
+    matrix sweeps per CG iteration), timed alone with CUDA events on the launching stream.  The vectors rotate over
+    three sets, so no launch finds its operands in L2 (matrix stream + 3 x 5 vectors >> 126 MB).
+
+    `roofline` reports the bytes the kernel HAS TO MOVE in its stored format against the measured copy bandwidth
+    (frac) and against the 8 TB/s figure north_star quotes (frac_vs_spec).  The format is a lossless 4 B-per-entry
+    encoding of the CRS matrix, so the same time against the CRS bytes of SURVEY.md §8d (12 B per entry) is a larger
+    number; it is kept as achieved_vs_crs_bytes / frac_vs_crs_bytes and is NOT an HBM fraction.
+    `roofline_plain` is the same sweep on the plain 12 B-per-entry stream (UG4B200_MAT_NO_COMPRESS) — the kernel every
+    matrix without a small value dictionary gets; there stored bytes = CRS bytes (+ 1.5 % SELL padding)."""
     import ctypes as C
     from ugcore_b200 import capi
     from ugcore_b200.solver import host_ctx, DeviceBuffer
@@ -233,72 +247,76 @@ def kernel_roofline(s, prob, top, peak_gbs, peak_src):
     ctx = host_ctx()
     A = prob.matrix(top)
     n, nnz = A.nrows, A.nnz
-    m = C.c_void_p()
-    capi.check(dev.ug4b200_matrix_upload_crs(ctx, 1, n, n, A.rowptr.ctypes.data_as(C.c_void_p), A.cols.ctypes.data_as(C.c_void_p),
-                                             A.vals.ctypes.data_as(C.c_void_p), 0, C.byref(m)), ctx)
-    info = capi.MatrixInfo()
-    dev.ug4b200_matrix_get_info(m, C.byref(info))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
     rng = np.random.default_rng(0)
-    sd, st, st2, sc, dinv = (DeviceBuffer.from_numpy(rng.standard_normal(n)) for _ in range(5))
-    capi.check(dev.ug4b200_jacobi_prepare(ctx, m, 0.66, 1, dinv.ptr), ctx)
+    NSET = 3
+    sets = [[DeviceBuffer.from_numpy(rng.standard_normal(n)) for _ in range(4)] for _ in range(NSET)]   # sd, st, st2, sc
+    dinv = DeviceBuffer(n)
     e0, e1 = C.c_void_p(), C.c_void_p()
     dev.ug4b200_event_create(ctx, C.byref(e0)); dev.ug4b200_event_create(ctx, C.byref(e1))
 
-    def timeit(fn, reps=20):
-        for _ in range(3):
-            fn()
+    def timeit(fn, reps=21):
+        for k in range(3):
+            fn(k % NSET)
         dev.ug4b200_sync(ctx)
         dev.ug4b200_event_record(ctx, e0)
-        for _ in range(reps):
-            fn()
+        for k in range(reps):
+            fn(k % NSET)
         dev.ug4b200_event_record(ctx, e1)
         dev.ug4b200_event_sync(ctx, e1)
         ms = C.c_float()
         dev.ug4b200_event_elapsed_ms(ctx, e0, e1, C.byref(ms))
         return ms.value / reps
 
-    flags = capi.SMOOTH_ADD_IN | capi.SMOOTH_JACOBI
-    t_fused = timeit(lambda: dev.ug4b200_jacobi_smooth_fused(ctx, m, dinv.ptr, sd.ptr, st.ptr, st2.ptr, sc.ptr, flags))
-    t_spmv = timeit(lambda: dev.ug4b200_matrix_matmul_minus(ctx, m, sd.ptr, st.ptr, 1))
-    t_apply = timeit(lambda: dev.ug4b200_matrix_apply(ctx, m, sd.ptr, st.ptr, 1))
-    dev.ug4b200_event_destroy(ctx, e0); dev.ug4b200_event_destroy(ctx, e1)
-    dev.ug4b200_matrix_destroy(ctx, m)
-    # algorithmic (compulsory) bytes, SURVEY.md §8d / DESIGN.md §Kernels
+    gbs = lambda b, ms: b / (ms * 1e-3) / 1e9
+    # CRS bytes of the reference sweep, SURVEY.md §8d / DESIGN.md §4
     b_apply = 12 * nnz + 4 * (n + 1) + 8 * n + 8 * n
     b_minus = b_apply + 8 * n
     b_fused = 12 * nnz + 4 * (n + 1) + 64 * n   # + st_in, sd r/w, dinv, st_out, sc r/w
-    b_unfused_seq = b_minus + 24 * n + 24 * n   # y -= Ax ; c = Dinv d ; sc += c as separate sweeps
-    gbs = lambda b, ms: b / (ms * 1e-3) / 1e9
-    # bytes the kernel really has to move with the stored format: the value-indexed stream holds one 32-bit
-    # word per (padded) entry instead of 12 B (lossless), + row lengths, slice offsets, column bases, vectors
-    ns = int(info.num_slices)
-    if info.value_indexed:
-        b_stored = 4 * int(info.padded_nnz) + 4 * n + 8 * (ns + 1) + 4 * ns + 64 * n
-        kname = "tma::spmv1_vi_kernel<-1,INPLACE,FUSE_JACOBI> (ug4b200_jacobi_smooth_fused, value-indexed SELL-32 stream)"
-    else:
-        b_stored = 12 * int(info.padded_nnz) + 4 * n + 8 * (ns + 1) + 64 * n
-        kname = "tma::spmv1_tma_kernel<-1,INPLACE,FUSE_JACOBI> (ug4b200_jacobi_smooth_fused, plain SELL-32 stream)"
-    traffic = None
-    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, from the committed ncu --set full capture
+    flags = capi.SMOOTH_ADD_IN | capi.SMOOTH_JACOBI
+    try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("spmv1_vi_kernel" if info.value_indexed else "spmv1_tma_kernel")
+            tr = json.load(f)
     except Exception:
-        pass
-    roof = {"bound": "hbm", "kernel": kname,
-            "achieved": gbs(b_fused, t_fused), "peak": peak_gbs, "unit": "GB/s", "frac": gbs(b_fused, t_fused) / peak_gbs,
-            "peak_source": peak_src, "traffic": traffic, "bytes_per_launch": b_fused, "ms_per_launch": t_fused,
-            "note": "achieved/frac use the ALGORITHMIC bytes of the CRS sweep (12 B per stored entry, SURVEY.md 8d); the kernel "
-                    "streams a lossless 4 B-per-entry encoding, so frac > 1 is possible; achieved_stored/frac_stored are the bytes "
-                    "it actually has to move (= traffic) against the same peak",
-            "stored_bytes_per_launch": b_stored, "achieved_stored": gbs(b_stored, t_fused), "frac_stored": gbs(b_stored, t_fused) / peak_gbs,
-            # north_star quotes its 70 % target against the ~8 TB/s spec figure of B200 HBM3e: the same two fractions against it
-            "spec_peak": 8000.0, "frac_vs_spec": gbs(b_fused, t_fused) / 8000.0, "frac_stored_vs_spec": gbs(b_stored, t_fused) / 8000.0,
-            "vs_unfused_bytes_gbs": gbs(b_unfused_seq, t_fused)}
-    extra = {"spmv_matmul_minus": {"achieved": gbs(b_minus, t_spmv), "frac": gbs(b_minus, t_spmv) / peak_gbs,
-                                   "bytes_per_launch": b_minus, "ms_per_launch": t_spmv},
-             "spmv_apply": {"achieved": gbs(b_apply, t_apply), "frac": gbs(b_apply, t_apply) / peak_gbs,
-                            "bytes_per_launch": b_apply, "ms_per_launch": t_apply}}
-    return roof, extra
+        tr = {}
+    out = {}
+    for name, mflags in (("roofline", 0), ("roofline_plain", capi.MAT_NO_COMPRESS)):
+        m = C.c_void_p()
+        capi.check(dev.ug4b200_matrix_upload_crs(ctx, 1, n, n, vp(A.rowptr), vp(A.cols), vp(A.vals), mflags, C.byref(m)), ctx)
+        info = capi.MatrixInfo()
+        dev.ug4b200_matrix_get_info(m, C.byref(info))
+        capi.check(dev.ug4b200_jacobi_prepare(ctx, m, 0.66, 1, dinv.ptr), ctx)
+        t_fused = timeit(lambda k: dev.ug4b200_jacobi_smooth_fused(ctx, m, dinv.ptr, sets[k][0].ptr, sets[k][1].ptr, sets[k][2].ptr, sets[k][3].ptr, flags))
+        t_spmv = timeit(lambda k: dev.ug4b200_matrix_matmul_minus(ctx, m, sets[k][0].ptr, sets[k][1].ptr, 1))
+        t_apply = timeit(lambda k: dev.ug4b200_matrix_apply(ctx, m, sets[k][0].ptr, sets[k][1].ptr, 1))
+        dev.ug4b200_matrix_destroy(ctx, m)
+        ns, pnnz = int(info.num_slices), int(info.padded_nnz)
+        vec_bytes = 8 * n * int(info.fused_vector_streams) if hasattr(info, "fused_vector_streams") and info.fused_vector_streams else 64 * n
+        if info.value_indexed:
+            # one 32-bit word per (padded) entry + row lengths + slice offsets + column bases + the vector streams
+            b_stored = 4 * pnnz + 4 * n + 8 * (ns + 1) + 4 * ns + vec_bytes
+            kname, tkey = "tma::spmv1_vi_kernel<-1,INPLACE,FUSE_JACOBI> (ug4b200_jacobi_smooth_fused, value-indexed SELL-32 stream, 4 B/entry)", "spmv1_vi_kernel"
+        else:
+            b_stored = 12 * pnnz + 4 * n + 8 * (ns + 1) + vec_bytes
+            kname, tkey = "tma::spmv1_tma_kernel<-1,INPLACE,FUSE_JACOBI> (ug4b200_jacobi_smooth_fused, plain SELL-32 stream, 12 B/entry)", "spmv1_tma_kernel"
+        out[name] = {
+            "bound": "hbm", "kernel": kname, "achieved": gbs(b_stored, t_fused), "peak": peak_gbs, "unit": "GB/s",
+            "frac": gbs(b_stored, t_fused) / peak_gbs, "peak_source": peak_src,
+            "traffic": tr.get(tkey), "traffic_source": (tr.get("_sources") or {}).get(tkey, tr.get("_source")),
+            "bytes_per_launch": b_stored, "ms_per_launch": t_fused,
+            "spec_peak": 8000.0, "frac_vs_spec": gbs(b_stored, t_fused) / 8000.0,
+            "crs_bytes_per_launch": b_fused, "achieved_vs_crs_bytes": gbs(b_fused, t_fused), "frac_vs_crs_bytes": gbs(b_fused, t_fused) / peak_gbs,
+            "note": "bytes_per_launch = what the kernel has to move in its stored format (entry stream incl. SELL padding, row / slice "
+                    "metadata, 8 vector streams); achieved = that / CUDA-event time per launch, operands rotated so that nothing is "
+                    "L2-resident; frac is against the measured copy bandwidth, frac_vs_spec against north_star's 8 TB/s. "
+                    "*_vs_crs_bytes use the CRS bytes of SURVEY.md 8d (12 B per entry) and exceed 1 for the 4 B encoding: not an HBM fraction.",
+            "other_sweeps": {
+                "matmul_minus": {"ms_per_launch": t_spmv, "crs_bytes_per_launch": b_minus, "stored_bytes_per_launch": b_stored - vec_bytes + 24 * n,
+                                 "achieved": gbs(b_stored - vec_bytes + 24 * n, t_spmv), "frac": gbs(b_stored - vec_bytes + 24 * n, t_spmv) / peak_gbs},
+                "apply": {"ms_per_launch": t_apply, "crs_bytes_per_launch": b_apply, "stored_bytes_per_launch": b_stored - vec_bytes + 16 * n,
+                          "achieved": gbs(b_stored - vec_bytes + 16 * n, t_apply), "frac": gbs(b_stored - vec_bytes + 16 * n, t_apply) / peak_gbs}}}
+    dev.ug4b200_event_destroy(ctx, e0); dev.ug4b200_event_destroy(ctx, e1)
+    return out["roofline"], out["roofline_plain"]
 
 
 def workload_roofline(workload, prob, top, peak_gbs, peak_src):
@@ -365,10 +383,10 @@ def workload_roofline(workload, prob, top, peak_gbs, peak_src):
             dev.ug4b200_matrix_destroy(ctx, m)
 
 
-def cpu_baseline_sample(refs, workload="poisson", base_mult=1):
+def cpu_baseline_sample(refs, workload="poisson", base_mult=1, order=0):
     """Bounded CPU sample for the default run: the SAME workload solved once by every host core
     concurrently with the reference's kernels (~10-30 s including set-up)."""
-    r = cpu_replicas(refs, host_cores(), 1, 0, workload, base_mult)
+    r = cpu_replicas(refs, host_cores(), 1, 0, workload, base_mult, order)
     nproc = r["cores"]
     serial_equiv = r["n"] / r["dt_per_step"] / 1e6
     return {"value": r["value"], "unit": UNIT, "cores": nproc, "kind": r["kind"],
@@ -383,6 +401,7 @@ def run_ours(args):
     import torch
     from ugcore_b200 import capi, problems as pr
     from ugcore_b200 import solver as S
+    from ugcore_b200.capi import check_host, host
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -403,30 +422,39 @@ def run_ours(args):
     desc = solver_desc(refs, workload=args.workload)
     bm = args.base_mult
 
+    strong = args.scaling == "strong"
+    order = {"lex": pr.ORDER_LEX, "hier": pr.ORDER_HIER}[args.order]
+    reorder = None if args.reorder == "none" else args.reorder
+    part = PART[world]
+    # global base grid: weak scaling = bm cells per GPU and direction, strong scaling = 2 bm cells per direction whatever N
+    gbase = tuple(2 * bm for _ in range(3)) if strong else tuple(bm * p for p in part)
     if world > 1:
         import torch.distributed as dist
         from ugcore_b200 import dist as ugdist
+        if reorder:
+            raise SystemExit("--reorder is a single-GPU option")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        part = PART[world]
         gen_kw = dict(spec["kw"])
-        if bm != 1:
-            gen_kw["base_mult"] = bm
+        gen_kw["base"] = gbase
+        gen_kw["order"] = order
         prob, s = ugdist.build_partitioned_solver(desc, refs, part, rank, dist, problem=spec["problem"], flags=args.flags, **gen_kw)
         barrier = lambda: (dist.barrier(), torch.cuda.synchronize())
     else:
-        part = (1, 1, 1)
-        prob = pr.Problem(dim=3, num_refs=refs, problem=spec["problem"], base=(bm,) * 3, **spec["kw"])
-        s = S.Solver.from_problem(desc, prob, flags=args.flags)
+        prob = pr.Problem(dim=3, num_refs=refs, problem=spec["problem"], base=gbase, order=order, **spec["kw"])
+        s = S.Solver.from_problem(desc, prob, flags=args.flags, order=reorder)
         barrier = lambda: torch.cuda.synchronize()
     t_setup = time.perf_counter()
     s.init()
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t_setup      # solver:init — uploads, smoother preprocess, base factorisation (not part of a step)
     n_local = prob.num_dofs
-    dims = [part[d] * bm * 2 ** refs + 1 for d in range(3)]
+    dims = [gbase[d] * 2 ** refs + 1 for d in range(3)]
     n_global = dims[0] * dims[1] * dims[2] * spec["block"]
 
-    b_host = torch.from_numpy(np.array(prob.rhs())).pin_memory()
+    rhs = np.array(prob.rhs())
+    if s.perm is not None:      # --reorder: the solver works in its own (Cuthill-McKee) numbering; hand it b in that numbering
+        pb = np.empty_like(rhs); pb[s.perm] = rhs; rhs = pb
+    b_host = torch.from_numpy(rhs).pin_memory()
     x_host = torch.zeros(n_local, dtype=torch.float64).pin_memory()
     b_dev = b_host.cuda()
     x_dev = torch.zeros(n_local, dtype=torch.float64, device="cuda")
@@ -438,7 +466,7 @@ def run_ours(args):
 
     def solve_e2e():
         x_host.zero_()
-        ok = s.apply_pinned(x_host.data_ptr(), b_host.data_ptr())
+        ok = check_host(host.ug4b200_solver_apply(s.h, C.c_void_p(x_host.data_ptr()), C.c_void_p(b_host.data_ptr()))) == 0
         assert ok, "solver did not converge"
 
     def timed(fn, steps, warmup):
@@ -476,10 +504,11 @@ def run_ours(args):
     top_gb = (8 * spec["block"] ** 2 + 4) * top.nnz / 1e9
     nodes = f"{dims[0]}x{dims[1]}x{dims[2]}" + (f" nodes x {spec['block']}" if spec["block"] > 1 else "")
     out = {"metric": spec["metric"], "value": n_global / (ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"{spec['label']} unit-cell hexahedra numRefs={refs}, {nodes} = {n_global} DoF "
-                                  f"({n_local} per GPU, boxes {part[0]}x{part[1]}x{part[2]}), {spec['method']}, base LU on level 0",
+           "config": {"workload": f"{spec['label']} unit-cell hexahedra, base grid {gbase[0]}x{gbase[1]}x{gbase[2]} cells, numRefs={refs}, "
+                                  f"{nodes} = {n_global} DoF ({n_local} per GPU, boxes {part[0]}x{part[1]}x{part[2]}), {spec['method']}, "
+                                  f"base LU on level 0, DoF order {args.order}" + (f" + {reorder} at upload" if reorder else ""),
                       "iterations": its, "solve_s": ms * 1e-3, "init_s": setup_s,
                       "l2_policy": f"inputs larger than L2 (top-level matrix {top_gb:.2f} GB per GPU)",
                       "wall_ms_per_step": wall_ms, "final_reduction": float(hist[-1] / hist[0]) if len(hist) else None},
@@ -488,15 +517,14 @@ def run_ours(args):
            "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": int(launches), "clocks": clocks}
     if world == 1:
         if args.workload == "poisson":
-            roof, extra = kernel_roofline(s, prob, refs, peak, peak_src)
-            out["roofline"] = roof
-            out["roofline_other_kernels"] = extra
-            # whole-solve figure against the unfused reference sequence (~2.9 kB per fine DoF per iteration)
-            out["solve_algorithmic_gbs_vs_unfused"] = 2.9e3 * n_global * max(its, 1) / (ms * 1e-3) / 1e9
+            out["roofline"], out["roofline_plain"] = kernel_roofline(s, prob, refs, peak, peak_src)
+            # whole solve against the bytes of the UNFUSED reference sequence (~2.9 kB per fine DoF and
+            # iteration) — a yardstick for fusion + encoding, explicitly not a roofline fraction
+            out["solve_gbs_vs_unfused_reference_bytes"] = 2.9e3 * n_global * max(its, 1) / (ms * 1e-3) / 1e9
         else:
             out["roofline"] = workload_roofline(args.workload, prob, refs, peak, peak_src)
         if not args.no_cpu_baseline:
-            cb, h_cpu = cpu_baseline_sample(refs, args.workload, bm)
+            cb, h_cpu = cpu_baseline_sample(refs, args.workload, gbase[0], order)
             out["cpu_baseline"] = cb
             if args.workload != "convdiff":   # the CPU arm sweeps in ugcore's lexicographic order: another smoother
                 k = min(len(h_cpu), len(hist))
@@ -518,6 +546,12 @@ def main():
     ap.add_argument("--flags", type=int, default=0, help="UG4B200_FLAG_* bits for the solver (32: device-resident BiCGStab)")
     ap.add_argument("--base-mult", type=int, default=1, help="base-grid elements per GPU and direction "
                     "(--workload elasticity --base-mult 3 --refs 5: 97^3 nodes per GPU, 193^3 x 3 = 21.6 M DoF on 8 GPUs)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): one box of base-mult cells per GPU; strong: the same 2x2x2-cell base grid (257^3 at "
+                         "--refs 7, BASELINE configs[2]) on every GPU count")
+    ap.add_argument("--order", default="lex", choices=["lex", "hier"], help="DoF numbering of the generator: lexicographic, "
+                    "or hierarchical like ugcore's global refinement (coarse vertices first)")
+    ap.add_argument("--reorder", default="none", choices=["none", "cmk", "rcmk"], help="(reverse) Cuthill-McKee of every level before upload")
     ap.add_argument("--cpu-procs", type=int, default=0, help="processes of the CPU arm (0 = all host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

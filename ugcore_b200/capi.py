@@ -54,6 +54,7 @@ class SolverDesc(C.Structure):
 
 FIN_STORE, FIN_A_DIV_R, FIN_R_DIV_A, FIN_SQRT, FIN_CONV_START, FIN_CONV_UPDATE = range(6)
 SMOOTH_ADD_IN, SMOOTH_JACOBI, SMOOTH_ADD_OUT, SMOOTH_SC_ZERO = 1, 2, 4, 8
+MAT_DEFAULT, MAT_NO_COMPRESS = 0, 1
 FLAG_HOST_SCALARS, FLAG_NO_GRAPH, FLAG_NO_FUSED_JACOBI, FLAG_FINAL_LEVEL_DEFECT, FLAG_RAP, FLAG_DEVICE_BICGSTAB, FLAG_DEVICE_LINEAR = 1, 2, 4, 8, 16, 32, 64
 
 # name -> (restype, argtypes); every symbol declared in include/ug4b200.h

@@ -165,18 +165,30 @@ def make_consistent(A: pr.Crs, rank: int, ranks, ptr, idx, dist) -> pr.Crs:
     return apply_contributions(A, rank, ranks, ptr, idx, received)
 
 
+def _global_base(part, base_mult=1, base=None):
+    """Base-grid elements per direction of the GLOBAL grid: ``base`` if given (strong scaling: the same grid for every
+    process grid that divides it), else base_mult elements per rank and direction (weak scaling)."""
+    if base is not None:
+        base = tuple(int(b) for b in base)
+        if any(b % p for b, p in zip(base, part)):
+            raise ValueError(f"process grid {tuple(part)} does not divide the base grid {base}")
+        return base
+    return tuple(base_mult * p for p in part)
+
+
 def local_problem(refs: int, part, rank: int, problem=pr.POISSON, order=pr.ORDER_LEX, dim=3, base_mult: int = 1,
-                  **kw) -> pr.Problem:
+                  base=None, **kw) -> pr.Problem:
     """This rank's sub-box of the global grid whose base grid has base_mult elements per rank and
-    direction (base_mult = 3, refs = 5: 97 nodes per direction and rank)."""
+    direction (base_mult = 3, refs = 5: 97 nodes per direction and rank) — or ``base`` elements per direction
+    in total (base = (2, 2, 2), refs = 7: the 257^3 grid of BASELINE configs[2] for every process grid up to 2x2x2)."""
     coord = rank_to_coord(rank, part)
-    return pr.Problem(dim=dim, num_refs=refs, problem=problem, base=tuple(base_mult * p for p in part), base_lev=0,
+    return pr.Problem(dim=dim, num_refs=refs, problem=problem, base=_global_base(part, base_mult, base), base_lev=0,
                       order=order, part=tuple(part), coord=coord, **kw)
 
 
-def global_problem(refs: int, part, problem=pr.POISSON, dim=3, base_mult: int = 1, **kw) -> pr.Problem:
+def global_problem(refs: int, part, problem=pr.POISSON, dim=3, base_mult: int = 1, base=None, **kw) -> pr.Problem:
     """The same grid assembled serially (parity target and gathered base matrix)."""
-    return pr.Problem(dim=dim, num_refs=refs, problem=problem, base=tuple(base_mult * p for p in part), base_lev=0, **kw)
+    return pr.Problem(dim=dim, num_refs=refs, problem=problem, base=_global_base(part, base_mult, base), base_lev=0, **kw)
 
 
 _nccl_ready = False
@@ -256,18 +268,19 @@ def p2p_bootstrap(dist) -> bool:
 
 
 def default_gather_level(refs: int, part, base: int = 0, max_local_rows: int = 40000, max_global_rows: int = 300000,
-                         dim: int = 3, base_mult: int = 1) -> int:
+                         dim: int = 3, base_mult: int = 1, global_base=None) -> int:
     """Highest level that is kept (and cycled) redundantly on every rank instead of being partitioned:
     a level whose LOCAL box has at most max_local_rows rows is latency-bound — its four interface
     exchanges per cycle (~6-8 us each) cost more than smoothing the whole (still small) global level
     on every rank.  Measured at 129^3 per GPU: gathering level 5 (33^3 local, 65^3 global at N = 8)
     instead of level 4 saves 0.15-0.25 ms per solve at N = 2 and N = 8."""
+    gb = _global_base(part, base_mult, global_base)
     lev = base
     for l in range(base, refs):
         loc, glob = 1, 1
         for d in range(dim):
-            loc *= base_mult * 2 ** l + 1
-            glob *= part[d] * base_mult * 2 ** l + 1
+            loc *= (gb[d] // part[d]) * 2 ** l + 1
+            glob *= gb[d] * 2 ** l + 1
         if loc <= max_local_rows and glob <= max_global_rows:
             lev = l
     return lev
@@ -322,7 +335,8 @@ def build_partitioned_solver(desc: dict, refs: int, part, rank: int, dist, probl
     if gather_level is None:
         env = os.environ.get("UG4B200_GATHER_LEVEL")
         gather_level = int(env) if env is not None else default_gather_level(refs, part, base, dim=prob.dim,
-                                                                             base_mult=kw.get("base_mult", 1))
+                                                                             base_mult=kw.get("base_mult", 1),
+                                                                             global_base=kw.get("base"))
     if pc.get("cycle", "V") != "V":
         gather_level = base
     gather = max(base, min(int(gather_level), refs - 1))
