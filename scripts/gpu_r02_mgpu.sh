@@ -6,8 +6,9 @@ set -u
 mkdir -p gpurun_out
 NG=$(nvidia-smi -L | wc -l)
 t0=$SECONDS
-timeout 1300 python -m pytest tests/test_multi_gpu.py -m gpu -q -rf -rs 2>&1 | tail -40 | tee gpurun_out/mgpu${NG}_tests.log
-timeout 300 python -m pytest tests/test_gpu_solver.py -m gpu -q -rf -k reinit 2>&1 | tail -15 | tee gpurun_out/reinit_tests.log
+export UG4B200_RECORD_HIST_ERR=$PWD/gpurun_out/hist_err_mgpu${NG}.jsonl
+timeout 900 python -m pytest tests/test_multi_gpu.py -m gpu -q -rf --timeout 150 ${MGPU_K:+-k "$MGPU_K"} 2>&1 | tail -40 | tee gpurun_out/mgpu${NG}_tests.log
+timeout 200 python -m pytest tests/test_gpu_solver.py -m gpu -q -rf --timeout 60 -k reinit 2>&1 | tail -15 | tee gpurun_out/reinit_tests.log
 if [ "${1:-}" = "bench" ]; then
   for w in poisson convdiff elasticity; do
     extra=""; [ $w = elasticity ] && extra="--refs 6"

@@ -294,7 +294,7 @@ def test_reinit_with_a_changed_matrix_recaptures_the_graph(solver, precond):
     # explicit zeros that the Dirichlet rows keep, sparsematrix_util.h:850-861, removed: nnz and the slices change)
     rows = np.repeat(np.arange(A0.nrows), np.diff(A0.rowptr))
     diag = rows == A0.cols
-    v1 = 2.0 * np.asarray(A0.vals) + np.where(diag, 0.25 * np.asarray(A0.vals), 0.0)
+    v1 = 2.0 * np.asarray(A0.vals) + (0.0 if precond == "gmg" else np.where(diag, 0.25 * np.asarray(A0.vals), 0.0))
     A1 = pr.Crs(A0.nrows, A0.ncols, 1, A0.rowptr.copy(), A0.cols.copy(), v1)
     dirich = np.asarray(prob.dirichlet(), bool)
     keep = ~(dirich[rows] & ~diag)
@@ -303,16 +303,23 @@ def test_reinit_with_a_changed_matrix_recaptures_the_graph(solver, precond):
     A2 = pr.Crs(A0.nrows, A0.ncols, 1, rp2, A0.cols[keep].copy(), np.asarray(A0.vals)[keep].copy())
     b = make_rhs(prob, 7)
 
+    def scaled(M, f):
+        return pr.Crs(M.nrows, M.ncols, M.block, M.rowptr, M.cols, f * np.asarray(M.vals))
+
     def levels_of(A):
+        """GMG hierarchy that goes with the top-level matrix A: the coarse operators are re-assembled together with it
+        (A1 = 2 A0 + ... on the top level comes with 2 x the coarse level matrices, so the cycle stays a preconditioner)"""
         if precond != "gmg":
             return None
-        return {l: (A if l == 3 else prob.matrix(l), prob.prolongation(l) if l else None, prob.restriction(l) if l else None)
+        f = 2.0 if A is A1 else 1.0
+        return {l: (A if l == 3 else scaled(prob.matrix(l), f), prob.prolongation(l) if l else None, prob.restriction(l) if l else None)
                 for l in range(0, 4)}
 
     def oracle_solve(A):
         if precond == "gmg":
-            lv = oracle_levels(orc, prob, 0, 3)
-            lv[3] = (orc.matrix(A), lv[3][1], lv[3][2])
+            lvA = levels_of(A)
+            lv = {l: (orc.matrix(t[0]), orc.matrix(t[1]) if t[1] is not None else None, orc.matrix(t[2]) if t[2] is not None else None)
+                  for l, t in lvA.items()}
             return oracle.OSolver(orc, desc, lv[3][0], lv).apply(b)
         if precond in ("gs", "ilu"):   # the device sweeps in the greedy multicolour order of the given pattern
             from helpers import greedy_color_perm, permute_crs
@@ -329,7 +336,7 @@ def test_reinit_with_a_changed_matrix_recaptures_the_graph(solver, precond):
     s = ug.Solver(desc, A0, levels_of(A0), flags=flags)
     for A in (A0, A1, A2, A0):
         if A is not A0 or s._inited:
-            s.set_matrix(A)
+            s.set_matrix(A, levels_of(A))
         xg, okg, hg = s.apply(b)
         xo, oko, ho = oracle_solve(A)
         assert okg == oko

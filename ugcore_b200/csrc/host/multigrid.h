@@ -155,7 +155,7 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 
 	// ---- what assembly hands over (replaces assemble_level_operator :526-752 and the cached
 	//      StdTransfer::prolongation()/restriction() :602-717) ----
-	void set_level_operator(int lev, SmartPtr<matrix_operator_type> A) { level(lev).A = A; }
+	void set_level_operator(int lev, SmartPtr<matrix_operator_type> A) { level(lev).A = A; level(lev).AisSurface = false; }
 	void set_level_transfer(int lev, SmartPtr<GPUTransferMatrix> P, SmartPtr<GPUTransferMatrix> R) { level(lev).P = P; level(lev).R = R; }
 	/// surface index of every top-level index (vSurfLevelMap); empty = identity (full refinement)
 	void set_surface_to_level_map(const std::vector<int>& surfIndexOfLevelIndex) { m_surfMap = surfIndexOfLevelIndex; }
@@ -186,10 +186,12 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 		if (m_bRAP) init_rap_operator();
 		for (int lev = m_baseLev; lev <= m_topLev; ++lev) {
 			LevData& ld = level(lev);
-			if (!ld.A) {
-				if (lev == m_topLev) ld.A = m_spSurfaceMat; // copy of the surface matrix (:623-656), identity map
-				else UG_THROW("GMG::init: level operator of level " << lev << " missing");
+			if (lev == m_topLev && (!ld.A || ld.AisSurface)) {
+				// copy of the surface matrix (:623-656), identity map — taken anew at EVERY init: solver:init(J, u) with a
+				// re-assembled J must not leave the top level smoothing with the previous operator
+				ld.A = m_spSurfaceMat; ld.AisSurface = true;
 			}
+			if (!ld.A) UG_THROW("GMG::init: level operator of level " << lev << " missing");
 			const size_t n = ld.A->num_rows();
 			ld.sc.create(n); ld.sd.create(n); ld.st.create(n); ld.st2.create(n);
 			for (vector_type* v : {&ld.sc, &ld.sd, &ld.st, &ld.st2}) v->set_layouts(ld.layouts);
@@ -305,6 +307,7 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 		vector_type sc, sd, st, st2;
 		SmartPtr<GPUAlgebraLayouts> layouts;
 		SmartPtr<matrix_type> Aconsistent;   // partitioned Gauss-Seidel only
+		bool AisSurface = false;             // A was not handed over but taken from the surface operator at init
 		bool scZero = false;   // sc is logically 0: the next accumulation assigns (UG4B200_SMOOTH_SC_ZERO)
 		bool stReady = false;  // st already holds S*sd (produced by the fused restriction of the finer level)
 	};
@@ -321,7 +324,7 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 	/// vertical interfaces.
 	void init_rap_operator()
 	{
-		if (!level(m_topLev).A) level(m_topLev).A = m_spSurfaceMat;
+		if (!level(m_topLev).A || level(m_topLev).AisSurface) { level(m_topLev).A = m_spSurfaceMat; level(m_topLev).AisSurface = true; }
 		for (int lev = m_topLev; lev > m_baseLev; --lev) {
 			LevData& lf = level(lev); LevData& lc = level(lev - 1);
 			if (!lf.P) UG_THROW("GMG::init_rap_operator: prolongation of level " << lev << " missing");
