@@ -511,7 +511,8 @@ def run_ours(args):
                                   f"base LU on level 0, DoF order {args.order}" + (f" + {reorder} at upload" if reorder else ""),
                       "iterations": its, "solve_s": ms * 1e-3, "init_s": setup_s,
                       "l2_policy": f"inputs larger than L2 (top-level matrix {top_gb:.2f} GB per GPU)",
-                      "wall_ms_per_step": wall_ms, "final_reduction": float(hist[-1] / hist[0]) if len(hist) else None},
+                      "wall_ms_per_step": wall_ms, "final_reduction": float(hist[-1] / hist[0]) if len(hist) else None,
+                      "history": [float(v) for v in hist]},
            "e2e": {"value": n_global / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 16 * n_local,
                    "d2h_bytes_per_step": 8 * n_local, "ms_per_step": ms_e2e, "wall_ms_per_step": wall_e2e},
            "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": int(launches), "clocks": clocks}
@@ -530,6 +531,7 @@ def run_ours(args):
                 k = min(len(h_cpu), len(hist))
                 out["config"]["history_rel_err_vs_cpu"] = float(np.max(np.abs(hist[:k] - h_cpu[:k]) / np.abs(h_cpu[:k])))
             out["config"]["iterations_cpu"] = len(h_cpu) - 1
+            out["config"]["history_cpu"] = [float(v) for v in h_cpu]
     print(json.dumps(out), flush=True)
 
 

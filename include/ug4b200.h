@@ -204,7 +204,7 @@ int ug4b200_conv_init(ug4b200_ctx* ctx, ug4b200_conv_state* dev_state, int max_s
  * bytes per entry (cf. CSR-VI / CSR-DU, Kourtis et al. 2008).  Lossless, so every result stays
  * bit-identical; the SpMV family streams this copy.  UG4B200_MAT_NO_COMPRESS (or the
  * environment variable UG4B200_NO_COMPRESS=1) keeps the plain stream only. */
-enum { UG4B200_MAT_DEFAULT = 0, UG4B200_MAT_NO_COMPRESS = 1 };
+enum { UG4B200_MAT_DEFAULT = 0, UG4B200_MAT_NO_COMPRESS = 1, UG4B200_MAT_NO_XSTAGE = 2 };
 
 typedef struct ug4b200_matrix_info {
 	int64_t nrows, ncols, nnz, padded_nnz, num_slices, device_bytes;
@@ -212,6 +212,10 @@ typedef struct ug4b200_matrix_info {
 	int max_row_len;
 	int value_indexed;        /* 1 if the value-indexed stream exists */
 	int num_distinct_values;
+	int x_staged;             /* 1 if the x-staged stream exists (value-indexed words + per-slice lists of the column runs that
+	                             the bulk-copy kernel stages in shared memory next to the entry words) */
+	int x_staged_runs;        /* run slots per slice of that stream */
+	int64_t x_staged_doubles; /* doubles of x staged per sweep (sum over the slices), aligned run ends included */
 } ug4b200_matrix_info;
 
 int ug4b200_matrix_upload_crs(ug4b200_ctx* ctx, int block, int64_t nrows, int64_t ncols, const int64_t* rowptr,

@@ -15,6 +15,7 @@ def main():
     A = prob.matrix(refs); n, nnz = A.nrows, A.nnz
     m = C.c_void_p()
     capi.check(dev.ug4b200_matrix_upload_crs(ctx, 1, n, n, A.rowptr.ctypes.data_as(C.c_void_p), A.cols.ctypes.data_as(C.c_void_p), A.vals.ctypes.data_as(C.c_void_p), 0, C.byref(m)), ctx)
+    info = capi.MatrixInfo(); dev.ug4b200_matrix_get_info(m, C.byref(info))
     rng = np.random.default_rng(0)
     sd, st, st2, sc, dinv, q = (DeviceBuffer.from_numpy(rng.standard_normal(n)) for _ in range(6))
     S = DeviceBuffer(16)
@@ -36,6 +37,7 @@ def main():
       "matmul_minus": (lambda: dev.ug4b200_matrix_matmul_minus(ctx, m, sd.ptr, st.ptr, 1), b_apply + 8*n),
       "apply": (lambda: dev.ug4b200_matrix_apply(ctx, m, sd.ptr, st.ptr, 1), b_apply),
       "apply_dot": (lambda: dev.ug4b200_matrix_apply_dot_ds(ctx, m, q.ptr, st.ptr, fin), b_apply),
+      "restrict_like_skip_empty": (lambda: dev.ug4b200_matrix_apply_ignore_zero_rows(ctx, m, sd.ptr, 1.0, st.ptr, 1), b_apply),
       "cg_update": (lambda: dev.ug4b200_cg_update_ds(ctx, n, sd.ptr, st.ptr, st2.ptr, sc.ptr, S.ptr, fin), 48*n),
       "dot": (lambda: dev.ug4b200_vec_dot_ds(ctx, n, sd.ptr, st.ptr, fin), 16*n),
       "axpy": (lambda: dev.ug4b200_vec_scale_add2(ctx, n, sd.ptr, 1.0, sd.ptr, 0.5, st.ptr), 24*n),
@@ -44,6 +46,7 @@ def main():
     for k, (fn, nbytes) in cases.items():
         ms = timeit(fn)
         res[k] = {"us": round(ms * 1e3, 2), "GBs": round(nbytes / ms / 1e6, 1)}
-    print(json.dumps({"variant": os.environ.get("UG4B200_LIBDIR", "default"), "n": n, "order": order, **res}))
+    print(json.dumps({"variant": os.path.basename(os.environ.get("UG4B200_LIBDIR", "default").rstrip("/")), "n": n, "order": order,
+                      "stream": "xs" if info.x_staged else ("vi" if info.value_indexed else "plain"), **res}))
 
 main()

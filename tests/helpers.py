@@ -29,26 +29,40 @@ def gmg_desc(top, solver="cg", smoother=None, nu=(2, 2), cycle="V", base=0, base
             "convCheck": {"iterations": its, "absolute": absolute, "reduction": reduction}}
 
 
-def rel_hist_err(h_gpu, h_ref, allowance=0.0):
-    """max_k |h_gpu[k] - h_ref[k]| / |h_ref[k]| over the common prefix — north_star's "residual history within
-    1e-10 relative per iteration", strict: no absolute allowance unless the caller asks for one.
+ROUND_OFF_FLOOR = 1e-12      # a defect below this fraction of the start defect is round-off of the start defect
+ROUND_OFF_ALLOWANCE = 1e-14  # absolute allowance (x start defect) for steps below the floor
 
-    (Round 1 subtracted 1e-14 * start defect first; at the end of a history that has dropped by 1e-10 that is a
-    relative 1e-4 — it hid everything but the first steps.  What a history can be held to is measured instead:
-    tests/test_reduction_order.py records how far the REFERENCE's own history moves when only the summation order
-    of its dot products changes.)  UG4B200_RECORD_HIST_ERR=<file>: every evaluation is appended to that file."""
+
+def rel_hist_err(h_gpu, h_ref, allowance=None):
+    """max_k |h_gpu[k] - h_ref[k]| / |h_ref[k]| over the common prefix — north_star's "residual history within
+    1e-10 relative per iteration", strict for every step whose defect is at least 1e-12 x the start defect (that
+    covers every step of the BASELINE configurations, which stop at a reduction of 1e-10 / 1e-8).
+
+    Steps BELOW 1e-12 x start defect (a solver that converges to machine precision in one or two steps: an exact
+    ILU, LU) are round-off of the start defect itself — eps * ||b|| * amplification — and have no meaningful relative
+    accuracy in any implementation; for those, and only those, differences up to 1e-14 x start defect are ignored.
+    (Round 1 applied that allowance to EVERY step: at the end of a history that has dropped by 1e-10 it is a relative
+    1e-4 and hid everything but the first steps.)  What a history above the floor can be held to is measured:
+    tests/test_reduction_order.py records how far the REFERENCE's own history moves when only the summation order of
+    its dot products changes, and sens_tol() turns that into the tolerance.
+    UG4B200_RECORD_HIST_ERR=<file>: every evaluation is appended to that file."""
     n = min(len(h_gpu), len(h_ref))
     if not n:
         return 0.0
     h_gpu, h_ref = np.asarray(h_gpu[:n], float), np.asarray(h_ref[:n], float)
-    diff = np.maximum(np.abs(h_gpu - h_ref) - allowance * abs(h_ref[0]), 0.0)
-    err = float(np.max(diff / np.abs(h_ref)))
+    diff = np.abs(h_gpu - h_ref)
+    below = np.abs(h_ref) < ROUND_OFF_FLOOR * abs(h_ref[0])
+    allow = (ROUND_OFF_ALLOWANCE if allowance is None else allowance) * abs(h_ref[0])
+    diff = np.where(below, np.maximum(diff - allow, 0.0), diff)
+    with np.errstate(all="ignore"):
+        q = np.where(diff == 0.0, 0.0, diff / np.abs(h_ref))
+    err = float(np.max(q))
     rec = os.environ.get("UG4B200_RECORD_HIST_ERR")
     if rec:
         import json
         with open(rec, "a") as f:
             f.write(json.dumps({"test": os.environ.get("PYTEST_CURRENT_TEST", ""), "steps": n - 1, "err": err,
-                                "strict": float(np.max(np.abs(h_gpu - h_ref) / np.abs(h_ref))),
+                                "strict": float(np.max(np.where(h_gpu == h_ref, 0.0, np.abs(h_gpu - h_ref) / np.abs(h_ref)))),
                                 "reduction": float(h_ref[-1] / h_ref[0])}) + "\n")
     return err
 
@@ -85,8 +99,9 @@ def sens_tol(orc, osol, b, base=1e-10, factor=10.0):
     changes (BiCGStab, GMRES, long unpreconditioned runs) — `factor` times that measured movement.  The GPU's
     reduction tree is one more summation order; it cannot be expected to land closer to the sequential sum than
     another valid order does."""
-    sens, _, _ = osolver_sensitivity(orc, osol, b)
-    sens = sens[np.isfinite(sens)]
+    sens, h0, _ = osolver_sensitivity(orc, osol, b)
+    ok = np.isfinite(sens) & (np.abs(h0[:sens.size]) >= ROUND_OFF_FLOOR * abs(h0[0]))
+    sens = sens[ok]
     return max(base, factor * float(sens.max())) if sens.size else base
 
 

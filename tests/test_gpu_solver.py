@@ -40,8 +40,11 @@ def _compare(prob, desc, flags=0):
     xg, okg, hg = s.apply(b)
     assert okg == oko
     assert abs(len(hg) - len(ho)) <= 1, (len(hg), len(ho))
-    assert rel_hist_err(hg, ho) < HIST_TOL, (hg, ho)
-    assert np.linalg.norm(xg - xo) <= SOL_TOL * np.linalg.norm(xo)
+    # north_star's 1e-10 — unless the reference's own history moves by more than a tenth of that under a reordered sum
+    # (measured on this very solve: helpers.sens_tol; 1e-10 for every GMG-CG case)
+    tol = sens_tol(orc, osol, b, base=HIST_TOL)
+    assert rel_hist_err(hg, ho) < tol, (rel_hist_err(hg, ho), tol, hg, ho)
+    assert np.linalg.norm(xg - xo) <= max(SOL_TOL, tol) * np.linalg.norm(xo)
     return s, hg, ho
 
 
@@ -50,6 +53,19 @@ def test_poisson3d_gmg_cg_matches_oracle():
     prob = pr.Problem(dim=3, num_refs=4)
     s, hg, ho = _compare(prob, gmg_desc(4))
     assert len(hg) == len(ho)
+
+
+@pytest.mark.parametrize("base", [(2, 2, 2), (3, 3, 3), (2, 1, 1)])
+def test_poisson3d_several_base_cells_matches_oracle(base):
+    """Base grids of more than one cell: the coarsest level then has interior DoFs, so the base solve (dense LU on the
+    device) contributes to every cycle — on the one-cell unit cube it only ever sees Dirichlet rows.  2x2x2 cells with
+    numRefs = 7 is the 257^3 grid of BASELINE configs[2] (bench.py --scaling strong), 3x3x3 the elasticity bench grid."""
+    from ugcore_b200 import problems as pr
+    prob = pr.Problem(dim=3, num_refs=3, base=base)
+    s, hg, ho = _compare(prob, gmg_desc(3))
+    assert len(hg) == len(ho)
+    prob = pr.Problem(dim=3, num_refs=2, base=base, problem=pr.ELASTICITY)
+    _compare(prob, gmg_desc(2, reduction=1e-8, its=200))
 
 
 def test_poisson2d_cfg1_standin_gmg_cg():

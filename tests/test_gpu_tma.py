@@ -11,20 +11,34 @@ from helpers import Dev
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["value_indexed", "plain"])
+@pytest.fixture(scope="module", params=["x_staged", "value_indexed", "plain"])
 def tma_ctx(request):
+    """x_staged: value-indexed words + x operand staged in shared memory (spmv1_xs_kernel, the default for matrices whose
+    slices touch a few runs of consecutive columns); value_indexed: UG4B200_NO_XSTAGE=1 (spmv1_vi_kernel, x gathered from
+    global memory); plain: UG4B200_NO_COMPRESS=1 (spmv1_tma_kernel, 12 B per entry)."""
     from ugcore_b200 import capi
     os.environ["UG4B200_TMA_MIN_SLICES"] = "0"
     if request.param == "plain":
         os.environ["UG4B200_NO_COMPRESS"] = "1"
+    if request.param == "value_indexed":
+        os.environ["UG4B200_NO_XSTAGE"] = "1"
     ctx = C.c_void_p()
     try:
         capi.check(capi.dev.ug4b200_ctx_create(0, None, C.byref(ctx)))
     finally:
         del os.environ["UG4B200_TMA_MIN_SLICES"]
         os.environ.pop("UG4B200_NO_COMPRESS", None)
+        os.environ.pop("UG4B200_NO_XSTAGE", None)
+    ctx.mode = request.param
     yield ctx
     capi.dev.ug4b200_ctx_destroy(ctx)
+
+
+def _info(D, dA):
+    from ugcore_b200 import capi
+    info = capi.MatrixInfo()
+    D.dev.ug4b200_matrix_get_info(dA, C.byref(info))
+    return info
 
 
 @pytest.fixture()
@@ -49,6 +63,12 @@ def test_tma_spmv_family_bit_exact(D, orc, i):
     A = prob.matrix()
     n = A.nrows
     oA, dA = orc.matrix(A), D.matrix(A)
+    info = _info(D, dA)
+    # the x-staged stream exists exactly for the banded (lexicographic) numberings, and only in its mode
+    if D.ctx.mode != "x_staged":
+        assert not info.x_staged
+    elif i != 1:      # (the hierarchical numbering scatters a slice's columns: usually not stageable, not asserted)
+        assert info.x_staged and info.value_indexed, (i, info.x_staged, info.value_indexed, info.num_distinct_values)
     x, y0, v = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(n)
     dx, dv = D.up(x), D.up(v)
     dy = D.up(y0)
@@ -106,3 +126,44 @@ def test_tma_ragged_and_empty_rows(D, orc):
     dd = D.up(d0)
     D.chk(D.dev.ug4b200_matrix_axpy(D.ctx, dA, dd, 1.0, dd, 0.37, dx, 1))
     assert np.array_equal(D.down(dd, n), oA.axpy(1.0, None, 0.37, x, dest=d0))
+
+
+def test_tma_transfers_and_banded_ragged_matrix(D, orc):
+    """The x-staged path on what is not a level operator: P (rows of 1 / 2 / 4 / 8 entries, rectangular, odd number of
+    columns), R = P^T with Dirichlet rows, and a ragged banded matrix with few distinct values, empty rows, an empty
+    slice and an odd number of columns (the last run of the last slices ends on the 16-byte unit behind the vector)."""
+    from ugcore_b200 import problems as pr
+    from ugcore_b200.problems import Crs
+    prob = pr.Problem(dim=3, num_refs=4)
+    rng = np.random.default_rng(9)
+    for M in (prob.prolongation(4), prob.restriction(4), prob.prolongation(3)):
+        oM, dM = orc.matrix(M), D.matrix(M)
+        x, d0 = rng.standard_normal(M.ncols), rng.standard_normal(M.nrows)
+        dx, dd = D.up(x), D.up(d0)
+        D.chk(D.dev.ug4b200_matrix_apply_ignore_zero_rows(D.ctx, dM, dd, 1.0, dx, 1))
+        assert np.array_equal(D.down(dd, M.nrows), oM.apply_ignore_zero_rows(d0, 1.0, x))
+        D.chk(D.dev.ug4b200_matrix_axpy(D.ctx, dM, dd, 0.0, None, 1.0, dx, 1))
+        assert np.array_equal(D.down(dd, M.nrows), oM.apply(x))
+        D.dev.ug4b200_matrix_destroy(D.ctx, dM)
+    n, m, band = 2001, 2003, 40
+    lens = rng.integers(0, 20, n)
+    lens[320:352] = 0
+    lens[7] = 0
+    vals_pool = np.array([1.0, -0.5, 0.25, 3.0, -0.0, 0.0, 1e-300, -7.5])
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    ci = np.concatenate([np.sort(rng.choice(np.arange(max(0, r - band), min(m, r + band)), l, replace=False))
+                         for r, l in enumerate(lens)]).astype(np.int32)
+    ci[-1] = m - 1 if lens[-1] else ci[-1]
+    va = vals_pool[rng.integers(0, vals_pool.size, ci.size)]
+    A = Crs(n, m, 1, rp, ci, va)
+    oA, dA = orc.matrix(A), D.matrix(A)
+    if D.ctx.mode == "x_staged":
+        assert _info(D, dA).x_staged == 1
+    x, d0 = rng.standard_normal(m), rng.standard_normal(n)
+    dx, dd = D.up(x), D.up(d0)
+    D.chk(D.dev.ug4b200_matrix_apply_ignore_zero_rows(D.ctx, dA, dd, -1.0, dx, 1))
+    assert np.array_equal(D.down(dd, n), oA.apply_ignore_zero_rows(d0, -1.0, x))
+    dd = D.up(d0)
+    D.chk(D.dev.ug4b200_matrix_matmul_minus(D.ctx, dA, dd, dx, 1))
+    assert np.array_equal(D.down(dd, n), oA.matmul_minus(d0, x))
+    D.dev.ug4b200_matrix_destroy(D.ctx, dA)

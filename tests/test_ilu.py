@@ -18,7 +18,7 @@ import numpy as np
 import pytest
 
 import oracle
-from helpers import gmg_desc, greedy_color_perm, permute_crs, rel_hist_err
+from helpers import gmg_desc, greedy_color_perm, permute_crs, rel_hist_err, sens_tol
 from ugcore_b200 import problems as pr
 
 
@@ -283,9 +283,10 @@ def test_gpu_block_ilu_multicolor_apply_and_solve():
     assert np.array_equal(c, orc.matrix(permute_crs(A, perm, perm)).ilu(0.0).ilu_apply(dp)[pp])
     desc["precond"] = {"type": "ilu"}
     x, ok, h = ug.Solver(desc, A).apply(prob.rhs())
-    xo, oko, ho = oracle.OSolver(orc, desc, orc.matrix(A)).apply(np.array(prob.rhs()))
+    osol = oracle.OSolver(orc, desc, orc.matrix(A))
+    xo, oko, ho = osol.apply(np.array(prob.rhs()))
     assert ok and oko and abs(len(h) - len(ho)) <= 1
-    assert rel_hist_err(h, ho) < 1e-9
+    assert rel_hist_err(h, ho) < sens_tol(orc, osol, np.array(prob.rhs()))
     assert np.linalg.norm(x - xo) <= 1e-8 * np.linalg.norm(xo)
 
 
@@ -321,10 +322,11 @@ def test_gpu_solvers_with_ilu_and_gmres_match_oracle(name):
     b = np.array(prob.rhs())
     x, ok, h = ug.Solver(DESCS[name], A).apply(b)
     orc = _best()
-    xo, oko, ho = oracle.OSolver(orc, DESCS[name], orc.matrix(A)).apply(b)
+    osol = oracle.OSolver(orc, DESCS[name], orc.matrix(A))
+    xo, oko, ho = osol.apply(b)
     assert ok and oko and abs(len(h) - len(ho)) <= 1
-    tol = 1e-8 if name in ("bicgstab_ilub", "gmres") else 1e-10      # BiCGStab / unrestarted GMRES amplify round-off
-    assert rel_hist_err(h, ho) < tol
+    tol = sens_tol(orc, osol, b)      # 1e-10, or 10 x the reference's own movement under a reordered sum (BiCGStab, GMRES)
+    assert rel_hist_err(h, ho) < tol, (rel_hist_err(h, ho), tol)
     assert np.linalg.norm(x - xo) <= 1e-7 * np.linalg.norm(xo)
 
 
@@ -344,9 +346,12 @@ def test_gpu_gmg_with_ilu_smoother_matches_oracle():
                  orc.matrix(permute_crs(prob.prolongation(l), perms[l], perms[l - 1])) if l else None,
                  orc.matrix(permute_crs(prob.restriction(l), perms[l - 1], perms[l])) if l else None)
     bp = np.empty(prob.num_dofs); bp[perms[3]] = prob.rhs()
-    xo, oko, ho = oracle.OSolver(orc, desc, lv[3][0], lv).apply(bp)
+    osol = oracle.OSolver(orc, desc, lv[3][0], lv)
+    xo, oko, ho = osol.apply(bp)
     assert ok and oko and abs(len(h) - len(ho)) <= 1
-    assert rel_hist_err(h, ho) < 1e-10
+    # the cycle reduces the defect by 1e-5 per step: the last step sits at 3e-12 x the start defect, where the reference's
+    # own history moves by ~1e-9 under a reordered sum (sens_tol measures it)
+    assert rel_hist_err(h, ho) < sens_tol(orc, osol, bp)
     assert np.linalg.norm(x - xo[perms[3]]) <= 1e-9 * np.linalg.norm(xo)
 
 
@@ -477,5 +482,6 @@ def test_gpu_bicgstab_periodic_restart_host_and_device_loop(rs):
     x1, ok1, h1 = ug.Solver(desc, prob.matrix(), flags=capi.FLAG_DEVICE_BICGSTAB).apply(prob.rhs())
     assert ok0 and ok1 and np.array_equal(h0, h1) and np.array_equal(x0, x1)
     orc = _best()
-    xo, oko, ho = oracle.OSolver(orc, desc, orc.matrix(prob.matrix())).apply(np.array(prob.rhs()))
-    assert oko and abs(len(h0) - len(ho)) <= 1 and rel_hist_err(h0, ho) < 1e-7
+    osol = oracle.OSolver(orc, desc, orc.matrix(prob.matrix()))
+    xo, oko, ho = osol.apply(np.array(prob.rhs()))
+    assert oko and abs(len(h0) - len(ho)) <= 1 and rel_hist_err(h0, ho) < sens_tol(orc, osol, np.array(prob.rhs()))

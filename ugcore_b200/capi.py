@@ -40,7 +40,7 @@ class ConvState(C.Structure):
 class MatrixInfo(C.Structure):
     _fields_ = [("nrows", c_i64), ("ncols", c_i64), ("nnz", c_i64), ("padded_nnz", c_i64), ("num_slices", c_i64),
                 ("device_bytes", c_i64), ("block", c_int), ("max_row_len", c_int), ("value_indexed", c_int),
-                ("num_distinct_values", c_int)]
+                ("num_distinct_values", c_int), ("x_staged", c_int), ("x_staged_runs", c_int), ("x_staged_doubles", c_i64)]
 
 
 class SolverDesc(C.Structure):
@@ -54,7 +54,7 @@ class SolverDesc(C.Structure):
 
 FIN_STORE, FIN_A_DIV_R, FIN_R_DIV_A, FIN_SQRT, FIN_CONV_START, FIN_CONV_UPDATE = range(6)
 SMOOTH_ADD_IN, SMOOTH_JACOBI, SMOOTH_ADD_OUT, SMOOTH_SC_ZERO = 1, 2, 4, 8
-MAT_DEFAULT, MAT_NO_COMPRESS = 0, 1
+MAT_DEFAULT, MAT_NO_COMPRESS, MAT_NO_XSTAGE = 0, 1, 2
 FLAG_HOST_SCALARS, FLAG_NO_GRAPH, FLAG_NO_FUSED_JACOBI, FLAG_FINAL_LEVEL_DEFECT, FLAG_RAP, FLAG_DEVICE_BICGSTAB, FLAG_DEVICE_LINEAR = 1, 2, 4, 8, 16, 32, 64
 
 # name -> (restype, argtypes); every symbol declared in include/ug4b200.h

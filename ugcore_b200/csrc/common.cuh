@@ -43,6 +43,7 @@ struct ug4b200_ctx {
 	bool tma_all = false;         // UG4B200_TMA_ALL=1: bulk-copy kernel also for unfused sweeps
 	bool no_tma = false;          // UG4B200_NO_TMA=1: register-staged SpMV everywhere (A/B measurements)
 	bool no_comp = false;         // UG4B200_NO_COMPRESS=1: never build / use the value-indexed entry stream
+	bool no_xs = false;           // UG4B200_NO_XSTAGE=1: never build / use the x-staged stream (A/B measurements)
 	bool pdl = false;             // UG4B200_PDL=1: programmatic dependent launch (next kernel's launch overlaps this one's tail)
 	// batched small operations: UG4B200_BATCH=0 disables, UG4B200_BATCH_MAX_ROWS sets the size limit
 	bool batch = true;
@@ -424,4 +425,15 @@ struct ug4b200_matrix {
 	unsigned int* vc = nullptr;       // [padded_nnz]
 	int* colbase = nullptr;           // [num_slices]
 	double* dict = nullptr;           // [ndict]
+	// x-staged copy of the value-indexed stream (spmv_tma.cuh: spmv1_xs_kernel): the words address x by its position
+	// in a per-slice staging buffer instead of by column; per slice a header {entry offset / 32, width, staged bytes,
+	// runs} and xs_rmax run slots {first column (even), doubles (even) | staging position << 16}.  Built when the
+	// dictionary has <= 256 values, rows have <= 27 entries and every slice's columns form <= xs_rmax runs of
+	// <= 384 doubles in total (any banded ordering of a structured grid); the kernel then reads x from shared memory.
+	bool xs = false;
+	int xs_rmax = 0;
+	int64_t xs_doubles = 0;
+	unsigned int* xw = nullptr;       // [padded_nnz]
+	int4* xs_hdr = nullptr;           // [num_slices]
+	int2* xs_runs = nullptr;          // [num_slices * xs_rmax]
 };

@@ -28,6 +28,7 @@ int ug4b200_ctx_create(int device, void* stream, ug4b200_ctx** out)
 	ctx->num_sms = prop.multiProcessorCount;
 	{ const char* e = getenv("UG4B200_NO_TMA"); ctx->no_tma = e && e[0] == '1'; }
 	{ const char* e = getenv("UG4B200_NO_COMPRESS"); ctx->no_comp = e && e[0] == '1'; }
+	{ const char* e = getenv("UG4B200_NO_XSTAGE"); ctx->no_xs = e && e[0] == '1'; }
 	{ const char* e = getenv("UG4B200_PDL"); ctx->pdl = e && e[0] == '1'; }
 	{ const char* e = getenv("UG4B200_TMA_ALL"); ctx->tma_all = e && e[0] == '1'; }
 	{ const char* e = getenv("UG4B200_TMA_MIN_SLICES"); if (e) ctx->tma_min_slices_per_warp = atoi(e); }
@@ -133,6 +134,9 @@ int ug4b200_alloc(ug4b200_ctx* ctx, size_t bytes, void** dptr)
 {
 	*dptr = nullptr;
 	if (bytes == 0) bytes = 8;
+	// every allocation is readable up to the next 16-byte boundary: the x-staging bulk copies of the SpMV kernels move
+	// whole 16-byte units and may read the 8 bytes behind a vector of odd length
+	bytes = (bytes + 15) & ~(size_t)15;
 	cudaError_t e = cudaMalloc(dptr, bytes);
 	if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return ug4b200_fail(ctx, UG4B200_ERR_NOMEM, "ug4b200_alloc: out of device memory"); }
 	UG_CUDA(ctx, e);

@@ -35,6 +35,8 @@ struct Sell {
 	int64_t nrows, num_slices;
 	// value-indexed stream (COMP kernels): word = column offset << 16 | dictionary index << vshift
 	const unsigned int* vc; const int* colbase; const double* dict; int ndict; int vshift;
+	// x-staged stream (spmv1_xs_kernel): word = staging position << 16 | dictionary index << 3
+	const unsigned int* xw; const int4* xs_hdr; const int2* xs_runs; int xs_rmax;
 };
 struct Fuse {
 	// FUSE_DOT (ar.nranks > 1: the last block also sums over the ranks through the peer windows)
@@ -336,7 +338,8 @@ inline int spmv_grid(const ug4b200_ctx*, int64_t num_slices)
 }
 
 inline Sell view(const ug4b200_matrix* A)
-{ return Sell{A->slice_ptr, A->rowlen, A->cols, A->vals, A->nrows, A->num_slices, A->vc, A->colbase, A->dict, A->ndict, A->vshift}; }
+{ return Sell{A->slice_ptr, A->rowlen, A->cols, A->vals, A->nrows, A->num_slices, A->vc, A->colbase, A->dict, A->ndict, A->vshift,
+              A->xw, A->xs_hdr, A->xs_runs, A->xs_rmax}; }
 
 #include "spmv_tma.cuh"
 
@@ -368,6 +371,13 @@ int launch_tma(ug4b200_ctx* ctx, const Sell& S, double* dest, const double* v, d
 {
 	if constexpr (COMP) {
 		typedef tma::VCfg C;
+		// x-staged stream: x operand through shared memory as well (needs a 16-byte aligned x: bulk copies)
+		if (S.xw != nullptr && ((uintptr_t)w & 15u) == 0) {
+			typedef tma::XCfg X;
+			static int cps = -1;
+			return launch_persistent(ctx, tma::spmv1_xs_kernel<BETAK, MODE, FUSE>, &cps, X::WPB * 32, X::SMEM_BYTES, X::WPB,
+			                         S, dest, v, alpha, beta, w, fz, used);
+		}
 		if (S.ndict <= tma::SDICT_MAX && S.vshift == 3) {
 			static int cps = -1;   // per instantiation
 			return launch_persistent(ctx, tma::spmv1_vi_kernel<BETAK, MODE, FUSE, true>, &cps, C::WPB * 32, C::SMEM_BYTES_SDICT, C::WPB,
@@ -388,7 +398,8 @@ int launch_scalar(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* dest, const
                   const double* w, const Fuse& fz)
 {
 	const int grid = spmv_grid(ctx, A->num_slices);
-	const Sell S = view(A);
+	Sell S = view(A);
+	if (ctx->no_xs) S.xw = nullptr;
 	bool used = false;
 	// measured (profiles/r01b): the bulk-copy kernel wins for the fused variants, the register-staged
 	// one for the plain sweep; the value-indexed stream always goes through the bulk-copy kernel when
@@ -644,6 +655,66 @@ int ug4b200_matrix_upload_crs(ug4b200_ctx* ctx, int block, int64_t nrows, int64_
 			if (!rc) rc = up((void**)&A->colbase, hcb.data(), sizeof(int) * hcb.size());
 			if (!rc) rc = up((void**)&A->dict, hdict.data(), sizeof(double) * hdict.size());
 			if (!rc) { A->comp = true; A->ndict = (int)hdict.size(); A->vshift = vshift; }
+			// ---- x-staged copy (spmv1_xs_kernel): per slice the sorted distinct columns are grouped into runs of
+			// consecutive columns (gaps of <= 2 merged, ends aligned to 16 bytes); the words then carry the position
+			// of their column in the concatenation of the runs.  Any banded numbering of a structured grid gives a
+			// handful of runs per slice (27-point operator, lexicographic: 9 runs of 34 columns).
+			if (!rc && !ctx->no_xs && !(flags & UG4B200_MAT_NO_XSTAGE) && hdict.size() <= (size_t)tma_xs_max_dict() && maxlen <= tma_xs_max_width()) {
+				const int RMAX = tma_xs_max_runs(), XCAP = tma_xs_max_doubles();
+				std::vector<unsigned int> hxw((size_t)pnnz, 0u);
+				std::vector<int4> hh((size_t)ns);
+				std::vector<int2> hr((size_t)ns * RMAX, make_int2(0, 0));
+				bool xok = true; int rmaxUsed = 1; int64_t xtotal = 0;
+#pragma omp parallel for schedule(static) reduction(&& : xok) reduction(max : rmaxUsed) reduction(+ : xtotal)
+				for (int64_t s = 0; s < ns; ++s) {
+					const int64_t base = sp[s];
+					const int width = (int)((sp[s + 1] - base) >> 5);
+					hh[s] = make_int4((int)(base >> 5), width, 0, 0);
+					std::vector<int> cs;
+					for (int l = 0; l < 32; ++l) {
+						const int64_t r = s * 32 + l;
+						if (r >= nrows) break;
+						for (int64_t p = rowptr[r]; p < rowptr[r + 1]; ++p) cs.push_back(cols[p]);
+					}
+					if (cs.empty()) continue;
+					std::sort(cs.begin(), cs.end());
+					cs.erase(std::unique(cs.begin(), cs.end()), cs.end());
+					int ra[64], rb[64], rd[64]; int nr = 0, tot = 0;   // run [ra, rb) staged at double index rd
+					bool fit = true;
+					for (size_t i = 0; i < cs.size(); ++i) {
+						const int c = cs[i];
+						if (nr > 0 && c < rb[nr - 1] + 3) { rb[nr - 1] = (c + 2) & ~1; continue; }   // extend (gap <= 2: cheaper than a new copy)
+						if (nr == RMAX) { fit = false; break; }
+						ra[nr] = c & ~1; rb[nr] = (c + 2) & ~1; ++nr;
+					}
+					if (fit) for (int q = 0; q < nr; ++q) { rd[q] = tot; tot += rb[q] - ra[q]; }
+					if (!fit || tot > XCAP) { xok = false; continue; }
+					for (int q = 0; q < nr; ++q) hr[(size_t)s * RMAX + q] = make_int2(ra[q], (rb[q] - ra[q]) | (rd[q] << 16));
+					hh[s].z = tot * 8; hh[s].w = nr;
+					if (nr > rmaxUsed) rmaxUsed = nr;
+					xtotal += tot;
+					for (int l = 0; l < 32; ++l) {
+						const int64_t r = s * 32 + l;
+						if (r >= nrows) break;
+						int q = 0;
+						for (int64_t p = rowptr[r], k = 0; p < rowptr[r + 1]; ++p, ++k) {
+							while (cols[p] >= rb[q]) ++q;     // columns ascend inside a row, runs ascend
+							uint64_t bits; std::memcpy(&bits, &vals[p], 8);
+							hxw[base + k * 32 + l] = ((unsigned int)(rd[q] + cols[p] - ra[q]) << 16) | ((unsigned int)dict.find(bits)->second << 3);
+						}
+					}
+				}
+				if (xok) {
+					// keep only the run slots any slice uses (stride of the run table)
+					std::vector<int2> hr2((size_t)ns * rmaxUsed);
+					for (int64_t s2 = 0; s2 < ns; ++s2) for (int q = 0; q < rmaxUsed; ++q) hr2[(size_t)s2 * rmaxUsed + q] = hr[(size_t)s2 * RMAX + q];
+					if (!rc) rc = up((void**)&A->xw, hxw.data(), sizeof(unsigned int) * hxw.size());
+					if (!rc) rc = up((void**)&A->xs_hdr, hh.data(), sizeof(int4) * hh.size());
+					if (!rc) rc = up((void**)&A->xs_runs, hr2.data(), sizeof(int2) * hr2.size());
+					if (!rc) { A->xs = true; A->xs_rmax = rmaxUsed; A->xs_doubles = xtotal; }
+					if (!rc) { const cudaError_t e = cudaStreamSynchronize(ctx->stream); if (e != cudaSuccess) rc = ug4b200_fail(ctx, UG4B200_ERR_CUDA, cudaGetErrorString(e)); }
+				}
+			}
 		}
 	}
 	if (rc) { ug4b200_matrix_destroy(ctx, A); return rc; }
@@ -658,6 +729,7 @@ int ug4b200_matrix_destroy(ug4b200_ctx* ctx, ug4b200_matrix* A)
 	if (ctx) { ug_batch_flush(ctx); cudaStreamSynchronize(ctx->stream); }
 	cudaFree(A->slice_ptr); cudaFree(A->rowlen); cudaFree(A->diagpos); cudaFree(A->cols); cudaFree(A->vals);
 	cudaFree(A->vc); cudaFree(A->colbase); cudaFree(A->dict);
+	cudaFree(A->xw); cudaFree(A->xs_hdr); cudaFree(A->xs_runs);
 	delete A;
 	return UG4B200_OK;
 }
@@ -668,6 +740,7 @@ int ug4b200_matrix_get_info(const ug4b200_matrix* A, ug4b200_matrix_info* info)
 	info->num_slices = A->num_slices; info->device_bytes = (int64_t)A->device_bytes; info->block = A->block;
 	info->max_row_len = A->max_row_len;
 	info->value_indexed = A->comp ? 1 : 0; info->num_distinct_values = A->ndict;
+	info->x_staged = A->xs ? 1 : 0; info->x_staged_runs = A->xs_rmax; info->x_staged_doubles = A->xs_doubles;
 	return UG4B200_OK;
 }
 

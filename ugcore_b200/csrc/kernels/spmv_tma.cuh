@@ -488,4 +488,224 @@ spmv1_vi_kernel(Sell A, double* dest, const double* v, double alpha, double beta
 	if (FUSE == FUSE_DOT) ug_block_reduce_fin(dot, fz.partials, fz.counter, fz.fin, fz.ar);
 }
 
+
+// ---------------------------------------------------------------- x-staged value-indexed stream
+// spmv1_vi_kernel is latency-bound on its x-gathers (ncu, profiles/r02c: 60 % of all stall samples are
+// long-scoreboard waits on LDG results, 24 warps/SM at 80 registers cannot cover them; the kernel stays at
+// ~0.81 of the copy bandwidth).  Here NOTHING on the consumer side waits for global memory inside a slice:
+// besides the entry words, the producer also brings the slice's x operand into shared memory — the slice's
+// distinct columns form a handful of runs of consecutive columns (27-point operator, banded numbering: 9 runs
+// of 34), each one bulk copy (cp.async.bulk, >= 16 bytes, 16-byte aligned) landing on the same mbarrier as
+// the words.  The words address x by its position in that staging buffer, so an entry is
+//     LDS.32 word ; IMAD.HI (staging address) ; LDS.64 x ; LOP3 (dictionary address) ; LDS.64 value ; DMUL ; DADD
+// with shared-memory latencies only.  Bytes in flight are set by the ring (independent of registers), and the
+// arithmetic per row is unchanged: ascending column order, separate multiply and add.
+// Per slice metadata: header {entry offset / 32, width, staged bytes, runs} and xs_rmax run slots
+// {first column (even), doubles (even) | staging position << 16} (built at upload, spmv.cu).
+#ifndef UG_XS_NST
+#define UG_XS_NST 2
+#endif
+#ifndef UG_XS_WPB
+#define UG_XS_WPB 8
+#endif
+#ifndef UG_XS_MINCTA
+#define UG_XS_MINCTA 2
+#endif
+#ifndef UG_XS_XCAP
+#define UG_XS_XCAP 384
+#endif
+struct XCfg {
+	static constexpr int UB = 9, NB = 3, KC = UB * NB, NST = UG_XS_NST, WPB = UG_XS_WPB;
+	static constexpr int XCAP = UG_XS_XCAP;              // doubles of x per slice
+	static constexpr int RMAX = 16;                      // run slots per slice (<= 32: one lane issues one run)
+	static constexpr int DICT_MAX = 256;                 // dictionary entries (2 KB, at a 2 KB-aligned shared address)
+	static constexpr int WORD_BYTES = KC * 128;
+	static constexpr int STAGE_BYTES = WORD_BYTES + XCAP * 8;
+	static constexpr int WARP_BYTES = NST * STAGE_BYTES;
+	static constexpr int RING_BYTES = WPB * WARP_BYTES;
+	static constexpr int BAR_BYTES = ((WPB * NST * 8 + 127) / 128) * 128;
+	static constexpr int SMEM_BYTES = RING_BYTES + BAR_BYTES + 2 * DICT_MAX * 8;
+};
+
+template <int BETAK, int MODE, int FUSE>
+__global__ void __launch_bounds__(XCfg::WPB * 32, UG_XS_MINCTA)
+spmv1_xs_kernel(Sell A, double* dest, const double* v, double alpha, double beta, const double* __restrict__ w,
+                Fuse fz, const int* guard)
+{
+	if (ug_guarded(guard)) return;
+	typedef XCfg C;
+	constexpr int UB = C::UB, NB = C::NB, NST = C::NST, XWPB = C::WPB;
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const uint32_t smem0 = smem_base_opaque(smem_raw);
+	const uint32_t ring_s = smem0 + (uint32_t)wid * C::WARP_BYTES;             // [NST]{words [KC][32], x [XCAP]}
+	const uint32_t bars = smem0 + C::RING_BYTES + (uint32_t)wid * NST * 8;     // [NST] mbarriers
+	const uint32_t sdict_s = (smem0 + C::RING_BYTES + C::BAR_BYTES + 2047u) & ~2047u;
+	const int gwarp = (int)blockIdx.x * XWPB + wid;
+	const int nwarps = (int)gridDim.x * XWPB;
+	const int nslices = (int)A.num_slices, nrows = (int)A.nrows;
+	const int rmax = A.xs_rmax;
+	for (int i = threadIdx.x; i < A.ndict; i += blockDim.x)
+		asm volatile("st.shared.f64 [%0], %1;" ::"r"(sdict_s + (uint32_t)i * 8u), "d"(A.dict[i]) : "memory");
+	__syncthreads();
+	if (lane == 0) {
+#pragma unroll
+		for (int i = 0; i < NST; ++i) mbar_init(bars + i * 8, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncwarp();
+
+	// ---- producer: the whole warp issues (lane 0: words, lane q < runs: run q); descriptors of the NEXT slice to
+	// produce are requested while the current one is issued, so that no production starts with a global round trip
+	struct Desc { int4 h; int2 r; };
+	auto fetch_desc = [&](int sl) {
+		Desc d; d.h = make_int4(0, 0, 0, 0); d.r = make_int2(0, 0);
+		if (sl < nslices) {
+			d.h = __ldg(A.xs_hdr + sl);
+			if (lane < rmax) d.r = __ldg(A.xs_runs + (int64_t)sl * rmax + lane);
+		}
+		return d;
+	};
+	int ps = gwarp;
+	Desc pd = fetch_desc(ps);
+	// issue the slice described by pd into ring stage st; lane 0 posts the expected byte count BEFORE any copy is issued
+	auto issue = [&](int st) {
+		const uint32_t bar = bars + st * 8;
+		const uint32_t dst = ring_s + (uint32_t)st * C::STAGE_BYTES;
+		const int width = pd.h.y, xbytes = pd.h.z, nruns = pd.h.w;
+		if (lane == 0) {
+			if (width > 0) mbar_expect_tx(bar, (uint32_t)(width * 128 + xbytes));
+			else mbar_arrive(bar);
+		}
+		__syncwarp();
+		if (lane == 0 && width > 0) bulk_g2s(dst, A.xw + (int64_t)pd.h.x * 32, (uint32_t)width * 128u, bar);
+		if (lane < nruns) {
+			const int len = pd.r.y & 0xffff, pos = pd.r.y >> 16;
+			bulk_g2s(dst + C::WORD_BYTES + (uint32_t)pos * 8u, w + pd.r.x, (uint32_t)len * 8u, bar);
+		}
+	};
+	auto produce = [&](int st) {
+		issue(st);
+		ps += nwarps;
+		pd = fetch_desc(ps);
+	};
+	{
+		// prologue: the descriptors of the first NST slices are requested together (one round trip, not NST)
+		Desc d1 = fetch_desc(gwarp + nwarps);
+		if (ps < nslices) { issue(0); ps += nwarps; pd = d1; }
+#pragma unroll
+		for (int i = 1; i < NST; ++i) {
+			if (ps < nslices) produce(i);
+		}
+	}
+
+	// ---- consumer
+	struct Meta { int s, width, len; double acc0; };
+	auto fetch_meta = [&](int sl) {
+		Meta m; m.s = sl; m.width = 0; m.len = 0; m.acc0 = 0.0;
+		if (sl < nslices) {
+			m.width = __ldg(&A.xs_hdr[sl].y);
+			m.len = A.rowlen[sl * 32 + lane];
+			if (MODE == MODE_INPLACE) { if (sl * 32 + lane < nrows) m.acc0 = dest[sl * 32 + lane]; }
+			else if (MODE == MODE_GENERAL) { if (sl * 32 + lane < nrows) m.acc0 = v[sl * 32 + lane]; }
+		}
+		return m;
+	};
+	Meta cur = fetch_meta(gwarp);
+	int stage = 0; uint32_t phase = 0;
+	double dot = 0.0;
+	const UgPushDev* push = (FUSE == FUSE_JACOBI || FUSE == FUSE_RESTRICT_JACOBI) ? fz.push : nullptr;
+	const unsigned long long pe = push ? *(volatile unsigned long long*)push->epoch + 1ull : 0ull;
+	while (cur.s < nslices) {
+		const Meta nxt = fetch_meta(cur.s + nwarps);
+		const int row = cur.s * 32 + lane;
+		const bool live = row < nrows;
+		const int len = cur.len;
+		const int width = cur.width;
+		const unsigned int pmask = push ? push->rowmask[cur.s] : 0u;
+		const int minlen = __reduce_min_sync(0xffffffffu, len);
+		double acc = 0.0, own = 0.0, scv = 0.0, dinv = 0.0;
+		if (MODE == MODE_INPLACE) acc = cur.acc0;
+		else if (MODE == MODE_GENERAL) acc = alpha * cur.acc0;
+		// per-row streams: requested before the slice is consumed, used after it
+		if (FUSE == FUSE_DOT) { if (live) own = w[row]; }
+		if (FUSE == FUSE_RESTRICT_JACOBI && live) { dinv = fz.diaginv[row]; if (len == 0) own = dest[row]; }
+		if (FUSE == FUSE_JACOBI && live) {
+			if (fz.flags & UG4B200_SMOOTH_ADD_IN) own = w[row];
+			if ((fz.flags & (UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_ADD_OUT)) && !(fz.flags & UG4B200_SMOOTH_SC_ZERO)) scv = fz.sc[row];
+			if (fz.flags & UG4B200_SMOOTH_JACOBI) dinv = fz.diaginv[row];
+		}
+		if (width > 0) {
+			mbar_wait(bars + stage * 8, phase);
+			const uint32_t cs = ring_s + (uint32_t)stage * C::STAGE_BYTES + (uint32_t)lane * 4u;
+			const uint32_t xs = ring_s + (uint32_t)stage * C::STAGE_BYTES + C::WORD_BYTES;
+#pragma unroll
+			for (int j = 0; j < NB; ++j) {
+				const int kb = j * UB;
+				if (kb < width) {
+					if (kb + UB <= minlen) {
+#pragma unroll
+						for (int u = 0; u < UB; ++u) {
+							const uint32_t e = lds_u32(cs + (uint32_t)(kb + u) * 128u);
+							const double x = lds_f64(__umulhi(e, 1u << 19) + xs);
+							const double t = mulbeta<BETAK>(lds_f64((e & 0x7f8u) | sdict_s), beta) * x;
+							if ((MODE == MODE_ASSIGN || MODE == MODE_ASSIGN_SKIP_EMPTY) && j == 0 && u == 0) acc = t;
+							else acc = acc + t;
+						}
+					} else {
+#pragma unroll
+						for (int u = 0; u < UB; ++u) {
+							if (kb + u < len) {
+								const uint32_t e = lds_u32(cs + (uint32_t)(kb + u) * 128u);
+								const double x = lds_f64(__umulhi(e, 1u << 19) + xs);
+								const double t = mulbeta<BETAK>(lds_f64((e & 0x7f8u) | sdict_s), beta) * x;
+								if ((MODE == MODE_ASSIGN || MODE == MODE_ASSIGN_SKIP_EMPTY) && kb + u == 0) acc = t;
+								else acc = acc + t;
+							}
+						}
+					}
+				}
+			}
+		} else {
+			mbar_wait(bars + stage * 8, phase);   // empty slice: the producer arrived without a copy
+		}
+		// every lane is done with the stage: refill it
+		__syncwarp();
+		if (ps < nslices) produce(stage);
+		if (++stage == NST) { stage = 0; phase ^= 1u; }
+		if (FUSE == FUSE_JACOBI) {
+			if (live) {
+				dest[row] = acc;
+				if (fz.flags & UG4B200_SMOOTH_ADD_IN) scv = scv + own;
+				if (fz.flags & UG4B200_SMOOTH_JACOBI) {
+					const double st = dinv * acc;
+					fz.st_out[row] = st;
+					if ((pmask >> lane) & 1u) ug_push_row(push, pe, cur.s, lane, pmask, st);
+					if (fz.flags & UG4B200_SMOOTH_ADD_OUT) scv = scv + st;
+				}
+				if (fz.flags & (UG4B200_SMOOTH_ADD_IN | UG4B200_SMOOTH_ADD_OUT)) fz.sc[row] = scv;
+			}
+		} else if (FUSE == FUSE_RESTRICT_JACOBI) {
+			if (live) {
+				double dv = own;
+				if (len > 0) { dest[row] = acc; dv = acc; }
+				const double st = dinv * dv;
+				fz.st_out[row] = st;
+				if ((pmask >> lane) & 1u) ug_push_row(push, pe, cur.s, lane, pmask, st);
+			}
+		} else {
+			if (live && (MODE != MODE_ASSIGN_SKIP_EMPTY || len > 0)) dest[row] = acc;
+			if (FUSE == FUSE_DOT && live) dot += acc * own;
+		}
+		cur = nxt;
+	}
+	if (FUSE == FUSE_DOT) ug_block_reduce_fin(dot, fz.partials, fz.counter, fz.fin, fz.ar);
+}
+
 } // namespace tma
+
+// limits of the x-staged format, for the builder in spmv.cu
+inline int tma_xs_max_dict() { return tma::XCfg::DICT_MAX; }
+inline int tma_xs_max_width() { return tma::XCfg::KC; }
+inline int tma_xs_max_runs() { return tma::XCfg::RMAX; }
+inline int tma_xs_max_doubles() { return tma::XCfg::XCAP; }
