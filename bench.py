@@ -413,7 +413,11 @@ def run_ours(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
     torch.cuda.set_device(local_rank)
-    stream = torch.cuda.current_stream()
+    # ONE explicit stream for torch and for the library: torch's default stream has handle 0, which the library would
+    # take as "create your own (non-blocking) stream" — the CUDA events below would then sit on an idle stream and
+    # x_dev.zero_() would race with the solver's first copy (seen at 257^3: a start defect of 5.3 instead of 0.0105)
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
     S.host_init(local_rank, C.c_void_p(stream.cuda_stream))
     ctx = S.host_ctx()
     dev = capi.dev

@@ -184,6 +184,10 @@ int ug4b200_cg_update_ds(ug4b200_ctx* ctx, int64_t n, double* x, const double* p
 /* generic one-thread scalar program: out = (a/b)*(c/d) with NULL operands = 1 (BiCGStab beta) */
 int ug4b200_scalar_ratio_ds(ug4b200_ctx* ctx, double* out, const double* a, const double* b, const double* c,
                             const double* d);
+/* the same with the breakdown exits of BiCGStab (bicgstab.h:216-224 "rhoOld == 0", :374-381 "omega == 0"): a zero
+ * divisor b or d ends the iteration (conv->done = 1, status 4) before anything is overwritten with inf / NaN */
+int ug4b200_scalar_ratio_conv_ds(ug4b200_ctx* ctx, double* out, const double* a, const double* b, const double* c,
+                                 const double* d, ug4b200_conv_state* conv);
 /* apply a finaliser to a value that already sits on the device (after an all-reduce) */
 int ug4b200_scalar_fin_ds(ug4b200_ctx* ctx, const double* r_dev, ug4b200_fin fin);
 int ug4b200_conv_init(ug4b200_ctx* ctx, ug4b200_conv_state* dev_state, int max_steps, double min_defect,

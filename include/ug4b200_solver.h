@@ -26,12 +26,14 @@ enum { UG4B200_ILU_ORDER_NATURAL = 0,    /* no ordering: level-scheduled triangu
        UG4B200_ILU_ORDER_CMK = 1,        /* set_sort(true): NativeCuthillMcKeeOrdering; level-scheduled */
        UG4B200_ILU_ORDER_MULTICOLOR = 2  /* greedy multicolour ordering: one launch per colour, bit-identical to the
                                             reference's ILU applied in that ordering */ };
-enum { UG4B200_FLAG_HOST_SCALARS = 1,   /* CG with host scalars (reference-shaped loop, one sync per dot) */
+enum { UG4B200_FLAG_HOST_SCALARS = 1,   /* CG / BiCGStab / LinearSolver as reference-shaped host loops (one sync per dot / norm) instead of
+                                           the default: scalars and convergence state on the device, one CUDA graph per iteration */
        UG4B200_FLAG_NO_GRAPH = 2,       /* do not capture the Krylov iteration into a CUDA graph */
        UG4B200_FLAG_NO_FUSED_JACOBI = 4,/* V-cycle with separate Jacobi / SpMV / AXPY launches */
        UG4B200_FLAG_FINAL_LEVEL_DEFECT = 8, /* also do the reference's unused top-level defect update */
-       UG4B200_FLAG_DEVICE_LINEAR = 64,   /* LinearSolver with the convergence state on the device + CUDA graph; default: host loop */
-       UG4B200_FLAG_DEVICE_BICGSTAB = 32, /* BiCGStab with device-resident scalars + CUDA graph (like CG); default: host scalars */
+       UG4B200_FLAG_DEVICE_LINEAR = 64,   /* accepted, no effect: the device-resident LinearSolver is the default since round 2 */
+       UG4B200_FLAG_DEVICE_BICGSTAB = 32, /* accepted, no effect: the device-resident BiCGStab is the default since round 2
+                                             (measured 33.3 vs 38.6 ms per solve on configs[3] at 129^3, identical histories) */
        UG4B200_FLAG_RAP = 16            /* gmg:set_rap(true): level operators below the top level are the Galerkin
                                            products R A P (mg_solver_impl.hpp:828-1013), computed on the host at init;
                                            ug4b200_solver_set_level then takes rowptr == NULL on those levels */ };

@@ -4,7 +4,7 @@
 set -u
 mkdir -p gpurun_out
 t0=$SECONDS
-timeout 600 python -m pytest tests/test_gpu_tma.py tests/test_gpu_kernels.py tests/test_gpu_solver.py -m gpu -q -x --timeout 120 2>&1 | tail -15 | tee gpurun_out/tests_xs.log
+timeout 600 python -m pytest tests/test_gpu_tma.py tests/test_gpu_kernels.py tests/test_gpu_solver.py tests/test_gpu_p2p.py -m gpu -q -x --timeout 120 2>&1 | tail -15 | tee gpurun_out/tests_xs.log
 {
 for r in 7 6; do
   echo "--- default refs $r"; timeout 120 python scripts/kbench.py $r 2>&1 | tail -1 | cut -c1-700
@@ -16,5 +16,5 @@ for r in 7 6; do
 done
 } | tee gpurun_out/variants_xs.txt
 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_xs.json 2> gpurun_out/bench_xs.err; cut -c1-600 gpurun_out/bench_xs.json; tail -3 gpurun_out/bench_xs.err
-timeout 600 python bench.py --scaling strong --refs 5 --steps 3 --warmup 3 > gpurun_out/bench_strong_r5.json 2> gpurun_out/bench_strong_r5.err; cut -c1-300 gpurun_out/bench_strong_r5.json; tail -3 gpurun_out/bench_strong_r5.err
+timeout 800 python bench.py --scaling strong --steps 5 --warmup 3 > gpurun_out/bench_strong_n1.json 2> gpurun_out/bench_strong_n1.err; cut -c1-300 gpurun_out/bench_strong_n1.json; tail -3 gpurun_out/bench_strong_n1.err
 echo "total: $((SECONDS-t0)) s"

@@ -305,7 +305,7 @@ def test_reinit_with_a_changed_matrix_recaptures_the_graph(solver, precond):
         pc = {"jac": {"type": "jac", "damp": 0.66}, "gs": {"type": "sgs" if solver == "cg" else "gs"},
               "ilu": {"type": "ilu", "ordering": "multicolor"}}[precond]
         desc = {"type": solver, "precond": pc, "convCheck": cc}
-    flags = capi.FLAG_DEVICE_BICGSTAB | capi.FLAG_DEVICE_LINEAR
+    flags = 0      # device-resident loops + CUDA graphs are the default for CG, BiCGStab and LinearSolver
     # second matrix: same pattern, other values (2 A + 25 % more diagonal); third: another pattern at the same n (the
     # explicit zeros that the Dirichlet rows keep, sparsematrix_util.h:850-861, removed: nnz and the slices change)
     rows = np.repeat(np.arange(A0.nrows), np.diff(A0.rowptr))
@@ -359,3 +359,25 @@ def test_reinit_with_a_changed_matrix_recaptures_the_graph(solver, precond):
         assert abs(len(hg) - len(ho)) <= 1, (len(hg), len(ho))
         assert rel_hist_err(hg, ho) < 1e-8, (hg, ho)    # a stale graph gives O(1) errors; exact parity is other tests' job
         assert np.linalg.norm(xg - xo) <= 1e-7 * np.linalg.norm(xo)
+
+
+def test_bicgstab_breakdown_ends_the_solve_like_the_reference():
+    """(v, r0) == 0 (bicgstab.h:276-281: "return false"): a matrix that maps the first search direction to 0.  Host loop,
+    device-resident loop and oracle all report failure, none of them leaves inf / NaN in x (the device loop flags the
+    breakdown in the finaliser that would divide, before x is updated; the guard turns the rest of the graph into no-ops)."""
+    import oracle
+    import ugcore_b200 as ug
+    from ugcore_b200 import capi
+    from ugcore_b200.problems import Crs
+    n = 96
+    A = Crs(n, n, 1, np.arange(n + 1, dtype=np.int64), np.arange(n, dtype=np.int32), np.zeros(n))
+    b = np.linspace(1.0, 2.0, n)
+    desc = {"type": "bicgstab", "precond": None, "convCheck": {"iterations": 20, "absolute": 1e-12, "reduction": 1e-8}}
+    orc = _best_oracle()
+    xo, oko, ho = oracle.OSolver(orc, desc, orc.matrix(A)).apply(b)
+    assert not oko
+    for flags in (capi.FLAG_HOST_SCALARS, 0, capi.FLAG_NO_GRAPH):
+        x, ok, h = ug.Solver(desc, A, flags=flags).apply(b)
+        assert not ok, flags
+        assert np.isfinite(x).all() and np.array_equal(x, xo), flags
+        assert len(h) == len(ho) and h[0] == pytest.approx(ho[0], rel=1e-14), flags

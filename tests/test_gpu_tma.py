@@ -13,22 +13,22 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module", params=["x_staged", "value_indexed", "plain"])
 def tma_ctx(request):
-    """x_staged: value-indexed words + x operand staged in shared memory (spmv1_xs_kernel, the default for matrices whose
-    slices touch a few runs of consecutive columns); value_indexed: UG4B200_NO_XSTAGE=1 (spmv1_vi_kernel, x gathered from
-    global memory); plain: UG4B200_NO_COMPRESS=1 (spmv1_tma_kernel, 12 B per entry)."""
+    """x_staged: UG4B200_XSTAGE=1 — value-indexed words + x operand staged in shared memory (spmv1_xs_kernel; by default
+    only built where the 16-bit column window of the value-indexed stream does not fit, e.g. 257^3); value_indexed:
+    spmv1_vi_kernel, x gathered from global memory; plain: UG4B200_NO_COMPRESS=1 (spmv1_tma_kernel, 12 B per entry)."""
     from ugcore_b200 import capi
     os.environ["UG4B200_TMA_MIN_SLICES"] = "0"
     if request.param == "plain":
         os.environ["UG4B200_NO_COMPRESS"] = "1"
-    if request.param == "value_indexed":
-        os.environ["UG4B200_NO_XSTAGE"] = "1"
+    if request.param == "x_staged":
+        os.environ["UG4B200_XSTAGE"] = "1"
     ctx = C.c_void_p()
     try:
         capi.check(capi.dev.ug4b200_ctx_create(0, None, C.byref(ctx)))
     finally:
         del os.environ["UG4B200_TMA_MIN_SLICES"]
         os.environ.pop("UG4B200_NO_COMPRESS", None)
-        os.environ.pop("UG4B200_NO_XSTAGE", None)
+        os.environ.pop("UG4B200_XSTAGE", None)
     ctx.mode = request.param
     yield ctx
     capi.dev.ug4b200_ctx_destroy(ctx)

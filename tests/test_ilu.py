@@ -424,8 +424,8 @@ def test_gpu_device_resident_bicgstab_equals_host_loop(graph):
              "maxsteps": {"type": "bicgstab", "precond": None, "convCheck": {"iterations": 7, "absolute": 1e-12, "reduction": 1e-30}}}
     for name, desc in cases.items():
         mk = (lambda fl: ug.Solver.from_problem(desc, prob, flags=fl)) if name == "gmg_gs" else (lambda fl: ug.Solver(desc, prob.matrix(), flags=fl))
-        x0, ok0, h0 = mk(0).apply(prob.rhs())
-        x1, ok1, h1 = mk(capi.FLAG_DEVICE_BICGSTAB | graph).apply(prob.rhs())
+        x0, ok0, h0 = mk(capi.FLAG_HOST_SCALARS).apply(prob.rhs())
+        x1, ok1, h1 = mk(graph).apply(prob.rhs())
         assert ok0 == ok1 and ok0 == (name != "maxsteps"), name
         assert np.array_equal(h0, h1) and np.array_equal(x0, x1), name
 
@@ -444,8 +444,8 @@ def test_gpu_device_resident_linear_solver_equals_host_loop(graph):
              "none": {"type": "linear", "precond": None, "convCheck": {"iterations": 5, "absolute": 1e-12, "reduction": 1e-6}}}
     for name, desc in cases.items():
         mk = (lambda fl: ug.Solver.from_problem(desc, prob, flags=fl)) if name.startswith("gmg") else (lambda fl: ug.Solver(desc, prob.matrix(), flags=fl))
-        x0, ok0, h0 = mk(0).apply(prob.rhs())
-        x1, ok1, h1 = mk(capi.FLAG_DEVICE_LINEAR | graph).apply(prob.rhs())
+        x0, ok0, h0 = mk(capi.FLAG_HOST_SCALARS).apply(prob.rhs())
+        x1, ok1, h1 = mk(graph).apply(prob.rhs())
         assert ok0 == ok1 and ok0 == (name not in ("jac", "none")), name
         assert np.array_equal(h0, h1) and np.array_equal(x0, x1), name
 
@@ -478,8 +478,8 @@ def test_gpu_bicgstab_periodic_restart_host_and_device_loop(rs):
     from ugcore_b200 import capi
     prob = pr.Problem(dim=3, num_refs=3, problem=pr.CONVDIFF, eps=1e-2)
     desc = _restart_desc(rs)
-    x0, ok0, h0 = ug.Solver(desc, prob.matrix()).apply(prob.rhs())
-    x1, ok1, h1 = ug.Solver(desc, prob.matrix(), flags=capi.FLAG_DEVICE_BICGSTAB).apply(prob.rhs())
+    x0, ok0, h0 = ug.Solver(desc, prob.matrix(), flags=capi.FLAG_HOST_SCALARS).apply(prob.rhs())
+    x1, ok1, h1 = ug.Solver(desc, prob.matrix()).apply(prob.rhs())
     assert ok0 and ok1 and np.array_equal(h0, h1) and np.array_equal(x0, x1)
     orc = _best()
     osol = oracle.OSolver(orc, desc, orc.matrix(prob.matrix()))

@@ -105,6 +105,7 @@ DEV_API = {
     "ug4b200_vec_scale_add2_norm_ds": (c_int, [c_vp, c_i64, c_vp, Coef, c_vp, Coef, c_vp, Fin]),
     "ug4b200_cg_update_ds": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, Fin]),
     "ug4b200_scalar_ratio_ds": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "ug4b200_scalar_ratio_conv_ds": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ug4b200_scalar_fin_ds": (c_int, [c_vp, c_vp, Fin]),
     "ug4b200_conv_init": (c_int, [c_vp, c_vp, c_int, c_dbl, c_dbl, c_vp, c_int]),
     "ug4b200_matrix_upload_crs": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_int, C.POINTER(c_vp)]),

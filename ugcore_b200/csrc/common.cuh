@@ -44,6 +44,7 @@ struct ug4b200_ctx {
 	bool no_tma = false;          // UG4B200_NO_TMA=1: register-staged SpMV everywhere (A/B measurements)
 	bool no_comp = false;         // UG4B200_NO_COMPRESS=1: never build / use the value-indexed entry stream
 	bool no_xs = false;           // UG4B200_NO_XSTAGE=1: never build / use the x-staged stream (A/B measurements)
+	bool force_xs = false;        // UG4B200_XSTAGE=1: build and use it also where the value-indexed stream applies (tests)
 	bool pdl = false;             // UG4B200_PDL=1: programmatic dependent launch (next kernel's launch overlaps this one's tail)
 	// batched small operations: UG4B200_BATCH=0 disables, UG4B200_BATCH_MAX_ROWS sets the size limit
 	bool batch = true;
@@ -210,6 +211,8 @@ __device__ inline void ug_apply_fin(double r, const ug4b200_fin& f)
 			break;
 		case UG4B200_FIN_R_DIV_A: {
 			const double av = *f.a;
+			// with a convergence state attached a zero divisor is a breakdown (BiCGStab "tt == 0", bicgstab.h:344-352)
+			if (av == 0.0 && f.conv) { f.conv->status = 4; f.conv->done = 1; }
 			*f.out2 = r / av;
 			if (f.out) *f.out = r;
 			break;

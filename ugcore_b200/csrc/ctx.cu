@@ -29,6 +29,7 @@ int ug4b200_ctx_create(int device, void* stream, ug4b200_ctx** out)
 	{ const char* e = getenv("UG4B200_NO_TMA"); ctx->no_tma = e && e[0] == '1'; }
 	{ const char* e = getenv("UG4B200_NO_COMPRESS"); ctx->no_comp = e && e[0] == '1'; }
 	{ const char* e = getenv("UG4B200_NO_XSTAGE"); ctx->no_xs = e && e[0] == '1'; }
+	{ const char* e = getenv("UG4B200_XSTAGE"); ctx->force_xs = e && e[0] == '1'; }
 	{ const char* e = getenv("UG4B200_PDL"); ctx->pdl = e && e[0] == '1'; }
 	{ const char* e = getenv("UG4B200_TMA_ALL"); ctx->tma_all = e && e[0] == '1'; }
 	{ const char* e = getenv("UG4B200_TMA_MIN_SLICES"); if (e) ctx->tma_min_slices_per_warp = atoi(e); }

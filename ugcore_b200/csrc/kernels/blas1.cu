@@ -158,11 +158,13 @@ inline int reduce_grid(const ug4b200_ctx* ctx, int64_t n)
 }
 
 __global__ void scalar_ratio_kernel(double* out, const double* a, const double* b, const double* c, const double* d,
-                                    const int* guard)
+                                    ug4b200_conv_state* conv, const int* guard)
 {
 	if (ug_guarded(guard)) return;
 	// BiCGStab: beta = (rho/rhoOld) * (alpha/omega)   (bicgstab.h:227)
 	const double n1 = a ? *a : 1.0, d1 = b ? *b : 1.0, n2 = c ? *c : 1.0, d2 = d ? *d : 1.0;
+	// breakdown (bicgstab.h: "rhoOld == 0" / "omega == 0" -> return false): end the iteration before anything is updated
+	if (conv && ((b && d1 == 0.0) || (d && d2 == 0.0))) { conv->status = 4; conv->done = 1; return; }
 	double r = n1;
 	if (b) r = n1 / d1;
 	if (c || d) { double s = n2; if (d) s = n2 / d2; r = r * s; }
@@ -277,7 +279,13 @@ int ug4b200_vec_norm(ug4b200_ctx* ctx, int64_t n, const double* a, double* host_
 int ug4b200_scalar_ratio_ds(ug4b200_ctx* ctx, double* out, const double* a, const double* b, const double* c,
                             const double* d)
 {
-	UG_LAUNCH(ctx, scalar_ratio_kernel, 1, 1, 0, out, a, b, c, d, ctx->guard);
+	UG_LAUNCH(ctx, scalar_ratio_kernel, 1, 1, 0, out, a, b, c, d, (ug4b200_conv_state*)nullptr, ctx->guard);
+	return UG4B200_OK;
+}
+int ug4b200_scalar_ratio_conv_ds(ug4b200_ctx* ctx, double* out, const double* a, const double* b, const double* c,
+                                 const double* d, ug4b200_conv_state* conv)
+{
+	UG_LAUNCH(ctx, scalar_ratio_kernel, 1, 1, 0, out, a, b, c, d, conv, ctx->guard);
 	return UG4B200_OK;
 }
 int ug4b200_scalar_fin_ds(ug4b200_ctx* ctx, const double* r_dev, ug4b200_fin fin)

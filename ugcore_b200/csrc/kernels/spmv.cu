@@ -371,13 +371,6 @@ int launch_tma(ug4b200_ctx* ctx, const Sell& S, double* dest, const double* v, d
 {
 	if constexpr (COMP) {
 		typedef tma::VCfg C;
-		// x-staged stream: x operand through shared memory as well (needs a 16-byte aligned x: bulk copies)
-		if (S.xw != nullptr && ((uintptr_t)w & 15u) == 0) {
-			typedef tma::XCfg X;
-			static int cps = -1;
-			return launch_persistent(ctx, tma::spmv1_xs_kernel<BETAK, MODE, FUSE>, &cps, X::WPB * 32, X::SMEM_BYTES, X::WPB,
-			                         S, dest, v, alpha, beta, w, fz, used);
-		}
 		if (S.ndict <= tma::SDICT_MAX && S.vshift == 3) {
 			static int cps = -1;   // per instantiation
 			return launch_persistent(ctx, tma::spmv1_vi_kernel<BETAK, MODE, FUSE, true>, &cps, C::WPB * 32, C::SMEM_BYTES_SDICT, C::WPB,
@@ -401,6 +394,15 @@ int launch_scalar(ug4b200_ctx* ctx, const ug4b200_matrix* A, double* dest, const
 	Sell S = view(A);
 	if (ctx->no_xs) S.xw = nullptr;
 	bool used = false;
+	// x-staged stream (x operand through shared memory by bulk copies: needs a 16-byte aligned x — anything from
+	// ug4b200_alloc is): taken when it exists, i.e. when the value-indexed stream does not (or on request)
+	if (S.xw != nullptr && !ctx->no_tma && ((uintptr_t)w & 15u) == 0) {
+		typedef tma::XCfg X;
+		static int cps = -1;   // per instantiation
+		const int rc = launch_persistent(ctx, tma::spmv1_xs_kernel<BETAK, MODE, FUSE>, &cps, X::WPB * 32, X::SMEM_BYTES, X::WPB,
+		                                 S, dest, v, alpha, beta, w, fz, &used);
+		if (rc || used) return rc;
+	}
 	// measured (profiles/r01b): the bulk-copy kernel wins for the fused variants, the register-staged
 	// one for the plain sweep; the value-indexed stream always goes through the bulk-copy kernel when
 	// the matrix is large enough (its 2-byte loads are a poor fit for register staging)
@@ -602,15 +604,20 @@ int ug4b200_matrix_upload_crs(ug4b200_ctx* ctx, int block, int64_t nrows, int64_
 	if (!rc) rc = up((void**)&A->diagpos, dp.data(), sizeof(int) * dp.size());
 	if (!rc) rc = up((void**)&A->cols, hc.data(), sizeof(int) * hc.size());
 	if (!rc) rc = up((void**)&A->vals, hv.data(), sizeof(double) * hv.size());
-	// ---- value-indexed copy of the entry stream (scalar matrices only) ----
-	// Conditions: at most 65536 distinct values (as bit patterns: -0.0 and 0.0 stay distinct) and, in
-	// every slice, all columns within 65535 of the slice's smallest column.  Typical for the level
-	// operators of a uniformly refined grid; otherwise the plain stream is used.
+	// ---- dictionary-encoded copies of the entry stream (scalar matrices only) ----
+	// With at most 65536 distinct values (as bit patterns: -0.0 and 0.0 stay distinct) an entry needs an index instead
+	// of 8 bytes.  Two lossless 4-byte-per-entry streams are built on that dictionary:
+	//   value-indexed (vc):  word = column offset from the slice's smallest column << 16 | index << vshift; needs every
+	//                        slice's columns within 65535 of its smallest column (129^3 lexicographic: yes; 257^3: no)
+	//   x-staged (xw):       word = position of the column in the slice's staged x segment << 16 | index << 3; needs
+	//                        <= 256 values, rows of <= 27 entries and per slice <= 16 runs / 352 doubles of columns
+	//                        (any banded numbering of a structured grid, whatever its size)
+	// Otherwise the plain 12-byte stream is used.
 	std::vector<unsigned int> hvc; std::vector<int> hcb; std::vector<double> hdict;
 	if (!rc && block == 1 && !ctx->no_comp && !(flags & UG4B200_MAT_NO_COMPRESS) && pnnz > 0) {
-		bool ok = true;
+		bool ok = true, window = true;
 		hcb.assign((size_t)ns, 0);
-#pragma omp parallel for schedule(static) reduction(&& : ok)
+#pragma omp parallel for schedule(static) reduction(&& : window)
 		for (int64_t s = 0; s < ns; ++s) {
 			int lo = 2147483647, hi = -1;
 			for (int l = 0; l < 32; ++l) {
@@ -620,22 +627,25 @@ int ug4b200_matrix_upload_crs(ug4b200_ctx* ctx, int block, int64_t nrows, int64_
 			}
 			if (hi < 0) lo = 0;
 			hcb[s] = lo;
-			if (hi >= 0 && (int64_t)hi - lo > 65535) ok = false;
+			if (hi >= 0 && (int64_t)hi - lo > 65535) window = false;
 		}
 		std::unordered_map<uint64_t, unsigned short> dict;
-		if (ok) {
-			dict.reserve(1024);
-			for (int64_t p = 0; p < nnz && ok; ++p) {
-				uint64_t bits; std::memcpy(&bits, &vals[p], 8);
-				if (dict.find(bits) == dict.end()) {
-					if (dict.size() >= 65536) { ok = false; break; }
-					const unsigned short id = (unsigned short)dict.size();
-					dict.emplace(bits, id);
-					hdict.push_back(vals[p]);
-				}
+		dict.reserve(1024);
+		for (int64_t p = 0; p < nnz && ok; ++p) {
+			uint64_t bits; std::memcpy(&bits, &vals[p], 8);
+			if (dict.find(bits) == dict.end()) {
+				if (dict.size() >= 65536) { ok = false; break; }
+				const unsigned short id = (unsigned short)dict.size();
+				dict.emplace(bits, id);
+				hdict.push_back(vals[p]);
 			}
 		}
 		if (ok) {
+			if (hdict.empty()) hdict.push_back(0.0);
+			if (!rc) rc = up((void**)&A->dict, hdict.data(), sizeof(double) * hdict.size());
+			if (!rc) A->ndict = (int)hdict.size();
+		}
+		if (ok && window) {
 			const int vshift = hdict.size() <= 1024 ? 3 : 0;
 			hvc.assign((size_t)pnnz, 0u);
 #pragma omp parallel for schedule(static)
@@ -650,16 +660,19 @@ int ug4b200_matrix_upload_crs(ug4b200_ctx* ctx, int block, int64_t nrows, int64_
 					}
 				}
 			}
-			if (hdict.empty()) hdict.push_back(0.0);
 			if (!rc) rc = up((void**)&A->vc, hvc.data(), sizeof(unsigned int) * hvc.size());
 			if (!rc) rc = up((void**)&A->colbase, hcb.data(), sizeof(int) * hcb.size());
-			if (!rc) rc = up((void**)&A->dict, hdict.data(), sizeof(double) * hdict.size());
-			if (!rc) { A->comp = true; A->ndict = (int)hdict.size(); A->vshift = vshift; }
+			if (!rc) { A->comp = true; A->vshift = vshift; }
+		}
+		if (ok) {
+			// the x-staged stream is the fall-back of the value-indexed one (same speed where both apply, measured):
+			// built when the column window is too wide for 16 bits, or on request (UG4B200_XSTAGE=1, tests)
+			const bool want_xs = !A->comp || ctx->force_xs;
 			// ---- x-staged copy (spmv1_xs_kernel): per slice the sorted distinct columns are grouped into runs of
 			// consecutive columns (gaps of <= 2 merged, ends aligned to 16 bytes); the words then carry the position
 			// of their column in the concatenation of the runs.  Any banded numbering of a structured grid gives a
 			// handful of runs per slice (27-point operator, lexicographic: 9 runs of 34 columns).
-			if (!rc && !ctx->no_xs && !(flags & UG4B200_MAT_NO_XSTAGE) && hdict.size() <= (size_t)tma_xs_max_dict() && maxlen <= tma_xs_max_width()) {
+			if (!rc && want_xs && !ctx->no_xs && !(flags & UG4B200_MAT_NO_XSTAGE) && hdict.size() <= (size_t)tma_xs_max_dict() && maxlen <= tma_xs_max_width()) {
 				const int RMAX = tma_xs_max_runs(), XCAP = tma_xs_max_doubles();
 				std::vector<unsigned int> hxw((size_t)pnnz, 0u);
 				std::vector<int4> hh((size_t)ns);

@@ -490,18 +490,24 @@ spmv1_vi_kernel(Sell A, double* dest, const double* v, double alpha, double beta
 
 
 // ---------------------------------------------------------------- x-staged value-indexed stream
-// spmv1_vi_kernel is latency-bound on its x-gathers (ncu, profiles/r02c: 60 % of all stall samples are
-// long-scoreboard waits on LDG results, 24 warps/SM at 80 registers cannot cover them; the kernel stays at
-// ~0.81 of the copy bandwidth).  Here NOTHING on the consumer side waits for global memory inside a slice:
-// besides the entry words, the producer also brings the slice's x operand into shared memory — the slice's
-// distinct columns form a handful of runs of consecutive columns (27-point operator, banded numbering: 9 runs
-// of 34), each one bulk copy (cp.async.bulk, >= 16 bytes, 16-byte aligned) landing on the same mbarrier as
-// the words.  The words address x by its position in that staging buffer, so an entry is
-//     LDS.32 word ; IMAD.HI (staging address) ; LDS.64 x ; LOP3 (dictionary address) ; LDS.64 value ; DMUL ; DADD
-// with shared-memory latencies only.  Bytes in flight are set by the ring (independent of registers), and the
-// arithmetic per row is unchanged: ascending column order, separate multiply and add.
-// Per slice metadata: header {entry offset / 32, width, staged bytes, runs} and xs_rmax run slots
+// The value-indexed words above carry a 16-bit column offset from the slice's smallest column: fine for 129^3
+// (window of two grid planes = 33 282 columns), too narrow for 257^3 (132 098) — BASELINE configs[2] on one GPU fell
+// back to the plain 12-byte stream (50.2 ms per solve, profiles/r02c).  This variant has no window: besides the entry
+// words the producer also brings the slice's x operand into shared memory — the slice's distinct columns form a
+// handful of runs of consecutive columns (27-point operator, banded numbering: 9 runs of 34), each one bulk copy
+// (cp.async.bulk, >= 16 bytes, 16-byte aligned) landing on the same mbarrier as the words — and the words address x
+// by its position in that staging buffer.  An entry is
+//     LDS.32 word ; LEA.HI (staging address) ; LDS.64 x ; LOP3 (dictionary address) ; LDS.64 value ; DMUL ; DADD
+// with shared-memory latencies only; the arithmetic per row is unchanged (ascending column order, separate multiply
+// and add).  Per slice metadata: header {entry offset / 32, width, staged bytes, runs} and xs_rmax run slots
 // {first column (even), doubles (even) | staging position << 16} (built at upload, spmv.cu).
+//
+// Measured at 129^3 where both streams apply (profiles/r02d, r02e): fused sweep 70.5 us vs 69.9 us for spmv1_vi_kernel —
+// the x-gathers were NOT what bounds that kernel.  What does: with 8 / 10 / 16 warps per SM this kernel takes
+// 110 / 92 / 70 us, time ~ 1 / warps — every warp spends ~2 us per slice on the per-row streams (defect, correction,
+// inverse diagonal) it requests at the start of a slice and needs at its end.  Staging those through bulk copies too
+// (one more variant, 15 copies of 128-3456 bytes per slice) was slower, 86-96 us: the copy engine, not HBM, became the
+// limit.  Hence: value-indexed kernel where its window fits, this one where it does not (or UG4B200_XSTAGE=1).
 #ifndef UG_XS_NST
 #define UG_XS_NST 2
 #endif

@@ -81,13 +81,13 @@ struct SolverImpl : SolverBase {
 			case UG4B200_SOLVER_BICGSTAB: {
 				SmartPtr<BiCGStab<vector_type> > s = make_sp<BiCGStab<vector_type> >();
 				s->set_restart(d.restart > 0 ? d.restart : 0);
-				s->set_device_resident((d.flags & UG4B200_FLAG_DEVICE_BICGSTAB) != 0);
+				s->set_device_resident(!(d.flags & UG4B200_FLAG_HOST_SCALARS));   // device-resident unless the reference-shaped host loop is asked for
 				s->set_use_graph(!(d.flags & UG4B200_FLAG_NO_GRAPH));
 				s->set_preconditioner(precond); inv = s; break;
 			}
 			case UG4B200_SOLVER_LINEAR: {
 				SmartPtr<LinearSolver<vector_type> > s = make_sp<LinearSolver<vector_type> >();
-				s->set_device_resident((d.flags & UG4B200_FLAG_DEVICE_LINEAR) != 0);
+				s->set_device_resident(!(d.flags & UG4B200_FLAG_HOST_SCALARS));
 				s->set_use_graph(!(d.flags & UG4B200_FLAG_NO_GRAPH));
 				s->set_preconditioner(precond); inv = s; break;
 			}
