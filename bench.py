@@ -296,6 +296,11 @@ def kernel_roofline(s, prob, top, peak_gbs, peak_src):
             # one 32-bit word per (padded) entry + row lengths + slice offsets + column bases + the vector streams
             b_stored = 4 * pnnz + 4 * n + 8 * (ns + 1) + 4 * ns + vec_bytes
             kname, tkey = "tma::spmv1_vi_kernel<-1,INPLACE,FUSE_JACOBI> (ug4b200_jacobi_smooth_fused, value-indexed SELL-32 stream, 4 B/entry)", "spmv1_vi_kernel"
+        elif info.x_staged:
+            # one 32-bit word per (padded) entry + row lengths + per-slice header (16 B) and run slots (8 B each) + the
+            # vector streams (x counted once, 8 B per column: its staged segments overlap and are served from L2)
+            b_stored = 4 * pnnz + 4 * n + ns * (16 + 8 * int(info.x_staged_runs)) + vec_bytes
+            kname, tkey = "tma::spmv1_xs_kernel<-1,INPLACE,FUSE_JACOBI> (ug4b200_jacobi_smooth_fused, x-staged value-indexed SELL-32 stream, 4 B/entry)", "spmv1_xs_kernel"
         else:
             b_stored = 12 * pnnz + 4 * n + 8 * (ns + 1) + vec_bytes
             kname, tkey = "tma::spmv1_tma_kernel<-1,INPLACE,FUSE_JACOBI> (ug4b200_jacobi_smooth_fused, plain SELL-32 stream, 12 B/entry)", "spmv1_tma_kernel"

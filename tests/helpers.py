@@ -33,7 +33,7 @@ ROUND_OFF_FLOOR = 1e-12      # a defect below this fraction of the start defect 
 ROUND_OFF_ALLOWANCE = 1e-14  # absolute allowance (x start defect) for steps below the floor
 
 
-def rel_hist_err(h_gpu, h_ref, allowance=None):
+def rel_hist_err(h_gpu, h_ref, allowance=None, floor=None):
     """max_k |h_gpu[k] - h_ref[k]| / |h_ref[k]| over the common prefix — north_star's "residual history within
     1e-10 relative per iteration", strict for every step whose defect is at least 1e-12 x the start defect (that
     covers every step of the BASELINE configurations, which stop at a reduction of 1e-10 / 1e-8).
@@ -51,7 +51,7 @@ def rel_hist_err(h_gpu, h_ref, allowance=None):
         return 0.0
     h_gpu, h_ref = np.asarray(h_gpu[:n], float), np.asarray(h_ref[:n], float)
     diff = np.abs(h_gpu - h_ref)
-    below = np.abs(h_ref) < ROUND_OFF_FLOOR * abs(h_ref[0])
+    below = np.abs(h_ref) < (ROUND_OFF_FLOOR if floor is None else floor) * abs(h_ref[0])
     allow = (ROUND_OFF_ALLOWANCE if allowance is None else allowance) * abs(h_ref[0])
     diff = np.where(below, np.maximum(diff - allow, 0.0), diff)
     with np.errstate(all="ignore"):
