@@ -128,3 +128,13 @@ def test_descriptor_errors_name_the_problem():
         with pytest.raises(ValueError, match=word):
             S.make_desc(bad)
     assert S.make_desc({"type": "bicgstab"}).restart == 0 and S.make_desc({"type": "bicgstab", "restart": 6}).restart == 6
+
+
+def test_profile_zones_carry_ugcore_names():
+    """NVTX ranges around the launches use ugcore's profiler zone names (mg_solver_impl.hpp:1698 GMG_PreSmooth, :1800
+    GMG_Restrict_Transfer, :1863 GMG_Prolongate_Transfer, :1913 GMG_PostSmooth, :1990 GMG_BaseSolver_Apply; cg.h:105
+    CG_apply_return_defect; sparsematrix_impl.h:298 SparseMatrix_axpy): the names are in the host library."""
+    blob = open(os.path.join(ROOT, "ugcore_b200", "lib", "libug4b200_host.so"), "rb").read()
+    for name in (b"GMG_PreSmooth", b"GMG_Restrict_Transfer", b"GMG_Prolongate_Transfer", b"GMG_PostSmooth", b"GMG_BaseSolver_Apply",
+                 b"GMG_Apply_lmgc", b"CG_apply_return_defect", b"LS_ApplyReturnDefect", b"SparseMatrix_axpy"):
+        assert name in blob, name

@@ -75,7 +75,9 @@ def build(force: bool = False, verbose: bool = False) -> None:
     host = os.path.join(LIB, "libug4b200_host.so")
     hsrc = [os.path.join(CSRC, "solver_capi.cpp")]
     if force or _newer(host, hsrc + headers + [dev]):
-        _run(["g++", "-O2", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-Wall", *hsrc, "-o", host,
+        _run(["g++", "-O2", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-Wall",
+              "-I" + os.path.join(os.path.dirname(os.path.dirname(NVCC)), "include"),   # nvtx3 (header-only)
+              *hsrc, "-o", host,
               "-L" + LIB, "-lug4b200", "-Wl,-rpath,$ORIGIN"], verbose)
 
 

@@ -228,6 +228,7 @@ class GPUSparseMatrix {
 	}
 	template <typename V> bool axpy(V& dest, const number& alpha1, const V& v1, const number& beta1, const V& w1) const
 	{
+		UG_GPU_ZONE(SparseMatrix_axpy);                               // sparsematrix_impl.h:298
 		UG_GPU_CHECK(ug4b200_matrix_axpy(GPUManager::ctx(), device(), dest.dev(), alpha1, alpha1 == 0.0 ? nullptr : v1.dev(), beta1,
 		                                 w1.dev(), V::blockSize));
 		return true;

@@ -183,7 +183,8 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 		if (!m_spTransferPrototype) m_spTransferPrototype = make_sp<StdTransfer<TAlgebra> >();
 		ug4b200_ctx* ctx = GPUManager::ctx();
 		GPUManager::bump_generation();   // level vectors / matrices are rebuilt: captured solver graphs are stale
-		if (m_bRAP) init_rap_operator();
+		UG_GPU_ZONE(GMG_Init);
+		if (m_bRAP) { UG_GPU_ZONE(GMG_BuildRAP_AllLevelMat); init_rap_operator(); }
 		for (int lev = m_baseLev; lev <= m_topLev; ++lev) {
 			LevData& ld = level(lev);
 			if (lev == m_topLev && (!ld.A || ld.AisSurface)) {
@@ -251,6 +252,7 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 	/// mg_solver_impl.hpp:174-275
 	virtual bool apply(vector_type& c, const vector_type& d)
 	{
+		UG_GPU_ZONE(GMG_Apply);
 		ug4b200_ctx* ctx = GPUManager::ctx();
 		LevData& top = level(m_topLev);
 		THROW_IF_NOT_EQUAL(d.size(), top.sd.size());
@@ -275,7 +277,7 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 		}
 		top.scZero = true;                     // sc = 0 (:234), carried out by the first accumulation
 		if (m_topLev == m_baseLev) materialize_sc(m_topLev);
-		lmgc(m_topLev, m_cycleType);           // :238
+		{ UG_GPU_ZONE(GMG_Apply_lmgc); lmgc(m_topLev, m_cycleType); }   // :238
 		// c = 0 (:231) ; c[surf] += sc[lev] (:244-248)
 		if (m_dSurfMap) {
 			c.set(0.0);
@@ -380,6 +382,8 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 		ug4b200_ctx* ctx = GPUManager::ctx();
 		LevData& lf = level(lev); LevData& lc = level(lev - 1);
 		Jacobi<TAlgebra>* jac = fused_jacobi(lf.PreSmoother);
+		{
+		UG_GPU_ZONE(GMG_PreSmooth);                                   // mg_solver_impl.hpp:1698
 		if (jac && m_numPreSmooth > 0) {
 			// fused: st0 = D sd ; then per step one kernel  { sc += st ; sd -= A st ; [st' = D sd] }
 			const int64_t n = (int64_t)lf.sd.size();
@@ -410,6 +414,8 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 			}
 			if (m_numPreSmooth > 0) SC(lev) += lf.st;               // :1783-1784
 		}
+		}
+		UG_GPU_ZONE(GMG_Restrict_Transfer);                           // mg_solver_impl.hpp:1800
 		// sc_{l-1} = 0 (:1780): deferred to the first accumulation; the base solvers overwrite it
 		if (lev - 1 == m_baseLev && base_solver_overwrites()) lc.scZero = false;
 		else lc.scZero = true;
@@ -436,7 +442,8 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 		LevData& lf = level(lev); LevData& lc = level(lev - 1);
 		lc.stReady = false;
 		materialize_sc(lev - 1);
-		lf.transfer->prolongate(lf.st, SC(lev - 1));                // :1865
+		{ UG_GPU_ZONE(GMG_Prolongate_Transfer); lf.transfer->prolongate(lf.st, SC(lev - 1)); }   // :1863-1865
+		UG_GPU_ZONE(GMG_PostSmooth);                                  // mg_solver_impl.hpp:1913 (incl. GMG_AddCoarseGridCorrection :1904)
 		Jacobi<TAlgebra>* jac = fused_jacobi(lf.PostSmoother);
 		if (jac) {
 			vector_type* cur = &lf.st; vector_type* alt = &lf.st2;
@@ -473,9 +480,11 @@ class AssembledMultiGridCycle : public ILinearIterator<typename TAlgebra::vector
 		ug4b200_ctx* ctx = GPUManager::ctx();
 		LevData& ld = level(lev);
 		if (!ld.layouts) {
+			UG_GPU_ZONE(GMG_BaseSolver_Apply);                        // mg_solver_impl.hpp:1990
 			if (!m_spBaseSolver->apply(ld.sc, ld.sd)) UG_THROW("GMG::lmgc: Base solver on base level " << lev << " failed.");
 		} else {
 			// gathered: additive local defects -> global consistent defect on every rank
+			UG_GPU_ZONE(GMG_GatheredBaseSolver_Apply);                // mg_solver_impl.hpp:2018-2045
 			UG_GPU_CHECK(ug4b200_gather_sum(ctx, m_gather, m_gatheredD.dev(), ld.sd.dev()));
 			if (!m_spBaseSolver->apply(m_gatheredC, m_gatheredD)) UG_THROW("GMG::lmgc: Base solver on base level " << lev << " failed.");
 			UG_GPU_CHECK(ug4b200_vec_gather(ctx, (int64_t)ld.sc.size(), B, ld.sc.dev(), m_gatheredC.dev(), m_dBaseMap));

@@ -77,6 +77,7 @@ class CG : public IPreconditionedLinearOperatorInverse<TVector> {
 
 	virtual bool apply_return_defect(vector_type& x, vector_type& b)
 	{
+		UG_GPU_ZONE(CG_apply_return_defect);                          // cg.h:105
 		if (x.layouts() && (!b.has_storage_type(PST_ADDITIVE) || !x.has_storage_type(PST_CONSISTENT)))
 			UG_THROW("CG::apply_return_defect: Inadequate storage format of Vectors.");
 		StdConvCheck<vector_type>* std_cc = dynamic_cast<StdConvCheck<vector_type>*>(convergence_check().get());
@@ -284,6 +285,7 @@ class BiCGStab : public IPreconditionedLinearOperatorInverse<TVector> {
 
 	virtual bool apply_return_defect(vector_type& x, vector_type& b)
 	{
+		UG_GPU_ZONE(LS_ApplyReturnDefect);                            // bicgstab.h:114
 		const bool par = (bool)x.layouts();
 		if (par && (!b.has_storage_type(PST_ADDITIVE) || !x.has_storage_type(PST_CONSISTENT)))
 			UG_THROW("BiCGStab: Inadequate storage format of Vectors.");

@@ -108,6 +108,33 @@ enum ParallelStorageType { PST_UNDEFINED = 0, PST_CONSISTENT = 1, PST_ADDITIVE =
 } // namespace ug
 #endif // UG4B200_WITH_UGCORE
 
+// ---- profiler zones (ugbase/common/profiler/profiler.h: PROFILE_BEGIN_GROUP / PROFILE_FUNC_GROUP; the GMG's own
+// GMG_PROFILE_BEGIN(GMG_PreSmooth) ..., mg_solver_impl.hpp:60-69) — as NVTX ranges with ugcore's zone names, so that an
+// Nsight Systems timeline of a solve reads like ugcore's profiler output.  nvtx3 is header-only and resolves its
+// injection library at run time (no link dependency); without the header the zones compile to nothing.
+#if defined(__has_include)
+#if __has_include(<nvtx3/nvToolsExt.h>) && !defined(UG4B200_NO_NVTX)
+#include <nvtx3/nvToolsExt.h>
+#define UG4B200_HAVE_NVTX 1
+#endif
+#endif
+namespace ug {
+struct GPUProfileZone {
+#ifdef UG4B200_HAVE_NVTX
+	explicit GPUProfileZone(const char* name) { nvtxRangePushA(name); }
+	~GPUProfileZone() { nvtxRangePop(); }
+#else
+	explicit GPUProfileZone(const char*) {}
+#endif
+	GPUProfileZone(const GPUProfileZone&) = delete;
+	GPUProfileZone& operator=(const GPUProfileZone&) = delete;
+};
+} // namespace ug
+#define UG_GPU_ZONE_CAT2(a, b) a##b
+#define UG_GPU_ZONE_CAT(a, b) UG_GPU_ZONE_CAT2(a, b)
+/// a zone that lasts until the end of the enclosing scope, named like ugcore's (GMG_PROFILE_BEGIN(GMG_PreSmooth))
+#define UG_GPU_ZONE(name) ::ug::GPUProfileZone UG_GPU_ZONE_CAT(ugGpuZone_, __LINE__)(#name)
+
 namespace ug {
 
 /// Turns a C-ABI error code into a UGError (what CUDA_CHECK_STATUS did, cuda_manager.h:61-77)
