@@ -133,6 +133,9 @@ int ug4b200_solver_init(ug4b200_solver* s);
 /* solver:apply(u, b) with HOST vectors: H2D of x and b, solve, D2H of x.
  * Returns 0 converged, 1 not converged / breakdown, < 0 error. */
 int ug4b200_solver_apply(ug4b200_solver* s, double* x_host, const double* b_host);
+/* the same for the usual call with a zero start vector (u:set(0.0) before solver:apply, solver_util.lua:1194-1200):
+ * x is set to 0 on the device instead of being copied there — a third less host-to-device traffic; x_host is output only */
+int ug4b200_solver_apply_zero_guess(ug4b200_solver* s, double* x_host, const double* b_host);
 /* same with DEVICE vectors (n = block * rows doubles) */
 int ug4b200_solver_apply_device(ug4b200_solver* s, double* x_dev, const double* b_dev);
 int ug4b200_solver_steps(const ug4b200_solver* s);

@@ -282,6 +282,26 @@ def test_lu_apply_bit_exact(D, orc):
         assert np.array_equal(D.down(dx, n), orc.matrix(A).lu_solve(bvec))
 
 
+def test_lu_apply_large_base_grid_parallel_order(D, orc):
+    """Above 128 unknowns the backward substitution runs column-oriented (parallel; SolveLU's own row order is one serial
+    chain of n^2/2 operations): same terms per row, other order -> equal to the reference to round-off, not bit for bit.
+    Stand-alone kernel and the recorded (batch) form give the same bits."""
+    from ugcore_b200 import problems as pr
+    import scipy.linalg
+    prob = pr.Problem(dim=3, num_refs=1, base=(3, 3, 3), problem=pr.ELASTICITY)     # 7^3 nodes x 3 = 1029 unknowns
+    A = prob.matrix()
+    n = A.nrows * A.block
+    M = A.to_scipy().toarray()
+    lu, piv = scipy.linalg.lu_factor(M)           # any valid LU with row interchanges serves as input of the apply kernel
+    bvec = np.random.default_rng(3).standard_normal(n)
+    dlu, dpiv, db, dx = D.up(lu.ravel()), D.up(piv.astype(np.int32), np.int32), D.up(bvec), D.up(np.zeros(n))
+    D.chk(D.dev.ug4b200_lu_apply(D.ctx, n, dlu, dpiv, dx, db))
+    x = D.down(dx, n)
+    ref = scipy.linalg.lu_solve((lu, piv), bvec)
+    assert np.linalg.norm(x - ref) <= 1e-12 * np.linalg.norm(ref)
+    assert np.linalg.norm(M @ x - bvec) <= 1e-10 * np.linalg.norm(bvec)
+
+
 def test_coarse_cg_solves(D, orc):
     from ugcore_b200 import problems as pr
     prob = pr.Problem(dim=3, num_refs=2)

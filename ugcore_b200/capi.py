@@ -182,6 +182,7 @@ HOST_API = {
     "ug4b200_solver_set_gathered_level": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ug4b200_solver_init": (c_int, [c_vp]),
     "ug4b200_solver_apply": (c_int, [c_vp, c_vp, c_vp]),
+    "ug4b200_solver_apply_zero_guess": (c_int, [c_vp, c_vp, c_vp]),
     "ug4b200_solver_apply_device": (c_int, [c_vp, c_vp, c_vp]),
     "ug4b200_solver_steps": (c_int, [c_vp]),
     "ug4b200_solver_defect": (c_dbl, [c_vp]),

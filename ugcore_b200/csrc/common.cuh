@@ -27,6 +27,9 @@ struct UgBatchOp {
 	double alpha, beta;
 };
 constexpr int kBatchMaxOps = 56;
+/// dense LU base solve: up to this many unknowns the backward substitution keeps SolveLU's (serial) operation order and is
+/// bit-identical to it; larger systems use the parallel column-oriented order (smoothers.cu: lu_apply_kernel)
+constexpr int kLuExactMax = 128;
 struct UgBatchParams { int nops; int pad_; UgBatchOp op[kBatchMaxOps]; };
 
 struct ug4b200_ctx {

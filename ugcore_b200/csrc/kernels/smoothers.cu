@@ -131,7 +131,7 @@ gs_color_kernel(Sell A, int64_t r0, int64_t r1, double relax, double* c, const d
 }
 
 // ---- dense LU apply, one CTA ---------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 lu_apply_kernel(int n, const double* __restrict__ lu, const int* __restrict__ piv, double* x, const double* b,
                 const int* guard)
 {
@@ -149,13 +149,27 @@ lu_apply_kernel(int n, const double* __restrict__ lu, const int* __restrict__ pi
 		for (int i = k + 1 + threadIdx.x; i < n; i += blockDim.x) sx[i] = sx[i] - lu[(size_t)i * n + k] * xk;
 		__syncthreads();
 	}
-	// backward substitution: sequential (each row subtracts in ascending k, starting with
-	// the most recently finished unknown) to stay bit-identical with SolveLU
-	if (threadIdx.x == 0) {
-		for (int i = n - 1; i >= 0; --i) {
-			double s = sx[i];
-			for (int k = i + 1; k < n; ++k) s = s - lu[(size_t)i * n + k] * sx[k];
-			sx[i] = s / lu[(size_t)i * n + i];
+	// backward substitution.  SolveLU (no_lapack/lu_decomp.h:160-195) subtracts, for every row, in ASCENDING k — starting
+	// with the unknown that was finished last — so a bit-identical evaluation is one serial chain of n^2/2 dependent
+	// operations (measured: 28 ms per base solve at n = 1029, the 7^3 x 3 base grid of the partitioned elasticity run).
+	// Up to kLuExactMax unknowns (every base grid of one to 3x3x3 cells) that chain is kept and the result equals
+	// SolveLU bit for bit; above it the column-oriented form runs (all rows updated in parallel as soon as an unknown is
+	// final: the same terms per row in DESCENDING k), which differs from SolveLU in the last bits only.
+	if (n <= kLuExactMax) {
+		if (threadIdx.x == 0) {
+			for (int i = n - 1; i >= 0; --i) {
+				double s = sx[i];
+				for (int k = i + 1; k < n; ++k) s = s - lu[(size_t)i * n + k] * sx[k];
+				sx[i] = s / lu[(size_t)i * n + i];
+			}
+		}
+	} else {
+		for (int k = n - 1; k >= 0; --k) {
+			if (threadIdx.x == 0) sx[k] = sx[k] / lu[(size_t)k * n + k];
+			__syncthreads();
+			const double xk = sx[k];
+			for (int i = threadIdx.x; i < k; i += blockDim.x) sx[i] = sx[i] - lu[(size_t)i * n + k] * xk;
+			__syncthreads();
 		}
 	}
 	__syncthreads();
@@ -337,7 +351,7 @@ int ug4b200_lu_apply(ug4b200_ctx* ctx, int n, const double* lu_dev, const int* p
 		UgBatchOp o{}; o.kind = UG_OP_LU; o.n = n; o.vals = lu_dev; o.cols = piv_dev; o.dest = x; o.w = b;
 		return ug_batch_push(ctx, o);
 	}
-	UG_LAUNCH(ctx, lu_apply_kernel, 1, 256, sizeof(double) * n, n, lu_dev, piv_dev, x, b, ctx->guard);
+	UG_LAUNCH(ctx, lu_apply_kernel, 1, n > 256 ? 1024 : 256, sizeof(double) * n, n, lu_dev, piv_dev, x, b, ctx->guard);
 	return UG4B200_OK;
 }
 

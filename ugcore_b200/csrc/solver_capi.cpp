@@ -27,7 +27,7 @@ struct SolverBase {
 	                                const int64_t* prp, const int* pci, const double* pva, const int64_t* rrp, const int* rci,
 	                                const double* rva) = 0;
 	virtual void init() = 0;
-	virtual int apply_host(double* x, const double* b) = 0;
+	virtual int apply_host(double* x, const double* b, bool zero_guess = false) = 0;
 	virtual int apply_device(double* x, const double* b) = 0;
 	virtual void precond_apply(double* c, const double* d) = 0;
 	virtual int64_t num_dofs() const = 0;
@@ -252,10 +252,11 @@ struct SolverImpl : SolverBase {
 		steps = conv->step(); defect = conv->defect(); history = conv->get_defects();
 		return ok ? 0 : 1;
 	}
-	int apply_host(double* xh, const double* bh) override
+	int apply_host(double* xh, const double* bh, bool zero_guess) override
 	{
 		ug4b200_ctx* c = GPUManager::ctx();
-		UG_GPU_CHECK(ug4b200_h2d(c, x.dev(), xh, x.len() * sizeof(double)));
+		if (zero_guess) x.set(0.0);
+		else UG_GPU_CHECK(ug4b200_h2d(c, x.dev(), xh, x.len() * sizeof(double)));
 		UG_GPU_CHECK(ug4b200_h2d(c, b.dev(), bh, b.len() * sizeof(double)));
 		x.set_storage_type(PST_CONSISTENT); b.set_storage_type(PST_ADDITIVE);
 		const bool ok = inv->apply(x, b);
@@ -343,6 +344,7 @@ int ug4b200_solver_set_gathered_level(ug4b200_solver* s, int lev, int64_t nrows,
 { return guard([&] { s->p->set_gathered_level(lev, nrows, rowptr, cols, vals, ncoarse, p_rowptr, p_cols, p_vals, r_rowptr, r_cols, r_vals); return 0; }); }
 int ug4b200_solver_init(ug4b200_solver* s) { return guard([&] { s->p->init(); return 0; }); }
 int ug4b200_solver_apply(ug4b200_solver* s, double* x_host, const double* b_host) { return guard([&] { return s->p->apply_host(x_host, b_host); }); }
+int ug4b200_solver_apply_zero_guess(ug4b200_solver* s, double* x_host, const double* b_host) { return guard([&] { return s->p->apply_host(x_host, b_host, true); }); }
 int ug4b200_solver_apply_device(ug4b200_solver* s, double* x_dev, const double* b_dev) { return guard([&] { return s->p->apply_device(x_dev, b_dev); }); }
 int ug4b200_solver_steps(const ug4b200_solver* s) { return s->p->steps; }
 double ug4b200_solver_defect(const ug4b200_solver* s) { return s->p->defect; }

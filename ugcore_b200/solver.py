@@ -344,21 +344,25 @@ class Solver:
             self.init()
         b = np.ascontiguousarray(b, dtype=np.float64)
         x = np.zeros(self.n) if x0 is None else np.ascontiguousarray(x0, dtype=np.float64).copy()
+        # no start vector given: it is 0 and is set on the device, not copied there
+        fn = host.ug4b200_solver_apply_zero_guess if x0 is None else host.ug4b200_solver_apply
         if self.perm is not None:      # Pv[perm[i]] = v[i]  (SetVectorAsPermutation, permutation_util.h:72-78)
             bp, xp = np.empty_like(b), np.empty_like(x)
             bp[self.perm], xp[self.perm] = b, x
-            rc = check_host(host.ug4b200_solver_apply(self.h, _ptr(xp), _ptr(bp)))
+            rc = check_host(fn(self.h, _ptr(xp), _ptr(bp)))
             return xp[self.perm], rc == 0, self.history()
-        rc = check_host(host.ug4b200_solver_apply(self.h, _ptr(x), _ptr(b)))
+        rc = check_host(fn(self.h, _ptr(x), _ptr(b)))
         return x, rc == 0, self.history()
 
-    def apply_pinned(self, x_ptr: int, b_ptr: int) -> bool:
-        """Same through raw host pointers (e.g. pinned torch tensors): x in/out, b in."""
+    def apply_pinned(self, x_ptr: int, b_ptr: int, zero_guess: bool = False) -> bool:
+        """Same through raw host pointers (e.g. pinned torch tensors): x in/out, b in.  zero_guess: the start vector is 0
+        (set on the device; x is output only)."""
         if self.perm is not None:
             raise ValueError("apply_pinned works in the solver's own numbering: permute the vectors (Solver.perm) or use apply")
         if not self._inited:
             self.init()
-        return check_host(host.ug4b200_solver_apply(self.h, C.c_void_p(x_ptr), C.c_void_p(b_ptr))) == 0
+        fn = host.ug4b200_solver_apply_zero_guess if zero_guess else host.ug4b200_solver_apply
+        return check_host(fn(self.h, C.c_void_p(x_ptr), C.c_void_p(b_ptr))) == 0
 
     def apply_device(self, x_dev, b_dev) -> bool:
         """Device-resident solve; x_dev / b_dev are DeviceBuffer or raw device pointers."""
