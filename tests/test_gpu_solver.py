@@ -260,6 +260,37 @@ def test_full_size_properties_129cubed():
     assert abs(its[6] - its[7]) <= 1
 
 
+def test_full_size_129cubed_history_matches_the_reference():
+    """BASELINE configs[1] at full size against the ORACLE (compiled ugcore kernels, one serial solve of 2.1 M DoF, ~10 s):
+    the kernels that bench.py times — persistent bulk-copy SpMV on the value-indexed stream, fused smoothing, batched
+    coarse levels, device-resident CG in a CUDA graph — are the ones compared here, at north_star's tolerances."""
+    prob = __import__("ugcore_b200").problems.Problem(dim=3, num_refs=7)
+    s, hg, ho = _compare(prob, gmg_desc(7))
+    assert len(hg) == len(ho) == 9
+
+
+@pytest.mark.parametrize("order", ["hier", "hier_cmk"])
+def test_65cubed_hierarchical_order_matches_the_reference(order):
+    """ugcore's DoF order after global refinement (coarse vertices first, then edge / face / volume midpoints): the
+    16-bit column window of the value-indexed stream does not fit, x-gathers lose their locality, the plain 12 B stream
+    runs — and with Cuthill-McKee at upload a banded numbering is restored.  Same bar as above."""
+    import oracle
+    import ugcore_b200 as ug
+    from ugcore_b200 import problems as pr
+    prob = pr.Problem(dim=3, num_refs=6, order=pr.ORDER_HIER)
+    desc = gmg_desc(6)
+    orc = _best_oracle()
+    lv = oracle_levels(orc, prob, 0, 6)
+    osol = oracle.OSolver(orc, desc, lv[6][0], lv)
+    b = np.array(prob.rhs())
+    xo, oko, ho = osol.apply(b)
+    s = ug.Solver.from_problem(desc, prob, order="cmk" if order == "hier_cmk" else None)
+    xg, okg, hg = s.apply(b)
+    assert okg and oko and len(hg) == len(ho)
+    assert rel_hist_err(hg, ho) < HIST_TOL
+    assert np.linalg.norm(xg - xo) <= SOL_TOL * np.linalg.norm(xo)
+
+
 def test_value_indexed_and_plain_streams_give_identical_histories():
     """The value-indexed entry stream is lossless: the whole solve (history, iterates) must be
     bit-identical to a run with the plain stream (UG4B200_NO_COMPRESS=1, separate process because
