@@ -44,16 +44,16 @@ UNIT = "MDoF/s"
 PART = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 
 
-def solver_desc(top, base=0, workload="poisson"):
+def solver_desc(top, base=0, workload="poisson", base_solver="lu"):
     if workload == "convdiff":     # BASELINE configs[3]: BiCGStab + GMG V(2,2), (multicolour) Gauss-Seidel smoothing
         return {"type": "bicgstab",
                 "precond": {"type": "gmg", "topLevel": top, "baseLevel": base, "smoother": {"type": "gs", "relax": 1.0},
-                            "cycle": "V", "preSmooth": 2, "postSmooth": 2, "baseSolver": "lu"},
+                            "cycle": "V", "preSmooth": 2, "postSmooth": 2, "baseSolver": base_solver},
                 "convCheck": {"iterations": 100, "absolute": 1e-12, "reduction": 1e-8}}
     red, its = (1e-8, 200) if workload == "elasticity" else (1e-10, 100)
     return {"type": "cg",
             "precond": {"type": "gmg", "topLevel": top, "baseLevel": base, "smoother": {"type": "jac", "damp": 0.66},
-                        "cycle": "V", "preSmooth": 2, "postSmooth": 2, "baseSolver": "lu"},
+                        "cycle": "V", "preSmooth": 2, "postSmooth": 2, "baseSolver": base_solver},
             "convCheck": {"iterations": its, "absolute": 1e-12, "reduction": red}}
 
 
@@ -428,7 +428,7 @@ def run_ours(args):
     dev = capi.dev
     refs = args.refs
     spec = workload_spec(args.workload)
-    desc = solver_desc(refs, workload=args.workload)
+    desc = solver_desc(refs, workload=args.workload, base_solver=args.base_solver)
     bm = args.base_mult
 
     strong = args.scaling == "strong"
@@ -518,7 +518,7 @@ def run_ours(args):
            "dtype": "f64", "data": "synthetic",
            "config": {"workload": f"{spec['label']} unit-cell hexahedra, base grid {gbase[0]}x{gbase[1]}x{gbase[2]} cells, numRefs={refs}, "
                                   f"{nodes} = {n_global} DoF ({n_local} per GPU, boxes {part[0]}x{part[1]}x{part[2]}), {spec['method']}, "
-                                  f"base LU on level 0, DoF order {args.order}" + (f" + {reorder} at upload" if reorder else ""),
+                                  f"base {'LU' if args.base_solver == 'lu' else 'on-device CG (1e-14)'} on level 0, DoF order {args.order}" + (f" + {reorder} at upload" if reorder else ""),
                       "iterations": its, "solve_s": ms * 1e-3, "init_s": setup_s,
                       "l2_policy": f"inputs larger than L2 (top-level matrix {top_gb:.2f} GB per GPU)",
                       "wall_ms_per_step": wall_ms, "final_reduction": float(hist[-1] / hist[0]) if len(hist) else None,
@@ -564,6 +564,9 @@ def main():
     ap.add_argument("--order", default="lex", choices=["lex", "hier"], help="DoF numbering of the generator: lexicographic, "
                     "or hierarchical like ugcore's global refinement (coarse vertices first)")
     ap.add_argument("--reorder", default="none", choices=["none", "cmk", "rcmk"], help="(reverse) Cuthill-McKee of every level before upload")
+    ap.add_argument("--base-solver", default="lu", choices=["lu", "cg"], help="GMG base solver: dense LU (ugcore's default) or the small "
+                    "on-device CG of north_star (single CTA, reduction 1e-14) — for base grids of many cells, where the dense triangular "
+                    "solves of an LU are a serial latency chain on the device")
     ap.add_argument("--cpu-procs", type=int, default=0, help="processes of the CPU arm (0 = all host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

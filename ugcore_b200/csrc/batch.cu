@@ -150,22 +150,12 @@ __device__ void lu_solve_cta(const UgBatchParams& P, const int opi, double* sx)
 		for (int i = k + 1 + threadIdx.x; i < n; i += blockDim.x) sx[i] = sx[i] - lu[(size_t)i * n + k] * xk;
 		__syncthreads();
 	}
-	if (n <= kLuExactMax) {
-		if (threadIdx.x == 0) {
-			for (int i = n - 1; i >= 0; --i) {
-				double s = sx[i];
-				for (int k = i + 1; k < n; ++k) s = s - lu[(size_t)i * n + k] * sx[k];
-				sx[i] = s / lu[(size_t)i * n + i];
-			}
-		}
-	} else {
-		// column-oriented (parallel) backward substitution, see lu_apply_kernel
-		for (int k = n - 1; k >= 0; --k) {
-			if (threadIdx.x == 0) sx[k] = sx[k] / lu[(size_t)k * n + k];
-			__syncthreads();
-			const double xk = sx[k];
-			for (int i = threadIdx.x; i < k; i += blockDim.x) sx[i] = sx[i] - lu[(size_t)i * n + k] * xk;
-			__syncthreads();
+	// (systems of more than kLuExactMax unknowns are not recorded: ug4b200_lu_apply launches lu_apply_large_kernel)
+	if (threadIdx.x == 0) {
+		for (int i = n - 1; i >= 0; --i) {
+			double s = sx[i];
+			for (int k = i + 1; k < n; ++k) s = s - lu[(size_t)i * n + k] * sx[k];
+			sx[i] = s / lu[(size_t)i * n + i];
 		}
 	}
 	__syncthreads();

@@ -152,10 +152,9 @@ lu_apply_kernel(int n, const double* __restrict__ lu, const int* __restrict__ pi
 	// backward substitution.  SolveLU (no_lapack/lu_decomp.h:160-195) subtracts, for every row, in ASCENDING k — starting
 	// with the unknown that was finished last — so a bit-identical evaluation is one serial chain of n^2/2 dependent
 	// operations (measured: 28 ms per base solve at n = 1029, the 7^3 x 3 base grid of the partitioned elasticity run).
-	// Up to kLuExactMax unknowns (every base grid of one to 3x3x3 cells) that chain is kept and the result equals
-	// SolveLU bit for bit; above it the column-oriented form runs (all rows updated in parallel as soon as an unknown is
-	// final: the same terms per row in DESCENDING k), which differs from SolveLU in the last bits only.
-	if (n <= kLuExactMax) {
+	// Up to kLuExactMax unknowns (every base grid of one to 2x2x2 cells, scalar) that chain is kept here and the result
+	// equals SolveLU bit for bit; larger systems go to lu_apply_large_kernel (column-oriented, parallel).
+	{
 		if (threadIdx.x == 0) {
 			for (int i = n - 1; i >= 0; --i) {
 				double s = sx[i];
@@ -163,15 +162,73 @@ lu_apply_kernel(int n, const double* __restrict__ lu, const int* __restrict__ pi
 				sx[i] = s / lu[(size_t)i * n + i];
 			}
 		}
-	} else {
-		for (int k = n - 1; k >= 0; --k) {
-			if (threadIdx.x == 0) sx[k] = sx[k] / lu[(size_t)k * n + k];
-			__syncthreads();
-			const double xk = sx[k];
-			for (int i = threadIdx.x; i < k; i += blockDim.x) sx[i] = sx[i] - lu[(size_t)i * n + k] * xk;
-			__syncthreads();
-		}
 	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] = sx[i];
+}
+
+// Dense LU apply for more than kLuExactMax unknowns: column-oriented forward and backward substitution (all rows
+// receive the update of an unknown as soon as it is final).  Every step needs one column of the row-major factor — a
+// strided global read whose ~1 us latency, paid 2 n times, was the whole cost (2.5 ms per apply at n = 1029).  The
+// columns are therefore prefetched D steps ahead into a shared-memory ring with cp.async (no registers involved); a step
+// is then two CTA barriers and n shared-memory updates.  Same terms per row as SolveLU, backward part in descending
+// instead of ascending k: equal to the reference to round-off (tests/test_gpu_kernels.py).
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc)
+{
+	const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int D>
+__global__ void __launch_bounds__(1024)
+lu_apply_large_kernel(int n, const double* __restrict__ lu, const int* __restrict__ piv, double* x, const double* b,
+                      const int* guard)
+{
+	if (ug_guarded(guard)) return;
+	extern __shared__ double sm[];
+	double* sx = sm;                 // [n]
+	double* ring = sm + n;           // [D][n]
+	for (int i = threadIdx.x; i < n; i += blockDim.x) sx[i] = b[i];
+	__syncthreads();
+	if (threadIdx.x == 0)
+		for (int i = 0; i < n; ++i) if (i < piv[i]) { const double t = sx[i]; sx[i] = sx[piv[i]]; sx[piv[i]] = t; }
+	// column k of the factor -> ring slot k % D (every thread copies the entries of its own rows)
+	auto fetch = [&](int k) {
+		if (k >= 0 && k < n) {
+			double* dst = ring + (size_t)(k % D) * n;
+			for (int i = threadIdx.x; i < n; i += blockDim.x) cp_async8(dst + i, lu + (size_t)i * n + k);
+		}
+		cp_async_commit();           // (an empty group keeps the group count in step)
+	};
+	// ---- forward: for k = 0 .. n-2: rows i > k: sx[i] -= L[i][k] * sx[k]
+	for (int d = 0; d < D; ++d) fetch(d);
+	for (int k = 0; k < n - 1; ++k) {
+		cp_async_wait<D - 1>();
+		__syncthreads();             // column k has landed for every thread; sx[k] is final
+		const double xk = sx[k];
+		const double* col = ring + (size_t)(k % D) * n;
+		for (int i = k + 1 + threadIdx.x; i < n; i += blockDim.x) sx[i] = sx[i] - col[i] * xk;
+		__syncthreads();             // slot k % D is free, sx updated
+		fetch(k + D);
+	}
+	cp_async_wait<0>();
+	__syncthreads();
+	// ---- backward: for k = n-1 .. 0: sx[k] /= U[k][k]; rows i < k: sx[i] -= U[i][k] * sx[k]
+	for (int d = 0; d < D; ++d) fetch(n - 1 - d);
+	for (int k = n - 1; k >= 0; --k) {
+		cp_async_wait<D - 1>();
+		__syncthreads();
+		const double* col = ring + (size_t)(k % D) * n;
+		const double xk = sx[k] / col[k];      // every thread computes the same value; thread 0 stores it below
+		__syncthreads();                       // all have read sx[k] before it is overwritten
+		if (threadIdx.x == 0) sx[k] = xk;
+		for (int i = threadIdx.x; i < k; i += blockDim.x) sx[i] = sx[i] - col[i] * xk;
+		__syncthreads();
+		fetch(k - D);
+	}
+	cp_async_wait<0>();
 	__syncthreads();
 	for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] = sx[i];
 }
@@ -347,6 +404,20 @@ int ug4b200_lu_apply(ug4b200_ctx* ctx, int n, const double* lu_dev, const int* p
 {
 	if (n <= 0) return UG4B200_OK;
 	UG_ARG(ctx, n <= 4096, "dense LU base solver limited to 4096 unknowns");
+	if (n > kLuExactMax) {
+		// large base system: its own kernel (shared-memory ring of prefetched factor columns; not recorded into the batch)
+		const int D = n <= 1536 ? 8 : 4;
+		const int smem = (int)sizeof(double) * n * (D + 1);
+		static bool attr = false;
+		if (!attr) {
+			cudaFuncSetAttribute(lu_apply_large_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+			cudaFuncSetAttribute(lu_apply_large_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+			attr = true;
+		}
+		if (D == 8) { UG_LAUNCH(ctx, lu_apply_large_kernel<8>, 1, 1024, smem, n, lu_dev, piv_dev, x, b, ctx->guard); }
+		else { UG_LAUNCH(ctx, lu_apply_large_kernel<4>, 1, 1024, smem, n, lu_dev, piv_dev, x, b, ctx->guard); }
+		return UG4B200_OK;
+	}
 	if (ug_batchable(ctx, n)) {
 		UgBatchOp o{}; o.kind = UG_OP_LU; o.n = n; o.vals = lu_dev; o.cols = piv_dev; o.dest = x; o.w = b;
 		return ug_batch_push(ctx, o);
