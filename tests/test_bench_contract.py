@@ -45,3 +45,22 @@ def test_cpu_arm_is_bounded_by_host_memory():
     assert bench.replica_bytes(7) < bench.replica_bytes(8) and bench.replica_bytes(6, "elasticity") > bench.replica_bytes(6)
     assert 1 <= bench.bounded_procs(64, 9, "elasticity") <= 64           # a 513^3 x 3 hierarchy never gets 64 replicas here
     assert bench.bounded_procs(1, 2) == 1
+
+
+def test_reference_arm_strong_scaling_grid_and_order():
+    """--scaling strong: the CPU arm solves the same 2x2x2-cell grid (here 9^3 at numRefs 2) and says so; --order hier is
+    passed through to the generator (same iteration count, another numbering)."""
+    d = json.loads(_run(["--refs", "2", "--scaling", "strong"])[0])
+    assert d["scaling"] == "strong" and "729 DoF" in d["cpu_baseline"]["sample"]
+    h = json.loads(_run(["--refs", "2", "--order", "hier"])[0])
+    l = json.loads(_run(["--refs", "2"])[0])
+    assert h["config"]["iterations"] == l["config"]["iterations"]
+
+
+def test_gpu_arm_json_fields_are_documented_in_the_source():
+    """The GPU arm cannot run here; pin the keys it emits by reading the source: the driver's contract keys plus the
+    roofline objects of DESIGN.md §4."""
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    for key in ('"roofline"', '"roofline_plain"', '"cpu_baseline"', '"e2e"', '"gpu_launches"', '"clocks"', '"h2d_bytes_per_step"',
+                '"frac_vs_spec"', '"crs_bytes_per_launch"', '"traffic"', '"history"', '"scaling": "strong" if strong else "weak"'):
+        assert key in src, key

@@ -123,6 +123,36 @@ def test_interfaces_2x2x2_symmetry():
     assert owned == (2 * 2 ** refs + 1) ** 3
 
 
+@pytest.mark.parametrize("part", [(2, 1, 1), (2, 2, 1), (2, 2, 2)])
+def test_strong_scaling_partitions_of_one_global_grid(part):
+    """bench.py --scaling strong: the SAME global grid (2x2x2 base cells) on every process grid.  All ranks in one process:
+    the local boxes tile the global grid (owned DoFs sum to its size), the additive right-hand sides sum to the serial
+    one, and — the point of the round-2 generator change — the solution is O(1) on the partition planes."""
+    sys.path.insert(0, ROOT)
+    from ugcore_b200 import dist as ugdist
+    refs, base = 3, (2, 2, 2)
+    world = part[0] * part[1] * part[2]
+    gprob = ugdist.global_problem(refs, part, base=base)
+    assert gprob.dims(refs) == (17, 17, 17)
+    probs = [ugdist.local_problem(refs, part, r, base=base) for r in range(world)]
+    acc = np.zeros(gprob.num_dofs)
+    owned = 0
+    for r, p in enumerate(probs):
+        gid = p.global_ids(refs)
+        np.add.at(acc, gid, np.array(p.rhs()))
+        owned += int(ugdist.owned_mask(p, refs, r).sum())
+        assert p.dims(refs) == tuple(16 // part[d] + 1 for d in range(3))
+    assert owned == 17 ** 3
+    assert np.allclose(acc, np.array(gprob.rhs()), rtol=1e-13, atol=1e-18)
+    ex = np.array(gprob.exact()).reshape(17, 17, 17)            # [k][j][i]
+    assert np.abs(ex[:, :, 8]).max() > 0.4 * np.abs(ex).max()   # the plane x = 1 between the two boxes in x
+    with pytest.raises(ValueError):
+        ugdist.local_problem(refs, (3, 1, 1), 0, base=base)     # 3 does not divide 2 base cells
+    # the gather rule sees the real local box: 129^3 per rank at refs 7 on 2x2x2 -> level 5, one rank with 257^3 -> level 4
+    assert ugdist.default_gather_level(7, (2, 2, 2), global_base=base) == 5
+    assert ugdist.default_gather_level(7, (2, 1, 1), global_base=base) <= 5
+
+
 def _comp(idx, b):
     idx = np.asarray(idx)
     return np.repeat(idx * b, b) + np.tile(np.arange(b), idx.size)
