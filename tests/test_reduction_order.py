@@ -9,10 +9,11 @@ sequential reductions and once with a pairwise tree over the same products (orac
 everything else bit-identical.  The measured movement is the yardstick for the tolerances in the GPU tests
 (tests/test_gpu_solver.py: hist_tol) and is committed as tests/golden/reduction_order_sensitivity.json.
 
-Findings (33^3 nodes, see the JSON): CG + GMG moves by <= 5e-12 per step -> 1e-10 holds with margin.
-BiCGStab + GMG moves by up to 4e-10 at 33^3 on Poisson and grows with the problem size: the reference itself
-cannot hold 1e-10 under a reordered sum, so BiCGStab histories are compared with
-max(1e-10, 10 x measured movement of the reference on the same problem)."""
+Findings (see the JSON): CG + GMG moves by <= 2e-11 per step up to 65^3, 3.7e-11 at 129^3 and 1.04e-10 at 257^3 (the
+error of a sequential sum grows with its length) -> 1e-10 holds with margin up to configs[1] and is exactly the
+reference's own noise level at configs[2].  BiCGStab + GMG(Jacobi) moves by 4e-10 at 33^3 and 1.5e-8 at 65^3 on
+Poisson: the reference itself cannot hold 1e-10 under a reordered sum there, so histories are compared with
+max(1e-10, 10 x measured movement of the reference on the same problem) (helpers.sens_tol)."""
 import json
 import os
 
@@ -85,14 +86,41 @@ def test_reference_history_sensitivity_matches_the_committed_measurement():
 def test_cg_holds_1e10_and_bicgstab_does_not_under_reordered_sums():
     with open(GOLDEN) as f:
         want = json.load(f)
-    cg = [v["max_rel_move"] for k, v in want.items() if k.startswith("cg_")]
+    cg = [v["max_rel_move"] for k, v in want.items() if k.startswith("cg_") and "257^3" not in k]
     bi = [v["max_rel_move"] for k, v in want.items() if k.startswith("bicgstab_gmg_jacobi")]
-    assert max(cg) < 5e-11          # CG: 1e-10 per iteration is attainable with margin
+    assert max(cg) < 5e-11          # CG up to 129^3: 1e-10 per iteration is attainable with margin (257^3: see below)
     assert max(bi) > 1e-10          # BiCGStab: the reference itself moves by more than north_star's tolerance
 
 
-if __name__ == "__main__":   # regenerate the committed measurement: python tests/test_reduction_order.py
+def test_full_size_entries_explain_the_gpu_deviation():
+    """The two full-size entries (129^3: 16 s, 257^3: 136 s and 20 GB on the CPU — generated once by
+    `python tests/test_reduction_order.py --full`, not recomputed here): the reference's own CG history moves by 3.66e-11
+    at 129^3 and 1.04e-10 at 257^3 when only its summation order changes — the very numbers by which the B200 history
+    differs from it (bench.py history_rel_err_vs_cpu: 3.67e-11 / 1.04e-10, profiles/r02h, r02f): the deviation is the
+    rounding of ugcore's sequential sums, not of the device path."""
+    with open(GOLDEN) as f:
+        want = json.load(f)
+    a, b = want["cg_gmg_jacobi_poisson@129^3"], want["cg_gmg_jacobi_poisson@257^3 (2x2x2 base cells)"]
+    assert a["steps"] == 8 and b["steps"] == 8
+    assert 3e-11 < a["max_rel_move"] < 5e-11 and 0.9e-10 < b["max_rel_move"] < 1.2e-10
+
+
+if __name__ == "__main__":   # regenerate the committed measurement: python tests/test_reduction_order.py [--full]
+    import sys
+    full = {}
+    if "--full" in sys.argv:
+        orc = oracle.Oracle("ref" if oracle.have_ref() else "port")
+        for name, mk in (("cg_gmg_jacobi_poisson@129^3", lambda: pr.Problem(dim=3, num_refs=7)),
+                         ("cg_gmg_jacobi_poisson@257^3 (2x2x2 base cells)", lambda: pr.Problem(dim=3, num_refs=7, base=(2, 2, 2)))):
+            p = mk()
+            sens, h0, h1 = reduction_order_sensitivity(orc, p, gmg_desc(7), np.array(p.rhs()))
+            full[name] = {"steps": len(h0) - 1, "steps_reordered": len(h1) - 1, "max_rel_move": float(sens.max()),
+                          "per_step": [float(v) for v in sens], "backend": orc.kind}
+    else:
+        with open(GOLDEN) as f:
+            full = {k: v for k, v in json.load(f).items() if "129^3" in k or "257^3" in k}
     res = _measure((3, 4, 5, 6))
+    res.update(full)
     with open(GOLDEN, "w") as f:
         json.dump(res, f, indent=1)
     for k, v in res.items():
