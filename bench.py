@@ -327,7 +327,7 @@ def kernel_roofline(s, prob, top, peak_gbs, peak_src):
 def workload_roofline(workload, prob, top, peak_gbs, peak_src):
     """Dominant kernel of the non-default workloads, timed alone like kernel_roofline:
     convdiff   — one forward multicolour Gauss-Seidel sweep over the colour-sorted top-level matrix
-                 (ug4b200_gs_step; a sweep reads every stored entry once: 12 nnz + 4(n+1) + 24 n bytes);
+                 (ug4b200_gs_step; a sweep reads the lower triangle incl. the diagonal: 12 nnz_lower + 4(n+1) + 24 n bytes);
     elasticity — y -= A x with 3x3 blocks (ug4b200_matrix_matmul_minus; (72+4) nnzb + 4(nb+1) + 72 nb bytes)."""
     import ctypes as C
     from ugcore_b200 import capi
@@ -371,8 +371,13 @@ def workload_roofline(workload, prob, top, peak_gbs, peak_src):
             capi.check(dev.ug4b200_matrix_upload_crs(ctx, 1, n, n, vp(rp), vp(ci), vp(va), 0, C.byref(m)), ctx)
             d, c = DeviceBuffer.from_numpy(rng.standard_normal(n)), DeviceBuffer.from_numpy(np.zeros(n))
             t = timeit(lambda: dev.ug4b200_gs_step(ctx, m, cptr.size - 1, vp(cptr), 0, C.c_double(1.0), c.ptr, d.ptr))
-            nbytes = 12 * nnz + 4 * (n + 1) + 24 * n
-            kname = f"gs_color_kernel x {cptr.size - 1} colours (ug4b200_gs_step, forward sweep, plain SELL-32 stream)"
+            # a forward sweep reads, per row, the connections up to and including the diagonal in the colour-sorted
+            # numbering (c_i = (d_i - sum_{j<i} a_ij c_j) / a_ii): about half of the stored entries — NOT the whole matrix
+            # (the lines of profiles/r02a, r02f, r02h counted 12 * nnz and overstated this fraction by 1.8x)
+            n_lower = int(np.count_nonzero(pc_ <= pr_))
+            nbytes = 12 * n_lower + 4 * (n + 1) + 24 * n
+            kname = (f"gs_color_kernel x {cptr.size - 1} colours (ug4b200_gs_step, forward sweep, plain SELL-32 stream; "
+                     f"{n_lower} of {nnz} entries read)")
         else:
             capi.check(dev.ug4b200_matrix_upload_crs(ctx, b, n, n, vp(A.rowptr), vp(A.cols), vp(A.vals), 0, C.byref(m)), ctx)
             y, x = DeviceBuffer.from_numpy(rng.standard_normal(n * b)), DeviceBuffer.from_numpy(rng.standard_normal(n * b))
