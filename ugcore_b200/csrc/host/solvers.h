@@ -610,8 +610,9 @@ class LinearSolver : public IPreconditionedLinearOperatorInverse<TVector> {
 	using base_type::preconditioner;
 	virtual const char* name() const { return "Iterative Linear Solver"; }
 	~LinearSolver() { drop_graph(); }
-	/// true: the convergence state stays on the device and one iteration (c = B d, d -= A c, x += c, ||d||) is a CUDA
-	/// graph, like CG::apply_device; false (default until measured): the reference-shaped loop, one host sync per step
+	/// true (default, like CG and BiCGStab): the convergence state stays on the device and one iteration (c = B d,
+	/// d -= A c, x += c, ||d||) is a CUDA graph; false: the reference-shaped loop, one host sync per step — identical
+	/// histories and iterates (tests/test_ilu.py: test_gpu_device_resident_linear_solver_equals_host_loop)
 	void set_device_resident(bool b) { m_deviceResident = b; }
 	void set_use_graph(bool b) { m_useGraph = b; }
 	virtual bool apply_return_defect(vector_type& x, vector_type& b)
@@ -702,7 +703,7 @@ class LinearSolver : public IPreconditionedLinearOperatorInverse<TVector> {
 		if (m_graph && GPUManager::ctx_or_null()) ug4b200_graph_destroy(GPUManager::ctx_or_null(), m_graph);
 		m_graph = nullptr;
 	}
-	bool m_deviceResident = false, m_useGraph = true;
+	bool m_deviceResident = true, m_useGraph = true;
 	KS m_ks;
 	ug4b200_graph* m_graph = nullptr;
 	unsigned long long m_graphGen = 0;   // GPUManager::generation() the graph was captured under

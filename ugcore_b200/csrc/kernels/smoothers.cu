@@ -131,7 +131,7 @@ gs_color_kernel(Sell A, int64_t r0, int64_t r1, double relax, double* c, const d
 }
 
 // ---- dense LU apply, one CTA ---------------------------------------------------------
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 lu_apply_kernel(int n, const double* __restrict__ lu, const int* __restrict__ piv, double* x, const double* b,
                 const int* guard)
 {
@@ -154,13 +154,11 @@ lu_apply_kernel(int n, const double* __restrict__ lu, const int* __restrict__ pi
 	// operations (measured: 28 ms per base solve at n = 1029, the 7^3 x 3 base grid of the partitioned elasticity run).
 	// Up to kLuExactMax unknowns (every base grid of one to 2x2x2 cells, scalar) that chain is kept here and the result
 	// equals SolveLU bit for bit; larger systems go to lu_apply_large_kernel (column-oriented, parallel).
-	{
-		if (threadIdx.x == 0) {
-			for (int i = n - 1; i >= 0; --i) {
-				double s = sx[i];
-				for (int k = i + 1; k < n; ++k) s = s - lu[(size_t)i * n + k] * sx[k];
-				sx[i] = s / lu[(size_t)i * n + i];
-			}
+	if (threadIdx.x == 0) {
+		for (int i = n - 1; i >= 0; --i) {
+			double s = sx[i];
+			for (int k = i + 1; k < n; ++k) s = s - lu[(size_t)i * n + k] * sx[k];
+			sx[i] = s / lu[(size_t)i * n + i];
 		}
 	}
 	__syncthreads();
@@ -422,7 +420,7 @@ int ug4b200_lu_apply(ug4b200_ctx* ctx, int n, const double* lu_dev, const int* p
 		UgBatchOp o{}; o.kind = UG_OP_LU; o.n = n; o.vals = lu_dev; o.cols = piv_dev; o.dest = x; o.w = b;
 		return ug_batch_push(ctx, o);
 	}
-	UG_LAUNCH(ctx, lu_apply_kernel, 1, n > 256 ? 1024 : 256, sizeof(double) * n, n, lu_dev, piv_dev, x, b, ctx->guard);
+	UG_LAUNCH(ctx, lu_apply_kernel, 1, 256, sizeof(double) * n, n, lu_dev, piv_dev, x, b, ctx->guard);
 	return UG4B200_OK;
 }
 

@@ -610,7 +610,7 @@ int ug4b200_matrix_upload_crs(ug4b200_ctx* ctx, int block, int64_t nrows, int64_
 	//   value-indexed (vc):  word = column offset from the slice's smallest column << 16 | index << vshift; needs every
 	//                        slice's columns within 65535 of its smallest column (129^3 lexicographic: yes; 257^3: no)
 	//   x-staged (xw):       word = position of the column in the slice's staged x segment << 16 | index << 3; needs
-	//                        <= 256 values, rows of <= 27 entries and per slice <= 16 runs / 352 doubles of columns
+	//                        <= 256 values, rows of <= 27 entries and per slice <= 32 runs / 384 doubles of columns
 	//                        (any banded numbering of a structured grid, whatever its size)
 	// Otherwise the plain 12-byte stream is used.
 	std::vector<unsigned int> hvc; std::vector<int> hcb; std::vector<double> hdict;
