@@ -224,6 +224,26 @@ typedef struct ug4b200_matrix_info {
 
 int ug4b200_matrix_upload_crs(ug4b200_ctx* ctx, int block, int64_t nrows, int64_t ncols, const int64_t* rowptr,
                               const int* cols, const double* vals, int flags, ug4b200_matrix** out);
+
+/* Which entry streams ug4b200_matrix_upload_crs would build for a scalar CRS matrix, and why not — host only, no
+ * device, no context (diagnosis: "why does my matrix run at 12 bytes per entry?").  Optionally returns the x-staged
+ * stream itself for inspection: xw [padded_nnz] words (position << 16 | dictionary index << 3), hdr [4 * num_slices]
+ * ints {entry offset / 32, width, staged bytes, runs}, runs [2 * num_slices * x_staged_runs] ints {first column,
+ * doubles | position << 16}, dict [num_distinct_values] doubles; any of them may be NULL.  Call once with NULL arrays
+ * to size them. */
+typedef struct ug4b200_stream_plan {
+	int64_t num_slices, padded_nnz;
+	int max_row_len;
+	int num_distinct_values;      /* -1: more than 65536 distinct values -> plain 12-byte stream */
+	int64_t max_column_window;    /* largest (max - min column) of a slice; the value-indexed stream needs <= 65535 */
+	int value_indexed;            /* 1: the value-indexed stream would be built */
+	int x_staged;                 /* 1: the x-staged stream could be built (dictionary <= 256, rows <= 27 entries, runs fit) */
+	int x_staged_runs;            /* run slots per slice it needs (limit 32) */
+	int x_staged_max_doubles;     /* widest staged x segment (limit 384) */
+	int64_t x_staged_doubles;     /* staged doubles summed over the slices */
+} ug4b200_stream_plan;
+int ug4b200_host_stream_plan(int64_t nrows, int64_t ncols, const int64_t* rowptr, const int* cols, const double* vals,
+                             ug4b200_stream_plan* plan, unsigned int* xw, int* hdr, int* runs, double* dict);
 int ug4b200_matrix_destroy(ug4b200_ctx* ctx, ug4b200_matrix* A);
 int ug4b200_matrix_get_info(const ug4b200_matrix* A, ug4b200_matrix_info* info);
 

@@ -43,6 +43,12 @@ class MatrixInfo(C.Structure):
                 ("num_distinct_values", c_int), ("x_staged", c_int), ("x_staged_runs", c_int), ("x_staged_doubles", c_i64)]
 
 
+class StreamPlan(C.Structure):
+    _fields_ = [("num_slices", c_i64), ("padded_nnz", c_i64), ("max_row_len", c_int), ("num_distinct_values", c_int),
+                ("max_column_window", c_i64), ("value_indexed", c_int), ("x_staged", c_int), ("x_staged_runs", c_int),
+                ("x_staged_max_doubles", c_int), ("x_staged_doubles", c_i64)]
+
+
 class SolverDesc(C.Structure):
     _fields_ = [("block", c_int), ("solver", c_int), ("precond", c_int), ("damp", c_dbl),
                 ("max_steps", c_int), ("min_defect", c_dbl), ("rel_reduction", c_dbl),
@@ -111,6 +117,7 @@ DEV_API = {
     "ug4b200_matrix_upload_crs": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_int, C.POINTER(c_vp)]),
     "ug4b200_matrix_destroy": (c_int, [c_vp, c_vp]),
     "ug4b200_matrix_get_info": (c_int, [c_vp, C.POINTER(MatrixInfo)]),
+    "ug4b200_host_stream_plan": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, C.POINTER(StreamPlan), c_vp, c_vp, c_vp, c_vp]),
     "ug4b200_matrix_axpy": (c_int, [c_vp, c_vp, c_vp, c_dbl, c_vp, c_dbl, c_vp, c_int]),
     "ug4b200_matrix_apply": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int]),
     "ug4b200_matrix_matmul_minus": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int]),

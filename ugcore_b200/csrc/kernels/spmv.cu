@@ -530,6 +530,74 @@ __global__ void jacobi_invert_kernel(int64_t nrows, int B, double invdamp, int b
 #undef II
 }
 
+// ---- x-staged stream, host side (shared by ug4b200_matrix_upload_crs and ug4b200_host_stream_plan) ----
+// Per slice the sorted distinct columns are grouped into runs of consecutive columns (gaps of <= 2 merged, ends aligned
+// to 16 bytes); the words then carry the position of their column in the concatenation of the runs.  Any banded numbering
+// of a structured grid gives a handful of runs per slice (27-point operator, lexicographic: 9 runs of 34 columns).
+struct XsPlan {
+	bool ok = false;
+	int rmax = 0;                  // run slots per slice actually needed (stride of `runs`)
+	int max_doubles = 0;           // widest staged x segment
+	int64_t doubles = 0;           // staged doubles summed over the slices
+	std::vector<unsigned int> xw;  // [pnnz] position << 16 | dictionary index << 3
+	std::vector<int4> hdr;         // [ns] {entry offset / 32, width, staged bytes, runs}
+	std::vector<int2> runs;        // [ns * rmax] {first column (even), doubles (even) | position << 16}
+};
+void build_xs_plan(int64_t nrows, int64_t ns, int64_t pnnz, const int64_t* sp, const int64_t* rowptr, const int* cols,
+                   const double* vals, const std::unordered_map<uint64_t, unsigned short>& dict, XsPlan& out)
+{
+	const int RMAX = tma_xs_max_runs(), XCAP = tma_xs_max_doubles();
+	std::vector<unsigned int>& hxw = out.xw; hxw.assign((size_t)pnnz, 0u);
+	std::vector<int4>& hh = out.hdr; hh.assign((size_t)ns, make_int4(0, 0, 0, 0));
+	std::vector<int2> hr((size_t)ns * RMAX, make_int2(0, 0));
+	bool xok = true; int rmaxUsed = 1, maxDoubles = 0; int64_t xtotal = 0;
+#pragma omp parallel for schedule(static) reduction(&& : xok) reduction(max : rmaxUsed, maxDoubles) reduction(+ : xtotal)
+	for (int64_t s = 0; s < ns; ++s) {
+		const int64_t base = sp[s];
+		const int width = (int)((sp[s + 1] - base) >> 5);
+		hh[s] = make_int4((int)(base >> 5), width, 0, 0);
+		std::vector<int> cs;
+		for (int l = 0; l < 32; ++l) {
+			const int64_t r = s * 32 + l;
+			if (r >= nrows) break;
+			for (int64_t p = rowptr[r]; p < rowptr[r + 1]; ++p) cs.push_back(cols[p]);
+		}
+		if (cs.empty()) continue;
+		std::sort(cs.begin(), cs.end());
+		cs.erase(std::unique(cs.begin(), cs.end()), cs.end());
+		int ra[64], rb[64], rd[64]; int nr = 0, tot = 0;   // run [ra, rb) staged at double index rd
+		bool fit = true;
+		for (size_t i = 0; i < cs.size(); ++i) {
+			const int c = cs[i];
+			if (nr > 0 && c < rb[nr - 1] + 3) { rb[nr - 1] = (c + 2) & ~1; continue; }   // extend (gap <= 2: cheaper than a new copy)
+			if (nr == RMAX) { fit = false; break; }
+			ra[nr] = c & ~1; rb[nr] = (c + 2) & ~1; ++nr;
+		}
+		if (fit) for (int q = 0; q < nr; ++q) { rd[q] = tot; tot += rb[q] - ra[q]; }
+		if (!fit || tot > XCAP) { xok = false; continue; }
+		for (int q = 0; q < nr; ++q) hr[(size_t)s * RMAX + q] = make_int2(ra[q], (rb[q] - ra[q]) | (rd[q] << 16));
+		hh[s].z = tot * 8; hh[s].w = nr;
+		if (nr > rmaxUsed) rmaxUsed = nr;
+		if (tot > maxDoubles) maxDoubles = tot;
+		xtotal += tot;
+		for (int l = 0; l < 32; ++l) {
+			const int64_t r = s * 32 + l;
+			if (r >= nrows) break;
+			int q = 0;
+			for (int64_t p = rowptr[r], k = 0; p < rowptr[r + 1]; ++p, ++k) {
+				while (cols[p] >= rb[q]) ++q;     // columns ascend inside a row, runs ascend
+				uint64_t bits; std::memcpy(&bits, &vals[p], 8);
+				hxw[base + k * 32 + l] = ((unsigned int)(rd[q] + cols[p] - ra[q]) << 16) | ((unsigned int)dict.find(bits)->second << 3);
+			}
+		}
+	}
+	out.ok = xok; out.rmax = rmaxUsed; out.max_doubles = maxDoubles; out.doubles = xtotal;
+	if (!xok) return;
+	// keep only the run slots any slice uses (stride of the run table)
+	out.runs.resize((size_t)ns * rmaxUsed);
+	for (int64_t s2 = 0; s2 < ns; ++s2) for (int q = 0; q < rmaxUsed; ++q) out.runs[(size_t)s2 * rmaxUsed + q] = hr[(size_t)s2 * RMAX + q];
+}
+
 } // namespace
 
 extern "C" {
@@ -673,58 +741,13 @@ int ug4b200_matrix_upload_crs(ug4b200_ctx* ctx, int block, int64_t nrows, int64_
 			// of their column in the concatenation of the runs.  Any banded numbering of a structured grid gives a
 			// handful of runs per slice (27-point operator, lexicographic: 9 runs of 34 columns).
 			if (!rc && want_xs && !ctx->no_xs && !(flags & UG4B200_MAT_NO_XSTAGE) && hdict.size() <= (size_t)tma_xs_max_dict() && maxlen <= tma_xs_max_width()) {
-				const int RMAX = tma_xs_max_runs(), XCAP = tma_xs_max_doubles();
-				std::vector<unsigned int> hxw((size_t)pnnz, 0u);
-				std::vector<int4> hh((size_t)ns);
-				std::vector<int2> hr((size_t)ns * RMAX, make_int2(0, 0));
-				bool xok = true; int rmaxUsed = 1; int64_t xtotal = 0;
-#pragma omp parallel for schedule(static) reduction(&& : xok) reduction(max : rmaxUsed) reduction(+ : xtotal)
-				for (int64_t s = 0; s < ns; ++s) {
-					const int64_t base = sp[s];
-					const int width = (int)((sp[s + 1] - base) >> 5);
-					hh[s] = make_int4((int)(base >> 5), width, 0, 0);
-					std::vector<int> cs;
-					for (int l = 0; l < 32; ++l) {
-						const int64_t r = s * 32 + l;
-						if (r >= nrows) break;
-						for (int64_t p = rowptr[r]; p < rowptr[r + 1]; ++p) cs.push_back(cols[p]);
-					}
-					if (cs.empty()) continue;
-					std::sort(cs.begin(), cs.end());
-					cs.erase(std::unique(cs.begin(), cs.end()), cs.end());
-					int ra[64], rb[64], rd[64]; int nr = 0, tot = 0;   // run [ra, rb) staged at double index rd
-					bool fit = true;
-					for (size_t i = 0; i < cs.size(); ++i) {
-						const int c = cs[i];
-						if (nr > 0 && c < rb[nr - 1] + 3) { rb[nr - 1] = (c + 2) & ~1; continue; }   // extend (gap <= 2: cheaper than a new copy)
-						if (nr == RMAX) { fit = false; break; }
-						ra[nr] = c & ~1; rb[nr] = (c + 2) & ~1; ++nr;
-					}
-					if (fit) for (int q = 0; q < nr; ++q) { rd[q] = tot; tot += rb[q] - ra[q]; }
-					if (!fit || tot > XCAP) { xok = false; continue; }
-					for (int q = 0; q < nr; ++q) hr[(size_t)s * RMAX + q] = make_int2(ra[q], (rb[q] - ra[q]) | (rd[q] << 16));
-					hh[s].z = tot * 8; hh[s].w = nr;
-					if (nr > rmaxUsed) rmaxUsed = nr;
-					xtotal += tot;
-					for (int l = 0; l < 32; ++l) {
-						const int64_t r = s * 32 + l;
-						if (r >= nrows) break;
-						int q = 0;
-						for (int64_t p = rowptr[r], k = 0; p < rowptr[r + 1]; ++p, ++k) {
-							while (cols[p] >= rb[q]) ++q;     // columns ascend inside a row, runs ascend
-							uint64_t bits; std::memcpy(&bits, &vals[p], 8);
-							hxw[base + k * 32 + l] = ((unsigned int)(rd[q] + cols[p] - ra[q]) << 16) | ((unsigned int)dict.find(bits)->second << 3);
-						}
-					}
-				}
-				if (xok) {
-					// keep only the run slots any slice uses (stride of the run table)
-					std::vector<int2> hr2((size_t)ns * rmaxUsed);
-					for (int64_t s2 = 0; s2 < ns; ++s2) for (int q = 0; q < rmaxUsed; ++q) hr2[(size_t)s2 * rmaxUsed + q] = hr[(size_t)s2 * RMAX + q];
-					if (!rc) rc = up((void**)&A->xw, hxw.data(), sizeof(unsigned int) * hxw.size());
-					if (!rc) rc = up((void**)&A->xs_hdr, hh.data(), sizeof(int4) * hh.size());
-					if (!rc) rc = up((void**)&A->xs_runs, hr2.data(), sizeof(int2) * hr2.size());
-					if (!rc) { A->xs = true; A->xs_rmax = rmaxUsed; A->xs_doubles = xtotal; }
+				XsPlan xp;
+				build_xs_plan(nrows, ns, pnnz, sp.data(), rowptr, cols, vals, dict, xp);
+				if (xp.ok) {
+					if (!rc) rc = up((void**)&A->xw, xp.xw.data(), sizeof(unsigned int) * xp.xw.size());
+					if (!rc) rc = up((void**)&A->xs_hdr, xp.hdr.data(), sizeof(int4) * xp.hdr.size());
+					if (!rc) rc = up((void**)&A->xs_runs, xp.runs.data(), sizeof(int2) * xp.runs.size());
+					if (!rc) { A->xs = true; A->xs_rmax = xp.rmax; A->xs_doubles = xp.doubles; }
 					if (!rc) { const cudaError_t e = cudaStreamSynchronize(ctx->stream); if (e != cudaSuccess) rc = ug4b200_fail(ctx, UG4B200_ERR_CUDA, cudaGetErrorString(e)); }
 				}
 			}
@@ -733,6 +756,57 @@ int ug4b200_matrix_upload_crs(ug4b200_ctx* ctx, int block, int64_t nrows, int64_
 	if (rc) { ug4b200_matrix_destroy(ctx, A); return rc; }
 	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // host staging buffers die here
 	*out = A;
+	return UG4B200_OK;
+}
+
+int ug4b200_host_stream_plan(int64_t nrows, int64_t ncols, const int64_t* rowptr, const int* cols, const double* vals,
+                             ug4b200_stream_plan* plan, unsigned int* xw, int* hdr, int* runs, double* dictOut)
+{
+	if (!plan || !rowptr || nrows < 0 || ncols < 0) return ug4b200_fail(nullptr, UG4B200_ERR_ARG, "ug4b200_host_stream_plan: bad argument");
+	const int64_t nnz = rowptr[nrows];
+	if (nnz > 0 && (!cols || !vals)) return ug4b200_fail(nullptr, UG4B200_ERR_ARG, "ug4b200_host_stream_plan: cols / vals are NULL");
+	const int64_t ns = (nrows + 31) / 32;
+	std::vector<int64_t> sp((size_t)ns + 1, 0);
+	int maxlen = 0; int64_t window = 0;
+	for (int64_t s = 0; s < ns; ++s) {
+		int w = 0, lo = 2147483647, hi = -1;
+		for (int l = 0; l < 32; ++l) {
+			const int64_t r = s * 32 + l;
+			if (r >= nrows) break;
+			const int len = (int)(rowptr[r + 1] - rowptr[r]);
+			if (len > w) w = len;
+			if (len > 0) { lo = std::min(lo, cols[rowptr[r]]); hi = std::max(hi, cols[rowptr[r + 1] - 1]); }
+		}
+		sp[s + 1] = sp[s] + (int64_t)w * 32;
+		if (w > maxlen) maxlen = w;
+		if (hi >= 0 && (int64_t)hi - lo > window) window = (int64_t)hi - lo;
+	}
+	*plan = ug4b200_stream_plan{};
+	plan->num_slices = ns; plan->padded_nnz = sp[ns]; plan->max_row_len = maxlen; plan->max_column_window = window;
+	std::unordered_map<uint64_t, unsigned short> dict;
+	std::vector<double> hdict;
+	bool ok = true;
+	for (int64_t p = 0; p < nnz; ++p) {
+		uint64_t bits; std::memcpy(&bits, &vals[p], 8);
+		if (dict.find(bits) == dict.end()) {
+			if (dict.size() >= 65536) { ok = false; break; }
+			dict.emplace(bits, (unsigned short)dict.size());
+			hdict.push_back(vals[p]);
+		}
+	}
+	plan->num_distinct_values = ok ? (int)hdict.size() : -1;
+	if (!ok || sp[ns] == 0) return UG4B200_OK;
+	plan->value_indexed = window <= 65535 ? 1 : 0;
+	if (dictOut) std::memcpy(dictOut, hdict.data(), sizeof(double) * hdict.size());
+	if (hdict.size() > (size_t)tma_xs_max_dict() || maxlen > tma_xs_max_width()) return UG4B200_OK;
+	XsPlan xp;
+	build_xs_plan(nrows, ns, sp[ns], sp.data(), rowptr, cols, vals, dict, xp);
+	plan->x_staged = xp.ok ? 1 : 0; plan->x_staged_runs = xp.rmax; plan->x_staged_max_doubles = xp.max_doubles;
+	plan->x_staged_doubles = xp.doubles;
+	if (!xp.ok) return UG4B200_OK;
+	if (xw) std::memcpy(xw, xp.xw.data(), sizeof(unsigned int) * xp.xw.size());
+	if (hdr) std::memcpy(hdr, xp.hdr.data(), sizeof(int4) * xp.hdr.size());
+	if (runs) std::memcpy(runs, xp.runs.data(), sizeof(int2) * xp.runs.size());
 	return UG4B200_OK;
 }
 
