@@ -19,10 +19,13 @@ GPUs; parallel efficiency = T1 / (P TP).  `--order hier` numbers the DoFs the wa
 
 `--impl reference` times ugcore's own CPU kernels (oracle/_ref: SparseMatrix/Vector/
 smoother templates compiled from the reference) driving the restated solver loop on ALL
-host cores: the reference has no threading on this path and no MPI is installed, so every
-core runs one serial solve of the workload concurrently (an upper bound for the MPI path:
-no interface exchange).  This and `cpu_baseline` are the only places bench.py executes
-anything under oracle/.
+host cores; the reference has no threading on this path and no MPI is installed.
+  N = 1 : every core runs one serial solve of the workload concurrently.
+  N > 1 : the SAME global grid the N GPUs solve, partitioned over N processes per job with ugcore's parallel
+          protocol (additive matrices, consistent / additive / unique vectors, gathered coarse levels; interface
+          exchange through shared memory: oracle/partitioned.py), as many jobs side by side as cores and memory
+          carry.  `--cpu-arm replicas` keeps the exchange-free replicas of one GPU's box (an upper bound).
+This and `cpu_baseline` are the only places bench.py executes anything under oracle/.
 """
 from __future__ import annotations
 
@@ -202,28 +205,86 @@ def host_cores():
         return max(1, os.cpu_count() or 1)
 
 
+def cpu_partitioned(refs, part, gbase, nproc, steps, warmup, workload="poisson", order=0):
+    """The N-GPU grid on the CPU, partitioned like ugcore's MPI run (oracle/partitioned.py): the
+    same process grid as the GPUs (the generator's base grid admits no finer one), one process per sub-box with its
+    additive matrices, ugcore's consistent / additive / unique protocol, interface exchange through shared memory; as
+    many such jobs side by side as the host cores and memory carry, so that all cores work.  Aggregate MDoF/s."""
+    from oracle import partitioned
+    spec = workload_spec(workload)
+    world = int(np.prod(part))
+    n_global = int(np.prod([gbase[d] * 2 ** refs + 1 for d in range(3)])) * spec["block"]
+    b = spec["block"]
+    job_bytes = int(2 * 1.25 * (8.0 / 7.0) * 27 * (n_global // b) * (8 * b * b + 4))
+    jobs = max(1, nproc // world)
+    try:
+        with open("/proc/meminfo") as f:
+            avail = next(int(l.split()[1]) * 1024 for l in f if l.startswith("MemAvailable"))
+        jobs = max(1, min(jobs, int(0.4 * avail / max(job_bytes, 1))))
+    except Exception:
+        pass
+    kw = dict(spec["kw"], base=tuple(gbase), order=order)
+    res = partitioned.run(part, refs, solver_desc(refs, workload=workload), steps=steps, warmup=warmup, jobs=jobs,
+                          problem=spec["problem"], **kw)
+    dt = max(r["dt"] for job in res for r in job)
+    r0 = res[0][0]
+    return {"value": jobs * steps * n_global / dt / 1e6, "dt_per_step": dt / steps, "its": len(r0["hist"]) - 1, "n": n_global,
+            "kind": "reference" if r0["kind"] == "ref" else "port", "cores": jobs * world, "jobs": jobs, "ranks": world,
+            "gather": r0["gather"], "hist": r0["hist"]}
+
+
 def run_reference(args):
-    """CPU arm: ugcore's own kernels (oracle/_ref, else the port) on all host cores."""
+    """CPU arm: ugcore's own kernels (oracle/_ref, else the port) on all host cores.  N = 1: concurrent serial solves of
+    the one-GPU workload.  N > 1 (CG + GMG-Jacobi workloads): the same global grid the N GPUs solve, partitioned over N
+    CPU processes per job (cpu_partitioned); `--cpu-arm replicas` keeps the exchange-free replicas of one GPU's box."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     refs = args.cpu_refs if args.cpu_refs is not None else args.refs
     nproc = args.cpu_procs or host_cores()
     spec = workload_spec(args.workload)
-    bmult = 2 * args.base_mult if args.scaling == "strong" else args.base_mult
     order = {"lex": 0, "hier": 1}[args.order]
-    r = cpu_replicas(refs, nproc, args.steps, args.warmup, args.workload, bmult, order)
+    strong = args.scaling == "strong"
+    part = PART[args.gpus]
+    arm = args.cpu_arm
+    if arm == "auto":
+        arm = "partitioned" if args.gpus > 1 and args.workload != "convdiff" else "replicas"
+    if arm == "partitioned":
+        if args.workload == "convdiff":
+            raise SystemExit("--cpu-arm partitioned: CG + GMG-Jacobi workloads only (poisson, elasticity)")
+        bm = args.base_mult
+        gbase = tuple(2 * bm for _ in range(3)) if strong else tuple(bm * p for p in part)
+        try:
+            r = cpu_partitioned(refs, part, gbase, nproc, args.steps, args.warmup, args.workload, order)
+        except Exception as e:
+            if args.cpu_arm != "auto":
+                raise
+            print(f"bench.py: partitioned CPU arm failed ({e!r}); falling back to --cpu-arm replicas", file=sys.stderr, flush=True)
+            args.cpu_arm = "replicas"
+            return run_reference(args)
+        n, its, val, dt = r["n"], r["its"], r["value"], r["dt_per_step"]
+        dims = "x".join(str(gbase[d] * 2 ** refs + 1) for d in range(3))
+        sample = (f"{r['jobs']} concurrent partitioned solves x {args.steps} steps of {spec['label']} {dims} nodes ({n} DoF, {its} "
+                  f"iterations, {dt:.2f} s per solve): each job = {r['ranks']} processes on the process grid {'x'.join(map(str, part))} "
+                  "of the GPU run, additive matrices, consistent/additive/unique vectors, interface exchange and all-reduce "
+                  f"through shared memory, levels <= {r['gather']} gathered on one process (ugcore's MPI path emulated, "
+                  "oracle/partitioned.py)")
+        what = f"{n} DoF per job, {r['jobs']} jobs x {r['ranks']} processes"
+    else:
+        bmult = 2 * args.base_mult if strong else args.base_mult
+        r = cpu_replicas(refs, nproc, args.steps, args.warmup, args.workload, bmult, order)
+        n, its, val, dt = r["n"], r["its"], r["value"], r["dt_per_step"]
+        nodes = bmult * 2 ** refs + 1
+        sample = (f"{r['cores']} concurrent serial solves x {args.steps} steps of {spec['label']} {nodes}^3 nodes ({n} DoF, {its} "
+                  f"iterations each, {dt:.2f} s per solve): one process per host core, no threads inside ugcore on this path, "
+                  "no MPI on the box -> no interface exchange (upper bound of the MPI weak-scaling throughput)")
+        what = f"{n} DoF per process, {r['cores']} processes"
     nproc = r["cores"]           # may have been reduced to fit the host memory
-    n, its, val, dt = r["n"], r["its"], r["value"], r["dt_per_step"]
-    nodes = bmult * 2 ** refs + 1
-    sample = (f"{nproc} concurrent serial solves x {args.steps} steps of {spec['label']} {nodes}^3 nodes ({n} DoF, {its} "
-              f"iterations each, {dt:.2f} s per solve): one process per host core, no threads inside ugcore on this path, "
-              "no MPI on the box -> no interface exchange (upper bound of the MPI weak-scaling throughput)")
     out = {"impl": "reference", "metric": spec["metric"], "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"{spec['label']} unit cube hexahedra numRefs={refs} ({n} DoF per process, {nproc} processes) "
-                                  f"{spec['method']}, base LU on level 0, ugcore CPU kernels", "iterations": its},
+           "config": {"workload": f"{spec['label']} unit cube hexahedra numRefs={refs} ({what}) "
+                                  f"{spec['method']}, base LU on level 0, ugcore CPU kernels", "iterations": its, "cpu_arm": arm},
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": nproc, "kind": r["kind"], "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
@@ -573,6 +634,9 @@ def main():
                     "on-device CG of north_star (single CTA, reduction 1e-14) — for base grids of many cells, where the dense triangular "
                     "solves of an LU are a serial latency chain on the device")
     ap.add_argument("--cpu-procs", type=int, default=0, help="processes of the CPU arm (0 = all host cores)")
+    ap.add_argument("--cpu-arm", default="auto", choices=["auto", "replicas", "partitioned"],
+                    help="CPU arm at --gpus N > 1: partitioned (auto for poisson / elasticity) = the N-GPU grid over N CPU processes "
+                         "per job with ugcore's parallel protocol; replicas = exchange-free serial solves of one GPU's box")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
