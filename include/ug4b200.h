@@ -244,6 +244,14 @@ typedef struct ug4b200_stream_plan {
 } ug4b200_stream_plan;
 int ug4b200_host_stream_plan(int64_t nrows, int64_t ncols, const int64_t* rowptr, const int* cols, const double* vals,
                              ug4b200_stream_plan* plan, unsigned int* xw, int* hdr, int* runs, double* dict);
+
+/* The value-indexed stream ug4b200_matrix_upload_crs would upload — host only, for inspection and tests: words
+ * [padded_nnz] = (column - colbase[slice]) << 16 | dictionary index << *vshift (dictionary = the `dict` of
+ * ug4b200_host_stream_plan; padding words 0), colbase [num_slices] = smallest column of the slice.  *vshift = -1 (and
+ * nothing written) when the matrix gets no such stream (column window > 65535, more than 65536 distinct values, no
+ * entries).  words / colbase may be NULL. */
+int ug4b200_host_value_indexed_stream(int64_t nrows, int64_t ncols, const int64_t* rowptr, const int* cols, const double* vals,
+                                      unsigned int* words, int* colbase, int* vshift);
 int ug4b200_matrix_destroy(ug4b200_ctx* ctx, ug4b200_matrix* A);
 int ug4b200_matrix_get_info(const ug4b200_matrix* A, ug4b200_matrix_info* info);
 

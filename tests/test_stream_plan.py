@@ -104,3 +104,108 @@ def test_plain_stream_cases():
     D = Crs(m, m, 1, np.arange(m + 1, dtype=np.int64), np.arange(m, dtype=np.int32), rng.standard_normal(m))
     p, _ = _plan(D)
     assert p.num_distinct_values == -1 and not p.value_indexed and not p.x_staged
+
+
+# ---- value-indexed stream and the value dictionary (host builder shared with ug4b200_matrix_upload_crs) ----
+
+def _vi(A):
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rp, ci, va = np.ascontiguousarray(A.rowptr, np.int64), np.ascontiguousarray(A.cols, np.int32), np.ascontiguousarray(A.vals)
+    p, _ = _plan(A)
+    words = np.zeros(max(p.padded_nnz, 1), np.uint32)
+    cb = np.zeros(max(p.num_slices, 1), np.int32)
+    vs = C.c_int(-7)
+    capi.check(capi.dev.ug4b200_host_value_indexed_stream(A.nrows, A.ncols, vp(rp), vp(ci), vp(va), vp(words), vp(cb), C.byref(vs)))
+    dic = np.zeros(max(p.num_distinct_values, 1))
+    if p.num_distinct_values > 0:
+        capi.check(capi.dev.ug4b200_host_stream_plan(A.nrows, A.ncols, vp(rp), vp(ci), vp(va), C.byref(p), None, None, None, vp(dic)))
+    return p, words[:p.padded_nnz], cb[:p.num_slices], vs.value, dic
+
+
+def _first_occurrence_order(vals):
+    bits = np.asarray(vals).view(np.int64)
+    _, first = np.unique(bits, return_index=True)
+    return np.asarray(vals)[np.sort(first)]
+
+
+@pytest.mark.parametrize("name", ["poisson3d", "convdiff3d", "prolongation", "random_300_values", "random_2000_values", "empty_rows"])
+def test_value_indexed_stream_is_a_lossless_reencoding(name):
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("make_stream_plan_golden", os.path.join(os.path.dirname(__file__), "golden", "make_stream_plan_golden.py"))
+    gold = importlib.util.module_from_spec(spec); spec.loader.exec_module(gold)
+    M = {"poisson3d": lambda: pr.Problem(dim=3, num_refs=3).matrix(),
+         "convdiff3d": lambda: pr.Problem(dim=3, num_refs=3, problem=pr.CONVDIFF, eps=1e-2).matrix(),
+         "prolongation": lambda: pr.Problem(dim=3, num_refs=3).prolongation(3),
+         "random_300_values": lambda: gold.random_crs(700, 9, 300, 1),
+         "random_2000_values": lambda: gold.random_crs(900, 12, 2000, 2),
+         "empty_rows": lambda: gold.matrices()["empty_rows"]}[name]()
+    p, words, cb, vshift, dic = _vi(M)
+    assert p.value_indexed and vshift == (3 if p.num_distinct_values <= 1024 else 0)
+    # the dictionary lists the values in the order a sequential scan of the CRS array first meets them (bit patterns:
+    # 0.0 and -0.0 are two entries) — the numbering the parallel scan has to reproduce
+    assert np.array_equal(dic.view(np.int64), _first_occurrence_order(M.vals).view(np.int64))
+    rowlen = np.diff(M.rowptr)
+    seen = np.zeros(p.padded_nnz, bool)
+    off = 0
+    for s in range(p.num_slices):
+        rows = np.arange(s * 32, min(s * 32 + 32, M.nrows))
+        width = int(rowlen[rows].max()) if rows.size else 0
+        lo = min((int(M.cols[M.rowptr[r]]) for r in rows if rowlen[r]), default=0)
+        assert cb[s] == lo
+        for r in rows:
+            k = np.arange(rowlen[r])
+            pos = off + k * 32 + (r - s * 32)
+            w = words[pos]
+            seen[pos] = True
+            assert np.array_equal((w >> 16).astype(np.int64) + lo, M.cols[M.rowptr[r]:M.rowptr[r + 1]])
+            got = dic[(w & 0xffff) >> vshift]
+            assert np.array_equal(got.view(np.int64), np.asarray(M.vals[M.rowptr[r]:M.rowptr[r + 1]]).view(np.int64))
+            if vshift:
+                assert np.all((w & 7) == 0)
+        off += width * 32
+    assert off == p.padded_nnz and np.all(words[~seen] == 0)          # padding: column base, dictionary entry 0
+
+
+def test_no_value_indexed_stream_beyond_the_limits():
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("make_stream_plan_golden", os.path.join(os.path.dirname(__file__), "golden", "make_stream_plan_golden.py"))
+    gold = importlib.util.module_from_spec(spec); spec.loader.exec_module(gold)
+    p, words, cb, vshift, dic = _vi(gold.random_crs(9000, 12, 70000, 3))       # > 65536 distinct values
+    assert p.num_distinct_values == -1 and not p.value_indexed and vshift == -1 and not words.any()
+    n = 70000                                                                   # one slice spans columns 0 .. 69999
+    wide = pr.Crs(n, n, 1, (np.arange(n + 1) * 2).astype(np.int64),
+                  np.stack([np.zeros(n, np.int32), np.full(n, n - 1, np.int32)], 1).ravel(), np.ones(2 * n))
+    p, words, cb, vshift, dic = _vi(wide)
+    assert p.max_column_window == n - 1 and not p.value_indexed and vshift == -1 and p.num_distinct_values == 1
+
+
+def test_large_matrix_dictionary_matches_the_sequential_scan():
+    """> 65536 entries: the scan runs in parallel chunks; values first met in late chunks must still be numbered in
+    global first-occurrence order."""
+    rng = np.random.default_rng(5)
+    n, per = 40000, 6
+    cols = (np.arange(n)[:, None] + np.arange(per)[None, :]) % n
+    cols.sort(axis=1)
+    pool = rng.standard_normal(5000)
+    idx = np.minimum(rng.integers(0, 5000, n * per), np.arange(n * per) // 40)   # new values keep appearing along the array
+    A = pr.Crs(n, n, 1, (np.arange(n + 1) * per).astype(np.int64), cols.ravel().astype(np.int32), pool[idx].copy())
+    p, words, cb, vshift, dic = _vi(A)
+    assert p.num_distinct_values == np.unique(idx).size and vshift == 0
+    assert np.array_equal(dic.view(np.int64), _first_occurrence_order(A.vals).view(np.int64))
+
+
+def test_stream_builder_reproduces_the_committed_hashes():
+    """tests/golden/stream_plan_hashes.json was written by the builder that the GPU suite validated (r02i); any later
+    change of the host-side builder has to reproduce every array bit for bit."""
+    import importlib.util
+    import json
+    import os
+    here = os.path.dirname(__file__)
+    spec = importlib.util.spec_from_file_location("make_stream_plan_golden", os.path.join(here, "golden", "make_stream_plan_golden.py"))
+    gold = importlib.util.module_from_spec(spec); spec.loader.exec_module(gold)
+    with open(os.path.join(here, "golden", "stream_plan_hashes.json")) as f:
+        want = json.load(f)
+    got = {k: gold.describe(A) for k, A in gold.matrices().items()}
+    assert got == want

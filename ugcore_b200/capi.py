@@ -118,6 +118,7 @@ DEV_API = {
     "ug4b200_matrix_destroy": (c_int, [c_vp, c_vp]),
     "ug4b200_matrix_get_info": (c_int, [c_vp, C.POINTER(MatrixInfo)]),
     "ug4b200_host_stream_plan": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, C.POINTER(StreamPlan), c_vp, c_vp, c_vp, c_vp]),
+    "ug4b200_host_value_indexed_stream": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, p_int]),
     "ug4b200_matrix_axpy": (c_int, [c_vp, c_vp, c_vp, c_dbl, c_vp, c_dbl, c_vp, c_int]),
     "ug4b200_matrix_apply": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int]),
     "ug4b200_matrix_matmul_minus": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int]),

@@ -19,8 +19,10 @@
 #include "../common.cuh"
 #include <algorithm>
 #include <cstring>
-#include <unordered_map>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace {
 
@@ -530,6 +532,130 @@ __global__ void jacobi_invert_kernel(int64_t nrows, int B, double invdamp, int b
 #undef II
 }
 
+// ---- value dictionary, host side ----------------------------------------------------------------------------------
+// The distinct values of a matrix as bit patterns (-0.0 and 0.0 stay distinct), numbered in the order a sequential scan
+// of the CRS value array first meets them.  Open addressing on a multiplicative hash; at most 65536 entries.
+// (The first version used std::unordered_map and a serial scan: 0.45 s of the 1.0 s solver:init at 129^3.)
+class ValueDict {
+public:
+	static constexpr int kMax = 65536;
+	ValueDict() { rehash(256); }
+	int size() const { return (int)m_bits.size(); }
+	uint64_t bits(int i) const { return m_bits[i]; }
+	int find(uint64_t b) const
+	{
+		for (uint64_t i = hash(b);; i = (i + 1) & m_mask) {
+			const int s = m_slot[i];
+			if (s == 0) return -1;
+			if (m_bits[s - 1] == b) return s - 1;
+		}
+	}
+	// index of b, appended if new; -1 if the dictionary is full
+	int insert(uint64_t b)
+	{
+		const int f = find(b);
+		if (f >= 0) return f;
+		if (size() >= kMax) return -1;
+		if ((uint64_t)(size() + 1) * 2 > m_mask + 1) rehash((m_mask + 1) * 4);
+		m_bits.push_back(b);
+		place(b, size());
+		return size() - 1;
+	}
+	void values(std::vector<double>& out) const
+	{
+		out.resize(m_bits.size());
+		if (!m_bits.empty()) std::memcpy(out.data(), m_bits.data(), 8 * m_bits.size());
+	}
+private:
+	uint64_t hash(uint64_t b) const { return ((b * 0x9E3779B97F4A7C15ull) >> 20) & m_mask; }
+	void place(uint64_t b, int slot1)
+	{
+		uint64_t i = hash(b);
+		while (m_slot[i] != 0) i = (i + 1) & m_mask;
+		m_slot[i] = slot1;
+	}
+	void rehash(uint64_t n)
+	{
+		m_mask = n - 1;
+		m_slot.assign(n, 0);
+		for (int k = 0; k < size(); ++k) place(m_bits[k], k + 1);
+	}
+	std::vector<uint64_t> m_bits;   // in order of first occurrence
+	std::vector<int> m_slot;        // index + 1, 0 = empty
+	uint64_t m_mask = 0;
+};
+
+// look-ups of consecutive entries: neighbouring entries of a stencil matrix often repeat the value
+struct DictCursor {
+	const ValueDict& d; uint64_t last = 0; int idx = -1;
+	explicit DictCursor(const ValueDict& dd) : d(dd) {}
+	unsigned int operator()(double v)
+	{
+		uint64_t b; std::memcpy(&b, &v, 8);
+		if (idx < 0 || b != last) { last = b; idx = d.find(b); }
+		return (unsigned int)idx;
+	}
+};
+
+inline uint64_t value_bits(double v) { uint64_t b; std::memcpy(&b, &v, 8); return b; }
+
+// false: more than 65536 distinct values.  The scan runs over contiguous chunks in parallel; merging the chunks'
+// finds in chunk order reproduces the numbering of the sequential scan exactly (a value's first occurrence lies in the
+// first chunk that holds it, and inside a chunk the finds are in scan order).
+bool build_value_dict(const double* vals, int64_t nnz, ValueDict& dict)
+{
+	int T = 1;
+#ifdef _OPENMP
+	if (nnz >= (1 << 16)) T = omp_get_max_threads();
+#endif
+	std::vector<std::vector<uint64_t>> found((size_t)T);
+	bool ok = true;
+#pragma omp parallel num_threads(T) reduction(&& : ok)
+	{
+		int t = 0, nt = 1;
+#ifdef _OPENMP
+		t = omp_get_thread_num(); nt = omp_get_num_threads();
+#endif
+		const int64_t lo = nnz * t / nt, hi = nnz * (t + 1) / nt;
+		ValueDict local;
+		std::vector<uint64_t>& mine = found[(size_t)t];
+		uint64_t last = 0; bool have = false;
+		for (int64_t p = lo; p < hi; ++p) {
+			const uint64_t b = value_bits(vals[p]);
+			if (have && b == last) continue;
+			last = b; have = true;
+			if (local.find(b) >= 0) continue;
+			if (local.insert(b) < 0) { ok = false; break; }
+			mine.push_back(b);
+		}
+	}
+	if (!ok) return false;
+	for (int t = 0; t < T; ++t)
+		for (const uint64_t b : found[(size_t)t])
+			if (dict.insert(b) < 0) return false;
+	return true;
+}
+
+// value-indexed words: (column - smallest column of the slice) << 16 | dictionary index << vshift; padding words 0
+void encode_value_indexed(int64_t nrows, int64_t ns, int64_t pnnz, const int64_t* sp, const int64_t* rowptr, const int* cols,
+                          const double* vals, const ValueDict& dict, const int* colbase, int vshift, std::vector<unsigned int>& out)
+{
+	out.assign((size_t)pnnz, 0u);
+#pragma omp parallel for schedule(static)
+	for (int64_t s = 0; s < ns; ++s) {
+		const int64_t base = sp[s];
+		DictCursor idx(dict);
+		for (int l = 0; l < 32; ++l) {
+			const int64_t r = s * 32 + l;
+			if (r >= nrows) break;
+			for (int64_t p = rowptr[r], k = 0; p < rowptr[r + 1]; ++p, ++k)
+				out[base + k * 32 + l] = ((unsigned int)(cols[p] - colbase[s]) << 16) | (idx(vals[p]) << vshift);
+		}
+	}
+}
+
+inline int value_indexed_shift(int ndict) { return ndict <= 1024 ? 3 : 0; }
+
 // ---- x-staged stream, host side (shared by ug4b200_matrix_upload_crs and ug4b200_host_stream_plan) ----
 // Per slice the sorted distinct columns are grouped into runs of consecutive columns (gaps of <= 2 merged, ends aligned
 // to 16 bytes); the words then carry the position of their column in the concatenation of the runs.  Any banded numbering
@@ -544,7 +670,7 @@ struct XsPlan {
 	std::vector<int2> runs;        // [ns * rmax] {first column (even), doubles (even) | position << 16}
 };
 void build_xs_plan(int64_t nrows, int64_t ns, int64_t pnnz, const int64_t* sp, const int64_t* rowptr, const int* cols,
-                   const double* vals, const std::unordered_map<uint64_t, unsigned short>& dict, XsPlan& out)
+                   const double* vals, const ValueDict& dict, XsPlan& out)
 {
 	const int RMAX = tma_xs_max_runs(), XCAP = tma_xs_max_doubles();
 	std::vector<unsigned int>& hxw = out.xw; hxw.assign((size_t)pnnz, 0u);
@@ -580,14 +706,14 @@ void build_xs_plan(int64_t nrows, int64_t ns, int64_t pnnz, const int64_t* sp, c
 		if (nr > rmaxUsed) rmaxUsed = nr;
 		if (tot > maxDoubles) maxDoubles = tot;
 		xtotal += tot;
+		DictCursor idx(dict);
 		for (int l = 0; l < 32; ++l) {
 			const int64_t r = s * 32 + l;
 			if (r >= nrows) break;
 			int q = 0;
 			for (int64_t p = rowptr[r], k = 0; p < rowptr[r + 1]; ++p, ++k) {
 				while (cols[p] >= rb[q]) ++q;     // columns ascend inside a row, runs ascend
-				uint64_t bits; std::memcpy(&bits, &vals[p], 8);
-				hxw[base + k * 32 + l] = ((unsigned int)(rd[q] + cols[p] - ra[q]) << 16) | ((unsigned int)dict.find(bits)->second << 3);
+				hxw[base + k * 32 + l] = ((unsigned int)(rd[q] + cols[p] - ra[q]) << 16) | (idx(vals[p]) << 3);
 			}
 		}
 	}
@@ -697,37 +823,17 @@ int ug4b200_matrix_upload_crs(ug4b200_ctx* ctx, int block, int64_t nrows, int64_
 			hcb[s] = lo;
 			if (hi >= 0 && (int64_t)hi - lo > 65535) window = false;
 		}
-		std::unordered_map<uint64_t, unsigned short> dict;
-		dict.reserve(1024);
-		for (int64_t p = 0; p < nnz && ok; ++p) {
-			uint64_t bits; std::memcpy(&bits, &vals[p], 8);
-			if (dict.find(bits) == dict.end()) {
-				if (dict.size() >= 65536) { ok = false; break; }
-				const unsigned short id = (unsigned short)dict.size();
-				dict.emplace(bits, id);
-				hdict.push_back(vals[p]);
-			}
-		}
+		ValueDict dict;
+		ok = build_value_dict(vals, nnz, dict);
 		if (ok) {
+			dict.values(hdict);
 			if (hdict.empty()) hdict.push_back(0.0);
 			if (!rc) rc = up((void**)&A->dict, hdict.data(), sizeof(double) * hdict.size());
 			if (!rc) A->ndict = (int)hdict.size();
 		}
 		if (ok && window) {
-			const int vshift = hdict.size() <= 1024 ? 3 : 0;
-			hvc.assign((size_t)pnnz, 0u);
-#pragma omp parallel for schedule(static)
-			for (int64_t s = 0; s < ns; ++s) {
-				const int64_t base = sp[s];
-				for (int l = 0; l < 32; ++l) {
-					const int64_t r = s * 32 + l;
-					if (r >= nrows) break;
-					for (int64_t p = rowptr[r], k = 0; p < rowptr[r + 1]; ++p, ++k) {
-						uint64_t bits; std::memcpy(&bits, &vals[p], 8);
-						hvc[base + k * 32 + l] = ((unsigned int)(cols[p] - hcb[s]) << 16) | ((unsigned int)dict.find(bits)->second << vshift);
-					}
-				}
-			}
+			const int vshift = value_indexed_shift((int)hdict.size());
+			encode_value_indexed(nrows, ns, pnnz, sp.data(), rowptr, cols, vals, dict, hcb.data(), vshift, hvc);
 			if (!rc) rc = up((void**)&A->vc, hvc.data(), sizeof(unsigned int) * hvc.size());
 			if (!rc) rc = up((void**)&A->colbase, hcb.data(), sizeof(int) * hcb.size());
 			if (!rc) { A->comp = true; A->vshift = vshift; }
@@ -783,17 +889,10 @@ int ug4b200_host_stream_plan(int64_t nrows, int64_t ncols, const int64_t* rowptr
 	}
 	*plan = ug4b200_stream_plan{};
 	plan->num_slices = ns; plan->padded_nnz = sp[ns]; plan->max_row_len = maxlen; plan->max_column_window = window;
-	std::unordered_map<uint64_t, unsigned short> dict;
+	ValueDict dict;
 	std::vector<double> hdict;
-	bool ok = true;
-	for (int64_t p = 0; p < nnz; ++p) {
-		uint64_t bits; std::memcpy(&bits, &vals[p], 8);
-		if (dict.find(bits) == dict.end()) {
-			if (dict.size() >= 65536) { ok = false; break; }
-			dict.emplace(bits, (unsigned short)dict.size());
-			hdict.push_back(vals[p]);
-		}
-	}
+	const bool ok = build_value_dict(vals, nnz, dict);
+	if (ok) dict.values(hdict);
 	plan->num_distinct_values = ok ? (int)hdict.size() : -1;
 	if (!ok || sp[ns] == 0) return UG4B200_OK;
 	plan->value_indexed = window <= 65535 ? 1 : 0;
@@ -807,6 +906,44 @@ int ug4b200_host_stream_plan(int64_t nrows, int64_t ncols, const int64_t* rowptr
 	if (xw) std::memcpy(xw, xp.xw.data(), sizeof(unsigned int) * xp.xw.size());
 	if (hdr) std::memcpy(hdr, xp.hdr.data(), sizeof(int4) * xp.hdr.size());
 	if (runs) std::memcpy(runs, xp.runs.data(), sizeof(int2) * xp.runs.size());
+	return UG4B200_OK;
+}
+
+int ug4b200_host_value_indexed_stream(int64_t nrows, int64_t ncols, const int64_t* rowptr, const int* cols, const double* vals,
+                                      unsigned int* words, int* colbase, int* vshift)
+{
+	if (!rowptr || !vshift || nrows < 0 || ncols < 0) return ug4b200_fail(nullptr, UG4B200_ERR_ARG, "ug4b200_host_value_indexed_stream: bad argument");
+	*vshift = -1;
+	const int64_t nnz = rowptr[nrows];
+	if (nnz > 0 && (!cols || !vals)) return ug4b200_fail(nullptr, UG4B200_ERR_ARG, "ug4b200_host_value_indexed_stream: cols / vals are NULL");
+	const int64_t ns = (nrows + 31) / 32;
+	std::vector<int64_t> sp((size_t)ns + 1, 0);
+	std::vector<int> hcb((size_t)ns, 0);
+	bool window = true;
+	for (int64_t s = 0; s < ns; ++s) {
+		int w = 0, lo = 2147483647, hi = -1;
+		for (int l = 0; l < 32; ++l) {
+			const int64_t r = s * 32 + l;
+			if (r >= nrows) break;
+			const int len = (int)(rowptr[r + 1] - rowptr[r]);
+			if (len > w) w = len;
+			if (len > 0) { lo = std::min(lo, cols[rowptr[r]]); hi = std::max(hi, cols[rowptr[r + 1] - 1]); }
+		}
+		sp[s + 1] = sp[s] + (int64_t)w * 32;
+		if (hi < 0) lo = 0;
+		hcb[s] = lo;
+		if (hi >= 0 && (int64_t)hi - lo > 65535) window = false;
+	}
+	ValueDict dict;
+	if (sp[ns] == 0 || !window || !build_value_dict(vals, nnz, dict)) return UG4B200_OK;
+	const int sh = value_indexed_shift(std::max(dict.size(), 1));
+	if (words) {
+		std::vector<unsigned int> w;
+		encode_value_indexed(nrows, ns, sp[ns], sp.data(), rowptr, cols, vals, dict, hcb.data(), sh, w);
+		std::memcpy(words, w.data(), sizeof(unsigned int) * w.size());
+	}
+	if (colbase && ns > 0) std::memcpy(colbase, hcb.data(), sizeof(int) * hcb.size());
+	*vshift = sh;
 	return UG4B200_OK;
 }
 
